@@ -1,0 +1,253 @@
+"""ctypes binding of the CPU oracle (oracle/oracle.c).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py.  The product package
+(go_webp_b200) never imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBS: dict[str, C.CDLL] = {}
+
+MODE_RGB, MODE_RGBA, MODE_BGR, MODE_BGRA, MODE_ARGB = 0, 1, 2, 3, 4
+MODE_RGBA_4444, MODE_RGB_565 = 5, 6
+DIV_EXACT, DIV_TABLE = 0, 1
+PREDICTOR, CROSS_COLOR, SUBTRACT_GREEN, COLOR_INDEXING = 0, 1, 2, 3
+
+_u8p = C.POINTER(C.c_uint8)
+_u32p = C.POINTER(C.c_uint32)
+
+
+def build(force: bool = False) -> None:
+    """Compile liboracle.so / liboracle_scalar.so with the committed Makefile."""
+    need = force or not all(
+        os.path.exists(os.path.join(_HERE, n))
+        and os.path.getmtime(os.path.join(_HERE, n))
+        >= os.path.getmtime(os.path.join(_HERE, "oracle.c"))
+        for n in ("liboracle.so", "liboracle_scalar.so"))
+    if need:
+        subprocess.check_call(["make", "-s", "-C", _HERE, "-B", "all"])
+
+
+def lib(scalar: bool = False) -> C.CDLL:
+    name = "liboracle_scalar.so" if scalar else "liboracle.so"
+    if name not in _LIBS:
+        path = os.path.join(_HERE, name)
+        if not os.path.exists(path):
+            build()
+        L = C.CDLL(path)
+        L.orc_init()
+        L.orc_LinearToGamma.argtypes = [C.c_uint32, C.c_int]
+        L.orc_synth_word.restype = C.c_uint32
+        L.orc_synth_word.argtypes = [C.c_uint32] * 5
+        L.orc_predict.restype = C.c_uint32
+        L.orc_predict.argtypes = [C.c_int] + [C.c_uint32] * 4
+        L.orc_ColorTransformDelta.argtypes = [C.c_int8, C.c_int8]
+        L.orc_vp8l_batch_mt.argtypes = [
+            C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
+            C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int]
+        _LIBS[name] = L
+    return _LIBS[name]
+
+
+def _p(a: np.ndarray | None):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def gamma_tables():
+    g2l = np.zeros(256, np.uint16)
+    l2g = np.zeros(33, np.int32)
+    lib().orc_gamma_tables(_p(g2l), _p(l2g))
+    return g2l, l2g
+
+
+# byte offsets (r, g, b, a) inside a pixel for the import entry points of
+# pkg/libwebp/enc/picture_csp_enc.c.go:189-225 and pkg/picture/conversions.go:22-26
+ORDERS = {
+    "RGBA": (0, 1, 2, 3, 4), "BGRA": (2, 1, 0, 3, 4),
+    "RGBX": (0, 1, 2, -1, 4), "BGRX": (2, 1, 0, -1, 4),
+    "RGB": (0, 1, 2, -1, 3), "BGR": (2, 1, 0, -1, 3),
+    "ARGB32": (2, 1, 0, 3, 4),  # u32 0xAARRGGBB little-endian == B,G,R,A bytes
+}
+
+
+def import_yuva(src: np.ndarray, width: int, height: int, order: str = "RGBA",
+                stride: int | None = None, divide_mode: int = DIV_EXACT,
+                want_a: bool = True, scalar: bool = False):
+    """src: uint8 buffer of interleaved pixels.  Returns (y,u,v,a,has_alpha)."""
+    r, g, b, a_off, step = ORDERS[order]
+    src = np.ascontiguousarray(src, np.uint8).reshape(-1)
+    if stride is None:
+        stride = step * width
+    uvw, uvh = (width + 1) >> 1, (height + 1) >> 1
+    y = np.zeros((height, width), np.uint8)
+    u = np.zeros((uvh, uvw), np.uint8)
+    v = np.zeros((uvh, uvw), np.uint8)
+    a = np.zeros((height, width), np.uint8) if want_a else None
+    base = src
+    if stride < 0:  # pointer addresses the last row (buffer_dec.c.go:161-184)
+        off = (-stride) * (height - 1)
+        ptr = C.c_void_p(src.ctypes.data + off)
+    else:
+        ptr = _p(base)
+    ha = lib(scalar).orc_import_yuva(
+        ptr, r, g, b, a_off, step, stride, width, height, _p(y), width, _p(u),
+        _p(v), uvw, _p(a), width, divide_mode)
+    if ha < 0:
+        raise ValueError("orc_import_yuva: bad arguments")
+    return y, u, v, a, bool(ha)
+
+
+def yuva_to_rgba(y, u, v, a=None, mode: int = MODE_RGBA):
+    h, w = y.shape
+    y = np.ascontiguousarray(y, np.uint8)
+    u = np.ascontiguousarray(u, np.uint8)
+    v = np.ascontiguousarray(v, np.uint8)
+    if a is not None:
+        a = np.ascontiguousarray(a, np.uint8)
+    bpp = lib().orc_mode_bpp(mode)
+    dst = np.zeros((h, w * bpp), np.uint8)
+    ok = lib().orc_yuva_to_rgba(mode, _p(y), w, _p(u), _p(v), u.shape[1],
+                                _p(a), w, w, h, _p(dst), w * bpp)
+    if not ok:
+        raise ValueError("orc_yuva_to_rgba: bad arguments")
+    return dst
+
+
+def emit_fancy_stream(y, u, v, splits, mode: int = MODE_RGBA):
+    h, w = y.shape
+    bpp = lib().orc_mode_bpp(mode)
+    dst = np.zeros((h, w * bpp), np.uint8)
+    sp = np.asarray(splits, np.int32)
+    n = lib().orc_emit_fancy_rgb_stream(
+        mode, _p(np.ascontiguousarray(y)), w, _p(np.ascontiguousarray(u)),
+        _p(np.ascontiguousarray(v)), u.shape[1], w, h, _p(sp), len(sp), _p(dst),
+        w * bpp)
+    return dst, n
+
+
+def upsample_line_pair(mode, top_y, bottom_y, top_u, top_v, cur_u, cur_v):
+    n = len(top_y)
+    bpp = lib().orc_mode_bpp(mode)
+    top = np.zeros(n * bpp, np.uint8)
+    bot = np.zeros(n * bpp, np.uint8) if bottom_y is not None else None
+    lib().orc_upsample_line_pair(mode, _p(top_y), _p(bottom_y), _p(top_u),
+                                 _p(top_v), _p(cur_u), _p(cur_v), _p(top),
+                                 _p(bot), n)
+    return top, bot
+
+
+def add_green(src):
+    src = np.ascontiguousarray(src, np.uint32)
+    dst = np.empty_like(src)
+    lib().orc_add_green(_p(src), src.size, _p(dst))
+    return dst
+
+
+def sub_green(src):
+    dst = np.array(src, np.uint32, copy=True)
+    lib().orc_sub_green(_p(dst), dst.size)
+    return dst
+
+
+def color_space_inverse(src, codes, bits):
+    src = np.ascontiguousarray(src, np.uint32)
+    codes = np.ascontiguousarray(codes, np.uint32)
+    h, w = src.shape
+    dst = np.empty_like(src)
+    lib().orc_color_space_inverse(bits, w, _p(codes), 0, h, _p(src), _p(dst))
+    return dst
+
+
+def color_space_forward(src, codes, bits):
+    dst = np.array(src, np.uint32, copy=True)
+    codes = np.ascontiguousarray(codes, np.uint32)
+    h, w = dst.shape
+    lib().orc_color_space_forward(bits, w, h, _p(codes), _p(dst))
+    return dst
+
+
+def color_index_inverse(src, color_map, bits, width):
+    src = np.ascontiguousarray(src, np.uint32)
+    color_map = np.ascontiguousarray(color_map, np.uint32)
+    assert color_map.size >= (1 << (8 >> bits))
+    h = src.shape[0]
+    dst = np.empty((h, width), np.uint32)
+    lib().orc_color_index_inverse(bits, width, _p(color_map), 0, h, _p(src),
+                                  _p(dst))
+    return dst
+
+
+def color_index_inverse_alpha(src, color_map, bits, width):
+    src = np.ascontiguousarray(src, np.uint8)
+    color_map = np.ascontiguousarray(color_map, np.uint32)
+    h = src.shape[0]
+    dst = np.empty((h, width), np.uint8)
+    lib().orc_color_index_inverse_alpha(bits, width, _p(color_map), 0, h,
+                                        _p(src), _p(dst))
+    return dst
+
+
+def expand_color_map(data, bits):
+    data = np.ascontiguousarray(data, np.uint32)
+    out = np.zeros(1 << (8 >> bits), np.uint32)
+    lib().orc_expand_color_map(data.size, bits, _p(data), _p(out))
+    return out
+
+
+def bundle_color_map(idx, xbits):
+    idx = np.ascontiguousarray(idx, np.uint8)
+    h, w = idx.shape
+    ow = (w + (1 << xbits) - 1) >> xbits
+    dst = np.zeros((h, ow), np.uint32)
+    for r in range(h):
+        lib().orc_bundle_color_map(_p(idx[r]), w, xbits, _p(dst[r]))
+    return dst
+
+
+def predictor_inverse(src, modes, bits):
+    src = np.ascontiguousarray(src, np.uint32)
+    modes = np.ascontiguousarray(modes, np.uint32)
+    h, w = src.shape
+    dst = np.empty_like(src)
+    lib().orc_predictor_inverse(bits, w, h, _p(modes), _p(src), _p(dst))
+    return dst
+
+
+def predictor_forward(src, modes, bits):
+    src = np.ascontiguousarray(src, np.uint32)
+    modes = np.ascontiguousarray(modes, np.uint32)
+    h, w = src.shape
+    dst = np.empty_like(src)
+    lib().orc_predictor_forward(bits, w, h, _p(modes), _p(src), _p(dst))
+    return dst
+
+
+def argb_to_y(row):
+    row = np.ascontiguousarray(row, np.uint32)
+    y = np.zeros(row.size, np.uint8)
+    lib().orc_ConvertARGBToY(_p(row), _p(y), row.size)
+    return y
+
+
+def argb_to_uv(row, u=None, v=None, do_store=True):
+    row = np.ascontiguousarray(row, np.uint32)
+    n = (row.size + 1) >> 1
+    u = np.zeros(n, np.uint8) if u is None else np.array(u, np.uint8)
+    v = np.zeros(n, np.uint8) if v is None else np.array(v, np.uint8)
+    lib().orc_ConvertARGBToUV(_p(row), _p(u), _p(v), row.size, int(do_store))
+    return u, v
+
+
+def synth_u32(seed, img, plane, words_per_row, rows):
+    out = np.empty((rows, words_per_row), np.uint32)
+    lib().orc_synth_fill_u32(C.c_uint32(seed), C.c_uint32(img),
+                             C.c_uint32(plane), _p(out), words_per_row, rows,
+                             words_per_row * 4)
+    return out

@@ -1,0 +1,129 @@
+"""The C oracle against the committed libwebp 1.6.0 fixtures (CPU only).
+
+Fixtures were written by tests/golden/make_golden.py from the upstream binary
+(the C original that go-webp transliterates).  This is what pins the oracle for
+parts 1 and 2 of the hot path.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def test_gamma_tables_literals():
+    # SURVEY.md 7 "Gamma tables on GPU" / Appendix D: known entries of the tables
+    g2l, l2g = oracle.gamma_tables()
+    assert list(g2l[:4]) == [0, 49, 85, 117] and g2l[255] == 4095
+    assert list(l2g[:4]) == [0, 3, 8, 13] and l2g[32] == 255
+    # formula check (pkg/libwebp/dsp/yuv.go:171-178, C-intended float division)
+    v = np.arange(256)
+    assert (g2l == (np.power(v / 255.0, 0.80) * 4095 + 0.5).astype(np.uint16)).all()
+    i = np.arange(33)
+    assert (l2g == (255.0 * np.power(i * (128.0 / 4095.0), 1 / 0.80) + 0.5).astype(np.int32)).all()
+
+
+def test_import_matches_libwebp_binary(golden_dir):
+    g = _load(golden_dir, "import_libwebp160.npz")
+    n = int(g["n"][0])
+    assert n == 70
+    translucent_cases = 0
+    for i in range(n):
+        k = f"c{i}"
+        w, h, ha = (int(x) for x in g[k + "_meta"])
+        src = g[k + "_src"]
+        y, u, v, a, has_alpha = oracle.import_yuva(src, w, h, "RGBA",
+                                                   divide_mode=oracle.DIV_TABLE)
+        assert has_alpha == bool(ha)
+        assert (y == g[k + "_y"]).all(), (w, h)
+        assert (u == g[k + "_u"]).all(), (w, h)
+        assert (v == g[k + "_v"]).all(), (w, h)
+        if ha:
+            assert (a == g[k + "_a"]).all()
+        else:
+            assert (a == 255).all()  # yuv.go:329-336
+        # exact-division mode (the arithmetic the Go text states, yuv.go:231):
+        # identical on Y/A always, and on U/V wherever no block is translucent.
+        ye, ue, ve, ae, _ = oracle.import_yuva(src, w, h, "RGBA",
+                                               divide_mode=oracle.DIV_EXACT)
+        assert (ye == y).all() and (ae == a).all()
+        al = src[..., 3].astype(np.int32)
+        alp = np.pad(al, ((0, h & 1), (0, w & 1)), mode="edge")
+        bs = alp[0::2, 0::2] + alp[0::2, 1::2] + alp[1::2, 0::2] + alp[1::2, 1::2]
+        solid = (bs == 0) | (bs == 1020)
+        assert (ue[solid] == u[solid]).all() and (ve[solid] == v[solid]).all()
+        d = np.abs(ue.astype(int) - u.astype(int)).max(), np.abs(ve.astype(int) - v.astype(int)).max()
+        assert max(d) <= 1  # flips the final 8-bit value by at most 1
+        translucent_cases += int((~solid).any())
+    assert translucent_cases > 20
+
+
+@pytest.mark.parametrize("order", ["BGRA", "RGBX", "BGRX", "RGB", "BGR"])
+def test_import_channel_orders(golden_dir, order):
+    g = _load(golden_dir, "import_libwebp160.npz")
+    w, h, ha, step, stride = (int(x) for x in g[f"o_{order}_meta"])
+    y, u, v, a, has_alpha = oracle.import_yuva(g[f"o_{order}_src"], w, h, order,
+                                               stride=stride,
+                                               divide_mode=oracle.DIV_TABLE)
+    assert has_alpha == bool(ha)
+    assert (y == g[f"o_{order}_y"]).all()
+    assert (u == g[f"o_{order}_u"]).all()
+    assert (v == g[f"o_{order}_v"]).all()
+    if ha:
+        assert (a == g[f"o_{order}_a"]).all()
+
+
+def test_upsample_matches_libwebp_binary(golden_dir):
+    g = _load(golden_dir, "upsample_libwebp160.npz")
+    n = int(g["n"][0])
+    assert n == 32
+    for i in range(n):
+        k = f"c{i}"
+        a = g[k + "_a"]
+        a = a if a.size else None
+        out = oracle.yuva_to_rgba(g[k + "_y"], g[k + "_u"], g[k + "_v"], a,
+                                  mode=oracle.MODE_BGRA)
+        argb = out.view(np.uint32).reshape(g[k + "_y"].shape)
+        assert (argb == g[k + "_argb"]).all(), g[k + "_y"].shape
+
+
+def test_decoder_output_modes_match_libwebp_binary(golden_dir):
+    """Pins the per-pixel writers the Go tree leaves undefined
+    (pkg/libwebp/dsp/upsampling.c.go:107-114) and the alpha dispatch
+    (pkg/libwebp/decoder/io_dec.c.go:175-195) through real lossy files."""
+    g = _load(golden_dir, "decode_libwebp160.npz")
+    n = int(g["n"][0])
+    for i in range(n):
+        k = f"c{i}"
+        a = g[k + "_a"]
+        a = a if a.size else None
+        for mode in range(7):
+            exp = g[k + f"_m{mode}"]
+            got = oracle.yuva_to_rgba(g[k + "_y"], g[k + "_u"], g[k + "_v"], a,
+                                      mode=mode)
+            if mode == oracle.MODE_RGBA_4444 and a is not None:
+                # alpha nibble comes from EmitAlphaRGBA4444 (8f-2, not on the path)
+                exp = exp.copy(); got = got.copy()
+                exp[:, 1::2] |= 0x0f; got[:, 1::2] |= 0x0f
+            assert (got == exp).all(), (i, mode)
+
+
+def test_streaming_schedule_equals_whole_image():
+    """EmitFancyRGB's row-batch schedule with a carried row (io_dec.c.go:65-115)
+    gives the same bytes as the whole-image schedule the GPU path batches
+    (picture_csp_enc.c.go:62-118)."""
+    rng = np.random.default_rng(5)
+    for (w, h) in [(1, 1), (7, 9), (16, 32), (33, 48), (40, 17)]:
+        y = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        u = rng.integers(0, 256, ((h + 1) // 2, (w + 1) // 2), dtype=np.uint8)
+        v = rng.integers(0, 256, ((h + 1) // 2, (w + 1) // 2), dtype=np.uint8)
+        whole = oracle.yuva_to_rgba(y, u, v, None, oracle.MODE_RGBA)
+        splits = list(range(16, h, 16)) + [h]  # macroblock rows
+        stream, nrows = oracle.emit_fancy_stream(y, u, v, splits, oracle.MODE_RGBA)
+        assert nrows == h
+        assert (stream == whole).all()

@@ -1,0 +1,109 @@
+"""ctypes declarations of include/b2webp.h (the C ABI of libb2webp.so).
+
+There is no CPU fallback: loading fails loudly when the CUDA library has not
+been built (python -c 'import __graft_entry__ as g; g.build()').
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libb2webp.so")
+
+B2_OK, B2_ERR_OOM, B2_ERR_BAD_DIM, B2_ERR_NULL, B2_ERR_INVALID_CONFIG, B2_ERR_CUDA = 0, -1, -2, -3, -4, -5
+ORDER_RGBA, ORDER_BGRA, ORDER_RGB, ORDER_BGR = 0, 1, 2, 3
+IMPORT_ALPHA, IMPORT_DIV_TABLE = 1, 2
+(MODE_RGB, MODE_RGBA, MODE_BGR, MODE_BGRA, MODE_ARGB, MODE_RGBA_4444, MODE_RGB_565,
+ MODE_rgbA, MODE_bgrA, MODE_Argb, MODE_rgbA_4444) = range(11)
+MODE_BPP = {0: 3, 1: 4, 2: 3, 3: 4, 4: 4, 5: 2, 6: 2, 7: 4, 8: 4, 9: 4, 10: 2}
+SYNTH_RAW, SYNTH_OPAQUE, SYNTH_SPARSE, SYNTH_BINARY = 0, 1, 2, 3
+
+
+class ImportJob(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("y", C.c_void_p), ("u", C.c_void_p),
+                ("v", C.c_void_p), ("a", C.c_void_p), ("src_stride", C.c_int32),
+                ("y_stride", C.c_int32), ("uv_stride", C.c_int32),
+                ("a_stride", C.c_int32), ("width", C.c_int32), ("height", C.c_int32)]
+
+
+class UpsampleJob(C.Structure):
+    _fields_ = [("y", C.c_void_p), ("u", C.c_void_p), ("v", C.c_void_p),
+                ("a", C.c_void_p), ("dst", C.c_void_p), ("y_stride", C.c_int32),
+                ("uv_stride", C.c_int32), ("a_stride", C.c_int32),
+                ("dst_stride", C.c_int32), ("width", C.c_int32), ("height", C.c_int32)]
+
+
+class ArgbJob(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("data", C.c_void_p),
+                ("width", C.c_int32), ("height", C.c_int32), ("bits", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+# every symbol include/b2webp.h declares: name -> (restype, argtypes)
+_vp = C.c_void_p
+_ctx = C.c_void_p
+SYMBOLS = {
+    "b2_abi_version": (C.c_int, []),
+    "b2_strerror": (C.c_char_p, [C.c_int]),
+    "b2_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "b2_ctx_create": (C.c_int, [C.c_int, C.c_int, C.POINTER(_ctx)]),
+    "b2_ctx_destroy": (None, [_ctx]),
+    "b2_ctx_device": (C.c_int, [_ctx]),
+    "b2_ctx_sm_count": (C.c_int, [_ctx]),
+    "b2_last_error": (C.c_char_p, [_ctx]),
+    "b2_launch_count": (C.c_uint64, [_ctx]),
+    "b2_pinned_alloc": (C.c_int, [_ctx, C.c_size_t, C.POINTER(_vp)]),
+    "b2_pinned_free": (C.c_int, [_ctx, _vp]),
+    "b2_host_register": (C.c_int, [_ctx, _vp, C.c_size_t]),
+    "b2_host_unregister": (C.c_int, [_ctx, _vp]),
+    "b2_dev_alloc": (C.c_int, [_ctx, C.c_size_t, C.POINTER(_vp)]),
+    "b2_dev_free": (C.c_int, [_ctx, _vp]),
+    "b2_h2d_async": (C.c_int, [_ctx, C.c_int, _vp, _vp, C.c_size_t]),
+    "b2_d2h_async": (C.c_int, [_ctx, C.c_int, _vp, _vp, C.c_size_t]),
+    "b2_h2d_2d_async": (C.c_int, [_ctx, C.c_int, _vp, C.c_size_t, _vp, C.c_size_t, C.c_size_t, C.c_size_t]),
+    "b2_d2h_2d_async": (C.c_int, [_ctx, C.c_int, _vp, C.c_size_t, _vp, C.c_size_t, C.c_size_t, C.c_size_t]),
+    "b2_memset_async": (C.c_int, [_ctx, C.c_int, _vp, C.c_int, C.c_size_t]),
+    "b2_sync": (C.c_int, [_ctx, C.c_int]),
+    "b2_event_record": (C.c_int, [_ctx, C.c_int, C.c_int]),
+    "b2_event_elapsed_ms": (C.c_int, [_ctx, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "b2_rgba_to_yuv420a": (C.c_int, [_ctx, C.c_int, C.POINTER(ImportJob), C.c_int, C.c_int, C.c_int, _vp]),
+    "b2_yuv420a_to_rgba_fancy": (C.c_int, [_ctx, C.c_int, C.POINTER(UpsampleJob), C.c_int, C.c_int]),
+    "b2_vp8l_add_green": (C.c_int, [_ctx, C.c_int, C.POINTER(ArgbJob), C.c_int]),
+    "b2_vp8l_sub_green": (C.c_int, [_ctx, C.c_int, C.POINTER(ArgbJob), C.c_int]),
+    "b2_vp8l_color_inverse": (C.c_int, [_ctx, C.c_int, C.POINTER(ArgbJob), C.c_int]),
+    "b2_vp8l_color_forward": (C.c_int, [_ctx, C.c_int, C.POINTER(ArgbJob), C.c_int]),
+    "b2_vp8l_inverse_chain": (C.c_int, [_ctx, C.c_int, C.POINTER(ArgbJob), C.c_int]),
+    "b2_vp8l_forward_chain": (C.c_int, [_ctx, C.c_int, C.POINTER(ArgbJob), C.c_int]),
+    "b2_vp8l_color_index_inverse": (C.c_int, [_ctx, C.c_int, C.POINTER(ArgbJob), C.c_int]),
+    "b2_vp8l_bundle_color_map": (C.c_int, [_ctx, C.c_int, C.POINTER(ArgbJob), C.c_int]),
+    "b2_synth_fill_batch_u32": (C.c_int, [_ctx, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_size_t,
+                                          C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]),
+}
+
+_LIB = None
+
+
+class B2Error(RuntimeError):
+    def __init__(self, status: int, msg: str):
+        super().__init__(f"b2webp status {status}: {msg}")
+        self.status = status
+
+
+def load() -> C.CDLL:
+    """Loads libb2webp.so; raises (never falls back) when it is missing."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: the CUDA library must be built "
+                "(__graft_entry__.build()); there is no CPU fallback")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)  # AttributeError if the export is missing
+            fn.restype = res
+            fn.argtypes = args
+        if lib.b2_abi_version() != 0x0101:
+            raise ImportError("libb2webp.so ABI version mismatch; rebuild")
+        _LIB = lib
+    return _LIB

@@ -1,0 +1,266 @@
+"""Host-side mirror of go-webp's dsp function tables for the pixel hot path.
+
+The reference dispatches through package-level function variables
+(pkg/libwebp/dsp: WebPUpsamplers[] upsampling.c.go:31,275-289; VP8L function
+types lossless.h.go:33-45, bound at lossless_enc.go:488-519; VP8LInverseTransform
+lossless.go:511-547).  The functions below keep those names and argument
+meanings, take HOST numpy arrays and run on the GPU through the C ABI.  The
+decoder-side symbols the Go tree uses but never binds (VP8LAddGreenToBlueAndRed,
+VP8LTransformColorInverse, VP8LMapColor32b) are supplied
+here.  No CPU implementation lives in this module.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _abi
+from .device import Context
+from .picture import _al, _arena, default_context
+
+# pkg/vp8/enums.go:33-40
+PREDICTOR_TRANSFORM, CROSS_COLOR_TRANSFORM, SUBTRACT_GREEN_TRANSFORM, COLOR_INDEXING_TRANSFORM = 0, 1, 2, 3
+
+
+def VP8LSubSampleSize(size: int, sampling_bits: int) -> int:  # lossless_common.go:34-36
+    return (size + (1 << sampling_bits) - 1) >> sampling_bits
+
+
+@dataclass
+class VP8LTransform:  # pkg/vp8/models.go:126-132
+    vtype: int
+    bits: int
+    xsize: int
+    ysize: int
+    data: np.ndarray | None = None
+
+
+@dataclass
+class VP8LImage:
+    """One image of the batched entry point: 'pixels' is what DecodeImageData
+    produced (uint32, row length = width after colour-index subsampling)."""
+    pixels: np.ndarray
+    width: int
+    height: int
+
+
+def _run(op: str, items, ctx: Context | None = None, chunk: int = 8):
+    """items: list of (src u32/u8 array, out_shape, data array or None, width, height, bits).
+    Returns the list of uint32 outputs.  Chunks are pipelined over the streams."""
+    ctx = ctx or default_context()
+    n = len(items)
+    need = 0
+    metas = []
+    for (src, oshape, data, w, h, bits) in items:
+        src = np.ascontiguousarray(src)
+        data = None if data is None else np.ascontiguousarray(data, np.uint32)
+        ob = int(np.prod(oshape)) * 4
+        sz = (_al(src.nbytes), _al(ob), _al(data.nbytes) if data is not None else 0)
+        metas.append((src, data, ob, sz))
+        need += sum(sz)
+    ar = _arena(ctx)
+    ar.reset(need)
+    lib, hnd, ns = ctx.lib, ctx.h, ctx.n_streams
+    fn = getattr(lib, "b2_vp8l_" + op)
+    outs, jobs, ptrs = [], [], []
+    for (src, data, ob, sz), (_, oshape, _, w, h, bits) in zip(metas, items):
+        ps, pd = ar.take(sz[0]), ar.take(sz[1])
+        pt = ar.take(sz[2]) if sz[2] else None
+        ptrs.append((ps, pd, pt))
+        jobs.append(_abi.ArgbJob(ps, pd, pt, w, h, bits, 0))
+        outs.append(np.empty(oshape, np.uint32))
+    for c0 in range(0, n, chunk):
+        c1 = min(n, c0 + chunk)
+        s = (c0 // chunk) % ns
+        for i in range(c0, c1):
+            src, data, ob, sz = metas[i]
+            ctx._chk(lib.b2_h2d_async(hnd, s, ptrs[i][0], src.ctypes.data, src.nbytes))
+            if data is not None:
+                ctx._chk(lib.b2_h2d_async(hnd, s, ptrs[i][2], data.ctypes.data, data.nbytes))
+        arr = (_abi.ArgbJob * (c1 - c0))(*jobs[c0:c1])
+        ctx._chk(fn(hnd, s, arr, c1 - c0))
+        for i in range(c0, c1):
+            ctx._chk(lib.b2_d2h_async(hnd, s, outs[i].ctypes.data, ptrs[i][1], metas[i][2]))
+    ctx.sync()
+    return outs
+
+
+def _flat(op, src, data=None, width=None, height=None, bits=0, ctx=None):
+    src = np.ascontiguousarray(src, np.uint32)
+    if width is None:
+        height, width = (src.shape if src.ndim == 2 else (1, src.size))
+    return _run(op, [(src, src.shape, data, width, height, bits)], ctx)[0]
+
+
+# ---- row-level functions with the reference's names -----------------------------
+def VP8LAddGreenToBlueAndRed(src: np.ndarray, num_pixels: int | None = None) -> np.ndarray:
+    """VP8LProcessDecBlueAndRedFunc (lossless.h.go:35); lossless.go:337-347."""
+    src = np.ascontiguousarray(src, np.uint32).reshape(-1)
+    n = src.size if num_pixels is None else num_pixels
+    return _flat("add_green", src[:n], None, n, 1)
+
+
+def VP8LSubtractGreenFromBlueAndRed(argb_data: np.ndarray, num_pixels: int | None = None) -> np.ndarray:
+    """VP8LProcessEncBlueAndRedFunc (lossless.h.go:44); lossless_enc.go:207-216.
+    Returns the transformed copy (the Go function works in place)."""
+    src = np.ascontiguousarray(argb_data, np.uint32).reshape(-1)
+    n = src.size if num_pixels is None else num_pixels
+    return _flat("sub_green", src[:n], None, n, 1)
+
+
+def MultipliersToColorCode(green_to_red: int, green_to_blue: int, red_to_blue: int) -> int:
+    """pkg/libwebp/enc/predictor_enc.go:729-731"""
+    return 0xff000000 | ((red_to_blue & 0xff) << 16) | ((green_to_blue & 0xff) << 8) | (green_to_red & 0xff)
+
+
+def VP8LTransformColorInverse(m_code: int, src: np.ndarray, num_pixels: int | None = None) -> np.ndarray:
+    """VP8LTransformColorInverseFunc (lossless.h.go:36); lossless.go:359-374.
+    m_code: the multipliers as a colour code (ColorCodeToMultipliers, :353-357)."""
+    src = np.ascontiguousarray(src, np.uint32).reshape(-1)
+    n = src.size if num_pixels is None else num_pixels
+    # one tile spanning the whole segment (bits = 9 covers up to 512 px per tile row)
+    out = np.empty(n, np.uint32)
+    for x0 in range(0, n, 512):
+        seg = src[x0:min(n, x0 + 512)]
+        out[x0:x0 + seg.size] = _flat("color_inverse", seg, np.array([m_code], np.uint32), seg.size, 1, 9)
+    return out
+
+
+def VP8LTransformColor(m_code: int, data: np.ndarray, num_pixels: int | None = None) -> np.ndarray:
+    """VP8LTransformColorFunc (lossless.h.go:45); lossless_enc.go:224-239."""
+    src = np.ascontiguousarray(data, np.uint32).reshape(-1)
+    n = src.size if num_pixels is None else num_pixels
+    out = np.empty(n, np.uint32)
+    for x0 in range(0, n, 512):
+        seg = src[x0:min(n, x0 + 512)]
+        out[x0:x0 + seg.size] = _flat("color_forward", seg, np.array([m_code], np.uint32), seg.size, 1, 9)
+    return out
+
+
+def VP8LMapColor32b(src: np.ndarray, color_map: np.ndarray, y_start: int, y_end: int, width: int) -> np.ndarray:
+    """VP8LMapARGBFunc (lossless.h.go:40); MapARGB_C lossless.go:415-426."""
+    src = np.ascontiguousarray(src, np.uint32).reshape(y_end - y_start, width)
+    pal = np.zeros(256, np.uint32)
+    cm = np.ascontiguousarray(color_map, np.uint32).reshape(-1)
+    pal[:cm.size] = cm
+    return _run("color_index_inverse", [(src, src.shape, pal, width, y_end - y_start, 0)])[0]
+
+
+def VP8LBundleColorMap(row: np.ndarray, width: int, xbits: int) -> np.ndarray:
+    """lossless_enc.go:293-312 for one row (or a [h, w] block of rows)."""
+    idx = np.ascontiguousarray(row, np.uint8)
+    if idx.ndim == 1:
+        idx = idx.reshape(1, -1)
+    h = idx.shape[0]
+    ow = VP8LSubSampleSize(width, xbits)
+    return _run("bundle_color_map", [(idx, (h, ow), None, width, h, xbits)])[0]
+
+
+def VP8LInverseTransform(transform: VP8LTransform, row_start: int, row_end: int, in_rows: np.ndarray) -> np.ndarray:
+    """lossless.go:511-547 for rows [row_start,row_end) of one transform; 'in_rows'
+    holds exactly those rows.  Out-of-place (the in-place colour-index trick of
+    :531-541 is a host-memory optimisation the device path does not need)."""
+    assert row_start < row_end <= transform.ysize
+    rows = row_end - row_start
+    w = transform.xsize
+    if transform.vtype == SUBTRACT_GREEN_TRANSFORM:
+        src = np.ascontiguousarray(in_rows, np.uint32).reshape(rows, w)
+        return _flat("add_green", src, None, w, rows)
+    if transform.vtype == CROSS_COLOR_TRANSFORM:
+        src = np.ascontiguousarray(in_rows, np.uint32).reshape(rows, w)
+        tpr = VP8LSubSampleSize(w, transform.bits)
+        # tile rows covering [row_start,row_end): hand the kernel a window whose
+        # row 0 is aligned to a tile boundary
+        t0 = row_start >> transform.bits
+        pad = row_start - (t0 << transform.bits)
+        data = np.ascontiguousarray(transform.data, np.uint32).reshape(-1, tpr)[t0:]
+        if pad:
+            src = np.concatenate([np.zeros((pad, w), np.uint32), src])
+        out = _flat("color_inverse", src, data, w, rows + pad, transform.bits)
+        return out[pad:]
+    if transform.vtype == COLOR_INDEXING_TRANSFORM:
+        sw = VP8LSubSampleSize(w, transform.bits)
+        src = np.ascontiguousarray(in_rows, np.uint32).reshape(rows, sw)
+        return _run("color_index_inverse", [(src, (rows, w), transform.data, w, rows, transform.bits)])[0]
+    raise NotImplementedError("PREDICTOR_TRANSFORM inverse is row-serial (SURVEY 8f-1): not on this path yet")
+
+
+def VP8LInverseTransformBatch(imgs, chain, ctx: Context | None = None):
+    """Added batched entry point for part 3.  imgs: list[VP8LImage];
+    chain: list (per image) of the transforms in READ order (ReadTransform,
+    vp8l_dec.c.go:1221-1269); they are applied last-read-first exactly like
+    ApplyInverseTransforms (vp8l_dec.c.go:710-729).  A cross-colour transform
+    directly followed by add-green is run as the fused single-pass kernel."""
+    ctx = ctx or default_context()
+    cur = [np.ascontiguousarray(im.pixels, np.uint32) for im in imgs]
+    chain = [list(c) for c in chain]
+    depth = max((len(c) for c in chain), default=0)
+    # step k applies chain[i][-1-k]; group images by the op of this step
+    for k in range(depth):
+        groups: dict[str, list] = {}
+        for i, c in enumerate(chain):
+            if k >= len(c) or c[-1 - k] is None:
+                continue
+            t = c[-1 - k]
+            if t.vtype == CROSS_COLOR_TRANSFORM and k + 1 < len(c) and c[-2 - k] is not None \
+                    and c[-2 - k].vtype == SUBTRACT_GREEN_TRANSFORM:
+                groups.setdefault("inverse_chain", []).append((i, t))
+                c[-2 - k] = None  # consumed by the fused kernel
+            elif t.vtype == CROSS_COLOR_TRANSFORM:
+                groups.setdefault("color_inverse", []).append((i, t))
+            elif t.vtype == SUBTRACT_GREEN_TRANSFORM:
+                groups.setdefault("add_green", []).append((i, t))
+            elif t.vtype == COLOR_INDEXING_TRANSFORM:
+                groups.setdefault("color_index_inverse", []).append((i, t))
+            else:
+                raise NotImplementedError("PREDICTOR_TRANSFORM inverse (SURVEY 8f-1)")
+        for op, members in groups.items():
+            items = []
+            for i, t in members:
+                w, h = t.xsize, t.ysize
+                if op == "color_index_inverse":
+                    sw = VP8LSubSampleSize(w, t.bits)
+                    items.append((cur[i].reshape(h, sw), (h, w), t.data, w, h, t.bits))
+                else:
+                    items.append((cur[i].reshape(h, w), (h, w), t.data, w, h, t.bits))
+            outs = _run(op, items, ctx)
+            for (i, _), o in zip(members, outs):
+                cur[i] = o
+    return cur
+
+
+# ---- fancy upsampler line-pair table ----------------------------------------------
+def _line_pair(mode):
+    def fn(top_y, bottom_y, top_u, top_v, cur_u, cur_v, length):
+        """WebPUpsampleLinePairFunc (dsp.h.go:144; upsampling.c.go:43-103): returns
+        (top_dst, bottom_dst or None).  A pair is a 2-row image whose chroma rows
+        are (top, cur); a single row (bottom_y None) is the mirrored-row case."""
+        from .picture import Picture, YUVAToRGBABatch, WEBP_YUV420
+        uw = (length + 1) >> 1
+        bpp = _abi.MODE_BPP[mode]
+        if bottom_y is None:
+            # first/last-row call sites pass top == cur (picture_csp_enc.c.go:88,103)
+            # -> a 1-row image with that chroma row.  Different top/cur with a nil
+            # bottom row never occurs in the reference.
+            assert np.array_equal(top_u[:uw], cur_u[:uw]) and np.array_equal(top_v[:uw], cur_v[:uw])
+            pic = Picture(Width=length, Height=1, ColorSpace=WEBP_YUV420,
+                          Y=np.asarray(top_y[:length], np.uint8).reshape(1, -1),
+                          U=np.asarray(top_u[:uw], np.uint8).reshape(1, -1),
+                          V=np.asarray(top_v[:uw], np.uint8).reshape(1, -1))
+            out = YUVAToRGBABatch([pic], mode)[0]
+            return out[0], None
+        # rows (1,2) of a 3-row image: row 0 is a dummy, rows 1 and 2 are the pair
+        # between chroma rows 0 (top) and 1 (cur)
+        y = np.stack([np.zeros(length, np.uint8), np.asarray(top_y[:length], np.uint8),
+                      np.asarray(bottom_y[:length], np.uint8)])
+        u = np.stack([np.asarray(top_u[:uw], np.uint8), np.asarray(cur_u[:uw], np.uint8)])
+        v = np.stack([np.asarray(top_v[:uw], np.uint8), np.asarray(cur_v[:uw], np.uint8)])
+        pic = Picture(Width=length, Height=3, ColorSpace=WEBP_YUV420, Y=y, U=u, V=v)
+        out = YUVAToRGBABatch([pic], mode)[0]
+        return out[1][:length * bpp], out[2][:length * bpp]
+    return fn
+
+
+# WebPUpsamplers[MODE_LAST] (upsampling.c.go:275-289)
+WebPUpsamplers = {m: _line_pair(m) for m in range(11)}

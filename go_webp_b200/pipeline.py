@@ -1,0 +1,270 @@
+"""Batched, pinned-host-staged entry points for uniform batches.
+
+This is the shape north_star gives pkg/picture: device-resident Y/U/V/A (or
+RGBA) planes with pinned-host staging.  A pipeline owns pinned host buffers for
+a batch of n equally sized images plus the matching device buffers; run() moves
+the batch host -> device, converts it and brings the results back, cut into
+chunks that are spread over the context's streams so that H2D, the kernel and
+D2H of different chunks overlap (PCIe is full duplex).  run_device() runs only
+the kernel on the resident buffers.
+
+Reference semantics per image: ImportPipeline == enc.Import ->
+picture.ImportYUVAFromRGBA (pkg/libwebp/enc/picture_csp_enc.c.go:123-137,
+pkg/picture/conversions.go:50-121); UpsamplePipeline == WebPPictureYUVAToARGB /
+EmitFancyRGB (picture_csp_enc.c.go:62-118, pkg/libwebp/decoder/io_dec.c.go:65-115).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _abi
+from .device import Context
+
+
+def _al(n: int, a: int = 256) -> int:
+    return (n + a - 1) & ~(a - 1)
+
+
+class ImportPipeline:
+    def __init__(self, ctx: Context, n: int, width: int, height: int, order: str = "RGBA",
+                 import_alpha: bool = True, divide_table: bool = False, chunk: int = 16,
+                 host: bool = True):
+        self.ctx, self.n, self.w, self.h = ctx, n, width, height
+        self.order = {"RGBA": _abi.ORDER_RGBA, "BGRA": _abi.ORDER_BGRA}[order]
+        self.flags = (_abi.IMPORT_ALPHA if import_alpha else 0) | (_abi.IMPORT_DIV_TABLE if divide_table else 0)
+        self.chunk = max(1, min(chunk, n))
+        self.uvw, self.uvh = (width + 1) >> 1, (height + 1) >> 1
+        self.ys, self.uvs = _al(width, 16), _al(self.uvw, 16)
+        self.src_img = _al(4 * width * height)
+        self.y_img, self.uv_img = _al(self.ys * height), _al(self.uvs * self.uvh)
+        # device: all src | all Y | all U | all V | all A | flags  (plane-major, so a
+        # chunk of images is one contiguous range per plane -> one copy per plane)
+        self.d_src = ctx.alloc(self.src_img * n)
+        self.d_y = ctx.alloc(self.y_img * n)
+        self.d_u = ctx.alloc(self.uv_img * n)
+        self.d_v = ctx.alloc(self.uv_img * n)
+        self.d_a = ctx.alloc(self.y_img * n)
+        self.d_flags = ctx.alloc(_al(4 * n))
+        self.jobs = [_abi.ImportJob(self.d_src.ptr + i * self.src_img, self.d_y.ptr + i * self.y_img,
+                                    self.d_u.ptr + i * self.uv_img, self.d_v.ptr + i * self.uv_img,
+                                    self.d_a.ptr + i * self.y_img, 4 * width, self.ys, self.uvs, self.ys,
+                                    width, height) for i in range(n)]
+        self._job_arr = (_abi.ImportJob * n)(*self.jobs)
+        self.host = host
+        if host:
+            self.p_src = ctx.pinned(self.src_img * n)
+            self.p_y = ctx.pinned(self.y_img * n)
+            self.p_u = ctx.pinned(self.uv_img * n)
+            self.p_v = ctx.pinned(self.uv_img * n)
+            self.p_a = ctx.pinned(self.y_img * n)
+            self.p_flags = ctx.pinned(_al(4 * n))
+
+    # pinned host views ----------------------------------------------------------
+    def src_view(self, i: int) -> np.ndarray:
+        o = i * self.src_img
+        return self.p_src.array[o:o + 4 * self.w * self.h].reshape(self.h, self.w, 4)
+
+    def planes(self, i: int):
+        """(Y, U, V, A or None, has_alpha) of image i after run(); A is dropped when the
+        image is opaque, as conversions.go:56-58 / allocations.go:52-58 do."""
+        y = self.p_y.array[i * self.y_img:i * self.y_img + self.ys * self.h].reshape(self.h, self.ys)[:, :self.w]
+        u = self.p_u.array[i * self.uv_img:i * self.uv_img + self.uvs * self.uvh].reshape(self.uvh, self.uvs)[:, :self.uvw]
+        v = self.p_v.array[i * self.uv_img:i * self.uv_img + self.uvs * self.uvh].reshape(self.uvh, self.uvs)[:, :self.uvw]
+        ha = bool(self.p_flags.array.view(np.int32)[i])
+        a = self.p_a.array[i * self.y_img:i * self.y_img + self.ys * self.h].reshape(self.h, self.ys)[:, :self.w] if ha else None
+        return y, u, v, a, ha
+
+    @property
+    def h2d_bytes(self) -> int:
+        return 4 * self.w * self.h * self.n
+
+    @property
+    def d2h_bytes(self) -> int:
+        return (2 * self.ys * self.h + 2 * self.uvs * self.uvh + 4) * self.n
+
+    # execution --------------------------------------------------------------------
+    def run_device(self, stream: int = 0):
+        """One kernel launch over the resident batch (inputs already in HBM)."""
+        c = self.ctx
+        c._chk(c.lib.b2_rgba_to_yuv420a(c.h, stream, self._job_arr, self.n, self.order, self.flags,
+                                        self.d_flags.ptr))
+
+    def run(self):
+        """Host -> device -> kernel -> host for the whole batch, chunk-pipelined."""
+        c, lib, hnd = self.ctx, self.ctx.lib, self.ctx.h
+        ns = c.n_streams
+        for k, c0 in enumerate(range(0, self.n, self.chunk)):
+            c1 = min(self.n, c0 + self.chunk)
+            m = c1 - c0
+            s = k % ns
+            c._chk(lib.b2_h2d_async(hnd, s, self.d_src.ptr + c0 * self.src_img,
+                                    self.p_src.ptr + c0 * self.src_img, m * self.src_img))
+            arr = (_abi.ImportJob * m).from_address(
+                _abi.C.addressof(self._job_arr) + c0 * _abi.C.sizeof(_abi.ImportJob))
+            c._chk(lib.b2_rgba_to_yuv420a(hnd, s, arr, m, self.order, self.flags, self.d_flags.ptr + 4 * c0))
+            c._chk(lib.b2_d2h_async(hnd, s, self.p_y.ptr + c0 * self.y_img, self.d_y.ptr + c0 * self.y_img, m * self.y_img))
+            c._chk(lib.b2_d2h_async(hnd, s, self.p_u.ptr + c0 * self.uv_img, self.d_u.ptr + c0 * self.uv_img, m * self.uv_img))
+            c._chk(lib.b2_d2h_async(hnd, s, self.p_v.ptr + c0 * self.uv_img, self.d_v.ptr + c0 * self.uv_img, m * self.uv_img))
+            c._chk(lib.b2_d2h_async(hnd, s, self.p_a.ptr + c0 * self.y_img, self.d_a.ptr + c0 * self.y_img, m * self.y_img))
+            c._chk(lib.b2_d2h_async(hnd, s, self.p_flags.ptr + 4 * c0, self.d_flags.ptr + 4 * c0, 4 * m))
+        c.sync()
+
+    def fill_synthetic(self, seed: int, first_img: int = 0, alpha_mode: int = _abi.SYNTH_OPAQUE,
+                       to_host: bool = False):
+        """Device-side generator (identical to the oracle's orc_synth_fill_u32)."""
+        c = self.ctx
+        c.synth_fill(self.d_src.ptr, self.w, self.h, 4 * self.w, self.src_img, self.n, seed, first_img, 0, alpha_mode)
+        c.sync()
+        if to_host and self.host:
+            c._chk(c.lib.b2_d2h_async(c.h, 0, self.p_src.ptr, self.d_src.ptr, self.src_img * self.n))
+            c.sync()
+
+    def device_planes(self, i: int):
+        """Copies image i's planes back from the device (after run_device())."""
+        c = self.ctx
+        y = c.d2h(self.d_y.ptr + i * self.y_img, self.ys * self.h).reshape(self.h, self.ys)[:, :self.w]
+        u = c.d2h(self.d_u.ptr + i * self.uv_img, self.uvs * self.uvh).reshape(self.uvh, self.uvs)[:, :self.uvw]
+        v = c.d2h(self.d_v.ptr + i * self.uv_img, self.uvs * self.uvh).reshape(self.uvh, self.uvs)[:, :self.uvw]
+        a = c.d2h(self.d_a.ptr + i * self.y_img, self.ys * self.h).reshape(self.h, self.ys)[:, :self.w]
+        ha = bool(c.d2h(self.d_flags.ptr + 4 * i, 4).view(np.int32)[0])
+        return y, u, v, a, ha
+
+    def close(self):
+        for b in ("d_src", "d_y", "d_u", "d_v", "d_a", "d_flags", "p_src", "p_y", "p_u", "p_v", "p_a", "p_flags"):
+            if hasattr(self, b):
+                getattr(self, b).free()
+
+
+class UpsamplePipeline:
+    def __init__(self, ctx: Context, n: int, width: int, height: int, mode: int = _abi.MODE_RGBA,
+                 with_alpha: bool = False, chunk: int = 8, host: bool = True):
+        self.ctx, self.n, self.w, self.h, self.mode = ctx, n, width, height, mode
+        self.bpp = _abi.MODE_BPP[mode]
+        self.chunk = max(1, min(chunk, n))
+        self.uvw, self.uvh = (width + 1) >> 1, (height + 1) >> 1
+        self.ys, self.uvs, self.ds = _al(width, 16), _al(self.uvw, 16), _al(width * self.bpp, 16)
+        self.y_img, self.uv_img, self.d_img = _al(self.ys * height), _al(self.uvs * self.uvh), _al(self.ds * height)
+        self.with_alpha = with_alpha
+        self.d_y = ctx.alloc(self.y_img * n)
+        self.d_u = ctx.alloc(self.uv_img * n)
+        self.d_v = ctx.alloc(self.uv_img * n)
+        self.d_a = ctx.alloc(self.y_img * n) if with_alpha else None
+        self.d_dst = ctx.alloc(self.d_img * n)
+        self.jobs = [_abi.UpsampleJob(self.d_y.ptr + i * self.y_img, self.d_u.ptr + i * self.uv_img,
+                                      self.d_v.ptr + i * self.uv_img,
+                                      self.d_a.ptr + i * self.y_img if with_alpha else None,
+                                      self.d_dst.ptr + i * self.d_img, self.ys, self.uvs, self.ys, self.ds,
+                                      width, height) for i in range(n)]
+        self._job_arr = (_abi.UpsampleJob * n)(*self.jobs)
+        self.host = host
+        if host:
+            self.p_y = ctx.pinned(self.y_img * n)
+            self.p_u = ctx.pinned(self.uv_img * n)
+            self.p_v = ctx.pinned(self.uv_img * n)
+            self.p_a = ctx.pinned(self.y_img * n) if with_alpha else None
+            self.p_dst = ctx.pinned(self.d_img * n)
+
+    @property
+    def h2d_bytes(self) -> int:
+        return (self.ys * self.h * (2 if self.with_alpha else 1) + 2 * self.uvs * self.uvh) * self.n
+
+    @property
+    def d2h_bytes(self) -> int:
+        return self.ds * self.h * self.n
+
+    def run_device(self, stream: int = 0):
+        c = self.ctx
+        c._chk(c.lib.b2_yuv420a_to_rgba_fancy(c.h, stream, self._job_arr, self.n, self.mode))
+
+    def run(self):
+        c, lib, hnd = self.ctx, self.ctx.lib, self.ctx.h
+        ns = c.n_streams
+        for k, c0 in enumerate(range(0, self.n, self.chunk)):
+            c1 = min(self.n, c0 + self.chunk)
+            m = c1 - c0
+            s = k % ns
+            c._chk(lib.b2_h2d_async(hnd, s, self.d_y.ptr + c0 * self.y_img, self.p_y.ptr + c0 * self.y_img, m * self.y_img))
+            c._chk(lib.b2_h2d_async(hnd, s, self.d_u.ptr + c0 * self.uv_img, self.p_u.ptr + c0 * self.uv_img, m * self.uv_img))
+            c._chk(lib.b2_h2d_async(hnd, s, self.d_v.ptr + c0 * self.uv_img, self.p_v.ptr + c0 * self.uv_img, m * self.uv_img))
+            if self.with_alpha:
+                c._chk(lib.b2_h2d_async(hnd, s, self.d_a.ptr + c0 * self.y_img, self.p_a.ptr + c0 * self.y_img, m * self.y_img))
+            arr = (_abi.UpsampleJob * m).from_address(
+                _abi.C.addressof(self._job_arr) + c0 * _abi.C.sizeof(_abi.UpsampleJob))
+            c._chk(lib.b2_yuv420a_to_rgba_fancy(hnd, s, arr, m, self.mode))
+            c._chk(lib.b2_d2h_async(hnd, s, self.p_dst.ptr + c0 * self.d_img, self.d_dst.ptr + c0 * self.d_img, m * self.d_img))
+        c.sync()
+
+    def fill_synthetic(self, seed: int, first_img: int = 0):
+        c = self.ctx
+        c.synth_fill(self.d_y.ptr, self.ys // 4, self.h, self.ys, self.y_img, self.n, seed, first_img, 1)
+        c.synth_fill(self.d_u.ptr, self.uvs // 4, self.uvh, self.uvs, self.uv_img, self.n, seed, first_img, 2)
+        c.synth_fill(self.d_v.ptr, self.uvs // 4, self.uvh, self.uvs, self.uv_img, self.n, seed, first_img, 3)
+        if self.with_alpha:
+            c.synth_fill(self.d_a.ptr, self.ys // 4, self.h, self.ys, self.y_img, self.n, seed, first_img, 4)
+        c.sync()
+
+    def device_image(self, i: int):
+        c = self.ctx
+        y = c.d2h(self.d_y.ptr + i * self.y_img, self.ys * self.h).reshape(self.h, self.ys)[:, :self.w]
+        u = c.d2h(self.d_u.ptr + i * self.uv_img, self.uvs * self.uvh).reshape(self.uvh, self.uvs)[:, :self.uvw]
+        v = c.d2h(self.d_v.ptr + i * self.uv_img, self.uvs * self.uvh).reshape(self.uvh, self.uvs)[:, :self.uvw]
+        a = None
+        if self.with_alpha:
+            a = c.d2h(self.d_a.ptr + i * self.y_img, self.ys * self.h).reshape(self.h, self.ys)[:, :self.w]
+        d = c.d2h(self.d_dst.ptr + i * self.d_img, self.ds * self.h).reshape(self.h, self.ds)[:, :self.w * self.bpp]
+        return y, u, v, a, d
+
+    def close(self):
+        for b in ("d_y", "d_u", "d_v", "d_a", "d_dst", "p_y", "p_u", "p_v", "p_a", "p_dst"):
+            x = getattr(self, b, None)
+            if x is not None:
+                x.free()
+
+
+class ArgbPipeline:
+    """Device-resident batch of n equal ARGB images for the VP8L transforms."""
+
+    def __init__(self, ctx: Context, n: int, width: int, height: int, op: str, bits: int):
+        self.ctx, self.n, self.w, self.h, self.op, self.bits = ctx, n, width, height, op, bits
+        self.index = op == "color_index_inverse"
+        sub = lambda v, b: (v + (1 << b) - 1) >> b  # noqa: E731
+        self.src_w = sub(width, bits) if self.index else width
+        self.src_img = _al(4 * self.src_w * height)
+        self.dst_img = _al(4 * width * height)
+        if self.index:
+            self.data_words = 1 << (8 >> bits)
+        elif op in ("add_green", "sub_green"):
+            self.data_words = 0
+        else:
+            self.data_words = sub(width, bits) * sub(height, bits)
+        self.data_img = _al(4 * max(self.data_words, 1))
+        self.d_src = ctx.alloc(self.src_img * n)
+        self.d_dst = ctx.alloc(self.dst_img * n)
+        self.d_data = ctx.alloc(self.data_img * n)
+        self.jobs = [_abi.ArgbJob(self.d_src.ptr + i * self.src_img, self.d_dst.ptr + i * self.dst_img,
+                                  self.d_data.ptr + i * self.data_img if self.data_words else None,
+                                  width, height, bits, 0) for i in range(n)]
+        self._job_arr = (_abi.ArgbJob * n)(*self.jobs)
+        self._fn = getattr(ctx.lib, "b2_vp8l_" + op)
+
+    def fill_synthetic(self, seed: int, first_img: int = 0):
+        c = self.ctx
+        c.synth_fill(self.d_src.ptr, self.src_w, self.h, 4 * self.src_w, self.src_img, self.n, seed, first_img, 5)
+        if self.data_words:
+            c.synth_fill(self.d_data.ptr, self.data_words, 1, 4 * self.data_words, self.data_img, self.n, seed, first_img, 6)
+        c.sync()
+
+    def run_device(self, stream: int = 0):
+        c = self.ctx
+        c._chk(self._fn(c.h, stream, self._job_arr, self.n))
+
+    def device_image(self, i: int):
+        c = self.ctx
+        src = c.d2h(self.d_src.ptr + i * self.src_img, 4 * self.src_w * self.h).view(np.uint32).reshape(self.h, self.src_w)
+        data = c.d2h(self.d_data.ptr + i * self.data_img, 4 * self.data_words).view(np.uint32) if self.data_words else None
+        dst = c.d2h(self.d_dst.ptr + i * self.dst_img, 4 * self.w * self.h).view(np.uint32).reshape(self.h, self.w)
+        return src, data, dst
+
+    def close(self):
+        for b in ("d_src", "d_dst", "d_data"):
+            getattr(self, b).free()

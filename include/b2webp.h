@@ -1,0 +1,202 @@
+/*
+ * b2webp.h -- C ABI of the B200 (sm_100a) pixel hot path for go-webp.
+ *
+ * This is the drop-in boundary: the only thing go-webp's Go packages bind
+ * (through the cgo shim go/pkg/cuda).  Plain pointers and
+ * sizes, no C++/torch types.  The library owns every device and pinned-host
+ * allocation; no caller pointer is retained after a call returns (cgo rule).
+ *
+ * All `file:line` citations are relative to the go-webp tree.
+ *
+ * Threading: a b2_ctx is bound to one device and is not thread-safe; use one
+ * context per host thread / per GPU.  All work is enqueued on the context's
+ * streams and is asynchronous until b2_sync().
+ *
+ * Status codes map onto go-webp's sentinels (pkg/picture/errors.go:8-21,
+ * pkg/vp8/enums.go:20-31): see b2_status below.
+ */
+#ifndef B2WEBP_H_
+#define B2WEBP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2_ABI_VERSION 0x0101
+
+typedef enum b2_status {
+  B2_OK = 0,
+  B2_ERR_OOM = -1,            /* ENC_ERROR_OUT_OF_MEMORY / VP8_STATUS_OUT_OF_MEMORY */
+  B2_ERR_BAD_DIM = -2,        /* ENC_ERROR_BAD_DIMENSION   */
+  B2_ERR_NULL = -3,           /* ENC_ERROR_nil_PARAMETER   */
+  B2_ERR_INVALID_CONFIG = -4, /* ENC_ERROR_INVALID_CONFIGURATION / VP8_STATUS_INVALID_PARAM */
+  B2_ERR_CUDA = -5            /* device/runtime failure; b2_last_error() has the text */
+} b2_status;
+
+/* WEBP_MAX_DIMENSION, pkg/libwebp/webp/encode.h.go:95 */
+#define B2_MAX_DIMENSION 16383
+
+typedef struct b2_ctx b2_ctx;
+
+/* ---- library / context ------------------------------------------------- */
+int b2_abi_version(void);
+const char* b2_strerror(int status);
+int b2_device_count(int* count);
+/* One context per GPU.  n_streams in [1,16]. */
+int b2_ctx_create(int device, int n_streams, b2_ctx** out);
+void b2_ctx_destroy(b2_ctx* ctx);
+int b2_ctx_device(const b2_ctx* ctx);
+int b2_ctx_sm_count(const b2_ctx* ctx);
+const char* b2_last_error(const b2_ctx* ctx);
+/* Kernels launched by this context so far (bench.py's gpu_launches claim). */
+uint64_t b2_launch_count(const b2_ctx* ctx);
+
+/* ---- memory, copies, sync, timing --------------------------------------- */
+int b2_pinned_alloc(b2_ctx* ctx, size_t bytes, void** host_ptr);
+int b2_pinned_free(b2_ctx* ctx, void* host_ptr);
+/* Page-lock caller memory for async copies (Go []byte must be pinned by the
+ * runtime.Pinner for the duration; the shim does that). */
+int b2_host_register(b2_ctx* ctx, void* host_ptr, size_t bytes);
+int b2_host_unregister(b2_ctx* ctx, void* host_ptr);
+int b2_dev_alloc(b2_ctx* ctx, size_t bytes, void** dev_ptr);
+int b2_dev_free(b2_ctx* ctx, void* dev_ptr);
+int b2_h2d_async(b2_ctx* ctx, int stream, void* dst_dev, const void* src_host, size_t bytes);
+int b2_d2h_async(b2_ctx* ctx, int stream, void* dst_host, const void* src_dev, size_t bytes);
+/* Pitched copies: the reference's planes have arbitrary (signed) strides;
+ * pitches here are the positive row distances of both sides. */
+int b2_h2d_2d_async(b2_ctx* ctx, int stream, void* dst_dev, size_t dst_pitch,
+                    const void* src_host, size_t src_pitch, size_t width_bytes, size_t rows);
+int b2_d2h_2d_async(b2_ctx* ctx, int stream, void* dst_host, size_t dst_pitch,
+                    const void* src_dev, size_t src_pitch, size_t width_bytes, size_t rows);
+int b2_memset_async(b2_ctx* ctx, int stream, void* dst_dev, int value, size_t bytes);
+/* stream < 0 waits for every stream of the context. */
+int b2_sync(b2_ctx* ctx, int stream);
+/* CUDA-event stopwatch on a context stream (slots 0..31). */
+int b2_event_record(b2_ctx* ctx, int stream, int slot);
+int b2_event_elapsed_ms(b2_ctx* ctx, int slot_start, int slot_stop, float* ms);
+
+/* ---- part 1: RGBA -> YUV420(+A) import ----------------------------------
+ * Replaces the row loop of dsp.WebPImportYUVAFromRGBA /
+ * WebPImportYUVAFromRGBALastLine (pkg/libwebp/dsp/yuv.go:304-382) and the
+ * has-alpha scan + driver of picture.ImportYUVAFromRGBA
+ * (pkg/picture/conversions.go:50-121) for a whole batch of images.
+ * All pointers are DEVICE pointers.  src addresses pixel (0,0); strides are in
+ * bytes and may be negative (flipped buffers, buffer_dec.c.go:161-184).
+ */
+typedef struct b2_import_job {
+  const uint8_t* src;
+  uint8_t* y;
+  uint8_t* u;
+  uint8_t* v;
+  uint8_t* a;         /* may be NULL: no alpha plane is written */
+  int32_t src_stride; /* |src_stride| >= bpp*width (picture_csp_enc.c.go:132) */
+  int32_t y_stride, uv_stride, a_stride;
+  int32_t width, height;
+} b2_import_job;
+
+/* Byte order of one source pixel (Import(): picture_csp_enc.c.go:123-137;
+ * ARGB-as-uint32 little-endian of PictureARGBToYUVA, conversions.go:22-26, is
+ * B,G,R,A in memory = B2_ORDER_BGRA). */
+typedef enum b2_pixel_order {
+  B2_ORDER_RGBA = 0, /* step 4: WebPPictureImportRGBA / RGBX */
+  B2_ORDER_BGRA = 1, /* step 4: WebPPictureImportBGRA / BGRX / ARGB32 */
+  B2_ORDER_RGB = 2,  /* step 3: WebPPictureImportRGB */
+  B2_ORDER_BGR = 3   /* step 3: WebPPictureImportBGR */
+} b2_pixel_order;
+
+#define B2_IMPORT_ALPHA 0x1     /* import_alpha=1: use byte 3 as alpha (step 4 only) */
+#define B2_IMPORT_DIV_TABLE 0x2 /* libwebp-binary kInvAlpha divide instead of the
+                                   reference's exact 4*sum/a (yuv.go:231) */
+
+/* has_alpha_dev: DEVICE int32[n_jobs]; entry i becomes 1 iff image i has any
+ * imported alpha != 0xff (conversions.go:56-58 -> WEBP_YUV420A), else 0.  May
+ * be NULL.  jobs is a HOST array (copied before return). */
+int b2_rgba_to_yuv420a(b2_ctx* ctx, int stream, const b2_import_job* jobs, int n_jobs,
+                       int order, int flags, int32_t* has_alpha_dev);
+
+/* ---- part 2: YUV420(+A) -> RGBA fancy upsampling -------------------------
+ * Replaces WebPUpsamplers[mode] line pairs (pkg/libwebp/dsp/upsampling.c.go:
+ * 43-114,275-289) driven by the whole-image schedule of WebPPictureYUVAToARGB
+ * (pkg/libwebp/enc/picture_csp_enc.c.go:62-118) == EmitFancyRGB's streaming
+ * schedule (pkg/libwebp/decoder/io_dec.c.go:65-115), with the alpha dispatch
+ * of EmitAlphaRGB (io_dec.c.go:175-195) fused into the store.
+ * mode: WEBP_CSP_MODE numbering (pkg/libwebp/webp/enums.go:45-64); premultiplied
+ * modes alias the plain ones exactly as upsampling.c.go:280-288 does.
+ */
+typedef enum b2_csp_mode {
+  B2_MODE_RGB = 0, B2_MODE_RGBA = 1, B2_MODE_BGR = 2, B2_MODE_BGRA = 3,
+  B2_MODE_ARGB = 4, B2_MODE_RGBA_4444 = 5, B2_MODE_RGB_565 = 6,
+  B2_MODE_rgbA = 7, B2_MODE_bgrA = 8, B2_MODE_Argb = 9, B2_MODE_rgbA_4444 = 10
+} b2_csp_mode;
+
+typedef struct b2_upsample_job {
+  const uint8_t* y;
+  const uint8_t* u;
+  const uint8_t* v;
+  const uint8_t* a; /* may be NULL: alpha byte = 0xff */
+  uint8_t* dst;
+  int32_t y_stride, uv_stride, a_stride, dst_stride; /* bytes, signed */
+  int32_t width, height;
+} b2_upsample_job;
+
+int b2_yuv420a_to_rgba_fancy(b2_ctx* ctx, int stream, const b2_upsample_job* jobs,
+                             int n_jobs, int mode);
+
+/* ---- part 3: VP8L per-pixel transforms -----------------------------------
+ * Pixels are uint32 0xAARRGGBB, images tightly packed (row stride == width,
+ * as dec.pixels / argb_cache are: pkg/vp8/vp8l_dec.c.go:710-760).
+ */
+typedef struct b2_argb_job {
+  const uint32_t* src;
+  uint32_t* dst;        /* may equal src for the same-size transforms */
+  const uint32_t* data; /* tile codes (cross-colour), palette (colour index), or NULL */
+  int32_t width, height;
+  int32_t bits;         /* VP8LTransform.bits (pkg/vp8/models.go:126-132) */
+  int32_t reserved;
+} b2_argb_job;
+
+/* VP8LAddGreenToBlueAndRed_C, pkg/libwebp/dsp/lossless.go:337-347 */
+int b2_vp8l_add_green(b2_ctx* ctx, int stream, const b2_argb_job* jobs, int n_jobs);
+/* VP8LSubtractGreenFromBlueAndRed_C, pkg/libwebp/dsp/lossless_enc.go:207-216 */
+int b2_vp8l_sub_green(b2_ctx* ctx, int stream, const b2_argb_job* jobs, int n_jobs);
+/* ColorSpaceInverseTransform_C + VP8LTransformColorInverse_C, lossless.go:359-413;
+ * data = ceil(w/2^bits) x ceil(h/2^bits) colour codes, bits in [2,9]. */
+int b2_vp8l_color_inverse(b2_ctx* ctx, int stream, const b2_argb_job* jobs, int n_jobs);
+/* VP8LTransformColor_C over given tile codes, lossless_enc.go:224-239 +
+ * pkg/libwebp/enc/predictor_enc.go:879-889. */
+int b2_vp8l_color_forward(b2_ctx* ctx, int stream, const b2_argb_job* jobs, int n_jobs);
+/* Fused cross-colour^-1 then add-green: the ApplyInverseTransforms order
+ * (pkg/vp8/vp8l_dec.c.go:710-729) for a chain without predictor, in one pass. */
+int b2_vp8l_inverse_chain(b2_ctx* ctx, int stream, const b2_argb_job* jobs, int n_jobs);
+/* Forward counterpart: sub-green then cross-colour forward in one pass
+ * (pkg/vp8/vp8l_encoder.go:926-961). */
+int b2_vp8l_forward_chain(b2_ctx* ctx, int stream, const b2_argb_job* jobs, int n_jobs);
+/* ColorIndexInverseTransform_C / MapARGB_C, lossless.go:415-459.  src rows are
+ * ceil(width/2^bits) pixels; data = palette of 1<<(8>>bits) entries (already
+ * expanded, vp8l_dec.c.go:1196-1219); bits in [0,3].  dst must not alias src. */
+int b2_vp8l_color_index_inverse(b2_ctx* ctx, int stream, const b2_argb_job* jobs, int n_jobs);
+/* VP8LBundleColorMap_C, lossless_enc.go:293-312: src = uint8 indices (one per
+ * pixel, row stride == width, passed through the src pointer), dst rows are
+ * ceil(width/2^bits) uint32. */
+int b2_vp8l_bundle_color_map(b2_ctx* ctx, int stream, const b2_argb_job* jobs, int n_jobs);
+
+/* ---- synthetic inputs (SURVEY.md 8d generator, identical to the oracle's) -
+ * One uint32 per (row, word) position of n images laid out 'image_bytes'
+ * apart, image ids first_img, first_img+1, ...  alpha_mode shapes the top byte
+ * (the alpha of a little-endian RGBA/BGRA pixel): */
+#define B2_SYNTH_RAW 0     /* uniform bytes everywhere                         */
+#define B2_SYNTH_OPAQUE 1  /* top byte forced to 0xff                          */
+#define B2_SYNTH_SPARSE 2  /* ~30% of pixels get a uniform alpha, rest 0xff     */
+#define B2_SYNTH_BINARY 3  /* alpha is 0x00 or 0xff, 50/50                      */
+int b2_synth_fill_batch_u32(b2_ctx* ctx, int stream, void* dst_dev, int words_per_row,
+                            int rows, int stride_bytes, size_t image_bytes, int n_images,
+                            uint32_t seed, uint32_t first_img, uint32_t plane,
+                            int alpha_mode);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2WEBP_H_ */

@@ -245,9 +245,9 @@ def argb_to_uv(row, u=None, v=None, do_store=True):
     return u, v
 
 
-def synth_u32(seed, img, plane, words_per_row, rows):
+def synth_u32(seed, img, plane, words_per_row, rows, alpha_mode=0):
     out = np.empty((rows, words_per_row), np.uint32)
     lib().orc_synth_fill_u32(C.c_uint32(seed), C.c_uint32(img),
                              C.c_uint32(plane), _p(out), words_per_row, rows,
-                             words_per_row * 4)
+                             words_per_row * 4, alpha_mode)
     return out

@@ -1066,15 +1066,30 @@ uint32_t orc_synth_word(uint32_t seed, uint32_t img, uint32_t plane,
   return lowbias32(seed ^ (img * 0x9E3779B1u) ^ (plane * 0x85EBCA77u) ^
                    (y * 0xC2B2AE3Du) ^ (x * 0x27D4EB2Fu));
 }
-/* One u32 per (y, x4) position; rows of 'words_per_row' u32 at 'stride' bytes. */
+/* Shapes the top byte (alpha of an LE RGBA pixel); modes as B2_SYNTH_* in    */
+/* include/b2webp.h: 0 raw, 1 opaque, 2 ~30% translucent, 3 binary.           */
+uint32_t orc_synth_alpha(uint32_t word, int alpha_mode) {
+  uint32_t h2;
+  if (alpha_mode == 0) return word;
+  if (alpha_mode == 1) return word | 0xff000000u;
+  h2 = lowbias32(word ^ 0x9E3779B9u);
+  if (alpha_mode == 2) {
+    if ((h2 & 0xff) >= 77) return word | 0xff000000u;
+    return (word & 0x00ffffffu) | (h2 & 0xff000000u);
+  }
+  return (word & 0x00ffffffu) | ((h2 & 1) ? 0xff000000u : 0u);
+}
+/* One u32 per (y, x) position; rows of 'words_per_row' u32 at 'stride' bytes. */
 void orc_synth_fill_u32(uint32_t seed, uint32_t img, uint32_t plane,
                         uint32_t* dst, int words_per_row, int rows,
-                        int stride_bytes) {
+                        int stride_bytes, int alpha_mode) {
   int y, x;
   for (y = 0; y < rows; ++y) {
     uint32_t* row = (uint32_t*)((uint8_t*)dst + (ptrdiff_t)y * stride_bytes);
     for (x = 0; x < words_per_row; ++x) {
-      row[x] = orc_synth_word(seed, img, plane, (uint32_t)y, (uint32_t)x);
+      row[x] = orc_synth_alpha(
+          orc_synth_word(seed, img, plane, (uint32_t)y, (uint32_t)x),
+          alpha_mode);
     }
   }
 }

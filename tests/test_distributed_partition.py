@@ -1,0 +1,59 @@
+"""world_size-2 gloo test of the N>1 path's host logic (no GPU): every rank
+derives its shard alone (no data-path collective), shards are disjoint and
+cover the batch, and the max-over-ranks timing reduction bench.py uses works."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    from go_webp_b200 import partition
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n = 37
+    mine = list(partition.contiguous_shard(n, world, rank))
+    costs = [(i * 7919) % 1000 + 1 for i in range(n)]
+    lpt = partition.lpt_partition(costs, world)[rank]
+    # verification-only collectives (the data path itself has none)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (mine, lpt))
+    t = torch.tensor([1.0 + rank], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        q.put((gathered, float(t)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharding_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    gathered, tmax = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    cont = sorted(i for g in gathered for i in g[0])
+    lpt = sorted(i for g in gathered for i in g[1])
+    assert cont == list(range(37)) and lpt == list(range(37))
+    assert tmax == 2.0

@@ -1,0 +1,375 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (via the host
+mirror of the reference API), against the CPU oracle and the committed libwebp
+1.6.0 fixtures.  Bar: bit-exact (all of this is integer fixed point)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+SIZES = [(1, 1), (1, 2), (2, 1), (2, 2), (3, 3), (4, 4), (5, 7), (6, 8), (7, 10), (16, 33),
+         (33, 16), (64, 64), (65, 31), (127, 129), (128, 2), (129, 3), (255, 9), (256, 8),
+         (257, 5), (260, 4), (515, 7), (1024, 6)]
+ALPHA = ["opaque", "rand", "sparse", "binary", "transp"]
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    from go_webp_b200 import _abi, device, dsp, picture
+    if device.device_count() < 1:
+        pytest.fail("no CUDA device: the gpu-marked tests must run on the B200 box")
+    return dict(abi=_abi, device=device, dsp=dsp, picture=picture, ctx=picture.default_context())
+
+
+def make_rgba(rng, w, h, kind):
+    rgba = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+    if kind == "opaque":
+        rgba[..., 3] = 255
+    elif kind == "sparse":
+        rgba[..., 3][rng.random((h, w)) < 0.7] = 255
+    elif kind == "binary":
+        rgba[..., 3] = np.where(rng.random((h, w)) < 0.5, 0, 255)
+    elif kind == "transp":
+        rgba[..., 3] = 0
+    return rgba
+
+
+def check_import(pic, exp, ctxt):
+    y, u, v, a, ha = exp
+    P = ctxt["picture"]
+    assert pic.ColorSpace == (P.WEBP_YUV420A if ha else P.WEBP_YUV420)
+    assert (pic.Y == y).all() and (pic.U == u).all() and (pic.V == v).all()
+    if ha:
+        assert (pic.A == a).all()
+    else:
+        assert pic.A is None
+
+
+# ---- part 1 ---------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ALPHA)
+def test_import_size_sweep_batched(gpu, kind):
+    """One mixed-size batch per alpha mix (odd widths/heights, 1x1 .. 1024x6)."""
+    P = gpu["picture"]
+    rng = np.random.default_rng(ALPHA.index(kind))
+    srcs = [make_rgba(rng, w, h, kind) for (w, h) in SIZES]
+    for table in (False, True):
+        pics = [P.Picture(Width=w, Height=h) for (w, h) in SIZES]
+        assert P.ImportRGBABatch(pics, srcs, [4 * w for (w, h) in SIZES], "RGBA", divide_table=table, chunk=5) == 1
+        for pic, src, (w, h) in zip(pics, srcs, SIZES):
+            exp = oracle.import_yuva(src, w, h, "RGBA",
+                                     divide_mode=oracle.DIV_TABLE if table else oracle.DIV_EXACT)
+            check_import(pic, exp, gpu)
+
+
+@pytest.mark.parametrize("order", ["BGRA", "RGBX", "BGRX", "RGB", "BGR"])
+def test_import_orders_strides(gpu, order):
+    P = gpu["picture"]
+    rng = np.random.default_rng(7)
+    step = 3 if len(order) == 3 else 4
+    for (w, h, pad) in [(37, 23, 12), (64, 16, 0), (5, 5, 3), (130, 9, 16)]:
+        stride = w * step + pad
+        src = rng.integers(0, 256, (h, stride), dtype=np.uint8)
+        pic = P.Picture(Width=w, Height=h)
+        fn = getattr(P, "WebPPictureImport" + order)
+        assert fn(pic, src, stride) == 1
+        check_import(pic, oracle.import_yuva(src, w, h, order, stride=stride), gpu)
+        # negative stride = vertically flipped buffer (buffer_dec.c.go:161-184)
+        pic2 = P.Picture(Width=w, Height=h)
+        assert P.ImportRGBABatch([pic2], [src], [-stride], order) == 1
+        check_import(pic2, oracle.import_yuva(src, w, h, order, stride=-stride), gpu)
+
+
+def test_import_golden_libwebp(gpu, golden_dir):
+    """Against the libwebp 1.6.0 binary's outputs (table-divide mode)."""
+    P = gpu["picture"]
+    g = np.load(os.path.join(golden_dir, "import_libwebp160.npz"))
+    n = int(g["n"][0])
+    pics, srcs, strides = [], [], []
+    for i in range(n):
+        w, h, ha = (int(x) for x in g[f"c{i}_meta"])
+        pics.append(P.Picture(Width=w, Height=h))
+        srcs.append(g[f"c{i}_src"])
+        strides.append(4 * w)
+    assert P.ImportRGBABatch(pics, srcs, strides, "RGBA", divide_table=True) == 1
+    for i, pic in enumerate(pics):
+        w, h, ha = (int(x) for x in g[f"c{i}_meta"])
+        assert (pic.Y == g[f"c{i}_y"]).all() and (pic.U == g[f"c{i}_u"]).all() and (pic.V == g[f"c{i}_v"]).all()
+        assert (pic.A is not None) == bool(ha)
+        if ha:
+            assert (pic.A == g[f"c{i}_a"]).all()
+
+
+def test_argb_to_yuva_route(gpu):
+    """PictureARGBToYUVA (conversions.go:12-30): ARGB u32 -> same planes as the
+    byte import of the equivalent RGBA image."""
+    P = gpu["picture"]
+    rng = np.random.default_rng(3)
+    w, h = 45, 19
+    rgba = make_rgba(rng, w, h, "sparse")
+    argb = (rgba[..., 3].astype(np.uint32) << 24) | (rgba[..., 0].astype(np.uint32) << 16) | \
+           (rgba[..., 1].astype(np.uint32) << 8) | rgba[..., 2]
+    pic = P.Picture(Width=w, Height=h, UseARGB=True, ARGB=argb, ARGBStride=w)
+    assert P.WebPPictureARGBToYUVA(pic, P.WEBP_YUV420) is None
+    assert pic.UseARGB is False
+    check_import(pic, oracle.import_yuva(rgba, w, h, "RGBA"), gpu)
+
+
+def test_import_error_behaviour(gpu):
+    P, abi, ctx = gpu["picture"], gpu["abi"], gpu["ctx"]
+    pic = P.Picture(Width=0, Height=4)
+    assert P.WebPPictureImportRGBA(pic, np.zeros(16, np.uint8), 4) == 0
+    assert pic.ErrorCode == P.ENC_ERROR_BAD_DIMENSION
+    pic = P.Picture(Width=8, Height=2)
+    assert P.WebPPictureImportRGBA(pic, np.zeros(64, np.uint8), 16) == 0  # |stride| < 4*w
+    assert P.WebPPictureImportRGBA(None, np.zeros(4, np.uint8), 4) == 0
+    # raw ABI: null plane, oversize dimension, alpha with a 3-byte order
+    job = abi.ImportJob(None, None, None, None, None, 16, 4, 2, 4, 4, 4)
+    arr = (abi.ImportJob * 1)(job)
+    assert ctx.lib.b2_rgba_to_yuv420a(ctx.h, 0, arr, 1, 0, 1, None) == abi.B2_ERR_NULL
+    buf = ctx.alloc(1 << 16)
+    job = abi.ImportJob(buf.ptr, buf.ptr, buf.ptr, buf.ptr, None, 4 * 16384, 16384, 8192, 0, 16384, 1)
+    arr = (abi.ImportJob * 1)(job)
+    assert ctx.lib.b2_rgba_to_yuv420a(ctx.h, 0, arr, 1, 0, 1, None) == abi.B2_ERR_BAD_DIM
+    job = abi.ImportJob(buf.ptr, buf.ptr, buf.ptr, buf.ptr, None, 12, 4, 2, 0, 4, 4)
+    arr = (abi.ImportJob * 1)(job)
+    assert ctx.lib.b2_rgba_to_yuv420a(ctx.h, 0, arr, 1, abi.ORDER_RGB, abi.IMPORT_ALPHA, None) == abi.B2_ERR_INVALID_CONFIG
+    assert ctx.lib.b2_rgba_to_yuv420a(ctx.h, 0, arr, 0, 0, 1, None) == abi.B2_OK  # empty batch
+    assert ctx.lib.b2_rgba_to_yuv420a(ctx.h, 99, arr, 1, 0, 1, None) == abi.B2_ERR_INVALID_CONFIG
+
+
+# ---- part 2 ---------------------------------------------------------------------
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9])
+def test_upsample_size_sweep_batched(gpu, mode):
+    P = gpu["picture"]
+    rng = np.random.default_rng(100 + mode)
+    for with_a in (False, True):
+        pics, exps = [], []
+        for (w, h) in SIZES:
+            uw, uh = (w + 1) // 2, (h + 1) // 2
+            y = rng.integers(0, 256, (h, w), dtype=np.uint8)
+            u = rng.integers(0, 256, (uh, uw), dtype=np.uint8)
+            v = rng.integers(0, 256, (uh, uw), dtype=np.uint8)
+            a = rng.integers(0, 256, (h, w), dtype=np.uint8) if with_a else None
+            pics.append(P.Picture(Width=w, Height=h, Y=y, U=u, V=v, A=a,
+                                  ColorSpace=P.WEBP_YUV420A if with_a else P.WEBP_YUV420))
+            omode = {7: 1, 8: 3, 9: 4}.get(mode, mode)  # premultiplied modes alias (upsampling.c.go:280-288)
+            exps.append(oracle.yuva_to_rgba(y, u, v, a, omode))
+        outs = P.YUVAToRGBABatch(pics, mode, chunk=7)
+        assert outs is not None
+        for o, e, s in zip(outs, exps, SIZES):
+            assert (o == e).all(), (s, mode, with_a)
+
+
+def test_upsample_golden_libwebp(gpu, golden_dir):
+    P = gpu["picture"]
+    g = np.load(os.path.join(golden_dir, "upsample_libwebp160.npz"))
+    for i in range(int(g["n"][0])):
+        y, u, v, a = g[f"c{i}_y"], g[f"c{i}_u"], g[f"c{i}_v"], g[f"c{i}_a"]
+        h, w = y.shape
+        pic = P.Picture(Width=w, Height=h, Y=y, U=u, V=v, A=a if a.size else None,
+                        ColorSpace=P.WEBP_YUV420A if a.size else P.WEBP_YUV420)
+        assert P.WebPPictureYUVAToARGB(pic) == 1 and pic.UseARGB
+        assert (pic.ARGB == g[f"c{i}_argb"]).all(), (w, h)
+
+
+def test_decoder_golden_all_modes(gpu, golden_dir):
+    """Real lossy files decoded by libwebp 1.6.0: planes in, every RGB mode out."""
+    P = gpu["picture"]
+    g = np.load(os.path.join(golden_dir, "decode_libwebp160.npz"))
+    for i in range(int(g["n"][0])):
+        y, u, v, a = g[f"c{i}_y"], g[f"c{i}_u"], g[f"c{i}_v"], g[f"c{i}_a"]
+        h, w = y.shape
+        for mode in range(7):
+            pic = P.Picture(Width=w, Height=h, Y=y, U=u, V=v, A=a if a.size else None,
+                            ColorSpace=P.WEBP_YUV420A if a.size else P.WEBP_YUV420)
+            got = P.YUVAToRGBABatch([pic], mode)[0]
+            exp = g[f"c{i}_m{mode}"]
+            if mode == 5 and a.size:
+                got, exp = got.copy(), exp.copy()
+                got[:, 1::2] |= 0x0f
+                exp[:, 1::2] |= 0x0f
+            assert (got == exp).all(), (i, mode)
+
+
+def test_upsample_line_pair_table(gpu):
+    """WebPUpsamplers[mode](top_y, bottom_y, top_u, top_v, cur_u, cur_v, len) with
+    the reference's argument meaning (dsp.h.go:144)."""
+    D = gpu["dsp"]
+    rng = np.random.default_rng(11)
+    for n in (1, 2, 7, 8, 33, 300):
+        uw = (n + 1) // 2
+        ty, by = rng.integers(0, 256, n, dtype=np.uint8), rng.integers(0, 256, n, dtype=np.uint8)
+        tu, tv, cu, cv = (rng.integers(0, 256, uw, dtype=np.uint8) for _ in range(4))
+        for mode in (1, 3, 4, 0):
+            top, bot = D.WebPUpsamplers[mode](ty, by, tu, tv, cu, cv, n)
+            etop, ebot = oracle.upsample_line_pair(mode, ty, by, tu, tv, cu, cv)
+            assert (top == etop).all() and (bot == ebot).all()
+            top, bot = D.WebPUpsamplers[mode](ty, None, tu, tv, tu, tv, n)
+            etop, _ = oracle.upsample_line_pair(mode, ty, None, tu, tv, tu, tv)
+            assert (top == etop).all() and bot is None
+
+
+def test_upsample_error_behaviour(gpu):
+    P, abi, ctx = gpu["picture"], gpu["abi"], gpu["ctx"]
+    pic = P.Picture(Width=4, Height=4)
+    assert P.WebPPictureYUVAToARGB(pic) == 0 and pic.ErrorCode == P.ENC_ERROR_nil_PARAMETER
+    y = np.zeros((4, 4), np.uint8)
+    uv = np.zeros((2, 2), np.uint8)
+    pic = P.Picture(Width=4, Height=4, Y=y, U=uv, V=uv, ColorSpace=P.WEBP_YUV420A)
+    assert P.WebPPictureYUVAToARGB(pic) == 0 and pic.ErrorCode == P.ENC_ERROR_nil_PARAMETER
+    pic = P.Picture(Width=4, Height=4, Y=y, U=uv, V=uv, ColorSpace=1)
+    assert P.WebPPictureYUVAToARGB(pic) == 0 and pic.ErrorCode == P.ENC_ERROR_INVALID_CONFIGURATION
+    buf = ctx.alloc(4096)
+    job = abi.UpsampleJob(buf.ptr, buf.ptr, buf.ptr, None, buf.ptr, 8, 4, 0, 8, 8, 2)  # dst_stride < 4*w
+    arr = (abi.UpsampleJob * 1)(job)
+    assert ctx.lib.b2_yuv420a_to_rgba_fancy(ctx.h, 0, arr, 1, abi.MODE_RGBA) == abi.B2_ERR_BAD_DIM
+    assert ctx.lib.b2_yuv420a_to_rgba_fancy(ctx.h, 0, arr, 1, 11) == abi.B2_ERR_INVALID_CONFIG
+
+
+def test_import_then_upsample_roundtrip_config0(gpu):
+    """BASELINE configs[0]: one 1920x1080 image, import then fancy upsample, GPU
+    vs the CPU path end to end (opaque and random alpha)."""
+    P = gpu["picture"]
+    w, h = 1920, 1080
+    for alpha_mode in (1, 0):
+        rgba = oracle.synth_u32(0xB2000001, 0, 0, w, h, alpha_mode).view(np.uint8).reshape(h, w, 4)
+        pic = P.Picture(Width=w, Height=h)
+        assert P.WebPPictureImportRGBA(pic, rgba, 4 * w) == 1
+        y, u, v, a, ha = oracle.import_yuva(rgba, w, h, "RGBA")
+        check_import(pic, (y, u, v, a, ha), gpu)
+        assert P.WebPPictureYUVAToARGB(pic) == 1
+        exp = oracle.yuva_to_rgba(y, u, v, a if ha else None, oracle.MODE_BGRA).view(np.uint32).reshape(h, w)
+        assert (pic.ARGB == exp).all()
+
+
+# ---- part 3 ---------------------------------------------------------------------
+VP8L_SIZES = [(1, 1), (3, 1), (4, 4), (5, 7), (33, 17), (100, 70), (128, 64), (129, 5), (256, 4), (1000, 3)]
+
+
+@pytest.mark.parametrize("bits", [2, 3, 5, 9])
+def test_vp8l_flat_transforms(gpu, bits):
+    D, ctx, abi = gpu["dsp"], gpu["ctx"], gpu["abi"]
+    rng = np.random.default_rng(bits)
+    for (w, h) in VP8L_SIZES:
+        x = rng.integers(0, 2**32, (h, w), dtype=np.uint32)
+        tw, th = D.VP8LSubSampleSize(w, bits), D.VP8LSubSampleSize(h, bits)
+        codes = rng.integers(0, 2**24, (th, tw), dtype=np.uint32) | 0xff000000
+        r = {op: D._flat(op, x, codes, w, h, bits) for op in
+             ("add_green", "sub_green", "color_inverse", "color_forward", "inverse_chain", "forward_chain")}
+        assert (r["add_green"] == oracle.add_green(x)).all()
+        assert (r["sub_green"] == oracle.sub_green(x)).all()
+        assert (r["color_inverse"] == oracle.color_space_inverse(x, codes, bits)).all()
+        assert (r["color_forward"] == oracle.color_space_forward(x, codes, bits)).all()
+        assert (r["inverse_chain"] == oracle.add_green(oracle.color_space_inverse(x, codes, bits))).all()
+        fwd = oracle.color_space_forward(oracle.sub_green(x), codes, bits)
+        assert (r["forward_chain"] == fwd).all()
+        # inverse o forward == identity on the device path
+        assert (D._flat("inverse_chain", r["forward_chain"], codes, w, h, bits) == x).all()
+
+
+def test_vp8l_in_place(gpu):
+    """dst may alias src for the same-size transforms (the reference's
+    VP8LSubtractGreenFromBlueAndRed / VP8LTransformColor work in place)."""
+    ctx, abi = gpu["ctx"], gpu["abi"]
+    rng = np.random.default_rng(5)
+    w, h = 260, 37
+    x = rng.integers(0, 2**32, (h, w), dtype=np.uint32)
+    buf = ctx.upload(x)
+    ctx.vp8l("sub_green", [abi.ArgbJob(buf.ptr, buf.ptr, None, w, h, 0, 0)])
+    got = ctx.d2h(buf.ptr, x.nbytes).view(np.uint32).reshape(h, w)
+    assert (got == oracle.sub_green(x)).all()
+
+
+@pytest.mark.parametrize("bits", [0, 1, 2, 3])
+def test_vp8l_color_index_and_bundle(gpu, bits):
+    D = gpu["dsp"]
+    rng = np.random.default_rng(40 + bits)
+    ncol = 1 << (8 >> bits)
+    for w in list(range(1, 41)) + [127, 128, 129, 255, 256, 257, 1000]:
+        h = 3 if w < 100 else 5
+        pal = rng.integers(0, 2**32, ncol, dtype=np.uint32)
+        idx = rng.integers(0, ncol, (h, w), dtype=np.uint8)
+        packed = D.VP8LBundleColorMap(idx, w, bits)
+        assert (packed == oracle.bundle_color_map(idx, bits)).all(), w
+        t = D.VP8LTransform(D.COLOR_INDEXING_TRANSFORM, bits, w, h, pal)
+        out = D.VP8LInverseTransform(t, 0, h, packed)
+        assert (out == oracle.color_index_inverse(packed, pal, bits, w)).all(), w
+        assert (out == pal[idx]).all()
+
+
+def test_vp8l_named_row_functions(gpu):
+    D = gpu["dsp"]
+    rng = np.random.default_rng(77)
+    src = rng.integers(0, 2**32, 777, dtype=np.uint32)
+    assert (D.VP8LAddGreenToBlueAndRed(src, 777) == oracle.add_green(src)).all()
+    assert (D.VP8LSubtractGreenFromBlueAndRed(src, 700) == oracle.sub_green(src[:700])).all()
+    code = D.MultipliersToColorCode(0x9c, 0x31, 0xe0)
+    exp = np.empty_like(src)
+    L = oracle.lib()
+    L.orc_transform_color_inverse(C.c_uint32(code), src.ctypes.data_as(C.c_void_p), src.size,
+                                  exp.ctypes.data_as(C.c_void_p))
+    assert (D.VP8LTransformColorInverse(code, src) == exp).all()
+    fw = src.copy()
+    L.orc_transform_color(C.c_uint32(code), fw.ctypes.data_as(C.c_void_p), fw.size)
+    assert (D.VP8LTransformColor(code, src) == fw).all()
+    pal = rng.integers(0, 2**32, 200, dtype=np.uint32)
+    img = (rng.integers(0, 200, (6, 50), dtype=np.uint32) << 8) | 0xff000000
+    assert (D.VP8LMapColor32b(img, pal, 0, 6, 50) == pal[(img >> 8) & 0xff]).all()
+
+
+def test_vp8l_inverse_transform_rows_and_batch(gpu):
+    """VP8LInverseTransform on row windows (as ProcessRows feeds <=16 rows,
+    vp8l_dec.c.go:733-760) and the batched chain entry point."""
+    D = gpu["dsp"]
+    rng = np.random.default_rng(88)
+    w, h, bits = 70, 50, 3
+    x = rng.integers(0, 2**32, (h, w), dtype=np.uint32)
+    codes = rng.integers(0, 2**24, (D.VP8LSubSampleSize(h, bits), D.VP8LSubSampleSize(w, bits)),
+                         dtype=np.uint32) | 0xff000000
+    t_cc = D.VP8LTransform(D.CROSS_COLOR_TRANSFORM, bits, w, h, codes)
+    t_sg = D.VP8LTransform(D.SUBTRACT_GREEN_TRANSFORM, 0, w, h)
+    full = oracle.color_space_inverse(x, codes, bits)
+    for (r0, r1) in [(0, 16), (16, 32), (32, 48), (48, 50), (5, 21)]:
+        assert (D.VP8LInverseTransform(t_cc, r0, r1, x[r0:r1]) == full[r0:r1]).all()
+        assert (D.VP8LInverseTransform(t_sg, r0, r1, x[r0:r1]) == oracle.add_green(x[r0:r1])).all()
+    # batch: image 0 = [sub-green, cross-colour] (fused), image 1 = colour index 2-bit,
+    # image 2 = cross-colour only
+    pal = rng.integers(0, 2**32, 4, dtype=np.uint32)
+    idx = rng.integers(0, 4, (h, w), dtype=np.uint8)
+    packed = oracle.bundle_color_map(idx, 2)
+    t_ci = D.VP8LTransform(D.COLOR_INDEXING_TRANSFORM, 2, w, h, pal)
+    outs = D.VP8LInverseTransformBatch(
+        [D.VP8LImage(x, w, h), D.VP8LImage(packed, w, h), D.VP8LImage(x, w, h)],
+        [[t_sg, t_cc], [t_ci], [t_cc]])
+    assert (outs[0] == oracle.add_green(full)).all()
+    assert (outs[1] == pal[idx]).all()
+    assert (outs[2] == full).all()
+
+
+def test_vp8l_error_behaviour(gpu):
+    ctx, abi = gpu["ctx"], gpu["abi"]
+    buf = ctx.alloc(4096)
+    bad_bits = (abi.ArgbJob * 1)(abi.ArgbJob(buf.ptr, buf.ptr, buf.ptr, 8, 8, 1, 0))
+    assert ctx.lib.b2_vp8l_color_inverse(ctx.h, 0, bad_bits, 1) == abi.B2_ERR_INVALID_CONFIG
+    no_codes = (abi.ArgbJob * 1)(abi.ArgbJob(buf.ptr, buf.ptr, None, 8, 8, 3, 0))
+    assert ctx.lib.b2_vp8l_inverse_chain(ctx.h, 0, no_codes, 1) == abi.B2_ERR_NULL
+    alias = (abi.ArgbJob * 1)(abi.ArgbJob(buf.ptr, buf.ptr, buf.ptr, 8, 8, 2, 0))
+    assert ctx.lib.b2_vp8l_color_index_inverse(ctx.h, 0, alias, 1) == abi.B2_ERR_INVALID_CONFIG
+    bad_dim = (abi.ArgbJob * 1)(abi.ArgbJob(buf.ptr, buf.ptr, None, 0, 8, 0, 0))
+    assert ctx.lib.b2_vp8l_add_green(ctx.h, 0, bad_dim, 1) == abi.B2_ERR_BAD_DIM
+
+
+# ---- device-resident synthetic inputs ----------------------------------------------
+def test_synth_generator_matches_oracle(gpu):
+    ctx, abi = gpu["ctx"], gpu["abi"]
+    w, h, n = 52, 9, 3
+    buf = ctx.alloc(4 * w * h * n)
+    for mode in range(4):
+        ctx.synth_fill(buf.ptr, w, h, 4 * w, 4 * w * h, n, 0xB2000002, 5, 1, mode)
+        got = ctx.d2h(buf.ptr, 4 * w * h * n).view(np.uint32).reshape(n, h, w)
+        for i in range(n):
+            assert (got[i] == oracle.synth_u32(0xB2000002, 5 + i, 1, w, h, mode)).all()

@@ -1,0 +1,417 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the go-webp pixel hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1]): a batch of 256 synthetic 1920x1080 RGBA
+frames per GPU, RGBA -> YUV420(+A) import.  A "step" is one pass of the import
+kernel over the resident batch (one kernel launch).  Weak scaling: every rank
+owns its own 256-frame batch, no data-path collective (images are independent).
+
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput (inputs in
+HBM before the timed region); `e2e` is the same metric through the batched
+public entry point (go_webp_b200.pipeline.ImportPipeline.run) with pinned HOST
+buffers, H2D and D2H inside the timed region.  `roofline` is for the import
+kernel; `cpu_baseline` is the CPU oracle port timed on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+W, H = 1920, 1080
+SEED = 0xB2000001  # config k uses seed 0xB2000000 + k
+METRIC = "Mpixel/s batched 1080p RGBA<->YUV420 + VP8L inverse at 1-8 B200; % of HBM peak"
+ALPHA_MODES = {"opaque": 1, "sparse": 2, "binary": 3, "raw": 0}
+# algorithmic bytes per pixel: 4 in + 1 Y + 0.5 UV + 1 A
+IMPORT_BYTES_PER_PX = 4 + 1 + 0.5 + 1
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """Polls NVML for SM clock and throttle reasons while the GPU is under load."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown",
+               0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting"}
+
+    def __init__(self, device_index: int):
+        super().__init__(daemon=True)
+        self.samples = []  # (t, sm_mhz, reasons_bitmask)
+        self.stop_flag = False
+        self.ok = False
+        self.sm_max = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = device_index
+            if vis:
+                try:
+                    idx = int(vis.split(",")[device_index])
+                except Exception:
+                    idx = device_index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((time.perf_counter(), mhz, int(r)))
+            except Exception:
+                pass
+            time.sleep(0.001)
+
+    def summary(self, t0, t1, t_load0):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": [], "samples": 0, "window": "unavailable"}
+        win = [s for s in self.samples if t0 <= s[0] <= t1]
+        window = "timed"
+        if len(win) < 3:
+            win = [s for s in self.samples if t_load0 <= s[0] <= t1]
+            window = "warmup+timed"
+        if not win:
+            win, window = self.samples, "run"
+        bits = 0
+        for s in win:
+            bits |= s[2]
+        reasons = sorted(n for b, n in self.REASONS.items() if bits & b)
+        return {"sm_mhz": float(np.median([s[1] for s in win])), "sm_max_mhz": self.sm_max,
+                "reasons": reasons, "samples": len(win), "window": window}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# ---- CPU side (oracle port): used only as the reported baseline -------------------
+def cpu_import_rate(n_frames: int, threads: int, alpha_mode: int, scalar: bool = False):
+    """Times the oracle's RGBA->YUV420A import over n_frames 1080p frames with
+    'threads' host threads (one image per task).  Returns (Mpx/s, seconds)."""
+    import oracle
+    L = oracle.lib(scalar)
+    distinct = min(n_frames, 32)
+    src = np.empty((distinct, H, W), np.uint32)
+    for i in range(distinct):
+        src[i] = oracle.synth_u32(SEED, i, 0, W, H, alpha_mode)
+    if distinct < n_frames:
+        src = np.concatenate([src] * ((n_frames + distinct - 1) // distinct))[:n_frames]
+    src = np.ascontiguousarray(src)
+    uvw, uvh = (W + 1) // 2, (H + 1) // 2
+    y = np.empty((n_frames, H, W), np.uint8)
+    u = np.empty((n_frames, uvh, uvw), np.uint8)
+    v = np.empty((n_frames, uvh, uvw), np.uint8)
+    a = np.empty((n_frames, H, W), np.uint8)
+    ha = np.zeros(n_frames, np.int32)
+    vp = lambda x: x.ctypes.data_as(C.c_void_p)  # noqa: E731
+    t0 = time.perf_counter()
+    rc = L.orc_import_batch_mt(vp(src), n_frames, W, H, vp(y), vp(u), vp(v), vp(a), vp(ha), 0, threads)
+    dt = time.perf_counter() - t0
+    assert rc == 0
+    return n_frames * W * H / dt / 1e6, dt
+
+
+def libwebp_import_rate(n_frames: int, threads: int, alpha_mode: int):
+    """Upstream libwebp 1.6.0 (SIMD C) WebPPictureImportRGBA, if Pillow's bundled
+    binary is present: the 'upstream SIMD C' figure of BASELINE.md 3."""
+    try:
+        import oracle
+        from concurrent.futures import ThreadPoolExecutor
+        from oracle import libwebp_ref as ref
+        ref.lib()
+        frames = [oracle.synth_u32(SEED, i, 0, W, H, alpha_mode).view(np.uint8) for i in range(min(8, n_frames))]
+
+        def work(i):
+            ref.import_yuva(frames[i % len(frames)], W, H, "RGBA")
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(threads) as ex:
+            list(ex.map(work, range(n_frames)))
+        dt = time.perf_counter() - t0
+        return n_frames * W * H / dt / 1e6
+    except Exception:
+        return None
+
+
+def host_threads() -> int:
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation of the path on the host cores.
+    The Go reference does not compile and no Go toolchain exists, so
+    this is the oracle port, with all host threads, on the same config/metric."""
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return 0
+    import oracle
+    oracle.build()
+    T = host_threads()
+    alpha_mode = ALPHA_MODES[args.alpha]
+    # bounded sample per step: sized from a probe so (K+W) steps take ~2 minutes at most
+    probe_frames = max(T, 8)
+    rate, dt = cpu_import_rate(probe_frames, T, alpha_mode)
+    budget = 100.0 / max(1, args.steps + args.warmup)
+    frames = int(min(args.frames, max(T, rate * 1e6 * min(budget, 4.0) / (W * H))))
+    for _ in range(args.warmup):
+        cpu_import_rate(frames, T, alpha_mode)
+    t = 0.0
+    for _ in range(args.steps):
+        t += cpu_import_rate(frames, T, alpha_mode)[1]
+    value = frames * W * H * args.steps / t / 1e6
+    sample = f"{frames} of {args.frames} 1080p frames per step, one image per task"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "Mpixel/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic", "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": "Mpixel/s", "cores": T, "kind": "port", "sample": sample,
+                         "note": "gcc -O2 C restatement of the reference (oracle/oracle.c); Go reference "
+                                 "cannot be built: GOMAXPROCS n/a"},
+        "e2e": {"value": value, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args):
+    return {"workload": f"configs[1]: {args.frames} x {W}x{H} synthetic RGBA frames per GPU, RGBA->YUV420A import "
+                        f"(Y,U,V,A planes + has_alpha flag), alpha mix '{args.alpha}'",
+            "frames_per_gpu": args.frames, "width": W, "height": H, "alpha_mix": args.alpha,
+            "partition": "images sharded by rank, no collective",
+            "l2": "input batch (2.1 GB) and outputs (1.3 GB) are >> 126 MB L2; no flush needed",
+            "seed": hex(SEED)}
+
+
+def other_kernels(ctx, peak, steps):
+    """Device-resident numbers for the rest of the path at reduced batch sizes
+    (explanatory; not the headline): 4K fancy upsample and the VP8L transforms."""
+    from go_webp_b200 import _abi
+    from go_webp_b200.pipeline import ArgbPipeline, UpsamplePipeline
+    out = {}
+
+    def timed(run, n_steps):
+        for _ in range(3):
+            run()
+        ctx.sync()
+        ctx.event_record(2)
+        for _ in range(n_steps):
+            run()
+        ctx.event_record(3)
+        ctx.sync()
+        return ctx.elapsed_ms(2, 3) / n_steps
+
+    k = max(3, min(steps, 20))
+    up = UpsamplePipeline(ctx, 64, 3840, 2160, _abi.MODE_RGBA, with_alpha=False, host=False)
+    up.fill_synthetic(0xB2000004)
+    ms = timed(up.run_device, k)
+    px = 64 * 3840 * 2160
+    out["fancy_upsample_4k_rgba"] = {"frames": 64, "mpixel_per_s": px / ms / 1e3, "bytes_per_px": 5.5,
+                                     "gbs": px * 5.5 / ms / 1e6, "frac": px * 5.5 / ms / 1e6 / peak}
+    up.close()
+    for op, bits, bpp, name in [("inverse_chain", 5, 8.0039, "vp8l_crosscolor_inv_addgreen_fused"),
+                                ("add_green", 0, 8.0, "vp8l_add_green"),
+                                ("color_index_inverse", 0, 8.0, "vp8l_color_index_8bit"),
+                                ("color_index_inverse", 2, 5.0, "vp8l_color_index_2bit")]:
+        ap = ArgbPipeline(ctx, 16, 4096, 4096, op, bits)
+        ap.fill_synthetic(0xB2000003)
+        ms = timed(ap.run_device, k)
+        px = 16 * 4096 * 4096
+        out[name] = {"frames": 16, "mpixel_per_s": px / ms / 1e3, "bytes_per_px": bpp,
+                     "gbs": px * bpp / ms / 1e6, "frac": px * bpp / ms / 1e6 / peak}
+        ap.close()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=256)
+    ap.add_argument("--alpha", default="sparse", choices=sorted(ALPHA_MODES))
+    ap.add_argument("--no-extras", action="store_true", help="skip other kernels / cpu baseline")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)  # timing rule: W >= 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    rank, world, local = dist_env()
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from go_webp_b200 import _abi
+    from go_webp_b200.device import Context
+    from go_webp_b200.pipeline import ImportPipeline
+
+    peak, peak_src = hbm_peak()
+    ctx = Context(local, n_streams=4)
+    alpha_mode = ALPHA_MODES[args.alpha]
+    pipe = ImportPipeline(ctx, args.frames, W, H, "RGBA", import_alpha=True, chunk=16, host=True)
+    pipe.fill_synthetic(SEED, first_img=rank * args.frames, alpha_mode=alpha_mode, to_host=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    t_load0 = time.perf_counter()
+    for _ in range(args.warmup):
+        pipe.run_device()
+    barrier()
+    launches0 = ctx.launches
+    t0 = time.perf_counter()
+    ctx.event_record(0)
+    for _ in range(args.steps):
+        pipe.run_device()
+    ctx.event_record(1)
+    barrier()
+    t1 = time.perf_counter()
+    launches = ctx.launches - launches0
+    ms = ctx.elapsed_ms(0, 1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clocks = sampler.summary(t0, t1, t_load0)
+    px_step = world * args.frames * W * H
+    ms_step = ms / args.steps
+    value = px_step / ms_step / 1e3  # Mpixel/s
+    gbs_rank = args.frames * W * H * IMPORT_BYTES_PER_PX / ms_step / 1e6
+
+    # parity spot check against the oracle (outside every timed region)
+    parity = "skipped"
+    if rank == 0:
+        import oracle
+        oracle.build()
+        ok = True
+        for i in (0, args.frames - 1):
+            src = oracle.synth_u32(SEED, rank * args.frames + i, 0, W, H, alpha_mode).view(np.uint8)
+            ey, eu, ev, ea, eha = oracle.import_yuva(src, W, H, "RGBA")
+            gy, gu, gv, ga, gha = pipe.device_planes(i)
+            ok &= bool((gy == ey).all() and (gu == eu).all() and (gv == ev).all() and (ga == ea).all() and gha == eha)
+        parity = "bit-exact vs oracle on frames 0 and %d" % (args.frames - 1) if ok else "MISMATCH"
+
+    # end to end: pinned host -> device -> kernel -> pinned host, every step
+    e2e_steps = max(2, min(args.steps, 8))
+    pipe.run()
+    barrier()
+    te0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        pipe.run()
+    barrier()
+    te = time.perf_counter() - te0
+    if world > 1:
+        t = torch.tensor([te], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        te = float(t.item())
+    e2e_value = px_step * e2e_steps / te / 1e6
+    if rank == 0 and parity != "MISMATCH":
+        y, u, v, a, ha = pipe.planes(0)
+        gy, gu, gv, ga, gha = pipe.device_planes(0)
+        if not ((y == gy).all() and (u == gu).all() and (v == gv).all() and ha == gha):
+            parity = "MISMATCH (e2e)"
+    sampler.stop_flag = True
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload_config(args),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "Mpixel/s", "h2d_bytes_per_step": pipe.h2d_bytes,
+                "d2h_bytes_per_step": pipe.d2h_bytes, "steps": e2e_steps,
+                "api": "go_webp_b200.pipeline.ImportPipeline.run (pinned host buffers, 4 streams)"},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "achieved": gbs_rank, "peak": peak, "unit": "GB/s",
+                     "frac": gbs_rank / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
+                     "kernel": "import_kernel<RGBA,alpha>", "algorithmic_bytes_per_px": IMPORT_BYTES_PER_PX,
+                     "frac_of_8000_nominal": gbs_rank / 8000.0, "per": "GPU (rank 0 step time = max over ranks)"},
+        "parity": parity,
+    }
+    if rank == 0 and world == 1 and not args.no_extras:
+        T = host_threads()
+        n_cpu = int(min(args.frames, max(2 * T, 64)))
+        rate, dt = cpu_import_rate(n_cpu, T, alpha_mode)
+        rate1, _ = cpu_import_rate(4, 1, alpha_mode)
+        line["cpu_baseline"] = {
+            "value": rate, "unit": "Mpixel/s", "cores": T, "kind": "port",
+            "sample": f"{n_cpu} of {args.frames} frames, one image per task, {dt:.2f} s wall",
+            "single_thread": rate1, "libwebp160_simd_all_threads": libwebp_import_rate(n_cpu, T, alpha_mode),
+            "note": "oracle/oracle.c (gcc -O2) restating the reference; the Go reference does not compile "
+                    "and no Go toolchain exists here: GOMAXPROCS n/a"}
+        alpha_mixes = {}
+        for name, am in ALPHA_MODES.items():
+            pipe.fill_synthetic(SEED, first_img=0, alpha_mode=am)
+            for _ in range(3):
+                pipe.run_device()
+            ctx.sync()
+            ctx.event_record(4)
+            for _ in range(10):
+                pipe.run_device()
+            ctx.event_record(5)
+            ctx.sync()
+            m = ctx.elapsed_ms(4, 5) / 10
+            alpha_mixes[name] = {"mpixel_per_s": args.frames * W * H / m / 1e3,
+                                 "frac": args.frames * W * H * IMPORT_BYTES_PER_PX / m / 1e6 / peak}
+        line["alpha_mixes"] = alpha_mixes
+        pipe.close()
+        line["other_kernels"] = other_kernels(ctx, peak, args.steps)
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the import kernel
+    from the committed ncu capture (profiles/import_traffic.json), else None."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "import_traffic.json")))["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -34,7 +34,8 @@ struct b2_ctx {
 #define B2_TAB_G2L 0      // 256 entries: kGammaToLinearTab
 #define B2_TAB_L2G 256    // 32 x {base', d} pairs for LinearToGamma
 #define B2_TAB_INVA 320   // 1021 entries: kInvAlpha (binary-compat divide)
-#define B2_TAB_WORDS (320 + 1024)
+#define B2_TAB_MAGIC 1344 // 1021 entries: exact-division magic  M | L << 27
+#define B2_TAB_WORDS (1344 + 1024)
 
 int b2_fail_cuda(b2_ctx* ctx, cudaError_t e, const char* what);
 

@@ -61,6 +61,15 @@ static void build_tables(uint32_t* tab) {
     tab[B2_TAB_L2G + 2 * pos + 1] = (uint32_t)d;
   }
   for (int a = 1; a <= 4 * 255; ++a) tab[B2_TAB_INVA + a] = (1u << 19) / (uint32_t)a;
+  // Exact n / a for n < 2^24 (Granlund-Montgomery): L = ceil(log2 a),
+  // M = floor(2^(24+L) / a) + 1  =>  n / a == umulhi(n << 8, M) >> L.
+  // (n = 4 * sum of alpha-weighted linear values <= 4 * 1020 * 4095 < 2^24.)
+  for (uint32_t a = 1; a <= 4 * 255; ++a) {
+    uint32_t L = 0;
+    while ((1u << L) < a) ++L;
+    const uint64_t M = ((uint64_t)1 << (24 + L)) / a + 1;
+    tab[B2_TAB_MAGIC + a] = (uint32_t)M | (L << 27);
+  }
 }
 
 extern "C" int b2_ctx_create(int device, int n_streams, b2_ctx** out) {

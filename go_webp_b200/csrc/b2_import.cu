@@ -18,21 +18,9 @@
 // The two gamma tables live in shared memory replicated per lane (bank ==
 // lane), which makes every data-dependent lookup conflict-free.
 #include "b2_common.cuh"
+#include "b2_import.cuh"
 
 namespace {
-
-struct ImportJobDev {
-  const uint8_t* src;
-  uint8_t* y;
-  uint8_t* u;
-  uint8_t* v;
-  uint8_t* a;
-  int32_t src_stride, y_stride, uv_stride, a_stride;
-  int32_t width, height;
-  uint32_t tiles_x;
-  uint32_t flags;
-};
-enum { JOB_Y_ALIGNED = 1, JOB_A_ALIGNED = 2, JOB_UV_ALIGNED = 4 };
 
 constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
@@ -319,15 +307,18 @@ extern "C" int b2_rgba_to_yuv420a(b2_ctx* ctx, int stream, const b2_import_job* 
   if (alpha && step != 4) return B2_ERR_INVALID_CONFIG;  // conversions.go:70 assert(step == 4)
 
   const size_t jb = sizeof(ImportJobDev) * (size_t)n_jobs;
-  const size_t pb = sizeof(uint32_t) * ((size_t)n_jobs + 1);
-  if (jb + pb + 64 > B2_DESC_RING_BYTES) return B2_ERR_INVALID_CONFIG;
-  uint8_t* host = (uint8_t*)malloc(jb + pb + 64);
+  const size_t pb = (sizeof(uint32_t) * ((size_t)n_jobs + 1) + 15) & ~(size_t)15;
+  if (jb + 2 * pb + 64 > B2_DESC_RING_BYTES) return B2_ERR_INVALID_CONFIG;
+  uint8_t* host = (uint8_t*)malloc(jb + 2 * pb + 64);
   if (host == NULL) return B2_ERR_OOM;
   ImportJobDev* dj = (ImportJobDev*)host;
   uint32_t* pre = (uint32_t*)(host + ((jb + 15) & ~(size_t)15));
+  uint32_t* upre = (uint32_t*)((uint8_t*)pre + pb);  // prefix in row pairs (fast kernel)
   bool fast = (step == 4);
-  uint64_t total = 0;
-  uint32_t uniform = 0;
+  bool tuned = (step == 4);   // b2_import_fast.cu preconditions
+  int n_with_a = 0;
+  uint64_t total = 0, utotal = 0;
+  uint32_t uniform = 0, uuniform = 0;
   for (int i = 0; i < n_jobs; ++i) {
     const b2_import_job& j = jobs[i];
     if (j.src == NULL || j.y == NULL || j.u == NULL || j.v == NULL) { free(host); return B2_ERR_NULL; }
@@ -348,20 +339,30 @@ extern "C" int b2_rgba_to_yuv420a(b2_ctx* ctx, int stream, const b2_import_job* 
     if (j.a && (((uintptr_t)j.a | (uintptr_t)(uint32_t)j.a_stride) & 3) == 0) d.flags |= JOB_A_ALIGNED;
     if ((((uintptr_t)j.u | (uintptr_t)j.v | (uintptr_t)(uint32_t)j.uv_stride) & 1) == 0) d.flags |= JOB_UV_ALIGNED;
     if ((((uintptr_t)j.src | (uintptr_t)(uint32_t)j.src_stride) & 3) != 0) fast = false;
-    const uint32_t items = d.tiles_x * (uint32_t)((j.height + 1) >> 1);
+    if ((((uintptr_t)j.src | (uintptr_t)(uint32_t)j.src_stride) & 15) != 0 || (j.width & 3) != 0 ||
+        !(d.flags & JOB_Y_ALIGNED) || !(d.flags & JOB_UV_ALIGNED) || (j.a && !(d.flags & JOB_A_ALIGNED))) tuned = false;
+    n_with_a += (j.a != NULL);
+    const uint32_t units = (uint32_t)((j.height + 1) >> 1);
+    const uint32_t items = d.tiles_x * units;
     if (i == 0) uniform = items; else if (items != uniform) uniform = 0;
+    if (i == 0) uuniform = units; else if (units != uuniform) uuniform = 0;
     pre[i] = (uint32_t)total;
+    upre[i] = (uint32_t)utotal;
     total += items;
+    utotal += units;
     if (total > 0x7fffffffull) { free(host); return B2_ERR_BAD_DIM; }
   }
   pre[n_jobs] = (uint32_t)total;
+  upre[n_jobs] = (uint32_t)utotal;
+  if (n_with_a != 0 && n_with_a != n_jobs) tuned = false;  // WRITE_A is a kernel-wide switch
   void* dev = NULL;
   const size_t pre_off = (size_t)((uint8_t*)pre - host);
-  int st = b2_upload_desc(ctx, stream, host, pre_off + pb, &dev);
+  int st = b2_upload_desc(ctx, stream, host, pre_off + 2 * pb, &dev);
   free(host);
   if (st != B2_OK) return st;
   const ImportJobDev* djobs = (const ImportJobDev*)dev;
   const uint32_t* dpre = (const uint32_t*)((uint8_t*)dev + pre_off);
+  const uint32_t* dupre = (const uint32_t*)((uint8_t*)dev + pre_off + pb);
   cudaStream_t s = ctx->streams[stream];
   if (alpha && has_alpha_dev != NULL) {
     B2_CUDA(ctx, cudaMemsetAsync(has_alpha_dev, 0, sizeof(int32_t) * (size_t)n_jobs, s));
@@ -371,7 +372,10 @@ extern "C" int b2_rgba_to_yuv420a(b2_ctx* ctx, int stream, const b2_import_job* 
   const int grid = b2_grid_for(ctx, 2, (total + kWarps - 1) / kWarps);
   const int divt = (flags & B2_IMPORT_DIV_TABLE) ? 1 : 0;
   const uint32_t tot = (uint32_t)total;
-  if (fast) {
+  if (tuned) {
+    B2_CUDA(ctx, b2_import_fast_launch(ctx, s, djobs, dupre, (uint32_t)n_jobs, uuniform, (uint32_t)utotal,
+                                       order, alpha, n_with_a != 0, divt, has_alpha_dev));
+  } else if (fast) {
     if (order == B2_ORDER_RGBA) {
       if (alpha) import_kernel<0, true><<<grid, kThreads, 0, s>>>(djobs, dpre, n_jobs, uniform, tot, ctx->tab_dev, divt, has_alpha_dev);
       else import_kernel<0, false><<<grid, kThreads, 0, s>>>(djobs, dpre, n_jobs, uniform, tot, ctx->tab_dev, divt, has_alpha_dev);

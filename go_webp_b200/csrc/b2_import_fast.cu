@@ -1,0 +1,250 @@
+// b2_import_fast.cu -- tuned RGBA -> YUV420(+A) import for the common case: 4-byte
+// pixels, width % 4 == 0, 16-byte aligned source rows, aligned planes.
+//
+// Same arithmetic as b2_import.cu (pkg/libwebp/dsp/yuv.go:124-382,
+// pkg/color/yuv/conversion.go:51-69); what changes is the instruction budget.  The
+// first version spent ~410 warp instructions per 4x2-pixel strip and was issue
+// bound at 48% of HBM peak (profiles/r01_*).  Here:
+//   * a warp walks one whole row pair (the reference's own unit of work,
+//     yuv.go:316), so image lookup, descriptor loads and 64-bit address math are
+//     paid once per row pair, and the next strip is prefetched while the current
+//     one is computed;
+//   * luma is two dp2a per pixel (16-bit coefficients x 8-bit channels);
+//   * the gamma tables sit in shared memory with a 256-byte row per entry and one
+//     word per lane, so a lookup address is ONE byte-permute, (value << 8) | lane*4,
+//     and every lookup is bank-conflict free.  Linear values are stored << 7 so the
+//     interpolation index of LinearToGamma is a whole byte of the sum;
+//   * U and V are scaled by 64 so the result is the top byte of the accumulator;
+//   * the translucent-block division 4*sum/a (yuv.go:231) is an exact
+//     multiply-high by a per-divisor magic number (verified for every divisor in
+//     tests/test_oracle_properties.py) instead of a hardware integer division.
+#include "b2_import.cuh"
+
+namespace {
+
+constexpr int kFastThreads = 512;
+constexpr int kFastWarps = kFastThreads / 32;
+constexpr int kFastCtasPerSm = 2;
+constexpr int kSmemBytes = 256 * 256;  // 64 KB
+
+// shared-memory map (byte offsets); row r = bytes [256 r, 256 r + 256)
+//   lower half of every row : g2l[r] << 7, one word per lane
+//   upper half, rows   0.. 31: LinearToGamma base'' per lane
+//   upper half, rows  32.. 63: LinearToGamma slope d per lane
+//   upper half, rows  64.. 95: exact-division magic numbers, entry a at word a
+//   upper half, rows  96..127: kInvAlpha (binary-compatible divide mode)
+constexpr uint32_t kOffL2GD = 32 * 256;
+constexpr uint32_t kOffMagic = 64 * 256 + 128;
+constexpr uint32_t kOffInvA = 96 * 256 + 128;
+
+template <int ORDER> struct Ch;
+template <> struct Ch<0> {  // R,G,B,A bytes
+  static constexpr uint32_t kLoPair = 16839u | (33059u << 16);  // bytes 0,1
+  static constexpr uint32_t kHiPair = 6420u;                    // bytes 2,3
+  static constexpr int kR = 0, kB = 2;
+};
+template <> struct Ch<1> {  // B,G,R,A bytes
+  static constexpr uint32_t kLoPair = 6420u | (33059u << 16);
+  static constexpr uint32_t kHiPair = 16839u;
+  static constexpr int kR = 2, kB = 0;
+};
+
+__device__ __forceinline__ uint32_t lds32(const uint8_t* smem, uint32_t off) {
+  return *reinterpret_cast<const uint32_t*>(smem + off);
+}
+// RGBToY (conversion.go:56-59) as two 16x8-bit dot products; Y = byte 2 of the sum
+template <int ORDER>
+__device__ __forceinline__ uint32_t luma_sum(uint32_t p) {
+  return __dp2a_hi(Ch<ORDER>::kHiPair, p, __dp2a_lo(Ch<ORDER>::kLoPair, p, (1u << 15) + (16u << 16)));
+}
+__device__ __forceinline__ uint32_t pack_b2(uint32_t s0, uint32_t s1, uint32_t s2, uint32_t s3) {
+  return __byte_perm(__byte_perm(s0, s1, 0x0062), __byte_perm(s2, s3, 0x0062), 0x5410);
+}
+__device__ __forceinline__ uint32_t pack_b3(uint32_t s0, uint32_t s1, uint32_t s2, uint32_t s3) {
+  return __byte_perm(__byte_perm(s0, s1, 0x0073), __byte_perm(s2, s3, 0x0073), 0x5410);
+}
+// g2l[channel K of p] << 7 for this lane: address = (byte << 8) | lane*4
+template <int K>
+__device__ __forceinline__ uint32_t g2l(const uint8_t* smem, uint32_t p, uint32_t lane4) {
+  return lds32(smem, __byte_perm(p, lane4, 0x5504 | (K << 4)));
+}
+// LinearToGamma (yuv.go:187-202) on a sum held << 7: index = byte 2 of the sum.
+// Returns the 10-bit gamma-domain value.
+__device__ __forceinline__ int l2g(const uint8_t* smem, uint32_t s7, uint32_t lane4hi) {
+  const uint32_t off = __byte_perm(s7, lane4hi, 0x5524);
+  const int base = (int)lds32(smem, off);
+  const int d = (int)lds32(smem, off + kOffL2GD);
+  return (base + d * (int)s7) >> 14;
+}
+// RGBToU / RGBToV on gamma-domain sums (conversion.go:51-69, rounding YUV_HALF<<2),
+// scaled by 64: the result is byte 3.  Inputs are <= 1020 so ClipUV never clamps.
+__device__ __forceinline__ uint32_t u_sum(int r, int g, int b) {
+  constexpr uint32_t kRnd = ((1u << 17) + (128u << 18)) << 6;
+  return (uint32_t)(-9719 * 64) * (uint32_t)r + (uint32_t)(-19081 * 64) * (uint32_t)g +
+         (uint32_t)(28800 * 64) * (uint32_t)b + kRnd;
+}
+__device__ __forceinline__ uint32_t v_sum(int r, int g, int b) {
+  constexpr uint32_t kRnd = ((1u << 17) + (128u << 18)) << 6;
+  return (uint32_t)(28800 * 64) * (uint32_t)r + (uint32_t)(-24116 * 64) * (uint32_t)g +
+         (uint32_t)(-4684 * 64) * (uint32_t)b + kRnd;
+}
+
+// DIVIDE_BY_ALPHA (yuv.go:231) on w7 = (sum of alpha_i * linear_i) << 7; returns the
+// quotient << 7 ready for l2g().
+__device__ __forceinline__ uint32_t div_alpha7(const uint8_t* smem, uint32_t w7, uint32_t magic,
+                                               uint32_t inva, bool table) {
+  if (table) return (((w7 >> 7) * inva) >> 17) << 7;      // libwebp-binary kInvAlpha form
+  const uint32_t q = __umulhi(w7 << 3, magic & 0x07ffffffu) >> (magic >> 27);  // exact 4*sum/a
+  return q << 7;
+}
+
+// Linear sums (<< 7) of one 2x2 block for the three channels.
+template <int ORDER, bool ALPHA>
+__device__ __forceinline__ void block_sums(const uint8_t* smem, uint32_t lane4, uint32_t pa, uint32_t pb,
+                                           uint32_t pc, uint32_t pd, uint32_t al4, bool table,
+                                           uint32_t* sr, uint32_t* sg, uint32_t* sb) {
+  const uint32_t ra = g2l<Ch<ORDER>::kR>(smem, pa, lane4), rb = g2l<Ch<ORDER>::kR>(smem, pb, lane4);
+  const uint32_t rc = g2l<Ch<ORDER>::kR>(smem, pc, lane4), rd = g2l<Ch<ORDER>::kR>(smem, pd, lane4);
+  const uint32_t ga = g2l<1>(smem, pa, lane4), gb = g2l<1>(smem, pb, lane4);
+  const uint32_t gc = g2l<1>(smem, pc, lane4), gd = g2l<1>(smem, pd, lane4);
+  const uint32_t ba = g2l<Ch<ORDER>::kB>(smem, pa, lane4), bb = g2l<Ch<ORDER>::kB>(smem, pb, lane4);
+  const uint32_t bc = g2l<Ch<ORDER>::kB>(smem, pc, lane4), bd = g2l<Ch<ORDER>::kB>(smem, pd, lane4);
+  if (!ALPHA || al4 == 0xffffffffu || al4 == 0u) {  // yuv.go:249 / :270
+    *sr = ra + rb + rc + rd;
+    *sg = ga + gb + gc + gd;
+    *sb = ba + bb + bc + bd;
+  } else {                                           // yuv.go:233-241,254-256
+    const uint32_t a0 = al4 & 0xff, a1 = (al4 >> 8) & 0xff, a2 = (al4 >> 16) & 0xff, a3 = al4 >> 24;
+    const uint32_t asum = __dp4a(al4, 0x01010101u, 0u);
+    const uint32_t toff = ((asum >> 5) << 8) | ((asum & 31u) << 2);
+    const uint32_t magic = lds32(smem, toff + kOffMagic);
+    const uint32_t inva = lds32(smem, toff + kOffInvA);
+    *sr = div_alpha7(smem, a0 * ra + a1 * rb + a2 * rc + a3 * rd, magic, inva, table);
+    *sg = div_alpha7(smem, a0 * ga + a1 * gb + a2 * gc + a3 * gd, magic, inva, table);
+    *sb = div_alpha7(smem, a0 * ba + a1 * bb + a2 * bc + a3 * bd, magic, inva, table);
+  }
+}
+
+template <int ORDER, bool ALPHA, bool WRITE_A>
+__global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm)
+import_fast_kernel(const ImportJobDev* __restrict__ jobs, const uint32_t* __restrict__ unit_prefix,
+                   uint32_t n_jobs, uint32_t uniform_units, uint32_t total_units,
+                   const uint32_t* __restrict__ tab, int div_table, int32_t* __restrict__ has_alpha) {
+  extern __shared__ __align__(256) uint8_t smem[];
+  for (int i = threadIdx.x; i < 256 * 32; i += kFastThreads) {
+    *reinterpret_cast<uint32_t*>(smem + (i >> 5) * 256 + (i & 31) * 4) = __ldg(tab + B2_TAB_G2L + (i >> 5)) << 7;
+  }
+  for (int i = threadIdx.x; i < 32 * 32; i += kFastThreads) {
+    const int pos = i >> 5;
+    const int base = (int)__ldg(tab + B2_TAB_L2G + 2 * pos) * 128;  // base' << 7
+    const int d = (int)__ldg(tab + B2_TAB_L2G + 2 * pos + 1);
+    *reinterpret_cast<int*>(smem + pos * 256 + 128 + (i & 31) * 4) = base;
+    *reinterpret_cast<int*>(smem + kOffL2GD + pos * 256 + 128 + (i & 31) * 4) = d;
+  }
+  for (int i = threadIdx.x; i < 1024; i += kFastThreads) {
+    const uint32_t off = ((i >> 5) << 8) | ((i & 31) << 2);
+    *reinterpret_cast<uint32_t*>(smem + off + kOffMagic) = __ldg(tab + B2_TAB_MAGIC + i);
+    *reinterpret_cast<uint32_t*>(smem + off + kOffInvA) = __ldg(tab + B2_TAB_INVA + i);
+  }
+  __syncthreads();
+
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t lane4 = lane * 4;
+  const uint32_t lane4hi = lane4 + 128;
+  const uint32_t warp = threadIdx.x >> 5;
+  const bool table = div_table != 0;
+
+  for (uint32_t unit = blockIdx.x * kFastWarps + warp; unit < total_units; unit += gridDim.x * kFastWarps) {
+    uint32_t rp;
+    const uint32_t img = b2_find_image(unit_prefix, n_jobs, uniform_units, unit, &rp);
+    const ImportJobDev* __restrict__ jp = jobs + img;
+    const int width = jp->width;
+    const int y0 = 2 * (int)rp;
+    const bool has_row1 = (y0 + 1 < jp->height);
+    const int sstride = jp->src_stride;
+    const int ystride = jp->y_stride;
+    const uint8_t* s0 = jp->src + (ptrdiff_t)y0 * sstride + lane * 16;
+    const uint8_t* s1 = has_row1 ? s0 + sstride : s0;  // odd last row duplicated (yuv.go:377)
+    uint8_t* yp = jp->y + (ptrdiff_t)y0 * ystride + lane4;
+    uint8_t* ap = nullptr;
+    int astride = 0;
+    if (WRITE_A) { astride = jp->a_stride; ap = jp->a + (ptrdiff_t)y0 * astride + lane4; }
+    const ptrdiff_t uvo = (ptrdiff_t)rp * jp->uv_stride + lane * 2;
+    uint8_t* up = jp->u + uvo;
+    uint8_t* vp = jp->v + uvo;
+    uint32_t and_acc = 0xffffffffu;
+
+    int x = (int)lane4;
+    uint4 c0, c1;
+    bool cur_ok = x < width;
+    if (cur_ok) { c0 = b2_ldg_stream_v4(s0); c1 = b2_ldg_stream_v4(s1); }
+    const int tiles_x = (width + 127) >> 7;
+    for (int t = 0; t < tiles_x; ++t) {
+      const int xn = x + 128;
+      const bool nxt_ok = xn < width;
+      uint4 n0, n1;
+      if (nxt_ok) { n0 = b2_ldg_stream_v4(s0 + 512); n1 = b2_ldg_stream_v4(s1 + 512); }
+      if (cur_ok) {
+        const uint32_t yw0 = pack_b2(luma_sum<ORDER>(c0.x), luma_sum<ORDER>(c0.y), luma_sum<ORDER>(c0.z), luma_sum<ORDER>(c0.w));
+        const uint32_t yw1 = pack_b2(luma_sum<ORDER>(c1.x), luma_sum<ORDER>(c1.y), luma_sum<ORDER>(c1.z), luma_sum<ORDER>(c1.w));
+        uint32_t ap0 = 0xffffffffu, ap1 = 0xffffffffu;
+        if (ALPHA) {
+          ap0 = pack_b3(c0.x, c0.y, c0.z, c0.w);
+          ap1 = pack_b3(c1.x, c1.y, c1.z, c1.w);
+          and_acc &= ap0 & ap1;
+        }
+        uint32_t sr0, sg0, sb0, sr1, sg1, sb1;
+        block_sums<ORDER, ALPHA>(smem, lane4, c0.x, c0.y, c1.x, c1.y, __byte_perm(ap0, ap1, 0x5410), table, &sr0, &sg0, &sb0);
+        block_sums<ORDER, ALPHA>(smem, lane4, c0.z, c0.w, c1.z, c1.w, __byte_perm(ap0, ap1, 0x7632), table, &sr1, &sg1, &sb1);
+        const int r0 = l2g(smem, sr0, lane4hi), g0 = l2g(smem, sg0, lane4hi), b0 = l2g(smem, sb0, lane4hi);
+        const int r1 = l2g(smem, sr1, lane4hi), g1 = l2g(smem, sg1, lane4hi), b1 = l2g(smem, sb1, lane4hi);
+        const uint32_t uu = __byte_perm(u_sum(r0, g0, b0), u_sum(r1, g1, b1), 0x0073);
+        const uint32_t vv = __byte_perm(v_sum(r0, g0, b0), v_sum(r1, g1, b1), 0x0073);
+        b2_stg_stream_u32(yp, yw0);
+        if (has_row1) b2_stg_stream_u32(yp + ystride, yw1);
+        if (WRITE_A) {
+          b2_stg_stream_u32(ap, ap0);
+          if (has_row1) b2_stg_stream_u32(ap + astride, ap1);
+        }
+        b2_stg_stream_u16(up, uu);
+        b2_stg_stream_u16(vp, vv);
+      }
+      s0 += 512; s1 += 512; yp += 128; up += 64; vp += 64;
+      if (WRITE_A) ap += 128;
+      c0 = n0; c1 = n1; cur_ok = nxt_ok; x = xn;
+    }
+    if (ALPHA && has_alpha != nullptr) {
+      if (__any_sync(0xffffffffu, and_acc != 0xffffffffu) && lane == 0) atomicOr(has_alpha + img, 1);
+    }
+  }
+}
+
+template <int ORDER, bool ALPHA, bool WRITE_A>
+cudaError_t launch(int grid, cudaStream_t s, const ImportJobDev* jobs, const uint32_t* unit_prefix,
+                   uint32_t n_jobs, uint32_t uniform_units, uint32_t total_units, const uint32_t* tab,
+                   int div_table, int32_t* has_alpha) {
+  auto k = import_fast_kernel<ORDER, ALPHA, WRITE_A>;
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  if (e != cudaSuccess) return e;
+  k<<<grid, kFastThreads, kSmemBytes, s>>>(jobs, unit_prefix, n_jobs, uniform_units, total_units, tab,
+                                            div_table, has_alpha);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t b2_import_fast_launch(const b2_ctx* ctx, cudaStream_t s, const ImportJobDev* jobs,
+                                  const uint32_t* unit_prefix, uint32_t n_jobs,
+                                  uint32_t uniform_units, uint32_t total_units, int order,
+                                  bool alpha, bool write_a, int div_table, int32_t* has_alpha) {
+  const int grid = b2_grid_for(ctx, kFastCtasPerSm, (total_units + kFastWarps - 1) / kFastWarps);
+#define B2_GO(O, A, W) return launch<O, A, W>(grid, s, jobs, unit_prefix, n_jobs, uniform_units, total_units, ctx->tab_dev, div_table, has_alpha)
+  if (order == B2_ORDER_RGBA) {
+    if (alpha) { if (write_a) B2_GO(0, true, true); else B2_GO(0, true, false); }
+    else       { if (write_a) B2_GO(0, false, true); else B2_GO(0, false, false); }
+  } else {
+    if (alpha) { if (write_a) B2_GO(1, true, true); else B2_GO(1, true, false); }
+    else       { if (write_a) B2_GO(1, false, true); else B2_GO(1, false, false); }
+  }
+#undef B2_GO
+}

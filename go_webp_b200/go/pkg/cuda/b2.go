@@ -1,0 +1,281 @@
+// Package cuda is the cgo shim between go-webp and libb2webp.so (the B200 pixel
+// path).  It is the only package that imports "C"; pkg/picture and
+// pkg/libwebp/dsp call it through plain Go types.
+//
+// NOTE: written without a Go toolchain at hand (the build image has none and
+// the go-webp tree does not compile); kept gofmt/go vet clean by inspection.
+package cuda
+
+/*
+#cgo CFLAGS: -I${SRCDIR}/../../../../include
+#cgo LDFLAGS: -L${SRCDIR}/../../../lib -lb2webp -Wl,-rpath,${SRCDIR}/../../../lib
+#include <stdlib.h>
+#include "b2webp.h"
+*/
+import "C"
+
+import (
+	"errors"
+	"fmt"
+	"runtime"
+	"unsafe"
+)
+
+// Sentinels mirror pkg/picture/errors.go:8-21; pkg/picture maps them onto its
+// own variables so existing errors.Is checks keep working.
+var (
+	ErrOutOfMemory   = errors.New("memory error allocating objects")
+	ErrBadDimension  = errors.New("picture has invalid width/height")
+	ErrNilParameter  = errors.New("a pointer parameter is nil")
+	ErrInvalidConfig = errors.New("configuration is invalid")
+)
+
+// Pixel orders and flags (include/b2webp.h).
+const (
+	OrderRGBA = int(C.B2_ORDER_RGBA)
+	OrderBGRA = int(C.B2_ORDER_BGRA)
+	OrderRGB  = int(C.B2_ORDER_RGB)
+	OrderBGR  = int(C.B2_ORDER_BGR)
+
+	ImportAlpha    = int(C.B2_IMPORT_ALPHA)
+	ImportDivTable = int(C.B2_IMPORT_DIV_TABLE)
+)
+
+// Context owns one GPU: streams, descriptor rings, gamma tables.  It is not
+// safe for concurrent use; create one per device and per OS thread.
+type Context struct {
+	h *C.b2_ctx
+}
+
+// DevicePtr is an address in device memory returned by Alloc.
+type DevicePtr uintptr
+
+func status(ctx *Context, st C.int) error {
+	switch st {
+	case C.B2_OK:
+		return nil
+	case C.B2_ERR_OOM:
+		return ErrOutOfMemory
+	case C.B2_ERR_BAD_DIM:
+		return ErrBadDimension
+	case C.B2_ERR_NULL:
+		return ErrNilParameter
+	case C.B2_ERR_INVALID_CONFIG:
+		return ErrInvalidConfig
+	default:
+		msg := "cuda error"
+		if ctx != nil && ctx.h != nil {
+			msg = C.GoString(C.b2_last_error(ctx.h))
+		}
+		return fmt.Errorf("%w: %s", ErrOutOfMemory, msg)
+	}
+}
+
+// DeviceCount reports the number of CUDA devices (0 when there is no driver).
+func DeviceCount() int {
+	var n C.int
+	if C.b2_device_count(&n) != C.B2_OK {
+		return 0
+	}
+	return int(n)
+}
+
+// NewContext binds a context to one device with the given number of streams.
+func NewContext(device, streams int) (*Context, error) {
+	var h *C.b2_ctx
+	if st := C.b2_ctx_create(C.int(device), C.int(streams), &h); st != C.B2_OK {
+		return nil, status(nil, st)
+	}
+	c := &Context{h: h}
+	runtime.SetFinalizer(c, (*Context).Close)
+	return c, nil
+}
+
+// Close releases every stream, event and buffer the context owns.
+func (c *Context) Close() {
+	if c.h != nil {
+		C.b2_ctx_destroy(c.h)
+		c.h = nil
+	}
+}
+
+// Pinned returns page-locked host memory as a Go slice for zero-copy staging.
+// The slice is owned by the library: release it with FreePinned.
+func (c *Context) Pinned(n int) ([]byte, error) {
+	var p unsafe.Pointer
+	if st := C.b2_pinned_alloc(c.h, C.size_t(n), &p); st != C.B2_OK {
+		return nil, status(c, st)
+	}
+	return unsafe.Slice((*byte)(p), n), nil
+}
+
+// FreePinned releases a slice obtained from Pinned.
+func (c *Context) FreePinned(b []byte) error {
+	if len(b) == 0 {
+		return nil
+	}
+	return status(c, C.b2_pinned_free(c.h, unsafe.Pointer(&b[0])))
+}
+
+// Alloc reserves device memory.
+func (c *Context) Alloc(n int) (DevicePtr, error) {
+	var p unsafe.Pointer
+	if st := C.b2_dev_alloc(c.h, C.size_t(n), &p); st != C.B2_OK {
+		return 0, status(c, st)
+	}
+	return DevicePtr(uintptr(p)), nil
+}
+
+// Free releases device memory.
+func (c *Context) Free(p DevicePtr) error {
+	return status(c, C.b2_dev_free(c.h, unsafe.Pointer(uintptr(p))))
+}
+
+// H2D enqueues a host-to-device copy; src must stay alive until Sync (use
+// pinned memory for true asynchrony).
+func (c *Context) H2D(stream int, dst DevicePtr, src []byte) error {
+	if len(src) == 0 {
+		return nil
+	}
+	return status(c, C.b2_h2d_async(c.h, C.int(stream), unsafe.Pointer(uintptr(dst)),
+		unsafe.Pointer(&src[0]), C.size_t(len(src))))
+}
+
+// D2H enqueues a device-to-host copy.
+func (c *Context) D2H(stream int, dst []byte, src DevicePtr) error {
+	if len(dst) == 0 {
+		return nil
+	}
+	return status(c, C.b2_d2h_async(c.h, C.int(stream), unsafe.Pointer(&dst[0]),
+		unsafe.Pointer(uintptr(src)), C.size_t(len(dst))))
+}
+
+// Sync waits for one stream, or for all when stream < 0.
+func (c *Context) Sync(stream int) error {
+	return status(c, C.b2_sync(c.h, C.int(stream)))
+}
+
+// ImportJob is one image of a batched RGBA->YUV420A import (device pointers).
+type ImportJob struct {
+	Src                            DevicePtr
+	Y, U, V, A                     DevicePtr
+	SrcStride                      int
+	YStride, UVStride, AStride     int
+	Width, Height                  int
+}
+
+// ImportRGBA replaces dsp.WebPImportYUVAFromRGBA (pkg/libwebp/dsp/yuv.go:304-382)
+// and the has-alpha scan of picture.ImportYUVAFromRGBA (conversions.go:56) for a
+// batch.  hasAlpha addresses int32[len(jobs)] in device memory (or 0).
+func (c *Context) ImportRGBA(stream int, jobs []ImportJob, order, flags int, hasAlpha DevicePtr) error {
+	if len(jobs) == 0 {
+		return nil
+	}
+	cj := make([]C.b2_import_job, len(jobs))
+	for i, j := range jobs {
+		cj[i] = C.b2_import_job{
+			src: (*C.uint8_t)(unsafe.Pointer(uintptr(j.Src))),
+			y:   (*C.uint8_t)(unsafe.Pointer(uintptr(j.Y))),
+			u:   (*C.uint8_t)(unsafe.Pointer(uintptr(j.U))),
+			v:   (*C.uint8_t)(unsafe.Pointer(uintptr(j.V))),
+			a:   (*C.uint8_t)(unsafe.Pointer(uintptr(j.A))),
+			src_stride: C.int32_t(j.SrcStride), y_stride: C.int32_t(j.YStride),
+			uv_stride: C.int32_t(j.UVStride), a_stride: C.int32_t(j.AStride),
+			width: C.int32_t(j.Width), height: C.int32_t(j.Height),
+		}
+	}
+	st := C.b2_rgba_to_yuv420a(c.h, C.int(stream), &cj[0], C.int(len(cj)), C.int(order),
+		C.int(flags), (*C.int32_t)(unsafe.Pointer(uintptr(hasAlpha))))
+	return status(c, st)
+}
+
+// UpsampleJob is one image of a batched fancy upsampling (device pointers).
+type UpsampleJob struct {
+	Y, U, V, A, Dst                          DevicePtr
+	YStride, UVStride, AStride, DstStride    int
+	Width, Height                            int
+}
+
+// UpsampleFancy replaces WebPUpsamplers[mode] driven by WebPPictureYUVAToARGB /
+// EmitFancyRGB (upsampling.c.go:43-114, picture_csp_enc.c.go:62-118,
+// io_dec.c.go:65-115,175-195) for a batch.  mode is a webp.WEBP_CSP_MODE.
+func (c *Context) UpsampleFancy(stream int, jobs []UpsampleJob, mode int) error {
+	if len(jobs) == 0 {
+		return nil
+	}
+	cj := make([]C.b2_upsample_job, len(jobs))
+	for i, j := range jobs {
+		cj[i] = C.b2_upsample_job{
+			y:   (*C.uint8_t)(unsafe.Pointer(uintptr(j.Y))),
+			u:   (*C.uint8_t)(unsafe.Pointer(uintptr(j.U))),
+			v:   (*C.uint8_t)(unsafe.Pointer(uintptr(j.V))),
+			a:   (*C.uint8_t)(unsafe.Pointer(uintptr(j.A))),
+			dst: (*C.uint8_t)(unsafe.Pointer(uintptr(j.Dst))),
+			y_stride: C.int32_t(j.YStride), uv_stride: C.int32_t(j.UVStride),
+			a_stride: C.int32_t(j.AStride), dst_stride: C.int32_t(j.DstStride),
+			width: C.int32_t(j.Width), height: C.int32_t(j.Height),
+		}
+	}
+	return status(c, C.b2_yuv420a_to_rgba_fancy(c.h, C.int(stream), &cj[0], C.int(len(cj)), C.int(mode)))
+}
+
+// ArgbJob is one image of a VP8L per-pixel transform (device pointers).
+type ArgbJob struct {
+	Src, Dst, Data DevicePtr
+	Width, Height  int
+	Bits           int
+}
+
+// VP8LOp selects the transform kernel.
+type VP8LOp int
+
+const (
+	AddGreen VP8LOp = iota
+	SubGreen
+	ColorInverse
+	ColorForward
+	InverseChain
+	ForwardChain
+	ColorIndexInverse
+	BundleColorMap
+)
+
+// VP8L runs one batched VP8L transform (pkg/libwebp/dsp/lossless.go:337-459,
+// lossless_enc.go:207-312).
+func (c *Context) VP8L(stream int, op VP8LOp, jobs []ArgbJob) error {
+	if len(jobs) == 0 {
+		return nil
+	}
+	cj := make([]C.b2_argb_job, len(jobs))
+	for i, j := range jobs {
+		cj[i] = C.b2_argb_job{
+			src:  (*C.uint32_t)(unsafe.Pointer(uintptr(j.Src))),
+			dst:  (*C.uint32_t)(unsafe.Pointer(uintptr(j.Dst))),
+			data: (*C.uint32_t)(unsafe.Pointer(uintptr(j.Data))),
+			width: C.int32_t(j.Width), height: C.int32_t(j.Height), bits: C.int32_t(j.Bits),
+		}
+	}
+	n, s := C.int(len(cj)), C.int(stream)
+	var st C.int
+	switch op {
+	case AddGreen:
+		st = C.b2_vp8l_add_green(c.h, s, &cj[0], n)
+	case SubGreen:
+		st = C.b2_vp8l_sub_green(c.h, s, &cj[0], n)
+	case ColorInverse:
+		st = C.b2_vp8l_color_inverse(c.h, s, &cj[0], n)
+	case ColorForward:
+		st = C.b2_vp8l_color_forward(c.h, s, &cj[0], n)
+	case InverseChain:
+		st = C.b2_vp8l_inverse_chain(c.h, s, &cj[0], n)
+	case ForwardChain:
+		st = C.b2_vp8l_forward_chain(c.h, s, &cj[0], n)
+	case ColorIndexInverse:
+		st = C.b2_vp8l_color_index_inverse(c.h, s, &cj[0], n)
+	case BundleColorMap:
+		st = C.b2_vp8l_bundle_color_map(c.h, s, &cj[0], n)
+	default:
+		return ErrInvalidConfig
+	}
+	return status(c, st)
+}

@@ -1,0 +1,154 @@
+"""BASELINE.json configs at full size on the GPU (device-resident synthetic
+inputs, SURVEY.md 8d generator), checked against the multi-threaded CPU oracle on
+every image where the oracle finishes in seconds, plus size-independent
+properties (inverse o forward == identity, idempotent re-run)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def env():
+    from go_webp_b200 import _abi, device, pipeline
+    if device.device_count() < 1:
+        pytest.fail("no CUDA device")
+    return dict(abi=_abi, pipeline=pipeline, ctx=device.Context(0, 4))
+
+
+def _threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+@pytest.mark.parametrize("alpha_mode", [1, 2, 3])
+def test_config1_256_frames_1080p_import(env, alpha_mode):
+    """configs[1]: 256 x 1920x1080 RGBA -> YUV420A on one GPU, every frame and
+    every plane bit-exact vs the oracle; opaque / 30%-translucent / binary alpha."""
+    ctx, PL = env["ctx"], env["pipeline"]
+    n, w, h = 256, 1920, 1080
+    seed = 0xB2000001
+    p = PL.ImportPipeline(ctx, n, w, h, host=False)
+    p.fill_synthetic(seed, 0, alpha_mode)
+    p.run_device()
+    ctx.sync()
+    L = oracle.lib()
+    uvw, uvh = w // 2, h // 2
+    batch = 32
+    vp = lambda x: x.ctypes.data_as(C.c_void_p)  # noqa: E731
+    for b0 in range(0, n, batch):
+        src = np.stack([oracle.synth_u32(seed, b0 + i, 0, w, h, alpha_mode) for i in range(batch)])
+        y = np.empty((batch, h, w), np.uint8)
+        u = np.empty((batch, uvh, uvw), np.uint8)
+        v = np.empty((batch, uvh, uvw), np.uint8)
+        a = np.empty((batch, h, w), np.uint8)
+        ha = np.zeros(batch, np.int32)
+        assert L.orc_import_batch_mt(vp(src), batch, w, h, vp(y), vp(u), vp(v), vp(a), vp(ha), 0, _threads()) == 0
+        gy = ctx.d2h(p.d_y.ptr + b0 * p.y_img, batch * p.y_img).reshape(batch, p.y_img)[:, :p.ys * h].reshape(batch, h, p.ys)[:, :, :w]
+        gu = ctx.d2h(p.d_u.ptr + b0 * p.uv_img, batch * p.uv_img).reshape(batch, p.uv_img)[:, :p.uvs * uvh].reshape(batch, uvh, p.uvs)[:, :, :uvw]
+        gv = ctx.d2h(p.d_v.ptr + b0 * p.uv_img, batch * p.uv_img).reshape(batch, p.uv_img)[:, :p.uvs * uvh].reshape(batch, uvh, p.uvs)[:, :, :uvw]
+        ga = ctx.d2h(p.d_a.ptr + b0 * p.y_img, batch * p.y_img).reshape(batch, p.y_img)[:, :p.ys * h].reshape(batch, h, p.ys)[:, :, :w]
+        gf = ctx.d2h(p.d_flags.ptr + 4 * b0, 4 * batch).view(np.int32)
+        assert (gy == y).all() and (gu == u).all() and (gv == v).all() and (ga == a).all()
+        assert (gf == ha).all() and (ha == (0 if alpha_mode == 1 else 1)).all()
+    p.close()
+
+
+def test_config2_vp8l_chain_4096(env):
+    """configs[2]: VP8L inverse chain on 4096x4096 ARGB images: cross-colour with
+    32x32-tile multipliers (bits = 5) + add-green, fused and unfused; 8-bit and
+    2-bit colour indexing.  Oracle on 4 of the images, identity property on all."""
+    ctx, PL, abi = env["ctx"], env["pipeline"], env["abi"]
+    n, w, h, bits = 16, 4096, 4096, 5
+    chain = PL.ArgbPipeline(ctx, n, w, h, "inverse_chain", bits)
+    chain.fill_synthetic(0xB2000003)
+    chain.run_device()
+    ctx.sync()
+    for i in (0, 5, 10, 15):
+        src, codes, dst = chain.device_image(i)
+        codes2 = codes.reshape(128, 128)
+        exp = oracle.add_green(oracle.color_space_inverse(src, codes2, bits))
+        assert (dst == exp).all()
+    # unfused = cross-colour^-1 then add-green as two launches, in place on dst
+    jobs_cc = [abi.ArgbJob(j.src, j.dst, j.data, w, h, bits, 0) for j in chain.jobs]
+    first = ctx.d2h(chain.d_dst.ptr, 4 * w * h).copy()
+    ctx.vp8l("color_inverse", jobs_cc)
+    ctx.vp8l("add_green", [abi.ArgbJob(j.dst, j.dst, None, w, h, 0, 0) for j in chain.jobs])
+    ctx.sync()
+    assert (ctx.d2h(chain.d_dst.ptr, 4 * w * h) == first).all()
+    # forward chain on the result restores the source for every image (identity)
+    ctx.vp8l("forward_chain", [abi.ArgbJob(j.dst, j.dst, j.data, w, h, bits, 0) for j in chain.jobs])
+    ctx.sync()
+    for i in range(n):
+        a = ctx.d2h(chain.d_dst.ptr + i * chain.dst_img, 4 * w * h)
+        b = ctx.d2h(chain.d_src.ptr + i * chain.src_img, 4 * w * h)
+        assert (a == b).all()
+    chain.close()
+    for cbits in (0, 2):
+        ci = PL.ArgbPipeline(ctx, 8, w, h, "color_index_inverse", cbits)
+        ci.fill_synthetic(0xB2000003)
+        ci.run_device()
+        ctx.sync()
+        for i in (0, 7):
+            src, pal, dst = ci.device_image(i)
+            assert (dst == oracle.color_index_inverse(src, pal, cbits, w)).all()
+        ci.close()
+
+
+def test_config3_4k_upsample(env):
+    """configs[3] (one rank's share at reduced count): 3840x2160 YUV420 -> RGBA,
+    oracle on 3 frames of 48, re-run idempotence on all."""
+    ctx, PL, abi = env["ctx"], env["pipeline"], env["abi"]
+    n, w, h = 48, 3840, 2160
+    for mode, with_a in ((abi.MODE_RGBA, False), (abi.MODE_BGRA, True)):
+        up = PL.UpsamplePipeline(ctx, n, w, h, mode, with_alpha=with_a, host=False)
+        up.fill_synthetic(0xB2000004)
+        up.run_device()
+        ctx.sync()
+        first = ctx.d2h(up.d_dst.ptr, up.d_img * 4).copy()
+        for i in (0, 23, 47):
+            y, u, v, a, d = up.device_image(i)
+            assert (d == oracle.yuva_to_rgba(y, u, v, a, mode)).all()
+        up.run_device()
+        ctx.sync()
+        assert (ctx.d2h(up.d_dst.ptr, up.d_img * 4) == first).all()
+        up.close()
+
+
+def test_config4_mixed_sizes_full_pipeline(env):
+    """configs[4] (one rank's share): mixed sizes 64..8192 with odd widths and
+    heights through import -> upsample and the ARGB chain, every image vs oracle
+    (the big ones on a row band to keep the CPU side short)."""
+    from go_webp_b200 import dsp, picture
+    rng = np.random.default_rng(0xB2000005)
+    sizes = [(64, 64), (65, 8191), (8191, 65), (8192, 512), (1001, 777), (4095, 33), (300, 301)]
+    pics, srcs = [], []
+    for (w, h) in sizes:
+        src = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+        src[..., 3][rng.random((h, w)) < 0.8] = 255
+        srcs.append(src)
+        pics.append(picture.Picture(Width=w, Height=h))
+    assert picture.ImportRGBABatch(pics, srcs, [4 * w for (w, h) in sizes], "RGBA") == 1
+    outs = picture.YUVAToRGBABatch(pics, env["abi"].MODE_BGRA)
+    for pic, src, out, (w, h) in zip(pics, srcs, outs, sizes):
+        y, u, v, a, ha = oracle.import_yuva(src, w, h, "RGBA")
+        assert (pic.Y == y).all() and (pic.U == u).all() and (pic.V == v).all() and ha
+        assert (pic.A == a).all()
+        assert (out == oracle.yuva_to_rgba(y, u, v, a, oracle.MODE_BGRA)).all()
+    argbs = [o.view(np.uint32).reshape(h, w) for o, (w, h) in zip(outs, sizes)]
+    chains = []
+    for (w, h) in sizes:
+        codes = rng.integers(0, 2**24, (dsp.VP8LSubSampleSize(h, 4), dsp.VP8LSubSampleSize(w, 4)),
+                             dtype=np.uint32) | 0xff000000
+        chains.append([dsp.VP8LTransform(dsp.SUBTRACT_GREEN_TRANSFORM, 0, w, h),
+                       dsp.VP8LTransform(dsp.CROSS_COLOR_TRANSFORM, 4, w, h, codes)])
+    res = dsp.VP8LInverseTransformBatch([dsp.VP8LImage(a, w, h) for a, (w, h) in zip(argbs, sizes)], chains)
+    for r, a, ch in zip(res, argbs, chains):
+        assert (r == oracle.add_green(oracle.color_space_inverse(a, ch[1].data, 4))).all()

@@ -65,6 +65,28 @@ def test_import_size_sweep_batched(gpu, kind):
             check_import(pic, exp, gpu)
 
 
+FAST_SIZES = [(4, 1), (4, 2), (8, 3), (64, 64), (128, 2), (132, 5), (256, 8), (260, 4), (1024, 6),
+              (1920, 8), (124, 7), (388, 2)]
+
+
+@pytest.mark.parametrize("order", ["RGBA", "BGRA", "RGBX", "BGRX"])
+@pytest.mark.parametrize("kind", ALPHA)
+def test_import_tuned_kernel(gpu, order, kind):
+    """Batches whose every image meets the tuned kernel's preconditions (width % 4
+    == 0, 16-byte aligned rows: b2_import_fast.cu), all alpha mixes, both channel
+    orders, with and without imported alpha, exact and table divide."""
+    P = gpu["picture"]
+    rng = np.random.default_rng(ALPHA.index(kind) * 7 + len(order))
+    srcs = [make_rgba(rng, w, h, kind) for (w, h) in FAST_SIZES]
+    for table in (False, True):
+        pics = [P.Picture(Width=w, Height=h) for (w, h) in FAST_SIZES]
+        assert P.ImportRGBABatch(pics, srcs, [4 * w for (w, h) in FAST_SIZES], order, divide_table=table) == 1
+        for pic, src, (w, h) in zip(pics, srcs, FAST_SIZES):
+            exp = oracle.import_yuva(src, w, h, order,
+                                     divide_mode=oracle.DIV_TABLE if table else oracle.DIV_EXACT)
+            check_import(pic, exp, gpu)
+
+
 @pytest.mark.parametrize("order", ["BGRA", "RGBX", "BGRX", "RGB", "BGR"])
 def test_import_orders_strides(gpu, order):
     P = gpu["picture"]

@@ -18,6 +18,8 @@
 // plus eight halo bytes (L1 hits), four 128-bit RGBA stores.  The interpolation
 // is the reference's own 2x16-bit SWAR, here packing two columns (or U and V)
 // per 32-bit register.
+#include <stdlib.h>
+
 #include "b2_common.cuh"
 
 namespace {
@@ -213,6 +215,225 @@ upsample_kernel(const UpsampleJobDev* __restrict__ jobs, const uint32_t* __restr
   }
 }
 
+// MultHi(x, c) (conversion.go:41-43) from x24 = x << 24 is one multiply-high.  The
+// three ">> 6" stay on the integer ALU: ncu shows the ALU and the FMA-heavy
+// (integer multiply) pipes both ~65% busy with that split; moving shifts onto the
+// multiplier (__mulhi by 2^26) or products off it was measured slower
+// (profiles/r01_upsample_pipe_balance.md).
+__device__ __forceinline__ void rgb6(uint32_t y24, uint32_t u24, uint32_t v24, int* r, int* g, int* b) {
+  const int yy = (int)__umulhi(y24, 19077u);
+  *r = (yy + (int)__umulhi(v24, 26149u) - 14234) >> 6;
+  *g = (yy - (int)__umulhi(u24, 6419u) - (int)__umulhi(v24, 13320u) + 8708) >> 6;
+  *b = (yy + (int)__umulhi(u24, 33050u) - 17685) >> 6;
+}
+
+// Converts and stores 8 pixels of one output row.  yw = 8 luma bytes, aw = 8 alpha
+// bytes (HAS_ALPHA), u24/v24 = interpolated chroma << 24 per pixel.
+template <int ST, bool HAS_ALPHA>
+__device__ __forceinline__ void emit_row8(uint2 yw, uint2 aw, const uint32_t (&u24)[8],
+                                          const uint32_t (&v24)[8], uint8_t* dp) {
+  int r[8], g[8], b[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const uint32_t w = (k < 4) ? yw.x : yw.y;
+    rgb6(__byte_perm(w, 0u, 0x0444 | ((k & 3) << 12)), u24[k], v24[k], &r[k], &g[k], &b[k]);
+  }
+  if (ST == ST_RGB || ST == ST_BGR) {
+    // 24 contiguous bytes: [c0 c1 c2 c0'] [c1' c2' c0'' c1''] [c2'' ...] x 2
+    uint32_t o[6];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int* c0 = (ST == ST_RGB) ? r : b;
+      const int* c2 = (ST == ST_RGB) ? b : r;
+      const int i = 4 * h;
+      o[3 * h + 0] = pack4_sat(c0[i], g[i], c2[i], c0[i + 1]);
+      o[3 * h + 1] = pack4_sat(g[i + 1], c2[i + 1], c0[i + 2], g[i + 2]);
+      o[3 * h + 2] = pack4_sat(c2[i + 2], c0[i + 3], g[i + 3], c2[i + 3]);
+    }
+    b2_stg_stream_v2(dp, make_uint2(o[0], o[1]));
+    b2_stg_stream_v2(dp + 8, make_uint2(o[2], o[3]));
+    b2_stg_stream_v2(dp + 16, make_uint2(o[4], o[5]));
+  } else {
+    uint32_t o[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const uint32_t w = (k < 4) ? aw.x : aw.y;
+      const int alpha = HAS_ALPHA ? (int)((w >> (8 * (k & 3))) & 0xff) : 0xff;
+      if (ST == ST_RGBA) o[k] = pack4_sat(r[k], g[k], b[k], alpha);
+      else if (ST == ST_BGRA) o[k] = pack4_sat(b[k], g[k], r[k], alpha);
+      else o[k] = pack4_sat(alpha, r[k], g[k], b[k]);
+    }
+    b2_stg_stream_v4(dp, make_uint4(o[0], o[1], o[2], o[3]));
+    b2_stg_stream_v4(dp + 16, make_uint4(o[4], o[5], o[6], o[7]));
+  }
+}
+
+// ---- cp.async-staged kernel -------------------------------------------------------
+// The row-walking kernel above is bound by exposed load latency (ncu: 50% of stall
+// samples on the first use of loaded data, 0.9 eligible warps per scheduler).  Here
+// every warp owns a 3-stage ring in shared memory and streams its items through it
+// with cp.async (LDGSTS): the copies for item i+2 are in flight while item i is
+// computed, across row-pair boundaries, at no register cost.  One 16-byte copy per
+// lane moves both Y rows, one moves the four chroma rows, eight lanes fetch the
+// halo words; the halo bytes are then ordinary shared-memory loads.
+// Extra preconditions: y/u/v(/a) pointers and strides are multiples of 16 bytes
+// (so 16-byte chunks never leave a row's stride span).
+constexpr int kStages = 3;
+template <bool HAS_ALPHA> struct StageLayout {
+  static constexpr int kY = 0;          // yT[256] yB[256]
+  static constexpr int kC = 512;        // 4 chroma rows x 160 B: [12 pad][left word][128 main][right word][12 pad]
+  static constexpr int kA = 1152;       // aT[256] aB[256]
+  static constexpr int kBytes = HAS_ALPHA ? 1664 : 1152;
+};
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory");
+}
+
+template <int ST, bool HAS_ALPHA>
+__global__ void __launch_bounds__(kThreads, 3)
+upsample_async_kernel(const UpsampleJobDev* __restrict__ jobs, const uint32_t* __restrict__ unit_prefix,
+                      uint32_t n_jobs, uint32_t uniform_units, uint32_t total_units) {
+  using SL = StageLayout<HAS_ALPHA>;
+  __shared__ __align__(16) uint8_t ring[kWarps * kStages * SL::kBytes];
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp = threadIdx.x >> 5;
+  uint8_t* wring = ring + warp * (kStages * SL::kBytes);
+  const uint32_t wring_s = (uint32_t)__cvta_generic_to_shared(wring);
+  const uint32_t first_unit = blockIdx.x * kWarps + warp;
+  const uint32_t unit_stride = gridDim.x * kWarps;
+
+  // ---- loader state (per lane: which 16-byte chunk of which row it copies) ----
+  const int yrow = lane >> 4, yk = lane & 15;          // Y / alpha: row 0 = top, 1 = bottom
+  const int crp = lane >> 3, ck = lane & 7;            // chroma: 0 uT, 1 uC, 2 vT, 3 vC
+  const int hrp = (lane >> 1) & 3, hside = lane & 1;   // halo words (lanes 0..7)
+  const uint32_t y_dst = SL::kY + yrow * 256 + yk * 16;
+  const uint32_t a_dst = SL::kA + yrow * 256 + yk * 16;
+  const uint32_t c_dst = SL::kC + crp * 160 + 16 + ck * 16;
+  const uint32_t h_dst = SL::kC + hrp * 160 + (hside ? 144 : 12);
+  uint32_t l_unit = first_unit;
+  int l_t = 0, l_tiles = 0, l_width = 0, l_uw = 0;
+  const uint8_t* l_y = nullptr; const uint8_t* l_a = nullptr; const uint8_t* l_c = nullptr; const uint8_t* l_h = nullptr;
+  auto loader_setup = [&]() {
+    if (l_unit >= total_units) return;
+    uint32_t q;
+    const uint32_t img = b2_find_image(unit_prefix, n_jobs, uniform_units, l_unit, &q);
+    const UpsampleJobDev* __restrict__ jp = jobs + img;
+    l_width = jp->width;
+    const int height = jp->height;
+    l_uw = (l_width + 1) >> 1;
+    const int uh = (height + 1) >> 1;
+    const int rt = 2 * (int)q - 1, rb = 2 * (int)q;
+    const int ry_t = (rt >= 0) ? rt : rb, ry_b = (rb < height) ? rb : rt;
+    const int ct = max((int)q - 1, 0), cc = min((int)q, uh - 1);
+    l_tiles = (l_width + kItemW - 1) / kItemW;
+    l_t = 0;
+    l_y = jp->y + (ptrdiff_t)(yrow ? ry_b : ry_t) * jp->y_stride + yk * 16;
+    if (HAS_ALPHA) l_a = jp->a + (ptrdiff_t)(yrow ? ry_b : ry_t) * jp->a_stride + yk * 16;
+    l_c = ((crp < 2) ? jp->u : jp->v) + (ptrdiff_t)((crp & 1) ? cc : ct) * jp->uv_stride + ck * 16;
+    l_h = ((hrp < 2) ? jp->u : jp->v) + (ptrdiff_t)((hrp & 1) ? cc : ct) * jp->uv_stride + (hside ? 128 : -4);
+  };
+  auto loader_issue = [&](int stage) {
+    if (l_unit < total_units) {
+      const uint32_t sb = wring_s + stage * SL::kBytes;
+      if (l_t * kItemW + yk * 16 < l_width) {
+        cp_async16(sb + y_dst, l_y);
+        if (HAS_ALPHA) cp_async16(sb + a_dst, l_a);
+      }
+      if (l_t * (kItemW / 2) + ck * 16 < l_uw) cp_async16(sb + c_dst, l_c);
+      if (lane < 8 && (hside ? (l_t * (kItemW / 2) + 128 < l_uw) : (l_t > 0))) cp_async4(sb + h_dst, l_h);
+      l_y += kItemW; l_c += kItemW / 2; l_h += kItemW / 2;
+      if (HAS_ALPHA) l_a += kItemW;
+      if (++l_t == l_tiles) { l_unit += unit_stride; loader_setup(); }
+    }
+    cp_async_commit();
+  };
+
+  // ---- consumer state ----
+  uint32_t c_unit = first_unit;
+  loader_setup();
+  loader_issue(0);
+  loader_issue(1);
+  int stage = 0;
+  while (c_unit < total_units) {
+    uint32_t q;
+    const uint32_t img = b2_find_image(unit_prefix, n_jobs, uniform_units, c_unit, &q);
+    const UpsampleJobDev* __restrict__ jp = jobs + img;
+    const int width = jp->width, height = jp->height;
+    const int uw = (width + 1) >> 1;
+    const int rt = 2 * (int)q - 1, rb = 2 * (int)q;
+    const bool top_ok = (rt >= 0), bot_ok = (rb < height);
+    const int dstride = jp->dst_stride;
+    constexpr int kBpp = (ST == ST_RGB || ST == ST_BGR) ? 3 : 4;
+    uint8_t* dtp = jp->dst + (ptrdiff_t)(top_ok ? rt : rb) * dstride + lane * (8 * kBpp);
+    uint8_t* dbp = jp->dst + (ptrdiff_t)(bot_ok ? rb : rt) * dstride + lane * (8 * kBpp);
+    const int tiles_x = (width + kItemW - 1) / kItemW;
+    int x0 = lane * 8;
+    for (int t = 0; t < tiles_x; ++t, x0 += kItemW) {
+      __syncwarp();  // every lane is done reading the stage about to be refilled
+      loader_issue(stage == 0 ? 2 : stage - 1);   // (stage + 2) % 3
+      cp_async_wait<2>();
+      __syncwarp();  // other lanes' copies of this item are visible
+      const uint8_t* sp = wring + stage * SL::kBytes;
+      if (x0 + 8 <= width) {
+        const int c0 = x0 >> 1;
+        const uint2 yt = *reinterpret_cast<const uint2*>(sp + SL::kY + lane * 8);
+        const uint2 yb = *reinterpret_cast<const uint2*>(sp + SL::kY + 256 + lane * 8);
+        uint2 at = make_uint2(0, 0), ab = make_uint2(0, 0);
+        if (HAS_ALPHA) {
+          at = *reinterpret_cast<const uint2*>(sp + SL::kA + lane * 8);
+          ab = *reinterpret_cast<const uint2*>(sp + SL::kA + 256 + lane * 8);
+        }
+        const uint8_t* cp = sp + SL::kC + 16 + lane * 4;
+        const uint32_t wtu = *reinterpret_cast<const uint32_t*>(cp);
+        const uint32_t wcu = *reinterpret_cast<const uint32_t*>(cp + 160);
+        const uint32_t wtv = *reinterpret_cast<const uint32_t*>(cp + 320);
+        const uint32_t wcv = *reinterpret_cast<const uint32_t*>(cp + 480);
+        uint32_t ltu = cp[-1], lcu = cp[159], ltv = cp[319], lcv = cp[479];
+        uint32_t rtu = cp[4], rcu = cp[164], rtv = cp[324], rcv = cp[484];
+        if (c0 == 0) { ltu = wtu & 0xff; lcu = wcu & 0xff; ltv = wtv & 0xff; lcv = wcv & 0xff; }  // mirrored
+        if (c0 + 4 >= uw) { rtu = wtu >> 24; rcu = wcu >> 24; rtv = wtv >> 24; rcv = wcv >> 24; }
+        const uint32_t etu = wtu & 0x00ff00ffu, otu = (wtu >> 8) & 0x00ff00ffu;
+        const uint32_t ecu = wcu & 0x00ff00ffu, ocu = (wcu >> 8) & 0x00ff00ffu;
+        const uint32_t etv = wtv & 0x00ff00ffu, otv = (wtv >> 8) & 0x00ff00ffu;
+        const uint32_t ecv = wcv & 0x00ff00ffu, ocv = (wcv >> 8) & 0x00ff00ffu;
+        const Quad au = interp(etu, otu, ecu, ocu);
+        const Quad av = interp(etv, otv, ecv, ocv);
+        const Quad bu = interp(otu, __byte_perm(etu, rtu, 0x7432), ocu, __byte_perm(ecu, rcu, 0x7432));
+        const Quad bv = interp(otv, __byte_perm(etv, rtv, 0x7432), ocv, __byte_perm(ecv, rcv, 0x7432));
+        const Quad cq = interp(__byte_perm(ltu, ltv, 0x7410), __byte_perm(etu, etv, 0x7410),
+                               __byte_perm(lcu, lcv, 0x7410), __byte_perm(ecu, ecv, 0x7410));
+        if (top_ok) {
+          const uint32_t u24[8] = {lo24(cq.ts), lo24(au.tf), lo24(au.ts), lo24(bu.tf), lo24(bu.ts), hi24(au.tf), hi24(au.ts), hi24(bu.tf)};
+          const uint32_t v24[8] = {hi24(cq.ts), lo24(av.tf), lo24(av.ts), lo24(bv.tf), lo24(bv.ts), hi24(av.tf), hi24(av.ts), hi24(bv.tf)};
+          emit_row8<ST, HAS_ALPHA>(yt, at, u24, v24, dtp);
+        }
+        if (bot_ok) {
+          const uint32_t u24[8] = {lo24(cq.bs), lo24(au.bf), lo24(au.bs), lo24(bu.bf), lo24(bu.bs), hi24(au.bf), hi24(au.bs), hi24(bu.bf)};
+          const uint32_t v24[8] = {hi24(cq.bs), lo24(av.bf), lo24(av.bs), lo24(bv.bf), lo24(bv.bs), hi24(av.bf), hi24(av.bs), hi24(bv.bf)};
+          emit_row8<ST, HAS_ALPHA>(yb, ab, u24, v24, dbp);
+        }
+      } else if (x0 < width) {  // ragged right edge: per-pixel path straight from global
+        const UpsampleJobDev j = *jp;
+        for (int x = x0; x < width; ++x) {
+          if (top_ok) pixel_generic<ST>(j, rt, x);
+          if (bot_ok) pixel_generic<ST>(j, rb, x);
+        }
+      }
+      dtp += kBpp * kItemW; dbp += kBpp * kItemW;
+      stage = (stage == kStages - 1) ? 0 : stage + 1;
+    }
+    c_unit += unit_stride;
+  }
+  cp_async_wait<0>();
+}
+
 int canonical_store_mode(int mode) {
   switch (mode) {
     case B2_MODE_RGBA: case B2_MODE_rgbA: return ST_RGBA;   // upsampling.c.go:278,280
@@ -240,15 +461,19 @@ extern "C" int b2_yuv420a_to_rgba_fancy(b2_ctx* ctx, int stream, const b2_upsamp
   const int bpp = kBpp[st_mode];
 
   const size_t jb = sizeof(UpsampleJobDev) * (size_t)n_jobs;
-  const size_t pb = sizeof(uint32_t) * ((size_t)n_jobs + 1);
+  const size_t pb = (sizeof(uint32_t) * ((size_t)n_jobs + 1) + 15) & ~(size_t)15;
   const size_t pre_off = (jb + 15) & ~(size_t)15;
-  if (pre_off + pb > B2_DESC_RING_BYTES) return B2_ERR_INVALID_CONFIG;
-  uint8_t* host = (uint8_t*)malloc(pre_off + pb);
+  if (pre_off + 2 * pb > B2_DESC_RING_BYTES) return B2_ERR_INVALID_CONFIG;
+  uint8_t* host = (uint8_t*)malloc(pre_off + 2 * pb);
   if (host == NULL) return B2_ERR_OOM;
   UpsampleJobDev* dj = (UpsampleJobDev*)host;
   uint32_t* pre = (uint32_t*)(host + pre_off);
-  uint64_t total = 0;
-  uint32_t uniform = 0;
+  uint32_t* upre = (uint32_t*)(host + pre_off + pb);  // prefix in row pairs (tuned kernel)
+  uint64_t total = 0, utotal = 0;
+  uint32_t uniform = 0, uuniform = 0;
+  bool tuned = (st_mode <= ST_BGR);  // 4- and 3-byte modes have a staged vector kernel
+  bool staged = true;  // cp.async kernel: 16-byte aligned planes with positive strides
+  int n_with_a = 0;
   for (int i = 0; i < n_jobs; ++i) {
     const b2_upsample_job& j = jobs[i];
     if (j.y == NULL || j.u == NULL || j.v == NULL || j.dst == NULL) { free(host); return B2_ERR_NULL; }
@@ -267,22 +492,53 @@ extern "C" int b2_yuv420a_to_rgba_fancy(b2_ctx* ctx, int stream, const b2_upsamp
                 (((uintptr_t)j.dst | (uintptr_t)(uint32_t)j.dst_stride) & 15) == 0;
     if (j.a != NULL && (((uintptr_t)j.a | (uintptr_t)(uint32_t)j.a_stride) & 7) != 0) fast = false;
     d.flags = fast ? JOB_FAST : 0;
-    const uint32_t items = d.tiles_x * (uint32_t)((j.height >> 1) + 1);
+    if (!fast && bpp == 4) tuned = false;
+    if (bpp == 3 && ((((uintptr_t)j.dst | (uintptr_t)(uint32_t)j.dst_stride) & 7) != 0)) tuned = false;
+    if ((((uintptr_t)j.y | (uintptr_t)j.u | (uintptr_t)j.v | (uintptr_t)j.a | (uintptr_t)(uint32_t)j.y_stride |
+          (uintptr_t)(uint32_t)j.uv_stride | (uintptr_t)(uint32_t)(j.a ? j.a_stride : 0)) & 15) != 0 ||
+        j.y_stride < 0 || j.uv_stride < 0 || (j.a && j.a_stride < 0)) staged = false;
+    n_with_a += (j.a != NULL);
+    const uint32_t units = (uint32_t)((j.height >> 1) + 1);
+    const uint32_t items = d.tiles_x * units;
     if (i == 0) uniform = items; else if (items != uniform) uniform = 0;
+    if (i == 0) uuniform = units; else if (units != uuniform) uuniform = 0;
     pre[i] = (uint32_t)total;
+    upre[i] = (uint32_t)utotal;
     total += items;
+    utotal += units;
     if (total > 0x7fffffffull) { free(host); return B2_ERR_BAD_DIM; }
   }
   pre[n_jobs] = (uint32_t)total;
+  upre[n_jobs] = (uint32_t)utotal;
+  if (n_with_a != 0 && n_with_a != n_jobs && bpp == 4) tuned = false;  // HAS_ALPHA is a kernel-wide switch
   void* dev = NULL;
-  int st = b2_upload_desc(ctx, stream, host, pre_off + pb, &dev);
+  int st = b2_upload_desc(ctx, stream, host, pre_off + 2 * pb, &dev);
   free(host);
   if (st != B2_OK) return st;
   const UpsampleJobDev* djobs = (const UpsampleJobDev*)dev;
   const uint32_t* dpre = (const uint32_t*)((uint8_t*)dev + pre_off);
+  const uint32_t* dupre = (const uint32_t*)((uint8_t*)dev + pre_off + pb);
   cudaStream_t s = ctx->streams[stream];
   const int grid = b2_grid_for(ctx, 8, (total + kWarps - 1) / kWarps);
   const uint32_t tot = (uint32_t)total;
+  if (tuned && staged) {
+    const int ugrid = b2_grid_for(ctx, 3, (utotal + kWarps - 1) / kWarps);
+    const uint32_t ut = (uint32_t)utotal;
+    const bool ha = n_with_a != 0;
+#define B2_UPA(ST_) do { if (ha) upsample_async_kernel<ST_, true><<<ugrid, kThreads, 0, s>>>(djobs, dupre, n_jobs, uuniform, ut); \
+                         else upsample_async_kernel<ST_, false><<<ugrid, kThreads, 0, s>>>(djobs, dupre, n_jobs, uuniform, ut); } while (0)
+    switch (st_mode) {
+      case ST_RGBA: B2_UPA(ST_RGBA); break;
+      case ST_BGRA: B2_UPA(ST_BGRA); break;
+      case ST_ARGB: B2_UPA(ST_ARGB); break;
+      case ST_RGB: upsample_async_kernel<ST_RGB, false><<<ugrid, kThreads, 0, s>>>(djobs, dupre, n_jobs, uuniform, ut); break;
+      default: upsample_async_kernel<ST_BGR, false><<<ugrid, kThreads, 0, s>>>(djobs, dupre, n_jobs, uuniform, ut); break;
+    }
+#undef B2_UPA
+    ctx->launches++;
+    B2_CUDA(ctx, cudaGetLastError());
+    return B2_OK;
+  }
   switch (st_mode) {
     case ST_RGBA: upsample_kernel<ST_RGBA><<<grid, kThreads, 0, s>>>(djobs, dpre, n_jobs, uniform, tot); break;
     case ST_BGRA: upsample_kernel<ST_BGRA><<<grid, kThreads, 0, s>>>(djobs, dpre, n_jobs, uniform, tot); break;

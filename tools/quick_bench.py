@@ -1,0 +1,64 @@
+#!/usr/bin/env python
+"""Device-resident timing of every hot-path kernel (CUDA events, inputs > L2)."""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from go_webp_b200 import _abi  # noqa: E402
+from go_webp_b200.device import Context  # noqa: E402
+from go_webp_b200.pipeline import ArgbPipeline, ImportPipeline, UpsamplePipeline  # noqa: E402
+
+PEAK = 6552.0
+try:
+    PEAK = float(json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    pass
+which = sys.argv[1:] or ["import", "upsample", "vp8l"]
+ctx = Context(0, 1)
+
+
+def timed(run, n=20):
+    for _ in range(3):
+        run()
+    ctx.sync()
+    ctx.event_record(0)
+    for _ in range(n):
+        run()
+    ctx.event_record(1)
+    ctx.sync()
+    return ctx.elapsed_ms(0, 1) / n
+
+
+def report(name, px, bpp, ms):
+    print(f"{name:42s} {px / ms / 1e3:10.0f} Mpx/s  {px * bpp / ms / 1e6:7.0f} GB/s  {px * bpp / ms / 1e6 / PEAK:6.3f} of measured peak")
+
+
+if "import" in which:
+    for name, mode in (("opaque", 1), ("sparse", 2), ("raw", 0)):
+        p = ImportPipeline(ctx, 128, 1920, 1080, host=False)
+        p.fill_synthetic(0xB2000001, 0, mode)
+        report(f"import 128x1080p alpha={name}", 128 * 1920 * 1080, 6.5, timed(p.run_device))
+        p.close()
+    p = ImportPipeline(ctx, 128, 1920, 1080, import_alpha=False, host=False)
+    p.fill_synthetic(0xB2000001, 0, 0)
+    report("import 128x1080p RGBX (A written 0xff)", 128 * 1920 * 1080, 6.5, timed(p.run_device))
+    p.close()
+if "upsample" in which:
+    for mode, wa, bpp in ((_abi.MODE_RGBA, False, 5.5), (_abi.MODE_BGRA, True, 6.5), (_abi.MODE_RGB, False, 4.5)):
+        p = UpsamplePipeline(ctx, 32, 3840, 2160, mode, with_alpha=wa, host=False)
+        p.fill_synthetic(0xB2000004)
+        report(f"upsample 32x4K mode={mode} alpha={wa}", 32 * 3840 * 2160, bpp, timed(p.run_device))
+        p.close()
+    p = UpsamplePipeline(ctx, 128, 1920, 1080, _abi.MODE_RGBA, host=False)
+    p.fill_synthetic(0xB2000004)
+    report("upsample 128x1080p RGBA", 128 * 1920 * 1080, 5.5, timed(p.run_device))
+    p.close()
+if "vp8l" in which:
+    for op, bits, bpp in (("inverse_chain", 5, 8.004), ("forward_chain", 5, 8.004), ("color_inverse", 5, 8.004),
+                          ("add_green", 0, 8.0), ("sub_green", 0, 8.0), ("color_index_inverse", 0, 8.0),
+                          ("color_index_inverse", 1, 6.0), ("color_index_inverse", 2, 5.0), ("color_index_inverse", 3, 4.5)):
+        p = ArgbPipeline(ctx, 8, 4096, 4096, op, bits)
+        p.fill_synthetic(0xB2000003)
+        report(f"vp8l {op} bits={bits} 8x4096^2", 8 * 4096 * 4096, bpp, timed(p.run_device))
+        p.close()

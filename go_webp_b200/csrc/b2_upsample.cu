@@ -21,6 +21,7 @@
 #include <stdlib.h>
 
 #include "b2_common.cuh"
+#include "b2_upsample_core.cuh"
 
 namespace {
 
@@ -268,6 +269,68 @@ __device__ __forceinline__ void emit_row8(uint2 yw, uint2 aw, const uint32_t (&u
   }
 }
 
+// Packed variant (b2_upsample_core.cuh): converts and stores 8 pixels of one output
+// row from four pixel PAIRS, two pixels per 32-bit register all the way to the
+// store.  Pair p holds pixels (1,5), (2,6), (3,7), (0,4) -- the lane layout the
+// interpolation produces.  u2/v2 = interpolated chroma, clean 8-bit lanes.
+template <int ST, bool HAS_ALPHA>
+__device__ __forceinline__ void emit_row8_packed(uint2 yw, uint2 aw, const uint32_t (&u2)[4],
+                                                 const uint32_t (&v2)[4], uint8_t* dp) {
+  const uint32_t ye_x = b2_even(yw.x), yo_x = b2_odd(yw.x), ye_y = b2_even(yw.y), yo_y = b2_odd(yw.y);
+  const uint32_t y2[4] = {b2_prmt(yo_x, yo_y, 0x5410), b2_prmt(ye_x, ye_y, 0x7632),
+                          b2_prmt(yo_x, yo_y, 0x7632), b2_prmt(ye_x, ye_y, 0x5410)};
+  uint32_t ap01 = 0xffffffffu, ap23 = 0xffffffffu;
+  if (HAS_ALPHA) {
+    ap01 = b2_prmt(aw.x, aw.y, 0x6251);  // a1 a5 a2 a6
+    ap23 = b2_prmt(aw.x, aw.y, 0x4073);  // a3 a7 a0 a4
+  }
+  uint32_t o[8];
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const B2Rgb14 c = b2_yuv_pair(b2_luma14(y2[p]), u2[p], v2[p]);
+    const uint32_t r4 = b2_to_byte1(c.r), g4 = b2_to_byte1(c.g), b4 = b2_to_byte1(c.b);
+    const uint32_t ap = (p < 2) ? ap01 : ap23;
+    const bool k0 = (p & 1) == 0;  // alpha bytes (0,1) or (2,3) of ap
+    uint32_t lo, hi;
+    if (ST == ST_RGBA || ST == ST_BGRA) {
+      const uint32_t c0 = (ST == ST_RGBA) ? r4 : b4, c2 = (ST == ST_RGBA) ? b4 : r4;
+      const uint32_t cg = b2_prmt(c0, g4, 0x7351);                  // c0 g c0' g'
+      const uint32_t ca = b2_prmt(c2, ap, k0 ? 0x5341 : 0x7361);    // c2 a c2' a'
+      lo = b2_prmt(cg, ca, 0x5410);
+      hi = b2_prmt(cg, ca, 0x7632);
+    } else if (ST == ST_ARGB) {
+      const uint32_t ar = b2_prmt(r4, ap, k0 ? 0x3514 : 0x3716);    // a r a' r'
+      const uint32_t gb = b2_prmt(g4, b4, 0x7351);                  // g b g' b'
+      lo = b2_prmt(ar, gb, 0x5410);
+      hi = b2_prmt(ar, gb, 0x7632);
+    } else {  // ST_RGB / ST_BGR: three bytes per pixel, byte 3 is dropped below
+      const uint32_t c0 = (ST == ST_RGB) ? r4 : b4, c2 = (ST == ST_RGB) ? b4 : r4;
+      const uint32_t cg = b2_prmt(c0, g4, 0x7351);
+      lo = b2_prmt(cg, c2, 0x5510);
+      hi = b2_prmt(cg, c2, 0x7732);
+    }
+    const int first = (p == 3) ? 0 : p + 1;
+    o[first] = lo;
+    o[first + 4] = hi;
+  }
+  if (ST == ST_RGB || ST == ST_BGR) {
+    uint32_t w[6];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const uint32_t* q = o + 4 * h;
+      w[3 * h + 0] = b2_prmt(q[0], q[1], 0x4210);
+      w[3 * h + 1] = b2_prmt(q[1], q[2], 0x5421);
+      w[3 * h + 2] = b2_prmt(q[2], q[3], 0x6542);
+    }
+    b2_stg_stream_v2(dp, make_uint2(w[0], w[1]));
+    b2_stg_stream_v2(dp + 8, make_uint2(w[2], w[3]));
+    b2_stg_stream_v2(dp + 16, make_uint2(w[4], w[5]));
+  } else {
+    b2_stg_stream_v4(dp, make_uint4(o[0], o[1], o[2], o[3]));
+    b2_stg_stream_v4(dp + 16, make_uint4(o[4], o[5], o[6], o[7]));
+  }
+}
+
 // ---- cp.async-staged kernel -------------------------------------------------------
 // The row-walking kernel above is bound by exposed load latency (ncu: 50% of stall
 // samples on the first use of loaded data, 0.9 eligible warps per scheduler).  Here
@@ -296,7 +359,7 @@ template <int N> __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory");
 }
 
-template <int ST, bool HAS_ALPHA>
+template <int ST, bool HAS_ALPHA, bool PACKED>
 __global__ void __launch_bounds__(kThreads, 3)
 upsample_async_kernel(const UpsampleJobDev* __restrict__ jobs, const uint32_t* __restrict__ unit_prefix,
                       uint32_t n_jobs, uint32_t uniform_units, uint32_t total_units) {
@@ -399,6 +462,30 @@ upsample_async_kernel(const UpsampleJobDev* __restrict__ jobs, const uint32_t* _
         uint32_t rtu = cp[4], rcu = cp[164], rtv = cp[324], rcv = cp[484];
         if (c0 == 0) { ltu = wtu & 0xff; lcu = wcu & 0xff; ltv = wtv & 0xff; lcv = wcv & 0xff; }  // mirrored
         if (c0 + 4 >= uw) { rtu = wtu >> 24; rcu = wcu >> 24; rtv = wtv >> 24; rcv = wcv >> 24; }
+        if (PACKED) {
+          const uint32_t etu = b2_even(wtu), otu = b2_odd(wtu), mtu = b2_prmt(etu, rtu, 0x5432);
+          const uint32_t ecu = b2_even(wcu), ocu = b2_odd(wcu), mcu = b2_prmt(ecu, rcu, 0x5432);
+          const uint32_t etv = b2_even(wtv), otv = b2_odd(wtv), mtv = b2_prmt(etv, rtv, 0x5432);
+          const uint32_t ecv = b2_even(wcv), ocv = b2_odd(wcv), mcv = b2_prmt(ecv, rcv, 0x5432);
+          // column pairs (c0,c0+1),(c0+2,c0+3) -> pixels 1,2 | 5,6 ; (c0+1,c0+2),(c0+3,c0+4) -> 3,4 | 7,(8)
+          const B2Quad16 au = b2_interp16(etu, otu, ecu, ocu), bu = b2_interp16(otu, mtu, ocu, mcu);
+          const B2Quad16 av = b2_interp16(etv, otv, ecv, ocv), bv = b2_interp16(otv, mtv, ocv, mcv);
+          // column pair (left,c0) -> pixel 0, U in the low lane and V in the high lane
+          const B2Quad16 cq = b2_interp16(b2_prmt(ltu, ltv, 0x5410), b2_prmt(etu, etv, 0x5410),
+                                          b2_prmt(lcu, lcv, 0x5410), b2_prmt(ecu, ecv, 0x5410));
+          if (top_ok) {
+            const uint32_t xc = b2_hi8(cq.ts);
+            const uint32_t u2[4] = {b2_hi8(au.tf), b2_hi8(au.ts), b2_hi8(bu.tf), b2_prmt(xc, b2_hi8(bu.ts), 0x5410)};
+            const uint32_t v2[4] = {b2_hi8(av.tf), b2_hi8(av.ts), b2_hi8(bv.tf), b2_prmt(xc, b2_hi8(bv.ts), 0x5432)};
+            emit_row8_packed<ST, HAS_ALPHA>(yt, at, u2, v2, dtp);
+          }
+          if (bot_ok) {
+            const uint32_t xc = b2_hi8(cq.bs);
+            const uint32_t u2[4] = {b2_hi8(au.bf), b2_hi8(au.bs), b2_hi8(bu.bf), b2_prmt(xc, b2_hi8(bu.bs), 0x5410)};
+            const uint32_t v2[4] = {b2_hi8(av.bf), b2_hi8(av.bs), b2_hi8(bv.bf), b2_prmt(xc, b2_hi8(bv.bs), 0x5432)};
+            emit_row8_packed<ST, HAS_ALPHA>(yb, ab, u2, v2, dbp);
+          }
+        } else {
         const uint32_t etu = wtu & 0x00ff00ffu, otu = (wtu >> 8) & 0x00ff00ffu;
         const uint32_t ecu = wcu & 0x00ff00ffu, ocu = (wcu >> 8) & 0x00ff00ffu;
         const uint32_t etv = wtv & 0x00ff00ffu, otv = (wtv >> 8) & 0x00ff00ffu;
@@ -419,6 +506,7 @@ upsample_async_kernel(const UpsampleJobDev* __restrict__ jobs, const uint32_t* _
           const uint32_t v24[8] = {hi24(cq.bs), lo24(av.bf), lo24(av.bs), lo24(bv.bf), lo24(bv.bs), hi24(av.bf), hi24(av.bs), hi24(bv.bf)};
           emit_row8<ST, HAS_ALPHA>(yb, ab, u24, v24, dbp);
         }
+        }  // !PACKED
       } else if (x0 < width) {  // ragged right edge: per-pixel path straight from global
         const UpsampleJobDev j = *jp;
         for (int x = x0; x < width; ++x) {
@@ -432,6 +520,206 @@ upsample_async_kernel(const UpsampleJobDev* __restrict__ jobs, const uint32_t* _
     c_unit += unit_stride;
   }
   cp_async_wait<0>();
+}
+
+// ---- bulk-copy (TMA) staged kernel -------------------------------------------------
+// Same packed arithmetic, cheaper plumbing.  ncu on the cp.async kernel: 535 warp
+// instructions per 256-pixel step, ~85 of them loader bookkeeping executed by every
+// lane, issue slots 73% busy -- the kernel is bound by instruction issue, not by HBM.
+// Here a warp owns a 2-stage ring whose stages hold a 512-pixel x 2-row tile; each
+// input row of a tile is ONE cp.async.bulk issued by one lane (lanes 0..5, or 0..7
+// with an alpha plane) that completes on the stage's mbarrier, so the per-tile
+// bookkeeping is ~25 instructions for 32 pixels per lane.
+// Preconditions (checked on the host): y/u/v(/a) pointers and strides are multiples
+// of 16 bytes, strides positive, so every copy is 16-byte aligned and sized.
+constexpr int kBulkThreads = 128;
+constexpr int kBulkWarps = kBulkThreads / 32;
+constexpr int kBulkCtasPerSm = 6;
+constexpr int kTileW = 512;
+template <bool HAS_ALPHA> struct BulkLayout {
+  static constexpr int kY = 0;               // yT[512] yB[512]
+  static constexpr int kC = 1024;            // uT uC vT vC, each [16 halo][256][16 halo]
+  static constexpr int kCRow = 288;
+  static constexpr int kA = kC + 4 * kCRow;  // aT[512] aB[512]
+  static constexpr int kBytes = HAS_ALPHA ? kA + 1024 : kA;
+  static constexpr int kRoles = HAS_ALPHA ? 8 : 6;
+};
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile("{\n\t.reg .pred p;\n\t"
+               "W: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+               "@!p bra W;\n\t}" :: "r"(bar), "r"(parity) : "memory");
+}
+
+// Converts 8 pixels x 2 rows from one stage.  sy/sa -> this lane's 8 luma / alpha
+// bytes of the top row (bottom row 512 bytes further); sc -> this lane's 4 chroma
+// bytes in row uT (uC, vT, vC follow at kCRow steps); loff/roff select the left /
+// right neighbour sample (mirrored at the image edges: upsampling.c.go:57,61,93,98).
+template <int ST, bool HAS_ALPHA>
+__device__ __forceinline__ void convert8(const uint8_t* sy, const uint8_t* sa, const uint8_t* sc, int loff, int roff,
+                                         bool top_ok, bool bot_ok, uint8_t* dtp, uint8_t* dbp) {
+  constexpr int R = BulkLayout<HAS_ALPHA>::kCRow;
+  const uint2 yt = *reinterpret_cast<const uint2*>(sy);
+  const uint2 yb = *reinterpret_cast<const uint2*>(sy + kTileW);
+  uint2 at = make_uint2(0, 0), ab = make_uint2(0, 0);
+  if (HAS_ALPHA) {
+    at = *reinterpret_cast<const uint2*>(sa);
+    ab = *reinterpret_cast<const uint2*>(sa + kTileW);
+  }
+  const uint32_t wtu = *reinterpret_cast<const uint32_t*>(sc);
+  const uint32_t wcu = *reinterpret_cast<const uint32_t*>(sc + R);
+  const uint32_t wtv = *reinterpret_cast<const uint32_t*>(sc + 2 * R);
+  const uint32_t wcv = *reinterpret_cast<const uint32_t*>(sc + 3 * R);
+  const uint8_t* lp = sc + loff;
+  const uint8_t* rp = sc + roff;
+  const uint32_t ltu = lp[0], lcu = lp[R], ltv = lp[2 * R], lcv = lp[3 * R];
+  const uint32_t rtu = rp[0], rcu = rp[R], rtv = rp[2 * R], rcv = rp[3 * R];
+  const uint32_t etu = b2_even(wtu), otu = b2_odd(wtu), mtu = b2_prmt(etu, rtu, 0x5432);
+  const uint32_t ecu = b2_even(wcu), ocu = b2_odd(wcu), mcu = b2_prmt(ecu, rcu, 0x5432);
+  const uint32_t etv = b2_even(wtv), otv = b2_odd(wtv), mtv = b2_prmt(etv, rtv, 0x5432);
+  const uint32_t ecv = b2_even(wcv), ocv = b2_odd(wcv), mcv = b2_prmt(ecv, rcv, 0x5432);
+  // column pairs (c0,c0+1),(c0+2,c0+3) -> pixels 1,2 | 5,6 ; (c0+1,c0+2),(c0+3,c0+4) -> 3,4 | 7,(8)
+  const B2Quad16 au = b2_interp16(etu, otu, ecu, ocu), bu = b2_interp16(otu, mtu, ocu, mcu);
+  const B2Quad16 av = b2_interp16(etv, otv, ecv, ocv), bv = b2_interp16(otv, mtv, ocv, mcv);
+  // column pair (left,c0) -> pixel 0, U in the low lane and V in the high lane
+  const B2Quad16 cq = b2_interp16(b2_prmt(ltu, ltv, 0x5410), b2_prmt(etu, etv, 0x5410),
+                                  b2_prmt(lcu, lcv, 0x5410), b2_prmt(ecu, ecv, 0x5410));
+  if (top_ok) {
+    const uint32_t xc = b2_hi8(cq.ts);
+    const uint32_t u2[4] = {b2_hi8(au.tf), b2_hi8(au.ts), b2_hi8(bu.tf), b2_prmt(xc, b2_hi8(bu.ts), 0x5410)};
+    const uint32_t v2[4] = {b2_hi8(av.tf), b2_hi8(av.ts), b2_hi8(bv.tf), b2_prmt(xc, b2_hi8(bv.ts), 0x5432)};
+    emit_row8_packed<ST, HAS_ALPHA>(yt, at, u2, v2, dtp);
+  }
+  if (bot_ok) {
+    const uint32_t xc = b2_hi8(cq.bs);
+    const uint32_t u2[4] = {b2_hi8(au.bf), b2_hi8(au.bs), b2_hi8(bu.bf), b2_prmt(xc, b2_hi8(bu.bs), 0x5410)};
+    const uint32_t v2[4] = {b2_hi8(av.bf), b2_hi8(av.bs), b2_hi8(bv.bf), b2_prmt(xc, b2_hi8(bv.bs), 0x5432)};
+    emit_row8_packed<ST, HAS_ALPHA>(yb, ab, u2, v2, dbp);
+  }
+}
+
+template <int ST, bool HAS_ALPHA>
+__global__ void __launch_bounds__(kBulkThreads, kBulkCtasPerSm)
+upsample_bulk_kernel(const UpsampleJobDev* __restrict__ jobs, const uint32_t* __restrict__ unit_prefix,
+                     uint32_t n_jobs, uint32_t uniform_units, uint32_t total_units) {
+  using BL = BulkLayout<HAS_ALPHA>;
+  __shared__ __align__(128) uint8_t ring[kBulkWarps * 2 * BL::kBytes];
+  __shared__ __align__(8) uint64_t bars[kBulkWarps * 2];
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp = threadIdx.x >> 5;
+  uint8_t* wring = ring + warp * (2 * BL::kBytes);
+  const uint32_t wring_s = (uint32_t)__cvta_generic_to_shared(wring);
+  const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(bars + 2 * warp);
+  if (lane == 0) {
+    mbar_init(bar_s, BL::kRoles);
+    mbar_init(bar_s + 8, BL::kRoles);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  const uint32_t first_unit = blockIdx.x * kBulkWarps + warp;
+  const uint32_t unit_stride = gridDim.x * kBulkWarps;
+
+  // ---- producer state: lane r < kRoles copies one input row of every tile ----
+  // role 0,1: Y top/bottom; 2,3: U upper/lower chroma row; 4,5: V; 6,7: alpha top/bottom
+  const int role = lane & 7;
+  const bool is_luma = (role < 2) || (role >= 6);
+  const int p_step = is_luma ? kTileW : kTileW / 2;
+  const int p_halo = is_luma ? 0 : 16;
+  const uint32_t p_dst = (role < 2) ? (uint32_t)(BL::kY + role * kTileW)
+                       : (role < 6) ? (uint32_t)(BL::kC + (role - 2) * BL::kCRow)
+                                    : (uint32_t)(BL::kA + (role - 6) * kTileW);
+  uint32_t p_unit = first_unit;
+  int p_t = 0, p_tiles = 0, p_len16 = 0;
+  const uint8_t* p_row = nullptr;
+  auto producer_setup = [&]() {
+    if (p_unit >= total_units) return;
+    uint32_t q;
+    const uint32_t img = b2_find_image(unit_prefix, n_jobs, uniform_units, p_unit, &q);
+    const UpsampleJobDev* __restrict__ jp = jobs + img;
+    const int width = jp->width, height = jp->height;
+    const int uh = (height + 1) >> 1;
+    const int rt = 2 * (int)q - 1, rb = 2 * (int)q;
+    const int ry_t = (rt >= 0) ? rt : rb, ry_b = (rb < height) ? rb : rt;
+    const int ct = max((int)q - 1, 0), cc = min((int)q, uh - 1);
+    p_tiles = (width + kTileW - 1) / kTileW;
+    p_t = 0;
+    const uint8_t* base = (role < 2) ? jp->y : (role < 4) ? jp->u : (role < 6) ? jp->v : jp->a;
+    const int stride = (role < 2) ? jp->y_stride : (role < 6) ? jp->uv_stride : jp->a_stride;
+    const int rowi = is_luma ? ((role & 1) ? ry_b : ry_t) : ((role & 1) ? cc : ct);
+    p_row = base + (ptrdiff_t)rowi * stride;
+    p_len16 = ((is_luma ? width : ((width + 1) >> 1)) + 15) & ~15;
+  };
+  auto producer_issue = [&](uint32_t stage) {
+    if (p_unit >= total_units) return;
+    if (lane < BL::kRoles) {
+      const int g0 = p_t * p_step - p_halo;
+      const int start = max(g0, 0);
+      const int end = min(g0 + p_step + 2 * p_halo, p_len16);
+      const uint32_t bytes = (uint32_t)(end - start);
+      const uint32_t bar = bar_s + 8 * stage;
+      mbar_expect_tx(bar, bytes);
+      bulk_g2s(wring_s + stage * BL::kBytes + p_dst + (uint32_t)(start - g0), p_row + start, bytes, bar);
+    }
+    if (++p_t == p_tiles) { p_unit += unit_stride; producer_setup(); }
+  };
+
+  // ---- consumer ----
+  uint32_t c_unit = first_unit;
+  producer_setup();
+  producer_issue(0);
+  uint32_t stage = 0, phase = 0;  // phase bit s = parity to wait for on stage s
+  while (c_unit < total_units) {
+    uint32_t q;
+    const uint32_t img = b2_find_image(unit_prefix, n_jobs, uniform_units, c_unit, &q);
+    const UpsampleJobDev* __restrict__ jp = jobs + img;
+    const int width = jp->width, height = jp->height;
+    const int uw = (width + 1) >> 1;
+    const int rt = 2 * (int)q - 1, rb = 2 * (int)q;
+    const bool top_ok = (rt >= 0), bot_ok = (rb < height);
+    const int dstride = jp->dst_stride;
+    constexpr int kBpp = (ST == ST_RGB || ST == ST_BGR) ? 3 : 4;
+    uint8_t* dtp = jp->dst + (ptrdiff_t)(top_ok ? rt : rb) * dstride + lane * (8 * kBpp);
+    uint8_t* dbp = jp->dst + (ptrdiff_t)(bot_ok ? rb : rt) * dstride + lane * (8 * kBpp);
+    const int tiles = (width + kTileW - 1) / kTileW;
+    int x0 = lane * 8;
+    for (int t = 0; t < tiles; ++t) {
+      producer_issue(stage ^ 1);  // the other stage was released by the __syncwarp below
+      mbar_wait(bar_s + 8 * stage, (phase >> stage) & 1);
+      phase ^= 1u << stage;
+      const uint8_t* sp = wring + stage * BL::kBytes;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int xh = x0 + half * 256;
+        if (xh + 8 <= width) {
+          const int c0 = xh >> 1;
+          const int loff = (c0 == 0) ? 0 : -1;          // left neighbour, mirrored at column 0
+          const int roff = (c0 + 4 >= uw) ? 3 : 4;      // right neighbour, mirrored at the last column
+          convert8<ST, HAS_ALPHA>(sp + BL::kY + half * 256 + lane * 8, sp + BL::kA + half * 256 + lane * 8,
+                                  sp + BL::kC + 16 + half * 128 + lane * 4, loff, roff, top_ok, bot_ok,
+                                  dtp + half * (256 * kBpp), dbp + half * (256 * kBpp));
+        } else if (xh < width) {  // ragged right edge: per-pixel path straight from global
+          const UpsampleJobDev j = *jp;
+          for (int x = xh; x < width; ++x) {
+            if (top_ok) pixel_generic<ST>(j, rt, x);
+            if (bot_ok) pixel_generic<ST>(j, rb, x);
+          }
+        }
+      }
+      __syncwarp();  // every lane is done reading this stage before it is refilled
+      dtp += kBpp * kTileW; dbp += kBpp * kTileW; x0 += kTileW;
+      stage ^= 1;
+    }
+    c_unit += unit_stride;
+  }
 }
 
 int canonical_store_mode(int mode) {
@@ -521,20 +809,41 @@ extern "C" int b2_yuv420a_to_rgba_fancy(b2_ctx* ctx, int stream, const b2_upsamp
   cudaStream_t s = ctx->streams[stream];
   const int grid = b2_grid_for(ctx, 8, (total + kWarps - 1) / kWarps);
   const uint32_t tot = (uint32_t)total;
+  static const int variant = getenv("B2_UP_VARIANT") ? atoi(getenv("B2_UP_VARIANT")) : 0;
+  if (tuned && staged && variant == 0) {
+    const int bgrid = b2_grid_for(ctx, kBulkCtasPerSm, (utotal + kBulkWarps - 1) / kBulkWarps);
+    const uint32_t ut = (uint32_t)utotal;
+    const bool ha = n_with_a != 0;
+#define B2_UPK(ST_, HA_) upsample_bulk_kernel<ST_, HA_><<<bgrid, kBulkThreads, 0, s>>>(djobs, dupre, n_jobs, uuniform, ut)
+    switch (st_mode) {
+      case ST_RGBA: if (ha) B2_UPK(ST_RGBA, true); else B2_UPK(ST_RGBA, false); break;
+      case ST_BGRA: if (ha) B2_UPK(ST_BGRA, true); else B2_UPK(ST_BGRA, false); break;
+      case ST_ARGB: if (ha) B2_UPK(ST_ARGB, true); else B2_UPK(ST_ARGB, false); break;
+      case ST_RGB: B2_UPK(ST_RGB, false); break;
+      default: B2_UPK(ST_BGR, false); break;
+    }
+#undef B2_UPK
+    ctx->launches++;
+    B2_CUDA(ctx, cudaGetLastError());
+    return B2_OK;
+  }
   if (tuned && staged) {
     const int ugrid = b2_grid_for(ctx, 3, (utotal + kWarps - 1) / kWarps);
     const uint32_t ut = (uint32_t)utotal;
     const bool ha = n_with_a != 0;
-#define B2_UPA(ST_) do { if (ha) upsample_async_kernel<ST_, true><<<ugrid, kThreads, 0, s>>>(djobs, dupre, n_jobs, uuniform, ut); \
-                         else upsample_async_kernel<ST_, false><<<ugrid, kThreads, 0, s>>>(djobs, dupre, n_jobs, uuniform, ut); } while (0)
+    static const bool unpacked = variant == 2;
+#define B2_UPB(ST_, HA_) do { if (unpacked) upsample_async_kernel<ST_, HA_, false><<<ugrid, kThreads, 0, s>>>(djobs, dupre, n_jobs, uuniform, ut); \
+                              else upsample_async_kernel<ST_, HA_, true><<<ugrid, kThreads, 0, s>>>(djobs, dupre, n_jobs, uuniform, ut); } while (0)
+#define B2_UPA(ST_) do { if (ha) B2_UPB(ST_, true); else B2_UPB(ST_, false); } while (0)
     switch (st_mode) {
       case ST_RGBA: B2_UPA(ST_RGBA); break;
       case ST_BGRA: B2_UPA(ST_BGRA); break;
       case ST_ARGB: B2_UPA(ST_ARGB); break;
-      case ST_RGB: upsample_async_kernel<ST_RGB, false><<<ugrid, kThreads, 0, s>>>(djobs, dupre, n_jobs, uuniform, ut); break;
-      default: upsample_async_kernel<ST_BGR, false><<<ugrid, kThreads, 0, s>>>(djobs, dupre, n_jobs, uuniform, ut); break;
+      case ST_RGB: B2_UPB(ST_RGB, false); break;
+      default: B2_UPB(ST_BGR, false); break;
     }
 #undef B2_UPA
+#undef B2_UPB
     ctx->launches++;
     B2_CUDA(ctx, cudaGetLastError());
     return B2_OK;

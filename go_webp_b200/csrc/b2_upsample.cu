@@ -18,8 +18,6 @@
 // plus eight halo bytes (L1 hits), four 128-bit RGBA stores.  The interpolation
 // is the reference's own 2x16-bit SWAR, here packing two columns (or U and V)
 // per 32-bit register.
-#include <stdlib.h>
-
 #include "b2_common.cuh"
 #include "b2_upsample_core.cuh"
 
@@ -216,66 +214,14 @@ upsample_kernel(const UpsampleJobDev* __restrict__ jobs, const uint32_t* __restr
   }
 }
 
-// MultHi(x, c) (conversion.go:41-43) from x24 = x << 24 is one multiply-high.  The
-// three ">> 6" stay on the integer ALU: ncu shows the ALU and the FMA-heavy
-// (integer multiply) pipes both ~65% busy with that split; moving shifts onto the
-// multiplier (__mulhi by 2^26) or products off it was measured slower
-// (profiles/r01_upsample_pipe_balance.md).
-__device__ __forceinline__ void rgb6(uint32_t y24, uint32_t u24, uint32_t v24, int* r, int* g, int* b) {
-  const int yy = (int)__umulhi(y24, 19077u);
-  *r = (yy + (int)__umulhi(v24, 26149u) - 14234) >> 6;
-  *g = (yy - (int)__umulhi(u24, 6419u) - (int)__umulhi(v24, 13320u) + 8708) >> 6;
-  *b = (yy + (int)__umulhi(u24, 33050u) - 17685) >> 6;
-}
-
-// Converts and stores 8 pixels of one output row.  yw = 8 luma bytes, aw = 8 alpha
-// bytes (HAS_ALPHA), u24/v24 = interpolated chroma << 24 per pixel.
-template <int ST, bool HAS_ALPHA>
-__device__ __forceinline__ void emit_row8(uint2 yw, uint2 aw, const uint32_t (&u24)[8],
-                                          const uint32_t (&v24)[8], uint8_t* dp) {
-  int r[8], g[8], b[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const uint32_t w = (k < 4) ? yw.x : yw.y;
-    rgb6(__byte_perm(w, 0u, 0x0444 | ((k & 3) << 12)), u24[k], v24[k], &r[k], &g[k], &b[k]);
-  }
-  if (ST == ST_RGB || ST == ST_BGR) {
-    // 24 contiguous bytes: [c0 c1 c2 c0'] [c1' c2' c0'' c1''] [c2'' ...] x 2
-    uint32_t o[6];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int* c0 = (ST == ST_RGB) ? r : b;
-      const int* c2 = (ST == ST_RGB) ? b : r;
-      const int i = 4 * h;
-      o[3 * h + 0] = pack4_sat(c0[i], g[i], c2[i], c0[i + 1]);
-      o[3 * h + 1] = pack4_sat(g[i + 1], c2[i + 1], c0[i + 2], g[i + 2]);
-      o[3 * h + 2] = pack4_sat(c2[i + 2], c0[i + 3], g[i + 3], c2[i + 3]);
-    }
-    b2_stg_stream_v2(dp, make_uint2(o[0], o[1]));
-    b2_stg_stream_v2(dp + 8, make_uint2(o[2], o[3]));
-    b2_stg_stream_v2(dp + 16, make_uint2(o[4], o[5]));
-  } else {
-    uint32_t o[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const uint32_t w = (k < 4) ? aw.x : aw.y;
-      const int alpha = HAS_ALPHA ? (int)((w >> (8 * (k & 3))) & 0xff) : 0xff;
-      if (ST == ST_RGBA) o[k] = pack4_sat(r[k], g[k], b[k], alpha);
-      else if (ST == ST_BGRA) o[k] = pack4_sat(b[k], g[k], r[k], alpha);
-      else o[k] = pack4_sat(alpha, r[k], g[k], b[k]);
-    }
-    b2_stg_stream_v4(dp, make_uint4(o[0], o[1], o[2], o[3]));
-    b2_stg_stream_v4(dp + 16, make_uint4(o[4], o[5], o[6], o[7]));
-  }
-}
-
-// Packed variant (b2_upsample_core.cuh): converts and stores 8 pixels of one output
+// Packed arithmetic (b2_upsample_core.cuh): converts and stores 8 pixels of one output
 // row from four pixel PAIRS, two pixels per 32-bit register all the way to the
 // store.  Pair p holds pixels (1,5), (2,6), (3,7), (0,4) -- the lane layout the
 // interpolation produces.  u2/v2 = interpolated chroma, clean 8-bit lanes.
 template <int ST, bool HAS_ALPHA>
 __device__ __forceinline__ void emit_row8_packed(uint2 yw, uint2 aw, const uint32_t (&u2)[4],
-                                                 const uint32_t (&v2)[4], uint8_t* dp) {
+                                                 const uint32_t (&v2)[4], uint8_t* dp, const B2YuvConsts& kc,
+                                                 uint8_t* xs, uint32_t xw0, uint32_t xw1) {
   const uint32_t ye_x = b2_even(yw.x), yo_x = b2_odd(yw.x), ye_y = b2_even(yw.y), yo_y = b2_odd(yw.y);
   const uint32_t y2[4] = {b2_prmt(yo_x, yo_y, 0x5410), b2_prmt(ye_x, ye_y, 0x7632),
                           b2_prmt(yo_x, yo_y, 0x7632), b2_prmt(ye_x, ye_y, 0x5410)};
@@ -287,7 +233,7 @@ __device__ __forceinline__ void emit_row8_packed(uint2 yw, uint2 aw, const uint3
   uint32_t o[8];
 #pragma unroll
   for (int p = 0; p < 4; ++p) {
-    const B2Rgb14 c = b2_yuv_pair(b2_luma14(y2[p]), u2[p], v2[p]);
+    const B2Rgb14 c = b2_yuv_pair(b2_luma14(y2[p], kc), u2[p], v2[p], kc);
     const uint32_t r4 = b2_to_byte1(c.r), g4 = b2_to_byte1(c.g), b4 = b2_to_byte1(c.b);
     const uint32_t ap = (p < 2) ? ap01 : ap23;
     const bool k0 = (p & 1) == 0;  // alpha bytes (0,1) or (2,3) of ap
@@ -325,225 +271,58 @@ __device__ __forceinline__ void emit_row8_packed(uint2 yw, uint2 aw, const uint3
     b2_stg_stream_v2(dp, make_uint2(w[0], w[1]));
     b2_stg_stream_v2(dp + 8, make_uint2(w[2], w[3]));
     b2_stg_stream_v2(dp + 16, make_uint2(w[4], w[5]));
+  } else if (xs != nullptr) {  // warp-uniform: through the transposition buffer (see XposeLane)
+    *reinterpret_cast<uint4*>(xs + xw0) = make_uint4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<uint4*>(xs + xw1) = make_uint4(o[4], o[5], o[6], o[7]);
   } else {
     b2_stg_stream_v4(dp, make_uint4(o[0], o[1], o[2], o[3]));
     b2_stg_stream_v4(dp + 16, make_uint4(o[4], o[5], o[6], o[7]));
   }
 }
 
-// ---- cp.async-staged kernel -------------------------------------------------------
-// The row-walking kernel above is bound by exposed load latency (ncu: 50% of stall
-// samples on the first use of loaded data, 0.9 eligible warps per scheduler).  Here
-// every warp owns a 3-stage ring in shared memory and streams its items through it
-// with cp.async (LDGSTS): the copies for item i+2 are in flight while item i is
-// computed, across row-pair boundaries, at no register cost.  One 16-byte copy per
-// lane moves both Y rows, one moves the four chroma rows, eight lanes fetch the
-// halo words; the halo bytes are then ordinary shared-memory loads.
-// Extra preconditions: y/u/v(/a) pointers and strides are multiples of 16 bytes
-// (so 16-byte chunks never leave a row's stride span).
-constexpr int kStages = 3;
-template <bool HAS_ALPHA> struct StageLayout {
-  static constexpr int kY = 0;          // yT[256] yB[256]
-  static constexpr int kC = 512;        // 4 chroma rows x 160 B: [12 pad][left word][128 main][right word][12 pad]
-  static constexpr int kA = 1152;       // aT[256] aB[256]
-  static constexpr int kBytes = HAS_ALPHA ? 1664 : 1152;
-};
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory");
-}
-
-template <int ST, bool HAS_ALPHA, bool PACKED>
-__global__ void __launch_bounds__(kThreads, 3)
-upsample_async_kernel(const UpsampleJobDev* __restrict__ jobs, const uint32_t* __restrict__ unit_prefix,
-                      uint32_t n_jobs, uint32_t uniform_units, uint32_t total_units) {
-  using SL = StageLayout<HAS_ALPHA>;
-  __shared__ __align__(16) uint8_t ring[kWarps * kStages * SL::kBytes];
-  const int lane = threadIdx.x & 31;
-  const uint32_t warp = threadIdx.x >> 5;
-  uint8_t* wring = ring + warp * (kStages * SL::kBytes);
-  const uint32_t wring_s = (uint32_t)__cvta_generic_to_shared(wring);
-  const uint32_t first_unit = blockIdx.x * kWarps + warp;
-  const uint32_t unit_stride = gridDim.x * kWarps;
-
-  // ---- loader state (per lane: which 16-byte chunk of which row it copies) ----
-  const int yrow = lane >> 4, yk = lane & 15;          // Y / alpha: row 0 = top, 1 = bottom
-  const int crp = lane >> 3, ck = lane & 7;            // chroma: 0 uT, 1 uC, 2 vT, 3 vC
-  const int hrp = (lane >> 1) & 3, hside = lane & 1;   // halo words (lanes 0..7)
-  const uint32_t y_dst = SL::kY + yrow * 256 + yk * 16;
-  const uint32_t a_dst = SL::kA + yrow * 256 + yk * 16;
-  const uint32_t c_dst = SL::kC + crp * 160 + 16 + ck * 16;
-  const uint32_t h_dst = SL::kC + hrp * 160 + (hside ? 144 : 12);
-  uint32_t l_unit = first_unit;
-  int l_t = 0, l_tiles = 0, l_width = 0, l_uw = 0;
-  const uint8_t* l_y = nullptr; const uint8_t* l_a = nullptr; const uint8_t* l_c = nullptr; const uint8_t* l_h = nullptr;
-  auto loader_setup = [&]() {
-    if (l_unit >= total_units) return;
-    uint32_t q;
-    const uint32_t img = b2_find_image(unit_prefix, n_jobs, uniform_units, l_unit, &q);
-    const UpsampleJobDev* __restrict__ jp = jobs + img;
-    l_width = jp->width;
-    const int height = jp->height;
-    l_uw = (l_width + 1) >> 1;
-    const int uh = (height + 1) >> 1;
-    const int rt = 2 * (int)q - 1, rb = 2 * (int)q;
-    const int ry_t = (rt >= 0) ? rt : rb, ry_b = (rb < height) ? rb : rt;
-    const int ct = max((int)q - 1, 0), cc = min((int)q, uh - 1);
-    l_tiles = (l_width + kItemW - 1) / kItemW;
-    l_t = 0;
-    l_y = jp->y + (ptrdiff_t)(yrow ? ry_b : ry_t) * jp->y_stride + yk * 16;
-    if (HAS_ALPHA) l_a = jp->a + (ptrdiff_t)(yrow ? ry_b : ry_t) * jp->a_stride + yk * 16;
-    l_c = ((crp < 2) ? jp->u : jp->v) + (ptrdiff_t)((crp & 1) ? cc : ct) * jp->uv_stride + ck * 16;
-    l_h = ((hrp < 2) ? jp->u : jp->v) + (ptrdiff_t)((hrp & 1) ? cc : ct) * jp->uv_stride + (hside ? 128 : -4);
-  };
-  auto loader_issue = [&](int stage) {
-    if (l_unit < total_units) {
-      const uint32_t sb = wring_s + stage * SL::kBytes;
-      if (l_t * kItemW + yk * 16 < l_width) {
-        cp_async16(sb + y_dst, l_y);
-        if (HAS_ALPHA) cp_async16(sb + a_dst, l_a);
-      }
-      if (l_t * (kItemW / 2) + ck * 16 < l_uw) cp_async16(sb + c_dst, l_c);
-      if (lane < 8 && (hside ? (l_t * (kItemW / 2) + 128 < l_uw) : (l_t > 0))) cp_async4(sb + h_dst, l_h);
-      l_y += kItemW; l_c += kItemW / 2; l_h += kItemW / 2;
-      if (HAS_ALPHA) l_a += kItemW;
-      if (++l_t == l_tiles) { l_unit += unit_stride; loader_setup(); }
-    }
-    cp_async_commit();
-  };
-
-  // ---- consumer state ----
-  uint32_t c_unit = first_unit;
-  loader_setup();
-  loader_issue(0);
-  loader_issue(1);
-  int stage = 0;
-  while (c_unit < total_units) {
-    uint32_t q;
-    const uint32_t img = b2_find_image(unit_prefix, n_jobs, uniform_units, c_unit, &q);
-    const UpsampleJobDev* __restrict__ jp = jobs + img;
-    const int width = jp->width, height = jp->height;
-    const int uw = (width + 1) >> 1;
-    const int rt = 2 * (int)q - 1, rb = 2 * (int)q;
-    const bool top_ok = (rt >= 0), bot_ok = (rb < height);
-    const int dstride = jp->dst_stride;
-    constexpr int kBpp = (ST == ST_RGB || ST == ST_BGR) ? 3 : 4;
-    uint8_t* dtp = jp->dst + (ptrdiff_t)(top_ok ? rt : rb) * dstride + lane * (8 * kBpp);
-    uint8_t* dbp = jp->dst + (ptrdiff_t)(bot_ok ? rb : rt) * dstride + lane * (8 * kBpp);
-    const int tiles_x = (width + kItemW - 1) / kItemW;
-    int x0 = lane * 8;
-    for (int t = 0; t < tiles_x; ++t, x0 += kItemW) {
-      __syncwarp();  // every lane is done reading the stage about to be refilled
-      loader_issue(stage == 0 ? 2 : stage - 1);   // (stage + 2) % 3
-      cp_async_wait<2>();
-      __syncwarp();  // other lanes' copies of this item are visible
-      const uint8_t* sp = wring + stage * SL::kBytes;
-      if (x0 + 8 <= width) {
-        const int c0 = x0 >> 1;
-        const uint2 yt = *reinterpret_cast<const uint2*>(sp + SL::kY + lane * 8);
-        const uint2 yb = *reinterpret_cast<const uint2*>(sp + SL::kY + 256 + lane * 8);
-        uint2 at = make_uint2(0, 0), ab = make_uint2(0, 0);
-        if (HAS_ALPHA) {
-          at = *reinterpret_cast<const uint2*>(sp + SL::kA + lane * 8);
-          ab = *reinterpret_cast<const uint2*>(sp + SL::kA + 256 + lane * 8);
-        }
-        const uint8_t* cp = sp + SL::kC + 16 + lane * 4;
-        const uint32_t wtu = *reinterpret_cast<const uint32_t*>(cp);
-        const uint32_t wcu = *reinterpret_cast<const uint32_t*>(cp + 160);
-        const uint32_t wtv = *reinterpret_cast<const uint32_t*>(cp + 320);
-        const uint32_t wcv = *reinterpret_cast<const uint32_t*>(cp + 480);
-        uint32_t ltu = cp[-1], lcu = cp[159], ltv = cp[319], lcv = cp[479];
-        uint32_t rtu = cp[4], rcu = cp[164], rtv = cp[324], rcv = cp[484];
-        if (c0 == 0) { ltu = wtu & 0xff; lcu = wcu & 0xff; ltv = wtv & 0xff; lcv = wcv & 0xff; }  // mirrored
-        if (c0 + 4 >= uw) { rtu = wtu >> 24; rcu = wcu >> 24; rtv = wtv >> 24; rcv = wcv >> 24; }
-        if (PACKED) {
-          const uint32_t etu = b2_even(wtu), otu = b2_odd(wtu), mtu = b2_prmt(etu, rtu, 0x5432);
-          const uint32_t ecu = b2_even(wcu), ocu = b2_odd(wcu), mcu = b2_prmt(ecu, rcu, 0x5432);
-          const uint32_t etv = b2_even(wtv), otv = b2_odd(wtv), mtv = b2_prmt(etv, rtv, 0x5432);
-          const uint32_t ecv = b2_even(wcv), ocv = b2_odd(wcv), mcv = b2_prmt(ecv, rcv, 0x5432);
-          // column pairs (c0,c0+1),(c0+2,c0+3) -> pixels 1,2 | 5,6 ; (c0+1,c0+2),(c0+3,c0+4) -> 3,4 | 7,(8)
-          const B2Quad16 au = b2_interp16(etu, otu, ecu, ocu), bu = b2_interp16(otu, mtu, ocu, mcu);
-          const B2Quad16 av = b2_interp16(etv, otv, ecv, ocv), bv = b2_interp16(otv, mtv, ocv, mcv);
-          // column pair (left,c0) -> pixel 0, U in the low lane and V in the high lane
-          const B2Quad16 cq = b2_interp16(b2_prmt(ltu, ltv, 0x5410), b2_prmt(etu, etv, 0x5410),
-                                          b2_prmt(lcu, lcv, 0x5410), b2_prmt(ecu, ecv, 0x5410));
-          if (top_ok) {
-            const uint32_t xc = b2_hi8(cq.ts);
-            const uint32_t u2[4] = {b2_hi8(au.tf), b2_hi8(au.ts), b2_hi8(bu.tf), b2_prmt(xc, b2_hi8(bu.ts), 0x5410)};
-            const uint32_t v2[4] = {b2_hi8(av.tf), b2_hi8(av.ts), b2_hi8(bv.tf), b2_prmt(xc, b2_hi8(bv.ts), 0x5432)};
-            emit_row8_packed<ST, HAS_ALPHA>(yt, at, u2, v2, dtp);
-          }
-          if (bot_ok) {
-            const uint32_t xc = b2_hi8(cq.bs);
-            const uint32_t u2[4] = {b2_hi8(au.bf), b2_hi8(au.bs), b2_hi8(bu.bf), b2_prmt(xc, b2_hi8(bu.bs), 0x5410)};
-            const uint32_t v2[4] = {b2_hi8(av.bf), b2_hi8(av.bs), b2_hi8(bv.bf), b2_prmt(xc, b2_hi8(bv.bs), 0x5432)};
-            emit_row8_packed<ST, HAS_ALPHA>(yb, ab, u2, v2, dbp);
-          }
-        } else {
-        const uint32_t etu = wtu & 0x00ff00ffu, otu = (wtu >> 8) & 0x00ff00ffu;
-        const uint32_t ecu = wcu & 0x00ff00ffu, ocu = (wcu >> 8) & 0x00ff00ffu;
-        const uint32_t etv = wtv & 0x00ff00ffu, otv = (wtv >> 8) & 0x00ff00ffu;
-        const uint32_t ecv = wcv & 0x00ff00ffu, ocv = (wcv >> 8) & 0x00ff00ffu;
-        const Quad au = interp(etu, otu, ecu, ocu);
-        const Quad av = interp(etv, otv, ecv, ocv);
-        const Quad bu = interp(otu, __byte_perm(etu, rtu, 0x7432), ocu, __byte_perm(ecu, rcu, 0x7432));
-        const Quad bv = interp(otv, __byte_perm(etv, rtv, 0x7432), ocv, __byte_perm(ecv, rcv, 0x7432));
-        const Quad cq = interp(__byte_perm(ltu, ltv, 0x7410), __byte_perm(etu, etv, 0x7410),
-                               __byte_perm(lcu, lcv, 0x7410), __byte_perm(ecu, ecv, 0x7410));
-        if (top_ok) {
-          const uint32_t u24[8] = {lo24(cq.ts), lo24(au.tf), lo24(au.ts), lo24(bu.tf), lo24(bu.ts), hi24(au.tf), hi24(au.ts), hi24(bu.tf)};
-          const uint32_t v24[8] = {hi24(cq.ts), lo24(av.tf), lo24(av.ts), lo24(bv.tf), lo24(bv.ts), hi24(av.tf), hi24(av.ts), hi24(bv.tf)};
-          emit_row8<ST, HAS_ALPHA>(yt, at, u24, v24, dtp);
-        }
-        if (bot_ok) {
-          const uint32_t u24[8] = {lo24(cq.bs), lo24(au.bf), lo24(au.bs), lo24(bu.bf), lo24(bu.bs), hi24(au.bf), hi24(au.bs), hi24(bu.bf)};
-          const uint32_t v24[8] = {hi24(cq.bs), lo24(av.bf), lo24(av.bs), lo24(bv.bf), lo24(bv.bs), hi24(av.bf), hi24(av.bs), hi24(bv.bf)};
-          emit_row8<ST, HAS_ALPHA>(yb, ab, u24, v24, dbp);
-        }
-        }  // !PACKED
-      } else if (x0 < width) {  // ragged right edge: per-pixel path straight from global
-        const UpsampleJobDev j = *jp;
-        for (int x = x0; x < width; ++x) {
-          if (top_ok) pixel_generic<ST>(j, rt, x);
-          if (bot_ok) pixel_generic<ST>(j, rb, x);
-        }
-      }
-      dtp += kBpp * kItemW; dbp += kBpp * kItemW;
-      stage = (stage == kStages - 1) ? 0 : stage + 1;
-    }
-    c_unit += unit_stride;
-  }
-  cp_async_wait<0>();
-}
-
 // ---- bulk-copy (TMA) staged kernel -------------------------------------------------
 // Same packed arithmetic, cheaper plumbing.  ncu on the cp.async kernel: 535 warp
 // instructions per 256-pixel step, ~85 of them loader bookkeeping executed by every
 // lane, issue slots 73% busy -- the kernel is bound by instruction issue, not by HBM.
-// Here a warp owns a 2-stage ring whose stages hold a 512-pixel x 2-row tile; each
-// input row of a tile is ONE cp.async.bulk issued by one lane (lanes 0..5, or 0..7
-// with an alpha plane) that completes on the stage's mbarrier, so the per-tile
-// bookkeeping is ~25 instructions for 32 pixels per lane.
+// Here a warp owns a 2-stage ring whose stages hold a 1024- (512-) pixel x 2-row tile; each
+// input row of a tile is ONE cp.async.bulk (6 per tile, 8 with an alpha plane), all
+// issued by lane 0 and completing on the stage's mbarrier: the copy engine takes its
+// operands from uniform registers, so a single issuing lane is the cheap form.
 // Preconditions (checked on the host): y/u/v(/a) pointers and strides are multiples
 // of 16 bytes, strides positive, so every copy is 16-byte aligned and sized.
 constexpr int kBulkThreads = 128;
 constexpr int kBulkWarps = kBulkThreads / 32;
-constexpr int kBulkCtasPerSm = 6;
-constexpr int kTileW = 512;
+#ifndef B2_BULK_CTAS
+#define B2_BULK_CTAS 6
+#endif
+#ifndef B2_BULK_TW
+#define B2_BULK_TW 1024
+#endif
+#ifndef B2_PASS_UNROLL
+#define B2_PASS_UNROLL 2
+#endif
+constexpr int kBulkCtasPerSm = B2_BULK_CTAS;
+constexpr int kPassUnroll = B2_PASS_UNROLL;
+// Stage = TW pixels x 2 rows: 1024 pixels without an alpha plane, 512 with one (shared
+// memory: 4 warps x 2 stages x 4.1 KB resp. 3.1 KB per CTA, six CTAs per SM).
 template <bool HAS_ALPHA> struct BulkLayout {
-  static constexpr int kY = 0;               // yT[512] yB[512]
-  static constexpr int kC = 1024;            // uT uC vT vC, each [16 halo][256][16 halo]
-  static constexpr int kCRow = 288;
-  static constexpr int kA = kC + 4 * kCRow;  // aT[512] aB[512]
-  static constexpr int kBytes = HAS_ALPHA ? kA + 1024 : kA;
-  static constexpr int kRoles = HAS_ALPHA ? 8 : 6;
+  static constexpr int kTW = HAS_ALPHA ? 512 : B2_BULK_TW;
+  static constexpr int kY = 0;               // yT[TW] yB[TW]
+  static constexpr int kC = 2 * kTW;         // uT uC vT vC, each [16 halo][TW/2][16 halo]
+  static constexpr int kCRow = kTW / 2 + 32;
+  static constexpr int kA = kC + 4 * kCRow;  // aT[TW] aB[TW]
+  static constexpr int kBytes = HAS_ALPHA ? kA + 2 * kTW : kA;
 };
+// Warp-uniform values: a shuffle from lane 0 tells ptxas the value is the same in every
+// lane, so the producer's arithmetic runs on the uniform datapath and the bulk copies
+// take their operands from uniform registers without a per-copy R2UR/ELECT loop.
+__device__ __forceinline__ uint32_t uni(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+__device__ __forceinline__ int uni(int v) { return __shfl_sync(0xffffffffu, v, 0); }
+__device__ __forceinline__ const uint8_t* uni(const uint8_t* p) {
+  const uint64_t v = (uint64_t)p;
+  const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, 0), hi = __shfl_sync(0xffffffffu, (uint32_t)(v >> 32), 0);
+  return (const uint8_t*)(((uint64_t)hi << 32) | lo);
+}
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
 }
@@ -564,10 +343,32 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // bytes of the top row (bottom row 512 bytes further); sc -> this lane's 4 chroma
 // bytes in row uT (uC, vT, vC follow at kCRow steps); loff/roff select the left /
 // right neighbour sample (mirrored at the image edges: upsampling.c.go:57,61,93,98).
+// Store coalescing.  A lane produces 32 contiguous bytes per row; storing them as two
+// 128-bit stores makes every store instruction write HALF of each 32-byte sector, and
+// ncu shows the price: twice the ideal number of L2 write sectors, the SM->L2 write
+// path 64-69% busy and the kernel stuck at ~4.1 TB/s whatever else changes.  So a full
+// 256-pixel pass goes through a per-warp 2 KB buffer instead: each lane writes its two
+// 16-byte chunks, reads back chunk `lane` and chunk `32 + lane`, and the two store
+// instructions each cover 512 contiguous bytes.  Chunk c lives at c ^ ((c >> 3) & 1),
+// which keeps both the writes (chunks 2*lane, 2*lane+1) and the reads bank-conflict free.
+struct XposeLane { uint32_t w0, w1, r; };
+__device__ __forceinline__ XposeLane xpose_lane(int lane) {
+  const uint32_t b = (uint32_t)(lane >> 2) & 1u;
+  XposeLane x;
+  x.w0 = ((2u * lane) ^ b) * 16u;
+  x.w1 = ((2u * lane + 1u) ^ b) * 16u;
+  x.r = ((uint32_t)lane ^ (((uint32_t)lane >> 3) & 1u)) * 16u;
+  return x;
+}
+
+// xs: this warp's transposition buffer (top row at 0, bottom row at 1024) for a full
+// pass of a 4-byte mode, else nullptr (direct stores).
 template <int ST, bool HAS_ALPHA>
 __device__ __forceinline__ void convert8(const uint8_t* sy, const uint8_t* sa, const uint8_t* sc, int loff, int roff,
-                                         bool top_ok, bool bot_ok, uint8_t* dtp, uint8_t* dbp) {
+                                         bool top_ok, bool bot_ok, uint8_t* dtp, uint8_t* dbp, const B2YuvConsts& kc,
+                                         uint8_t* xs, const XposeLane& xl, int lane) {
   constexpr int R = BulkLayout<HAS_ALPHA>::kCRow;
+  constexpr int kTileW = BulkLayout<HAS_ALPHA>::kTW;
   const uint2 yt = *reinterpret_cast<const uint2*>(sy);
   const uint2 yb = *reinterpret_cast<const uint2*>(sy + kTileW);
   uint2 at = make_uint2(0, 0), ab = make_uint2(0, 0);
@@ -597,13 +398,27 @@ __device__ __forceinline__ void convert8(const uint8_t* sy, const uint8_t* sa, c
     const uint32_t xc = b2_hi8(cq.ts);
     const uint32_t u2[4] = {b2_hi8(au.tf), b2_hi8(au.ts), b2_hi8(bu.tf), b2_prmt(xc, b2_hi8(bu.ts), 0x5410)};
     const uint32_t v2[4] = {b2_hi8(av.tf), b2_hi8(av.ts), b2_hi8(bv.tf), b2_prmt(xc, b2_hi8(bv.ts), 0x5432)};
-    emit_row8_packed<ST, HAS_ALPHA>(yt, at, u2, v2, dtp);
+    emit_row8_packed<ST, HAS_ALPHA>(yt, at, u2, v2, dtp, kc, xs, xl.w0, xl.w1);
   }
   if (bot_ok) {
     const uint32_t xc = b2_hi8(cq.bs);
     const uint32_t u2[4] = {b2_hi8(au.bf), b2_hi8(au.bs), b2_hi8(bu.bf), b2_prmt(xc, b2_hi8(bu.bs), 0x5410)};
     const uint32_t v2[4] = {b2_hi8(av.bf), b2_hi8(av.bs), b2_hi8(bv.bf), b2_prmt(xc, b2_hi8(bv.bs), 0x5432)};
-    emit_row8_packed<ST, HAS_ALPHA>(yb, ab, u2, v2, dbp);
+    emit_row8_packed<ST, HAS_ALPHA>(yb, ab, u2, v2, dbp, kc, xs ? xs + 1024 : nullptr, xl.w0, xl.w1);
+  }
+  if (xs != nullptr) {
+    __syncwarp();
+    if (top_ok) {
+      uint8_t* d = dtp - lane * 16;  // row start of this pass + lane * 16
+      b2_stg_stream_v4(d, *reinterpret_cast<const uint4*>(xs + xl.r));
+      b2_stg_stream_v4(d + 512, *reinterpret_cast<const uint4*>(xs + 512 + xl.r));
+    }
+    if (bot_ok) {
+      uint8_t* d = dbp - lane * 16;
+      b2_stg_stream_v4(d, *reinterpret_cast<const uint4*>(xs + 1024 + xl.r));
+      b2_stg_stream_v4(d + 512, *reinterpret_cast<const uint4*>(xs + 1536 + xl.r));
+    }
+    __syncwarp();
   }
 }
 
@@ -612,34 +427,30 @@ __global__ void __launch_bounds__(kBulkThreads, kBulkCtasPerSm)
 upsample_bulk_kernel(const UpsampleJobDev* __restrict__ jobs, const uint32_t* __restrict__ unit_prefix,
                      uint32_t n_jobs, uint32_t uniform_units, uint32_t total_units) {
   using BL = BulkLayout<HAS_ALPHA>;
+  constexpr int kTileW = BL::kTW;
   __shared__ __align__(128) uint8_t ring[kBulkWarps * 2 * BL::kBytes];
+  __shared__ __align__(16) uint8_t xpose[kBulkWarps * 2048];
   __shared__ __align__(8) uint64_t bars[kBulkWarps * 2];
   const int lane = threadIdx.x & 31;
-  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t warp = uni(threadIdx.x >> 5);
   uint8_t* wring = ring + warp * (2 * BL::kBytes);
   const uint32_t wring_s = (uint32_t)__cvta_generic_to_shared(wring);
   const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(bars + 2 * warp);
   if (lane == 0) {
-    mbar_init(bar_s, BL::kRoles);
-    mbar_init(bar_s + 8, BL::kRoles);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_s + 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
   const uint32_t first_unit = blockIdx.x * kBulkWarps + warp;
   const uint32_t unit_stride = gridDim.x * kBulkWarps;
+  total_units = uni(total_units);
 
-  // ---- producer state: lane r < kRoles copies one input row of every tile ----
-  // role 0,1: Y top/bottom; 2,3: U upper/lower chroma row; 4,5: V; 6,7: alpha top/bottom
-  const int role = lane & 7;
-  const bool is_luma = (role < 2) || (role >= 6);
-  const int p_step = is_luma ? kTileW : kTileW / 2;
-  const int p_halo = is_luma ? 0 : 16;
-  const uint32_t p_dst = (role < 2) ? (uint32_t)(BL::kY + role * kTileW)
-                       : (role < 6) ? (uint32_t)(BL::kC + (role - 2) * BL::kCRow)
-                                    : (uint32_t)(BL::kA + (role - 6) * kTileW);
+  // ---- producer: lane 0 issues every copy of a tile (one mbarrier arrival) ----
   uint32_t p_unit = first_unit;
-  int p_t = 0, p_tiles = 0, p_len16 = 0;
-  const uint8_t* p_row = nullptr;
+  int p_t = 0, p_tiles = 0, p_ylen = 0, p_clen = 0;
+  const uint8_t* p_y = nullptr; const uint8_t* p_u = nullptr; const uint8_t* p_v = nullptr; const uint8_t* p_a = nullptr;
+  int p_ydelta = 0, p_cdelta = 0, p_adelta = 0;  // byte distance from the first to the second row of a pair
   auto producer_setup = [&]() {
     if (p_unit >= total_units) return;
     uint32_t q;
@@ -650,29 +461,53 @@ upsample_bulk_kernel(const UpsampleJobDev* __restrict__ jobs, const uint32_t* __
     const int rt = 2 * (int)q - 1, rb = 2 * (int)q;
     const int ry_t = (rt >= 0) ? rt : rb, ry_b = (rb < height) ? rb : rt;
     const int ct = max((int)q - 1, 0), cc = min((int)q, uh - 1);
-    p_tiles = (width + kTileW - 1) / kTileW;
+    p_tiles = uni((width + kTileW - 1) / kTileW);
     p_t = 0;
-    const uint8_t* base = (role < 2) ? jp->y : (role < 4) ? jp->u : (role < 6) ? jp->v : jp->a;
-    const int stride = (role < 2) ? jp->y_stride : (role < 6) ? jp->uv_stride : jp->a_stride;
-    const int rowi = is_luma ? ((role & 1) ? ry_b : ry_t) : ((role & 1) ? cc : ct);
-    p_row = base + (ptrdiff_t)rowi * stride;
-    p_len16 = ((is_luma ? width : ((width + 1) >> 1)) + 15) & ~15;
+    p_y = uni(jp->y + (ptrdiff_t)ry_t * jp->y_stride);
+    p_ydelta = uni((ry_b - ry_t) * jp->y_stride);
+    p_u = uni(jp->u + (ptrdiff_t)ct * jp->uv_stride);
+    p_v = uni(jp->v + (ptrdiff_t)ct * jp->uv_stride);
+    p_cdelta = uni((cc - ct) * jp->uv_stride);
+    if (HAS_ALPHA) {
+      p_a = uni(jp->a + (ptrdiff_t)ry_t * jp->a_stride);
+      p_adelta = uni((ry_b - ry_t) * jp->a_stride);
+    }
+    p_ylen = uni((width + 15) & ~15);
+    p_clen = uni((((width + 1) >> 1) + 15) & ~15);
   };
   auto producer_issue = [&](uint32_t stage) {
     if (p_unit >= total_units) return;
-    if (lane < BL::kRoles) {
-      const int g0 = p_t * p_step - p_halo;
-      const int start = max(g0, 0);
-      const int end = min(g0 + p_step + 2 * p_halo, p_len16);
-      const uint32_t bytes = (uint32_t)(end - start);
+    if (lane == 0) {
       const uint32_t bar = bar_s + 8 * stage;
-      mbar_expect_tx(bar, bytes);
-      bulk_g2s(wring_s + stage * BL::kBytes + p_dst + (uint32_t)(start - g0), p_row + start, bytes, bar);
+      const uint32_t sb = wring_s + stage * BL::kBytes;
+      const int ys0 = p_t * kTileW;
+      const uint32_t yb = (uint32_t)min(kTileW, p_ylen - ys0);
+      const int g0 = p_t * (kTileW / 2) - 16;     // first chroma byte of the stage row (halo included)
+      const int cs = max(g0, 0);
+      const uint32_t cb = (uint32_t)(min(g0 + BL::kCRow, p_clen) - cs);
+      const uint32_t cd = sb + BL::kC + (uint32_t)(cs - g0);
+      mbar_expect_tx(bar, (HAS_ALPHA ? 4u : 2u) * yb + 4u * cb);
+      bulk_g2s(sb + BL::kY, p_y + ys0, yb, bar);
+      bulk_g2s(sb + BL::kY + kTileW, p_y + p_ydelta + ys0, yb, bar);
+      bulk_g2s(cd, p_u + cs, cb, bar);
+      bulk_g2s(cd + BL::kCRow, p_u + p_cdelta + cs, cb, bar);
+      bulk_g2s(cd + 2 * BL::kCRow, p_v + cs, cb, bar);
+      bulk_g2s(cd + 3 * BL::kCRow, p_v + p_cdelta + cs, cb, bar);
+      if (HAS_ALPHA) {
+        bulk_g2s(sb + BL::kA, p_a + ys0, yb, bar);
+        bulk_g2s(sb + BL::kA + kTileW, p_a + p_adelta + ys0, yb, bar);
+      }
     }
     if (++p_t == p_tiles) { p_unit += unit_stride; producer_setup(); }
   };
 
   // ---- consumer ----
+  // The three register constants of the conversion; made opaque so they stay in
+  // registers instead of being rematerialised before every use.
+  const XposeLane xl = xpose_lane(lane);
+  uint8_t* const xbuf = xpose + warp * 2048;
+  B2YuvConsts kc = b2_yuv_consts();
+  asm volatile("" : "+r"(kc.yoff), "+r"(kc.kr), "+r"(kc.kb));
   uint32_t c_unit = first_unit;
   producer_setup();
   producer_issue(0);
@@ -696,8 +531,8 @@ upsample_bulk_kernel(const UpsampleJobDev* __restrict__ jobs, const uint32_t* __
       mbar_wait(bar_s + 8 * stage, (phase >> stage) & 1);
       phase ^= 1u << stage;
       const uint8_t* sp = wring + stage * BL::kBytes;
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
+#pragma unroll kPassUnroll
+      for (int half = 0; half < kTileW / 256; ++half) {
         const int xh = x0 + half * 256;
         if (xh + 8 <= width) {
           const int c0 = xh >> 1;
@@ -705,7 +540,8 @@ upsample_bulk_kernel(const UpsampleJobDev* __restrict__ jobs, const uint32_t* __
           const int roff = (c0 + 4 >= uw) ? 3 : 4;      // right neighbour, mirrored at the last column
           convert8<ST, HAS_ALPHA>(sp + BL::kY + half * 256 + lane * 8, sp + BL::kA + half * 256 + lane * 8,
                                   sp + BL::kC + 16 + half * 128 + lane * 4, loff, roff, top_ok, bot_ok,
-                                  dtp + half * (256 * kBpp), dbp + half * (256 * kBpp));
+                                  dtp + half * (256 * kBpp), dbp + half * (256 * kBpp), kc,
+                                  (kBpp == 4 && xh - lane * 8 + 256 <= width) ? xbuf : nullptr, xl, lane);
         } else if (xh < width) {  // ragged right edge: per-pixel path straight from global
           const UpsampleJobDev j = *jp;
           for (int x = xh; x < width; ++x) {
@@ -809,8 +645,7 @@ extern "C" int b2_yuv420a_to_rgba_fancy(b2_ctx* ctx, int stream, const b2_upsamp
   cudaStream_t s = ctx->streams[stream];
   const int grid = b2_grid_for(ctx, 8, (total + kWarps - 1) / kWarps);
   const uint32_t tot = (uint32_t)total;
-  static const int variant = getenv("B2_UP_VARIANT") ? atoi(getenv("B2_UP_VARIANT")) : 0;
-  if (tuned && staged && variant == 0) {
+  if (tuned && staged) {
     const int bgrid = b2_grid_for(ctx, kBulkCtasPerSm, (utotal + kBulkWarps - 1) / kBulkWarps);
     const uint32_t ut = (uint32_t)utotal;
     const bool ha = n_with_a != 0;
@@ -823,27 +658,6 @@ extern "C" int b2_yuv420a_to_rgba_fancy(b2_ctx* ctx, int stream, const b2_upsamp
       default: B2_UPK(ST_BGR, false); break;
     }
 #undef B2_UPK
-    ctx->launches++;
-    B2_CUDA(ctx, cudaGetLastError());
-    return B2_OK;
-  }
-  if (tuned && staged) {
-    const int ugrid = b2_grid_for(ctx, 3, (utotal + kWarps - 1) / kWarps);
-    const uint32_t ut = (uint32_t)utotal;
-    const bool ha = n_with_a != 0;
-    static const bool unpacked = variant == 2;
-#define B2_UPB(ST_, HA_) do { if (unpacked) upsample_async_kernel<ST_, HA_, false><<<ugrid, kThreads, 0, s>>>(djobs, dupre, n_jobs, uuniform, ut); \
-                              else upsample_async_kernel<ST_, HA_, true><<<ugrid, kThreads, 0, s>>>(djobs, dupre, n_jobs, uuniform, ut); } while (0)
-#define B2_UPA(ST_) do { if (ha) B2_UPB(ST_, true); else B2_UPB(ST_, false); } while (0)
-    switch (st_mode) {
-      case ST_RGBA: B2_UPA(ST_RGBA); break;
-      case ST_BGRA: B2_UPA(ST_BGRA); break;
-      case ST_ARGB: B2_UPA(ST_ARGB); break;
-      case ST_RGB: B2_UPB(ST_RGB, false); break;
-      default: B2_UPB(ST_BGR, false); break;
-    }
-#undef B2_UPA
-#undef B2_UPB
     ctx->launches++;
     B2_CUDA(ctx, cudaGetLastError());
     return B2_OK;

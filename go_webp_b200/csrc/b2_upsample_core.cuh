@@ -65,22 +65,43 @@ B2_HD B2Quad16 b2_interp16(uint32_t tl, uint32_t t, uint32_t l, uint32_t c) {
 // MultHi(v, k) = (v*k) >> 8 with k = 256*kh + kl is v*kh + ((v*kl) >> 8); for 8-bit
 // v both products fit a 16-bit lane: 19077 = 74*256+133, 26149 = 102*256+37,
 // 33050 = 129*256+26, 6419 = 25*256+19, 13320 = 52*256+8.
-B2_HD uint32_t b2_luma14(uint32_t y2) { return y2 * 74u + b2_hi8(y2 * 133u); }  // MultHi(y,19077)
+//
+// VIADDMNMX computes relu(min(a + b, c)) per 16-bit lane with a wrapping add and only
+// c may be an immediate, so the constants of the three channels are arranged to need
+// as few register operands as possible:
+//  * luma carries a free offset: the PRMT that extracts (y*133) >> 8 takes its zero
+//    bytes from `k.yoff` instead (byte 0x23), i.e. yh2 = MultHi(y,19077) + 0x2300;
+//  * G = a + b with a = yh2 - MultHi(u,6419) (>= 0 thanks to the offset) and
+//    b = 65284 - 52 v - (v >> 5); 0x2300 + 65284 = 8708 + 65536, so the wrapped sum
+//    is exactly the reference's G before clipping -- no constant operand at all;
+//  * R and B subtract (14234 + 0x2300) and (17685 + 0x2300) through `k.kr`, `k.kb`.
+struct B2YuvConsts { uint32_t yoff, kr, kb; };
+B2_HD B2YuvConsts b2_yuv_consts() {
+  B2YuvConsts k;
+  k.yoff = 0x23u;
+  k.kr = B2_K2(-14234 - 0x2300);
+  k.kb = B2_K2(-17685 - 0x2300);
+  return k;
+}
+// MultHi(y,19077) + 0x2300 in both lanes
+B2_HD uint32_t b2_luma14(uint32_t y2, const B2YuvConsts& k) {
+  return y2 * 74u + b2_prmt(y2 * 133u, k.yoff, 0x4341);
+}
 
 struct B2Rgb14 { uint32_t r, g, b; };  // lanes = pre-shift channel clamped to [0,16383]
-B2_HD B2Rgb14 b2_yuv_pair(uint32_t yh2, uint32_t u2, uint32_t v2) {
+B2_HD B2Rgb14 b2_yuv_pair(uint32_t yh2, uint32_t u2, uint32_t v2, const B2YuvConsts& k) {
   B2Rgb14 o;
-  // R = Clip8(MultHi(y,19077) + MultHi(v,26149) - 14234); lanes of wr <= 45049
+  // R = Clip8(MultHi(y,19077) + MultHi(v,26149) - 14234); lanes of wr <= 54009
   const uint32_t wr = v2 * 102u + (yh2 + b2_hi8(v2 * 37u));
-  o.r = __viaddmin_s16x2_relu(wr, B2_K2(-14234), B2_K2(16383));
-  // B = Clip8(MultHi(y,19077) + MultHi(u,33050) - 17685); lanes of wb reach 51922,
-  // and wb - 17685 would leave int16, so saturate the top first (unsigned min)
-  const uint32_t wb = u2 * 129u + (yh2 + b2_hi8(u2 * 26u));
-  o.b = __viaddmin_s16x2_relu(__viaddmin_u16x2(wb, 0u, B2_K2(17685 + 16383)), B2_K2(-17685), B2_K2(16383));
-  // G = Clip8(MultHi(y,19077) - MultHi(u,6419) - MultHi(v,13320) + 8708); the bias
-  // keeps every lane of the packed subtraction non-negative (no borrow across lanes)
-  const uint32_t wg = (yh2 + B2_K2(20000) - b2_hi8(u2 * 19u)) - b2_hi8(v2 * 8u) - u2 * 25u - v2 * 52u;
-  o.g = __viaddmin_s16x2_relu(wg, B2_K2(8708 - 20000), B2_K2(16383));
+  o.r = __viaddmin_s16x2_relu(wr, k.kr, B2_K2(16383));
+  // B = Clip8(MultHi(y,19077) + MultHi(u,33050) - 17685); the sum reaches 60882 and
+  // sum - 26645 would leave int16, so the add saturates the top first (unsigned min)
+  const uint32_t bu = u2 * 129u + b2_hi8(u2 * 26u);
+  o.b = __viaddmin_s16x2_relu(__viaddmin_u16x2(bu, yh2, B2_K2(17685 + 0x2300 + 16383)), k.kb, B2_K2(16383));
+  // G = Clip8(MultHi(y,19077) - MultHi(u,6419) - MultHi(v,13320) + 8708)
+  const uint32_t ga = (yh2 - b2_hi8(u2 * 19u)) - u2 * 25u;              // lanes in [2560, 27962]
+  const uint32_t gb = B2_K2(65284) - b2_hi8(v2 * 8u) - v2 * 52u;        // lanes in [52017, 65284]
+  o.g = __viaddmin_s16x2_relu(ga, gb, B2_K2(16383));
   return o;
 }
 

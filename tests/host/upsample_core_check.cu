@@ -22,7 +22,8 @@ int main() {
         const int y1 = 255 - y, u1 = (v * 7 + 3) & 255, v1 = (u * 13 + 5) & 255;
         const uint32_t y2 = (uint32_t)y | ((uint32_t)y1 << 16), u2 = (uint32_t)u | ((uint32_t)u1 << 16),
                        v2 = (uint32_t)v | ((uint32_t)v1 << 16);
-        const B2Rgb14 o = b2_yuv_pair(b2_luma14(y2), u2, v2);
+        const B2YuvConsts kc = b2_yuv_consts();
+        const B2Rgb14 o = b2_yuv_pair(b2_luma14(y2, kc), u2, v2, kc);
         const uint32_t r = b2_hi8(b2_to_byte1(o.r)), g = b2_hi8(b2_to_byte1(o.g)), b = b2_hi8(b2_to_byte1(o.b));
         const uint32_t er = (uint32_t)RefR(y, v) | ((uint32_t)RefR(y1, v1) << 16);
         const uint32_t eg = (uint32_t)RefG(y, u, v) | ((uint32_t)RefG(y1, u1, v1) << 16);

@@ -220,8 +220,8 @@ upsample_kernel(const UpsampleJobDev* __restrict__ jobs, const uint32_t* __restr
 // interpolation produces.  u2/v2 = interpolated chroma, clean 8-bit lanes.
 template <int ST, bool HAS_ALPHA>
 __device__ __forceinline__ void emit_row8_packed(uint2 yw, uint2 aw, const uint32_t (&u2)[4],
-                                                 const uint32_t (&v2)[4], uint8_t* dp, const B2YuvConsts& kc,
-                                                 uint8_t* xs, uint32_t xw0, uint32_t xw1) {
+                                                 const uint32_t (&v2)[4], uint8_t* dp, bool store_ok,
+                                                 const B2YuvConsts& kc, uint8_t* xs, uint32_t xw0, uint32_t xw1) {
   const uint32_t ye_x = b2_even(yw.x), yo_x = b2_odd(yw.x), ye_y = b2_even(yw.y), yo_y = b2_odd(yw.y);
   const uint32_t y2[4] = {b2_prmt(yo_x, yo_y, 0x5410), b2_prmt(ye_x, ye_y, 0x7632),
                           b2_prmt(yo_x, yo_y, 0x7632), b2_prmt(ye_x, ye_y, 0x5410)};
@@ -268,15 +268,14 @@ __device__ __forceinline__ void emit_row8_packed(uint2 yw, uint2 aw, const uint3
       w[3 * h + 1] = b2_prmt(q[1], q[2], 0x5421);
       w[3 * h + 2] = b2_prmt(q[2], q[3], 0x6542);
     }
-    b2_stg_stream_v2(dp, make_uint2(w[0], w[1]));
-    b2_stg_stream_v2(dp + 8, make_uint2(w[2], w[3]));
-    b2_stg_stream_v2(dp + 16, make_uint2(w[4], w[5]));
-  } else if (xs != nullptr) {  // warp-uniform: through the transposition buffer (see XposeLane)
+    if (store_ok) {
+      b2_stg_stream_v2(dp, make_uint2(w[0], w[1]));
+      b2_stg_stream_v2(dp + 8, make_uint2(w[2], w[3]));
+      b2_stg_stream_v2(dp + 16, make_uint2(w[4], w[5]));
+    }
+  } else {  // 4-byte modes: through the warp's transposition buffer (see XposeLane)
     *reinterpret_cast<uint4*>(xs + xw0) = make_uint4(o[0], o[1], o[2], o[3]);
     *reinterpret_cast<uint4*>(xs + xw1) = make_uint4(o[4], o[5], o[6], o[7]);
-  } else {
-    b2_stg_stream_v4(dp, make_uint4(o[0], o[1], o[2], o[3]));
-    b2_stg_stream_v4(dp + 16, make_uint4(o[4], o[5], o[6], o[7]));
   }
 }
 
@@ -361,14 +360,21 @@ __device__ __forceinline__ XposeLane xpose_lane(int lane) {
   return x;
 }
 
-// xs: this warp's transposition buffer (top row at 0, bottom row at 1024) for a full
-// pass of a 4-byte mode, else nullptr (direct stores).
+// One 256-pixel pass of a warp: every lane converts 8 pixels x 2 rows (lanes past the
+// end of the row compute on stale stage bytes and store nothing).  xpass = first pixel
+// of the pass, wv = width rounded down to 8 (the part of the row the vector path
+// covers); drt/drb = start of the two output rows; xs = this warp's transposition
+// buffer (top row at 0, bottom row at 1024).
 template <int ST, bool HAS_ALPHA>
-__device__ __forceinline__ void convert8(const uint8_t* sy, const uint8_t* sa, const uint8_t* sc, int loff, int roff,
-                                         bool top_ok, bool bot_ok, uint8_t* dtp, uint8_t* dbp, const B2YuvConsts& kc,
-                                         uint8_t* xs, const XposeLane& xl, int lane) {
+__device__ __forceinline__ void convert_pass(const uint8_t* sy, const uint8_t* sa, const uint8_t* sc, int lane,
+                                             int xpass, int wv, int uw, bool top_ok, bool bot_ok, uint8_t* drt,
+                                             uint8_t* drb, const B2YuvConsts& kc, uint8_t* xs, const XposeLane& xl) {
   constexpr int R = BulkLayout<HAS_ALPHA>::kCRow;
   constexpr int kTileW = BulkLayout<HAS_ALPHA>::kTW;
+  constexpr int kBpp = (ST == ST_RGB || ST == ST_BGR) ? 3 : 4;
+  const int xh = xpass + lane * 8, c0 = xh >> 1;
+  const int loff = (c0 == 0) ? 0 : -1;      // left neighbour, mirrored at column 0
+  const int roff = (c0 + 4 >= uw) ? 3 : 4;  // right neighbour, mirrored at the last column
   const uint2 yt = *reinterpret_cast<const uint2*>(sy);
   const uint2 yb = *reinterpret_cast<const uint2*>(sy + kTileW);
   uint2 at = make_uint2(0, 0), ab = make_uint2(0, 0);
@@ -394,29 +400,32 @@ __device__ __forceinline__ void convert8(const uint8_t* sy, const uint8_t* sa, c
   // column pair (left,c0) -> pixel 0, U in the low lane and V in the high lane
   const B2Quad16 cq = b2_interp16(b2_prmt(ltu, ltv, 0x5410), b2_prmt(etu, etv, 0x5410),
                                   b2_prmt(lcu, lcv, 0x5410), b2_prmt(ecu, ecv, 0x5410));
+  const bool lane_ok = xh + 8 <= wv;
   if (top_ok) {
     const uint32_t xc = b2_hi8(cq.ts);
     const uint32_t u2[4] = {b2_hi8(au.tf), b2_hi8(au.ts), b2_hi8(bu.tf), b2_prmt(xc, b2_hi8(bu.ts), 0x5410)};
     const uint32_t v2[4] = {b2_hi8(av.tf), b2_hi8(av.ts), b2_hi8(bv.tf), b2_prmt(xc, b2_hi8(bv.ts), 0x5432)};
-    emit_row8_packed<ST, HAS_ALPHA>(yt, at, u2, v2, dtp, kc, xs, xl.w0, xl.w1);
+    emit_row8_packed<ST, HAS_ALPHA>(yt, at, u2, v2, drt + xh * kBpp, lane_ok, kc, xs, xl.w0, xl.w1);
   }
   if (bot_ok) {
     const uint32_t xc = b2_hi8(cq.bs);
     const uint32_t u2[4] = {b2_hi8(au.bf), b2_hi8(au.bs), b2_hi8(bu.bf), b2_prmt(xc, b2_hi8(bu.bs), 0x5410)};
     const uint32_t v2[4] = {b2_hi8(av.bf), b2_hi8(av.bs), b2_hi8(bv.bf), b2_prmt(xc, b2_hi8(bv.bs), 0x5432)};
-    emit_row8_packed<ST, HAS_ALPHA>(yb, ab, u2, v2, dbp, kc, xs ? xs + 1024 : nullptr, xl.w0, xl.w1);
+    emit_row8_packed<ST, HAS_ALPHA>(yb, ab, u2, v2, drb + xh * kBpp, lane_ok, kc, xs + 1024, xl.w0, xl.w1);
   }
-  if (xs != nullptr) {
+  if (kBpp == 4) {
     __syncwarp();
+    const int xa = xpass + lane * 4;  // this lane stores pixels xa..xa+3 and xa+128..xa+131
+    const bool ok0 = xa + 4 <= wv, ok1 = xa + 132 <= wv;
     if (top_ok) {
-      uint8_t* d = dtp - lane * 16;  // row start of this pass + lane * 16
-      b2_stg_stream_v4(d, *reinterpret_cast<const uint4*>(xs + xl.r));
-      b2_stg_stream_v4(d + 512, *reinterpret_cast<const uint4*>(xs + 512 + xl.r));
+      uint8_t* d = drt + xa * 4;
+      if (ok0) b2_stg_stream_v4(d, *reinterpret_cast<const uint4*>(xs + xl.r));
+      if (ok1) b2_stg_stream_v4(d + 512, *reinterpret_cast<const uint4*>(xs + 512 + xl.r));
     }
     if (bot_ok) {
-      uint8_t* d = dbp - lane * 16;
-      b2_stg_stream_v4(d, *reinterpret_cast<const uint4*>(xs + 1024 + xl.r));
-      b2_stg_stream_v4(d + 512, *reinterpret_cast<const uint4*>(xs + 1536 + xl.r));
+      uint8_t* d = drb + xa * 4;
+      if (ok0) b2_stg_stream_v4(d, *reinterpret_cast<const uint4*>(xs + 1024 + xl.r));
+      if (ok1) b2_stg_stream_v4(d + 512, *reinterpret_cast<const uint4*>(xs + 1536 + xl.r));
     }
     __syncwarp();
   }
@@ -425,7 +434,7 @@ __device__ __forceinline__ void convert8(const uint8_t* sy, const uint8_t* sa, c
 template <int ST, bool HAS_ALPHA>
 __global__ void __launch_bounds__(kBulkThreads, kBulkCtasPerSm)
 upsample_bulk_kernel(const UpsampleJobDev* __restrict__ jobs, const uint32_t* __restrict__ unit_prefix,
-                     uint32_t n_jobs, uint32_t uniform_units, uint32_t total_units) {
+                     uint32_t n_jobs, uint32_t uniform_units, uint32_t total_units, const B2YuvConsts kc) {
   using BL = BulkLayout<HAS_ALPHA>;
   constexpr int kTileW = BL::kTW;
   __shared__ __align__(128) uint8_t ring[kBulkWarps * 2 * BL::kBytes];
@@ -502,12 +511,11 @@ upsample_bulk_kernel(const UpsampleJobDev* __restrict__ jobs, const uint32_t* __
   };
 
   // ---- consumer ----
-  // The three register constants of the conversion; made opaque so they stay in
-  // registers instead of being rematerialised before every use.
+  // kc: the three non-immediate constants of the conversion arrive as kernel
+  // parameters, so they are constant-bank operands instead of registers that ptxas
+  // would rematerialise with a move before every use.
   const XposeLane xl = xpose_lane(lane);
   uint8_t* const xbuf = xpose + warp * 2048;
-  B2YuvConsts kc = b2_yuv_consts();
-  asm volatile("" : "+r"(kc.yoff), "+r"(kc.kr), "+r"(kc.kb));
   uint32_t c_unit = first_unit;
   producer_setup();
   producer_issue(0);
@@ -521,38 +529,30 @@ upsample_bulk_kernel(const UpsampleJobDev* __restrict__ jobs, const uint32_t* __
     const int rt = 2 * (int)q - 1, rb = 2 * (int)q;
     const bool top_ok = (rt >= 0), bot_ok = (rb < height);
     const int dstride = jp->dst_stride;
-    constexpr int kBpp = (ST == ST_RGB || ST == ST_BGR) ? 3 : 4;
-    uint8_t* dtp = jp->dst + (ptrdiff_t)(top_ok ? rt : rb) * dstride + lane * (8 * kBpp);
-    uint8_t* dbp = jp->dst + (ptrdiff_t)(bot_ok ? rb : rt) * dstride + lane * (8 * kBpp);
+    const int wv = width & ~7;  // the vector path covers pixels [0, wv)
+    uint8_t* const drt = jp->dst + (ptrdiff_t)(top_ok ? rt : rb) * dstride;
+    uint8_t* const drb = jp->dst + (ptrdiff_t)(bot_ok ? rb : rt) * dstride;
     const int tiles = (width + kTileW - 1) / kTileW;
-    int x0 = lane * 8;
     for (int t = 0; t < tiles; ++t) {
       producer_issue(stage ^ 1);  // the other stage was released by the __syncwarp below
       mbar_wait(bar_s + 8 * stage, (phase >> stage) & 1);
       phase ^= 1u << stage;
       const uint8_t* sp = wring + stage * BL::kBytes;
 #pragma unroll kPassUnroll
-      for (int half = 0; half < kTileW / 256; ++half) {
-        const int xh = x0 + half * 256;
-        if (xh + 8 <= width) {
-          const int c0 = xh >> 1;
-          const int loff = (c0 == 0) ? 0 : -1;          // left neighbour, mirrored at column 0
-          const int roff = (c0 + 4 >= uw) ? 3 : 4;      // right neighbour, mirrored at the last column
-          convert8<ST, HAS_ALPHA>(sp + BL::kY + half * 256 + lane * 8, sp + BL::kA + half * 256 + lane * 8,
-                                  sp + BL::kC + 16 + half * 128 + lane * 4, loff, roff, top_ok, bot_ok,
-                                  dtp + half * (256 * kBpp), dbp + half * (256 * kBpp), kc,
-                                  (kBpp == 4 && xh - lane * 8 + 256 <= width) ? xbuf : nullptr, xl, lane);
-        } else if (xh < width) {  // ragged right edge: per-pixel path straight from global
-          const UpsampleJobDev j = *jp;
-          for (int x = xh; x < width; ++x) {
-            if (top_ok) pixel_generic<ST>(j, rt, x);
-            if (bot_ok) pixel_generic<ST>(j, rb, x);
-          }
-        }
+      for (int p = 0; p < kTileW / 256; ++p) {
+        const int xpass = t * kTileW + p * 256;
+        if (xpass < wv)
+          convert_pass<ST, HAS_ALPHA>(sp + BL::kY + p * 256 + lane * 8, sp + BL::kA + p * 256 + lane * 8,
+                                      sp + BL::kC + 16 + p * 128 + lane * 4, lane, xpass, wv, uw, top_ok, bot_ok,
+                                      drt, drb, kc, xbuf, xl);
       }
       __syncwarp();  // every lane is done reading this stage before it is refilled
-      dtp += kBpp * kTileW; dbp += kBpp * kTileW; x0 += kTileW;
       stage ^= 1;
+    }
+    if (wv + lane < width) {  // ragged right edge (width % 8 pixels): per-pixel path straight from global
+      const UpsampleJobDev j = *jp;
+      if (top_ok) pixel_generic<ST>(j, rt, wv + lane);
+      if (bot_ok) pixel_generic<ST>(j, rb, wv + lane);
     }
     c_unit += unit_stride;
   }
@@ -649,7 +649,7 @@ extern "C" int b2_yuv420a_to_rgba_fancy(b2_ctx* ctx, int stream, const b2_upsamp
     const int bgrid = b2_grid_for(ctx, kBulkCtasPerSm, (utotal + kBulkWarps - 1) / kBulkWarps);
     const uint32_t ut = (uint32_t)utotal;
     const bool ha = n_with_a != 0;
-#define B2_UPK(ST_, HA_) upsample_bulk_kernel<ST_, HA_><<<bgrid, kBulkThreads, 0, s>>>(djobs, dupre, n_jobs, uuniform, ut)
+#define B2_UPK(ST_, HA_) upsample_bulk_kernel<ST_, HA_><<<bgrid, kBulkThreads, 0, s>>>(djobs, dupre, n_jobs, uuniform, ut, b2_yuv_consts())
     switch (st_mode) {
       case ST_RGBA: if (ha) B2_UPK(ST_RGBA, true); else B2_UPK(ST_RGBA, false); break;
       case ST_BGRA: if (ha) B2_UPK(ST_BGRA, true); else B2_UPK(ST_BGRA, false); break;

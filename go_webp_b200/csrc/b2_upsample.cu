@@ -268,7 +268,11 @@ __device__ __forceinline__ void emit_row8_packed(uint2 yw, uint2 aw, const uint3
       w[3 * h + 1] = b2_prmt(q[1], q[2], 0x5421);
       w[3 * h + 2] = b2_prmt(q[2], q[3], 0x6542);
     }
-    if (store_ok) {
+    if (xs != nullptr) {  // warp-uniform: a full pass goes through the transposition buffer, 24 bytes per lane
+      *reinterpret_cast<uint2*>(xs + xw0) = make_uint2(w[0], w[1]);
+      *reinterpret_cast<uint2*>(xs + xw0 + 8) = make_uint2(w[2], w[3]);
+      *reinterpret_cast<uint2*>(xs + xw0 + 16) = make_uint2(w[4], w[5]);
+    } else if (store_ok) {
       b2_stg_stream_v2(dp, make_uint2(w[0], w[1]));
       b2_stg_stream_v2(dp + 8, make_uint2(w[2], w[3]));
       b2_stg_stream_v2(dp + 16, make_uint2(w[4], w[5]));
@@ -401,17 +405,22 @@ __device__ __forceinline__ void convert_pass(const uint8_t* sy, const uint8_t* s
   const B2Quad16 cq = b2_interp16(b2_prmt(ltu, ltv, 0x5410), b2_prmt(etu, etv, 0x5410),
                                   b2_prmt(lcu, lcv, 0x5410), b2_prmt(ecu, ecv, 0x5410));
   const bool lane_ok = xh + 8 <= wv;
+  // 3-byte modes: only full passes are transposed (768 contiguous bytes per row); the
+  // last, partial pass of a row stores straight from the lanes
+  const bool full3 = (kBpp == 3) && (xpass + 256 <= wv);
+  uint8_t* const xst = (kBpp == 4 || full3) ? xs : nullptr;
+  const uint32_t xw0 = (kBpp == 4) ? xl.w0 : (uint32_t)lane * 24u;
   if (top_ok) {
     const uint32_t xc = b2_hi8(cq.ts);
     const uint32_t u2[4] = {b2_hi8(au.tf), b2_hi8(au.ts), b2_hi8(bu.tf), b2_prmt(xc, b2_hi8(bu.ts), 0x5410)};
     const uint32_t v2[4] = {b2_hi8(av.tf), b2_hi8(av.ts), b2_hi8(bv.tf), b2_prmt(xc, b2_hi8(bv.ts), 0x5432)};
-    emit_row8_packed<ST, HAS_ALPHA>(yt, at, u2, v2, drt + xh * kBpp, lane_ok, kc, xs, xl.w0, xl.w1);
+    emit_row8_packed<ST, HAS_ALPHA>(yt, at, u2, v2, drt + xh * kBpp, lane_ok, kc, xst, xw0, xl.w1);
   }
   if (bot_ok) {
     const uint32_t xc = b2_hi8(cq.bs);
     const uint32_t u2[4] = {b2_hi8(au.bf), b2_hi8(au.bs), b2_hi8(bu.bf), b2_prmt(xc, b2_hi8(bu.bs), 0x5410)};
     const uint32_t v2[4] = {b2_hi8(av.bf), b2_hi8(av.bs), b2_hi8(bv.bf), b2_prmt(xc, b2_hi8(bv.bs), 0x5432)};
-    emit_row8_packed<ST, HAS_ALPHA>(yb, ab, u2, v2, drb + xh * kBpp, lane_ok, kc, xs + 1024, xl.w0, xl.w1);
+    emit_row8_packed<ST, HAS_ALPHA>(yb, ab, u2, v2, drb + xh * kBpp, lane_ok, kc, xst ? xst + 1024 : nullptr, xw0, xl.w1);
   }
   if (kBpp == 4) {
     __syncwarp();
@@ -426,6 +435,20 @@ __device__ __forceinline__ void convert_pass(const uint8_t* sy, const uint8_t* s
       uint8_t* d = drb + xa * 4;
       if (ok0) b2_stg_stream_v4(d, *reinterpret_cast<const uint4*>(xs + 1024 + xl.r));
       if (ok1) b2_stg_stream_v4(d + 512, *reinterpret_cast<const uint4*>(xs + 1536 + xl.r));
+    }
+    __syncwarp();
+  } else if (full3) {
+    __syncwarp();
+    const uint32_t ro = (uint32_t)lane * 16u;  // 768 bytes per row: chunk `lane`, and chunk 32 + lane for lanes < 16
+    if (top_ok) {
+      uint8_t* d = drt + xpass * 3 + ro;
+      b2_stg_stream_v4(d, *reinterpret_cast<const uint4*>(xs + ro));
+      if (lane < 16) b2_stg_stream_v4(d + 512, *reinterpret_cast<const uint4*>(xs + 512 + ro));
+    }
+    if (bot_ok) {
+      uint8_t* d = drb + xpass * 3 + ro;
+      b2_stg_stream_v4(d, *reinterpret_cast<const uint4*>(xs + 1024 + ro));
+      if (lane < 16) b2_stg_stream_v4(d + 512, *reinterpret_cast<const uint4*>(xs + 1536 + ro));
     }
     __syncwarp();
   }
@@ -617,7 +640,7 @@ extern "C" int b2_yuv420a_to_rgba_fancy(b2_ctx* ctx, int stream, const b2_upsamp
     if (j.a != NULL && (((uintptr_t)j.a | (uintptr_t)(uint32_t)j.a_stride) & 7) != 0) fast = false;
     d.flags = fast ? JOB_FAST : 0;
     if (!fast && bpp == 4) tuned = false;
-    if (bpp == 3 && ((((uintptr_t)j.dst | (uintptr_t)(uint32_t)j.dst_stride) & 7) != 0)) tuned = false;
+    if (bpp == 3 && ((((uintptr_t)j.dst | (uintptr_t)(uint32_t)j.dst_stride) & 15) != 0)) tuned = false;
     if ((((uintptr_t)j.y | (uintptr_t)j.u | (uintptr_t)j.v | (uintptr_t)j.a | (uintptr_t)(uint32_t)j.y_stride |
           (uintptr_t)(uint32_t)j.uv_stride | (uintptr_t)(uint32_t)(j.a ? j.a_stride : 0)) & 15) != 0 ||
         j.y_stride < 0 || j.uv_stride < 0 || (j.a && j.a_stride < 0)) staged = false;

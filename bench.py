@@ -236,17 +236,25 @@ def other_kernels(ctx, peak, steps):
         return ctx.elapsed_ms(2, 3) / n_steps
 
     k = max(3, min(steps, 20))
-    up = UpsamplePipeline(ctx, 64, 3840, 2160, _abi.MODE_RGBA, with_alpha=False, host=False)
-    up.fill_synthetic(0xB2000004)
-    ms = timed(up.run_device, k)
-    px = 64 * 3840 * 2160
-    out["fancy_upsample_4k_rgba"] = {"frames": 64, "mpixel_per_s": px / ms / 1e3, "bytes_per_px": 5.5,
-                                     "gbs": px * 5.5 / ms / 1e6, "frac": px * 5.5 / ms / 1e6 / peak}
-    up.close()
+    for name, frames, w, h, mode, wa, bpp in [
+            ("fancy_upsample_4k_rgba", 64, 3840, 2160, _abi.MODE_RGBA, False, 5.5),
+            ("fancy_upsample_4k_bgra_with_alpha_plane", 32, 3840, 2160, _abi.MODE_BGRA, True, 6.5),
+            ("fancy_upsample_4k_rgb", 32, 3840, 2160, _abi.MODE_RGB, False, 4.5),
+            ("fancy_upsample_1080p_rgba", 128, 1920, 1080, _abi.MODE_RGBA, False, 5.5)]:
+        up = UpsamplePipeline(ctx, frames, w, h, mode, with_alpha=wa, host=False)
+        up.fill_synthetic(0xB2000004)
+        ms = timed(up.run_device, k)
+        px = frames * w * h
+        out[name] = {"frames": frames, "mpixel_per_s": px / ms / 1e3, "bytes_per_px": bpp,
+                     "gbs": px * bpp / ms / 1e6, "frac": px * bpp / ms / 1e6 / peak}
+        up.close()
     for op, bits, bpp, name in [("inverse_chain", 5, 8.0039, "vp8l_crosscolor_inv_addgreen_fused"),
+                                ("forward_chain", 5, 8.0039, "vp8l_subgreen_crosscolor_fwd_fused"),
                                 ("add_green", 0, 8.0, "vp8l_add_green"),
                                 ("color_index_inverse", 0, 8.0, "vp8l_color_index_8bit"),
-                                ("color_index_inverse", 2, 5.0, "vp8l_color_index_2bit")]:
+                                ("color_index_inverse", 1, 6.0, "vp8l_color_index_4bit"),
+                                ("color_index_inverse", 2, 5.0, "vp8l_color_index_2bit"),
+                                ("color_index_inverse", 3, 4.5, "vp8l_color_index_1bit")]:
         ap = ArgbPipeline(ctx, 16, 4096, 4096, op, bits)
         ap.fill_synthetic(0xB2000003)
         ms = timed(ap.run_device, k)

@@ -40,6 +40,24 @@ class ArgbJob(C.Structure):
                 ("reserved", C.c_int32)]
 
 
+class PlainJob(C.Structure):
+    _fields_ = [("argb", C.c_void_p), ("y", C.c_void_p), ("u", C.c_void_p), ("v", C.c_void_p),
+                ("a", C.c_void_p), ("argb_stride", C.c_int32), ("y_stride", C.c_int32),
+                ("uv_stride", C.c_int32), ("a_stride", C.c_int32), ("width", C.c_int32),
+                ("height", C.c_int32), ("y_pos", C.c_int32), ("reserved", C.c_int32)]
+
+
+class AlphaIndexJob(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("palette", C.c_void_p),
+                ("width", C.c_int32), ("height", C.c_int32), ("bits", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class ExpandJob(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("num_colors", C.c_int32),
+                ("bits", C.c_int32)]
+
+
 # every symbol include/b2webp.h declares: name -> (restype, argtypes)
 _vp = C.c_void_p
 _ctx = C.c_void_p
@@ -77,6 +95,9 @@ SYMBOLS = {
     "b2_vp8l_forward_chain": (C.c_int, [_ctx, C.c_int, C.POINTER(ArgbJob), C.c_int]),
     "b2_vp8l_color_index_inverse": (C.c_int, [_ctx, C.c_int, C.POINTER(ArgbJob), C.c_int]),
     "b2_vp8l_bundle_color_map": (C.c_int, [_ctx, C.c_int, C.POINTER(ArgbJob), C.c_int]),
+    "b2_argb_to_yuva_plain": (C.c_int, [_ctx, C.c_int, C.POINTER(PlainJob), C.c_int]),
+    "b2_vp8l_color_index_inverse_alpha": (C.c_int, [_ctx, C.c_int, C.POINTER(AlphaIndexJob), C.c_int]),
+    "b2_vp8l_expand_color_map": (C.c_int, [_ctx, C.c_int, C.POINTER(ExpandJob), C.c_int]),
     "b2_synth_fill_batch_u32": (C.c_int, [_ctx, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_size_t,
                                           C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]),
 }
@@ -103,7 +124,7 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)  # AttributeError if the export is missing
             fn.restype = res
             fn.argtypes = args
-        if lib.b2_abi_version() != 0x0101:
+        if lib.b2_abi_version() != 0x0102:
             raise ImportError("libb2webp.so ABI version mismatch; rebuild")
         _LIB = lib
     return _LIB

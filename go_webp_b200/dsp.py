@@ -147,6 +147,105 @@ def VP8LMapColor32b(src: np.ndarray, color_map: np.ndarray, y_start: int, y_end:
     return _run("color_index_inverse", [(src, src.shape, pal, width, y_end - y_start, 0)])[0]
 
 
+def _simple(fn_name: str, job_type, uploads, make_job, out_nbytes: int, out_dtype, out_shape, ctx=None):
+    """Upload 'uploads' (arrays), run one job, download one output."""
+    ctx = ctx or default_context()
+    ar = _arena(ctx)
+    ar.reset(sum(_al(a.nbytes) for a in uploads) + _al(out_nbytes))
+    ptrs = []
+    for a in uploads:
+        pa = ar.take(_al(a.nbytes))
+        ctx._chk(ctx.lib.b2_h2d_async(ctx.h, 0, pa, a.ctypes.data, a.nbytes))
+        ptrs.append(pa)
+    po = ar.take(_al(out_nbytes))
+    job = make_job(ptrs, po)
+    ctx._chk(getattr(ctx.lib, fn_name)(ctx.h, 0, (job_type * 1)(job), 1))
+    out = np.empty(out_shape, out_dtype)
+    ctx._chk(ctx.lib.b2_d2h_async(ctx.h, 0, out.ctypes.data, po, out_nbytes))
+    ctx.sync()
+    return out
+
+
+def VP8LColorIndexInverseTransformAlpha(transform: VP8LTransform, y_start: int, y_end: int,
+                                        src: np.ndarray) -> np.ndarray:
+    """lossless.go:461-505 (MapAlpha_C for bits == 0): 8-bit source rows of
+    VP8LSubSampleSize(xsize, bits) bytes -> 8-bit rows of xsize bytes holding the
+    green byte of the palette entry (VP8GetAlphaValue, lossless_common.go:31)."""
+    rows, w, bits = y_end - y_start, transform.xsize, transform.bits
+    sw = VP8LSubSampleSize(w, bits)
+    srcb = np.ascontiguousarray(src, np.uint8).reshape(rows, sw)
+    pal = np.zeros(1 << (8 >> bits), np.uint32)
+    cm = np.ascontiguousarray(transform.data, np.uint32).reshape(-1)
+    pal[:min(cm.size, pal.size)] = cm[:pal.size]
+    return _simple("b2_vp8l_color_index_inverse_alpha", _abi.AlphaIndexJob, [srcb, pal],
+                   lambda p, po: _abi.AlphaIndexJob(p[0], po, p[1], w, rows, bits, 0),
+                   rows * w, np.uint8, (rows, w))
+
+
+def VP8LMapColor8b(src: np.ndarray, color_map: np.ndarray, y_start: int, y_end: int, width: int) -> np.ndarray:
+    """VP8LMapAlphaFunc (lossless.h.go:41); MapAlpha_C lossless.go:461-472."""
+    t = VP8LTransform(COLOR_INDEXING_TRANSFORM, 0, width, y_end, color_map)
+    return VP8LColorIndexInverseTransformAlpha(t, y_start, y_end, src)
+
+
+def ExpandColorMap(num_colors: int, transform: VP8LTransform) -> np.ndarray:
+    """pkg/vp8/vp8l_dec.c.go:1196-1219: un-delta the palette read from the bitstream
+    and zero-pad it to 1 << (8 >> bits) entries; returns the new colour map (the
+    reference stores it back into transform.data)."""
+    bits = transform.bits
+    final = 1 << (8 >> bits)
+    data = np.ascontiguousarray(transform.data, np.uint32).reshape(-1)[:num_colors]
+    return _simple("b2_vp8l_expand_color_map", _abi.ExpandJob, [data],
+                   lambda p, po: _abi.ExpandJob(p[0], po, num_colors, bits), final * 4, np.uint32, (final,))
+
+
+def ConvertToYUVA(argb: np.ndarray, with_alpha: bool = False, y_pos: int = 0, u=None, v=None):
+    """ConvertToYUVA (pkg/vp8/vp8l_dec.c.go:543-562) over rows y_pos .. y_pos + h - 1:
+    every row through WebPConvertARGBToY and WebPConvertARGBToUV (pkg/libwebp/dsp/
+    yuv.go:74-120; rows at even positions store U/V, rows at odd positions average
+    into them), alpha = byte 3 when asked.  argb: [h, w] uint32 0xAARRGGBB.  When
+    y_pos is odd, u / v must hold the chroma rows stored by the previous call (first
+    row = chroma row y_pos >> 1).  Returns (y, u, v, a-or-None)."""
+    argb = np.ascontiguousarray(argb, np.uint32)
+    h, w = argb.shape
+    uw, uh = (w + 1) // 2, (h + (y_pos & 1) + 1) // 2
+    ctx = default_context()
+    ar = _arena(ctx)
+    sizes = [_al(argb.nbytes), _al(w * h), _al(uw * uh), _al(uw * uh), _al(w * h)]
+    ar.reset(sum(sizes))
+    ps, py, pu, pv, pa = (ar.take(n) for n in sizes)
+    ctx._chk(ctx.lib.b2_h2d_async(ctx.h, 0, ps, argb.ctypes.data, argb.nbytes))
+    if y_pos & 1:
+        for plane, ptr in ((u, pu), (v, pv)):
+            prev = np.ascontiguousarray(plane, np.uint8).reshape(-1)[:uw]
+            ctx._chk(ctx.lib.b2_h2d_async(ctx.h, 0, ptr, prev.ctypes.data, prev.nbytes))
+    job = _abi.PlainJob(ps, py, pu, pv, pa if with_alpha else None, w, w, uw, w, w, h, y_pos, 0)
+    ctx._chk(ctx.lib.b2_argb_to_yuva_plain(ctx.h, 0, (_abi.PlainJob * 1)(job), 1))
+    outs = [np.empty((h, w), np.uint8), np.empty((uh, uw), np.uint8), np.empty((uh, uw), np.uint8)]
+    for o, p_ in zip(outs, (py, pu, pv)):
+        ctx._chk(ctx.lib.b2_d2h_async(ctx.h, 0, o.ctypes.data, p_, o.nbytes))
+    a = None
+    if with_alpha:
+        a = np.empty((h, w), np.uint8)
+        ctx._chk(ctx.lib.b2_d2h_async(ctx.h, 0, a.ctypes.data, pa, a.nbytes))
+    ctx.sync()
+    return outs[0], outs[1], outs[2], a
+
+
+def WebPConvertARGBToY(argb: np.ndarray, width: int) -> np.ndarray:
+    """pkg/libwebp/dsp/yuv.go:74-80 for one row."""
+    row = np.ascontiguousarray(argb, np.uint32).reshape(-1)[:width].reshape(1, width)
+    return ConvertToYUVA(row)[0][0]
+
+
+def WebPConvertARGBToUV(argb: np.ndarray, u: np.ndarray, v: np.ndarray, src_width: int, do_store: bool):
+    """pkg/libwebp/dsp/yuv.go:82-120 for one row: returns the new (u, v) rows; with
+    do_store false the previous values are averaged in, (old + new + 1) >> 1."""
+    row = np.ascontiguousarray(argb, np.uint32).reshape(-1)[:src_width].reshape(1, src_width)
+    _, nu, nv, _ = ConvertToYUVA(row, y_pos=0 if do_store else 1, u=u, v=v)
+    return nu[0], nv[0]
+
+
 def VP8LBundleColorMap(row: np.ndarray, width: int, xbits: int) -> np.ndarray:
     """lossless_enc.go:293-312 for one row (or a [h, w] block of rows)."""
     idx = np.ascontiguousarray(row, np.uint8)

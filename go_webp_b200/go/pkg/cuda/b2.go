@@ -279,3 +279,82 @@ func (c *Context) VP8L(stream int, op VP8LOp, jobs []ArgbJob) error {
 	}
 	return status(c, st)
 }
+
+// PlainJob is one chunk of rows of the non-gamma ARGB -> YUVA conversion (device
+// pointers; Argb/Y/A at row YPos, U/V at chroma row YPos>>1).
+type PlainJob struct {
+	Argb                          DevicePtr
+	Y, U, V, A                    DevicePtr
+	ArgbStride                    int // pixels
+	YStride, UVStride, AStride    int
+	Width, Height, YPos           int
+}
+
+// ArgbToYUVAPlain replaces WebPConvertARGBToY / WebPConvertARGBToUV
+// (pkg/libwebp/dsp/yuv.go:74-120) as driven by ConvertToYUVA
+// (pkg/vp8/vp8l_dec.c.go:543-562) for a batch.
+func (c *Context) ArgbToYUVAPlain(stream int, jobs []PlainJob) error {
+	if len(jobs) == 0 {
+		return nil
+	}
+	cj := make([]C.b2_plain_job, len(jobs))
+	for i, j := range jobs {
+		cj[i] = C.b2_plain_job{
+			argb: (*C.uint32_t)(unsafe.Pointer(uintptr(j.Argb))),
+			y:    (*C.uint8_t)(unsafe.Pointer(uintptr(j.Y))),
+			u:    (*C.uint8_t)(unsafe.Pointer(uintptr(j.U))),
+			v:    (*C.uint8_t)(unsafe.Pointer(uintptr(j.V))),
+			a:    (*C.uint8_t)(unsafe.Pointer(uintptr(j.A))),
+			argb_stride: C.int32_t(j.ArgbStride), y_stride: C.int32_t(j.YStride),
+			uv_stride: C.int32_t(j.UVStride), a_stride: C.int32_t(j.AStride),
+			width: C.int32_t(j.Width), height: C.int32_t(j.Height), y_pos: C.int32_t(j.YPos),
+		}
+	}
+	return status(c, C.b2_argb_to_yuva_plain(c.h, C.int(stream), &cj[0], C.int(len(cj))))
+}
+
+// AlphaIndexJob is one 8-bit plane of VP8LColorIndexInverseTransformAlpha.
+type AlphaIndexJob struct {
+	Src, Dst, Palette      DevicePtr
+	Width, Height, Bits    int
+}
+
+// ColorIndexInverseAlpha replaces VP8LColorIndexInverseTransformAlpha / MapAlpha_C
+// (pkg/libwebp/dsp/lossless.go:461-505) for a batch.
+func (c *Context) ColorIndexInverseAlpha(stream int, jobs []AlphaIndexJob) error {
+	if len(jobs) == 0 {
+		return nil
+	}
+	cj := make([]C.b2_alpha_index_job, len(jobs))
+	for i, j := range jobs {
+		cj[i] = C.b2_alpha_index_job{
+			src:     (*C.uint8_t)(unsafe.Pointer(uintptr(j.Src))),
+			dst:     (*C.uint8_t)(unsafe.Pointer(uintptr(j.Dst))),
+			palette: (*C.uint32_t)(unsafe.Pointer(uintptr(j.Palette))),
+			width:   C.int32_t(j.Width), height: C.int32_t(j.Height), bits: C.int32_t(j.Bits),
+		}
+	}
+	return status(c, C.b2_vp8l_color_index_inverse_alpha(c.h, C.int(stream), &cj[0], C.int(len(cj))))
+}
+
+// ExpandJob is one palette of ExpandColorMap.
+type ExpandJob struct {
+	Src, Dst           DevicePtr
+	NumColors, Bits    int
+}
+
+// ExpandColorMap replaces ExpandColorMap (pkg/vp8/vp8l_dec.c.go:1196-1219) for a batch.
+func (c *Context) ExpandColorMap(stream int, jobs []ExpandJob) error {
+	if len(jobs) == 0 {
+		return nil
+	}
+	cj := make([]C.b2_expand_job, len(jobs))
+	for i, j := range jobs {
+		cj[i] = C.b2_expand_job{
+			src: (*C.uint32_t)(unsafe.Pointer(uintptr(j.Src))),
+			dst: (*C.uint32_t)(unsafe.Pointer(uintptr(j.Dst))),
+			num_colors: C.int32_t(j.NumColors), bits: C.int32_t(j.Bits),
+		}
+	}
+	return status(c, C.b2_vp8l_expand_color_map(c.h, C.int(stream), &cj[0], C.int(len(cj))))
+}

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define B2_ABI_VERSION 0x0101
+#define B2_ABI_VERSION 0x0102
 
 typedef enum b2_status {
   B2_OK = 0,
@@ -182,6 +182,58 @@ int b2_vp8l_color_index_inverse(b2_ctx* ctx, int stream, const b2_argb_job* jobs
  * pixel, row stride == width, passed through the src pointer), dst rows are
  * ceil(width/2^bits) uint32. */
 int b2_vp8l_bundle_color_map(b2_ctx* ctx, int stream, const b2_argb_job* jobs, int n_jobs);
+
+/* ---- remaining rows of the hot-path table (a14, a28, a29) ----- */
+
+/* Non-gamma ARGB -> Y, U, V (+A): WebPConvertARGBToY / WebPConvertARGBToUV
+ * (pkg/libwebp/dsp/yuv.go:74-120) applied row by row exactly as ConvertToYUVA does
+ * (pkg/vp8/vp8l_dec.c.go:543-562): even rows store U/V from 2-pixel sums, odd rows
+ * average into them with (u + tmp + 1) >> 1; A = byte 3 of every pixel when a != NULL
+ * (WebPExtractAlpha, alpha_processing.go:193-207).  Pixels are uint32 0xAARRGGBB;
+ * argb_stride is in pixels, the plane strides in bytes.  DEVICE pointers.
+ * The job covers rows y_pos .. y_pos + height - 1 of the output (ConvertToYUVA's y_pos):
+ * argb, y and a point at row y_pos, u and v at chroma row y_pos >> 1.  When y_pos is odd
+ * the first row averages into the U/V values an earlier call stored, exactly like the
+ * streamed reference. */
+typedef struct b2_plain_job {
+  const uint32_t* argb;
+  uint8_t* y;
+  uint8_t* u;
+  uint8_t* v;
+  uint8_t* a; /* may be NULL */
+  int32_t argb_stride;
+  int32_t y_stride, uv_stride, a_stride;
+  int32_t width, height;
+  int32_t y_pos;
+  int32_t reserved;
+} b2_plain_job;
+int b2_argb_to_yuva_plain(b2_ctx* ctx, int stream, const b2_plain_job* jobs, int n_jobs);
+
+/* VP8LColorIndexInverseTransformAlpha / MapAlpha_C (pkg/libwebp/dsp/lossless.go:
+ * 461-505; caller pkg/vp8/vp8l_dec.c.go:816-838): 8-bit source plane whose bytes pack
+ * 1 << bits indices, 8-bit destination = green byte of the palette entry.  src rows
+ * are ceil(width / 2^bits) bytes, dst rows width bytes, both tightly packed; palette
+ * holds 1 << (8 >> bits) entries; bits in [0,3]; dst must not alias src. */
+typedef struct b2_alpha_index_job {
+  const uint8_t* src;
+  uint8_t* dst;
+  const uint32_t* palette;
+  int32_t width, height;
+  int32_t bits;
+  int32_t reserved;
+} b2_alpha_index_job;
+int b2_vp8l_color_index_inverse_alpha(b2_ctx* ctx, int stream, const b2_alpha_index_job* jobs, int n_jobs);
+
+/* ExpandColorMap (pkg/vp8/vp8l_dec.c.go:1196-1219): src = num_colors delta-coded
+ * entries, dst = 1 << (8 >> bits) entries: byte-wise running sum (VP8LAddPixels,
+ * lossless_common.go:110-114) then zero padding.  dst may equal src. */
+typedef struct b2_expand_job {
+  const uint32_t* src;
+  uint32_t* dst;
+  int32_t num_colors;
+  int32_t bits;
+} b2_expand_job;
+int b2_vp8l_expand_color_map(b2_ctx* ctx, int stream, const b2_expand_job* jobs, int n_jobs);
 
 /* ---- synthetic inputs (SURVEY.md 8d generator, identical to the oracle's) -
  * One uint32 per (row, word) position of n images laid out 'image_bytes'

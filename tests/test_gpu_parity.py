@@ -395,3 +395,92 @@ def test_synth_generator_matches_oracle(gpu):
         got = ctx.d2h(buf.ptr, 4 * w * h * n).view(np.uint32).reshape(n, h, w)
         for i in range(n):
             assert (got[i] == oracle.synth_u32(0xB2000002, 5 + i, 1, w, h, mode)).all()
+
+
+# ---- rows a14, a28, a29 of the hot-path table --------------------------------------
+def _oracle_to_yuva(argb):
+    """ConvertToYUVA (vp8l_dec.c.go:543-562) row by row with the oracle's row functions."""
+    h, w = argb.shape
+    uw = (w + 1) // 2
+    y = np.stack([oracle.argb_to_y(argb[r]) for r in range(h)])
+    u = np.zeros(((h + 1) // 2, uw), np.uint8)
+    v = np.zeros_like(u)
+    for r in range(h):
+        u[r >> 1], v[r >> 1] = oracle.argb_to_uv(argb[r], u[r >> 1], v[r >> 1], do_store=(r & 1) == 0)
+    return y, u, v, (argb >> 24).astype(np.uint8)
+
+
+@pytest.mark.parametrize("size", [(1, 1), (2, 2), (3, 3), (5, 4), (7, 9), (64, 32), (129, 7), (260, 5), (1024, 3)])
+def test_argb_to_yuva_plain(gpu, size):
+    D = gpu["dsp"]
+    w, h = size
+    rng = np.random.default_rng(w * 31 + h)
+    argb = rng.integers(0, 2**32, (h, w), dtype=np.uint32)
+    ey, eu, ev, ea = _oracle_to_yuva(argb)
+    y, u, v, a = D.ConvertToYUVA(argb, with_alpha=True)
+    assert (y == ey).all() and (u == eu).all() and (v == ev).all() and (a == ea).all()
+    # streamed the way ExportYUVA feeds it: arbitrary row chunks, odd y_pos averaging
+    # into the chroma stored by the previous call (yuv.go:100-102)
+    u2 = np.zeros_like(eu)
+    v2 = np.zeros_like(ev)
+    pos = 0
+    for n in [1, 2, 3, 1, 5, 1 << 20]:
+        if pos >= h:
+            break
+        n = min(n, h - pos)
+        cy, cu, cv, _ = D.ConvertToYUVA(argb[pos:pos + n], y_pos=pos, u=u2[pos >> 1], v=v2[pos >> 1])
+        assert (cy == ey[pos:pos + n]).all()
+        u2[pos >> 1:(pos >> 1) + cu.shape[0]] = cu
+        v2[pos >> 1:(pos >> 1) + cv.shape[0]] = cv
+        pos += n
+    assert (u2 == eu).all() and (v2 == ev).all()
+    # the row functions under the reference's names
+    assert (D.WebPConvertARGBToY(argb[0], w) == ey[0]).all()
+    ru, rv = D.WebPConvertARGBToUV(argb[h - 1], eu[0], ev[0], w, False)
+    xu, xv = oracle.argb_to_uv(argb[h - 1], eu[0], ev[0], do_store=False)
+    assert (ru == xu).all() and (rv == xv).all()
+
+
+@pytest.mark.parametrize("bits", [0, 1, 2, 3])
+def test_color_index_inverse_alpha(gpu, bits):
+    D = gpu["dsp"]
+    rng = np.random.default_rng(40 + bits)
+    ncol = 1 << (8 >> bits)
+    for (w, h) in [(1, 1), (3, 2), (7, 3), (8, 1), (33, 5), (128, 4), (257, 3), (4100, 2)]:
+        pal = rng.integers(0, 2**32, ncol, dtype=np.uint32)
+        sw = D.VP8LSubSampleSize(w, bits)
+        src = rng.integers(0, 256, (h, sw), dtype=np.uint8)
+        t = D.VP8LTransform(D.COLOR_INDEXING_TRANSFORM, bits, w, h, pal)
+        got = D.VP8LColorIndexInverseTransformAlpha(t, 0, h, src)
+        assert (got == oracle.color_index_inverse_alpha(src, pal, bits, w)).all(), (w, h, bits)
+    pal = rng.integers(0, 2**32, 256, dtype=np.uint32)
+    src = rng.integers(0, 256, (3, 50), dtype=np.uint8)
+    assert (D.VP8LMapColor8b(src, pal, 0, 3, 50) == oracle.color_index_inverse_alpha(src, pal, 0, 50)).all()
+
+
+def test_expand_color_map(gpu):
+    D = gpu["dsp"]
+    rng = np.random.default_rng(5)
+    # bits from the colour count exactly as vp8l_dec.c.go:1248-1254
+    for ncol in [1, 2, 3, 4, 5, 15, 16, 17, 100, 255, 256]:
+        bits = 0 if ncol > 16 else 1 if ncol > 4 else 2 if ncol > 2 else 3
+        data = rng.integers(0, 2**32, ncol, dtype=np.uint32)
+        t = D.VP8LTransform(D.COLOR_INDEXING_TRANSFORM, bits, 10, 10, data)
+        assert (D.ExpandColorMap(ncol, t) == oracle.expand_color_map(data, bits)).all(), ncol
+
+
+def test_new_entry_points_reject_bad_arguments(gpu):
+    A = gpu["abi"]
+    ctx = gpu["ctx"]
+    lib = ctx.lib
+    buf = ctx.alloc(4096)
+    j = A.AlphaIndexJob(buf.ptr, buf.ptr + 1024, buf.ptr + 2048, 8, 8, 4, 0)   # bits out of range
+    assert lib.b2_vp8l_color_index_inverse_alpha(ctx.h, 0, (A.AlphaIndexJob * 1)(j), 1) == A.B2_ERR_INVALID_CONFIG
+    j = A.AlphaIndexJob(buf.ptr, buf.ptr, buf.ptr + 2048, 8, 8, 0, 0)          # in place
+    assert lib.b2_vp8l_color_index_inverse_alpha(ctx.h, 0, (A.AlphaIndexJob * 1)(j), 1) == A.B2_ERR_INVALID_CONFIG
+    e = A.ExpandJob(buf.ptr, buf.ptr, 17, 1, )                                # 17 colours need bits == 0
+    assert lib.b2_vp8l_expand_color_map(ctx.h, 0, (A.ExpandJob * 1)(e), 1) == A.B2_ERR_INVALID_CONFIG
+    p = A.PlainJob(buf.ptr, buf.ptr, buf.ptr, buf.ptr, None, 4, 8, 4, 8, 8, 8, 0, 0)  # stride < width
+    assert lib.b2_argb_to_yuva_plain(ctx.h, 0, (A.PlainJob * 1)(p), 1) == A.B2_ERR_BAD_DIM
+    assert lib.b2_argb_to_yuva_plain(ctx.h, 0, None, 1) == A.B2_ERR_NULL
+    buf.free()

@@ -25,17 +25,15 @@ namespace {
 constexpr int kFastThreads = 512;
 constexpr int kFastWarps = kFastThreads / 32;
 constexpr int kFastCtasPerSm = 2;
-constexpr int kSmemBytes = 256 * 256;  // 64 KB
 
-// shared-memory map (byte offsets); row r = bytes [256 r, 256 r + 256)
-//   lower half of every row : g2l[r] << 7, one word per lane
-//   upper half, rows   0.. 31: LinearToGamma base'' per lane
-//   upper half, rows  32.. 63: LinearToGamma slope d per lane
-//   upper half, rows  64.. 95: exact-division magic numbers, entry a at word a
-//   upper half, rows  96..127: kInvAlpha (binary-compatible divide mode)
-constexpr uint32_t kOffL2GD = 32 * 256;
-constexpr uint32_t kOffMagic = 64 * 256 + 128;
-constexpr uint32_t kOffInvA = 96 * 256 + 128;
+// shared-memory map (byte offsets)
+//   [0, 64K)    g2l rows: row v = 256 bytes, lower half = g2l[v] << 7, one word per lane
+//   [64K, 72K)  LinearToGamma: entry pos = 256 bytes, lane l at +8 l: {base' << 7, slope d}
+//   [72K, 80K)  divide table, entry a at +8 a: exact mode {magic << 3, shift}, binary-
+//               compatible mode {kInvAlpha[a], 0}
+constexpr uint32_t kOffL2G = 65536;
+constexpr uint32_t kOffDiv = kOffL2G + 32 * 256;
+constexpr int kSmemBytes = kOffDiv + 1024 * 8;  // 80 KB
 
 template <int ORDER> struct Ch;
 template <> struct Ch<0> {  // R,G,B,A bytes
@@ -68,13 +66,12 @@ template <int K>
 __device__ __forceinline__ uint32_t g2l(const uint8_t* smem, uint32_t p, uint32_t lane4) {
   return lds32(smem, __byte_perm(p, lane4, 0x5504 | (K << 4)));
 }
-// LinearToGamma (yuv.go:187-202) on a sum held << 7: index = byte 2 of the sum.
-// Returns the 10-bit gamma-domain value.
-__device__ __forceinline__ int l2g(const uint8_t* smem, uint32_t s7, uint32_t lane4hi) {
-  const uint32_t off = __byte_perm(s7, lane4hi, 0x5524);
-  const int base = (int)lds32(smem, off);
-  const int d = (int)lds32(smem, off + kOffL2GD);
-  return (base + d * (int)s7) >> 14;
+// LinearToGamma (yuv.go:187-202) on a sum held << 7: index = byte 2 of the sum, base
+// and slope come in one 64-bit load.  Returns the 10-bit gamma-domain value.
+__device__ __forceinline__ int l2g(const uint8_t* smem, uint32_t s7, uint32_t lane8) {
+  const uint32_t off = __byte_perm(s7, lane8, 0x5524);
+  const int2 bd = *reinterpret_cast<const int2*>(smem + kOffL2G + off);
+  return (bd.x + bd.y * (int)s7) >> 14;
 }
 // RGBToU / RGBToV on gamma-domain sums (conversion.go:51-69, rounding YUV_HALF<<2),
 // scaled by 64: the result is byte 3.  Inputs are <= 1020 so ClipUV never clamps.
@@ -90,18 +87,22 @@ __device__ __forceinline__ uint32_t v_sum(int r, int g, int b) {
 }
 
 // DIVIDE_BY_ALPHA (yuv.go:231) on w7 = (sum of alpha_i * linear_i) << 7; returns the
-// quotient << 7 ready for l2g().
-__device__ __forceinline__ uint32_t div_alpha7(const uint8_t* smem, uint32_t w7, uint32_t magic,
-                                               uint32_t inva, bool table) {
-  if (table) return (((w7 >> 7) * inva) >> 17) << 7;      // libwebp-binary kInvAlpha form
-  const uint32_t q = __umulhi(w7 << 3, magic & 0x07ffffffu) >> (magic >> 27);  // exact 4*sum/a
-  return q << 7;
+// quotient << 7 ready for l2g().  dv = this divisor's table entry.
+template <bool TABLE>
+__device__ __forceinline__ uint32_t div_alpha7(uint32_t w7, uint2 dv) {
+  if (TABLE) return (((w7 >> 7) * dv.x) >> 17) << 7;   // libwebp-binary kInvAlpha form
+  return (__umulhi(w7, dv.x) >> dv.y) << 7;            // exact 4*sum/a: magic multiply-high
 }
 
 // Linear sums (<< 7) of one 2x2 block for the three channels.
-template <int ORDER, bool ALPHA>
+// Exact-divide mode is branch-free across the warp: when any lane holds a translucent
+// block every lane takes the weighted form, which is exact for the other blocks too
+// (four alphas of 255: 4*255*S/1020 == S; an all-transparent block is given equal
+// weights, any equal weights reproduce SUM4, yuv.go:249-252).  The binary-compatible
+// table divide is not exact for opaque blocks, so that mode branches per lane.
+template <int ORDER, bool ALPHA, bool TABLE>
 __device__ __forceinline__ void block_sums(const uint8_t* smem, uint32_t lane4, uint32_t pa, uint32_t pb,
-                                           uint32_t pc, uint32_t pd, uint32_t al4, bool table,
+                                           uint32_t pc, uint32_t pd, uint32_t al4,
                                            uint32_t* sr, uint32_t* sg, uint32_t* sb) {
   const uint32_t ra = g2l<Ch<ORDER>::kR>(smem, pa, lane4), rb = g2l<Ch<ORDER>::kR>(smem, pb, lane4);
   const uint32_t rc = g2l<Ch<ORDER>::kR>(smem, pc, lane4), rd = g2l<Ch<ORDER>::kR>(smem, pd, lane4);
@@ -109,27 +110,27 @@ __device__ __forceinline__ void block_sums(const uint8_t* smem, uint32_t lane4, 
   const uint32_t gc = g2l<1>(smem, pc, lane4), gd = g2l<1>(smem, pd, lane4);
   const uint32_t ba = g2l<Ch<ORDER>::kB>(smem, pa, lane4), bb = g2l<Ch<ORDER>::kB>(smem, pb, lane4);
   const uint32_t bc = g2l<Ch<ORDER>::kB>(smem, pc, lane4), bd = g2l<Ch<ORDER>::kB>(smem, pd, lane4);
-  if (!ALPHA || al4 == 0xffffffffu || al4 == 0u) {  // yuv.go:249 / :270
+  const bool plain = !ALPHA || al4 == 0xffffffffu || al4 == 0u;  // yuv.go:249 / :270
+  if (!ALPHA || (TABLE ? plain : __all_sync(0xffffffffu, plain))) {
     *sr = ra + rb + rc + rd;
     *sg = ga + gb + gc + gd;
     *sb = ba + bb + bc + bd;
   } else {                                           // yuv.go:233-241,254-256
-    const uint32_t a0 = al4 & 0xff, a1 = (al4 >> 8) & 0xff, a2 = (al4 >> 16) & 0xff, a3 = al4 >> 24;
-    const uint32_t asum = __dp4a(al4, 0x01010101u, 0u);
-    const uint32_t toff = ((asum >> 5) << 8) | ((asum & 31u) << 2);
-    const uint32_t magic = lds32(smem, toff + kOffMagic);
-    const uint32_t inva = lds32(smem, toff + kOffInvA);
-    *sr = div_alpha7(smem, a0 * ra + a1 * rb + a2 * rc + a3 * rd, magic, inva, table);
-    *sg = div_alpha7(smem, a0 * ga + a1 * gb + a2 * gc + a3 * gd, magic, inva, table);
-    *sb = div_alpha7(smem, a0 * ba + a1 * bb + a2 * bc + a3 * bd, magic, inva, table);
+    const uint32_t al = (!TABLE && al4 == 0u) ? 0xffffffffu : al4;
+    const uint32_t a0 = al & 0xff, a1 = (al >> 8) & 0xff, a2 = (al >> 16) & 0xff, a3 = al >> 24;
+    const uint32_t asum = __dp4a(al, 0x01010101u, 0u);
+    const uint2 dv = *reinterpret_cast<const uint2*>(smem + kOffDiv + asum * 8u);
+    *sr = div_alpha7<TABLE>(a0 * ra + a1 * rb + a2 * rc + a3 * rd, dv);
+    *sg = div_alpha7<TABLE>(a0 * ga + a1 * gb + a2 * gc + a3 * gd, dv);
+    *sb = div_alpha7<TABLE>(a0 * ba + a1 * bb + a2 * bc + a3 * bd, dv);
   }
 }
 
-template <int ORDER, bool ALPHA, bool WRITE_A>
+template <int ORDER, bool ALPHA, bool WRITE_A, bool TABLE>
 __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm)
 import_fast_kernel(const ImportJobDev* __restrict__ jobs, const uint32_t* __restrict__ unit_prefix,
                    uint32_t n_jobs, uint32_t uniform_units, uint32_t total_units,
-                   const uint32_t* __restrict__ tab, int div_table, int32_t* __restrict__ has_alpha) {
+                   const uint32_t* __restrict__ tab, int32_t* __restrict__ has_alpha) {
   extern __shared__ __align__(256) uint8_t smem[];
   for (int i = threadIdx.x; i < 256 * 32; i += kFastThreads) {
     *reinterpret_cast<uint32_t*>(smem + (i >> 5) * 256 + (i & 31) * 4) = __ldg(tab + B2_TAB_G2L + (i >> 5)) << 7;
@@ -138,21 +139,24 @@ import_fast_kernel(const ImportJobDev* __restrict__ jobs, const uint32_t* __rest
     const int pos = i >> 5;
     const int base = (int)__ldg(tab + B2_TAB_L2G + 2 * pos) * 128;  // base' << 7
     const int d = (int)__ldg(tab + B2_TAB_L2G + 2 * pos + 1);
-    *reinterpret_cast<int*>(smem + pos * 256 + 128 + (i & 31) * 4) = base;
-    *reinterpret_cast<int*>(smem + kOffL2GD + pos * 256 + 128 + (i & 31) * 4) = d;
+    *reinterpret_cast<int2*>(smem + kOffL2G + pos * 256 + (i & 31) * 8) = make_int2(base, d);
   }
   for (int i = threadIdx.x; i < 1024; i += kFastThreads) {
-    const uint32_t off = ((i >> 5) << 8) | ((i & 31) << 2);
-    *reinterpret_cast<uint32_t*>(smem + off + kOffMagic) = __ldg(tab + B2_TAB_MAGIC + i);
-    *reinterpret_cast<uint32_t*>(smem + off + kOffInvA) = __ldg(tab + B2_TAB_INVA + i);
+    uint2 e;
+    if (TABLE) {
+      e = make_uint2(__ldg(tab + B2_TAB_INVA + i), 0u);
+    } else {
+      const uint32_t m = __ldg(tab + B2_TAB_MAGIC + i);  // M | L << 27, M < 2^26: umulhi(w << 3, M) == umulhi(w, M << 3)
+      e = make_uint2((m & 0x07ffffffu) << 3, m >> 27);
+    }
+    *reinterpret_cast<uint2*>(smem + kOffDiv + i * 8) = e;
   }
   __syncthreads();
 
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t lane4 = lane * 4;
-  const uint32_t lane4hi = lane4 + 128;
+  const uint32_t lane8 = lane * 8;
   const uint32_t warp = threadIdx.x >> 5;
-  const bool table = div_table != 0;
 
   for (uint32_t unit = blockIdx.x * kFastWarps + warp; unit < total_units; unit += gridDim.x * kFastWarps) {
     uint32_t rp;
@@ -174,32 +178,35 @@ import_fast_kernel(const ImportJobDev* __restrict__ jobs, const uint32_t* __rest
     uint8_t* vp = jp->v + uvo;
     uint32_t and_acc = 0xffffffffu;
 
+    // One 128-pixel strip per iteration, the next strip's loads in flight meanwhile.
+    // Lanes past the end of the row run on zeros (every lane takes part in the vote of
+    // block_sums) and store nothing.
     int x = (int)lane4;
-    uint4 c0, c1;
+    uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0;
     bool cur_ok = x < width;
     if (cur_ok) { c0 = b2_ldg_stream_v4(s0); c1 = b2_ldg_stream_v4(s1); }
     const int tiles_x = (width + 127) >> 7;
     for (int t = 0; t < tiles_x; ++t) {
       const int xn = x + 128;
       const bool nxt_ok = xn < width;
-      uint4 n0, n1;
+      uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;
       if (nxt_ok) { n0 = b2_ldg_stream_v4(s0 + 512); n1 = b2_ldg_stream_v4(s1 + 512); }
+      const uint32_t yw0 = pack_b2(luma_sum<ORDER>(c0.x), luma_sum<ORDER>(c0.y), luma_sum<ORDER>(c0.z), luma_sum<ORDER>(c0.w));
+      const uint32_t yw1 = pack_b2(luma_sum<ORDER>(c1.x), luma_sum<ORDER>(c1.y), luma_sum<ORDER>(c1.z), luma_sum<ORDER>(c1.w));
+      uint32_t ap0 = 0xffffffffu, ap1 = 0xffffffffu;
+      if (ALPHA) {
+        ap0 = pack_b3(c0.x, c0.y, c0.z, c0.w);
+        ap1 = pack_b3(c1.x, c1.y, c1.z, c1.w);
+        if (cur_ok) and_acc &= ap0 & ap1;
+      }
+      uint32_t sr0, sg0, sb0, sr1, sg1, sb1;
+      block_sums<ORDER, ALPHA, TABLE>(smem, lane4, c0.x, c0.y, c1.x, c1.y, __byte_perm(ap0, ap1, 0x5410), &sr0, &sg0, &sb0);
+      block_sums<ORDER, ALPHA, TABLE>(smem, lane4, c0.z, c0.w, c1.z, c1.w, __byte_perm(ap0, ap1, 0x7632), &sr1, &sg1, &sb1);
+      const int r0 = l2g(smem, sr0, lane8), g0 = l2g(smem, sg0, lane8), b0 = l2g(smem, sb0, lane8);
+      const int r1 = l2g(smem, sr1, lane8), g1 = l2g(smem, sg1, lane8), b1 = l2g(smem, sb1, lane8);
+      const uint32_t uu = __byte_perm(u_sum(r0, g0, b0), u_sum(r1, g1, b1), 0x0073);
+      const uint32_t vv = __byte_perm(v_sum(r0, g0, b0), v_sum(r1, g1, b1), 0x0073);
       if (cur_ok) {
-        const uint32_t yw0 = pack_b2(luma_sum<ORDER>(c0.x), luma_sum<ORDER>(c0.y), luma_sum<ORDER>(c0.z), luma_sum<ORDER>(c0.w));
-        const uint32_t yw1 = pack_b2(luma_sum<ORDER>(c1.x), luma_sum<ORDER>(c1.y), luma_sum<ORDER>(c1.z), luma_sum<ORDER>(c1.w));
-        uint32_t ap0 = 0xffffffffu, ap1 = 0xffffffffu;
-        if (ALPHA) {
-          ap0 = pack_b3(c0.x, c0.y, c0.z, c0.w);
-          ap1 = pack_b3(c1.x, c1.y, c1.z, c1.w);
-          and_acc &= ap0 & ap1;
-        }
-        uint32_t sr0, sg0, sb0, sr1, sg1, sb1;
-        block_sums<ORDER, ALPHA>(smem, lane4, c0.x, c0.y, c1.x, c1.y, __byte_perm(ap0, ap1, 0x5410), table, &sr0, &sg0, &sb0);
-        block_sums<ORDER, ALPHA>(smem, lane4, c0.z, c0.w, c1.z, c1.w, __byte_perm(ap0, ap1, 0x7632), table, &sr1, &sg1, &sb1);
-        const int r0 = l2g(smem, sr0, lane4hi), g0 = l2g(smem, sg0, lane4hi), b0 = l2g(smem, sb0, lane4hi);
-        const int r1 = l2g(smem, sr1, lane4hi), g1 = l2g(smem, sg1, lane4hi), b1 = l2g(smem, sb1, lane4hi);
-        const uint32_t uu = __byte_perm(u_sum(r0, g0, b0), u_sum(r1, g1, b1), 0x0073);
-        const uint32_t vv = __byte_perm(v_sum(r0, g0, b0), v_sum(r1, g1, b1), 0x0073);
         b2_stg_stream_u32(yp, yw0);
         if (has_row1) b2_stg_stream_u32(yp + ystride, yw1);
         if (WRITE_A) {
@@ -219,16 +226,23 @@ import_fast_kernel(const ImportJobDev* __restrict__ jobs, const uint32_t* __rest
   }
 }
 
+template <int ORDER, bool ALPHA, bool WRITE_A, bool TABLE>
+cudaError_t launch1(int grid, cudaStream_t s, const ImportJobDev* jobs, const uint32_t* unit_prefix,
+                    uint32_t n_jobs, uint32_t uniform_units, uint32_t total_units, const uint32_t* tab,
+                    int32_t* has_alpha) {
+  auto k = import_fast_kernel<ORDER, ALPHA, WRITE_A, TABLE>;
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  if (e != cudaSuccess) return e;
+  k<<<grid, kFastThreads, kSmemBytes, s>>>(jobs, unit_prefix, n_jobs, uniform_units, total_units, tab, has_alpha);
+  return cudaGetLastError();
+}
 template <int ORDER, bool ALPHA, bool WRITE_A>
 cudaError_t launch(int grid, cudaStream_t s, const ImportJobDev* jobs, const uint32_t* unit_prefix,
                    uint32_t n_jobs, uint32_t uniform_units, uint32_t total_units, const uint32_t* tab,
                    int div_table, int32_t* has_alpha) {
-  auto k = import_fast_kernel<ORDER, ALPHA, WRITE_A>;
-  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-  if (e != cudaSuccess) return e;
-  k<<<grid, kFastThreads, kSmemBytes, s>>>(jobs, unit_prefix, n_jobs, uniform_units, total_units, tab,
-                                            div_table, has_alpha);
-  return cudaGetLastError();
+  // the divide mode only matters when alpha is imported
+  if (ALPHA && div_table) return launch1<ORDER, ALPHA, WRITE_A, true>(grid, s, jobs, unit_prefix, n_jobs, uniform_units, total_units, tab, has_alpha);
+  return launch1<ORDER, ALPHA, WRITE_A, false>(grid, s, jobs, unit_prefix, n_jobs, uniform_units, total_units, tab, has_alpha);
 }
 
 }  // namespace

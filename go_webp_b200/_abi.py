@@ -95,6 +95,8 @@ SYMBOLS = {
     "b2_vp8l_forward_chain": (C.c_int, [_ctx, C.c_int, C.POINTER(ArgbJob), C.c_int]),
     "b2_vp8l_color_index_inverse": (C.c_int, [_ctx, C.c_int, C.POINTER(ArgbJob), C.c_int]),
     "b2_vp8l_bundle_color_map": (C.c_int, [_ctx, C.c_int, C.POINTER(ArgbJob), C.c_int]),
+    "b2_vp8l_predictor_inverse": (C.c_int, [_ctx, C.c_int, C.POINTER(ArgbJob), C.c_int]),
+    "b2_vp8l_predictor_forward": (C.c_int, [_ctx, C.c_int, C.POINTER(ArgbJob), C.c_int]),
     "b2_argb_to_yuva_plain": (C.c_int, [_ctx, C.c_int, C.POINTER(PlainJob), C.c_int]),
     "b2_vp8l_color_index_inverse_alpha": (C.c_int, [_ctx, C.c_int, C.POINTER(AlphaIndexJob), C.c_int]),
     "b2_vp8l_expand_color_map": (C.c_int, [_ctx, C.c_int, C.POINTER(ExpandJob), C.c_int]),

@@ -246,6 +246,15 @@ def WebPConvertARGBToUV(argb: np.ndarray, u: np.ndarray, v: np.ndarray, src_widt
     return nu[0], nv[0]
 
 
+def VP8LPredictorForward(argb: np.ndarray, modes: np.ndarray, bits: int) -> np.ndarray:
+    """Residuals of a whole image for GIVEN predictor modes: PredictorSub0..13_C
+    (lossless_enc.go:339-557) driven as predictor_enc.go:666-712 does.  argb: [h, w]
+    uint32; modes: the mode image (mode in bits 8..11)."""
+    src = np.ascontiguousarray(argb, np.uint32)
+    h, w = src.shape
+    return _run("predictor_forward", [(src, (h, w), modes, w, h, bits)])[0]
+
+
 def VP8LBundleColorMap(row: np.ndarray, width: int, xbits: int) -> np.ndarray:
     """lossless_enc.go:293-312 for one row (or a [h, w] block of rows)."""
     idx = np.ascontiguousarray(row, np.uint8)
@@ -282,7 +291,12 @@ def VP8LInverseTransform(transform: VP8LTransform, row_start: int, row_end: int,
         sw = VP8LSubSampleSize(w, transform.bits)
         src = np.ascontiguousarray(in_rows, np.uint32).reshape(rows, sw)
         return _run("color_index_inverse", [(src, (rows, w), transform.data, w, rows, transform.bits)])[0]
-    raise NotImplementedError("PREDICTOR_TRANSFORM inverse is row-serial (SURVEY 8f-1): not on this path yet")
+    if transform.vtype == PREDICTOR_TRANSFORM:
+        if row_start != 0:
+            raise NotImplementedError("predictor inverse needs the rows above: pass the image from row 0")
+        src = np.ascontiguousarray(in_rows, np.uint32).reshape(rows, w)
+        return _run("predictor_inverse", [(src, (rows, w), transform.data, w, rows, transform.bits)])[0]
+    raise ValueError("unknown transform type")
 
 
 def VP8LInverseTransformBatch(imgs, chain, ctx: Context | None = None):
@@ -312,8 +326,10 @@ def VP8LInverseTransformBatch(imgs, chain, ctx: Context | None = None):
                 groups.setdefault("add_green", []).append((i, t))
             elif t.vtype == COLOR_INDEXING_TRANSFORM:
                 groups.setdefault("color_index_inverse", []).append((i, t))
+            elif t.vtype == PREDICTOR_TRANSFORM:
+                groups.setdefault("predictor_inverse", []).append((i, t))
             else:
-                raise NotImplementedError("PREDICTOR_TRANSFORM inverse (SURVEY 8f-1)")
+                raise ValueError("unknown transform type")
         for op, members in groups.items():
             items = []
             for i, t in members:

@@ -183,6 +183,17 @@ int b2_vp8l_color_index_inverse(b2_ctx* ctx, int stream, const b2_argb_job* jobs
  * ceil(width/2^bits) uint32. */
 int b2_vp8l_bundle_color_map(b2_ctx* ctx, int stream, const b2_argb_job* jobs, int n_jobs);
 
+/* ---- next row of the table: VP8L predictor transform -----------
+ * data = mode image, ceil(w/2^bits) x ceil(h/2^bits) words, mode in bits 8..11
+ * (lossless.go:313); bits in [2,9]; dst must not alias src.
+ * Inverse: PredictorInverseTransform_C + PredictorAdd0..13_C over whole images
+ * (pkg/libwebp/dsp/lossless.go:31-333): src = residuals, dst = pixels.  Runs as one
+ * launch per wavefront diagonal (see b2_predict.cu).
+ * Forward: PredictorSub0..13_C with the given modes (lossless_enc.go:339-557, driven as
+ * pkg/libwebp/enc/predictor_enc.go:666-712): src = pixels, dst = residuals. */
+int b2_vp8l_predictor_inverse(b2_ctx* ctx, int stream, const b2_argb_job* jobs, int n_jobs);
+int b2_vp8l_predictor_forward(b2_ctx* ctx, int stream, const b2_argb_job* jobs, int n_jobs);
+
 /* ---- remaining rows of the hot-path table (a14, a28, a29) ----- */
 
 /* Non-gamma ARGB -> Y, U, V (+A): WebPConvertARGBToY / WebPConvertARGBToUV

@@ -484,3 +484,67 @@ def test_new_entry_points_reject_bad_arguments(gpu):
     assert lib.b2_argb_to_yuva_plain(ctx.h, 0, (A.PlainJob * 1)(p), 1) == A.B2_ERR_BAD_DIM
     assert lib.b2_argb_to_yuva_plain(ctx.h, 0, None, 1) == A.B2_ERR_NULL
     buf.free()
+
+
+# ---- predictor transform ----------------------------------------------
+def _rand_modes(rng, w, h, bits, modes=None):
+    tw, th = (w + (1 << bits) - 1) >> bits, (h + (1 << bits) - 1) >> bits
+    m = rng.integers(0, 16, (th, tw), dtype=np.uint32) if modes is None else rng.choice(modes, (th, tw)).astype(np.uint32)
+    return (m << 8) | 0xff000000 | rng.integers(0, 256, (th, tw), dtype=np.uint32)  # other bits are ignored
+
+
+@pytest.mark.parametrize("bits", [2, 3, 5])
+def test_predictor_inverse_and_forward(gpu, bits):
+    """All 14 predictors (+ the two aliases of mode 0), ragged tiles, images narrower and
+    wider than one 128-column wavefront tile, shorter and taller than one 32-row band."""
+    D = gpu["dsp"]
+    rng = np.random.default_rng(100 + bits)
+    for (w, h) in [(1, 1), (1, 5), (2, 2), (5, 1), (7, 9), (33, 34), (64, 65), (127, 3), (129, 40),
+                   (200, 33), (300, 70), (513, 97)]:
+        modes = _rand_modes(rng, w, h, bits)
+        img = rng.integers(0, 2**32, (h, w), dtype=np.uint32)
+        t = D.VP8LTransform(D.PREDICTOR_TRANSFORM, bits, w, h, modes)
+        got = D.VP8LInverseTransform(t, 0, h, img)
+        assert (got == oracle.predictor_inverse(img, modes, bits)).all(), (w, h, bits)
+        fwd = D.VP8LPredictorForward(img, modes, bits)
+        assert (fwd == oracle.predictor_forward(img, modes, bits)).all(), (w, h, bits)
+        # inverse(forward(x)) == x, the identity the codec relies on
+        assert (D.VP8LInverseTransform(t, 0, h, fwd) == img).all(), (w, h, bits)
+
+
+@pytest.mark.parametrize("mode", list(range(14)))
+def test_predictor_each_mode_alone(gpu, mode):
+    D = gpu["dsp"]
+    rng = np.random.default_rng(mode)
+    w, h, bits = 150, 45, 4
+    modes = _rand_modes(rng, w, h, bits, [mode])
+    # smooth-ish content plus extremes so the clamped / select predictors hit both branches
+    img = rng.integers(0, 2**32, (h, w), dtype=np.uint32)
+    img[::3] &= 0x0f0f0f0f
+    img[1::5] |= 0xf0f0f0f0
+    t = D.VP8LTransform(D.PREDICTOR_TRANSFORM, bits, w, h, modes)
+    assert (D.VP8LInverseTransform(t, 0, h, img) == oracle.predictor_inverse(img, modes, bits)).all()
+    assert (D.VP8LPredictorForward(img, modes, bits) == oracle.predictor_forward(img, modes, bits)).all()
+
+
+def test_predictor_in_batched_chain(gpu):
+    """Full decoder order (vp8l_dec.c.go:710-729): predictor, cross-colour and subtract-green
+    read in that order are undone last-read-first."""
+    D = gpu["dsp"]
+    rng = np.random.default_rng(9)
+    imgs, chains, exp = [], [], []
+    for (w, h) in [(96, 40), (257, 66)]:
+        bits = 3
+        modes = _rand_modes(rng, w, h, bits)
+        codes = rng.integers(0, 2**24, (D.VP8LSubSampleSize(h, bits), D.VP8LSubSampleSize(w, bits)), dtype=np.uint32)
+        px = rng.integers(0, 2**32, (h, w), dtype=np.uint32)
+        chains.append([D.VP8LTransform(D.PREDICTOR_TRANSFORM, bits, w, h, modes),
+                       D.VP8LTransform(D.CROSS_COLOR_TRANSFORM, bits, w, h, codes),
+                       D.VP8LTransform(D.SUBTRACT_GREEN_TRANSFORM, 0, w, h)])
+        imgs.append(D.VP8LImage(px, w, h))
+        e = oracle.add_green(px)
+        e = oracle.color_space_inverse(e, codes, bits)
+        exp.append(oracle.predictor_inverse(e, modes, bits))
+    outs = D.VP8LInverseTransformBatch(imgs, chains)
+    for o, e in zip(outs, exp):
+        assert (o.reshape(e.shape) == e).all()

@@ -254,7 +254,9 @@ def other_kernels(ctx, peak, steps):
                                 ("color_index_inverse", 0, 8.0, "vp8l_color_index_8bit"),
                                 ("color_index_inverse", 1, 6.0, "vp8l_color_index_4bit"),
                                 ("color_index_inverse", 2, 5.0, "vp8l_color_index_2bit"),
-                                ("color_index_inverse", 3, 4.5, "vp8l_color_index_1bit")]:
+                                ("color_index_inverse", 3, 4.5, "vp8l_color_index_1bit"),
+                                ("predictor_forward", 5, 8.0039, "vp8l_predictor_forward"),
+                                ("predictor_inverse", 5, 8.0039, "vp8l_predictor_inverse_wavefront")]:
         ap = ArgbPipeline(ctx, 16, 4096, 4096, op, bits)
         ap.fill_synthetic(0xB2000003)
         ms = timed(ap.run_device, k)

@@ -16,9 +16,9 @@
 //     SKEWED columns k = c + 2r: at step k every lane has its left / top-left / top /
 //     top-right neighbours ready (TR comes from the lane above by one shuffle, the
 //     rest are its own history), and all 32 lanes are busy on every step;
-//   * a band is cut into tiles of 128 skewed columns; tile (i, j) depends on tiles
-//     (i, j-1), (i-1, j) and (i-1, j+1), so all tiles with 2i + j == d are independent:
-//     one launch per diagonal d, no flags, no spinning, every dependency satisfied by
+//   * a band is cut into tiles of 32 skewed columns; tile (i, j) depends on tiles
+//     (i, j-1) and (i-1, j .. j+2), so all tiles with 3i + j == d are independent: one
+//     launch per diagonal d, no flags, no spinning, every dependency satisfied by
 //     stream order.  Tile boundaries read their neighbours back from the output image.
 #include <stdlib.h>
 
@@ -33,7 +33,7 @@ struct PredJobDev {
   int32_t width, height, bits;
   uint32_t tiles_per_row;  // mode image row length
   uint32_t bands;          // ceil(height / 32)
-  uint32_t ktiles;         // skewed tiles per band: ceil((width + 62) / 128)
+  uint32_t ktiles;         // skewed tiles per band: ceil((width + 62) / kTileK)
 };
 
 // ---- pixel arithmetic (lossless_common.go:110-121, lossless.go:31-149) -----------
@@ -55,27 +55,32 @@ __device__ __forceinline__ uint32_t select_px(uint32_t a, uint32_t b, uint32_t c
   const int d = (int)__vsadu4(b, c) - (int)__vsadu4(a, c);  // per-byte sums of absolute differences
   return (d <= 0) ? a : b;
 }
-// ClampedAddSubtractFull (lossless.go:64-73): per channel clip255(a + b - c)
+// ClampedAddSubtractFull (lossless.go:64-73): per channel clip255(a + b - c), two
+// channels per 16-bit-lane word: a + b + (255 - c) needs no borrow, then one packed
+// add-min-relu subtracts the 255 again and clamps to [0, 255].
 __device__ __forceinline__ uint32_t clamp_add_sub_full(uint32_t a, uint32_t b, uint32_t c) {
-  uint32_t out = 0;
-#pragma unroll
-  for (int sh = 0; sh < 32; sh += 8) {
-    const int v = (int)((a >> sh) & 0xff) + (int)((b >> sh) & 0xff) - (int)((c >> sh) & 0xff);
-    out |= (uint32_t)min(max(v, 0), 255) << sh;
-  }
-  return out;
+  constexpr uint32_t m = 0x00ff00ffu;
+  const uint32_t lo = (a & m) + (b & m) + ((c & m) ^ m);
+  const uint32_t hi = ((a >> 8) & m) + ((b >> 8) & m) + (((c >> 8) & m) ^ m);
+  const uint32_t rl = __viaddmin_s16x2_relu(lo, 0xff01ff01u, m);   // + (-255), min 255, max 0
+  const uint32_t rh = __viaddmin_s16x2_relu(hi, 0xff01ff01u, m);
+  return rl | (rh << 8);
 }
-// ClampedAddSubtractHalf (lossless.go:79-89): per channel clip255(ave + (ave - c) / 2), C division
+// ClampedAddSubtractHalf (lossless.go:79-89): per channel clip255(ave + (ave - c) / 2)
+// with C's truncating division.  With e = ave - c + 256 in [1, 511]:
+// trunc((ave - c) / 2) = ((e + 1 - (e >> 8)) >> 1) - 128.
 __device__ __forceinline__ uint32_t clamp_add_sub_half(uint32_t a, uint32_t b, uint32_t c) {
+  constexpr uint32_t m = 0x00ff00ffu;
   const uint32_t ave = avg2(a, b);
-  uint32_t out = 0;
+  uint32_t r[2];
 #pragma unroll
-  for (int sh = 0; sh < 32; sh += 8) {
-    const int av = (int)((ave >> sh) & 0xff), cv = (int)((c >> sh) & 0xff);
-    const int v = av + (av - cv) / 2;
-    out |= (uint32_t)min(max(v, 0), 255) << sh;
+  for (int k = 0; k < 2; ++k) {
+    const uint32_t av = (ave >> (8 * k)) & m, cv = (c >> (8 * k)) & m;
+    const uint32_t e = av + (cv ^ m) + 0x00010001u;                 // ave - c + 256 per lane
+    const uint32_t h = ((e + 0x00010001u - ((e >> 8) & 0x00010001u)) >> 1) & 0x01ff01ffu;
+    r[k] = __viaddmin_s16x2_relu(av + h, 0xff80ff80u, m);           // - 128, clamp to [0, 255]
   }
-  return out;
+  return r[0] | (r[1] << 8);
 }
 // VP8LPredictor0..13_C (lossless.go:113-149); modes 14, 15 alias 0 (table of 16).
 __device__ __forceinline__ uint32_t predict(uint32_t mode, uint32_t l, uint32_t tl, uint32_t t, uint32_t tr) {
@@ -99,42 +104,74 @@ __device__ __forceinline__ uint32_t predict(uint32_t mode, uint32_t l, uint32_t 
 
 // ---- forward ----------------------------------------------------------------------
 constexpr int kFwdThreads = 256;
+// item = 1024 consecutive pixels of the flat image, 4 per thread.  With width % 4 == 0
+// and aligned images a thread's 4 pixels share a row and a mode tile (bits >= 2): two
+// 128-bit loads (current and upper row) plus three scalar neighbours, one 128-bit store.
 __global__ void __launch_bounds__(kFwdThreads, 8)
 predictor_forward_kernel(const PredJobDev* __restrict__ jobs, const uint32_t* __restrict__ prefix,
                          uint32_t n_jobs, uint32_t uniform, uint32_t total_items) {
-  // item = 256 consecutive pixels of the flat image, one per thread
   for (uint32_t item = blockIdx.x; item < total_items; item += gridDim.x) {
     uint32_t local;
     const uint32_t img = b2_find_image(prefix, n_jobs, uniform, item, &local);
     const PredJobDev* __restrict__ j = jobs + img;
     const int w = j->width;
     const size_t n = (size_t)w * j->height;
-    const size_t p = (size_t)local * kFwdThreads + threadIdx.x;
-    if (p >= n) continue;
+    const size_t p0 = ((size_t)local * kFwdThreads + threadIdx.x) * 4;
+    if (p0 >= n) continue;
     const uint32_t* __restrict__ a = j->src;
-    const int y = (int)(p / (uint32_t)w), x = (int)(p - (size_t)y * w);
-    const uint32_t cur = __ldg(a + p);
-    uint32_t pred;
-    if (y == 0) {
-      pred = (x == 0) ? 0xff000000u : __ldg(a + p - 1);          // lossless_enc.go: first row = L
-    } else if (x == 0) {
-      pred = __ldg(a + p - w);                                     // first column = T
+    const bool vec = ((w & 3) == 0) && (((((uintptr_t)a) | ((uintptr_t)j->dst)) & 15) == 0);
+    if (vec) {
+      const int y = (int)(p0 / (uint32_t)w), x = (int)(p0 - (size_t)y * w);
+      const uint4 cv = b2_ldg_stream_v4(a + p0);
+      const uint32_t cur[4] = {cv.x, cv.y, cv.z, cv.w};
+      uint32_t o[4];
+      if (y == 0) {  // first row = L, first pixel = black (lossless_enc.go / predictor_enc.go:683-689)
+        uint32_t l = (x == 0) ? 0xff000000u : __ldg(a + p0 - 1);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { o[k] = sub_pixels(cur[k], l); l = cur[k]; }
+      } else {
+        const uint4 uv = __ldg(reinterpret_cast<const uint4*>(a + p0 - w));
+        // upper[x + 1] of the last column is the first pixel of the current row (contiguous image)
+        const uint32_t up[6] = {(x == 0) ? 0u : __ldg(a + p0 - w - 1), uv.x, uv.y, uv.z, uv.w, __ldg(a + p0 - w + 4)};
+        const uint32_t mode = (__ldg(j->modes + (size_t)(y >> j->bits) * j->tiles_per_row + (x >> j->bits)) >> 8) & 0xf;
+        uint32_t l = (x == 0) ? 0u : __ldg(a + p0 - 1);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t pred = (x + k == 0) ? up[1] : predict(mode, l, up[k], up[k + 1], up[k + 2]);  // first column = T
+          o[k] = sub_pixels(cur[k], pred);
+          l = cur[k];
+        }
+      }
+      b2_stg_stream_v4(j->dst + p0, make_uint4(o[0], o[1], o[2], o[3]));
     } else {
-      const uint32_t mode = (__ldg(j->modes + (size_t)(y >> j->bits) * j->tiles_per_row + (x >> j->bits)) >> 8) & 0xf;
-      // upper[x + 1] of the last column is the first pixel of the current row (contiguous image)
-      pred = predict(mode, __ldg(a + p - 1), __ldg(a + p - w - 1), __ldg(a + p - w), __ldg(a + p - w + 1));
+      for (size_t p = p0; p < min(p0 + 4, n); ++p) {
+        const int y = (int)(p / (uint32_t)w), x = (int)(p - (size_t)y * w);
+        uint32_t pred;
+        if (y == 0) pred = (x == 0) ? 0xff000000u : __ldg(a + p - 1);
+        else if (x == 0) pred = __ldg(a + p - w);
+        else {
+          const uint32_t mode = (__ldg(j->modes + (size_t)(y >> j->bits) * j->tiles_per_row + (x >> j->bits)) >> 8) & 0xf;
+          pred = predict(mode, __ldg(a + p - 1), __ldg(a + p - w - 1), __ldg(a + p - w), __ldg(a + p - w + 1));
+        }
+        j->dst[p] = sub_pixels(__ldg(a + p), pred);
+      }
     }
-    j->dst[p] = sub_pixels(cur, pred);
   }
 }
 
 // ---- inverse ----------------------------------------------------------------------
 constexpr int kInvWarps = 4;
 constexpr int kInvThreads = kInvWarps * 32;
-constexpr int kTileK = 128;  // skewed columns per tile
+constexpr int kTileK = 32;   // skewed columns per tile: the wavefront needs W + 2H steps in all, and the
+                             // diagonal schedule spends (2 H/32 + (W+62)/K) K of them, so small K is optimal
 
-// One launch = one diagonal d: tile (band i, skewed tile j) with 2 i + j == d of every
-// image; grid.y = image, the warps of grid.x enumerate i.
+// Lane 31 of a band runs 62 columns behind lane 0, so lane 0 of tile (i, j) reads the
+// row above up to skewed tile j + kDep of band i - 1: with d = (kDep + 1) i + j every
+// dependency ((i, j-1), (i-1, j .. j+kDep)) lies on an earlier diagonal.
+constexpr uint32_t kDep = (kTileK + 62) / kTileK;
+constexpr uint32_t kDiag = kDep + 1;
+// One launch = one diagonal d of every image; grid.y = image, the warps of grid.x
+// enumerate the bands i that have a tile on it.
 __global__ void __launch_bounds__(kInvThreads, 8)
 predictor_inverse_diag_kernel(const PredJobDev* __restrict__ jobs, uint32_t d) {
   __shared__ uint32_t upper_all[kInvWarps][kTileK + 2];
@@ -142,12 +179,12 @@ predictor_inverse_diag_kernel(const PredJobDev* __restrict__ jobs, uint32_t d) {
   const uint32_t warp = threadIdx.x >> 5;
   const PredJobDev* __restrict__ jp = jobs + blockIdx.y;
   const uint32_t bands = jp->bands, ktiles = jp->ktiles;
-  // bands on this diagonal: i in [i_lo, i_hi], j = d - 2 i in [0, ktiles)
-  const uint32_t i_hi = min(bands - 1, d >> 1);
-  const uint32_t i_lo = (d + 1 > ktiles) ? (d + 1 - ktiles + 1) >> 1 : 0;
+  // tiles on this diagonal: (kDiag i + j == d), j in [0, ktiles)
+  const uint32_t i_hi = min(bands - 1, d / kDiag);
+  const uint32_t i_lo = (d + 1 > ktiles) ? (d + 1 - ktiles + kDiag - 1) / kDiag : 0;
   const uint32_t slot = blockIdx.x * kInvWarps + warp;
   if (i_lo > i_hi || slot > i_hi - i_lo) return;
-  const uint32_t i = i_lo + slot, j = d - 2 * i;
+  const uint32_t i = i_lo + slot, j = d - kDiag * i;
   const int w = jp->width, h = jp->height, bits = jp->bits;
   const int row = (int)i * 32 + lane;
   const bool row_ok = row < h;
@@ -159,7 +196,7 @@ predictor_inverse_diag_kernel(const PredJobDev* __restrict__ jobs, uint32_t d) {
 
   const int k0 = (int)j * kTileK;   // first skewed column of the tile
   int c = k0 - 2 * lane;            // this lane's column at the first step
-  // lane 0's upper row comes from the band above: out[32 i - 1][k0 - 1 .. k0 + 128]
+  // lane 0's upper row comes from the band above: out[32 i - 1][k0 - 1 .. k0 + kTileK]
   if (i > 0) {
     const uint32_t* up = out + (size_t)(i * 32 - 1) * w;
     for (int t = lane; t < kTileK + 2; t += 32) {
@@ -180,39 +217,56 @@ predictor_inverse_diag_kernel(const PredJobDev* __restrict__ jobs, uint32_t d) {
   // what the lane below needs as its first TR: (row, c + 1 - 2) ... = this lane's pixel at c - 1
   last_out = left;
   if (row_ok && c > 0) first_px = out_row[0];  // TR of the last column (lossless.go: upper[x+1] wraps to the row start)
-  uint32_t mode = 0;
-  if (row_ok && c > 0 && c < w) mode = (__ldg(mode_row + (c >> bits)) >> 8) & 0xf;
+  // Predictor mode of the current 2^bits-wide mode tile and of the next one (fetched a
+  // whole tile ahead so its latency never sits on the dependency chain).
   const int tile_mask = (1 << bits) - 1;
-  uint32_t res = (row_ok && c >= 0 && c < w) ? __ldg(in_row + c) : 0u;
+  const int mt_last = (int)jp->tiles_per_row - 1;
+  auto load_mode = [&](int mt) -> uint32_t {
+    return (row_ok && mt >= 0 && mt <= mt_last) ? (__ldg(mode_row + mt) >> 8) & 0xf : 0u;
+  };
+  // (initialised for column c - 1, so that a tile starting exactly on a mode-tile
+  // boundary takes the regular switch on its first step)
+  uint32_t mode = load_mode(max(c - 1, 0) >> bits);
+  uint32_t mode_nxt = load_mode((max(c - 1, 0) >> bits) + 1);
+  // Residuals: a 16-deep ring of scalar prefetches per lane (each lane walks its own
+  // row, so a warp-wide load touches 32 lines; 16 steps of lead hide the DRAM latency).
+  constexpr int kRing = 16;
+  uint32_t ring[kRing];
+#pragma unroll
+  for (int q = 0; q < kRing; ++q) {
+    const int cq = c + q;
+    ring[q] = (row_ok && cq >= 0 && cq < w) ? __ldg(in_row + cq) : 0u;
+  }
 
-  for (int s = 0; s < kTileK; ++s, ++c) {
-    // TR = (row-1, c+1): the lane above finished it on the previous step
-    uint32_t tr = __shfl_up_sync(0xffffffffu, last_out, 1);
-    if (lane == 0) tr = upper[s + 2];
-    const bool live = row_ok && c >= 0 && c < w;
-    // prefetch the next residual and, at a mode-tile boundary, the next mode
-    uint32_t res_next = 0, mode_next = mode;
-    const int cn = c + 1;
-    if (row_ok && cn >= 0 && cn < w) {
-      res_next = __ldg(in_row + cn);
-      if ((cn & tile_mask) == 0 || cn == 1) mode_next = (__ldg(mode_row + (cn >> bits)) >> 8) & 0xf;
+  for (int s0 = 0; s0 < kTileK; s0 += kRing) {
+#pragma unroll
+    for (int q = 0; q < kRing; ++q, ++c) {
+      const int s = s0 + q;
+      // TR = (row-1, c+1): the lane above finished it on the previous step
+      uint32_t tr = __shfl_up_sync(0xffffffffu, last_out, 1);
+      if (lane == 0) tr = upper[s + 2];
+      const uint32_t res = ring[q];
+      const int ca = c + kRing;
+      ring[q] = (row_ok && ca >= 0 && ca < w) ? __ldg(in_row + ca) : 0u;
+      if (c > 0 && (c & tile_mask) == 0) {  // entering the next mode tile
+        mode = mode_nxt;
+        mode_nxt = load_mode((c >> bits) + 1);
+      }
+      if (row_ok && c >= 0 && c < w) {
+        if (c == w - 1) tr = first_px;
+        uint32_t pred;
+        if (row == 0) pred = (c == 0) ? 0xff000000u : left;   // lossless.go:292-295
+        else if (c == 0) pred = t;                               // :312
+        else pred = predict(mode, left, tl, t, tr);
+        const uint32_t o = add_pixels(res, pred);
+        out_row[c] = o;
+        if (c == 0) first_px = o;
+        left = o;
+        last_out = o;
+      }
+      tl = t;
+      t = tr;
     }
-    if (live) {
-      if (c == w - 1) tr = (c == 0) ? 0u : first_px;
-      uint32_t pred;
-      if (row == 0) pred = (c == 0) ? 0xff000000u : left;   // lossless.go:292-295
-      else if (c == 0) pred = t;                               // :312
-      else pred = predict(mode, left, tl, t, tr);
-      const uint32_t o = add_pixels(res, pred);
-      out_row[c] = o;
-      if (c == 0) first_px = o;
-      left = o;
-      last_out = o;
-    }
-    tl = t;
-    t = tr;
-    res = res_next;
-    mode = mode_next;
   }
 }
 
@@ -241,13 +295,13 @@ int prepare_pred(b2_ctx* ctx, int stream, const b2_argb_job* jobs, int n_jobs, c
     d.bands = (uint32_t)((j.height + 31) / 32);
     d.ktiles = (uint32_t)((j.width + 62 + kTileK - 1) / kTileK);
     const uint64_t n = (uint64_t)j.width * (uint64_t)j.height;
-    const uint32_t items = (uint32_t)((n + kFwdThreads - 1) / kFwdThreads);
+    const uint32_t items = (uint32_t)((n + 4 * kFwdThreads - 1) / (4 * kFwdThreads));
     if (i == 0) uni = items; else if (items != uni) uni = 0;
     pre[i] = (uint32_t)tot;
     tot += items;
     if (tot > 0x7fffffffull) { free(host); return B2_ERR_BAD_DIM; }
     if (d.bands > mb) mb = d.bands;
-    const uint32_t diags = 2 * (d.bands - 1) + d.ktiles;
+    const uint32_t diags = kDiag * (d.bands - 1) + d.ktiles;
     if (diags > nd) nd = diags;
   }
   pre[n_jobs] = (uint32_t)tot;

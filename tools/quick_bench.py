@@ -59,7 +59,8 @@ if "upsample" in which:
 if "vp8l" in which:
     for op, bits, bpp in (("inverse_chain", 5, 8.004), ("forward_chain", 5, 8.004), ("color_inverse", 5, 8.004),
                           ("add_green", 0, 8.0), ("sub_green", 0, 8.0), ("color_index_inverse", 0, 8.0),
-                          ("color_index_inverse", 1, 6.0), ("color_index_inverse", 2, 5.0), ("color_index_inverse", 3, 4.5)):
+                          ("color_index_inverse", 1, 6.0), ("color_index_inverse", 2, 5.0), ("color_index_inverse", 3, 4.5),
+                          ("predictor_forward", 5, 8.004), ("predictor_inverse", 5, 8.004)):
         p = ArgbPipeline(ctx, 8, 4096, 4096, op, bits)
         p.fill_synthetic(0xB2000003)
         report(f"vp8l {op} bits={bits} 8x4096^2", 8 * 4096 * 4096, bpp, timed(p.run_device))

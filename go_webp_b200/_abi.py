@@ -31,7 +31,8 @@ class UpsampleJob(C.Structure):
     _fields_ = [("y", C.c_void_p), ("u", C.c_void_p), ("v", C.c_void_p),
                 ("a", C.c_void_p), ("dst", C.c_void_p), ("y_stride", C.c_int32),
                 ("uv_stride", C.c_int32), ("a_stride", C.c_int32),
-                ("dst_stride", C.c_int32), ("width", C.c_int32), ("height", C.c_int32)]
+                ("dst_stride", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
+                ("row_begin", C.c_int32), ("row_end", C.c_int32)]
 
 
 class ArgbJob(C.Structure):
@@ -126,7 +127,7 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)  # AttributeError if the export is missing
             fn.restype = res
             fn.argtypes = args
-        if lib.b2_abi_version() != 0x0102:
+        if lib.b2_abi_version() != 0x0103:
             raise ImportError("libb2webp.so ABI version mismatch; rebuild")
         _LIB = lib
     return _LIB

@@ -33,6 +33,9 @@ struct UpsampleJobDev {
   int32_t width, height;
   uint32_t tiles_x;
   uint32_t flags;
+  int32_t row_begin, row_end;  // output rows to produce (whole image: 0, height)
+  uint32_t q_lo;               // first row-pair unit: (row_begin + 1) >> 1
+  uint32_t pad;
 };
 enum { JOB_FAST = 1 };
 
@@ -131,12 +134,13 @@ upsample_kernel(const UpsampleJobDev* __restrict__ jobs, const uint32_t* __restr
     uint32_t local;
     const uint32_t img = b2_find_image(prefix, n_jobs, uniform, item, &local);
     const UpsampleJobDev j = jobs[img];
-    const uint32_t q = local / j.tiles_x;
-    const uint32_t tx = local - q * j.tiles_x;
+    const uint32_t ql = local / j.tiles_x;
+    const uint32_t tx = local - ql * j.tiles_x;
+    const uint32_t q = ql + j.q_lo;
     const int x0 = (int)tx * kItemW + lane * 8;
     if (x0 >= j.width) continue;
     const int rt = 2 * (int)q - 1, rb = 2 * (int)q;
-    const bool top_ok = (rt >= 0), bot_ok = (rb < j.height);
+    const bool top_ok = (rt >= j.row_begin) && (rt < j.row_end), bot_ok = (rb >= j.row_begin) && (rb < j.row_end);
     constexpr bool kVec = (ST == ST_RGBA || ST == ST_BGRA || ST == ST_ARGB);
     if (!kVec || !(j.flags & JOB_FAST) || x0 + 8 > j.width) {
       const int xe = min(x0 + 8, j.width);
@@ -488,6 +492,7 @@ upsample_bulk_kernel(const UpsampleJobDev* __restrict__ jobs, const uint32_t* __
     uint32_t q;
     const uint32_t img = b2_find_image(unit_prefix, n_jobs, uniform_units, p_unit, &q);
     const UpsampleJobDev* __restrict__ jp = jobs + img;
+    q += jp->q_lo;
     const int width = jp->width, height = jp->height;
     const int uh = (height + 1) >> 1;
     const int rt = 2 * (int)q - 1, rb = 2 * (int)q;
@@ -547,10 +552,12 @@ upsample_bulk_kernel(const UpsampleJobDev* __restrict__ jobs, const uint32_t* __
     uint32_t q;
     const uint32_t img = b2_find_image(unit_prefix, n_jobs, uniform_units, c_unit, &q);
     const UpsampleJobDev* __restrict__ jp = jobs + img;
-    const int width = jp->width, height = jp->height;
+    q += jp->q_lo;
+    const int width = jp->width;
     const int uw = (width + 1) >> 1;
     const int rt = 2 * (int)q - 1, rb = 2 * (int)q;
-    const bool top_ok = (rt >= 0), bot_ok = (rb < height);
+    const int row_begin = jp->row_begin, row_end = jp->row_end;
+    const bool top_ok = (rt >= row_begin) && (rt < row_end), bot_ok = (rb >= row_begin) && (rb < row_end);
     const int dstride = jp->dst_stride;
     const int wv = width & ~7;  // the vector path covers pixels [0, wv)
     uint8_t* const drt = jp->dst + (ptrdiff_t)(top_ok ? rt : rb) * dstride;
@@ -645,7 +652,16 @@ extern "C" int b2_yuv420a_to_rgba_fancy(b2_ctx* ctx, int stream, const b2_upsamp
           (uintptr_t)(uint32_t)j.uv_stride | (uintptr_t)(uint32_t)(j.a ? j.a_stride : 0)) & 15) != 0 ||
         j.y_stride < 0 || j.uv_stride < 0 || (j.a && j.a_stride < 0)) staged = false;
     n_with_a += (j.a != NULL);
-    const uint32_t units = (uint32_t)((j.height >> 1) + 1);
+    // EmitFancyRGB-style partial output (io_dec.c.go:65-115): rows [row_begin, row_end)
+    int rb0 = 0, re0 = j.height;
+    if (j.row_end != 0 || j.row_begin != 0) {
+      if (j.row_begin < 0 || j.row_end <= j.row_begin || j.row_end > j.height) { free(host); return B2_ERR_INVALID_CONFIG; }
+      rb0 = j.row_begin; re0 = j.row_end;
+    }
+    d.row_begin = rb0; d.row_end = re0;
+    d.q_lo = (uint32_t)((rb0 + 1) >> 1);
+    d.pad = 0;
+    const uint32_t units = (uint32_t)(re0 >> 1) - d.q_lo + 1;
     const uint32_t items = d.tiles_x * units;
     if (i == 0) uniform = items; else if (items != uniform) uniform = 0;
     if (i == 0) uuniform = units; else if (units != uuniform) uuniform = 0;

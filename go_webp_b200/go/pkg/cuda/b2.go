@@ -194,6 +194,7 @@ type UpsampleJob struct {
 	Y, U, V, A, Dst                          DevicePtr
 	YStride, UVStride, AStride, DstStride    int
 	Width, Height                            int
+	RowBegin, RowEnd                         int // output rows [RowBegin, RowEnd); 0, 0 = whole image (EmitFancyRGB batches)
 }
 
 // UpsampleFancy replaces WebPUpsamplers[mode] driven by WebPPictureYUVAToARGB /

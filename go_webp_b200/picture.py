@@ -351,6 +351,43 @@ def YUVAToRGBABatch(pics, mode: int = _abi.MODE_BGRA, dsts=None, ctx: Context | 
     return out
 
 
+def EmitFancyRGB(pic: Picture, mode: int, mb_y: int, mb_h: int, dst: np.ndarray, ctx: Context | None = None) -> int:
+    """EmitFancyRGB (pkg/libwebp/decoder/io_dec.c.go:65-115) for the macroblock-row batch
+    [mb_y, mb_y + mb_h) of a decoded picture: writes the output rows that batch completes
+    into dst (uint8 [h, w*bpp]) and returns their number.  First batch: row 0 is
+    mirrored; every batch leaves its last row for the next call (it needs the chroma
+    row below), the last batch also emits the final row.  The reference carries the
+    unfinished row in tmp_y/u/v; here the planes are whole, so the carried row is simply
+    read again, and EmitAlphaRGB (io_dec.c.go:175-195) is fused when pic has alpha."""
+    ctx = ctx or default_context()
+    w, h = pic.Width, pic.Height
+    bpp = _abi.MODE_BPP[mode]
+    y_end = min(mb_y + mb_h, h)
+    row_begin = max(mb_y - 1, 0)
+    row_end = h if y_end >= h else y_end - 1
+    if row_end <= row_begin:
+        return 0
+    uvw, uvh = (w + 1) >> 1, (h + 1) >> 1
+    ys, uvs, ds = _al(w, 16), _al(uvw, 16), _al(w * bpp, 16)
+    has_a = bool(pic.ColorSpace & WEBP_CSP_ALPHA_BIT) and bpp == 4 and pic.A is not None
+    sz = dict(y=_al(ys * h), u=_al(uvs * uvh), v=_al(uvs * uvh), a=_al(ys * h) if has_a else 0, d=_al(ds * h))
+    ar = _arena(ctx)
+    ar.reset(sum(sz.values()))
+    p = {k: (ar.take(v) if v else None) for k, v in sz.items()}
+    lib, hnd = ctx.lib, ctx.h
+    for key, plane, stride, pw, ph in (("y", pic.Y, ys, w, h), ("u", pic.U, uvs, uvw, uvh), ("v", pic.V, uvs, uvw, uvh)) + \
+            ((("a", pic.A, ys, w, h),) if has_a else ()):
+        arr = np.ascontiguousarray(plane)
+        ctx._chk(lib.b2_h2d_2d_async(hnd, 0, p[key], stride, arr.ctypes.data, arr.shape[1], pw, ph))
+    job = _abi.UpsampleJob(p["y"], p["u"], p["v"], p["a"], p["d"], ys, uvs, ys, ds, w, h, row_begin, row_end)
+    ctx._chk(lib.b2_yuv420a_to_rgba_fancy(hnd, 0, (_abi.UpsampleJob * 1)(job), 1, mode))
+    rows = dst[row_begin:row_end]
+    ctx._chk(lib.b2_d2h_2d_async(hnd, 0, rows.ctypes.data, dst.strides[0], p["d"] + row_begin * ds, ds,
+                                 w * bpp, row_end - row_begin))
+    ctx.sync()
+    return row_end - row_begin
+
+
 def WebPPictureYUVAToARGB(pic: Picture) -> int:
     """picture_csp_enc.c.go:62-118: fills pic.ARGB (uint32 0xAARRGGBB, i.e. the
     MODE_BGRA byte order on little-endian, :85) and sets UseARGB."""

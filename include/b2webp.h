@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define B2_ABI_VERSION 0x0102
+#define B2_ABI_VERSION 0x0103
 
 typedef enum b2_status {
   B2_OK = 0,
@@ -140,6 +140,13 @@ typedef struct b2_upsample_job {
   uint8_t* dst;
   int32_t y_stride, uv_stride, a_stride, dst_stride; /* bytes, signed */
   int32_t width, height;
+  /* Output rows to produce, [row_begin, row_end); both 0 = the whole image.  This is
+   * EmitFancyRGB's streaming schedule (pkg/libwebp/decoder/io_dec.c.go:65-115): for a
+   * macroblock-row batch [mb_y, mb_y + mb_h) it emits rows max(mb_y - 1, 0) ..
+   * mb_y + mb_h - 2 (the last row of a batch waits for the chroma row below it) and, on
+   * the last batch, the final row as well.  Pointers always address row 0 of the
+   * image; rows outside the range are neither read for output nor written. */
+  int32_t row_begin, row_end;
 } b2_upsample_job;
 
 int b2_yuv420a_to_rgba_fancy(b2_ctx* ctx, int stream, const b2_upsample_job* jobs,

@@ -548,3 +548,36 @@ def test_predictor_in_batched_chain(gpu):
     outs = D.VP8LInverseTransformBatch(imgs, chains)
     for o, e in zip(outs, exp):
         assert (o.reshape(e.shape) == e).all()
+
+
+def test_emit_fancy_rgb_streaming(gpu):
+    """EmitFancyRGB's macroblock-row batches (io_dec.c.go:65-115) through the row-range
+    form of the kernel: every batch writes exactly the rows the reference would, and
+    the assembled image equals the whole-image conversion (aligned fast kernel and
+    ragged generic kernel)."""
+    P, A = gpu["picture"], gpu["abi"]
+    rng = np.random.default_rng(77)
+    for (w, h, mode, alpha) in [(256, 64, A.MODE_RGBA, False), (520, 49, A.MODE_BGRA, True), (37, 35, A.MODE_RGB, False),
+                                (1024, 34, A.MODE_ARGB, False), (64, 16, A.MODE_RGB_565, False)]:
+        uw, uh = (w + 1) // 2, (h + 1) // 2
+        y = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        u = rng.integers(0, 256, (uh, uw), dtype=np.uint8)
+        v = rng.integers(0, 256, (uh, uw), dtype=np.uint8)
+        a = rng.integers(0, 256, (h, w), dtype=np.uint8) if alpha else None
+        exp = oracle.yuva_to_rgba(y, u, v, a, mode)
+        pic = P.Picture(Width=w, Height=h, ColorSpace=P.WEBP_YUV420A if alpha else P.WEBP_YUV420, Y=y, U=u, V=v, A=a)
+        bpp = A.MODE_BPP[mode]
+        dst = np.full((h, w * bpp), 0xA5, np.uint8)
+        total, mb_y = 0, 0
+        while mb_y < h:
+            mb_h = min(16, h - mb_y)
+            before = dst.copy()
+            n = P.EmitFancyRGB(pic, mode, mb_y, mb_h, dst)
+            lo = max(mb_y - 1, 0)
+            hi = h if mb_y + mb_h >= h else mb_y + mb_h - 1
+            assert n == hi - lo
+            assert (dst[:lo] == before[:lo]).all() and (dst[hi:] == before[hi:]).all()  # nothing else touched
+            total += n
+            mb_y += mb_h
+        assert total == h
+        assert (dst == exp.reshape(h, w * bpp)).all(), (w, h, mode)

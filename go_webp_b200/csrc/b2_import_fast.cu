@@ -22,6 +22,9 @@
 
 namespace {
 
+#ifndef B2_IMPORT_L2_PREFETCH
+#define B2_IMPORT_L2_PREFETCH 0
+#endif
 constexpr int kFastThreads = 512;
 constexpr int kFastWarps = kFastThreads / 32;
 constexpr int kFastCtasPerSm = 2;
@@ -191,6 +194,16 @@ import_fast_kernel(const ImportJobDev* __restrict__ jobs, const uint32_t* __rest
       const bool nxt_ok = xn < width;
       uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;
       if (nxt_ok) { n0 = b2_ldg_stream_v4(s0 + 512); n1 = b2_ldg_stream_v4(s1 + 512); }
+#if B2_IMPORT_L2_PREFETCH
+      // Optional: pull the strips after that into L2.  Measured (profiles/r01d_*): with
+      // opaque input the kernel waits on load latency and distance 5 gains 3%, but with
+      // translucent input it is issue bound and the two extra instructions cost 6%, so
+      // the default is off.
+      if (xn + 128 * (B2_IMPORT_L2_PREFETCH - 1) < width) {
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(s0 + 512 * B2_IMPORT_L2_PREFETCH));
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(s1 + 512 * B2_IMPORT_L2_PREFETCH));
+      }
+#endif
       const uint32_t yw0 = pack_b2(luma_sum<ORDER>(c0.x), luma_sum<ORDER>(c0.y), luma_sum<ORDER>(c0.z), luma_sum<ORDER>(c0.w));
       const uint32_t yw1 = pack_b2(luma_sum<ORDER>(c1.x), luma_sum<ORDER>(c1.y), luma_sum<ORDER>(c1.z), luma_sum<ORDER>(c1.w));
       uint32_t ap0 = 0xffffffffu, ap1 = 0xffffffffu;

@@ -59,6 +59,15 @@ class ExpandJob(C.Structure):
                 ("bits", C.c_int32)]
 
 
+class ConvertJob(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("u", C.c_void_p), ("v", C.c_void_p), ("dst", C.c_void_p),
+                ("src_stride", C.c_int32), ("uv_stride", C.c_int32), ("dst_stride", C.c_int32),
+                ("width", C.c_int32), ("height", C.c_int32), ("reserved", C.c_int32)]
+
+
+CONVERT_UPSTREAM_16BIT = 1
+ALPHA_APPLY, ALPHA_APPLY_4444, ALPHA_MULT_ARGB, ALPHA_MULT_ROW = 0, 1, 2, 3
+
 # every symbol include/b2webp.h declares: name -> (restype, argtypes)
 _vp = C.c_void_p
 _ctx = C.c_void_p
@@ -98,6 +107,9 @@ SYMBOLS = {
     "b2_vp8l_bundle_color_map": (C.c_int, [_ctx, C.c_int, C.POINTER(ArgbJob), C.c_int]),
     "b2_vp8l_predictor_inverse": (C.c_int, [_ctx, C.c_int, C.POINTER(ArgbJob), C.c_int]),
     "b2_vp8l_predictor_forward": (C.c_int, [_ctx, C.c_int, C.POINTER(ArgbJob), C.c_int]),
+    "b2_vp8l_convert_from_bgra": (C.c_int, [_ctx, C.c_int, C.POINTER(ConvertJob), C.c_int, C.c_int, C.c_int]),
+    "b2_alpha_multiply": (C.c_int, [_ctx, C.c_int, C.POINTER(ConvertJob), C.c_int, C.c_int, C.c_int]),
+    "b2_yuv_to_rgb_point": (C.c_int, [_ctx, C.c_int, C.POINTER(ConvertJob), C.c_int, C.c_int, C.c_int]),
     "b2_argb_to_yuva_plain": (C.c_int, [_ctx, C.c_int, C.POINTER(PlainJob), C.c_int]),
     "b2_vp8l_color_index_inverse_alpha": (C.c_int, [_ctx, C.c_int, C.POINTER(AlphaIndexJob), C.c_int]),
     "b2_vp8l_expand_color_map": (C.c_int, [_ctx, C.c_int, C.POINTER(ExpandJob), C.c_int]),
@@ -127,7 +139,7 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)  # AttributeError if the export is missing
             fn.restype = res
             fn.argtypes = args
-        if lib.b2_abi_version() != 0x0103:
+        if lib.b2_abi_version() != 0x0104:
             raise ImportError("libb2webp.so ABI version mismatch; rebuild")
         _LIB = lib
     return _LIB

@@ -1,0 +1,318 @@
+// b2_convert.cu -- the output conversions that follow parts 2 and 3 in the decoder
+// (SURVEY.md 8f-2):
+//   VP8LConvertFromBGRA and its rows          pkg/libwebp/dsp/lossless.go:549-666
+//   ApplyAlphaMultiply_C / ..4444_C           pkg/libwebp/dsp/alpha_processing.go:100-163
+//   WebPMultARGBRow_C / WebPMultRow_C         pkg/libwebp/dsp/alpha_processing.go:17-89
+//   point samplers (row_func, WebPSamplerProcessPlane == EmitSampledRGB)
+//                                             pkg/libwebp/dsp/yuv.go:19-72, decoder/io_dec.c.go:53-59
+//   YUV444 converters                         pkg/libwebp/dsp/upsampling.c.go:191-245
+// All per-pixel and HBM-bound; one thread handles 4 pixels of a row.
+//
+// 16-bit modes follow the Go text (ba / gb byte first, rg_byte_pos 1: upstream built
+// with WEBP_SWAP_16BIT_CSP); B2_CONVERT_UPSTREAM_16BIT flips it.
+// The YUV writers keep the upstream default order, like b2_upsample.cu.
+#include <stdlib.h>
+
+#include "b2_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+
+struct ConvJobDev {
+  const void* src;     // uint32 pixels, or the Y plane
+  const uint8_t* u;    // chroma planes (samplers) or alpha plane (mult rows)
+  const uint8_t* v;
+  uint8_t* dst;
+  int32_t src_stride;  // pixels for uint32 sources, bytes for planes
+  int32_t uv_stride;
+  int32_t dst_stride;  // bytes
+  int32_t width, height;
+  uint32_t chunks_x;   // 128-pixel chunks per row
+};
+
+enum {  // canonical store modes
+  ST_RGB = 0, ST_RGBA = 1, ST_BGR = 2, ST_BGRA = 3, ST_ARGB = 4, ST_4444 = 5, ST_565 = 6
+};
+__host__ __device__ inline int canonical(int mode, bool* premult) {
+  *premult = (mode == B2_MODE_rgbA || mode == B2_MODE_bgrA || mode == B2_MODE_Argb || mode == B2_MODE_rgbA_4444);
+  switch (mode) {
+    case B2_MODE_RGB: return ST_RGB;
+    case B2_MODE_BGR: return ST_BGR;
+    case B2_MODE_RGBA: case B2_MODE_rgbA: return ST_RGBA;
+    case B2_MODE_BGRA: case B2_MODE_bgrA: return ST_BGRA;
+    case B2_MODE_ARGB: case B2_MODE_Argb: return ST_ARGB;
+    case B2_MODE_RGBA_4444: case B2_MODE_rgbA_4444: return ST_4444;
+    case B2_MODE_RGB_565: return ST_565;
+    default: return -1;
+  }
+}
+__host__ __device__ inline int bpp_of(int st) { return st == ST_RGB || st == ST_BGR ? 3 : (st >= ST_4444 ? 2 : 4); }
+
+// PREMULTIPLY(x, MULTIPLIER1(a)), alpha_processing.go:103-108
+__device__ __forceinline__ uint32_t premul(uint32_t x, uint32_t a) { return (x * (a * 32897u)) >> 23; }
+// ApplyAlphaMultiply4444_C on one pixel (alpha_processing.go:128-156)
+__device__ __forceinline__ void premul4444(uint32_t* rg, uint32_t* ba) {
+  const uint32_t a = *ba & 0x0f;
+  const uint32_t mult = a * 0x1111u;
+  const uint32_t hi_rg = (*rg & 0xf0) | (*rg >> 4), lo_rg = ((*rg & 0x0f) | (*rg << 4)) & 0xff;
+  const uint32_t hi_ba = (*ba & 0xf0) | (*ba >> 4);
+  const uint32_t r = (hi_rg * mult) >> 16, g = (lo_rg * mult) >> 16, b = (hi_ba * mult) >> 16;
+  *rg = (r & 0xf0) | ((g >> 4) & 0x0f);
+  *ba = (b & 0xf0) | a;
+}
+// One pixel (a, r, g, b bytes) into 'st' byte order at d.
+__device__ __forceinline__ void store_px(int st, bool premult, bool upstream16, uint32_t a, uint32_t r, uint32_t g,
+                                         uint32_t b, uint8_t* d) {
+  if (st == ST_4444) {
+    uint32_t rg = (r & 0xf0) | (g >> 4), ba = (b & 0xf0) | (a >> 4);
+    if (premult) premul4444(&rg, &ba);
+    d[upstream16 ? 0 : 1] = (uint8_t)rg;
+    d[upstream16 ? 1 : 0] = (uint8_t)ba;
+    return;
+  }
+  if (st == ST_565) {
+    const uint32_t rg = (r & 0xf8) | (g >> 5), gb = ((g << 3) & 0xe0) | (b >> 3);
+    d[upstream16 ? 0 : 1] = (uint8_t)rg;
+    d[upstream16 ? 1 : 0] = (uint8_t)gb;
+    return;
+  }
+  if (premult && a != 0xff) { r = premul(r, a); g = premul(g, a); b = premul(b, a); }
+  switch (st) {
+    case ST_RGB: d[0] = r; d[1] = g; d[2] = b; break;
+    case ST_BGR: d[0] = b; d[1] = g; d[2] = r; break;
+    case ST_RGBA: d[0] = r; d[1] = g; d[2] = b; d[3] = a; break;
+    case ST_BGRA: d[0] = b; d[1] = g; d[2] = r; d[3] = a; break;
+    default: d[0] = a; d[1] = r; d[2] = g; d[3] = b; break;  // ST_ARGB
+  }
+}
+__device__ __forceinline__ uint32_t pack_px(int st, bool premult, uint32_t a, uint32_t r, uint32_t g, uint32_t b) {
+  if (premult && a != 0xff) { r = premul(r, a); g = premul(g, a); b = premul(b, a); }
+  if (st == ST_RGBA) return r | (g << 8) | (b << 16) | (a << 24);
+  if (st == ST_BGRA) return b | (g << 8) | (r << 16) | (a << 24);
+  return a | (r << 8) | (g << 16) | (b << 24);  // ST_ARGB
+}
+
+// Common item walk: a warp takes 128 pixels of one row, a lane 4 of them.
+#define B2_CONV_ITEM_PROLOGUE                                                                        \
+  const int lane = threadIdx.x & 31;                                                                 \
+  const uint32_t warp = threadIdx.x >> 5;                                                            \
+  for (uint32_t item = blockIdx.x * kWarps + warp; item < total_items; item += gridDim.x * kWarps) { \
+    uint32_t local;                                                                                  \
+    const uint32_t img = b2_find_image(prefix, n_jobs, uniform, item, &local);                       \
+    const ConvJobDev j = jobs[img];                                                                  \
+    const uint32_t y = local / j.chunks_x;                                                           \
+    const int x0 = (int)(local - y * j.chunks_x) * 128 + lane * 4;                                   \
+    if (x0 >= j.width) continue;                                                                     \
+    const int nv = min(4, j.width - x0);
+
+// ---- VP8LConvertFromBGRA ----------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 8)
+convert_from_bgra_kernel(const ConvJobDev* __restrict__ jobs, const uint32_t* __restrict__ prefix, uint32_t n_jobs,
+                         uint32_t uniform, uint32_t total_items, int st, int premult, int upstream16) {
+  B2_CONV_ITEM_PROLOGUE
+    const uint32_t* s = (const uint32_t*)j.src + (ptrdiff_t)y * j.src_stride + x0;
+    uint32_t p[4];
+    if (nv == 4 && (((uintptr_t)s) & 15) == 0) {
+      const uint4 q = b2_ldg_stream_v4(s);
+      p[0] = q.x; p[1] = q.y; p[2] = q.z; p[3] = q.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) p[k] = (k < nv) ? __ldg(s + k) : 0u;
+    }
+    const int bpp = bpp_of(st);
+    uint8_t* d = j.dst + (ptrdiff_t)y * j.dst_stride + x0 * bpp;
+    if (bpp == 4 && nv == 4 && (((uintptr_t)d) & 15) == 0) {
+      uint4 o;
+      o.x = pack_px(st, premult, p[0] >> 24, (p[0] >> 16) & 0xff, (p[0] >> 8) & 0xff, p[0] & 0xff);
+      o.y = pack_px(st, premult, p[1] >> 24, (p[1] >> 16) & 0xff, (p[1] >> 8) & 0xff, p[1] & 0xff);
+      o.z = pack_px(st, premult, p[2] >> 24, (p[2] >> 16) & 0xff, (p[2] >> 8) & 0xff, p[2] & 0xff);
+      o.w = pack_px(st, premult, p[3] >> 24, (p[3] >> 16) & 0xff, (p[3] >> 8) & 0xff, p[3] & 0xff);
+      b2_stg_stream_v4(d, o);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (k < nv) store_px(st, premult, upstream16, p[k] >> 24, (p[k] >> 16) & 0xff, (p[k] >> 8) & 0xff, p[k] & 0xff, d + k * bpp);
+    }
+  }
+}
+
+// ---- alpha multiplies (in place) ----------------------------------------------------
+enum { AM_APPLY = 0, AM_APPLY_4444 = 1, AM_MULT_ARGB = 2, AM_MULT_ROW = 3 };
+#define MFIX 24
+// Mult / GetScale, alpha_processing.go:17-31
+__device__ __forceinline__ uint32_t mult_scale(uint32_t a, bool inverse) {
+  return inverse ? (255u << MFIX) / a : a * ((1u << MFIX) / 255u);
+}
+__device__ __forceinline__ uint32_t mult_fix(uint32_t x, uint32_t scale) { return (x * scale + (1u << (MFIX - 1))) >> MFIX; }
+
+__global__ void __launch_bounds__(kThreads, 8)
+alpha_multiply_kernel(const ConvJobDev* __restrict__ jobs, const uint32_t* __restrict__ prefix, uint32_t n_jobs,
+                      uint32_t uniform, uint32_t total_items, int kind, int flag) {
+  B2_CONV_ITEM_PROLOGUE
+    if (kind == AM_APPLY) {  // ApplyAlphaMultiply_C: 4 bytes per pixel, flag = alpha_first
+      uint8_t* d = j.dst + (ptrdiff_t)y * j.dst_stride + x0 * 4;
+      for (int k = 0; k < nv; ++k) {
+        uint8_t* px = d + 4 * k;
+        const uint32_t a = px[flag ? 0 : 3];
+        if (a != 0xff) {
+          uint8_t* rgb = px + (flag ? 1 : 0);
+          rgb[0] = (uint8_t)premul(rgb[0], a); rgb[1] = (uint8_t)premul(rgb[1], a); rgb[2] = (uint8_t)premul(rgb[2], a);
+        }
+      }
+    } else if (kind == AM_APPLY_4444) {  // flag = rg_byte_pos
+      uint8_t* d = j.dst + (ptrdiff_t)y * j.dst_stride + x0 * 2;
+      for (int k = 0; k < nv; ++k) {
+        uint32_t rg = d[2 * k + flag], ba = d[2 * k + (flag ^ 1)];
+        premul4444(&rg, &ba);
+        d[2 * k + flag] = (uint8_t)rg; d[2 * k + (flag ^ 1)] = (uint8_t)ba;
+      }
+    } else if (kind == AM_MULT_ARGB) {  // WebPMultARGBRow_C, flag = inverse
+      uint32_t* d = (uint32_t*)(j.dst + (ptrdiff_t)y * j.dst_stride) + x0;
+      for (int k = 0; k < nv; ++k) {
+        const uint32_t argb = d[k];
+        if (argb < 0xff000000u) {
+          if (argb <= 0x00ffffffu) {
+            d[k] = 0;
+          } else {
+            const uint32_t scale = mult_scale(argb >> 24, flag != 0);
+            d[k] = (argb & 0xff000000u) | mult_fix(argb & 0xff, scale) | (mult_fix((argb >> 8) & 0xff, scale) << 8) |
+                   (mult_fix((argb >> 16) & 0xff, scale) << 16);
+          }
+        }
+      }
+    } else {  // WebPMultRow_C: plane dst, alpha plane u, flag = inverse
+      uint8_t* d = j.dst + (ptrdiff_t)y * j.dst_stride + x0;
+      const uint8_t* al = j.u + (ptrdiff_t)y * j.uv_stride + x0;
+      for (int k = 0; k < nv; ++k) {
+        const uint32_t a = al[k];
+        if (a != 255) d[k] = (a == 0) ? 0 : (uint8_t)mult_fix(d[k], mult_scale(a, flag != 0));
+      }
+    }
+  }
+}
+
+// ---- point-sampled / 4:4:4 YUV -> RGB -----------------------------------------------
+// VP8YUVToR/G/B (pkg/color/yuv/conversion.go:28-48)
+__device__ __forceinline__ void yuv_rgb(uint32_t y, uint32_t u, uint32_t v, uint32_t* r, uint32_t* g, uint32_t* b) {
+  const int yy = (int)(y * 19077u) >> 8;
+  const int r6 = (yy + ((int)(v * 26149u) >> 8) - 14234) >> 6;
+  const int g6 = (yy - ((int)(u * 6419u) >> 8) - ((int)(v * 13320u) >> 8) + 8708) >> 6;
+  const int b6 = (yy + ((int)(u * 33050u) >> 8) - 17685) >> 6;
+  *r = (uint32_t)min(max(r6, 0), 255); *g = (uint32_t)min(max(g6, 0), 255); *b = (uint32_t)min(max(b6, 0), 255);
+}
+template <bool YUV444>
+__global__ void __launch_bounds__(kThreads, 8)
+yuv_point_kernel(const ConvJobDev* __restrict__ jobs, const uint32_t* __restrict__ prefix, uint32_t n_jobs,
+                 uint32_t uniform, uint32_t total_items, int st) {
+  B2_CONV_ITEM_PROLOGUE
+    const uint8_t* yr = (const uint8_t*)j.src + (ptrdiff_t)y * j.src_stride + x0;
+    // WebPSamplerProcessPlane advances u/v after every odd row (yuv.go:52-55): chroma row y >> 1
+    const ptrdiff_t crow = (ptrdiff_t)(YUV444 ? y : (y >> 1)) * j.uv_stride;
+    const uint8_t* ur = j.u + crow;
+    const uint8_t* vr = j.v + crow;
+    const int bpp = bpp_of(st);
+    uint8_t* d = j.dst + (ptrdiff_t)y * j.dst_stride + x0 * bpp;
+    for (int k = 0; k < nv; ++k) {
+      const int cx = YUV444 ? (x0 + k) : ((x0 + k) >> 1);  // row_func: two pixels share a sample (yuv.go:24-30)
+      uint32_t r, g, b;
+      yuv_rgb(yr[k], ur[cx], vr[cx], &r, &g, &b);
+      if (st == ST_4444) { d[2 * k] = (uint8_t)((r & 0xf0) | (g >> 4)); d[2 * k + 1] = (uint8_t)((b & 0xf0) | 0x0f); }
+      else if (st == ST_565) { d[2 * k] = (uint8_t)((r & 0xf8) | (g >> 5)); d[2 * k + 1] = (uint8_t)(((g << 3) & 0xe0) | (b >> 3)); }
+      else store_px(st, false, true, 0xff, r, g, b, d + k * bpp);
+    }
+  }
+}
+
+int prepare_conv(b2_ctx* ctx, int stream, const b2_convert_job* jobs, int n_jobs, bool need_uv, int min_dst_bpp,
+                 const ConvJobDev** dj, const uint32_t** dp, uint32_t* uniform, uint32_t* total) {
+  const size_t jb = (sizeof(ConvJobDev) * (size_t)n_jobs + 15) & ~(size_t)15;
+  const size_t pb = sizeof(uint32_t) * ((size_t)n_jobs + 1);
+  if (jb + pb > B2_DESC_RING_BYTES) return B2_ERR_INVALID_CONFIG;
+  uint8_t* host = (uint8_t*)malloc(jb + pb);
+  if (host == NULL) return B2_ERR_OOM;
+  ConvJobDev* d = (ConvJobDev*)host;
+  uint32_t* pre = (uint32_t*)(host + jb);
+  uint64_t tot = 0;
+  uint32_t uni = 0;
+  for (int i = 0; i < n_jobs; ++i) {
+    const b2_convert_job& j = jobs[i];
+    int st = B2_OK;
+    if (j.dst == NULL || (need_uv && j.u == NULL)) st = B2_ERR_NULL;
+    else if (j.width <= 0 || j.height <= 0 || j.width > B2_MAX_DIMENSION || j.height > B2_MAX_DIMENSION) st = B2_ERR_BAD_DIM;
+    else if ((j.dst_stride < 0 ? -(int64_t)j.dst_stride : j.dst_stride) < (int64_t)min_dst_bpp * j.width) st = B2_ERR_BAD_DIM;
+    if (st != B2_OK) { free(host); return st; }
+    d[i].src = j.src; d[i].u = j.u; d[i].v = j.v; d[i].dst = j.dst;
+    d[i].src_stride = j.src_stride; d[i].uv_stride = j.uv_stride; d[i].dst_stride = j.dst_stride;
+    d[i].width = j.width; d[i].height = j.height;
+    d[i].chunks_x = (uint32_t)((j.width + 127) / 128);
+    const uint32_t items = d[i].chunks_x * (uint32_t)j.height;
+    if (i == 0) uni = items; else if (items != uni) uni = 0;
+    pre[i] = (uint32_t)tot;
+    tot += items;
+    if (tot > 0x7fffffffull) { free(host); return B2_ERR_BAD_DIM; }
+  }
+  pre[n_jobs] = (uint32_t)tot;
+  void* dev = NULL;
+  const int st = b2_upload_desc(ctx, stream, host, jb + pb, &dev);
+  free(host);
+  if (st != B2_OK) return st;
+  *dj = (const ConvJobDev*)dev; *dp = (const uint32_t*)((uint8_t*)dev + jb); *uniform = uni; *total = (uint32_t)tot;
+  return B2_OK;
+}
+
+}  // namespace
+
+#define B2_CONV_ENTRY_CHECKS          \
+  B2_CHECK_CTX(ctx, stream);          \
+  if (n_jobs < 0) return B2_ERR_INVALID_CONFIG; \
+  if (n_jobs == 0) return B2_OK;      \
+  if (jobs == NULL) return B2_ERR_NULL;
+
+extern "C" int b2_vp8l_convert_from_bgra(b2_ctx* ctx, int stream, const b2_convert_job* jobs, int n_jobs, int mode, int flags) {
+  B2_CONV_ENTRY_CHECKS
+  bool premult;
+  const int st = canonical(mode, &premult);
+  if (st < 0) return B2_ERR_INVALID_CONFIG;
+  for (int i = 0; i < n_jobs; ++i) if (jobs[i].src == NULL) return B2_ERR_NULL;
+  const ConvJobDev* dj; const uint32_t* dp; uint32_t uni, tot;
+  const int rc = prepare_conv(ctx, stream, jobs, n_jobs, false, bpp_of(st), &dj, &dp, &uni, &tot);
+  if (rc != B2_OK) return rc;
+  convert_from_bgra_kernel<<<b2_grid_for(ctx, 8, (tot + kWarps - 1) / kWarps), kThreads, 0, ctx->streams[stream]>>>(
+      dj, dp, (uint32_t)n_jobs, uni, tot, st, premult ? 1 : 0, (flags & B2_CONVERT_UPSTREAM_16BIT) ? 1 : 0);
+  ctx->launches++;
+  B2_CUDA(ctx, cudaGetLastError());
+  return B2_OK;
+}
+
+extern "C" int b2_alpha_multiply(b2_ctx* ctx, int stream, const b2_convert_job* jobs, int n_jobs, int kind, int flag) {
+  B2_CONV_ENTRY_CHECKS
+  if (kind < 0 || kind > 3) return B2_ERR_INVALID_CONFIG;
+  const int bpp = (kind == B2_ALPHA_APPLY || kind == B2_ALPHA_MULT_ARGB) ? 4 : (kind == B2_ALPHA_APPLY_4444 ? 2 : 1);
+  const ConvJobDev* dj; const uint32_t* dp; uint32_t uni, tot;
+  const int rc = prepare_conv(ctx, stream, jobs, n_jobs, kind == B2_ALPHA_MULT_ROW, bpp, &dj, &dp, &uni, &tot);
+  if (rc != B2_OK) return rc;
+  alpha_multiply_kernel<<<b2_grid_for(ctx, 8, (tot + kWarps - 1) / kWarps), kThreads, 0, ctx->streams[stream]>>>(
+      dj, dp, (uint32_t)n_jobs, uni, tot, kind, flag ? 1 : 0);
+  ctx->launches++;
+  B2_CUDA(ctx, cudaGetLastError());
+  return B2_OK;
+}
+
+extern "C" int b2_yuv_to_rgb_point(b2_ctx* ctx, int stream, const b2_convert_job* jobs, int n_jobs, int mode, int yuv444) {
+  B2_CONV_ENTRY_CHECKS
+  bool premult;
+  const int st = canonical(mode, &premult);  // premultiplied modes alias the plain samplers (yuv.go:67-71)
+  if (st < 0) return B2_ERR_INVALID_CONFIG;
+  for (int i = 0; i < n_jobs; ++i) if (jobs[i].src == NULL || jobs[i].v == NULL) return B2_ERR_NULL;
+  const ConvJobDev* dj; const uint32_t* dp; uint32_t uni, tot;
+  const int rc = prepare_conv(ctx, stream, jobs, n_jobs, true, bpp_of(st), &dj, &dp, &uni, &tot);
+  if (rc != B2_OK) return rc;
+  const int grid = b2_grid_for(ctx, 8, (tot + kWarps - 1) / kWarps);
+  if (yuv444) yuv_point_kernel<true><<<grid, kThreads, 0, ctx->streams[stream]>>>(dj, dp, (uint32_t)n_jobs, uni, tot, st);
+  else yuv_point_kernel<false><<<grid, kThreads, 0, ctx->streams[stream]>>>(dj, dp, (uint32_t)n_jobs, uni, tot, st);
+  ctx->launches++;
+  B2_CUDA(ctx, cudaGetLastError());
+  return B2_OK;
+}

@@ -246,6 +246,93 @@ def WebPConvertARGBToUV(argb: np.ndarray, u: np.ndarray, v: np.ndarray, src_widt
     return nu[0], nv[0]
 
 
+# ---- output conversions after parts 2 and 3 ---------------------------
+def _convert(fn_name, uploads, make_job, out_ptr_index, out_shape, out_dtype, extra, ctx=None):
+    """uploads: list of (array, role); the output is uploads[out_ptr_index] (in place) or,
+    when out_ptr_index is None, a fresh buffer of out_shape/out_dtype."""
+    ctx = ctx or default_context()
+    out_nbytes = int(np.prod(out_shape)) * np.dtype(out_dtype).itemsize
+    ar = _arena(ctx)
+    ar.reset(sum(_al(a.nbytes) for a in uploads) + _al(out_nbytes))
+    ptrs = []
+    for a in uploads:
+        pa = ar.take(_al(a.nbytes))
+        ctx._chk(ctx.lib.b2_h2d_async(ctx.h, 0, pa, a.ctypes.data, a.nbytes))
+        ptrs.append(pa)
+    po = ptrs[out_ptr_index] if out_ptr_index is not None else ar.take(_al(out_nbytes))
+    job = make_job(ptrs, po)
+    ctx._chk(getattr(ctx.lib, fn_name)(ctx.h, 0, (_abi.ConvertJob * 1)(job), 1, *extra))
+    out = np.empty(out_shape, out_dtype)
+    ctx._chk(ctx.lib.b2_d2h_async(ctx.h, 0, out.ctypes.data, po, out_nbytes))
+    ctx.sync()
+    return out
+
+
+def VP8LConvertFromBGRA(in_data: np.ndarray, num_pixels: int | None, out_colorspace: int,
+                        upstream_16bit_order: bool = False) -> np.ndarray:
+    """lossless.go:616-666.  in_data: uint32 pixels ([h, w] or flat); returns the bytes of
+    'out_colorspace' ([h, w*bpp]).  Premultiplied modes include WebPApplyAlphaMultiply."""
+    src = np.ascontiguousarray(in_data, np.uint32)
+    if src.ndim == 1:
+        src = src[:num_pixels].reshape(1, -1)
+    h, w = src.shape
+    bpp = _abi.MODE_BPP[out_colorspace]
+    return _convert("b2_vp8l_convert_from_bgra", [src],
+                    lambda p, po: _abi.ConvertJob(p[0], None, None, po, w, 0, w * bpp, w, h, 0),
+                    None, (h, w * bpp), np.uint8,
+                    (out_colorspace, _abi.CONVERT_UPSTREAM_16BIT if upstream_16bit_order else 0))
+
+
+def WebPApplyAlphaMultiply(rgba: np.ndarray, alpha_first: int, w: int, h: int, stride: int) -> np.ndarray:
+    """ApplyAlphaMultiply_C (alpha_processing.go:110-126); returns the premultiplied copy."""
+    buf = np.ascontiguousarray(rgba, np.uint8).reshape(h, stride)
+    return _convert("b2_alpha_multiply", [buf], lambda p, po: _abi.ConvertJob(None, None, None, po, 0, 0, stride, w, h, 0),
+                    0, (h, stride), np.uint8, (_abi.ALPHA_APPLY, int(alpha_first)))
+
+
+def WebPApplyAlphaMultiply4444(rgba4444: np.ndarray, w: int, h: int, stride: int, rg_byte_pos: int = 1) -> np.ndarray:
+    """ApplyAlphaMultiply4444_C (alpha_processing.go:141-163; the Go text binds rg_byte_pos = 1)."""
+    buf = np.ascontiguousarray(rgba4444, np.uint8).reshape(h, stride)
+    return _convert("b2_alpha_multiply", [buf], lambda p, po: _abi.ConvertJob(None, None, None, po, 0, 0, stride, w, h, 0),
+                    0, (h, stride), np.uint8, (_abi.ALPHA_APPLY_4444, int(rg_byte_pos)))
+
+
+def WebPMultARGBRows(ptr: np.ndarray, width: int, num_rows: int, inverse: int) -> np.ndarray:
+    """WebPMultARGBRow_C over rows (alpha_processing.go:33-52,73-79); ptr: [num_rows, width] uint32."""
+    buf = np.ascontiguousarray(ptr, np.uint32).reshape(num_rows, width)
+    return _convert("b2_alpha_multiply", [buf], lambda p, po: _abi.ConvertJob(None, None, None, po, 0, 0, 4 * width, width, num_rows, 0),
+                    0, (num_rows, width), np.uint32, (_abi.ALPHA_MULT_ARGB, int(inverse)))
+
+
+def WebPMultRows(ptr: np.ndarray, alpha: np.ndarray, width: int, num_rows: int, inverse: int) -> np.ndarray:
+    """WebPMultRow_C over rows (alpha_processing.go:54-67,81-89)."""
+    buf = np.ascontiguousarray(ptr, np.uint8).reshape(num_rows, width)
+    al = np.ascontiguousarray(alpha, np.uint8).reshape(num_rows, width)
+    return _convert("b2_alpha_multiply", [buf, al], lambda p, po: _abi.ConvertJob(None, p[1], None, po, 0, width, width, width, num_rows, 0),
+                    0, (num_rows, width), np.uint8, (_abi.ALPHA_MULT_ROW, int(inverse)))
+
+
+def WebPSamplerProcessPlane(y: np.ndarray, u: np.ndarray, v: np.ndarray, mode: int) -> np.ndarray:
+    """dsp/yuv.go:47-58 with WebPSamplers[mode] (== EmitSampledRGB, io_dec.c.go:53-59):
+    point-sampled chroma, y [h, w], u/v [ceil(h/2), ceil(w/2)] -> bytes [h, w*bpp]."""
+    y, u, v = (np.ascontiguousarray(x, np.uint8) for x in (y, u, v))
+    h, w = y.shape
+    bpp = _abi.MODE_BPP[mode]
+    return _convert("b2_yuv_to_rgb_point", [y, u, v],
+                    lambda p, po: _abi.ConvertJob(p[0], p[1], p[2], po, w, u.shape[1], w * bpp, w, h, 0),
+                    None, (h, w * bpp), np.uint8, (mode, 0))
+
+
+def WebPYUV444ToRGB(y: np.ndarray, u: np.ndarray, v: np.ndarray, mode: int) -> np.ndarray:
+    """WebPYUV444Converters[mode] over rows (upsampling.c.go:191-245): full-resolution chroma."""
+    y, u, v = (np.ascontiguousarray(x, np.uint8) for x in (y, u, v))
+    h, w = y.shape
+    bpp = _abi.MODE_BPP[mode]
+    return _convert("b2_yuv_to_rgb_point", [y, u, v],
+                    lambda p, po: _abi.ConvertJob(p[0], p[1], p[2], po, w, w, w * bpp, w, h, 0),
+                    None, (h, w * bpp), np.uint8, (mode, 1))
+
+
 def VP8LPredictorForward(argb: np.ndarray, modes: np.ndarray, bits: int) -> np.ndarray:
     """Residuals of a whole image for GIVEN predictor modes: PredictorSub0..13_C
     (lossless_enc.go:339-557) driven as predictor_enc.go:666-712 does.  argb: [h, w]

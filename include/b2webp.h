@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define B2_ABI_VERSION 0x0103
+#define B2_ABI_VERSION 0x0104
 
 typedef enum b2_status {
   B2_OK = 0,
@@ -200,6 +200,43 @@ int b2_vp8l_bundle_color_map(b2_ctx* ctx, int stream, const b2_argb_job* jobs, i
  * pkg/libwebp/enc/predictor_enc.go:666-712): src = pixels, dst = residuals. */
 int b2_vp8l_predictor_inverse(b2_ctx* ctx, int stream, const b2_argb_job* jobs, int n_jobs);
 int b2_vp8l_predictor_forward(b2_ctx* ctx, int stream, const b2_argb_job* jobs, int n_jobs);
+
+/* ---- next rows: output conversions after parts 2 and 3 ---------
+ * One job layout for the three entry points (DEVICE pointers, signed strides). */
+typedef struct b2_convert_job {
+  const void* src;     /* uint32 0xAARRGGBB pixels (convert) or the Y plane (point samplers); unused by alpha multiply */
+  const uint8_t* u;    /* U plane (samplers) or the alpha plane (B2_ALPHA_MULT_ROW) */
+  const uint8_t* v;    /* V plane (samplers) */
+  uint8_t* dst;        /* output bytes; the in-place buffer for alpha multiply */
+  int32_t src_stride;  /* pixels for uint32 sources, bytes for planes */
+  int32_t uv_stride;   /* bytes */
+  int32_t dst_stride;  /* bytes */
+  int32_t width, height;
+  int32_t reserved;
+} b2_convert_job;
+
+/* VP8LConvertFromBGRA (pkg/libwebp/dsp/lossless.go:616-666) with its row converters
+ * (:549-614) and, for the premultiplied modes, WebPApplyAlphaMultiply{,4444}
+ * (pkg/libwebp/dsp/alpha_processing.go:100-163).  mode: WEBP_CSP_MODE.  The 16-bit
+ * modes write the ba / gb byte first as the Go text does (lossless.go:581-584,593-596:
+ * upstream built with WEBP_SWAP_16BIT_CSP); B2_CONVERT_UPSTREAM_16BIT in flags selects
+ * the upstream default order (rg first). */
+#define B2_CONVERT_UPSTREAM_16BIT 0x1
+int b2_vp8l_convert_from_bgra(b2_ctx* ctx, int stream, const b2_convert_job* jobs, int n_jobs, int mode, int flags);
+
+/* In-place alpha multiplies on dst (pkg/libwebp/dsp/alpha_processing.go):
+ *   B2_ALPHA_APPLY       ApplyAlphaMultiply_C :110-126, 4 bytes/pixel, flag = alpha_first
+ *   B2_ALPHA_APPLY_4444  ApplyAlphaMultiply4444_C :141-163, 2 bytes/pixel, flag = rg_byte_pos
+ *   B2_ALPHA_MULT_ARGB   WebPMultARGBRow_C / WebPMultARGBRows :33-52,73-79, uint32 pixels, flag = inverse
+ *   B2_ALPHA_MULT_ROW    WebPMultRow_C / WebPMultRows :54-67,81-89, plane dst with alpha plane u, flag = inverse */
+enum { B2_ALPHA_APPLY = 0, B2_ALPHA_APPLY_4444 = 1, B2_ALPHA_MULT_ARGB = 2, B2_ALPHA_MULT_ROW = 3 };
+int b2_alpha_multiply(b2_ctx* ctx, int stream, const b2_convert_job* jobs, int n_jobs, int kind, int flag);
+
+/* Point-sampled YUV420 -> RGB: WebPSamplers[mode] driven by WebPSamplerProcessPlane
+ * (pkg/libwebp/dsp/yuv.go:19-72) == EmitSampledRGB (pkg/libwebp/decoder/io_dec.c.go:
+ * 53-59); with yuv444 != 0 the WebPYUV444Converters rows (pkg/libwebp/dsp/
+ * upsampling.c.go:191-245) over full-resolution chroma planes. */
+int b2_yuv_to_rgb_point(b2_ctx* ctx, int stream, const b2_convert_job* jobs, int n_jobs, int mode, int yuv444);
 
 /* ---- remaining rows of the hot-path table (a14, a28, a29) ----- */
 

@@ -17,6 +17,7 @@ _LIBS: dict[str, C.CDLL] = {}
 
 MODE_RGB, MODE_RGBA, MODE_BGR, MODE_BGRA, MODE_ARGB = 0, 1, 2, 3, 4
 MODE_RGBA_4444, MODE_RGB_565 = 5, 6
+MODE_rgbA, MODE_bgrA, MODE_Argb, MODE_rgbA_4444 = 7, 8, 9, 10
 DIV_EXACT, DIV_TABLE = 0, 1
 PREDICTOR, CROSS_COLOR, SUBTRACT_GREEN, COLOR_INDEXING = 0, 1, 2, 3
 
@@ -26,10 +27,10 @@ _u32p = C.POINTER(C.c_uint32)
 
 def build(force: bool = False) -> None:
     """Compile liboracle.so / liboracle_scalar.so with the committed Makefile."""
+    newest = max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("oracle.c", "oracle_post.c"))
     need = force or not all(
         os.path.exists(os.path.join(_HERE, n))
-        and os.path.getmtime(os.path.join(_HERE, n))
-        >= os.path.getmtime(os.path.join(_HERE, "oracle.c"))
+        and os.path.getmtime(os.path.join(_HERE, n)) >= newest
         for n in ("liboracle.so", "liboracle_scalar.so"))
     if need:
         subprocess.check_call(["make", "-s", "-C", _HERE, "-B", "all"])
@@ -251,3 +252,64 @@ def synth_u32(seed, img, plane, words_per_row, rows, alpha_mode=0):
                              C.c_uint32(plane), _p(out), words_per_row, rows,
                              words_per_row * 4, alpha_mode)
     return out
+
+
+# ---- output conversions (oracle_post.c) ------------------------------
+def convert_from_bgra(src, mode, swap16=0):
+    """VP8LConvertFromBGRA (lossless.go:616-666) over a [h, w] uint32 image -> uint8 [h, w*bpp]."""
+    src = np.ascontiguousarray(src, np.uint32)
+    h, w = src.shape
+    bpp = lib().orc_mode_bpp(mode)
+    dst = np.zeros((h, w * bpp), np.uint8)
+    for r in range(h):
+        lib().orc_convert_from_bgra(_p(src[r]), w, mode, swap16, _p(dst[r]))
+    return dst
+
+
+def apply_alpha_multiply(rgba, alpha_first):
+    out = np.array(rgba, np.uint8)
+    h, wb = out.shape
+    lib().orc_apply_alpha_multiply(_p(out), int(alpha_first), wb // 4, h, wb)
+    return out
+
+
+def apply_alpha_multiply_4444(rgba4444, rg_byte_pos=1):
+    out = np.array(rgba4444, np.uint8)
+    h, wb = out.shape
+    lib().orc_apply_alpha_multiply_4444(_p(out), wb // 2, h, wb, rg_byte_pos)
+    return out
+
+
+def mult_argb_rows(argb, inverse):
+    out = np.array(argb, np.uint32)
+    for r in range(out.shape[0]):
+        lib().orc_mult_argb_row(_p(out[r]), out.shape[1], int(inverse))
+    return out
+
+
+def mult_rows(plane, alpha, inverse):
+    out = np.array(plane, np.uint8)
+    alpha = np.ascontiguousarray(alpha, np.uint8)
+    for r in range(out.shape[0]):
+        lib().orc_mult_row(_p(out[r]), _p(alpha[r]), out.shape[1], int(inverse))
+    return out
+
+
+def sampler_process_plane(y, u, v, mode):
+    """WebPSamplerProcessPlane (dsp/yuv.go:47-58) = EmitSampledRGB: point-sampled chroma."""
+    y, u, v = (np.ascontiguousarray(x, np.uint8) for x in (y, u, v))
+    h, w = y.shape
+    bpp = lib().orc_mode_bpp(mode)
+    dst = np.zeros((h, w * bpp), np.uint8)
+    lib().orc_sampler_process_plane(mode, _p(y), w, _p(u), _p(v), u.shape[1], _p(dst), w * bpp, w, h)
+    return dst
+
+
+def yuv444_to_rgb(y, u, v, mode):
+    y, u, v = (np.ascontiguousarray(x, np.uint8) for x in (y, u, v))
+    h, w = y.shape
+    bpp = lib().orc_mode_bpp(mode)
+    dst = np.zeros((h, w * bpp), np.uint8)
+    for r in range(h):
+        lib().orc_yuv444_row(mode, _p(y[r]), _p(u[r]), _p(v[r]), _p(dst[r]), w)
+    return dst

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_strerror():
     lib = _abi.load()
-    assert lib.b2_abi_version() == 0x0103
+    assert lib.b2_abi_version() == 0x0104
     assert lib.b2_strerror(0) == b"ok"
     # messages are the reference's sentinels (pkg/picture/errors.go:8-21)
     assert lib.b2_strerror(_abi.B2_ERR_BAD_DIM) == b"picture has invalid width/height"
@@ -44,6 +44,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_abi.PlainJob) == 5 * 8 + 8 * 4
     assert C.sizeof(_abi.AlphaIndexJob) == 3 * 8 + 4 * 4
     assert C.sizeof(_abi.ExpandJob) == 2 * 8 + 2 * 4
+    assert C.sizeof(_abi.ConvertJob) == 4 * 8 + 6 * 4
 
 
 def test_null_context_is_rejected_without_a_gpu():

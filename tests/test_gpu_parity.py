@@ -581,3 +581,64 @@ def test_emit_fancy_rgb_streaming(gpu):
             mb_y += mb_h
         assert total == h
         assert (dst == exp.reshape(h, w * bpp)).all(), (w, h, mode)
+
+
+# ---- output conversions -----------------------------------------------
+@pytest.mark.parametrize("mode", list(range(11)))
+def test_convert_from_bgra(gpu, mode):
+    D = gpu["dsp"]
+    rng = np.random.default_rng(200 + mode)
+    for (w, h) in [(1, 1), (3, 2), (4, 4), (7, 5), (128, 3), (131, 4), (516, 2)]:
+        argb = rng.integers(0, 2**32, (h, w), dtype=np.uint32)
+        argb[0, 0] |= 0xff000000            # opaque, translucent and transparent pixels all present
+        if w > 2:
+            argb[0, 1] &= 0x00ffffff
+        for up16 in (False, True):
+            got = D.VP8LConvertFromBGRA(argb, None, mode, upstream_16bit_order=up16)
+            assert (got == oracle.convert_from_bgra(argb, mode, int(up16))).all(), (w, h, mode, up16)
+
+
+def test_alpha_multiplies(gpu):
+    D = gpu["dsp"]
+    rng = np.random.default_rng(31)
+    for (w, h) in [(1, 1), (5, 3), (64, 4), (130, 2)]:
+        rgba = rng.integers(0, 256, (h, 4 * w + 8), dtype=np.uint8)   # stride > 4 w
+        rgba[:, 3::4][rng.random((h, rgba[:, 3::4].shape[1])) < 0.3] = 255
+        for af in (0, 1):
+            exp = rgba.copy()
+            exp[:, :4 * w] = oracle.apply_alpha_multiply(np.ascontiguousarray(rgba[:, :4 * w]), af)
+            assert (D.WebPApplyAlphaMultiply(rgba, af, w, h, rgba.shape[1]) == exp).all()
+        p16 = rng.integers(0, 256, (h, 2 * w), dtype=np.uint8)
+        for pos in (0, 1):
+            assert (D.WebPApplyAlphaMultiply4444(p16, w, h, 2 * w, pos) == oracle.apply_alpha_multiply_4444(p16, pos)).all()
+        argb = rng.integers(0, 2**32, (h, w), dtype=np.uint32)
+        argb[rng.random((h, w)) < 0.2] |= 0xff000000
+        argb[rng.random((h, w)) < 0.2] &= 0x00ffffff
+        plane = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        alpha = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        alpha[rng.random((h, w)) < 0.2] = 255
+        alpha[rng.random((h, w)) < 0.2] = 0
+        for inv in (0, 1):
+            if inv:   # the inverse scale needs premultiplied input (value <= alpha), as the reference asserts
+                a8 = (argb >> 24)
+                m = np.minimum
+                src = (argb & 0xff000000) | m(argb & 0xff, a8) | (m((argb >> 8) & 0xff, a8) << 8) | (m((argb >> 16) & 0xff, a8) << 16)
+                pl = np.minimum(plane, alpha)
+            else:
+                src, pl = argb, plane
+            assert (D.WebPMultARGBRows(src, w, h, inv) == oracle.mult_argb_rows(src, inv)).all()
+            assert (D.WebPMultRows(pl, alpha, w, h, inv) == oracle.mult_rows(pl, alpha, inv)).all()
+
+
+@pytest.mark.parametrize("mode", list(range(11)))
+def test_point_sampler_and_yuv444(gpu, mode):
+    D = gpu["dsp"]
+    rng = np.random.default_rng(300 + mode)
+    for (w, h) in [(1, 1), (2, 3), (5, 4), (127, 3), (260, 5)]:
+        y = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        u = rng.integers(0, 256, ((h + 1) // 2, (w + 1) // 2), dtype=np.uint8)
+        v = rng.integers(0, 256, ((h + 1) // 2, (w + 1) // 2), dtype=np.uint8)
+        assert (D.WebPSamplerProcessPlane(y, u, v, mode) == oracle.sampler_process_plane(y, u, v, mode)).all(), (w, h, mode)
+        u4 = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        v4 = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        assert (D.WebPYUV444ToRGB(y, u4, v4, mode) == oracle.yuv444_to_rgb(y, u4, v4, mode)).all(), (w, h, mode)

@@ -132,3 +132,40 @@ def test_synth_generator_matches_spec():
            ^ np.uint64((plane * 0x85EBCA77) & 0xffffffff)
            ^ ((yy * 0xC2B2AE3D) & 0xffffffff) ^ ((xx * 0x27D4EB2F) & 0xffffffff))
     assert (got == lowbias32(key)).all()
+
+
+# ---- oracle_post.c: identities that pin the restatement -----------------
+def test_post_conversions_identities():
+    rng = np.random.default_rng(17)
+    argb = rng.integers(0, 2**32, (6, 37), dtype=np.uint32)
+    a, r, g, b = (argb >> 24) & 0xff, (argb >> 16) & 0xff, (argb >> 8) & 0xff, argb & 0xff
+    bgra = oracle.convert_from_bgra(argb, oracle.MODE_BGRA)
+    assert (bgra.view(np.uint32) == argb).all()                                  # CopyOrSwap(…, 1) on little endian
+    rgba = oracle.convert_from_bgra(argb, oracle.MODE_RGBA)
+    assert (rgba[:, 0::4] == r).all() and (rgba[:, 3::4] == a).all()
+    rgb = oracle.convert_from_bgra(argb, oracle.MODE_RGB)
+    assert (rgb[:, 0::3] == r).all() and (rgb[:, 1::3] == g).all() and (rgb[:, 2::3] == b).all()
+    # premultiply == (int)(x * a / 255.) for every 8-bit pair (alpha_processing.go:96-99)
+    x, al = np.meshgrid(np.arange(256, dtype=np.uint32), np.arange(256, dtype=np.uint32))
+    px = np.zeros((256, 256 * 4), np.uint8)
+    px[:, 0::4] = x; px[:, 1::4] = x; px[:, 2::4] = x; px[:, 3::4] = al
+    pm = oracle.apply_alpha_multiply(px, 0)
+    want = np.where(al == 255, x, (x * al) // 255)
+    assert (pm[:, 0::4] == want).all() and (pm[:, 3::4] == al).all()
+    # rgbA == RGBA then premultiply; 16-bit orders are byte swaps of each other
+    assert (oracle.convert_from_bgra(argb, oracle.MODE_rgbA) == oracle.apply_alpha_multiply(rgba, 0)).all()
+    for m in (oracle.MODE_RGBA_4444, oracle.MODE_RGB_565, oracle.MODE_rgbA_4444):
+        s0, s1 = oracle.convert_from_bgra(argb, m, 0), oracle.convert_from_bgra(argb, m, 1)
+        assert (s0[:, 0::2] == s1[:, 1::2]).all() and (s0[:, 1::2] == s1[:, 0::2]).all()
+    # point sampling == 4:4:4 conversion of the replicated chroma; WebPMultRow(255 alpha) is the identity
+    y = rng.integers(0, 256, (5, 9), dtype=np.uint8)
+    u = rng.integers(0, 256, (3, 5), dtype=np.uint8)
+    v = rng.integers(0, 256, (3, 5), dtype=np.uint8)
+    rep = lambda c: np.repeat(np.repeat(c, 2, axis=0), 2, axis=1)[:5, :9]  # noqa: E731
+    for m in range(11):
+        assert (oracle.sampler_process_plane(y, u, v, m) == oracle.yuv444_to_rgb(y, rep(u), rep(v), m)).all()
+    assert (oracle.mult_rows(y, np.full_like(y, 255), 0) == y).all()
+    assert (oracle.mult_rows(y, np.zeros_like(y), 0) == 0).all()
+    # multiply then inverse-multiply recovers premultiplied values up to the reference's own rounding
+    m1 = oracle.mult_argb_rows(argb | 0x80000000, 0)
+    assert ((m1 >> 24) == ((argb | 0x80000000) >> 24)).all()

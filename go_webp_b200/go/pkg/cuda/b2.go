@@ -359,3 +359,83 @@ func (c *Context) ExpandColorMap(stream int, jobs []ExpandJob) error {
 	}
 	return status(c, C.b2_vp8l_expand_color_map(c.h, C.int(stream), &cj[0], C.int(len(cj))))
 }
+
+// PredictorInverse / PredictorForward run the VP8L predictor transform on whole images
+// (pkg/libwebp/dsp/lossless.go:31-333, lossless_enc.go:339-557); jobs[i].Data is the
+// mode image, Bits the transform's size bits.
+func (c *Context) PredictorInverse(stream int, jobs []ArgbJob) error { return c.predictor(stream, jobs, true) }
+func (c *Context) PredictorForward(stream int, jobs []ArgbJob) error { return c.predictor(stream, jobs, false) }
+
+func (c *Context) predictor(stream int, jobs []ArgbJob, inverse bool) error {
+	if len(jobs) == 0 {
+		return nil
+	}
+	cj := make([]C.b2_argb_job, len(jobs))
+	for i, j := range jobs {
+		cj[i] = C.b2_argb_job{
+			src:  (*C.uint32_t)(unsafe.Pointer(uintptr(j.Src))),
+			dst:  (*C.uint32_t)(unsafe.Pointer(uintptr(j.Dst))),
+			data: (*C.uint32_t)(unsafe.Pointer(uintptr(j.Data))),
+			width: C.int32_t(j.Width), height: C.int32_t(j.Height), bits: C.int32_t(j.Bits),
+		}
+	}
+	if inverse {
+		return status(c, C.b2_vp8l_predictor_inverse(c.h, C.int(stream), &cj[0], C.int(len(cj))))
+	}
+	return status(c, C.b2_vp8l_predictor_forward(c.h, C.int(stream), &cj[0], C.int(len(cj))))
+}
+
+// ConvertJob is one image of the output conversions (include/b2webp.h b2_convert_job).
+type ConvertJob struct {
+	Src, U, V, Dst                    DevicePtr
+	SrcStride, UVStride, DstStride    int
+	Width, Height                     int
+}
+
+func convertJobs(jobs []ConvertJob) []C.b2_convert_job {
+	cj := make([]C.b2_convert_job, len(jobs))
+	for i, j := range jobs {
+		cj[i] = C.b2_convert_job{
+			src: unsafe.Pointer(uintptr(j.Src)),
+			u:   (*C.uint8_t)(unsafe.Pointer(uintptr(j.U))),
+			v:   (*C.uint8_t)(unsafe.Pointer(uintptr(j.V))),
+			dst: (*C.uint8_t)(unsafe.Pointer(uintptr(j.Dst))),
+			src_stride: C.int32_t(j.SrcStride), uv_stride: C.int32_t(j.UVStride), dst_stride: C.int32_t(j.DstStride),
+			width: C.int32_t(j.Width), height: C.int32_t(j.Height),
+		}
+	}
+	return cj
+}
+
+// ConvertFromBGRA replaces VP8LConvertFromBGRA (pkg/libwebp/dsp/lossless.go:616-666).
+func (c *Context) ConvertFromBGRA(stream int, jobs []ConvertJob, mode, flags int) error {
+	if len(jobs) == 0 {
+		return nil
+	}
+	cj := convertJobs(jobs)
+	return status(c, C.b2_vp8l_convert_from_bgra(c.h, C.int(stream), &cj[0], C.int(len(cj)), C.int(mode), C.int(flags)))
+}
+
+// AlphaMultiply replaces ApplyAlphaMultiply_C / ..4444_C / WebPMultARGBRow_C / WebPMultRow_C
+// (pkg/libwebp/dsp/alpha_processing.go:17-163); kind is one of the B2_ALPHA_* values.
+func (c *Context) AlphaMultiply(stream int, jobs []ConvertJob, kind, flag int) error {
+	if len(jobs) == 0 {
+		return nil
+	}
+	cj := convertJobs(jobs)
+	return status(c, C.b2_alpha_multiply(c.h, C.int(stream), &cj[0], C.int(len(cj)), C.int(kind), C.int(flag)))
+}
+
+// YUVToRGBPoint replaces WebPSamplers[]/WebPSamplerProcessPlane (pkg/libwebp/dsp/yuv.go:19-72)
+// and, with yuv444, WebPYUV444Converters[] (pkg/libwebp/dsp/upsampling.c.go:191-245).
+func (c *Context) YUVToRGBPoint(stream int, jobs []ConvertJob, mode int, yuv444 bool) error {
+	if len(jobs) == 0 {
+		return nil
+	}
+	cj := convertJobs(jobs)
+	f := 0
+	if yuv444 {
+		f = 1
+	}
+	return status(c, C.b2_yuv_to_rgb_point(c.h, C.int(stream), &cj[0], C.int(len(cj)), C.int(mode), C.int(f)))
+}

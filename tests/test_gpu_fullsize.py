@@ -152,3 +152,36 @@ def test_config4_mixed_sizes_full_pipeline(env):
     res = dsp.VP8LInverseTransformBatch([dsp.VP8LImage(a, w, h) for a, (w, h) in zip(argbs, sizes)], chains)
     for r, a, ch in zip(res, argbs, chains):
         assert (r == oracle.add_green(oracle.color_space_inverse(a, ch[1].data, 4))).all()
+
+
+@pytest.mark.parametrize("size", [(16383, 5), (6, 16383)])
+def test_maximum_dimension(env, size):
+    """WEBP_MAX_DIMENSION = 16383 (pkg/libwebp/webp/encode.h.go:95) in either direction,
+    odd on purpose: import, fancy upsample, VP8L chain and predictor through the public
+    mirror of the reference API, against the oracle."""
+    from go_webp_b200 import _abi, dsp, picture
+    w, h = size
+    rng = np.random.default_rng(w + h)
+    rgba = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+    rgba[..., 3][rng.random((h, w)) < 0.8] = 255
+    pic = picture.Picture(Width=w, Height=h)
+    assert picture.WebPPictureImportRGBA(pic, rgba, 4 * w) == 1
+    y, u, v, a, ha = oracle.import_yuva(rgba, w, h, "RGBA")
+    assert (pic.Y == y).all() and (pic.U == u).all() and (pic.V == v).all() and (pic.A == a).all()
+    out = picture.YUVAToRGBABatch([pic], _abi.MODE_RGBA)[0]
+    assert (out == oracle.yuva_to_rgba(y, u, v, a, oracle.MODE_RGBA).reshape(h, 4 * w)).all()
+    bits = 4
+    argb = rng.integers(0, 2**32, (h, w), dtype=np.uint32)
+    codes = rng.integers(0, 2**24, (dsp.VP8LSubSampleSize(h, bits), dsp.VP8LSubSampleSize(w, bits)), dtype=np.uint32)
+    modes = rng.integers(0, 16, codes.shape, dtype=np.uint32) << 8
+    chain = [dsp.VP8LTransform(dsp.PREDICTOR_TRANSFORM, bits, w, h, modes),
+             dsp.VP8LTransform(dsp.CROSS_COLOR_TRANSFORM, bits, w, h, codes),
+             dsp.VP8LTransform(dsp.SUBTRACT_GREEN_TRANSFORM, 0, w, h)]
+    got = dsp.VP8LInverseTransformBatch([dsp.VP8LImage(argb, w, h)], [chain])[0]
+    exp = oracle.predictor_inverse(oracle.color_space_inverse(oracle.add_green(argb), codes, bits), modes, bits)
+    assert (got.reshape(h, w) == exp).all()
+    pal = rng.integers(0, 2**32, 4, dtype=np.uint32)
+    sw = dsp.VP8LSubSampleSize(w, 2)
+    packed = rng.integers(0, 2**32, (h, sw), dtype=np.uint32)
+    t = dsp.VP8LTransform(dsp.COLOR_INDEXING_TRANSFORM, 2, w, h, pal)
+    assert (dsp.VP8LInverseTransform(t, 0, h, packed) == oracle.color_index_inverse(packed, pal, 2, w)).all()

@@ -339,7 +339,7 @@ extern "C" int b2_rgba_to_yuv420a(b2_ctx* ctx, int stream, const b2_import_job* 
     if (j.a && (((uintptr_t)j.a | (uintptr_t)(uint32_t)j.a_stride) & 3) == 0) d.flags |= JOB_A_ALIGNED;
     if ((((uintptr_t)j.u | (uintptr_t)j.v | (uintptr_t)(uint32_t)j.uv_stride) & 1) == 0) d.flags |= JOB_UV_ALIGNED;
     if ((((uintptr_t)j.src | (uintptr_t)(uint32_t)j.src_stride) & 3) != 0) fast = false;
-    if ((((uintptr_t)j.src | (uintptr_t)(uint32_t)j.src_stride) & 15) != 0 || (j.width & 3) != 0 ||
+    if ((((uintptr_t)j.src | (uintptr_t)(uint32_t)j.src_stride) & 3) != 0 ||
         !(d.flags & JOB_Y_ALIGNED) || !(d.flags & JOB_UV_ALIGNED) || (j.a && !(d.flags & JOB_A_ALIGNED))) tuned = false;
     n_with_a += (j.a != NULL);
     const uint32_t units = (uint32_t)((j.height + 1) >> 1);

@@ -15,8 +15,8 @@ struct ImportJobDev {
 };
 enum { JOB_Y_ALIGNED = 1, JOB_A_ALIGNED = 2, JOB_UV_ALIGNED = 4 };
 
-// Fast path (b2_import_fast.cu): every job is step 4, width % 4 == 0, source rows
-// 16-byte aligned, Y/A rows 4-byte and U/V rows 2-byte aligned.  unit_prefix counts
+// Fast path (b2_import_fast.cu): every job is step 4, source rows 4-byte aligned
+// (pointer and stride, any width), Y/A rows 4-byte and U/V rows 2-byte aligned.  unit_prefix counts
 // row pairs.  Returns a cudaError_t from the launch.
 cudaError_t b2_import_fast_launch(const b2_ctx* ctx, cudaStream_t s, const ImportJobDev* jobs,
                                   const uint32_t* unit_prefix, uint32_t n_jobs,

@@ -1,5 +1,6 @@
 // b2_import_fast.cu -- tuned RGBA -> YUV420(+A) import for the common case: 4-byte
-// pixels, width % 4 == 0, 16-byte aligned source rows, aligned planes.
+// pixels, 4-byte aligned source rows (128-bit loads when they are 16-byte aligned),
+// any width, 4-byte aligned Y/A rows.
 //
 // Same arithmetic as b2_import.cu (pkg/libwebp/dsp/yuv.go:124-382,
 // pkg/color/yuv/conversion.go:51-69); what changes is the instruction budget.  The
@@ -185,15 +186,28 @@ import_fast_kernel(const ImportJobDev* __restrict__ jobs, const uint32_t* __rest
     // Lanes past the end of the row run on zeros (every lane takes part in the vote of
     // block_sums) and store nothing.
     int x = (int)lane4;
+    // rows that are only 4-byte aligned (a tight 4*width stride with width % 4 != 0) are
+    // read with 32-bit loads of the valid pixels; 16-byte aligned rows with one 128-bit load
+    const bool al16 = ((((uintptr_t)jp->src) | (uintptr_t)(uint32_t)sstride) & 15) == 0;  // warp-uniform
+    auto load4 = [&](const uint8_t* p, int xx) -> uint4 {
+      if (al16) return b2_ldg_stream_v4(p);
+      const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
+      uint4 r;
+      r.x = __ldg(q);
+      r.y = (xx + 1 < width) ? __ldg(q + 1) : 0u;
+      r.z = (xx + 2 < width) ? __ldg(q + 2) : 0u;
+      r.w = (xx + 3 < width) ? __ldg(q + 3) : 0u;
+      return r;
+    };
     uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0;
     bool cur_ok = x < width;
-    if (cur_ok) { c0 = b2_ldg_stream_v4(s0); c1 = b2_ldg_stream_v4(s1); }
+    if (cur_ok) { c0 = load4(s0, x); c1 = load4(s1, x); }
     const int tiles_x = (width + 127) >> 7;
     for (int t = 0; t < tiles_x; ++t) {
       const int xn = x + 128;
       const bool nxt_ok = xn < width;
       uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;
-      if (nxt_ok) { n0 = b2_ldg_stream_v4(s0 + 512); n1 = b2_ldg_stream_v4(s1 + 512); }
+      if (nxt_ok) { n0 = load4(s0 + 512, xn); n1 = load4(s1 + 512, xn); }
 #if B2_IMPORT_L2_PREFETCH
       // Optional: pull the strips after that into L2.  Measured (profiles/r01d_*): with
       // opaque input the kernel waits on load latency and distance 5 gains 3%, but with
@@ -204,6 +218,17 @@ import_fast_kernel(const ImportJobDev* __restrict__ jobs, const uint32_t* __rest
         asm volatile("prefetch.global.L2 [%0];" :: "l"(s1 + 512 * B2_IMPORT_L2_PREFETCH));
       }
 #endif
+      // Last group of a row whose width is not a multiple of 4: a 128-bit load stays inside
+      // the row's 16-byte-aligned stride span, the 32-bit loads fetch valid pixels only;
+      // the missing pixels become copies of valid ones.  Duplicating the odd last column is exactly the reference's SUM2 / SUM2ALPHA
+      // forms (yuv.go:211-213,270-277: twice a 2-pixel sum == the 4-pixel sum of the
+      // duplicated column), and copies cannot disturb the has-alpha reduction.
+      const int nvalid = width - x;
+      if (nvalid < 4 && nvalid > 0) {
+        if (nvalid == 1) { c0.y = c0.x; c1.y = c1.x; }
+        if (nvalid <= 2) { c0.z = c0.x; c1.z = c1.x; c0.w = c0.y; c1.w = c1.y; }
+        else { c0.w = c0.z; c1.w = c1.z; }
+      }
       const uint32_t yw0 = pack_b2(luma_sum<ORDER>(c0.x), luma_sum<ORDER>(c0.y), luma_sum<ORDER>(c0.z), luma_sum<ORDER>(c0.w));
       const uint32_t yw1 = pack_b2(luma_sum<ORDER>(c1.x), luma_sum<ORDER>(c1.y), luma_sum<ORDER>(c1.z), luma_sum<ORDER>(c1.w));
       uint32_t ap0 = 0xffffffffu, ap1 = 0xffffffffu;
@@ -219,7 +244,7 @@ import_fast_kernel(const ImportJobDev* __restrict__ jobs, const uint32_t* __rest
       const int r1 = l2g(smem, sr1, lane8), g1 = l2g(smem, sg1, lane8), b1 = l2g(smem, sb1, lane8);
       const uint32_t uu = __byte_perm(u_sum(r0, g0, b0), u_sum(r1, g1, b1), 0x0073);
       const uint32_t vv = __byte_perm(v_sum(r0, g0, b0), v_sum(r1, g1, b1), 0x0073);
-      if (cur_ok) {
+      if (nvalid >= 4) {
         b2_stg_stream_u32(yp, yw0);
         if (has_row1) b2_stg_stream_u32(yp + ystride, yw1);
         if (WRITE_A) {
@@ -228,6 +253,17 @@ import_fast_kernel(const ImportJobDev* __restrict__ jobs, const uint32_t* __rest
         }
         b2_stg_stream_u16(up, uu);
         b2_stg_stream_u16(vp, vv);
+      } else if (nvalid > 0) {  // partial group: byte stores of the valid samples only
+        for (int k = 0; k < nvalid; ++k) {
+          yp[k] = (uint8_t)(yw0 >> (8 * k));
+          if (has_row1) yp[ystride + k] = (uint8_t)(yw1 >> (8 * k));
+          if (WRITE_A) {
+            ap[k] = (uint8_t)(ap0 >> (8 * k));
+            if (has_row1) ap[astride + k] = (uint8_t)(ap1 >> (8 * k));
+          }
+        }
+        up[0] = (uint8_t)uu; vp[0] = (uint8_t)vv;
+        if (nvalid > 2) { up[1] = (uint8_t)(uu >> 8); vp[1] = (uint8_t)(vv >> 8); }
       }
       s0 += 512; s1 += 512; yp += 128; up += 64; vp += 64;
       if (WRITE_A) ap += 128;

@@ -185,3 +185,24 @@ def test_maximum_dimension(env, size):
     packed = rng.integers(0, 2**32, (h, sw), dtype=np.uint32)
     t = dsp.VP8LTransform(dsp.COLOR_INDEXING_TRANSFORM, 2, w, h, pal)
     assert (dsp.VP8LInverseTransform(t, 0, h, packed) == oracle.color_index_inverse(packed, pal, 2, w)).all()
+
+
+@pytest.mark.parametrize("size", [(5, 5), (6, 2), (7, 3), (13, 7), (130, 5), (1917, 4), (1918, 3), (1919, 5)])
+@pytest.mark.parametrize("alpha_mode", [0, 2, 3])
+def test_tuned_import_tight_rows_any_width(env, size, alpha_mode):
+    """Tight source rows (stride 4*w, only 4-byte aligned when w % 4 != 0) with padded
+    planes take the tuned kernel's 32-bit-load path and its partial last group: the odd
+    last column must behave as the reference's SUM2 / SUM2ALPHA forms (yuv.go:270-277)."""
+    ctx, PL = env["ctx"], env["pipeline"]
+    w, h = size
+    n, seed = 3, 0xB2000005
+    p = PL.ImportPipeline(ctx, n, w, h, host=False)
+    p.fill_synthetic(seed, 0, alpha_mode)
+    p.run_device()
+    ctx.sync()
+    for i in range(n):
+        src = oracle.synth_u32(seed, i, 0, w, h, alpha_mode).view(np.uint8)
+        ey, eu, ev, ea, eha = oracle.import_yuva(src, w, h, "RGBA")
+        gy, gu, gv, ga, gha = p.device_planes(i)
+        assert (gy == ey).all() and (gu == eu).all() and (gv == ev).all() and (ga == ea).all() and gha == eha, (size, i)
+    p.close()

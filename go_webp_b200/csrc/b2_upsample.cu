@@ -370,19 +370,19 @@ __device__ __forceinline__ XposeLane xpose_lane(int lane) {
 
 // One 256-pixel pass of a warp: every lane converts 8 pixels x 2 rows (lanes past the
 // end of the row compute on stale stage bytes and store nothing).  xpass = first pixel
-// of the pass, wv = width rounded down to 8 (the part of the row the vector path
-// covers); drt/drb = start of the two output rows; xs = this warp's transposition
-// buffer (top row at 0, bottom row at 1024).
-template <int ST, bool HAS_ALPHA>
+// of the pass, wv = number of pixels of the row the vector path covers (the width for
+// the 4-byte modes, whose stores are masked per pixel; the width rounded down to 8 for
+// the 3-byte modes); drt/drb = start of the two output rows; xs = this warp's
+// transposition buffer (top row at 0, bottom row at 1024).
+template <int ST, bool HAS_ALPHA, bool EDGE>
 __device__ __forceinline__ void convert_pass(const uint8_t* sy, const uint8_t* sa, const uint8_t* sc, int lane,
                                              int xpass, int wv, int uw, bool top_ok, bool bot_ok, uint8_t* drt,
                                              uint8_t* drb, const B2YuvConsts& kc, uint8_t* xs, const XposeLane& xl) {
   constexpr int R = BulkLayout<HAS_ALPHA>::kCRow;
   constexpr int kTileW = BulkLayout<HAS_ALPHA>::kTW;
   constexpr int kBpp = (ST == ST_RGB || ST == ST_BGR) ? 3 : 4;
-  const int xh = xpass + lane * 8, c0 = xh >> 1;
-  const int loff = (c0 == 0) ? 0 : -1;      // left neighbour, mirrored at column 0
-  const int roff = (c0 + 4 >= uw) ? 3 : 4;  // right neighbour, mirrored at the last column
+  const int xh = xpass + lane * 8;
+  constexpr int loff = -1, roff = 4;  // left / right neighbour samples; the image edges are fixed up below
   const uint2 yt = *reinterpret_cast<const uint2*>(sy);
   const uint2 yb = *reinterpret_cast<const uint2*>(sy + kTileW);
   uint2 at = make_uint2(0, 0), ab = make_uint2(0, 0);
@@ -390,14 +390,29 @@ __device__ __forceinline__ void convert_pass(const uint8_t* sy, const uint8_t* s
     at = *reinterpret_cast<const uint2*>(sa);
     ab = *reinterpret_cast<const uint2*>(sa + kTileW);
   }
-  const uint32_t wtu = *reinterpret_cast<const uint32_t*>(sc);
-  const uint32_t wcu = *reinterpret_cast<const uint32_t*>(sc + R);
-  const uint32_t wtv = *reinterpret_cast<const uint32_t*>(sc + 2 * R);
-  const uint32_t wcv = *reinterpret_cast<const uint32_t*>(sc + 3 * R);
+  uint32_t wtu = *reinterpret_cast<const uint32_t*>(sc);
+  uint32_t wcu = *reinterpret_cast<const uint32_t*>(sc + R);
+  uint32_t wtv = *reinterpret_cast<const uint32_t*>(sc + 2 * R);
+  uint32_t wcv = *reinterpret_cast<const uint32_t*>(sc + 3 * R);
   const uint8_t* lp = sc + loff;
   const uint8_t* rp = sc + roff;
-  const uint32_t ltu = lp[0], lcu = lp[R], ltv = lp[2 * R], lcv = lp[3 * R];
-  const uint32_t rtu = rp[0], rcu = rp[R], rtv = rp[2 * R], rcv = rp[3 * R];
+  uint32_t ltu = lp[0], lcu = lp[R], ltv = lp[2 * R], lcv = lp[3 * R];
+  uint32_t rtu = rp[0], rcu = rp[R], rtv = rp[2 * R], rcv = rp[3 * R];
+  // Image edges mirror the chroma samples (upsampling.c.go:57,61,93,98).  Only the EDGE
+  // instantiation (first and last pass of a row) carries this code and the masked
+  // stores below; interior passes are straight-line.
+  if (EDGE && xpass == 0 && lane == 0) { ltu = wtu & 0xff; lcu = wcu & 0xff; ltv = wtv & 0xff; lcv = wcv & 0xff; }
+  if (EDGE && xpass + 256 >= 2 * uw) {
+    // kk = position of the last chroma column in this lane's 4-sample word: 3 -> the right
+    // neighbour is its copy; 0..2 (a row that ends inside this lane's 8 pixels) -> the
+    // sample after it inside the word is its copy
+    const int kk = uw - 1 - (xh >> 1);
+    if (kk == 3) { rtu = wtu >> 24; rcu = wcu >> 24; rtv = wtv >> 24; rcv = wcv >> 24; }
+    else if (kk >= 0 && kk < 3) {
+      const uint32_t sel = (kk == 0) ? 0x3200u : (kk == 1) ? 0x3110u : 0x2210u;
+      wtu = b2_prmt(wtu, 0u, sel); wcu = b2_prmt(wcu, 0u, sel); wtv = b2_prmt(wtv, 0u, sel); wcv = b2_prmt(wcv, 0u, sel);
+    }
+  }
   const uint32_t etu = b2_even(wtu), otu = b2_odd(wtu), mtu = b2_prmt(etu, rtu, 0x5432);
   const uint32_t ecu = b2_even(wcu), ocu = b2_odd(wcu), mcu = b2_prmt(ecu, rcu, 0x5432);
   const uint32_t etv = b2_even(wtv), otv = b2_odd(wtv), mtv = b2_prmt(etv, rtv, 0x5432);
@@ -408,10 +423,10 @@ __device__ __forceinline__ void convert_pass(const uint8_t* sy, const uint8_t* s
   // column pair (left,c0) -> pixel 0, U in the low lane and V in the high lane
   const B2Quad16 cq = b2_interp16(b2_prmt(ltu, ltv, 0x5410), b2_prmt(etu, etv, 0x5410),
                                   b2_prmt(lcu, lcv, 0x5410), b2_prmt(ecu, ecv, 0x5410));
-  const bool lane_ok = xh + 8 <= wv;
+  const bool lane_ok = !EDGE || xh + 8 <= wv;
   // 3-byte modes: only full passes are transposed (768 contiguous bytes per row); the
   // last, partial pass of a row stores straight from the lanes
-  const bool full3 = (kBpp == 3) && (xpass + 256 <= wv);
+  const bool full3 = (kBpp == 3) && (!EDGE || xpass + 256 <= wv);
   uint8_t* const xst = (kBpp == 4 || full3) ? xs : nullptr;
   const uint32_t xw0 = (kBpp == 4) ? xl.w0 : (uint32_t)lane * 24u;
   if (top_ok) {
@@ -429,16 +444,35 @@ __device__ __forceinline__ void convert_pass(const uint8_t* sy, const uint8_t* s
   if (kBpp == 4) {
     __syncwarp();
     const int xa = xpass + lane * 4;  // this lane stores pixels xa..xa+3 and xa+128..xa+131
-    const bool ok0 = xa + 4 <= wv, ok1 = xa + 132 <= wv;
+    // wv is the image width here: the last group of a row may hold 1..3 pixels
+    auto put4 = [&](uint8_t* d, const uint8_t* src, int n) {
+      const uint4 v = *reinterpret_cast<const uint4*>(src);
+      if (n >= 4) { b2_stg_stream_v4(d, v); return; }
+      if (n > 0) b2_stg_stream_u32(d, v.x);
+      if (n > 1) b2_stg_stream_u32(d + 4, v.y);
+      if (n > 2) b2_stg_stream_u32(d + 8, v.z);
+    };
+    const bool full = !EDGE || xpass + 256 <= wv;  // warp-uniform: every pass but the last one of a row
+    const int n0 = full ? 4 : wv - xa, n1 = full ? 4 : wv - xa - 128;
     if (top_ok) {
       uint8_t* d = drt + xa * 4;
-      if (ok0) b2_stg_stream_v4(d, *reinterpret_cast<const uint4*>(xs + xl.r));
-      if (ok1) b2_stg_stream_v4(d + 512, *reinterpret_cast<const uint4*>(xs + 512 + xl.r));
+      if (full) {
+        b2_stg_stream_v4(d, *reinterpret_cast<const uint4*>(xs + xl.r));
+        b2_stg_stream_v4(d + 512, *reinterpret_cast<const uint4*>(xs + 512 + xl.r));
+      } else {
+        put4(d, xs + xl.r, n0);
+        put4(d + 512, xs + 512 + xl.r, n1);
+      }
     }
     if (bot_ok) {
       uint8_t* d = drb + xa * 4;
-      if (ok0) b2_stg_stream_v4(d, *reinterpret_cast<const uint4*>(xs + 1024 + xl.r));
-      if (ok1) b2_stg_stream_v4(d + 512, *reinterpret_cast<const uint4*>(xs + 1536 + xl.r));
+      if (full) {
+        b2_stg_stream_v4(d, *reinterpret_cast<const uint4*>(xs + 1024 + xl.r));
+        b2_stg_stream_v4(d + 512, *reinterpret_cast<const uint4*>(xs + 1536 + xl.r));
+      } else {
+        put4(d, xs + 1024 + xl.r, n0);
+        put4(d + 512, xs + 1536 + xl.r, n1);
+      }
     }
     __syncwarp();
   } else if (full3) {
@@ -559,7 +593,8 @@ upsample_bulk_kernel(const UpsampleJobDev* __restrict__ jobs, const uint32_t* __
     const int row_begin = jp->row_begin, row_end = jp->row_end;
     const bool top_ok = (rt >= row_begin) && (rt < row_end), bot_ok = (rb >= row_begin) && (rb < row_end);
     const int dstride = jp->dst_stride;
-    const int wv = width & ~7;  // the vector path covers pixels [0, wv)
+    constexpr int kBppK = (ST == ST_RGB || ST == ST_BGR) ? 3 : 4;
+    const int wv = (kBppK == 4) ? width : (width & ~7);  // the vector path covers pixels [0, wv)
     uint8_t* const drt = jp->dst + (ptrdiff_t)(top_ok ? rt : rb) * dstride;
     uint8_t* const drb = jp->dst + (ptrdiff_t)(bot_ok ? rb : rt) * dstride;
     const int tiles = (width + kTileW - 1) / kTileW;
@@ -571,15 +606,19 @@ upsample_bulk_kernel(const UpsampleJobDev* __restrict__ jobs, const uint32_t* __
 #pragma unroll kPassUnroll
       for (int p = 0; p < kTileW / 256; ++p) {
         const int xpass = t * kTileW + p * 256;
-        if (xpass < wv)
-          convert_pass<ST, HAS_ALPHA>(sp + BL::kY + p * 256 + lane * 8, sp + BL::kA + p * 256 + lane * 8,
-                                      sp + BL::kC + 16 + p * 128 + lane * 4, lane, xpass, wv, uw, top_ok, bot_ok,
-                                      drt, drb, kc, xbuf, xl);
+        if (xpass >= wv) break;
+        const uint8_t* sy = sp + BL::kY + p * 256 + lane * 8;
+        const uint8_t* sa = sp + BL::kA + p * 256 + lane * 8;
+        const uint8_t* sc = sp + BL::kC + 16 + p * 128 + lane * 4;
+        if (xpass == 0 || xpass + 256 >= 2 * uw || xpass + 256 > wv)  // warp-uniform: first / last pass of the row
+          convert_pass<ST, HAS_ALPHA, true>(sy, sa, sc, lane, xpass, wv, uw, top_ok, bot_ok, drt, drb, kc, xbuf, xl);
+        else
+          convert_pass<ST, HAS_ALPHA, false>(sy, sa, sc, lane, xpass, wv, uw, top_ok, bot_ok, drt, drb, kc, xbuf, xl);
       }
       __syncwarp();  // every lane is done reading this stage before it is refilled
       stage ^= 1;
     }
-    if (wv + lane < width) {  // ragged right edge (width % 8 pixels): per-pixel path straight from global
+    if (kBppK == 3 && wv + lane < width) {  // 3-byte modes: ragged right edge (width % 8 pixels), per pixel from global
       const UpsampleJobDev j = *jp;
       if (top_ok) pixel_generic<ST>(j, rt, wv + lane);
       if (bot_ok) pixel_generic<ST>(j, rb, wv + lane);

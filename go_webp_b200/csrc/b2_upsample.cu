@@ -18,6 +18,8 @@
 // plus eight halo bytes (L1 hits), four 128-bit RGBA stores.  The interpolation
 // is the reference's own 2x16-bit SWAR, here packing two columns (or U and V)
 // per 32-bit register.
+#include <stdlib.h>
+
 #include "b2_common.cuh"
 #include "b2_upsample_core.cuh"
 
@@ -667,8 +669,10 @@ extern "C" int b2_yuv420a_to_rgba_fancy(b2_ctx* ctx, int stream, const b2_upsamp
   bool tuned = (st_mode <= ST_BGR);  // 4- and 3-byte modes have a staged vector kernel
   bool staged = true;  // cp.async kernel: 16-byte aligned planes with positive strides
   int n_with_a = 0;
+  int max_width = 0;
   for (int i = 0; i < n_jobs; ++i) {
     const b2_upsample_job& j = jobs[i];
+    if (j.width > max_width) max_width = j.width;
     if (j.y == NULL || j.u == NULL || j.v == NULL || j.dst == NULL) { free(host); return B2_ERR_NULL; }
     if (j.width <= 0 || j.height <= 0 || j.width > B2_MAX_DIMENSION || j.height > B2_MAX_DIMENSION) {
       free(host); return B2_ERR_BAD_DIM;
@@ -724,7 +728,13 @@ extern "C" int b2_yuv420a_to_rgba_fancy(b2_ctx* ctx, int stream, const b2_upsamp
   const int grid = b2_grid_for(ctx, 8, (total + kWarps - 1) / kWarps);
   const uint32_t tot = (uint32_t)total;
   if (tuned && staged) {
-    const int bgrid = b2_grid_for(ctx, kBulkCtasPerSm, (utotal + kBulkWarps - 1) / kBulkWarps);
+    // Persistent CTAs per SM (of the 6 that fit).  Measured (profiles/r01d_upsample_grid_sweep.txt):
+    // 4 per SM is best for 4K rows (0.85 of the measured HBM peak vs 0.82 at 6), 5 per SM for
+    // 1080p rows (0.785 vs 0.755); the address window the warps sweep together matters
+    // more than the extra latency hiding.
+    static const int grid_override = getenv("B2_UP_GRID") ? atoi(getenv("B2_UP_GRID")) : 0;
+    const int bulk_grid_ctas = grid_override ? grid_override : (max_width >= 2560 ? 4 : 5);
+    const int bgrid = b2_grid_for(ctx, bulk_grid_ctas, (utotal + kBulkWarps - 1) / kBulkWarps);
     const uint32_t ut = (uint32_t)utotal;
     const bool ha = n_with_a != 0;
 #define B2_UPK(ST_, HA_) upsample_bulk_kernel<ST_, HA_><<<bgrid, kBulkThreads, 0, s>>>(djobs, dupre, n_jobs, uuniform, ut, b2_yuv_consts())

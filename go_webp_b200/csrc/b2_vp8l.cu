@@ -105,9 +105,50 @@ __device__ __forceinline__ Mult fetch_mult(const ArgbJobDev& j, uint32_t i) {
   }
   return m;
 }
-
+// Tile codes of the 4 consecutive flat pixels i .. i+3 (i % 4 == 0).  With width % 4
+// == 0 (and bits >= 2) they share a row and a tile; otherwise the group may run over
+// the end of a row, so every pixel looks its own tile up.
 template <int OP>
-__global__ void __launch_bounds__(kThreads, 8)
+__device__ __forceinline__ uint4 fetch_codes4(const ArgbJobDev& j, uint32_t i) {
+  uint4 c = make_uint4(0, 0, 0, 0);
+  if (!needs_codes<OP>()) return c;
+  const uint32_t w = (uint32_t)j.width;
+  const uint32_t y = i / w, x = i - y * w;
+  const uint32_t* __restrict__ row = j.data + (y >> j.bits) * j.tiles_per_row;
+  c.x = __ldg(row + (x >> j.bits));
+  if ((w & 3u) == 0) {
+    c.y = c.z = c.w = c.x;
+  } else if (x + 3 < w) {
+    c.y = __ldg(row + ((x + 1) >> j.bits)); c.z = __ldg(row + ((x + 2) >> j.bits)); c.w = __ldg(row + ((x + 3) >> j.bits));
+  } else {  // the group runs over the end of the row
+    const uint32_t* __restrict__ nrow = j.data + ((y + 1) >> j.bits) * j.tiles_per_row;
+    uint32_t xx = x + 1;
+    c.y = (xx < w) ? __ldg(row + (xx >> j.bits)) : __ldg(nrow + ((xx - w) >> j.bits));
+    xx = x + 2;
+    c.z = (xx < w) ? __ldg(row + (xx >> j.bits)) : __ldg(nrow + ((xx - w) >> j.bits));
+    xx = x + 3;
+    c.w = (xx < w) ? __ldg(row + (xx >> j.bits)) : __ldg(nrow + ((xx - w) >> j.bits));
+  }
+  return c;
+}
+template <int OP>
+__device__ __forceinline__ uint4 apply4(uint4 codes, uint4 p, bool one_tile) {
+  uint4 o;
+  if (one_tile) {  // warp-uniform (width % 4 == 0): one set of multipliers for the group
+    const Mult m = code_to_mult(codes.x);
+    o.x = apply_px<OP>(m, p.x); o.y = apply_px<OP>(m, p.y); o.z = apply_px<OP>(m, p.z); o.w = apply_px<OP>(m, p.w);
+  } else {
+    o.x = apply_px<OP>(code_to_mult(codes.x), p.x); o.y = apply_px<OP>(code_to_mult(codes.y), p.y);
+    o.z = apply_px<OP>(code_to_mult(codes.z), p.z); o.w = apply_px<OP>(code_to_mult(codes.w), p.w);
+  }
+  return o;
+}
+
+#ifndef B2_FLAT_CTAS
+#define B2_FLAT_CTAS 6
+#endif
+template <int OP>
+__global__ void __launch_bounds__(kThreads, B2_FLAT_CTAS)
 flat_kernel(const ArgbJobDev* __restrict__ jobs, const uint32_t* __restrict__ prefix,
             uint32_t n_jobs, uint32_t uniform, uint32_t total_items) {
   const int lane = threadIdx.x & 31;
@@ -122,15 +163,10 @@ flat_kernel(const ArgbJobDev* __restrict__ jobs, const uint32_t* __restrict__ pr
     if ((j.flags & JOB_VEC) && i1 + 4 <= n) {
       const uint4 a = b2_ld_stream_v4(j.src + i0);  // not .nc: dst may alias src
       const uint4 b = b2_ld_stream_v4(j.src + i1);
-      const Mult ma = fetch_mult<OP>(j, i0);
-      const Mult mb = fetch_mult<OP>(j, i1);
-      uint4 oa, ob;
-      oa.x = apply_px<OP>(ma, a.x); oa.y = apply_px<OP>(ma, a.y);
-      oa.z = apply_px<OP>(ma, a.z); oa.w = apply_px<OP>(ma, a.w);
-      ob.x = apply_px<OP>(mb, b.x); ob.y = apply_px<OP>(mb, b.y);
-      ob.z = apply_px<OP>(mb, b.z); ob.w = apply_px<OP>(mb, b.w);
-      b2_stg_stream_v4(j.dst + i0, oa);
-      b2_stg_stream_v4(j.dst + i1, ob);
+      const uint4 ca = fetch_codes4<OP>(j, i0), cb = fetch_codes4<OP>(j, i1);
+      const bool one_tile = (j.width & 3) == 0;
+      b2_stg_stream_v4(j.dst + i0, apply4<OP>(ca, a, one_tile));
+      b2_stg_stream_v4(j.dst + i1, apply4<OP>(cb, b, one_tile));
     } else {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -370,8 +406,7 @@ int prepare(b2_ctx* ctx, int stream, const b2_argb_job* jobs, int n_jobs, Kind k
         d.tiles_per_row = (uint32_t)((j.width + (1 << j.bits) - 1) >> j.bits);
         // fallthrough
       case KIND_FLAT:
-        if ((((uintptr_t)j.src | (uintptr_t)j.dst) & 15) == 0 &&
-            (kind == KIND_FLAT || (j.width & 3) == 0)) d.flags |= JOB_VEC;
+        if ((((uintptr_t)j.src | (uintptr_t)j.dst) & 15) == 0) d.flags |= JOB_VEC;
         items = (uint32_t)((n + kItemPx - 1) / kItemPx);
         break;
       case KIND_INDEX:
@@ -429,7 +464,11 @@ int run_flat(b2_ctx* ctx, int stream, const b2_argb_job* jobs, int n_jobs) {
   Prepared p;
   const int st = prepare(ctx, stream, jobs, n_jobs, needs_codes<OP>() ? KIND_FLAT_CODES : KIND_FLAT, &p);
   if (st != B2_OK) return st;
-  const int grid = b2_grid_for(ctx, 8, (p.total + kWarps - 1) / kWarps);
+  // Persistent CTAs per SM.  Measured on 4096^2 batches (profiles/r01d_flat_grid_sweep.txt):
+  // the pure copies (add/sub-green) peak at 4 per SM (0.95 of the measured HBM peak vs
+  // 0.88 at 3, 5 or 6), the cross-colour kernels need the extra warps of 6 per SM.
+  const int grid_ctas = needs_codes<OP>() ? B2_FLAT_CTAS : 4;
+  const int grid = b2_grid_for(ctx, grid_ctas, (p.total + kWarps - 1) / kWarps);
   flat_kernel<OP><<<grid, kThreads, 0, ctx->streams[stream]>>>(p.jobs, p.prefix, n_jobs, p.uniform, p.total);
   ctx->launches++;
   B2_CUDA(ctx, cudaGetLastError());
@@ -478,7 +517,9 @@ extern "C" int b2_vp8l_color_index_inverse(b2_ctx* ctx, int stream, const b2_arg
     if (st != B2_OK) return st;
     cudaStream_t s = ctx->streams[stream];
     if (rows) {
-      const int rgrid = b2_grid_for(ctx, 8, (p.total + kWarps - 1) / kWarps);
+      // 3 persistent CTAs per SM measured best for the sub-byte depths (0.85-0.92 of the
+      // measured HBM peak vs 0.80-0.84 at 8; profiles/r01d_index_grid_sweep.txt)
+      const int rgrid = b2_grid_for(ctx, 3, (p.total + kWarps - 1) / kWarps);
       switch (bits) {
         case 0: color_index_rows_kernel<0><<<rgrid, kThreads, 0, s>>>(p.jobs, p.prefix, cnt, p.uniform, p.total); break;
         case 1: color_index_rows_kernel<1><<<rgrid, kThreads, 0, s>>>(p.jobs, p.prefix, cnt, p.uniform, p.total); break;

@@ -21,23 +21,60 @@
 //     tests/test_oracle_properties.py) instead of a hardware integer division.
 #include "b2_import.cuh"
 
+#include <type_traits>
+
 namespace {
 
-#ifndef B2_IMPORT_L2_PREFETCH
-#define B2_IMPORT_L2_PREFETCH 0
+// One CTA of 1024 threads per SM: the tables are held once, every warp owns a ring of
+// kRingStages source strips in shared memory that per-thread cp.async keeps kRingStages-1
+// strips ahead of the computation.  (Measured alternatives, profiles/r01d_* and r01e_*:
+// one strip ahead in registers with 2 x 512 threads; L2 prefetch instructions.)
+#ifndef B2_IMPORT_RING
+#define B2_IMPORT_RING 2
 #endif
-constexpr int kFastThreads = 512;
+#ifndef B2_IMPORT_THREADS
+#define B2_IMPORT_THREADS 896
+#endif
+#ifndef B2_IMPORT_UNROLL
+#define B2_IMPORT_UNROLL 2
+#endif
+constexpr int kFastThreads = B2_IMPORT_THREADS;
+constexpr int kUnroll = B2_IMPORT_UNROLL;
+// kSplit warps share one row pair, taking every kSplit-th strip: fewer concurrent DRAM
+// streams for the same number of warps.
+#ifndef B2_IMPORT_CHUNKED
+#define B2_IMPORT_CHUNKED 0
+#endif
+#ifndef B2_IMPORT_SPLIT
+#define B2_IMPORT_SPLIT 1
+#endif
+constexpr int kSplit = B2_IMPORT_SPLIT;  // power of two
 constexpr int kFastWarps = kFastThreads / 32;
-constexpr int kFastCtasPerSm = 2;
+constexpr int kFastCtasPerSm = 1;
+constexpr int kRingStages = B2_IMPORT_RING;         // power of two
+constexpr int kDist = kRingStages - 1;              // strips in flight ahead of the computation
+constexpr uint32_t kStageBytes = 1024;              // row 0 at +0, row 1 at +512, 16 bytes per lane
+constexpr uint32_t kRingBytes = kRingStages * kStageBytes;   // per warp; rings are aligned to their size
+constexpr uint32_t kStageMask = kRingBytes - kStageBytes;
+static_assert((kRingStages & (kRingStages - 1)) == 0 && kRingStages >= 2 && kRingStages <= 4, "ring");
 
-// shared-memory map (byte offsets)
-//   [0, 64K)    g2l rows: row v = 256 bytes, lower half = g2l[v] << 7, one word per lane
-//   [64K, 72K)  LinearToGamma: entry pos = 256 bytes, lane l at +8 l: {base' << 7, slope d}
-//   [72K, 80K)  divide table, entry a at +8 a: exact mode {magic << 3, shift}, binary-
-//               compatible mode {kInvAlpha[a], 0}
-constexpr uint32_t kOffL2G = 65536;
-constexpr uint32_t kOffDiv = kOffL2G + 32 * 256;
-constexpr int kSmemBytes = kOffDiv + 1024 * 8;  // 80 KB
+// Shared-memory map, in shared-window addresses (what LDS takes).  T = the first 64 KB
+// boundary at or after the start of dynamic shared memory; with the tables on 64 KB
+// boundaries the lookup byte lands in address byte 1 with nothing to add, so a lookup
+// address -- window base included -- is ONE byte permute:
+//   [T, T+64K)          row v = 256 bytes, one word per lane: lower half g2l[v] << 7;
+//                       upper half of rows 0..31 LinearToGamma segment v, (base' << 7) + slope
+//   [T+64K, T+72K)      divide table, entry a at +8 a: exact mode {magic << 3, shift}, binary-
+//                       compatible mode {kInvAlpha[a], 0}
+//   rings               as many as fit below T, the rest from T+72K
+constexpr uint32_t kOffL2G = 128;
+constexpr uint32_t kOffDiv = 65536;
+constexpr uint32_t kOffRingHi = kOffDiv + 1024 * 8;
+// worst case over the start address: slack below T (up to 64 KB) + tables + the rings that
+// do not fit in the slack
+constexpr uint32_t kRingWorst = kFastWarps * kRingBytes + 2 * kRingBytes;
+constexpr int kSmemBytes = (int)(kOffRingHi + (kRingWorst > 65536u ? kRingWorst : 65536u));
+static_assert(kSmemBytes <= 232448, "dynamic shared memory limit");
 
 template <int ORDER> struct Ch;
 template <> struct Ch<0> {  // R,G,B,A bytes
@@ -51,8 +88,17 @@ template <> struct Ch<1> {  // B,G,R,A bytes
   static constexpr int kR = 2, kB = 0;
 };
 
-__device__ __forceinline__ uint32_t lds32(const uint8_t* smem, uint32_t off) {
-  return *reinterpret_cast<const uint32_t*>(smem + off);
+// table reads by shared-window address; the tables are read-only once filled, so these
+// may be scheduled freely
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+  uint2 v;
+  asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
 }
 // RGBToY (conversion.go:56-59) as two 16x8-bit dot products; Y = byte 2 of the sum
 template <int ORDER>
@@ -65,17 +111,18 @@ __device__ __forceinline__ uint32_t pack_b2(uint32_t s0, uint32_t s1, uint32_t s
 __device__ __forceinline__ uint32_t pack_b3(uint32_t s0, uint32_t s1, uint32_t s2, uint32_t s3) {
   return __byte_perm(__byte_perm(s0, s1, 0x0073), __byte_perm(s2, s3, 0x0073), 0x5410);
 }
-// g2l[channel K of p] << 7 for this lane: address = (byte << 8) | lane*4
+// g2l[channel K of p] << 7 for this lane.  gbase = T | lane*4; address = gbase | (byte << 8)
 template <int K>
-__device__ __forceinline__ uint32_t g2l(const uint8_t* smem, uint32_t p, uint32_t lane4) {
-  return lds32(smem, __byte_perm(p, lane4, 0x5504 | (K << 4)));
+__device__ __forceinline__ uint32_t g2l(uint32_t p, uint32_t gbase) {
+  return lds32(__byte_perm(p, gbase, 0x7604 | (K << 4)));
 }
-// LinearToGamma (yuv.go:187-202) on a sum held << 7: index = byte 2 of the sum, base
-// and slope come in one 64-bit load.  Returns the 10-bit gamma-domain value.
-__device__ __forceinline__ int l2g(const uint8_t* smem, uint32_t s7, uint32_t lane8) {
-  const uint32_t off = __byte_perm(s7, lane8, 0x5524);
-  const int2 bd = *reinterpret_cast<const int2*>(smem + kOffL2G + off);
-  return (bd.x + bd.y * (int)s7) >> 14;
+// LinearToGamma (yuv.go:187-202) on a sum held << 7: index = byte 2 of the sum.  The
+// segment's base (<< 7) and slope (< 128) share one word; the low 7 bits of base << 7
+// and of slope * s7 are zero, so the slope rides through the sum without a carry and is
+// shifted out.  lbase = (T + kOffL2G) | lane*4.  Returns the 10-bit gamma-domain value.
+__device__ __forceinline__ int l2g(uint32_t s7, uint32_t lbase) {
+  const uint32_t w = lds32(__byte_perm(s7, lbase, 0x7624));
+  return ((int)w + (int)(w & 127u) * (int)s7) >> 14;
 }
 // RGBToU / RGBToV on gamma-domain sums (conversion.go:51-69, rounding YUV_HALF<<2),
 // scaled by 64: the result is byte 3.  Inputs are <= 1020 so ClipUV never clamps.
@@ -105,15 +152,15 @@ __device__ __forceinline__ uint32_t div_alpha7(uint32_t w7, uint2 dv) {
 // weights, any equal weights reproduce SUM4, yuv.go:249-252).  The binary-compatible
 // table divide is not exact for opaque blocks, so that mode branches per lane.
 template <int ORDER, bool ALPHA, bool TABLE>
-__device__ __forceinline__ void block_sums(const uint8_t* smem, uint32_t lane4, uint32_t pa, uint32_t pb,
+__device__ __forceinline__ void block_sums(uint32_t gbase, uint32_t dbase, uint32_t pa, uint32_t pb,
                                            uint32_t pc, uint32_t pd, uint32_t al4,
                                            uint32_t* sr, uint32_t* sg, uint32_t* sb) {
-  const uint32_t ra = g2l<Ch<ORDER>::kR>(smem, pa, lane4), rb = g2l<Ch<ORDER>::kR>(smem, pb, lane4);
-  const uint32_t rc = g2l<Ch<ORDER>::kR>(smem, pc, lane4), rd = g2l<Ch<ORDER>::kR>(smem, pd, lane4);
-  const uint32_t ga = g2l<1>(smem, pa, lane4), gb = g2l<1>(smem, pb, lane4);
-  const uint32_t gc = g2l<1>(smem, pc, lane4), gd = g2l<1>(smem, pd, lane4);
-  const uint32_t ba = g2l<Ch<ORDER>::kB>(smem, pa, lane4), bb = g2l<Ch<ORDER>::kB>(smem, pb, lane4);
-  const uint32_t bc = g2l<Ch<ORDER>::kB>(smem, pc, lane4), bd = g2l<Ch<ORDER>::kB>(smem, pd, lane4);
+  const uint32_t ra = g2l<Ch<ORDER>::kR>(pa, gbase), rb = g2l<Ch<ORDER>::kR>(pb, gbase);
+  const uint32_t rc = g2l<Ch<ORDER>::kR>(pc, gbase), rd = g2l<Ch<ORDER>::kR>(pd, gbase);
+  const uint32_t ga = g2l<1>(pa, gbase), gb = g2l<1>(pb, gbase);
+  const uint32_t gc = g2l<1>(pc, gbase), gd = g2l<1>(pd, gbase);
+  const uint32_t ba = g2l<Ch<ORDER>::kB>(pa, gbase), bb = g2l<Ch<ORDER>::kB>(pb, gbase);
+  const uint32_t bc = g2l<Ch<ORDER>::kB>(pc, gbase), bd = g2l<Ch<ORDER>::kB>(pd, gbase);
   const bool plain = !ALPHA || al4 == 0xffffffffu || al4 == 0u;  // yuv.go:249 / :270
   if (!ALPHA || (TABLE ? plain : __all_sync(0xffffffffu, plain))) {
     *sr = ra + rb + rc + rd;
@@ -123,11 +170,30 @@ __device__ __forceinline__ void block_sums(const uint8_t* smem, uint32_t lane4, 
     const uint32_t al = (!TABLE && al4 == 0u) ? 0xffffffffu : al4;
     const uint32_t a0 = al & 0xff, a1 = (al >> 8) & 0xff, a2 = (al >> 16) & 0xff, a3 = al >> 24;
     const uint32_t asum = __dp4a(al, 0x01010101u, 0u);
-    const uint2 dv = *reinterpret_cast<const uint2*>(smem + kOffDiv + asum * 8u);
+    const uint2 dv = lds64(dbase + asum * 8u);
     *sr = div_alpha7<TABLE>(a0 * ra + a1 * rb + a2 * rc + a3 * rd, dv);
     *sg = div_alpha7<TABLE>(a0 * ga + a1 * gb + a2 * gc + a3 * gd, dv);
     *sb = div_alpha7<TABLE>(a0 * ba + a1 * bb + a2 * bc + a3 * bd, dv);
   }
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t nbytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(src), "r"(nbytes) : "memory");
+}
+__device__ __forceinline__ void cp_async16_full(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src, uint32_t nbytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(dst), "l"(src), "r"(nbytes) : "memory");
+}
+__device__ __forceinline__ uint4 lds128_ring(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+// next stage of a ring slot address (rings are aligned to their size)
+__device__ __forceinline__ uint32_t ring_next(uint32_t a) {
+  return (a & ~kStageMask) | ((a + kStageBytes) & kStageMask);
 }
 
 template <int ORDER, bool ALPHA, bool WRITE_A, bool TABLE>
@@ -135,15 +201,18 @@ __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm)
 import_fast_kernel(const ImportJobDev* __restrict__ jobs, const uint32_t* __restrict__ unit_prefix,
                    uint32_t n_jobs, uint32_t uniform_units, uint32_t total_units,
                    const uint32_t* __restrict__ tab, int32_t* __restrict__ has_alpha) {
-  extern __shared__ __align__(256) uint8_t smem[];
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
+  const uint32_t tbase = (sbase + 0xffffu) & ~0xffffu;       // T
+  uint8_t* const tabs = smem + (tbase - sbase);
   for (int i = threadIdx.x; i < 256 * 32; i += kFastThreads) {
-    *reinterpret_cast<uint32_t*>(smem + (i >> 5) * 256 + (i & 31) * 4) = __ldg(tab + B2_TAB_G2L + (i >> 5)) << 7;
+    *reinterpret_cast<uint32_t*>(tabs + (i >> 5) * 256 + (i & 31) * 4) = __ldg(tab + B2_TAB_G2L + (i >> 5)) << 7;
   }
   for (int i = threadIdx.x; i < 32 * 32; i += kFastThreads) {
     const int pos = i >> 5;
     const int base = (int)__ldg(tab + B2_TAB_L2G + 2 * pos) * 128;  // base' << 7
     const int d = (int)__ldg(tab + B2_TAB_L2G + 2 * pos + 1);
-    *reinterpret_cast<int2*>(smem + kOffL2G + pos * 256 + (i & 31) * 8) = make_int2(base, d);
+    *reinterpret_cast<int*>(tabs + kOffL2G + pos * 256 + (i & 31) * 4) = base + d;
   }
   for (int i = threadIdx.x; i < 1024; i += kFastThreads) {
     uint2 e;
@@ -153,81 +222,110 @@ import_fast_kernel(const ImportJobDev* __restrict__ jobs, const uint32_t* __rest
       const uint32_t m = __ldg(tab + B2_TAB_MAGIC + i);  // M | L << 27, M < 2^26: umulhi(w << 3, M) == umulhi(w, M << 3)
       e = make_uint2((m & 0x07ffffffu) << 3, m >> 27);
     }
-    *reinterpret_cast<uint2*>(smem + kOffDiv + i * 8) = e;
+    *reinterpret_cast<uint2*>(tabs + kOffDiv + i * 8) = e;
   }
   __syncthreads();
 
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t lane4 = lane * 4;
-  const uint32_t lane8 = lane * 8;
   const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t gbase = tbase | lane4;
+  const uint32_t lbase = (tbase + kOffL2G) | lane4;
+  const uint32_t dbase = tbase + kOffDiv;
+  // this warp's ring: below the tables while there is room, else above them
+  const uint32_t ring_lo = (sbase + kRingBytes - 1) & ~(kRingBytes - 1);
+  const uint32_t n_lo = (tbase - ring_lo) / kRingBytes;
+  const uint32_t slot0 = (warp < n_lo ? ring_lo + warp * kRingBytes
+                                      : tbase + kOffRingHi + (warp - n_lo) * kRingBytes) + lane * 16;
 
-  for (uint32_t unit = blockIdx.x * kFastWarps + warp; unit < total_units; unit += gridDim.x * kFastWarps) {
+#if B2_IMPORT_CHUNKED
+  // every CTA takes one contiguous share of the row pairs (equal to within one), its warps
+  // walk it round-robin: all SMs finish together whatever the batch size
+  const uint32_t all_units = total_units * kSplit;
+  const uint32_t unit_lo = (uint32_t)(((uint64_t)all_units * blockIdx.x) / gridDim.x);
+  const uint32_t unit_hi = (uint32_t)(((uint64_t)all_units * (blockIdx.x + 1)) / gridDim.x);
+  for (uint32_t unit = unit_lo + warp; unit < unit_hi; unit += kFastWarps) {
+#else
+  for (uint32_t unit = blockIdx.x * kFastWarps + warp; unit < total_units * kSplit; unit += gridDim.x * kFastWarps) {
+#endif
     uint32_t rp;
-    const uint32_t img = b2_find_image(unit_prefix, n_jobs, uniform_units, unit, &rp);
+    const uint32_t img = b2_find_image(unit_prefix, n_jobs, uniform_units, unit / kSplit, &rp);
+    const int phase = (int)(unit % kSplit);
     const ImportJobDev* __restrict__ jp = jobs + img;
     const int width = jp->width;
     const int y0 = 2 * (int)rp;
     const bool has_row1 = (y0 + 1 < jp->height);
     const int sstride = jp->src_stride;
-    const int ystride = jp->y_stride;
-    const uint8_t* s0 = jp->src + (ptrdiff_t)y0 * sstride + lane * 16;
-    const uint8_t* s1 = has_row1 ? s0 + sstride : s0;  // odd last row duplicated (yuv.go:377)
-    uint8_t* yp = jp->y + (ptrdiff_t)y0 * ystride + lane4;
+    // odd last row: the source row is duplicated (yuv.go:377), so row 1 of every output is
+    // the same as row 0 and is written over it
+    const int ystride = has_row1 ? jp->y_stride : 0;
+    const uint8_t* const s0 = jp->src + (ptrdiff_t)y0 * sstride + lane * 16 + phase * 512;
+    const uint8_t* const s1 = has_row1 ? s0 + sstride : s0;
+    uint8_t* yp = jp->y + (ptrdiff_t)y0 * jp->y_stride + lane4 + phase * 128;
     uint8_t* ap = nullptr;
     int astride = 0;
-    if (WRITE_A) { astride = jp->a_stride; ap = jp->a + (ptrdiff_t)y0 * astride + lane4; }
-    const ptrdiff_t uvo = (ptrdiff_t)rp * jp->uv_stride + lane * 2;
+    if (WRITE_A) { astride = has_row1 ? jp->a_stride : 0; ap = jp->a + (ptrdiff_t)y0 * jp->a_stride + lane4 + phase * 128; }
+    const ptrdiff_t uvo = (ptrdiff_t)rp * jp->uv_stride + lane * 2 + phase * 64;
     uint8_t* up = jp->u + uvo;
     uint8_t* vp = jp->v + uvo;
     uint32_t and_acc = 0xffffffffu;
 
-    // One 128-pixel strip per iteration, the next strip's loads in flight meanwhile.
-    // Lanes past the end of the row run on zeros (every lane takes part in the vote of
-    // block_sums) and store nothing.
-    int x = (int)lane4;
-    // rows that are only 4-byte aligned (a tight 4*width stride with width % 4 != 0) are
-    // read with 32-bit loads of the valid pixels; 16-byte aligned rows with one 128-bit load
+    // Strips of 128 pixels.  Rows that are 16-byte aligned are fetched with one 16-byte
+    // cp.async per lane and row; whole strips of such rows take the check-free code.  The
+    // last partial strip, and every strip of rows that are only 4-byte aligned (a tight
+    // 4*width stride with width % 4 != 0), fetch the valid pixels only and take the
+    // general code, where lanes past the end of the row run on zeros (every lane takes
+    // part in the vote of block_sums) and store nothing.
     const bool al16 = ((((uintptr_t)jp->src) | (uintptr_t)(uint32_t)sstride) & 15) == 0;  // warp-uniform
-    auto load4 = [&](const uint8_t* p, int xx) -> uint4 {
-      if (al16) return b2_ldg_stream_v4(p);
-      const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
-      uint4 r;
-      r.x = __ldg(q);
-      r.y = (xx + 1 < width) ? __ldg(q + 1) : 0u;
-      r.z = (xx + 2 < width) ? __ldg(q + 2) : 0u;
-      r.w = (xx + 3 < width) ? __ldg(q + 3) : 0u;
-      return r;
-    };
-    uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0;
-    bool cur_ok = x < width;
-    if (cur_ok) { c0 = load4(s0, x); c1 = load4(s1, x); }
     const int tiles_x = (width + 127) >> 7;
-    for (int t = 0; t < tiles_x; ++t) {
-      const int xn = x + 128;
-      const bool nxt_ok = xn < width;
-      uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;
-      if (nxt_ok) { n0 = load4(s0 + 512, xn); n1 = load4(s1 + 512, xn); }
-#if B2_IMPORT_L2_PREFETCH
-      // Optional: pull the strips after that into L2.  Measured (profiles/r01d_*): with
-      // opaque input the kernel waits on load latency and distance 5 gains 3%, but with
-      // translucent input it is issue bound and the two extra instructions cost 6%, so
-      // the default is off.
-      if (xn + 128 * (B2_IMPORT_L2_PREFETCH - 1) < width) {
-        asm volatile("prefetch.global.L2 [%0];" :: "l"(s0 + 512 * B2_IMPORT_L2_PREFETCH));
-        asm volatile("prefetch.global.L2 [%0];" :: "l"(s1 + 512 * B2_IMPORT_L2_PREFETCH));
+    const int full = al16 ? (width >> 7) : 0;
+    const uint8_t* g0 = s0;
+    const uint8_t* g1 = s1;
+    uint32_t wr = slot0, rd = slot0;
+    auto issue = [&](int t) {  // one commit group per call, possibly empty
+      if (t < full) {
+        cp_async16_full(wr, g0);
+        cp_async16_full(wr + 512, g1);
+      } else if (t < tiles_x) {
+        const int nv = min(max(width - ((int)lane4 + t * 128), 0), 4);
+        const uint8_t* q0 = nv ? g0 : s0 - phase * 512;   // lanes past the row: zero fill from a valid address
+        const uint8_t* q1 = nv ? g1 : s1 - phase * 512;
+        if (al16) {
+          cp_async16(wr, q0, 4u * nv);
+          cp_async16(wr + 512, q1, 4u * nv);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t nb = (k < nv) ? 4u : 0u;
+            cp_async4(wr + 4 * k, q0 + (nb ? 4 * k : 0), nb);
+            cp_async4(wr + 512 + 4 * k, q1 + (nb ? 4 * k : 0), nb);
+          }
+        }
       }
-#endif
-      // Last group of a row whose width is not a multiple of 4: a 128-bit load stays inside
-      // the row's 16-byte-aligned stride span, the 32-bit loads fetch valid pixels only;
-      // the missing pixels become copies of valid ones.  Duplicating the odd last column is exactly the reference's SUM2 / SUM2ALPHA
-      // forms (yuv.go:211-213,270-277: twice a 2-pixel sum == the 4-pixel sum of the
-      // duplicated column), and copies cannot disturb the has-alpha reduction.
-      const int nvalid = width - x;
-      if (nvalid < 4 && nvalid > 0) {
-        if (nvalid == 1) { c0.y = c0.x; c1.y = c1.x; }
-        if (nvalid <= 2) { c0.z = c0.x; c1.z = c1.x; c0.w = c0.y; c1.w = c1.y; }
-        else { c0.w = c0.z; c1.w = c1.z; }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      wr = ring_next(wr);
+      g0 += 512 * kSplit; g1 += 512 * kSplit;
+    };
+    auto strip = [&](auto full_tag, int t) {
+      constexpr bool FULL = decltype(full_tag)::value;
+      issue(t + kDist * kSplit);
+      asm volatile("cp.async.wait_group %0;" :: "n"(kDist) : "memory");
+      uint4 c0 = lds128_ring(rd);
+      uint4 c1 = lds128_ring(rd + 512);
+      rd = ring_next(rd);
+      int nvalid = 4;
+      if (!FULL) {
+        // Last group of a row whose width is not a multiple of 4: only valid pixels were
+        // fetched; the missing pixels become copies of valid ones.  Duplicating the odd
+        // last column is exactly the reference's SUM2 / SUM2ALPHA forms (yuv.go:211-213,
+        // 270-277: twice a 2-pixel sum == the 4-pixel sum of the duplicated column), and
+        // copies cannot disturb the has-alpha reduction.
+        nvalid = width - ((int)lane4 + t * 128);
+        if (nvalid < 4 && nvalid > 0) {
+          if (nvalid == 1) { c0.y = c0.x; c1.y = c1.x; }
+          if (nvalid <= 2) { c0.z = c0.x; c1.z = c1.x; c0.w = c0.y; c1.w = c1.y; }
+          else { c0.w = c0.z; c1.w = c1.z; }
+        }
       }
       const uint32_t yw0 = pack_b2(luma_sum<ORDER>(c0.x), luma_sum<ORDER>(c0.y), luma_sum<ORDER>(c0.z), luma_sum<ORDER>(c0.w));
       const uint32_t yw1 = pack_b2(luma_sum<ORDER>(c1.x), luma_sum<ORDER>(c1.y), luma_sum<ORDER>(c1.z), luma_sum<ORDER>(c1.w));
@@ -235,40 +333,45 @@ import_fast_kernel(const ImportJobDev* __restrict__ jobs, const uint32_t* __rest
       if (ALPHA) {
         ap0 = pack_b3(c0.x, c0.y, c0.z, c0.w);
         ap1 = pack_b3(c1.x, c1.y, c1.z, c1.w);
-        if (cur_ok) and_acc &= ap0 & ap1;
+        if (FULL || nvalid > 0) and_acc &= ap0 & ap1;
       }
       uint32_t sr0, sg0, sb0, sr1, sg1, sb1;
-      block_sums<ORDER, ALPHA, TABLE>(smem, lane4, c0.x, c0.y, c1.x, c1.y, __byte_perm(ap0, ap1, 0x5410), &sr0, &sg0, &sb0);
-      block_sums<ORDER, ALPHA, TABLE>(smem, lane4, c0.z, c0.w, c1.z, c1.w, __byte_perm(ap0, ap1, 0x7632), &sr1, &sg1, &sb1);
-      const int r0 = l2g(smem, sr0, lane8), g0 = l2g(smem, sg0, lane8), b0 = l2g(smem, sb0, lane8);
-      const int r1 = l2g(smem, sr1, lane8), g1 = l2g(smem, sg1, lane8), b1 = l2g(smem, sb1, lane8);
-      const uint32_t uu = __byte_perm(u_sum(r0, g0, b0), u_sum(r1, g1, b1), 0x0073);
-      const uint32_t vv = __byte_perm(v_sum(r0, g0, b0), v_sum(r1, g1, b1), 0x0073);
-      if (nvalid >= 4) {
+      block_sums<ORDER, ALPHA, TABLE>(gbase, dbase, c0.x, c0.y, c1.x, c1.y, __byte_perm(ap0, ap1, 0x5410), &sr0, &sg0, &sb0);
+      block_sums<ORDER, ALPHA, TABLE>(gbase, dbase, c0.z, c0.w, c1.z, c1.w, __byte_perm(ap0, ap1, 0x7632), &sr1, &sg1, &sb1);
+      const int r0 = l2g(sr0, lbase), gg0 = l2g(sg0, lbase), b0 = l2g(sb0, lbase);
+      const int r1 = l2g(sr1, lbase), gg1 = l2g(sg1, lbase), b1 = l2g(sb1, lbase);
+      const uint32_t uu = __byte_perm(u_sum(r0, gg0, b0), u_sum(r1, gg1, b1), 0x0073);
+      const uint32_t vv = __byte_perm(v_sum(r0, gg0, b0), v_sum(r1, gg1, b1), 0x0073);
+      if (FULL || nvalid >= 4) {
         b2_stg_stream_u32(yp, yw0);
-        if (has_row1) b2_stg_stream_u32(yp + ystride, yw1);
+        b2_stg_stream_u32(yp + ystride, yw1);
         if (WRITE_A) {
           b2_stg_stream_u32(ap, ap0);
-          if (has_row1) b2_stg_stream_u32(ap + astride, ap1);
+          b2_stg_stream_u32(ap + astride, ap1);
         }
         b2_stg_stream_u16(up, uu);
         b2_stg_stream_u16(vp, vv);
       } else if (nvalid > 0) {  // partial group: byte stores of the valid samples only
         for (int k = 0; k < nvalid; ++k) {
           yp[k] = (uint8_t)(yw0 >> (8 * k));
-          if (has_row1) yp[ystride + k] = (uint8_t)(yw1 >> (8 * k));
+          yp[ystride + k] = (uint8_t)(yw1 >> (8 * k));
           if (WRITE_A) {
             ap[k] = (uint8_t)(ap0 >> (8 * k));
-            if (has_row1) ap[astride + k] = (uint8_t)(ap1 >> (8 * k));
+            ap[astride + k] = (uint8_t)(ap1 >> (8 * k));
           }
         }
         up[0] = (uint8_t)uu; vp[0] = (uint8_t)vv;
         if (nvalid > 2) { up[1] = (uint8_t)(uu >> 8); vp[1] = (uint8_t)(vv >> 8); }
       }
-      s0 += 512; s1 += 512; yp += 128; up += 64; vp += 64;
-      if (WRITE_A) ap += 128;
-      c0 = n0; c1 = n1; cur_ok = nxt_ok; x = xn;
-    }
+      yp += 128 * kSplit; up += 64 * kSplit; vp += 64 * kSplit;
+      if (WRITE_A) ap += 128 * kSplit;
+    };
+#pragma unroll
+    for (int k = 0; k < kDist; ++k) issue(phase + k * kSplit);
+    int t = phase;
+#pragma unroll kUnroll
+    for (; t < full; t += kSplit) strip(std::true_type{}, t);
+    for (; t < tiles_x; t += kSplit) strip(std::false_type{}, t);
     if (ALPHA && has_alpha != nullptr) {
       if (__any_sync(0xffffffffu, and_acc != 0xffffffffu) && lane == 0) atomicOr(has_alpha + img, 1);
     }
@@ -300,7 +403,7 @@ cudaError_t b2_import_fast_launch(const b2_ctx* ctx, cudaStream_t s, const Impor
                                   const uint32_t* unit_prefix, uint32_t n_jobs,
                                   uint32_t uniform_units, uint32_t total_units, int order,
                                   bool alpha, bool write_a, int div_table, int32_t* has_alpha) {
-  const int grid = b2_grid_for(ctx, kFastCtasPerSm, (total_units + kFastWarps - 1) / kFastWarps);
+  const int grid = b2_grid_for(ctx, kFastCtasPerSm, ((uint64_t)total_units * kSplit + kFastWarps - 1) / kFastWarps);
 #define B2_GO(O, A, W) return launch<O, A, W>(grid, s, jobs, unit_prefix, n_jobs, uniform_units, total_units, ctx->tab_dev, div_table, has_alpha)
   if (order == B2_ORDER_RGBA) {
     if (alpha) { if (write_a) B2_GO(0, true, true); else B2_GO(0, true, false); }

@@ -7,6 +7,8 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 from go_webp_b200 import _abi  # noqa: E402
+if os.environ.get("B2_LIB"):  # experiment builds (tools/variants.sh)
+    _abi.LIB_PATH = os.environ["B2_LIB"]
 from go_webp_b200.device import Context  # noqa: E402
 from go_webp_b200.pipeline import ArgbPipeline, ImportPipeline, UpsamplePipeline  # noqa: E402
 

@@ -17,6 +17,7 @@ try:
 except Exception:
     pass
 which = sys.argv[1:] or ["import", "upsample", "vp8l"]
+NF = int(os.environ.get("B2_FRAMES", "128"))  # 1080p frames of the import runs
 ctx = Context(0, 1)
 
 
@@ -38,13 +39,13 @@ def report(name, px, bpp, ms):
 
 if "import" in which:
     for name, mode in (("opaque", 1), ("sparse", 2), ("raw", 0)):
-        p = ImportPipeline(ctx, 128, 1920, 1080, host=False)
+        p = ImportPipeline(ctx, NF, 1920, 1080, host=False)
         p.fill_synthetic(0xB2000001, 0, mode)
-        report(f"import 128x1080p alpha={name}", 128 * 1920 * 1080, 6.5, timed(p.run_device))
+        report(f"import {NF}x1080p alpha={name}", NF * 1920 * 1080, 6.5, timed(p.run_device))
         p.close()
-    p = ImportPipeline(ctx, 128, 1920, 1080, import_alpha=False, host=False)
+    p = ImportPipeline(ctx, NF, 1920, 1080, import_alpha=False, host=False)
     p.fill_synthetic(0xB2000001, 0, 0)
-    report("import 128x1080p RGBX (A written 0xff)", 128 * 1920 * 1080, 6.5, timed(p.run_device))
+    report(f"import {NF}x1080p RGBX (A written 0xff)", NF * 1920 * 1080, 6.5, timed(p.run_device))
     p.close()
 if "upsample" in which:
     for mode, wa, bpp in ((_abi.MODE_RGBA, False, 5.5), (_abi.MODE_BGRA, True, 6.5), (_abi.MODE_RGB, False, 4.5)):

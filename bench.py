@@ -257,11 +257,11 @@ def other_kernels(ctx, peak, steps):
                                 ("color_index_inverse", 3, 4.5, "vp8l_color_index_1bit"),
                                 ("predictor_forward", 5, 8.0039, "vp8l_predictor_forward"),
                                 ("predictor_inverse", 5, 8.0039, "vp8l_predictor_inverse_wavefront")]:
-        ap = ArgbPipeline(ctx, 16, 4096, 4096, op, bits)
+        ap = ArgbPipeline(ctx, 64, 4096, 4096, op, bits)   # configs[2]: 64 x 4096^2
         ap.fill_synthetic(0xB2000003)
         ms = timed(ap.run_device, k)
-        px = 16 * 4096 * 4096
-        out[name] = {"frames": 16, "mpixel_per_s": px / ms / 1e3, "bytes_per_px": bpp,
+        px = 64 * 4096 * 4096
+        out[name] = {"frames": 64, "mpixel_per_s": px / ms / 1e3, "bytes_per_px": bpp,
                      "gbs": px * bpp / ms / 1e6, "frac": px * bpp / ms / 1e6 / peak}
         ap.close()
     return out

@@ -33,7 +33,7 @@ struct PredJobDev {
   int32_t width, height, bits;
   uint32_t tiles_per_row;  // mode image row length
   uint32_t bands;          // ceil(height / 32)
-  uint32_t ktiles;         // skewed tiles per band: ceil((width + 62) / kTileK)
+  uint32_t flag_off;       // first progress counter of this image (one per band)
 };
 
 // ---- pixel arithmetic (lossless_common.go:110-121, lossless.go:31-149) -----------
@@ -160,158 +160,223 @@ predictor_forward_kernel(const PredJobDev* __restrict__ jobs, const uint32_t* __
 }
 
 // ---- inverse ----------------------------------------------------------------------
+// Persistent wavefront.  A warp takes a band of 32 rows (lane r = row r of the band) and
+// walks it once, left to right, in skewed columns c = k - 2r.  TR comes from the lane above
+// by one shuffle; lane 0's row above is the last row of the band above, read back from the
+// output image behind a progress counter that the band above publishes (release) and this
+// band polls (acquire) every 32 columns.  Bands are handed out through one ticket counter
+// in band-major order (band 0 of every image, then band 1, ...): the band a warp waits on
+// always holds a lower ticket, so it is already running and the wait cannot deadlock,
+// whatever the number of resident warps.  The wavefront needs W + 2H serial steps per image
+// (plus the 32-column publishing granularity per band); what fills the GPU is the ~W/100
+// bands per image that are in flight at once, times the images of the batch.
+//
+// Memory traffic is kept to whole sectors although every lane walks its own row: a lane
+// fetches 8 residuals at a time with two 16-byte cp.async, 8 steps ahead, into a private
+// 16-pixel ring in shared memory indexed by column, and collects 8 outputs in a second
+// private ring before writing them as one sector.  A lane's rings are 28 words apart:
+// with the 2-column skew between lanes the per-step accesses are at most 2-way bank
+// conflicted, the 128-bit flush reads are conflict free.
 constexpr int kInvWarps = 4;
 constexpr int kInvThreads = kInvWarps * 32;
-constexpr int kTileK = 32;   // skewed columns per tile: the wavefront needs W + 2H steps in all, and the
-                             // diagonal schedule spends (2 H/32 + (W+62)/K) K of them, so small K is optimal
+constexpr int kInSlots = 16, kOutSlots = 8;
+constexpr int kLaneWords = 28;   // 16 in + 8 out + 4 pad; 16-byte aligned, 28 l mod 32 has period 8
+#ifndef B2_PRED_PUBLISH
+#define B2_PRED_PUBLISH 32
+#endif
+constexpr int kPublish = B2_PRED_PUBLISH;   // columns between two progress publications
 
-// Lane 31 of a band runs 62 columns behind lane 0, so lane 0 of tile (i, j) reads the
-// row above up to skewed tile j + kDep of band i - 1: with d = (kDep + 1) i + j every
-// dependency ((i, j-1), (i-1, j .. j+kDep)) lies on an earlier diagonal.
-constexpr uint32_t kDep = (kTileK + 62) / kTileK;
-constexpr uint32_t kDiag = kDep + 1;
-// One launch = one diagonal d of every image; grid.y = image, the warps of grid.x
-// enumerate the bands i that have a tile on it.
-__global__ void __launch_bounds__(kInvThreads, 8)
-predictor_inverse_diag_kernel(const PredJobDev* __restrict__ jobs, uint32_t d) {
-  __shared__ uint32_t upper_all[kInvWarps][kTileK + 2];
-  const int lane = threadIdx.x & 31;
-  const uint32_t warp = threadIdx.x >> 5;
-  const PredJobDev* __restrict__ jp = jobs + blockIdx.y;
-  const uint32_t bands = jp->bands, ktiles = jp->ktiles;
-  // tiles on this diagonal: (kDiag i + j == d), j in [0, ktiles)
-  const uint32_t i_hi = min(bands - 1, d / kDiag);
-  const uint32_t i_lo = (d + 1 > ktiles) ? (d + 1 - ktiles + kDiag - 1) / kDiag : 0;
-  const uint32_t slot = blockIdx.x * kInvWarps + warp;
-  if (i_lo > i_hi || slot > i_hi - i_lo) return;
-  const uint32_t i = i_lo + slot, j = d - kDiag * i;
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+
+// One band.  VEC: width % 4 == 0 and 16-byte aligned images, so a lane's 8-pixel groups
+// are two aligned 128-bit accesses.
+template <bool VEC>
+__device__ __forceinline__ void inverse_band(const PredJobDev* __restrict__ jp, uint32_t i, uint32_t* __restrict__ flags,
+                                             uint32_t* ring, int lane) {
   const int w = jp->width, h = jp->height, bits = jp->bits;
   const int row = (int)i * 32 + lane;
   const bool row_ok = row < h;
   const uint32_t* __restrict__ in_row = jp->src + (size_t)row * w;
-  uint32_t* __restrict__ out = jp->dst;
-  uint32_t* out_row = out + (size_t)row * w;
+  uint32_t* __restrict__ out_row = jp->dst + (size_t)row * w;
+  const uint32_t* up_row = jp->dst + (size_t)(i * 32 - 1) * w;      // last row of the band above (i > 0)
   const uint32_t* __restrict__ mode_row = jp->modes + (size_t)(row >> bits) * jp->tiles_per_row;
-  uint32_t* upper = upper_all[warp];
-
-  const int k0 = (int)j * kTileK;   // first skewed column of the tile
-  int c = k0 - 2 * lane;            // this lane's column at the first step
-  // lane 0's upper row comes from the band above: out[32 i - 1][k0 - 1 .. k0 + kTileK]
-  if (i > 0) {
-    const uint32_t* up = out + (size_t)(i * 32 - 1) * w;
-    for (int t = lane; t < kTileK + 2; t += 32) {
-      const int cc = k0 - 1 + t;
-      upper[t] = (cc >= 0 && cc < w) ? up[cc] : 0u;
-    }
-  }
-  __syncwarp();
-  // state carried from the tile to the left (or the image edge): left = (row, c-1),
-  // tl = (row-1, c-1), t = (row-1, c); and this lane's last output for the lane below
+  const uint32_t* flag_up = flags + jp->flag_off + i - 1;
+  uint32_t* flag_me = flags + jp->flag_off + i;
+  const bool publish = (lane == 31) && (i + 1 < jp->bands);
+  uint32_t avail = 0;            // columns of up_row known to be complete
+  uint32_t upc = 0;              // lane q: up_row[k0 + 1 + q] of the current 32-column chunk
   uint32_t left = 0, tl = 0, t = 0, last_out = 0, first_px = 0;
-  if (row_ok && row > 0) {
-    const uint32_t* up = out_row - w;
-    if (c - 1 >= 0 && c - 1 < w) tl = up[c - 1];
-    if (c >= 0 && c < w) t = up[c];
-  }
-  if (row_ok && c - 1 >= 0 && c - 1 < w) left = out_row[c - 1];
-  // what the lane below needs as its first TR: (row, c + 1 - 2) ... = this lane's pixel at c - 1
-  last_out = left;
-  if (row_ok && c > 0) first_px = out_row[0];  // TR of the last column (lossless.go: upper[x+1] wraps to the row start)
-  // Predictor mode of the current 2^bits-wide mode tile and of the next one (fetched a
-  // whole tile ahead so its latency never sits on the dependency chain).
   const int tile_mask = (1 << bits) - 1;
   const int mt_last = (int)jp->tiles_per_row - 1;
   auto load_mode = [&](int mt) -> uint32_t {
-    return (row_ok && mt >= 0 && mt <= mt_last) ? (__ldg(mode_row + mt) >> 8) & 0xf : 0u;
+    return (row_ok && mt <= mt_last) ? (__ldg(mode_row + mt) >> 8) & 0xf : 0u;
   };
-  // (initialised for column c - 1, so that a tile starting exactly on a mode-tile
-  // boundary takes the regular switch on its first step)
-  uint32_t mode = load_mode(max(c - 1, 0) >> bits);
-  uint32_t mode_nxt = load_mode((max(c - 1, 0) >> bits) + 1);
-  // Residuals: a 16-deep ring of scalar prefetches per lane (each lane walks its own
-  // row, so a warp-wide load touches 32 lines; 16 steps of lead hide the DRAM latency).
-  constexpr int kRing = 16;
-  uint32_t ring[kRing];
-#pragma unroll
-  for (int q = 0; q < kRing; ++q) {
-    const int cq = c + q;
-    ring[q] = (row_ok && cq >= 0 && cq < w) ? __ldg(in_row + cq) : 0u;
-  }
-
-  for (int s0 = 0; s0 < kTileK; s0 += kRing) {
-#pragma unroll
-    for (int q = 0; q < kRing; ++q, ++c) {
-      const int s = s0 + q;
-      // TR = (row-1, c+1): the lane above finished it on the previous step
-      uint32_t tr = __shfl_up_sync(0xffffffffu, last_out, 1);
-      if (lane == 0) tr = upper[s + 2];
-      const uint32_t res = ring[q];
-      const int ca = c + kRing;
-      ring[q] = (row_ok && ca >= 0 && ca < w) ? __ldg(in_row + ca) : 0u;
-      if (c > 0 && (c & tile_mask) == 0) {  // entering the next mode tile
-        mode = mode_nxt;
-        mode_nxt = load_mode((c >> bits) + 1);
+  uint32_t mode = load_mode(0), mode_nxt = load_mode(1);
+  uint32_t* const in_l = ring + lane * kLaneWords;
+  uint32_t* const out_l = in_l + kInSlots;
+  const uint32_t in_s = (uint32_t)__cvta_generic_to_shared(in_l);
+  const int k_end = w + 62;
+  int c = -8 - 2 * lane;
+  for (int k = -8; k < k_end; ++k, ++c) {
+    if (((k + 1) & 31) == 0 && i > 0) {          // next chunk of the row above: columns k+1 .. k+32
+      const uint32_t need = (uint32_t)min(w, k + 33);
+      while (avail < need) {
+        avail = ld_acquire_u32(flag_up);
+        if (avail < need) __nanosleep(64);
       }
-      if (row_ok && c >= 0 && c < w) {
-        if (c == w - 1) tr = first_px;
-        uint32_t pred;
-        if (row == 0) pred = (c == 0) ? 0xff000000u : left;   // lossless.go:292-295
-        else if (c == 0) pred = t;                               // :312
-        else pred = predict(mode, left, tl, t, tr);
-        const uint32_t o = add_pixels(res, pred);
-        out_row[c] = o;
-        if (c == 0) first_px = o;
-        left = o;
-        last_out = o;
-      }
-      tl = t;
-      t = tr;
+      const int col = k + 1 + lane;
+      upc = (col < w) ? __ldcg(up_row + col) : 0u;
     }
+    // TR = (row-1, c+1): the lane above finished it on the previous step
+    uint32_t tr = __shfl_up_sync(0xffffffffu, last_out, 1);
+    const uint32_t u = __shfl_sync(0xffffffffu, upc, (k + 1) & 31);
+    if (lane == 0) tr = u;
+    if ((c & 7) == 0 && row_ok) {
+      // the group fetched 8 steps ago (columns c .. c+7) must have landed; then fetch
+      // columns c+8 .. c+15 into the other half of the ring
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      const int cc = c + 8;
+      if (cc < w) {
+        const uint32_t dst = in_s + (uint32_t)(cc & 8) * 4u;
+        if (VEC) {
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(in_row + cc) : "memory");
+          if (cc + 4 < w) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + 16), "l"(in_row + cc + 4) : "memory");
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (cc + e < w) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst + 4 * e), "l"(in_row + cc + e) : "memory");
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    if (c > 0 && (c & tile_mask) == 0) {         // entering the next mode tile
+      mode = mode_nxt;
+      mode_nxt = load_mode((c >> bits) + 1);
+    }
+    if (row_ok && c >= 0 && c < w) {
+      const uint32_t res = *reinterpret_cast<volatile uint32_t*>(in_l + (c & (kInSlots - 1)));
+      if (c == w - 1) tr = first_px;             // upper[x+1] of the last column wraps to the row start
+      uint32_t pred;
+      if (row == 0) pred = (c == 0) ? 0xff000000u : left;   // lossless.go:292-295
+      else if (c == 0) pred = t;                               // :312
+      else pred = predict(mode, left, tl, t, tr);
+      const uint32_t o = add_pixels(res, pred);
+      out_l[c & 7] = o;
+      if (c == 0) first_px = o;
+      left = o;
+      last_out = o;
+      if ((c & 7) == 7 || c == w - 1) {          // a finished group of 8 (or the row's tail)
+        const int base = c & ~7;
+        const int n = c - base + 1;
+        if (VEC) {
+          b2_stg_stream_v4(out_row + base, *reinterpret_cast<const uint4*>(out_l));
+          if (n > 4) b2_stg_stream_v4(out_row + base + 4, *reinterpret_cast<const uint4*>(out_l + 4));
+        } else {
+          for (int e = 0; e < n; ++e) out_row[base + e] = out_l[e];
+        }
+        if (publish && (((c + 1) & (kPublish - 1)) == 0 || c == w - 1)) st_release_u32(flag_me, (uint32_t)(c + 1));
+      }
+    }
+    tl = t;
+    t = tr;
   }
 }
 
-int prepare_pred(b2_ctx* ctx, int stream, const b2_argb_job* jobs, int n_jobs, const PredJobDev** djobs,
-                 const uint32_t** dprefix, uint32_t* uniform, uint32_t* total, uint32_t* max_bands, uint32_t* n_diag) {
+__global__ void __launch_bounds__(kInvThreads, 8)
+predictor_inverse_wave_kernel(const PredJobDev* __restrict__ jobs, const uint32_t* __restrict__ order,
+                              uint32_t n_bands, uint32_t* __restrict__ ctl) {
+  __shared__ __align__(16) uint32_t rings[kInvWarps][kLaneWords * 32];
+  const int lane = threadIdx.x & 31;
+  uint32_t* ring = rings[threadIdx.x >> 5];
+  uint32_t* flags = ctl + 1;
+  for (;;) {
+    uint32_t ticket = 0;
+    if (lane == 0) ticket = atomicAdd(ctl, 1u);
+    ticket = __shfl_sync(0xffffffffu, ticket, 0);
+    if (ticket >= n_bands) break;
+    const uint32_t e = __ldg(order + ticket);    // image << 10 | band
+    const PredJobDev* __restrict__ jp = jobs + (e >> 10);
+    const bool vec = ((jp->width & 3) == 0) && (((((uintptr_t)jp->src) | ((uintptr_t)jp->dst)) & 15) == 0);
+    if (vec) inverse_band<true>(jp, e & 1023u, flags, ring, lane);
+    else inverse_band<false>(jp, e & 1023u, flags, ring, lane);
+    __syncwarp();
+  }
+}
+
+// Uploads the job table and the flat-item prefix (forward), plus -- with_wave -- the
+// band-major ticket order and a zeroed control block {ticket counter, one progress
+// counter per band} for the inverse.
+struct PredPlan {
+  const PredJobDev* jobs;
+  const uint32_t* prefix;
+  const uint32_t* order;
+  uint32_t* ctl;
+  uint32_t uniform, total_items, total_bands;
+};
+int prepare_pred(b2_ctx* ctx, int stream, const b2_argb_job* jobs, int n_jobs, bool with_wave, PredPlan* plan) {
+  uint64_t bands_all = 0;
+  uint32_t max_bands = 0;
+  for (int i = 0; i < n_jobs; ++i) {
+    const b2_argb_job& j = jobs[i];
+    if (j.src == NULL || j.dst == NULL || j.data == NULL) return B2_ERR_NULL;
+    if (j.width <= 0 || j.height <= 0 || j.width > B2_MAX_DIMENSION || j.height > B2_MAX_DIMENSION) return B2_ERR_BAD_DIM;
+    if (j.bits < 2 || j.bits > 9 || j.src == j.dst) return B2_ERR_INVALID_CONFIG;  // vp8l_dec.c.go:1243
+    const uint32_t nb = (uint32_t)((j.height + 31) / 32);
+    bands_all += nb;
+    if (nb > max_bands) max_bands = nb;
+  }
+  if (with_wave && (n_jobs > (1 << 22) || max_bands > 1024)) return B2_ERR_INVALID_CONFIG;  // order entry = image << 10 | band
   const size_t jb = (sizeof(PredJobDev) * (size_t)n_jobs + 15) & ~(size_t)15;
-  const size_t pb = sizeof(uint32_t) * ((size_t)n_jobs + 1);
-  if (jb + pb > B2_DESC_RING_BYTES) return B2_ERR_INVALID_CONFIG;
-  uint8_t* host = (uint8_t*)malloc(jb + pb);
+  const size_t pb = (sizeof(uint32_t) * ((size_t)n_jobs + 1) + 15) & ~(size_t)15;
+  const size_t ob = with_wave ? (sizeof(uint32_t) * (size_t)bands_all + 15) & ~(size_t)15 : 0;
+  const size_t cb = with_wave ? sizeof(uint32_t) * ((size_t)bands_all + 1) : 0;
+  if (jb + pb + ob + cb > B2_DESC_RING_BYTES) return B2_ERR_INVALID_CONFIG;
+  uint8_t* host = (uint8_t*)calloc(1, jb + pb + ob + cb);
   if (host == NULL) return B2_ERR_OOM;
   PredJobDev* dj = (PredJobDev*)host;
   uint32_t* pre = (uint32_t*)(host + jb);
+  uint32_t* ord = (uint32_t*)(host + jb + pb);
   uint64_t tot = 0;
-  uint32_t uni = 0, mb = 0, nd = 0;
+  uint32_t uni = 0, flag_off = 0;
   for (int i = 0; i < n_jobs; ++i) {
     const b2_argb_job& j = jobs[i];
-    int st = B2_OK;
-    if (j.src == NULL || j.dst == NULL || j.data == NULL) st = B2_ERR_NULL;
-    else if (j.width <= 0 || j.height <= 0 || j.width > B2_MAX_DIMENSION || j.height > B2_MAX_DIMENSION) st = B2_ERR_BAD_DIM;
-    else if (j.bits < 2 || j.bits > 9 || j.src == j.dst) st = B2_ERR_INVALID_CONFIG;  // vp8l_dec.c.go:1243
-    if (st != B2_OK) { free(host); return st; }
     PredJobDev& d = dj[i];
     d.src = j.src; d.dst = j.dst; d.modes = j.data;
     d.width = j.width; d.height = j.height; d.bits = j.bits;
     d.tiles_per_row = (uint32_t)((j.width + (1 << j.bits) - 1) >> j.bits);
     d.bands = (uint32_t)((j.height + 31) / 32);
-    d.ktiles = (uint32_t)((j.width + 62 + kTileK - 1) / kTileK);
+    d.flag_off = flag_off;
+    flag_off += d.bands;
     const uint64_t n = (uint64_t)j.width * (uint64_t)j.height;
     const uint32_t items = (uint32_t)((n + 4 * kFwdThreads - 1) / (4 * kFwdThreads));
     if (i == 0) uni = items; else if (items != uni) uni = 0;
     pre[i] = (uint32_t)tot;
     tot += items;
     if (tot > 0x7fffffffull) { free(host); return B2_ERR_BAD_DIM; }
-    if (d.bands > mb) mb = d.bands;
-    const uint32_t diags = kDiag * (d.bands - 1) + d.ktiles;
-    if (diags > nd) nd = diags;
   }
   pre[n_jobs] = (uint32_t)tot;
+  if (with_wave) {
+    size_t q = 0;
+    for (uint32_t band = 0; band < max_bands; ++band)
+      for (int i = 0; i < n_jobs; ++i)
+        if (band < dj[i].bands) ord[q++] = ((uint32_t)i << 10) | band;
+  }
   void* dev = NULL;
-  const int st = b2_upload_desc(ctx, stream, host, jb + pb, &dev);
+  const int st = b2_upload_desc(ctx, stream, host, jb + pb + ob + cb, &dev);
   free(host);
   if (st != B2_OK) return st;
-  *djobs = (const PredJobDev*)dev;
-  *dprefix = (const uint32_t*)((uint8_t*)dev + jb);
-  *uniform = uni; *total = (uint32_t)tot; *max_bands = mb; *n_diag = nd;
+  plan->jobs = (const PredJobDev*)dev;
+  plan->prefix = (const uint32_t*)((uint8_t*)dev + jb);
+  plan->order = (const uint32_t*)((uint8_t*)dev + jb + pb);
+  plan->ctl = (uint32_t*)((uint8_t*)dev + jb + pb + ob);
+  plan->uniform = uni; plan->total_items = (uint32_t)tot; plan->total_bands = (uint32_t)bands_all;
   return B2_OK;
 }
 
@@ -322,11 +387,11 @@ extern "C" int b2_vp8l_predictor_forward(b2_ctx* ctx, int stream, const b2_argb_
   if (n_jobs < 0) return B2_ERR_INVALID_CONFIG;
   if (n_jobs == 0) return B2_OK;
   if (jobs == NULL) return B2_ERR_NULL;
-  const PredJobDev* dj; const uint32_t* dp; uint32_t uni, tot, mb, nd;
-  const int st = prepare_pred(ctx, stream, jobs, n_jobs, &dj, &dp, &uni, &tot, &mb, &nd);
+  PredPlan pl;
+  const int st = prepare_pred(ctx, stream, jobs, n_jobs, false, &pl);
   if (st != B2_OK) return st;
-  const int grid = b2_grid_for(ctx, 8, tot);
-  predictor_forward_kernel<<<grid, kFwdThreads, 0, ctx->streams[stream]>>>(dj, dp, (uint32_t)n_jobs, uni, tot);
+  const int grid = b2_grid_for(ctx, 8, pl.total_items);
+  predictor_forward_kernel<<<grid, kFwdThreads, 0, ctx->streams[stream]>>>(pl.jobs, pl.prefix, (uint32_t)n_jobs, pl.uniform, pl.total_items);
   ctx->launches++;
   B2_CUDA(ctx, cudaGetLastError());
   return B2_OK;
@@ -337,16 +402,12 @@ extern "C" int b2_vp8l_predictor_inverse(b2_ctx* ctx, int stream, const b2_argb_
   if (n_jobs < 0) return B2_ERR_INVALID_CONFIG;
   if (n_jobs == 0) return B2_OK;
   if (jobs == NULL) return B2_ERR_NULL;
-  if (n_jobs > 65535) return B2_ERR_INVALID_CONFIG;  // grid.y = image
-  const PredJobDev* dj; const uint32_t* dp; uint32_t uni, tot, mb, nd;
-  const int st = prepare_pred(ctx, stream, jobs, n_jobs, &dj, &dp, &uni, &tot, &mb, &nd);
+  PredPlan pl;
+  const int st = prepare_pred(ctx, stream, jobs, n_jobs, true, &pl);
   if (st != B2_OK) return st;
-  // at most min(bands, ceil(ktiles / 2) + 1) tiles of one image share a diagonal
-  const dim3 grid((mb + kInvWarps - 1) / kInvWarps, (unsigned)n_jobs);
-  for (uint32_t d = 0; d < nd; ++d) {
-    predictor_inverse_diag_kernel<<<grid, kInvThreads, 0, ctx->streams[stream]>>>(dj, d);
-    ctx->launches++;
-  }
+  const int grid = b2_grid_for(ctx, 8, (pl.total_bands + kInvWarps - 1) / kInvWarps);
+  predictor_inverse_wave_kernel<<<grid, kInvThreads, 0, ctx->streams[stream]>>>(pl.jobs, pl.order, pl.total_bands, pl.ctl);
+  ctx->launches++;
   B2_CUDA(ctx, cudaGetLastError());
   return B2_OK;
 }

@@ -62,7 +62,12 @@ if "vp8l" in which:
                           ("add_green", 0, 8.0), ("sub_green", 0, 8.0), ("color_index_inverse", 0, 8.0),
                           ("color_index_inverse", 1, 6.0), ("color_index_inverse", 2, 5.0), ("color_index_inverse", 3, 4.5),
                           ("predictor_forward", 5, 8.004), ("predictor_inverse", 5, 8.004)):
-        p = ArgbPipeline(ctx, 8, 4096, 4096, op, bits)
+        if os.environ.get("B2_OPS") and op not in os.environ["B2_OPS"].split(","):
+            continue
+        nf = int(os.environ.get("B2_ARGB_FRAMES", "8"))
+        aw, ah = int(os.environ.get("B2_ARGB_W", "4096")), int(os.environ.get("B2_ARGB_H", "4096"))
+        p = ArgbPipeline(ctx, nf, aw, ah, op, bits)
         p.fill_synthetic(0xB2000003)
-        report(f"vp8l {op} bits={bits} 8x4096^2", 8 * 4096 * 4096, bpp, timed(p.run_device))
+        ms = timed(p.run_device, 5 if "predictor" in op else 20)
+        report(f"vp8l {op} bits={bits} {nf}x{aw}x{ah} ({ms * 1e3:.0f} us)", nf * aw * ah, bpp, ms)
         p.close()

@@ -240,7 +240,7 @@ def other_kernels(ctx, peak, steps):
             ("fancy_upsample_4k_rgba", 64, 3840, 2160, _abi.MODE_RGBA, False, 5.5),
             ("fancy_upsample_4k_bgra_with_alpha_plane", 32, 3840, 2160, _abi.MODE_BGRA, True, 6.5),
             ("fancy_upsample_4k_rgb", 32, 3840, 2160, _abi.MODE_RGB, False, 4.5),
-            ("fancy_upsample_1080p_rgba", 128, 1920, 1080, _abi.MODE_RGBA, False, 5.5)]:
+            ("fancy_upsample_1080p_rgba", 256, 1920, 1080, _abi.MODE_RGBA, False, 5.5)]:
         up = UpsamplePipeline(ctx, frames, w, h, mode, with_alpha=wa, host=False)
         up.fill_synthetic(0xB2000004)
         ms = timed(up.run_device, k)

@@ -102,59 +102,110 @@ __device__ __forceinline__ uint32_t predict(uint32_t mode, uint32_t l, uint32_t 
   }
 }
 
+// predict() with the mode known at compile time, and the 4 pixels of a lane
+template <int MODE>
+__device__ __forceinline__ uint32_t predict_c(uint32_t l, uint32_t tl, uint32_t t, uint32_t tr) {
+  if (MODE == 1) return l;
+  if (MODE == 2) return t;
+  if (MODE == 3) return tr;
+  if (MODE == 4) return tl;
+  if (MODE == 5) return avg2(avg2(l, tr), t);
+  if (MODE == 6) return avg2(l, tl);
+  if (MODE == 7) return avg2(l, t);
+  if (MODE == 8) return avg2(tl, t);
+  if (MODE == 9) return avg2(t, tr);
+  if (MODE == 10) return avg2(avg2(l, tl), avg2(t, tr));
+  if (MODE == 11) return select_px(t, l, tl);
+  if (MODE == 12) return clamp_add_sub_full(l, t, tl);
+  if (MODE == 13) return clamp_add_sub_half(l, t, tl);
+  return 0xff000000u;
+}
+template <int MODE>
+__device__ __forceinline__ void forward4(const uint32_t (&cur)[4], const uint32_t (&up)[6], uint32_t l, bool first_col,
+                                         uint32_t (&o)[4]) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    uint32_t pred = predict_c<MODE>(l, up[k], up[k + 1], up[k + 2]);
+    if (k == 0 && first_col) pred = up[1];   // first column = T (lossless_enc.go / predictor_enc.go:690)
+    o[k] = sub_pixels(cur[k], pred);
+    l = cur[k];
+  }
+}
+
 // ---- forward ----------------------------------------------------------------------
 constexpr int kFwdThreads = 256;
-// item = 1024 consecutive pixels of the flat image, 4 per thread.  With width % 4 == 0
-// and aligned images a thread's 4 pixels share a row and a mode tile (bits >= 2): two
-// 128-bit loads (current and upper row) plus three scalar neighbours, one 128-bit store.
+constexpr int kFwdBlock = 256;  // item = a 256-pixel wide, kFwdRows tall block of one image: a warp per 32-pixel
+constexpr int kFwdRows = 64;    // column, 4 rows per pass
+// A CTA takes a 256-pixel wide block (1 KB of every row it touches), a warp a 32-pixel
+// column of it, 4 rows per pass, a lane 4 consecutive pixels of one row: a warp-wide
+// access is four whole 128-byte lines.  With the reference's usual tile
+// sizes (bits >= 5) the block lies in ONE mode tile, so the predictor switch is uniform
+// over the warp; with smaller tiles a lane's 4 aligned pixels still share a tile
+// (bits >= 2).  Two 128-bit loads (current and upper row) plus three scalar neighbours,
+// one 128-bit store.  Rows that are not 16-byte aligned take the same mapping with scalar
+// accesses.
 __global__ void __launch_bounds__(kFwdThreads, 8)
 predictor_forward_kernel(const PredJobDev* __restrict__ jobs, const uint32_t* __restrict__ prefix,
                          uint32_t n_jobs, uint32_t uniform, uint32_t total_items) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (uint32_t item = blockIdx.x; item < total_items; item += gridDim.x) {
     uint32_t local;
     const uint32_t img = b2_find_image(prefix, n_jobs, uniform, item, &local);
     const PredJobDev* __restrict__ j = jobs + img;
-    const int w = j->width;
-    const size_t n = (size_t)w * j->height;
-    const size_t p0 = ((size_t)local * kFwdThreads + threadIdx.x) * 4;
-    if (p0 >= n) continue;
+    const int w = j->width, h = j->height;
+    const uint32_t bx = (uint32_t)(w + kFwdBlock - 1) / kFwdBlock;
+    const int by0 = (int)(local / bx) * kFwdRows, bx0 = (int)(local % bx) * kFwdBlock;
+    const int x = bx0 + warp * 32 + (lane & 7) * 4;
+    if (x >= w) continue;
     const uint32_t* __restrict__ a = j->src;
+    const uint32_t mode_shift = (uint32_t)j->bits;
+    const uint32_t* __restrict__ mode_col = j->modes + (x >> mode_shift);
+    const uint32_t tiles_per_row = j->tiles_per_row;
+    uint32_t* __restrict__ dst = j->dst;
+    const int y_end = min(h, by0 + kFwdRows);
+    for (int y = by0 + (lane >> 3); y < y_end; y += 4) {
+    const size_t p0 = (size_t)y * w + x;
     const bool vec = ((w & 3) == 0) && (((((uintptr_t)a) | ((uintptr_t)j->dst)) & 15) == 0);
+    const int n = min(4, w - x);
+    uint32_t cur[4] = {0, 0, 0, 0}, o[4];
     if (vec) {
-      const int y = (int)(p0 / (uint32_t)w), x = (int)(p0 - (size_t)y * w);
       const uint4 cv = b2_ldg_stream_v4(a + p0);
-      const uint32_t cur[4] = {cv.x, cv.y, cv.z, cv.w};
-      uint32_t o[4];
-      if (y == 0) {  // first row = L, first pixel = black (lossless_enc.go / predictor_enc.go:683-689)
-        uint32_t l = (x == 0) ? 0xff000000u : __ldg(a + p0 - 1);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { o[k] = sub_pixels(cur[k], l); l = cur[k]; }
-      } else {
-        const uint4 uv = __ldg(reinterpret_cast<const uint4*>(a + p0 - w));
-        // upper[x + 1] of the last column is the first pixel of the current row (contiguous image)
-        const uint32_t up[6] = {(x == 0) ? 0u : __ldg(a + p0 - w - 1), uv.x, uv.y, uv.z, uv.w, __ldg(a + p0 - w + 4)};
-        const uint32_t mode = (__ldg(j->modes + (size_t)(y >> j->bits) * j->tiles_per_row + (x >> j->bits)) >> 8) & 0xf;
-        uint32_t l = (x == 0) ? 0u : __ldg(a + p0 - 1);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint32_t pred = (x + k == 0) ? up[1] : predict(mode, l, up[k], up[k + 1], up[k + 2]);  // first column = T
-          o[k] = sub_pixels(cur[k], pred);
-          l = cur[k];
-        }
-      }
-      b2_stg_stream_v4(j->dst + p0, make_uint4(o[0], o[1], o[2], o[3]));
+      cur[0] = cv.x; cur[1] = cv.y; cur[2] = cv.z; cur[3] = cv.w;
     } else {
-      for (size_t p = p0; p < min(p0 + 4, n); ++p) {
-        const int y = (int)(p / (uint32_t)w), x = (int)(p - (size_t)y * w);
-        uint32_t pred;
-        if (y == 0) pred = (x == 0) ? 0xff000000u : __ldg(a + p - 1);
-        else if (x == 0) pred = __ldg(a + p - w);
-        else {
-          const uint32_t mode = (__ldg(j->modes + (size_t)(y >> j->bits) * j->tiles_per_row + (x >> j->bits)) >> 8) & 0xf;
-          pred = predict(mode, __ldg(a + p - 1), __ldg(a + p - w - 1), __ldg(a + p - w), __ldg(a + p - w + 1));
-        }
-        j->dst[p] = sub_pixels(__ldg(a + p), pred);
+      for (int k = 0; k < n; ++k) cur[k] = __ldg(a + p0 + k);
+    }
+    if (y == 0) {  // first row = L, first pixel = black (lossless_enc.go / predictor_enc.go:683-689)
+      uint32_t l = (x == 0) ? 0xff000000u : __ldg(a + p0 - 1);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { o[k] = sub_pixels(cur[k], l); l = cur[k]; }
+    } else {
+      // upper[x + 1] of the last column is the first pixel of the current row (contiguous image)
+      uint32_t up[6];
+      up[0] = (x == 0) ? 0u : __ldg(a + p0 - w - 1);
+      if (vec) {
+        const uint4 uv = __ldg(reinterpret_cast<const uint4*>(a + p0 - w));
+        up[1] = uv.x; up[2] = uv.y; up[3] = uv.z; up[4] = uv.w;
+        up[5] = __ldg(a + p0 - w + 4);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) up[1 + k] = (k <= n) ? __ldg(a + p0 - w + k) : 0u;
       }
+      const uint32_t mode = (__ldg(mode_col + (size_t)((uint32_t)y >> mode_shift) * tiles_per_row) >> 8) & 0xf;
+      const uint32_t l0 = (x == 0) ? 0u : __ldg(a + p0 - 1);
+      // one dispatch for the lane's 4 pixels: the mode is a compile-time constant inside
+      switch (mode) {
+#define B2_FWD_CASE(M) case M: forward4<M>(cur, up, l0, x == 0, o); break;
+        B2_FWD_CASE(1) B2_FWD_CASE(2) B2_FWD_CASE(3) B2_FWD_CASE(4) B2_FWD_CASE(5) B2_FWD_CASE(6) B2_FWD_CASE(7)
+        B2_FWD_CASE(8) B2_FWD_CASE(9) B2_FWD_CASE(10) B2_FWD_CASE(11) B2_FWD_CASE(12) B2_FWD_CASE(13)
+#undef B2_FWD_CASE
+        default: forward4<0>(cur, up, l0, x == 0, o); break;
+      }
+    }
+    if (vec) {
+      b2_stg_stream_v4(dst + p0, make_uint4(o[0], o[1], o[2], o[3]));
+    } else {
+      for (int k = 0; k < n; ++k) dst[p0 + k] = o[k];
+    }
     }
   }
 }
@@ -354,8 +405,7 @@ int prepare_pred(b2_ctx* ctx, int stream, const b2_argb_job* jobs, int n_jobs, b
     d.bands = (uint32_t)((j.height + 31) / 32);
     d.flag_off = flag_off;
     flag_off += d.bands;
-    const uint64_t n = (uint64_t)j.width * (uint64_t)j.height;
-    const uint32_t items = (uint32_t)((n + 4 * kFwdThreads - 1) / (4 * kFwdThreads));
+    const uint32_t items = (uint32_t)((j.width + kFwdBlock - 1) / kFwdBlock) * (uint32_t)((j.height + kFwdRows - 1) / kFwdRows);
     if (i == 0) uni = items; else if (items != uni) uni = 0;
     pre[i] = (uint32_t)tot;
     tot += items;

@@ -22,6 +22,8 @@
 //     stream order.  Tile boundaries read their neighbours back from the output image.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "b2_common.cuh"
 
 namespace {
@@ -246,8 +248,38 @@ __device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
 
+// predict() without divergent branches: the serial chain of the wavefront is one step long,
+// and a divergent switch (the lanes of a band sit in 2-3 different mode tiles) costs more
+// than computing the candidates.  `need` = warp-wide union of the modes in use (bit m set
+// when some lane is in mode m), so whole candidate groups are skipped by UNIFORM branches
+// when no lane wants them.  Late candidates go last in the select chain.
+__device__ __forceinline__ uint32_t predict_flat(uint32_t mode, uint32_t need, uint32_t l, uint32_t tl, uint32_t t, uint32_t tr) {
+  uint32_t p = 0xff000000u;                              // modes 0, 14, 15
+  p = (mode == 2) ? t : p;
+  p = (mode == 4) ? tl : p;
+  p = (mode == 3) ? tr : p;
+  p = (mode == 1) ? l : p;
+  if (need & 0x07e0u) {                                  // the averaging modes 5..10
+    const uint32_t x1 = avg2(l, tr), x2 = avg2(l, tl), x3 = avg2(t, tr);
+    const uint32_t a = (mode == 5) ? x1 : (mode == 7) ? l : (mode == 8) ? tl : x2;
+    const uint32_t b = (mode == 10) ? x3 : t;
+    const uint32_t pav = avg2(a, b);                     // modes 5, 7, 8, 10
+    p = (mode == 9) ? x3 : p;
+    p = (mode == 6) ? x2 : p;
+    p = (mode == 5 || mode == 7 || mode == 8 || mode == 10) ? pav : p;
+  }
+  if (need & (1u << 11)) p = (mode == 11) ? select_px(t, l, tl) : p;
+  if (need & (1u << 12)) p = (mode == 12) ? clamp_add_sub_full(l, t, tl) : p;
+  if (need & (1u << 13)) p = (mode == 13) ? clamp_add_sub_half(l, t, tl) : p;
+  return p;
+}
+
 // One band.  VEC: width % 4 == 0 and 16-byte aligned images, so a lane's 8-pixel groups
-// are two aligned 128-bit accesses.
+// are two aligned 128-bit accesses.  The step is written without divergent branches: what
+// happens for only some lanes (fetching the next 8 residuals when c % 8 == 0 -- always an
+// even step --, writing 8 finished outputs when c % 8 == 7 -- always an odd step --,
+// switching mode tile) is predicated; the branches left are warp-uniform or rare (the
+// chunk of the row above every 32 steps, publishing progress, unaligned images).
 template <bool VEC>
 __device__ __forceinline__ void inverse_band(const PredJobDev* __restrict__ jp, uint32_t i, uint32_t* __restrict__ flags,
                                              uint32_t* ring, int lane) {
@@ -263,81 +295,115 @@ __device__ __forceinline__ void inverse_band(const PredJobDev* __restrict__ jp, 
   const bool publish = (lane == 31) && (i + 1 < jp->bands);
   uint32_t avail = 0;            // columns of up_row known to be complete
   uint32_t upc = 0;              // lane q: up_row[k0 + 1 + q] of the current 32-column chunk
-  uint32_t left = 0, tl = 0, t = 0, last_out = 0, first_px = 0;
+  uint32_t left = 0, tl = 0, t = 0, first_px = 0;   // left doubles as the value the lane below takes as TR
   const int tile_mask = (1 << bits) - 1;
   const int mt_last = (int)jp->tiles_per_row - 1;
   auto load_mode = [&](int mt) -> uint32_t {
     return (row_ok && mt <= mt_last) ? (__ldg(mode_row + mt) >> 8) & 0xf : 0u;
   };
-  uint32_t mode = load_mode(0), mode_nxt = load_mode(1);
+  // The mode of a lane's current 8-column group; the next group's is fetched one group
+  // ahead, both on the even steps where the lane's c % 8 == 0 (8 aligned columns share a
+  // mode tile when bits >= 3; 4-pixel tiles re-read the mode every 4 columns instead).
+  uint32_t mode = 0, mode_nxt = load_mode(0);
+  uint32_t need = 0;             // warp-wide union of 1 << mode
   uint32_t* const in_l = ring + lane * kLaneWords;
-  uint32_t* const out_l = in_l + kInSlots;
   const uint32_t in_s = (uint32_t)__cvta_generic_to_shared(in_l);
+  const uint32_t out_s = in_s + kInSlots * 4;
+  const bool row0 = (row == 0);
   const int k_end = w + 62;
-  int c = -8 - 2 * lane;
-  for (int k = -8; k < k_end; ++k, ++c) {
-    if (((k + 1) & 31) == 0 && i > 0) {          // next chunk of the row above: columns k+1 .. k+32
-      const uint32_t need = (uint32_t)min(w, k + 33);
-      while (avail < need) {
+
+  auto step = [&](auto odd_tag, auto steady_tag, int k) {
+    constexpr bool ODD = decltype(odd_tag)::value;
+    constexpr bool STEADY = decltype(steady_tag)::value;   // every lane at 1 <= c <= w-2 of an existing row > 0
+    const int c = k - 2 * lane;
+    if (((k + 1) & 31) == 0 && i > 0) {          // next chunk of the row above: columns k+1 .. k+32 (uniform)
+      const uint32_t need_cols = (uint32_t)min(w, k + 33);
+      while (avail < need_cols) {
         avail = ld_acquire_u32(flag_up);
-        if (avail < need) __nanosleep(64);
+        if (avail < need_cols) __nanosleep(64);
       }
       const int col = k + 1 + lane;
       upc = (col < w) ? __ldcg(up_row + col) : 0u;
     }
     // TR = (row-1, c+1): the lane above finished it on the previous step
-    uint32_t tr = __shfl_up_sync(0xffffffffu, last_out, 1);
+    uint32_t tr = __shfl_up_sync(0xffffffffu, left, 1);
     const uint32_t u = __shfl_sync(0xffffffffu, upc, (k + 1) & 31);
-    if (lane == 0) tr = u;
-    if ((c & 7) == 0 && row_ok) {
-      // the group fetched 8 steps ago (columns c .. c+7) must have landed; then fetch
-      // columns c+8 .. c+15 into the other half of the ring
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    tr = (lane == 0) ? u : tr;
+    if (!ODD) {
+      // lanes with c % 8 == 0 fetch columns c+8 .. c+15 into the other half of their ring.
+      // Every lane commits one (possibly empty) group per even step; the group a lane
+      // reads from now on was committed 4 even steps ago.
       const int cc = c + 8;
-      if (cc < w) {
-        const uint32_t dst = in_s + (uint32_t)(cc & 8) * 4u;
-        if (VEC) {
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(in_row + cc) : "memory");
-          if (cc + 4 < w) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + 16), "l"(in_row + cc + 4) : "memory");
-        } else {
+      const bool grp = (c & 7) == 0;
+      const bool trig = grp && (STEADY || (row_ok && cc >= 0)) && cc < w;
+      const uint32_t dst = in_s + (uint32_t)(cc & 8) * 4u;
+      if (VEC) {
+        if (trig) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(in_row + cc) : "memory");
+        if (trig && cc + 4 < w) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + 16), "l"(in_row + cc + 4) : "memory");
+      } else if (trig) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e)
-            if (cc + e < w) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst + 4 * e), "l"(in_row + cc + e) : "memory");
-        }
+        for (int e = 0; e < 8; ++e)
+          if (cc + e < w) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst + 4 * e), "l"(in_row + cc + e) : "memory");
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
-    }
-    if (c > 0 && (c & tile_mask) == 0) {         // entering the next mode tile
-      mode = mode_nxt;
-      mode_nxt = load_mode((c >> bits) + 1);
-    }
-    if (row_ok && c >= 0 && c < w) {
-      const uint32_t res = *reinterpret_cast<volatile uint32_t*>(in_l + (c & (kInSlots - 1)));
-      if (c == w - 1) tr = first_px;             // upper[x+1] of the last column wraps to the row start
-      uint32_t pred;
-      if (row == 0) pred = (c == 0) ? 0xff000000u : left;   // lossless.go:292-295
-      else if (c == 0) pred = t;                               // :312
-      else pred = predict(mode, left, tl, t, tr);
-      const uint32_t o = add_pixels(res, pred);
-      out_l[c & 7] = o;
-      if (c == 0) first_px = o;
-      left = o;
-      last_out = o;
-      if ((c & 7) == 7 || c == w - 1) {          // a finished group of 8 (or the row's tail)
-        const int base = c & ~7;
-        const int n = c - base + 1;
-        if (VEC) {
-          b2_stg_stream_v4(out_row + base, *reinterpret_cast<const uint4*>(out_l));
-          if (n > 4) b2_stg_stream_v4(out_row + base + 4, *reinterpret_cast<const uint4*>(out_l + 4));
-        } else {
-          for (int e = 0; e < n; ++e) out_row[base + e] = out_l[e];
-        }
-        if (publish && (((c + 1) & (kPublish - 1)) == 0 || c == w - 1)) st_release_u32(flag_me, (uint32_t)(c + 1));
+      asm volatile("cp.async.wait_group 4;" ::: "memory");
+      if (bits >= 3) {
+        if (grp && c >= 0) { mode = mode_nxt; mode_nxt = load_mode((c + 8) >> bits); }
+      } else if ((c & 3) == 0 && c >= 0) {
+        mode = load_mode(c >> bits);
       }
+      need = __reduce_or_sync(0xffffffffu, 1u << mode);
     }
+    const bool active = STEADY || (row_ok && (unsigned)c < (unsigned)w);
+    uint32_t res;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(res) : "r"(in_s + (uint32_t)(c & (kInSlots - 1)) * 4u) : "memory");
+    if (!STEADY) tr = (c == w - 1) ? first_px : tr;      // upper[x+1] of the last column wraps to the row start
+    uint32_t pred = predict_flat(mode, need, left, tl, t, tr);
+    if (!STEADY) {
+      pred = (c == 0) ? t : pred;                  // lossless.go:312
+      pred = row0 ? ((c == 0) ? 0xff000000u : left) : pred;   // :292-295
+    }
+    const uint32_t o = add_pixels(res, pred);
+    asm volatile("st.shared.u32 [%0], %1;" :: "r"(out_s + (uint32_t)(c & 7) * 4u), "r"(o) : "memory");
+    if (!STEADY) first_px = (active && c == 0) ? o : first_px;
+    left = active ? o : left;
     tl = t;
     t = tr;
+    // a finished group of 8, or the row's tail (an odd step when width % 4 == 0)
+    const bool fl = active && ((c & 7) == 7 || (!STEADY && c == w - 1));
+    if (VEC) {
+      if (ODD) {
+        uint4 q0, q1;
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q0.x), "=r"(q0.y), "=r"(q0.z), "=r"(q0.w) : "r"(out_s) : "memory");
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q1.x), "=r"(q1.y), "=r"(q1.z), "=r"(q1.w) : "r"(out_s + 16) : "memory");
+        uint32_t* g = out_row + (c & ~7);
+        if (fl) b2_stg_stream_v4(g, q0);
+        if (fl && (c & 4)) b2_stg_stream_v4(g + 4, q1);
+      }
+    } else if (fl) {
+      const int base = c & ~7;
+      const uint32_t* out_l = in_l + kInSlots;
+      for (int e = 0; e <= c - base; ++e) out_row[base + e] = *reinterpret_cast<const volatile uint32_t*>(out_l + e);
+    }
+    if ((ODD || !VEC) && publish && fl && (((c + 1) & (kPublish - 1)) == 0 || c == w - 1)) st_release_u32(flag_me, (uint32_t)(c + 1));
+  };
+  // steady steps: lane 31 at c >= 1 (k >= 63) and lane 0 at c <= w - 2 (k <= w - 2), full band below row 0
+  const bool full_band = (i > 0) && ((int)i * 32 + 31 < h);
+  const int ks0 = 64, ks1 = full_band ? ((w - 1) & ~1) : 0;   // [ks0, ks1), both even
+  int k = -8;
+  for (; k < k_end && (k < ks0 || ks1 <= ks0); k += 2) {
+    step(std::false_type{}, std::false_type{}, k);
+    step(std::true_type{}, std::false_type{}, k + 1);
   }
+  for (; k < ks1; k += 2) {
+    step(std::false_type{}, std::true_type{}, k);
+    step(std::true_type{}, std::true_type{}, k + 1);
+  }
+  for (; k < k_end; k += 2) {
+    step(std::false_type{}, std::false_type{}, k);
+    step(std::true_type{}, std::false_type{}, k + 1);
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 __global__ void __launch_bounds__(kInvThreads, 8)

@@ -268,3 +268,99 @@ class ArgbPipeline:
     def close(self):
         for b in ("d_src", "d_dst", "d_data"):
             getattr(self, b).free()
+
+
+def mixed_sizes(n: int = 256, seed: int = 0xB2000005, lo: int = 64, hi: int = 8192):
+    """The configs[4] batch: w and h independently log-uniform in
+    [lo, hi] from the counter-based generator, parities forced so the four (odd/even w
+    x odd/even h) classes are equally represented, corner cases always included."""
+    def lowbias32(x):
+        x &= 0xFFFFFFFF
+        x ^= x >> 16; x = (x * 0x7FEB352D) & 0xFFFFFFFF
+        x ^= x >> 15; x = (x * 0x846CA68B) & 0xFFFFFFFF
+        x ^= x >> 16
+        return x
+    fixed = [(64, 64), (8192, 8192), (65, 8191), (8191, 65)]
+    out = list(fixed[:max(0, min(len(fixed), n))])
+    ratio = hi / lo
+    for i in range(len(out), n):
+        uw = lowbias32(seed ^ (2 * i * 0x9E3779B1)) / 2.0**32
+        uh = lowbias32(seed ^ ((2 * i + 1) * 0x9E3779B1)) / 2.0**32
+        w = int(lo * ratio**uw)
+        h = int(lo * ratio**uh)
+        w = min(hi, max(lo, (w & ~1) | (i & 1)))
+        h = min(hi, max(lo, (h & ~1) | ((i >> 1) & 1)))
+        out.append((w, h))
+    return out
+
+
+class MixedPipeline:
+    """Device-resident batch of images of DIFFERENT sizes through the whole pixel path
+    (configs[4]): RGBA -> YUV420A import, fancy upsample back to BGRA, and the VP8L
+    inverse chain (cross-colour inverse + add-green, bits = 5) on the result -- three
+    launches per pass, each over the whole batch as one flat work list."""
+
+    def __init__(self, ctx: Context, sizes, mode: int = _abi.MODE_BGRA, bits: int = 5):
+        self.ctx, self.sizes, self.mode, self.bits = ctx, list(sizes), mode, bits
+        n = self.n = len(self.sizes)
+        sub = lambda v, b: (v + (1 << b) - 1) >> b  # noqa: E731
+        off = {k: [0] for k in ("src", "y", "uv", "dst", "data")}
+        self.geo = []
+        for (w, h) in self.sizes:
+            uvw, uvh = (w + 1) >> 1, (h + 1) >> 1
+            ys, uvs, ds = _al(w, 16), _al(uvw, 16), _al(4 * w, 16)
+            self.geo.append((w, h, uvw, uvh, ys, uvs, ds))
+            off["src"].append(off["src"][-1] + _al(4 * w * h))
+            off["y"].append(off["y"][-1] + _al(ys * h))
+            off["uv"].append(off["uv"][-1] + _al(uvs * uvh))
+            off["dst"].append(off["dst"][-1] + _al(ds * h))
+            off["data"].append(off["data"][-1] + _al(4 * sub(w, bits) * sub(h, bits)))
+        self.off = off
+        self.d_src = ctx.alloc(off["src"][-1])
+        self.d_y = ctx.alloc(off["y"][-1])
+        self.d_a = ctx.alloc(off["y"][-1])
+        self.d_u = ctx.alloc(off["uv"][-1])
+        self.d_v = ctx.alloc(off["uv"][-1])
+        self.d_dst = ctx.alloc(off["dst"][-1])
+        self.d_out = ctx.alloc(off["src"][-1])
+        self.d_data = ctx.alloc(off["data"][-1])
+        self.d_flags = ctx.alloc(_al(4 * n))
+        imp, ups, arg = [], [], []
+        for i, (w, h, uvw, uvh, ys, uvs, ds) in enumerate(self.geo):
+            y, a = self.d_y.ptr + off["y"][i], self.d_a.ptr + off["y"][i]
+            u, v = self.d_u.ptr + off["uv"][i], self.d_v.ptr + off["uv"][i]
+            imp.append(_abi.ImportJob(self.d_src.ptr + off["src"][i], y, u, v, a, 4 * w, ys, uvs, ys, w, h))
+            ups.append(_abi.UpsampleJob(y, u, v, a, self.d_dst.ptr + off["dst"][i], ys, uvs, ys, ds, w, h, 0, h))
+            # the ARGB chain runs on the tightly packed source image (same pixel count)
+            arg.append(_abi.ArgbJob(self.d_src.ptr + off["src"][i], self.d_out.ptr + off["src"][i],
+                                    self.d_data.ptr + off["data"][i], w, h, bits, 0))
+        self._imp = (_abi.ImportJob * n)(*imp)
+        self._ups = (_abi.UpsampleJob * n)(*ups)
+        self._arg = (_abi.ArgbJob * n)(*arg)
+        self.pixels = sum(w * h for (w, h) in self.sizes)
+
+    def algorithmic_bytes(self) -> int:
+        """import 4+1+1 (+UV), upsample 1+1 (+UV) + 4, chain 4+4 per pixel (tile codes negligible)."""
+        t = 0
+        for (w, h, uvw, uvh, ys, uvs, ds) in self.geo:
+            t += (6 * w * h + 2 * uvw * uvh) + (6 * w * h + 2 * uvw * uvh) + 8 * w * h
+        return t
+
+    def fill_synthetic(self, seed: int):
+        c = self.ctx
+        sub = lambda v, b: (v + (1 << b) - 1) >> b  # noqa: E731
+        for i, (w, h, *_rest) in enumerate(self.geo):
+            c.synth_fill(self.d_src.ptr + self.off["src"][i], w, h, 4 * w, _al(4 * w * h), 1, seed, i, 0, _abi.SYNTH_SPARSE)
+            words = sub(w, self.bits) * sub(h, self.bits)
+            c.synth_fill(self.d_data.ptr + self.off["data"][i], words, 1, 4 * words, _al(4 * words), 1, seed, i, 6)
+        c.sync()
+
+    def run_device(self, stream: int = 0):
+        c = self.ctx
+        c._chk(c.lib.b2_rgba_to_yuv420a(c.h, stream, self._imp, self.n, _abi.ORDER_RGBA, _abi.IMPORT_ALPHA, self.d_flags.ptr))
+        c._chk(c.lib.b2_yuv420a_to_rgba_fancy(c.h, stream, self._ups, self.n, self.mode))
+        c._chk(c.lib.b2_vp8l_inverse_chain(c.h, stream, self._arg, self.n))
+
+    def close(self):
+        for b in ("d_src", "d_y", "d_a", "d_u", "d_v", "d_dst", "d_out", "d_data", "d_flags"):
+            getattr(self, b).free()

@@ -57,3 +57,26 @@ def test_two_rank_sharding_gloo():
     lpt = sorted(i for g in gathered for i in g[1])
     assert cont == list(range(37)) and lpt == list(range(37))
     assert tmax == 2.0
+
+
+def test_mixed_size_batch_and_lpt_balance():
+    """configs[4] batch generator: deterministic, corner cases first, the
+    four parity classes equally represented, sizes within [64, 8192]; LPT on algorithmic
+    bytes balances 2/4/8 ranks to well under 1 %."""
+    sys.path.insert(0, ROOT)
+    from go_webp_b200 import partition
+    from go_webp_b200.pipeline import mixed_sizes
+    s = mixed_sizes(256)
+    assert s == mixed_sizes(256)
+    assert s[:4] == [(64, 64), (8192, 8192), (65, 8191), (8191, 65)]
+    assert all(64 <= w <= 8192 and 64 <= h <= 8192 for (w, h) in s)
+    classes = [0, 0, 0, 0]
+    for (w, h) in s[4:]:
+        classes[(w & 1) | ((h & 1) << 1)] += 1
+    assert max(classes) - min(classes) <= 1
+    assert 0.4e9 < sum(w * h for (w, h) in s) < 1.2e9
+    costs = [partition.import_cost_bytes(w, h) + partition.upsample_cost_bytes(w, h, True) + 8 * w * h for (w, h) in s]
+    for g in (2, 4, 8):
+        parts = partition.lpt_partition(costs, g)
+        assert sorted(i for p in parts for i in p) == list(range(256))
+        assert max(sum(costs[i] for i in p) for p in parts) * g / sum(costs) < 1.01

@@ -206,3 +206,33 @@ def test_tuned_import_tight_rows_any_width(env, size, alpha_mode):
         gy, gu, gv, ga, gha = p.device_planes(i)
         assert (gy == ey).all() and (gu == eu).all() and (gv == ev).all() and (ga == ea).all() and gha == eha, (size, i)
     p.close()
+
+
+def test_mixed_pipeline_device_resident(env):
+    """MixedPipeline (the configs[4] throughput path: three flat launches over images of
+    different sizes): every image of a small mixed batch vs the oracle, inputs from the
+    counter-based generator on both sides."""
+    from go_webp_b200.pipeline import MixedPipeline, mixed_sizes
+    abi, ctx = env["abi"], env["ctx"]
+    sizes = [(64, 64), (65, 131), (130, 67), (1001, 77), (257, 300), (96, 33)]
+    seed = 0xB2000005
+    p = MixedPipeline(ctx, sizes, mode=abi.MODE_BGRA, bits=5)
+    p.fill_synthetic(seed)
+    p.run_device()
+    ctx.sync()
+    sub = lambda v, b: (v + (1 << b) - 1) >> b  # noqa: E731
+    for i, (w, h, uvw, uvh, ys, uvs, ds) in enumerate(p.geo):
+        src = oracle.synth_u32(seed, i, 0, w, h, abi.SYNTH_SPARSE)
+        y, u, v, a, ha = oracle.import_yuva(src.view(np.uint8).reshape(h, w, 4), w, h, "RGBA")
+        gy = ctx.d2h(p.d_y.ptr + p.off["y"][i], ys * h).reshape(h, ys)[:, :w]
+        ga = ctx.d2h(p.d_a.ptr + p.off["y"][i], ys * h).reshape(h, ys)[:, :w]
+        gu = ctx.d2h(p.d_u.ptr + p.off["uv"][i], uvs * uvh).reshape(uvh, uvs)[:, :uvw]
+        gv = ctx.d2h(p.d_v.ptr + p.off["uv"][i], uvs * uvh).reshape(uvh, uvs)[:, :uvw]
+        assert (gy == y).all() and (gu == u).all() and (gv == v).all() and (ga == a).all()
+        gd = ctx.d2h(p.d_dst.ptr + p.off["dst"][i], ds * h).reshape(h, ds)[:, :4 * w]
+        assert (gd == oracle.yuva_to_rgba(y, u, v, a, oracle.MODE_BGRA).reshape(h, 4 * w)).all()
+        words = sub(w, 5) * sub(h, 5)
+        codes = oracle.synth_u32(seed, i, 6, words, 1).reshape(sub(h, 5), sub(w, 5))
+        go = ctx.d2h(p.d_out.ptr + p.off["src"][i], 4 * w * h).view(np.uint32).reshape(h, w)
+        assert (go == oracle.add_green(oracle.color_space_inverse(src, codes, 5))).all()
+    p.close()

@@ -48,8 +48,38 @@ def time_share(ctx, sizes, steps=5, warmup=2):
     return ms, px, by
 
 
+def breakdown(ctx, sizes, label):
+    """Per-kernel device times of one pass over `sizes` (B2_MIXED_BREAKDOWN=1)."""
+    from go_webp_b200 import _abi
+    p = MixedPipeline(ctx, sizes)
+    p.fill_synthetic(SEED)
+    c = ctx
+    calls = [("import", lambda: c._chk(c.lib.b2_rgba_to_yuv420a(c.h, 0, p._imp, p.n, _abi.ORDER_RGBA, _abi.IMPORT_ALPHA, p.d_flags.ptr)), 6.5),
+             ("upsample", lambda: c._chk(c.lib.b2_yuv420a_to_rgba_fancy(c.h, 0, p._ups, p.n, p.mode)), 6.5),
+             ("chain", lambda: c._chk(c.lib.b2_vp8l_inverse_chain(c.h, 0, p._arg, p.n)), 8.0)]
+    out = {"subset": label, "n_images": len(sizes), "mpixel": p.pixels / 1e6}
+    for name, fn, bpp in calls:
+        for _ in range(2):
+            fn()
+        c.sync(); c.event_record(0)
+        for _ in range(5):
+            fn()
+        c.event_record(1); c.sync()
+        ms = c.elapsed_ms(0, 1) / 5
+        out[name] = {"ms": ms, "mpixel_per_s": p.pixels / ms / 1e3, "frac": p.pixels * bpp / ms / 1e6 / PEAK}
+    p.close()
+    print(json.dumps(out), flush=True)
+
+
 def main():
     sizes = mixed_sizes(N_IMAGES, SEED)
+    if os.environ.get("B2_MIXED_BREAKDOWN"):
+        ctx = Context(0, 1)
+        breakdown(ctx, sizes, "all")
+        breakdown(ctx, [s for s in sizes if s[0] % 4 == 0], "width % 4 == 0")
+        breakdown(ctx, [s for s in sizes if s[0] % 2 == 1], "odd width")
+        breakdown(ctx, [s for s in sizes if s[0] % 4 == 2], "width % 4 == 2")
+        return
     costs = [cost(w, h) for (w, h) in sizes]
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world > 1:

@@ -6,11 +6,16 @@
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg
  * use it, and only as the checker / the reported CPU baseline.
  *
- * Parity status: PINNED for parts 1 and 2 against the libwebp 1.6.0 binary the
- * reference transliterates (oracle/libwebp_ref.py, tests/golden/); part 3 has
- * no binary or reference-test pin beyond algebraic identities (the reference's
- * own tests hold no vectors for this path: pkg/generics/sizeof_test.go is its
- * only test) -- see DESIGN.md "Oracle".
+ * Parity status: PINNED against the libwebp 1.6.0 binary the reference
+ * transliterates (the reference's own tests hold no vectors for this path:
+ * pkg/generics/sizeof_test.go is its only test).  Parts 1 and 2: the binary's
+ * import / upsample / decode entry points (oracle/libwebp_ref.py,
+ * tests/golden/make_golden.py).  Part 3: residual images and transform data cut
+ * out of lossless streams the binary wrote, checked against what the binary
+ * decodes them to (tests/golden/make_golden_vp8l.py, vp8l_libwebp160.npz:
+ * predictor with all 14 modes, cross-colour, subtract-green, colour indexing at
+ * 1/2/4/8 bits); the forward transforms are pinned as exact inverses on the same
+ * vectors.  See DESIGN.md "Oracle".
  *
  * Every function cites the reference file:line (relative to the go-webp tree)
  * whose arithmetic it restates.  Where the Go text is ill-typed the intended C

@@ -642,3 +642,28 @@ def test_point_sampler_and_yuv444(gpu, mode):
         u4 = rng.integers(0, 256, (h, w), dtype=np.uint8)
         v4 = rng.integers(0, 256, (h, w), dtype=np.uint8)
         assert (D.WebPYUV444ToRGB(y, u4, v4, mode) == oracle.yuv444_to_rgb(y, u4, v4, mode)).all(), (w, h, mode)
+
+
+def test_vp8l_golden_libwebp_streams(gpu, golden_dir):
+    """Part 3 against the upstream binary: residual images and transform data cut out of
+    libwebp 1.6.0 lossless streams (tests/golden/make_golden_vp8l.py) through
+    VP8LInverseTransformBatch must give what WebPDecodeBGRA gave -- predictor with the
+    encoder's own mode mix, cross-colour, subtract-green (fused and alone), colour
+    indexing at 1/2/4/8 bits with ExpandColorMap on the device."""
+    from test_oracle_golden import vp8l_vectors
+    dsp = gpu["dsp"]
+    imgs, chains, exps, names = [], [], [], []
+    for name, res, trs, expected in vp8l_vectors(golden_dir):
+        chain = []
+        for (t, b, w, h, data) in trs:
+            tr = dsp.VP8LTransform(t, b, w, h, data)
+            if t == dsp.COLOR_INDEXING_TRANSFORM:
+                tr.data = dsp.ExpandColorMap(int(data.size), tr)
+            chain.append(tr)
+        imgs.append(dsp.VP8LImage(res, res.shape[1], res.shape[0]))
+        chains.append(chain)
+        exps.append(expected)
+        names.append(name)
+    outs = dsp.VP8LInverseTransformBatch(imgs, chains)
+    for name, o, e in zip(names, outs, exps):
+        assert o.shape == e.shape and (o == e).all(), name

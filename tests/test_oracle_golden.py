@@ -127,3 +127,63 @@ def test_streaming_schedule_equals_whole_image():
         stream, nrows = oracle.emit_fancy_stream(y, u, v, splits, oracle.MODE_RGBA)
         assert nrows == h
         assert (stream == whole).all()
+
+
+# ---- part 3: VP8L inverse transforms vs streams written and decoded by libwebp 1.6.0 ----
+def vp8l_vectors(golden_dir):
+    """(name, residual, [(type, bits, xsize, ysize, data)], expected) per vector of
+    vp8l_libwebp160.npz (tests/golden/make_golden_vp8l.py)."""
+    g = _load(golden_dir, "vp8l_libwebp160.npz")
+    for name in g["names"]:
+        name = str(name)
+        trs = []
+        for k, (t, b, xs, ys) in enumerate(zip(g[f"{name}/types"], g[f"{name}/bits"], g[f"{name}/xsize"], g[f"{name}/ysize"])):
+            data = g[f"{name}/data{k}"] if f"{name}/data{k}" in g.files else None
+            trs.append((int(t), int(b), int(xs), int(ys), data))
+        yield name, g[f"{name}/residual"], trs, g[f"{name}/expected"]
+
+
+def test_vp8l_inverse_chain_matches_libwebp_streams(golden_dir):
+    """ApplyInverseTransforms (pkg/vp8/vp8l_dec.c.go:710-729) with the oracle's transforms on
+    the residual image and transform data cut out of real libwebp lossless streams must
+    give what WebPDecodeBGRA gives: predictor (all 14 modes occur), cross-colour,
+    subtract-green, colour indexing at 1/2/4/8 bits, ExpandColorMap."""
+    sub = lambda v, b: (v + (1 << b) - 1) >> b  # noqa: E731
+    n, kinds = 0, set()
+    for name, img, trs, expected in vp8l_vectors(golden_dir):
+        for (t, b, w, h, data) in reversed(trs):
+            kinds.add((t, b))
+            if t == 0:
+                img = oracle.predictor_inverse(img, data.reshape(sub(h, b), sub(w, b)), b)
+            elif t == 1:
+                img = oracle.color_space_inverse(img, data.reshape(sub(h, b), sub(w, b)), b)
+            elif t == 2:
+                img = oracle.add_green(img)
+            else:
+                img = oracle.color_index_inverse(img, oracle.expand_color_map(data, b), b, w)
+        assert img.shape == expected.shape and (img == expected).all(), name
+        n += 1
+    assert n >= 15 and {t for (t, _) in kinds} == {0, 1, 2, 3}
+    assert {b for (t, b) in kinds if t == 3} == {0, 1, 2, 3}
+
+
+def test_vp8l_forward_inverts_on_libwebp_vectors(golden_dir):
+    """The forward transforms with the stream's own modes / multipliers are the exact
+    inverses of the pinned inverse transforms (so they are pinned by the same vectors)."""
+    sub = lambda v, b: (v + (1 << b) - 1) >> b  # noqa: E731
+    for name, img, trs, expected in vp8l_vectors(golden_dir):
+        stages = [img]
+        for (t, b, w, h, data) in reversed(trs):
+            cur = stages[-1]
+            if t == 0:
+                nxt = oracle.predictor_inverse(cur, data.reshape(sub(h, b), sub(w, b)), b)
+                assert (oracle.predictor_forward(nxt, data.reshape(sub(h, b), sub(w, b)), b) == cur).all(), name
+            elif t == 1:
+                nxt = oracle.color_space_inverse(cur, data.reshape(sub(h, b), sub(w, b)), b)
+                assert (oracle.color_space_forward(nxt, data.reshape(sub(h, b), sub(w, b)), b) == cur).all(), name
+            elif t == 2:
+                nxt = oracle.add_green(cur)
+                assert (oracle.sub_green(nxt) == cur).all(), name
+            else:
+                nxt = oracle.color_index_inverse(cur, oracle.expand_color_map(data, b), b, w)
+            stages.append(nxt)

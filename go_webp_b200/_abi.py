@@ -65,6 +65,13 @@ class ConvertJob(C.Structure):
                 ("width", C.c_int32), ("height", C.c_int32), ("reserved", C.c_int32)]
 
 
+class PictureJob(C.Structure):
+    _fields_ = [("y", C.c_void_p), ("u", C.c_void_p), ("v", C.c_void_p), ("a", C.c_void_p),
+                ("argb", C.c_void_p), ("y_stride", C.c_int32), ("uv_stride", C.c_int32),
+                ("a_stride", C.c_int32), ("argb_stride", C.c_int32), ("width", C.c_int32),
+                ("height", C.c_int32)]
+
+
 CONVERT_UPSTREAM_16BIT = 1
 ALPHA_APPLY, ALPHA_APPLY_4444, ALPHA_MULT_ARGB, ALPHA_MULT_ROW = 0, 1, 2, 3
 
@@ -111,6 +118,9 @@ SYMBOLS = {
     "b2_alpha_multiply": (C.c_int, [_ctx, C.c_int, C.POINTER(ConvertJob), C.c_int, C.c_int, C.c_int]),
     "b2_yuv_to_rgb_point": (C.c_int, [_ctx, C.c_int, C.POINTER(ConvertJob), C.c_int, C.c_int, C.c_int]),
     "b2_argb_to_yuva_plain": (C.c_int, [_ctx, C.c_int, C.POINTER(PlainJob), C.c_int]),
+    "b2_picture_cleanup_transparent": (C.c_int, [_ctx, C.c_int, C.POINTER(PictureJob), C.c_int, C.c_int]),
+    "b2_picture_blend_alpha": (C.c_int, [_ctx, C.c_int, C.POINTER(PictureJob), C.c_int, C.c_int, C.c_uint32]),
+    "b2_picture_replace_transparent": (C.c_int, [_ctx, C.c_int, C.POINTER(PictureJob), C.c_int, C.c_uint32]),
     "b2_vp8l_color_index_inverse_alpha": (C.c_int, [_ctx, C.c_int, C.POINTER(AlphaIndexJob), C.c_int]),
     "b2_vp8l_expand_color_map": (C.c_int, [_ctx, C.c_int, C.POINTER(ExpandJob), C.c_int]),
     "b2_synth_fill_batch_u32": (C.c_int, [_ctx, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_size_t,

@@ -439,3 +439,63 @@ func (c *Context) YUVToRGBPoint(stream int, jobs []ConvertJob, mode int, yuv444 
 	}
 	return status(c, C.b2_yuv_to_rgb_point(c.h, C.int(stream), &cj[0], C.int(len(cj)), C.int(mode), C.int(f)))
 }
+
+// PictureJob is one device-resident picture of the pre-processing entry points
+// (include/b2webp.h b2_picture_job): Y/U/V/A planes with byte strides, or ARGB rows with
+// a stride in pixels (pkg/picture/picture.go:33-105).
+type PictureJob struct {
+	Y, U, V, A, ARGB                       DevicePtr
+	YStride, UVStride, AStride, ARGBStride int
+	Width, Height                          int
+}
+
+func pictureJobs(jobs []PictureJob) []C.b2_picture_job {
+	cj := make([]C.b2_picture_job, len(jobs))
+	for i, j := range jobs {
+		cj[i] = C.b2_picture_job{
+			y: (*C.uint8_t)(unsafe.Pointer(uintptr(j.Y))), u: (*C.uint8_t)(unsafe.Pointer(uintptr(j.U))),
+			v: (*C.uint8_t)(unsafe.Pointer(uintptr(j.V))), a: (*C.uint8_t)(unsafe.Pointer(uintptr(j.A))),
+			argb:     (*C.uint32_t)(unsafe.Pointer(uintptr(j.ARGB))),
+			y_stride: C.int32_t(j.YStride), uv_stride: C.int32_t(j.UVStride), a_stride: C.int32_t(j.AStride),
+			argb_stride: C.int32_t(j.ARGBStride), width: C.int32_t(j.Width), height: C.int32_t(j.Height),
+		}
+	}
+	return cj
+}
+
+func boolInt(b bool) C.int {
+	if b {
+		return 1
+	}
+	return 0
+}
+
+// CleanupTransparentArea replaces WebPCleanupTransparentArea
+// (pkg/libwebp/enc/picture_tools_enc.c.go:110-183), called by the encoder right after the
+// import when !config.Exact (pkg/libwebp/enc/webp_encoding.go:49-72).
+func (c *Context) CleanupTransparentArea(stream int, jobs []PictureJob, useARGB bool) error {
+	if len(jobs) == 0 {
+		return nil
+	}
+	cj := pictureJobs(jobs)
+	return status(c, C.b2_picture_cleanup_transparent(c.h, C.int(stream), &cj[0], C.int(len(cj)), boolInt(useARGB)))
+}
+
+// BlendAlpha replaces WebPBlendAlpha (pkg/libwebp/enc/picture_tools_enc.c.go:199-276).
+func (c *Context) BlendAlpha(stream int, jobs []PictureJob, useARGB bool, backgroundRGB uint32) error {
+	if len(jobs) == 0 {
+		return nil
+	}
+	cj := pictureJobs(jobs)
+	return status(c, C.b2_picture_blend_alpha(c.h, C.int(stream), &cj[0], C.int(len(cj)), boolInt(useARGB), C.uint32_t(backgroundRGB)))
+}
+
+// ReplaceTransparentPixels replaces WebPReplaceTransparentPixels
+// (pkg/libwebp/enc/picture_tools_enc.c.go:95-108).
+func (c *Context) ReplaceTransparentPixels(stream int, jobs []PictureJob, color uint32) error {
+	if len(jobs) == 0 {
+		return nil
+	}
+	cj := pictureJobs(jobs)
+	return status(c, C.b2_picture_replace_transparent(c.h, C.int(stream), &cj[0], C.int(len(cj)), C.uint32_t(color)))
+}

@@ -290,6 +290,39 @@ typedef struct b2_expand_job {
 } b2_expand_job;
 int b2_vp8l_expand_color_map(b2_ctx* ctx, int stream, const b2_expand_job* jobs, int n_jobs);
 
+/* ---- next rows: picture pre-processing after the import ---------
+ * In-place operations on a picture the library holds on the device.  YUVA form: y, u, v,
+ * a planes with byte strides (pkg/picture/picture.go:33-105 Y/U/V/A + strides); ARGB
+ * form: uint32 0xAARRGGBB rows, argb_stride in PIXELS (Picture.ARGBStride). */
+typedef struct b2_picture_job {
+  uint8_t* y;
+  uint8_t* u;
+  uint8_t* v;
+  uint8_t* a;
+  uint32_t* argb;
+  int32_t y_stride, uv_stride, a_stride; /* bytes, >= the plane's width */
+  int32_t argb_stride;                   /* pixels, >= width */
+  int32_t width, height;
+} b2_picture_job;
+
+/* WebPCleanupTransparentArea (pkg/libwebp/enc/picture_tools_enc.c.go:110-183): fully
+ * transparent 8x8 blocks are flattened to the first value of their run along the block
+ * row (need_reset carry), partially transparent blocks get their transparent luma
+ * replaced by the block average (SmoothenBlock :62-91), left-overs on the right / bottom
+ * are smoothened only (YUVA) or ignored (ARGB).  use_argb selects the form, as
+ * Picture.UseARGB does. */
+int b2_picture_cleanup_transparent(b2_ctx* ctx, int stream, const b2_picture_job* jobs, int n_jobs, int use_argb);
+/* WebPBlendAlpha (picture_tools_enc.c.go:199-276): blends with background_rgb (24-bit RGB)
+ * and resets alpha to 0xff; YUVA form: luma per pixel, chroma with the summed alpha of
+ * its 2x2 block (BLEND / BLEND_10BIT :191-194).  The caller keeps the reference's
+ * "nothing to do without an alpha plane" rule (:218-219). */
+int b2_picture_blend_alpha(b2_ctx* ctx, int stream, const b2_picture_job* jobs, int n_jobs, int use_argb,
+                           uint32_t background_rgb);
+/* WebPReplaceTransparentPixels (picture_tools_enc.c.go:95-108; WebPAlphaReplace,
+ * pkg/color/colorspace/alpha/opague.go:47-53): ARGB pixels with alpha 0 become
+ * color & 0xffffff. */
+int b2_picture_replace_transparent(b2_ctx* ctx, int stream, const b2_picture_job* jobs, int n_jobs, uint32_t color);
+
 /* ---- synthetic inputs (SURVEY.md 8d generator, identical to the oracle's) -
  * One uint32 per (row, word) position of n images laid out 'image_bytes'
  * apart, image ids first_img, first_img+1, ...  alpha_mode shapes the top byte

@@ -27,7 +27,7 @@ _u32p = C.POINTER(C.c_uint32)
 
 def build(force: bool = False) -> None:
     """Compile liboracle.so / liboracle_scalar.so with the committed Makefile."""
-    newest = max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("oracle.c", "oracle_post.c"))
+    newest = max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("oracle.c", "oracle_post.c", "oracle_tools.c"))
     need = force or not all(
         os.path.exists(os.path.join(_HERE, n))
         and os.path.getmtime(os.path.join(_HERE, n)) >= newest
@@ -313,3 +313,43 @@ def yuv444_to_rgb(y, u, v, mode):
     for r in range(h):
         lib().orc_yuv444_row(mode, _p(y[r]), _p(u[r]), _p(v[r]), _p(dst[r]), w)
     return dst
+
+
+# ---- picture pre-processing (oracle_tools.c) -------------------------
+def cleanup_transparent_yuva(y, u, v, a):
+    """WebPCleanupTransparentArea on Y,U,V,A planes; returns new (y, u, v)."""
+    y, u, v = (np.array(p, np.uint8, order="C") for p in (y, u, v))
+    a = np.ascontiguousarray(a, np.uint8)
+    h, w = y.shape
+    lib().orc_cleanup_transparent_yuva(_p(y), _p(u), _p(v), _p(a), y.shape[1], u.shape[1], a.shape[1], w, h)
+    return y, u, v
+
+
+def cleanup_transparent_argb(argb):
+    argb = np.array(argb, np.uint32, order="C")
+    h, w = argb.shape
+    lib().orc_cleanup_transparent_argb(_p(argb), w, w, h)
+    return argb
+
+
+def replace_transparent(argb, color):
+    argb = np.array(argb, np.uint32, order="C")
+    h, w = argb.shape
+    lib().orc_replace_transparent(_p(argb), w, w, h, C.c_uint32(color))
+    return argb
+
+
+def blend_alpha_yuva(y, u, v, a, background_rgb):
+    """WebPBlendAlpha on Y,U,V,A planes; returns new (y, u, v, a)."""
+    y, u, v, a = (np.array(p, np.uint8, order="C") for p in (y, u, v, a))
+    h, w = y.shape
+    lib().orc_blend_alpha_yuva(_p(y), _p(u), _p(v), _p(a), y.shape[1], u.shape[1], a.shape[1], w, h,
+                               C.c_uint32(background_rgb))
+    return y, u, v, a
+
+
+def blend_alpha_argb(argb, background_rgb):
+    argb = np.array(argb, np.uint32, order="C")
+    h, w = argb.shape
+    lib().orc_blend_alpha_argb(_p(argb), w, w, h, C.c_uint32(background_rgb))
+    return argb

@@ -135,3 +135,79 @@ def yuva_to_argb(y, u, v, a=None):
     out = np.frombuffer(buf, np.uint32).reshape(h, p.argb_stride)[:, :w].copy()
     L.WebPPictureFree(C.byref(p))
     return out
+
+
+def _picture_yuva(y, u, v, a):
+    L = lib()
+    h, w = y.shape
+    p = WebPPicture()
+    assert L.WebPPictureInitInternal(C.byref(p), 0x0210)
+    p.width, p.height, p.use_argb = w, h, 0
+    p.colorspace = 4
+    assert L.WebPPictureAlloc(C.byref(p))
+    for ptr, stride, arr in ((p.y, p.y_stride, y), (p.u, p.uv_stride, u), (p.v, p.uv_stride, v), (p.a, p.a_stride, a)):
+        hh, ww = arr.shape
+        buf = (C.c_uint8 * (stride * hh)).from_address(ptr)
+        np.frombuffer(buf, np.uint8).reshape(hh, stride)[:, :ww] = arr
+    return p
+
+
+def _read_yuva(p):
+    w, h = p.width, p.height
+    uvw, uvh = (w + 1) >> 1, (h + 1) >> 1
+    return (_plane(p.y, p.y_stride, w, h), _plane(p.u, p.uv_stride, uvw, uvh),
+            _plane(p.v, p.uv_stride, uvw, uvh), _plane(p.a, p.a_stride, w, h))
+
+
+def _picture_argb(argb):
+    L = lib()
+    h, w = argb.shape
+    p = WebPPicture()
+    assert L.WebPPictureInitInternal(C.byref(p), 0x0210)
+    p.width, p.height, p.use_argb = w, h, 1
+    assert L.WebPPictureAlloc(C.byref(p))
+    buf = (C.c_uint32 * (p.argb_stride * h)).from_address(p.argb)
+    np.frombuffer(buf, np.uint32).reshape(h, p.argb_stride)[:, :w] = argb
+    return p
+
+
+def _read_argb(p):
+    buf = (C.c_uint32 * (p.argb_stride * p.height)).from_address(p.argb)
+    return np.frombuffer(buf, np.uint32).reshape(p.height, p.argb_stride)[:, :p.width].copy()
+
+
+def cleanup_transparent_yuva(y, u, v, a):
+    """WebPCleanupTransparentArea (exported by the binary) on a YUVA picture -> (y, u, v)."""
+    L = lib()
+    p = _picture_yuva(y, u, v, a)
+    L.WebPCleanupTransparentArea(C.byref(p))
+    out = _read_yuva(p)[:3]
+    L.WebPPictureFree(C.byref(p))
+    return out
+
+
+def cleanup_transparent_argb(argb):
+    L = lib()
+    p = _picture_argb(argb)
+    L.WebPCleanupTransparentArea(C.byref(p))
+    out = _read_argb(p)
+    L.WebPPictureFree(C.byref(p))
+    return out
+
+
+def blend_alpha_yuva(y, u, v, a, background_rgb):
+    L = lib()
+    p = _picture_yuva(y, u, v, a)
+    L.WebPBlendAlpha(C.byref(p), C.c_uint32(background_rgb))
+    out = _read_yuva(p)
+    L.WebPPictureFree(C.byref(p))
+    return out
+
+
+def blend_alpha_argb(argb, background_rgb):
+    L = lib()
+    p = _picture_argb(argb)
+    L.WebPBlendAlpha(C.byref(p), C.c_uint32(background_rgb))
+    out = _read_argb(p)
+    L.WebPPictureFree(C.byref(p))
+    return out

@@ -1,0 +1,221 @@
+/*
+ * oracle_tools.c -- CPU restatement of the picture pre-processing that follows the
+ * import in the encoder: WebPCleanupTransparentArea,
+ * WebPReplaceTransparentPixels, WebPBlendAlpha.
+ *
+ * TEST INFRASTRUCTURE ONLY (see oracle.c).  Pinned against the libwebp 1.6.0 binary,
+ * which exports WebPCleanupTransparentArea and WebPBlendAlpha
+ * (tests/golden/make_golden_tools.py).  File:line citations are relative to the
+ * go-webp tree.
+ */
+#include <stdint.h>
+#include <string.h>
+
+/* pkg/libwebp/enc/picture_tools_enc.c.go:29-30 */
+#define SIZE 8
+#define SIZE2 (SIZE / 2)
+
+/* picture_tools_enc.c.go:31-42 */
+static int IsTransparentARGBArea(const uint32_t* ptr, int stride, int size) {
+  for (int y = 0; y < size; ++y) {
+    for (int x = 0; x < size; ++x) {
+      if (ptr[x] & 0xff000000u) return 0;
+    }
+    ptr += stride;
+  }
+  return 1;
+}
+/* picture_tools_enc.c.go:44-50 */
+static void Flatten(uint8_t* ptr, int v, int stride, int size) {
+  for (int y = 0; y < size; ++y) {
+    memset(ptr, v, (size_t)size);
+    ptr += stride;
+  }
+}
+/* picture_tools_enc.c.go:52-58 */
+static void FlattenARGB(uint32_t* ptr, uint32_t v, int stride, int size) {
+  for (int y = 0; y < size; ++y) {
+    for (int x = 0; x < size; ++x) ptr[x] = v;
+    ptr += stride;
+  }
+}
+/* picture_tools_enc.c.go:62-91 */
+static int SmoothenBlock(const uint8_t* a_ptr, int a_stride, uint8_t* y_ptr, int y_stride, int width, int height) {
+  int sum = 0, count = 0;
+  const uint8_t* alpha_ptr = a_ptr;
+  uint8_t* luma_ptr = y_ptr;
+  for (int y = 0; y < height; ++y) {
+    for (int x = 0; x < width; ++x) {
+      if (alpha_ptr[x] != 0) {
+        ++count;
+        sum += luma_ptr[x];
+      }
+    }
+    alpha_ptr += a_stride;
+    luma_ptr += y_stride;
+  }
+  if (count > 0 && count < width * height) {
+    const uint8_t avg_u8 = (uint8_t)(sum / count);
+    alpha_ptr = a_ptr;
+    luma_ptr = y_ptr;
+    for (int y = 0; y < height; ++y) {
+      for (int x = 0; x < width; ++x) {
+        if (alpha_ptr[x] == 0) luma_ptr[x] = avg_u8;
+      }
+      alpha_ptr += a_stride;
+      luma_ptr += y_stride;
+    }
+  }
+  return (count == 0);
+}
+
+/* WebPCleanupTransparentArea, use_argb branch: picture_tools_enc.c.go:116-133.
+ * argb_stride in pixels. */
+void orc_cleanup_transparent_argb(uint32_t* argb, int argb_stride, int width, int height) {
+  const int w = width / SIZE, h = height / SIZE;
+  uint32_t argb_value = 0;
+  for (int y = 0; y < h; ++y) {
+    int need_reset = 1;
+    for (int x = 0; x < w; ++x) {
+      const int off = (y * argb_stride + x) * SIZE;
+      if (IsTransparentARGBArea(argb + off, argb_stride, SIZE)) {
+        if (need_reset) {
+          argb_value = argb[off];
+          need_reset = 0;
+        }
+        FlattenARGB(argb + off, argb_value, argb_stride, SIZE);
+      } else {
+        need_reset = 1;
+      }
+    }
+  }
+}
+
+/* WebPCleanupTransparentArea, YUVA branch: picture_tools_enc.c.go:134-183 */
+void orc_cleanup_transparent_yuva(uint8_t* y_ptr, uint8_t* u_ptr, uint8_t* v_ptr, const uint8_t* a_ptr,
+                                  int y_stride, int uv_stride, int a_stride, int width, int height) {
+  int values[3] = {0, 0, 0};
+  int x, y;
+  if (a_ptr == NULL || y_ptr == NULL || u_ptr == NULL || v_ptr == NULL) return;
+  for (y = 0; y + SIZE <= height; y += SIZE) {
+    int need_reset = 1;
+    for (x = 0; x + SIZE <= width; x += SIZE) {
+      if (SmoothenBlock(a_ptr + x, a_stride, y_ptr + x, y_stride, SIZE, SIZE)) {
+        if (need_reset) {
+          values[0] = y_ptr[x];
+          values[1] = u_ptr[x >> 1];
+          values[2] = v_ptr[x >> 1];
+          need_reset = 0;
+        }
+        Flatten(y_ptr + x, values[0], y_stride, SIZE);
+        Flatten(u_ptr + (x >> 1), values[1], uv_stride, SIZE2);
+        Flatten(v_ptr + (x >> 1), values[2], uv_stride, SIZE2);
+      } else {
+        need_reset = 1;
+      }
+    }
+    if (x < width) SmoothenBlock(a_ptr + x, a_stride, y_ptr + x, y_stride, width - x, SIZE);
+    a_ptr += SIZE * a_stride;
+    y_ptr += SIZE * y_stride;
+    u_ptr += SIZE2 * uv_stride;
+    v_ptr += SIZE2 * uv_stride;
+  }
+  if (y < height) {
+    const int sub_height = height - y;
+    for (x = 0; x + SIZE <= width; x += SIZE) {
+      SmoothenBlock(a_ptr + x, a_stride, y_ptr + x, y_stride, SIZE, sub_height);
+    }
+    if (x < width) SmoothenBlock(a_ptr + x, a_stride, y_ptr + x, y_stride, width - x, sub_height);
+  }
+}
+
+/* WebPReplaceTransparentPixels (picture_tools_enc.c.go:95-108) over WebPAlphaReplace
+ * (pkg/color/colorspace/alpha/opague.go:47-53; upstream AlphaReplace_C: a pixel whose
+ * alpha byte is 0 becomes 'color' with alpha forced to 0). */
+void orc_replace_transparent(uint32_t* argb, int argb_stride, int width, int height, uint32_t color) {
+  color &= 0xffffffu;
+  for (int y = 0; y < height; ++y) {
+    for (int x = 0; x < width; ++x) {
+      if ((argb[x] >> 24) == 0) argb[x] = color;
+    }
+    argb += argb_stride;
+  }
+}
+
+/* picture_tools_enc.c.go:191-194 */
+#define BLEND(V0, V1, ALPHA) ((((V0) * (255 - (ALPHA)) + (V1) * (ALPHA)) * 0x101 + 256) >> 16)
+#define BLEND_10BIT(V0, V1, ALPHA) ((((V0) * (1020 - (ALPHA)) + (V1) * (ALPHA)) * 0x101 + 1024) >> 18)
+
+/* pkg/color/yuv/conversion.go:51-69 */
+enum { T_YUV_FIX = 16, T_YUV_HALF = 1 << 15 };
+static int t_ClipUV(int uv, int rounding) {
+  uv = (uv + rounding + (128 << (T_YUV_FIX + 2))) >> (T_YUV_FIX + 2);
+  return ((uv & ~0xff) == 0) ? uv : (uv < 0) ? 0 : 255;
+}
+static int t_RGBToY(int r, int g, int b, int rounding) {
+  return (16839 * r + 33059 * g + 6420 * b + rounding + (16 << T_YUV_FIX)) >> T_YUV_FIX;
+}
+static int t_RGBToU(int r, int g, int b, int rounding) { return t_ClipUV(-9719 * r - 19081 * g + 28800 * b, rounding); }
+static int t_RGBToV(int r, int g, int b, int rounding) { return t_ClipUV(28800 * r - 24116 * g - 4684 * b, rounding); }
+
+/* WebPBlendAlpha, YUVA branch: picture_tools_enc.c.go:208-252.  The caller checks
+ * has_alpha / a != NULL (:218-219). */
+void orc_blend_alpha_yuva(uint8_t* y_ptr, uint8_t* u_ptr, uint8_t* v_ptr, uint8_t* a_ptr, int y_stride, int uv_stride,
+                          int a_stride, int width, int height, uint32_t background_rgb) {
+  const int red = (background_rgb >> 16) & 0xff, green = (background_rgb >> 8) & 0xff, blue = background_rgb & 0xff;
+  const int uv_width = width >> 1;   /* omit last pixel during u/v loop */
+  const int Y0 = t_RGBToY(red, green, blue, T_YUV_HALF);
+  /* VP8RGBToU/V expects the u/v values summed over four pixels */
+  const int U0 = t_RGBToU(4 * red, 4 * green, 4 * blue, 4 * T_YUV_HALF);
+  const int V0 = t_RGBToV(4 * red, 4 * green, 4 * blue, 4 * T_YUV_HALF);
+  int x, y;
+  if (a_ptr == NULL) return;
+  for (y = 0; y < height; ++y) {
+    for (x = 0; x < width; ++x) {
+      const uint8_t alpha = a_ptr[x];
+      if (alpha < 0xff) y_ptr[x] = (uint8_t)BLEND(Y0, y_ptr[x], alpha);
+    }
+    if ((y & 1) == 0) {
+      const uint8_t* const a_ptr2 = (y + 1 == height) ? a_ptr : a_ptr + a_stride;
+      for (x = 0; x < uv_width; ++x) {
+        const uint32_t alpha = a_ptr[2 * x + 0] + a_ptr[2 * x + 1] + a_ptr2[2 * x + 0] + a_ptr2[2 * x + 1];
+        u_ptr[x] = (uint8_t)BLEND_10BIT(U0, u_ptr[x], alpha);
+        v_ptr[x] = (uint8_t)BLEND_10BIT(V0, v_ptr[x], alpha);
+      }
+      if (width & 1) {   /* rightmost pixel */
+        const uint32_t alpha = 2 * (a_ptr[2 * x + 0] + a_ptr2[2 * x + 0]);
+        u_ptr[x] = (uint8_t)BLEND_10BIT(U0, u_ptr[x], alpha);
+        v_ptr[x] = (uint8_t)BLEND_10BIT(V0, v_ptr[x], alpha);
+      }
+    } else {
+      u_ptr += uv_stride;
+      v_ptr += uv_stride;
+    }
+    memset(a_ptr, 0xff, (size_t)width);   /* reset alpha value to opaque */
+    a_ptr += a_stride;
+    y_ptr += y_stride;
+  }
+}
+
+/* WebPBlendAlpha, ARGB branch: picture_tools_enc.c.go:253-276 */
+void orc_blend_alpha_argb(uint32_t* argb, int argb_stride, int width, int height, uint32_t background_rgb) {
+  const int red = (background_rgb >> 16) & 0xff, green = (background_rgb >> 8) & 0xff, blue = background_rgb & 0xff;
+  const uint32_t background = 0xff000000u | ((uint32_t)red << 16) | ((uint32_t)green << 8) | (uint32_t)blue;
+  for (int y = 0; y < height; ++y) {
+    for (int x = 0; x < width; ++x) {
+      const int alpha = (argb[x] >> 24) & 0xff;
+      if (alpha != 0xff) {
+        if (alpha > 0) {
+          int r = (argb[x] >> 16) & 0xff, g = (argb[x] >> 8) & 0xff, b = argb[x] & 0xff;
+          r = BLEND(red, r, alpha);
+          g = BLEND(green, g, alpha);
+          b = BLEND(blue, b, alpha);
+          argb[x] = 0xff000000u | ((uint32_t)r << 16) | ((uint32_t)g << 8) | (uint32_t)b;
+        } else {
+          argb[x] = background;
+        }
+      }
+    }
+    argb += argb_stride;
+  }
+}

@@ -1,0 +1,86 @@
+"""Generate tests/golden/tools_libwebp160.npz: WebPCleanupTransparentArea and
+WebPBlendAlpha (both exported by the libwebp 1.6.0 binary) on YUVA and ARGB pictures.
+
+    python tests/golden/make_golden_tools.py
+
+Pins oracle/oracle_tools.c (pkg/libwebp/enc/picture_tools_enc.c.go:
+110-183, 199-276).  Transparent regions are laid out in 8x8-aligned patches, runs of
+patches, partial blocks and ragged right/bottom edges so that the need_reset carry, the
+SmoothenBlock averages and the left-over handling are all exercised.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+import oracle  # noqa: E402
+from oracle import libwebp_ref as ref  # noqa: E402
+
+SIZES = [(8, 8), (16, 8), (9, 9), (24, 17), (33, 40), (64, 48), (71, 29), (7, 5), (100, 20)]
+
+
+def alpha_plane(rng, w, h, kind):
+    a = rng.integers(1, 256, (h, w), dtype=np.uint8)
+    if kind == "opaque":
+        a[:] = 255
+    elif kind == "blocks":      # whole 8x8 blocks transparent, in runs
+        bw, bh = (w + 7) // 8, (h + 7) // 8
+        m = rng.random((bh, bw)) < 0.55
+        a[np.kron(m, np.ones((8, 8), bool))[:h, :w]] = 0
+    elif kind == "speckle":     # partially transparent blocks
+        a[rng.random((h, w)) < 0.4] = 0
+    elif kind == "mixed":
+        bw, bh = (w + 7) // 8, (h + 7) // 8
+        m = rng.random((bh, bw)) < 0.4
+        a[np.kron(m, np.ones((8, 8), bool))[:h, :w]] = 0
+        a[rng.random((h, w)) < 0.15] = 0
+        a[rng.random((h, w)) < 0.3] = 255
+    elif kind == "transp":
+        a[:] = 0
+    return a
+
+
+def main():
+    rng = np.random.default_rng(0xB2004)
+    store, names = {}, []
+    n = 0
+    for (w, h) in SIZES:
+        for kind in ("opaque", "blocks", "speckle", "mixed", "transp"):
+            uvw, uvh = (w + 1) >> 1, (h + 1) >> 1
+            y = rng.integers(0, 256, (h, w), dtype=np.uint8)
+            u = rng.integers(0, 256, (uvh, uvw), dtype=np.uint8)
+            v = rng.integers(0, 256, (uvh, uvw), dtype=np.uint8)
+            a = alpha_plane(rng, w, h, kind)
+            argb = (rng.integers(0, 1 << 24, (h, w), dtype=np.uint32)) | (a.astype(np.uint32) << 24)
+            bg = int(rng.integers(0, 1 << 24))
+            k = f"c{n}"
+            names.append(k)
+            n += 1
+            store[f"{k}/y"], store[f"{k}/u"], store[f"{k}/v"], store[f"{k}/a"], store[f"{k}/argb"] = y, u, v, a, argb
+            store[f"{k}/bg"] = np.uint32(bg)
+            cy, cu, cv = ref.cleanup_transparent_yuva(y, u, v, a)
+            oy, ou, ov = oracle.cleanup_transparent_yuva(y, u, v, a)
+            assert (cy == oy).all() and (cu == ou).all() and (cv == ov).all(), (k, "cleanup yuva")
+            store[f"{k}/clean_y"], store[f"{k}/clean_u"], store[f"{k}/clean_v"] = cy, cu, cv
+            ca = ref.cleanup_transparent_argb(argb)
+            assert (ca == oracle.cleanup_transparent_argb(argb)).all(), (k, "cleanup argb")
+            store[f"{k}/clean_argb"] = ca
+            by, bu, bv, ba = ref.blend_alpha_yuva(y, u, v, a, bg)
+            qy, qu, qv, qa = oracle.blend_alpha_yuva(y, u, v, a, bg)
+            assert (by == qy).all() and (bu == qu).all() and (bv == qv).all() and (ba == qa).all(), (k, "blend yuva")
+            store[f"{k}/blend_y"], store[f"{k}/blend_u"], store[f"{k}/blend_v"], store[f"{k}/blend_a"] = by, bu, bv, ba
+            bb = ref.blend_alpha_argb(argb, bg)
+            assert (bb == oracle.blend_alpha_argb(argb, bg)).all(), (k, "blend argb")
+            store[f"{k}/blend_argb"] = bb
+    store["names"] = np.array(names)
+    np.savez_compressed(os.path.join(HERE, "tools_libwebp160.npz"), **store)
+    print(f"{n} cases: oracle == libwebp binary for cleanup (YUVA, ARGB) and blend (YUVA, ARGB)")
+
+
+if __name__ == "__main__":
+    main()

@@ -667,3 +667,82 @@ def test_vp8l_golden_libwebp_streams(gpu, golden_dir):
     outs = dsp.VP8LInverseTransformBatch(imgs, chains)
     for name, o, e in zip(names, outs, exps):
         assert o.shape == e.shape and (o == e).all(), name
+
+
+# ---- picture pre-processing ----------------------------------------------
+def _yuva_pic(P, c):
+    h, w = c["y"].shape
+    return P.Picture(Width=w, Height=h, ColorSpace=P.WEBP_YUV420A, Y=c["y"].copy(), U=c["u"].copy(), V=c["v"].copy(),
+                     A=c["a"].copy(), YStride=w, UVStride=(w + 1) >> 1, AStride=w)
+
+
+def _argb_pic(P, argb):
+    h, w = argb.shape
+    return P.Picture(Width=w, Height=h, UseARGB=True, ARGB=argb.copy(), ARGBStride=w)
+
+
+def test_picture_tools_golden_libwebp(gpu, golden_dir):
+    """WebPCleanupTransparentArea / WebPBlendAlpha through the batched entry points on the
+    vectors the libwebp 1.6.0 binary produced (YUVA and ARGB pictures in one batch)."""
+    from test_oracle_golden import tools_vectors
+    from go_webp_b200 import picture_tools as T
+    P = gpu["picture"]
+    cases = [c for _, c in tools_vectors(golden_dir)]
+    pics = [_yuva_pic(P, c) for c in cases] + [_argb_pic(P, c["argb"]) for c in cases]
+    T.WebPCleanupTransparentAreaBatch(pics)
+    for c, py, pa in zip(cases, pics[:len(cases)], pics[len(cases):]):
+        assert (py.Y == c["clean_y"]).all() and (py.U == c["clean_u"]).all() and (py.V == c["clean_v"]).all()
+        assert (py.A == c["a"]).all()
+        assert (pa.ARGB == c["clean_argb"]).all()
+    for c in cases:   # one background colour per call
+        py, pa = _yuva_pic(P, c), _argb_pic(P, c["argb"])
+        T.WebPBlendAlphaBatch([py, pa], int(c["bg"]))
+        assert (py.Y == c["blend_y"]).all() and (py.U == c["blend_u"]).all() and (py.V == c["blend_v"]).all()
+        assert (py.A == 255).all() and (pa.ARGB == c["blend_argb"]).all()
+
+
+@pytest.mark.parametrize("size", [(8, 8), (7, 7), (40, 9), (264, 16), (263, 23), (1000, 33), (2056, 64), (521, 130)])
+def test_picture_tools_vs_oracle(gpu, size):
+    """Same functions on seeded pictures against the oracle: long runs of transparent
+    blocks across the 32-block chunks of a warp, ragged right / bottom edges, all-
+    transparent and opaque pictures; WebPReplaceTransparentPixels."""
+    from go_webp_b200 import picture_tools as T
+    P = gpu["picture"]
+    w, h = size
+    rng = np.random.default_rng(w * 131 + h)
+    for kind in ("runs", "speckle", "transp", "opaque"):
+        a = rng.integers(1, 256, (h, w), dtype=np.uint8)
+        if kind == "runs":
+            bw, bh = (w + 7) // 8, (h + 7) // 8
+            m = rng.random((bh, bw)) < 0.8
+            a[np.kron(m, np.ones((8, 8), bool))[:h, :w]] = 0
+        elif kind == "speckle":
+            a[rng.random((h, w)) < 0.5] = 0
+        elif kind == "transp":
+            a[:] = 0
+        else:
+            a[:] = 255
+        c = dict(y=rng.integers(0, 256, (h, w), dtype=np.uint8), u=rng.integers(0, 256, ((h + 1) // 2, (w + 1) // 2), dtype=np.uint8),
+                 v=rng.integers(0, 256, ((h + 1) // 2, (w + 1) // 2), dtype=np.uint8), a=a)
+        argb = rng.integers(0, 1 << 24, (h, w), dtype=np.uint32) | (a.astype(np.uint32) << 24)
+        bg = int(rng.integers(0, 1 << 24))
+        py, pa = _yuva_pic(P, c), _argb_pic(P, argb)
+        T.WebPCleanupTransparentAreaBatch([py, pa])
+        ey, eu, ev = oracle.cleanup_transparent_yuva(c["y"], c["u"], c["v"], a)
+        assert (py.Y == ey).all() and (py.U == eu).all() and (py.V == ev).all(), kind
+        assert (pa.ARGB == oracle.cleanup_transparent_argb(argb)).all(), kind
+        py, pa = _yuva_pic(P, c), _argb_pic(P, argb)
+        T.WebPBlendAlpha(py, bg)
+        T.WebPBlendAlpha(pa, bg)
+        ey, eu, ev, ea = oracle.blend_alpha_yuva(c["y"], c["u"], c["v"], a, bg)
+        assert (py.Y == ey).all() and (py.U == eu).all() and (py.V == ev).all() and (py.A == ea).all(), kind
+        assert (pa.ARGB == oracle.blend_alpha_argb(argb, bg)).all(), kind
+        pa = _argb_pic(P, argb)
+        T.WebPReplaceTransparentPixels(pa, 0xff000000 | bg)
+        assert (pa.ARGB == oracle.replace_transparent(argb, bg)).all(), kind
+    # reference "nothing to do" rules: YUV picture without alpha, non-ARGB picture for replace
+    p = P.Picture(Width=w, Height=h, ColorSpace=P.WEBP_YUV420, Y=c["y"].copy(), U=c["u"].copy(), V=c["v"].copy())
+    T.WebPBlendAlpha(p, 0x123456)
+    T.WebPCleanupTransparentArea(p)
+    T.WebPReplaceTransparentPixels(p, 0)
+    assert (p.Y == c["y"]).all() and p.A is None

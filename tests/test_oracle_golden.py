@@ -187,3 +187,36 @@ def test_vp8l_forward_inverts_on_libwebp_vectors(golden_dir):
             else:
                 nxt = oracle.color_index_inverse(cur, oracle.expand_color_map(data, b), b, w)
             stages.append(nxt)
+
+
+# ---- picture pre-processing vs the libwebp binary ------------------------
+def tools_vectors(golden_dir):
+    g = _load(golden_dir, "tools_libwebp160.npz")
+    for k in g["names"]:
+        k = str(k)
+        yield k, {n: g[f"{k}/{n}"] for n in ("y", "u", "v", "a", "argb", "bg", "clean_y", "clean_u", "clean_v", "clean_argb",
+                                             "blend_y", "blend_u", "blend_v", "blend_a", "blend_argb")}
+
+
+def test_picture_tools_match_libwebp_binary(golden_dir):
+    """WebPCleanupTransparentArea and WebPBlendAlpha (exported by the binary), YUVA and
+    ARGB forms: pkg/libwebp/enc/picture_tools_enc.c.go:110-183, 199-276."""
+    n = 0
+    for k, c in tools_vectors(golden_dir):
+        cy, cu, cv = oracle.cleanup_transparent_yuva(c["y"], c["u"], c["v"], c["a"])
+        assert (cy == c["clean_y"]).all() and (cu == c["clean_u"]).all() and (cv == c["clean_v"]).all(), k
+        assert (oracle.cleanup_transparent_argb(c["argb"]) == c["clean_argb"]).all(), k
+        by, bu, bv, ba = oracle.blend_alpha_yuva(c["y"], c["u"], c["v"], c["a"], int(c["bg"]))
+        assert (by == c["blend_y"]).all() and (bu == c["blend_u"]).all() and (bv == c["blend_v"]).all(), k
+        assert (ba == 255).all() and (ba == c["blend_a"]).all(), k
+        assert (oracle.blend_alpha_argb(c["argb"], int(c["bg"])) == c["blend_argb"]).all(), k
+        n += 1
+    assert n >= 40
+
+
+def test_replace_transparent_pixels_oracle():
+    """WebPReplaceTransparentPixels (picture_tools_enc.c.go:95-108) is not exported by the
+    binary: known-answer check of the one-line rule."""
+    argb = np.array([[0x00123456, 0x01123456, 0xff000000, 0x00ffffff]], np.uint32)
+    out = oracle.replace_transparent(argb, 0xffabcdef)
+    assert out.tolist() == [[0x00abcdef, 0x01123456, 0xff000000, 0x00abcdef]]

@@ -71,3 +71,29 @@ if "vp8l" in which:
         ms = timed(p.run_device, 5 if "predictor" in op else 20)
         report(f"vp8l {op} bits={bits} {nf}x{aw}x{ah} ({ms * 1e3:.0f} us)", nf * aw * ah, bpp, ms)
         p.close()
+if "tools" in which:
+    # picture pre-processing on the planes an import just wrote (binary alpha: every 8x8 block is
+    # partially transparent, the SmoothenBlock stress case: read A + Y, rewrite Y = 3 B/px; blend:
+    # read A, Y, U, V, write all four = 5 B/px)
+    import ctypes as C
+    p = ImportPipeline(ctx, NF, 1920, 1080, host=False)
+    p.fill_synthetic(0xB2000001, 0, 3)
+    p.run_device()
+    ctx.sync()
+    jobs = (_abi.PictureJob * NF)(*[_abi.PictureJob(j.y, j.u, j.v, j.a, None, j.y_stride, j.uv_stride, j.a_stride, 0, j.width, j.height)
+                                     for j in p.jobs])
+    report(f"cleanup transparent {NF}x1080p YUVA (binary alpha)", NF * 1920 * 1080, 3.0,
+           timed(lambda: ctx._chk(ctx.lib.b2_picture_cleanup_transparent(ctx.h, 0, jobs, NF, 0))))
+    report(f"blend alpha {NF}x1080p YUVA", NF * 1920 * 1080, 5.0,
+           timed(lambda: ctx._chk(ctx.lib.b2_picture_blend_alpha(ctx.h, 0, jobs, NF, 0, 0x336699))))
+    p.close()
+    a = ArgbPipeline(ctx, 8, 4096, 4096, "add_green", 0)
+    a.fill_synthetic(0xB2000003)
+    aj = (_abi.PictureJob * 8)(*[_abi.PictureJob(None, None, None, None, j.src, 0, 0, 0, 4096, 4096, 4096) for j in a.jobs])
+    report("cleanup transparent 8x4096^2 ARGB (random alpha: read only)", 8 * 4096 * 4096, 4.0,
+           timed(lambda: ctx._chk(ctx.lib.b2_picture_cleanup_transparent(ctx.h, 0, aj, 8, 1))))
+    report("blend alpha 8x4096^2 ARGB", 8 * 4096 * 4096, 8.0,
+           timed(lambda: ctx._chk(ctx.lib.b2_picture_blend_alpha(ctx.h, 0, aj, 8, 1, 0x336699))))
+    report("replace transparent 8x4096^2 ARGB", 8 * 4096 * 4096, 8.0,
+           timed(lambda: ctx._chk(ctx.lib.b2_picture_replace_transparent(ctx.h, 0, aj, 8, 0x112233))))
+    a.close()

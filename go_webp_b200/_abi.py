@@ -118,6 +118,7 @@ SYMBOLS = {
     "b2_alpha_multiply": (C.c_int, [_ctx, C.c_int, C.POINTER(ConvertJob), C.c_int, C.c_int, C.c_int]),
     "b2_yuv_to_rgb_point": (C.c_int, [_ctx, C.c_int, C.POINTER(ConvertJob), C.c_int, C.c_int, C.c_int]),
     "b2_argb_to_yuva_plain": (C.c_int, [_ctx, C.c_int, C.POINTER(PlainJob), C.c_int]),
+    "b2_import_to_argb": (C.c_int, [_ctx, C.c_int, C.POINTER(ConvertJob), C.c_int, C.c_int, C.c_int]),
     "b2_picture_cleanup_transparent": (C.c_int, [_ctx, C.c_int, C.POINTER(PictureJob), C.c_int, C.c_int]),
     "b2_picture_blend_alpha": (C.c_int, [_ctx, C.c_int, C.POINTER(PictureJob), C.c_int, C.c_int, C.c_uint32]),
     "b2_picture_replace_transparent": (C.c_int, [_ctx, C.c_int, C.POINTER(PictureJob), C.c_int, C.c_uint32]),

@@ -138,6 +138,48 @@ convert_from_bgra_kernel(const ConvJobDev* __restrict__ jobs, const uint32_t* __
   }
 }
 
+// ---- Import() into an ARGB picture (picture_csp_enc.c.go:138-181) -----------------------
+// WebPPackRGB (step 3 or 4, alpha forced to 0xff), the memcpy of BGRA input and
+// VP8LConvertBGRAToRGBA of RGBA input all give out = A << 24 | R << 16 | G << 8 | B.
+// src_stride is in BYTES here (the caller's rgb_stride, possibly negative).
+__global__ void __launch_bounds__(kThreads, 8)
+import_argb_kernel(const ConvJobDev* __restrict__ jobs, const uint32_t* __restrict__ prefix, uint32_t n_jobs,
+                   uint32_t uniform, uint32_t total_items, int order, int import_alpha) {
+  const int step = (order == B2_ORDER_RGB || order == B2_ORDER_BGR) ? 3 : 4;
+  const bool swap_rb = (order == B2_ORDER_BGRA || order == B2_ORDER_BGR);   // b,g,r(,a) in memory
+  B2_CONV_ITEM_PROLOGUE
+    const uint8_t* s = (const uint8_t*)j.src + (ptrdiff_t)y * j.src_stride + (ptrdiff_t)x0 * step;
+    uint32_t* d = (uint32_t*)(j.dst + (ptrdiff_t)y * j.dst_stride) + x0;
+    uint32_t o[4];
+    if (step == 4 && nv == 4 && (((uintptr_t)s) & 15) == 0) {
+      const uint4 q = b2_ldg_stream_v4(s);
+      const uint32_t p[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t v = swap_rb ? p[k] : __byte_perm(p[k], 0, 0x3012);   // R,G,B,A bytes -> B,G,R,A
+        o[k] = import_alpha ? v : (v | 0xff000000u);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        o[k] = 0u;
+        if (k < nv) {
+          const uint8_t* q = s + k * step;
+          const uint32_t c0 = q[0], c1 = q[1], c2 = q[2];
+          const uint32_t a = (step == 4 && import_alpha) ? q[3] : 0xffu;
+          o[k] = (a << 24) | ((swap_rb ? c2 : c0) << 16) | (c1 << 8) | (swap_rb ? c0 : c2);
+        }
+      }
+    }
+    if (nv == 4 && (((uintptr_t)d) & 15) == 0) {
+      b2_stg_stream_v4(d, make_uint4(o[0], o[1], o[2], o[3]));
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) if (k < nv) d[k] = o[k];
+    }
+  }
+}
+
 // ---- alpha multiplies (in place) ----------------------------------------------------
 enum { AM_APPLY = 0, AM_APPLY_4444 = 1, AM_MULT_ARGB = 2, AM_MULT_ROW = 3 };
 #define MFIX 24
@@ -312,6 +354,27 @@ extern "C" int b2_yuv_to_rgb_point(b2_ctx* ctx, int stream, const b2_convert_job
   const int grid = b2_grid_for(ctx, 8, (tot + kWarps - 1) / kWarps);
   if (yuv444) yuv_point_kernel<true><<<grid, kThreads, 0, ctx->streams[stream]>>>(dj, dp, (uint32_t)n_jobs, uni, tot, st);
   else yuv_point_kernel<false><<<grid, kThreads, 0, ctx->streams[stream]>>>(dj, dp, (uint32_t)n_jobs, uni, tot, st);
+  ctx->launches++;
+  B2_CUDA(ctx, cudaGetLastError());
+  return B2_OK;
+}
+
+extern "C" int b2_import_to_argb(b2_ctx* ctx, int stream, const b2_convert_job* jobs, int n_jobs, int order, int import_alpha) {
+  B2_CONV_ENTRY_CHECKS
+  if (order < B2_ORDER_RGBA || order > B2_ORDER_BGR) return B2_ERR_INVALID_CONFIG;
+  const int step = (order == B2_ORDER_RGB || order == B2_ORDER_BGR) ? 3 : 4;
+  if (import_alpha && step != 4) return B2_ERR_INVALID_CONFIG;   // assert(step == 4), picture_csp_enc.c.go:146
+  for (int i = 0; i < n_jobs; ++i) {
+    if (jobs[i].src == NULL) return B2_ERR_NULL;
+    const int64_t st = jobs[i].src_stride < 0 ? -(int64_t)jobs[i].src_stride : jobs[i].src_stride;
+    if (jobs[i].width > 0 && st < (int64_t)(import_alpha ? 4 : 3) * jobs[i].width) return B2_ERR_BAD_DIM;   // :132
+    if (jobs[i].width > 0 && st < (int64_t)step * jobs[i].width) return B2_ERR_BAD_DIM;
+  }
+  const ConvJobDev* dj; const uint32_t* dp; uint32_t uni, tot;
+  const int rc = prepare_conv(ctx, stream, jobs, n_jobs, false, 4, &dj, &dp, &uni, &tot);
+  if (rc != B2_OK) return rc;
+  import_argb_kernel<<<b2_grid_for(ctx, 8, (tot + kWarps - 1) / kWarps), kThreads, 0, ctx->streams[stream]>>>(
+      dj, dp, (uint32_t)n_jobs, uni, tot, order, import_alpha ? 1 : 0);
   ctx->launches++;
   B2_CUDA(ctx, cudaGetLastError());
   return B2_OK;

@@ -499,3 +499,15 @@ func (c *Context) ReplaceTransparentPixels(stream int, jobs []PictureJob, color 
 	cj := pictureJobs(jobs)
 	return status(c, C.b2_picture_replace_transparent(c.h, C.int(stream), &cj[0], C.int(len(cj)), C.uint32_t(color)))
 }
+
+// ImportToARGB replaces the use_argb branch of Import()
+// (pkg/libwebp/enc/picture_csp_enc.c.go:138-181): WebPPackRGB, the BGRA row copy and
+// VP8LConvertBGRAToRGBA.  SrcStride is the caller's rgb_stride in bytes (may be negative),
+// DstStride = 4 * Picture.ARGBStride.
+func (c *Context) ImportToARGB(stream int, jobs []ConvertJob, order int, importAlpha bool) error {
+	if len(jobs) == 0 {
+		return nil
+	}
+	cj := convertJobs(jobs)
+	return status(c, C.b2_import_to_argb(c.h, C.int(stream), &cj[0], C.int(len(cj)), C.int(order), boolInt(importAlpha)))
+}

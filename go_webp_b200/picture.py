@@ -152,6 +152,41 @@ _ORDERS = {  # name -> (b2 order, step, import_alpha)   picture_csp_enc.c.go:189
 }
 
 
+def _import_argb_batch(pics, srcs, strides, b2order, step, import_alpha, ctx) -> int:
+    """Import() into ARGB pictures: WebPPictureAlloc + WebPPackRGB / row copy /
+    VP8LConvertBGRAToRGBA (picture_csp_enc.c.go:138-181) as one b2_import_to_argb launch."""
+    lib, hnd = ctx.lib, ctx.h
+    metas, need = [], 0
+    for pic, stride in zip(pics, strides):
+        w, h = pic.Width, pic.Height
+        ds = _al(4 * w, 16)
+        sz = dict(src=_al(abs(stride) * h), dst=_al(ds * h))
+        metas.append((w, h, ds, sz))
+        need += sum(sz.values())
+    ar = _arena(ctx)
+    ar.reset(need)
+    jobs, dptr = [], []
+    try:
+        for (w, h, ds, sz), stride, src in zip(metas, strides, srcs):
+            p = {k: ar.take(v) for k, v in sz.items()}
+            dptr.append(p)
+            flat = np.ascontiguousarray(src).reshape(-1)
+            ctx._chk(lib.b2_h2d_async(hnd, 0, p["src"], flat.ctypes.data, abs(stride) * (h - 1) + step * w))
+            src0 = p["src"] + (abs(stride) * (h - 1) if stride < 0 else 0)
+            jobs.append(_abi.ConvertJob(src0, None, None, p["dst"], stride, 0, ds, w, h, 0))
+        arr = (_abi.ConvertJob * len(jobs))(*jobs)
+        ctx._chk(lib.b2_import_to_argb(hnd, 0, arr, len(jobs), b2order, int(import_alpha)))
+        for pic, (w, h, ds, sz), p in zip(pics, metas, dptr):
+            WebPPictureAllocARGB(pic)
+            ctx._chk(lib.b2_d2h_2d_async(hnd, 0, pic.ARGB.ctypes.data, 4 * w, p["dst"], ds, 4 * w, h))
+        ctx.sync()
+    except B2Error as e:
+        for pic in pics:
+            pic.SetEncodingError(_STATUS_TO_ENC.get(e.status, ENC_ERROR_OUT_OF_MEMORY))
+        return 0
+    return 1
+
+
 def ImportRGBABatch(pics, srcs, strides, order: str = "RGBA", ctx: Context | None = None,
                     divide_table: bool = False, chunk: int = 16) -> int:
     """Added batched entry point (one per part): imports srcs[i]
@@ -176,8 +211,16 @@ def ImportRGBABatch(pics, srcs, strides, order: str = "RGBA", ctx: Context | Non
             return pic.SetEncodingError(err)
         if abs(stride) < (4 if import_alpha else 3) * pic.Width or abs(stride) < step * pic.Width:
             return 0  # picture_csp_enc.c.go:132
-        if pic.UseARGB:
-            raise NotImplementedError("use_argb import (WebPPackRGB path) is 8f-3, not on the hot path")
+    argb_idx = [i for i, pic in enumerate(pics) if pic.UseARGB]
+    if argb_idx:  # use_argb branch of Import() (picture_csp_enc.c.go:138-181)
+        if not _import_argb_batch([pics[i] for i in argb_idx], [srcs[i] for i in argb_idx],
+                                  [strides[i] for i in argb_idx], b2order, step, import_alpha, ctx):
+            return 0
+        rest = [i for i in range(n) if not pics[i].UseARGB]
+        if not rest:
+            return 1
+        return ImportRGBABatch([pics[i] for i in rest], [srcs[i] for i in rest], [strides[i] for i in rest],
+                               order, ctx, divide_table, chunk)
     # device layout per image: src rows (caller stride kept), then Y | U | V | A
     metas = []
     need = 0

@@ -290,6 +290,14 @@ typedef struct b2_expand_job {
 } b2_expand_job;
 int b2_vp8l_expand_color_map(b2_ctx* ctx, int stream, const b2_expand_job* jobs, int n_jobs);
 
+/* Import() into an ARGB picture, the use_argb branch of WebPPictureImportRGB/RGBA/RGBX/
+ * BGR/BGRA/BGRX (pkg/libwebp/enc/picture_csp_enc.c.go:138-181,189-225): WebPPackRGB /
+ * PackRGB_C (pkg/libwebp/dsp/alpha_processing.go:227-233) for the orders without alpha,
+ * the row copy of BGRA and VP8LConvertBGRAToRGBA of RGBA with it.  src = interleaved
+ * bytes, src_stride in BYTES (signed), dst = uint32 0xAARRGGBB rows, dst_stride in bytes
+ * (4 * Picture.ARGBStride).  import_alpha needs a 4-byte order. */
+int b2_import_to_argb(b2_ctx* ctx, int stream, const b2_convert_job* jobs, int n_jobs, int order, int import_alpha);
+
 /* ---- next rows: picture pre-processing after the import ---------
  * In-place operations on a picture the library holds on the device.  YUVA form: y, u, v,
  * a planes with byte strides (pkg/picture/picture.go:33-105 Y/U/V/A + strides); ARGB

@@ -353,3 +353,19 @@ def blend_alpha_argb(argb, background_rgb):
     h, w = argb.shape
     lib().orc_blend_alpha_argb(_p(argb), w, w, h, C.c_uint32(background_rgb))
     return argb
+
+
+_ARGB_ORDERS = {"RGBA": (4, 0, 1), "RGBX": (4, 0, 0), "BGRA": (4, 1, 1), "BGRX": (4, 1, 0), "RGB": (3, 0, 0), "BGR": (3, 1, 0)}
+
+
+def import_to_argb(src, width, height, order="RGBA", stride=None):
+    """Import() with use_argb = 1 -> uint32 (h, w) 0xAARRGGBB."""
+    step, swap_rb, import_alpha = _ARGB_ORDERS[order]
+    src = np.ascontiguousarray(src, np.uint8).reshape(-1)
+    if stride is None:
+        stride = step * width
+    dst = np.empty((height, width), np.uint32)
+    base = src.ctypes.data + (abs(stride) * (height - 1) if stride < 0 else 0)
+    ok = lib().orc_import_to_argb(C.c_void_p(base), stride, step, swap_rb, import_alpha, width, height, _p(dst), width)
+    assert ok
+    return dst

@@ -211,3 +211,20 @@ def blend_alpha_argb(argb, background_rgb):
     out = _read_argb(p)
     L.WebPPictureFree(C.byref(p))
     return out
+
+
+def import_to_argb(src: np.ndarray, width: int, height: int, order="RGBA", stride=None):
+    """WebPPictureImport* with use_argb = 1 -> uint32 (h, w) 0xAARRGGBB from the binary."""
+    L = lib()
+    fn, step = _IMPORTERS[order]
+    src = np.ascontiguousarray(src, np.uint8).reshape(-1)
+    if stride is None:
+        stride = step * width
+    p = WebPPicture()
+    assert L.WebPPictureInitInternal(C.byref(p), 0x0210)
+    p.width, p.height, p.use_argb = width, height, 1
+    if not getattr(L, fn)(C.byref(p), src.ctypes.data_as(C.c_void_p), stride):
+        raise ValueError("libwebp import failed")
+    out = _read_argb(p)
+    L.WebPPictureFree(C.byref(p))
+    return out

@@ -219,3 +219,33 @@ void orc_blend_alpha_argb(uint32_t* argb, int argb_stride, int width, int height
     argb += argb_stride;
   }
 }
+
+/* Import() into an ARGB picture: pkg/libwebp/enc/picture_csp_enc.c.go:138-181.
+ * import_alpha: BGRA rows are copied (:149-154), RGBA rows go through
+ * VP8LConvertBGRAToRGBA (:165-166, pkg/libwebp/dsp/lossless.go:549-560: swaps bytes 0 and
+ * 2); otherwise WebPPackRGB / PackRGB_C (pkg/libwebp/dsp/alpha_processing.go:227-233).
+ * Every branch yields A << 24 | R << 16 | G << 8 | B with A = 0xff when not imported. */
+int orc_import_to_argb(const uint8_t* rgb, int rgb_stride, int step, int swap_rb, int import_alpha, int width, int height,
+                       uint32_t* dst, int dst_stride) {
+  const int a_stride = rgb_stride < 0 ? -rgb_stride : rgb_stride;
+  if (a_stride < (import_alpha ? 4 : 3) * width) return 0;   /* :132 */
+  for (int y = 0; y < height; ++y) {
+    const uint8_t* r_ptr = rgb + (swap_rb ? 2 : 0);
+    const uint8_t* g_ptr = rgb + 1;
+    const uint8_t* b_ptr = rgb + (swap_rb ? 0 : 2);
+    if (import_alpha) {
+      for (int i = 0; i < width; ++i) {
+        dst[i] = ((uint32_t)rgb[4 * i + 3] << 24) | ((uint32_t)r_ptr[4 * i] << 16) | ((uint32_t)g_ptr[4 * i] << 8) | b_ptr[4 * i];
+      }
+    } else {
+      int offset = 0;
+      for (int i = 0; i < width; ++i) {
+        dst[i] = 0xff000000u | ((uint32_t)r_ptr[offset] << 16) | ((uint32_t)g_ptr[offset] << 8) | b_ptr[offset];
+        offset += step;
+      }
+    }
+    rgb += rgb_stride;
+    dst += dst_stride;
+  }
+  return 1;
+}

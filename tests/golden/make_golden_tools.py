@@ -1,5 +1,6 @@
 """Generate tests/golden/tools_libwebp160.npz: WebPCleanupTransparentArea and
-WebPBlendAlpha (both exported by the libwebp 1.6.0 binary) on YUVA and ARGB pictures.
+WebPBlendAlpha (both exported by the libwebp 1.6.0 binary) on YUVA and ARGB pictures,
+and tests/golden/import_argb_libwebp160.npz: the use_argb branch of WebPPictureImport*.
 
     python tests/golden/make_golden_tools.py
 
@@ -82,5 +83,27 @@ def main():
     print(f"{n} cases: oracle == libwebp binary for cleanup (YUVA, ARGB) and blend (YUVA, ARGB)")
 
 
+def gen_import_argb():
+    """import_argb_libwebp160.npz: WebPPictureImport{RGBA,RGBX,BGRA,BGRX,RGB,BGR} with
+    use_argb = 1 (Import(), pkg/libwebp/enc/picture_csp_enc.c.go:138-181)."""
+    rng = np.random.default_rng(5)
+    store, names = {}, []
+    n = 0
+    for (w, h) in [(1, 1), (2, 3), (5, 7), (16, 9), (33, 16), (64, 20), (127, 5)]:
+        for order in ("RGBA", "RGBX", "BGRA", "BGRX", "RGB", "BGR"):
+            step = 3 if order in ("RGB", "BGR") else 4
+            src = rng.integers(0, 256, (h, w * step), dtype=np.uint8)
+            e = ref.import_to_argb(src, w, h, order)
+            assert (e == oracle.import_to_argb(src, w, h, order)).all(), (w, h, order)
+            k = f"c{n}"
+            n += 1
+            names.append(k)
+            store[f"{k}/src"], store[f"{k}/argb"], store[f"{k}/order"] = src, e, np.array(order)
+    store["names"] = np.array(names)
+    np.savez_compressed(os.path.join(HERE, "import_argb_libwebp160.npz"), **store)
+    print(f"{n} cases: oracle == libwebp binary for the use_argb import")
+
+
 if __name__ == "__main__":
     main()
+    gen_import_argb()

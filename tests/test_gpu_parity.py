@@ -746,3 +746,34 @@ def test_picture_tools_vs_oracle(gpu, size):
     T.WebPCleanupTransparentArea(p)
     T.WebPReplaceTransparentPixels(p, 0)
     assert (p.Y == c["y"]).all() and p.A is None
+
+
+def test_import_to_argb(gpu, golden_dir):
+    """use_argb import (Import(), picture_csp_enc.c.go:138-181): libwebp vectors for all six
+    entry points in one batch, then seeded sizes / flipped and padded strides vs the oracle."""
+    P = gpu["picture"]
+    g = np.load(os.path.join(golden_dir, "import_argb_libwebp160.npz"))
+    by_order = {}
+    for k in g["names"]:
+        by_order.setdefault(str(g[f"{k}/order"]), []).append((g[f"{k}/src"], g[f"{k}/argb"]))
+    for order, cases in by_order.items():
+        step = 3 if order in ("RGB", "BGR") else 4
+        pics = [P.Picture(Width=e.shape[1], Height=e.shape[0], UseARGB=True) for _, e in cases]
+        assert P.ImportRGBABatch(pics, [s for s, _ in cases], [step * e.shape[1] for _, e in cases], order) == 1
+        for pic, (_, e) in zip(pics, cases):
+            assert pic.UseARGB and (pic.ARGB == e).all(), order
+    rng = np.random.default_rng(77)
+    for (w, h) in [(1, 1), (3, 2), (129, 7), (1000, 3), (1921, 5)]:
+        for order in ("RGBA", "BGRX", "RGB", "BGR"):
+            step = 3 if order in ("RGB", "BGR") else 4
+            stride = step * w + 8
+            buf = rng.integers(0, 256, (h, stride), dtype=np.uint8)
+            pic = P.Picture(Width=w, Height=h, UseARGB=True)
+            fn = getattr(P, "WebPPictureImport" + order)
+            assert fn(pic, buf, stride) == 1
+            assert (pic.ARGB == oracle.import_to_argb(buf, w, h, order, stride)).all(), (w, h, order)
+            pic = P.Picture(Width=w, Height=h, UseARGB=True)      # bottom-up source
+            assert fn(pic, buf, -stride) == 1
+            assert (pic.ARGB == oracle.import_to_argb(buf, w, h, order, -stride)).all(), (w, h, order, "flipped")
+    pic = P.Picture(Width=8, Height=2, UseARGB=True)
+    assert P.WebPPictureImportRGBA(pic, np.zeros((2, 16), np.uint8), 16) == 0   # stride < 4 * width (:132)

@@ -220,3 +220,12 @@ def test_replace_transparent_pixels_oracle():
     argb = np.array([[0x00123456, 0x01123456, 0xff000000, 0x00ffffff]], np.uint32)
     out = oracle.replace_transparent(argb, 0xffabcdef)
     assert out.tolist() == [[0x00abcdef, 0x01123456, 0xff000000, 0x00abcdef]]
+
+
+def test_import_to_argb_matches_libwebp_binary(golden_dir):
+    """Import() with use_argb = 1 (picture_csp_enc.c.go:138-181) for all six entry points."""
+    g = _load(golden_dir, "import_argb_libwebp160.npz")
+    for k in g["names"]:
+        src, exp, order = g[f"{k}/src"], g[f"{k}/argb"], str(g[f"{k}/order"])
+        h, w = exp.shape
+        assert (oracle.import_to_argb(src, w, h, order) == exp).all(), (k, order)

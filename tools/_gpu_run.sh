@@ -1,2 +1,1 @@
-timeout 600 python -m pytest tests -m gpu -x -q -k "picture_tools" 2>&1 | tail -3
-timeout 300 python tools/quick_bench.py tools 2>&1 | tail -8
+timeout 600 python -m pytest tests -m gpu -x -q -k "import_to_argb or import" 2>&1 | tail -12

@@ -777,3 +777,38 @@ def test_import_to_argb(gpu, golden_dir):
             assert (pic.ARGB == oracle.import_to_argb(buf, w, h, order, -stride)).all(), (w, h, order, "flipped")
     pic = P.Picture(Width=8, Height=2, UseARGB=True)
     assert P.WebPPictureImportRGBA(pic, np.zeros((2, 16), np.uint8), 16) == 0   # stride < 4 * width (:132)
+
+
+def test_picture_tools_and_argb_import_error_behaviour(gpu):
+    """Raw ABI of the 8f-3 entry points: null planes, bad dimensions / strides, bad order,
+    empty batch, bad stream -- never a launch, always a status."""
+    abi, ctx = gpu["abi"], gpu["ctx"]
+    lib, h = ctx.lib, ctx.h
+    buf = ctx.alloc(1 << 16)
+    one = lambda j: (type(j) * 1)(j)  # noqa: E731
+    yuva = abi.PictureJob(buf.ptr, buf.ptr, buf.ptr, None, None, 16, 8, 16, 0, 16, 8)       # a == NULL
+    assert lib.b2_picture_cleanup_transparent(h, 0, one(yuva), 1, 0) == abi.B2_ERR_NULL
+    assert lib.b2_picture_blend_alpha(h, 0, one(yuva), 1, 0, 0) == abi.B2_ERR_NULL
+    argb = abi.PictureJob(None, None, None, None, None, 0, 0, 0, 16, 16, 8)                  # argb == NULL
+    assert lib.b2_picture_cleanup_transparent(h, 0, one(argb), 1, 1) == abi.B2_ERR_NULL
+    assert lib.b2_picture_replace_transparent(h, 0, one(argb), 1, 0) == abi.B2_ERR_NULL
+    bad = abi.PictureJob(None, None, None, None, buf.ptr, 0, 0, 0, 8, 16, 8)                 # argb_stride < width
+    assert lib.b2_picture_blend_alpha(h, 0, one(bad), 1, 1, 0) == abi.B2_ERR_BAD_DIM
+    bad = abi.PictureJob(buf.ptr, buf.ptr, buf.ptr, buf.ptr, None, 16, 4, 16, 0, 16, 8)      # uv_stride < (w + 1) / 2
+    assert lib.b2_picture_cleanup_transparent(h, 0, one(bad), 1, 0) == abi.B2_ERR_BAD_DIM
+    bad = abi.PictureJob(None, None, None, None, buf.ptr, 0, 0, 0, 20000, 16384, 1)           # > WEBP_MAX_DIMENSION
+    assert lib.b2_picture_replace_transparent(h, 0, one(bad), 1, 0) == abi.B2_ERR_BAD_DIM
+    ok = abi.PictureJob(None, None, None, None, buf.ptr, 0, 0, 0, 16, 16, 4)                  # lower than a block row: nothing to do
+    assert lib.b2_picture_cleanup_transparent(h, 0, one(ok), 1, 1) == abi.B2_OK
+    assert lib.b2_picture_cleanup_transparent(h, 0, one(ok), 0, 1) == abi.B2_OK               # empty batch
+    assert lib.b2_picture_cleanup_transparent(h, 99, one(ok), 1, 1) == abi.B2_ERR_INVALID_CONFIG
+    cj = abi.ConvertJob(None, None, None, buf.ptr, 64, 0, 64, 16, 2, 0)                       # src == NULL
+    assert lib.b2_import_to_argb(h, 0, one(cj), 1, abi.ORDER_RGBA, 1) == abi.B2_ERR_NULL
+    cj = abi.ConvertJob(buf.ptr, None, None, buf.ptr, 48, 0, 64, 16, 2, 0)
+    assert lib.b2_import_to_argb(h, 0, one(cj), 1, abi.ORDER_RGB, 1) == abi.B2_ERR_INVALID_CONFIG   # alpha needs 4 bytes
+    assert lib.b2_import_to_argb(h, 0, one(cj), 1, abi.ORDER_RGBA, 1) == abi.B2_ERR_BAD_DIM         # |stride| < 4 * width
+    assert lib.b2_import_to_argb(h, 0, one(cj), 1, 7, 0) == abi.B2_ERR_INVALID_CONFIG
+    cj = abi.ConvertJob(buf.ptr, None, None, buf.ptr, 64, 0, 32, 16, 2, 0)                    # dst_stride < 4 * width
+    assert lib.b2_import_to_argb(h, 0, one(cj), 1, abi.ORDER_RGBA, 1) == abi.B2_ERR_BAD_DIM
+    ctx.sync()
+    buf.free()

@@ -103,6 +103,7 @@ SYMBOLS = {
     "b2_event_record": (C.c_int, [_ctx, C.c_int, C.c_int]),
     "b2_event_elapsed_ms": (C.c_int, [_ctx, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "b2_rgba_to_yuv420a": (C.c_int, [_ctx, C.c_int, C.POINTER(ImportJob), C.c_int, C.c_int, C.c_int, _vp]),
+    "b2_rgba_to_yuv420a_dithered": (C.c_int, [_ctx, C.c_int, C.POINTER(ImportJob), C.c_int, C.c_int, C.c_int, _vp, C.c_float]),
     "b2_yuv420a_to_rgba_fancy": (C.c_int, [_ctx, C.c_int, C.POINTER(UpsampleJob), C.c_int, C.c_int]),
     "b2_vp8l_add_green": (C.c_int, [_ctx, C.c_int, C.POINTER(ArgbJob), C.c_int]),
     "b2_vp8l_sub_green": (C.c_int, [_ctx, C.c_int, C.POINTER(ArgbJob), C.c_int]),

@@ -26,6 +26,9 @@ struct b2_ctx {
   size_t desc_off[B2_MAX_STREAMS];
   // constant tables living in global memory (gamma, inverse alpha)
   uint32_t* tab_dev;
+  // grow-only device scratch per stream (dithered import: generator states per row pair)
+  void* scratch[B2_MAX_STREAMS];
+  size_t scratch_bytes[B2_MAX_STREAMS];
   uint64_t launches;
   char err[256];
 };
@@ -51,6 +54,10 @@ int b2_fail_cuda(b2_ctx* ctx, cudaError_t e, const char* what);
     if ((stream) < 0 || (stream) >= (ctx)->n_streams) return B2_ERR_INVALID_CONFIG; \
     B2_CUDA(ctx, cudaSetDevice((ctx)->device));                          \
   } while (0)
+
+// Device scratch of at least 'bytes' for work enqueued on 'stream' (valid until the next
+// call for the same stream; growing it waits for the stream).
+int b2_stream_scratch(b2_ctx* ctx, int stream, size_t bytes, void** dev_out);
 
 // Copies 'bytes' of host descriptors into the stream's ring; returns device ptr.
 int b2_upload_desc(b2_ctx* ctx, int stream, const void* host, size_t bytes, void** dev_out);

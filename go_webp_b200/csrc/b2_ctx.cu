@@ -122,6 +122,7 @@ extern "C" void b2_ctx_destroy(b2_ctx* ctx) {
     if (ctx->streams[i]) { (void)cudaStreamSynchronize(ctx->streams[i]); (void)cudaStreamDestroy(ctx->streams[i]); }
     if (ctx->desc_host[i]) (void)cudaFreeHost(ctx->desc_host[i]);
     if (ctx->desc_dev[i]) (void)cudaFree(ctx->desc_dev[i]);
+    if (ctx->scratch[i]) (void)cudaFree(ctx->scratch[i]);
   }
   for (int i = 0; i < B2_EVENT_SLOTS; ++i) if (ctx->events[i]) (void)cudaEventDestroy(ctx->events[i]);
   if (ctx->tab_dev) (void)cudaFree(ctx->tab_dev);
@@ -132,6 +133,18 @@ extern "C" int b2_ctx_device(const b2_ctx* ctx) { return ctx ? ctx->device : -1;
 extern "C" int b2_ctx_sm_count(const b2_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
 extern "C" const char* b2_last_error(const b2_ctx* ctx) { return ctx ? ctx->err : "nil context"; }
 extern "C" uint64_t b2_launch_count(const b2_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int b2_stream_scratch(b2_ctx* ctx, int stream, size_t bytes, void** dev_out) {
+  if (bytes > ctx->scratch_bytes[stream]) {
+    B2_CUDA(ctx, cudaStreamSynchronize(ctx->streams[stream]));
+    if (ctx->scratch[stream]) { B2_CUDA(ctx, cudaFree(ctx->scratch[stream])); ctx->scratch[stream] = NULL; ctx->scratch_bytes[stream] = 0; }
+    const size_t cap = bytes + bytes / 4 + (1u << 20);
+    B2_CUDA(ctx, cudaMalloc(&ctx->scratch[stream], cap));
+    ctx->scratch_bytes[stream] = cap;
+  }
+  *dev_out = ctx->scratch[stream];
+  return B2_OK;
+}
 
 int b2_upload_desc(b2_ctx* ctx, int stream, const void* host, size_t bytes, void** dev_out) {
   const size_t need = (bytes + 255) & ~(size_t)255;

@@ -295,8 +295,8 @@ import_generic_kernel(const ImportJobDev* __restrict__ jobs, const uint32_t* __r
 
 }  // namespace
 
-extern "C" int b2_rgba_to_yuv420a(b2_ctx* ctx, int stream, const b2_import_job* jobs, int n_jobs,
-                                  int order, int flags, int32_t* has_alpha_dev) {
+static int import_impl(b2_ctx* ctx, int stream, const b2_import_job* jobs, int n_jobs,
+                       int order, int flags, int32_t* has_alpha_dev, float dithering) {
   B2_CHECK_CTX(ctx, stream);
   if (n_jobs < 0) return B2_ERR_INVALID_CONFIG;
   if (n_jobs == 0) return B2_OK;
@@ -372,9 +372,46 @@ extern "C" int b2_rgba_to_yuv420a(b2_ctx* ctx, int stream, const b2_import_job* 
   const int grid = b2_grid_for(ctx, 2, (total + kWarps - 1) / kWarps);
   const int divt = (flags & B2_IMPORT_DIV_TABLE) ? 1 : 0;
   const uint32_t tot = (uint32_t)total;
+  ImportDither dither = {nullptr, nullptr, 0};
+  const int amp = (dithering > 0.f) ? b2_rng_amp(dithering) : 0;   // amp 0: every draw is exactly YUV_HALF
+  if (amp > 0) {
+    // Dithered import (conversions.go:122-165): only on the tuned kernel's preconditions
+    // (4-byte pixels, 4-byte aligned rows and planes), which PictureARGBToYUVA always meets.
+    if (!tuned) return B2_ERR_INVALID_CONFIG;
+    const size_t poly_bytes = sizeof(uint32_t) * B2_RNG_N * (size_t)n_jobs;
+    if (2 * poly_bytes > B2_DESC_RING_BYTES) return B2_ERR_INVALID_CONFIG;
+    uint32_t* polys = (uint32_t*)malloc(2 * poly_bytes);
+    if (polys == NULL) return B2_ERR_OOM;
+    int last_w = -1, last_i = 0;
+    for (int i = 0; i < n_jobs; ++i) {
+      uint32_t* pk = polys + (size_t)i * B2_RNG_N;
+      uint32_t* pw = polys + (size_t)(n_jobs + i) * B2_RNG_N;
+      if (jobs[i].width == last_w) {   // batches are mostly of one size
+        memcpy(pk, polys + (size_t)last_i * B2_RNG_N, sizeof(uint32_t) * B2_RNG_N);
+        memcpy(pw, polys + (size_t)(n_jobs + last_i) * B2_RNG_N, sizeof(uint32_t) * B2_RNG_N);
+        continue;
+      }
+      const uint64_t w = (uint64_t)jobs[i].width;
+      b2_rng_jump_poly(2 * w + 2 * ((w + 1) >> 1), pk);   // draws of one row pair
+      b2_rng_jump_poly(w, pw);                            // draws of one luma row
+      last_w = jobs[i].width; last_i = i;
+    }
+    void* pdev = NULL;
+    st = b2_upload_desc(ctx, stream, polys, 2 * poly_bytes, &pdev);
+    free(polys);
+    if (st != B2_OK) return st;
+    void* states = NULL;
+    st = b2_stream_scratch(ctx, stream, sizeof(uint32_t) * B2_RNG_N * (size_t)utotal, &states);
+    if (st != B2_OK) return st;
+    B2_CUDA(ctx, b2_rng_states_launch(s, djobs, dupre, (uint32_t)n_jobs, (const uint32_t*)pdev, (uint32_t*)states));
+    ctx->launches++;
+    dither.rng_states = (const uint32_t*)states;
+    dither.rng_poly_w = (const uint32_t*)pdev + (size_t)n_jobs * B2_RNG_N;
+    dither.amp = amp;
+  }
   if (tuned) {
     B2_CUDA(ctx, b2_import_fast_launch(ctx, s, djobs, dupre, (uint32_t)n_jobs, uuniform, (uint32_t)utotal,
-                                       order, alpha, n_with_a != 0, divt, has_alpha_dev));
+                                       order, alpha, n_with_a != 0, divt, has_alpha_dev, dither));
   } else if (fast) {
     if (order == B2_ORDER_RGBA) {
       if (alpha) import_kernel<0, true><<<grid, kThreads, 0, s>>>(djobs, dpre, n_jobs, uniform, tot, ctx->tab_dev, divt, has_alpha_dev);
@@ -392,4 +429,14 @@ extern "C" int b2_rgba_to_yuv420a(b2_ctx* ctx, int stream, const b2_import_job* 
   ctx->launches++;
   B2_CUDA(ctx, cudaGetLastError());
   return B2_OK;
+}
+
+extern "C" int b2_rgba_to_yuv420a(b2_ctx* ctx, int stream, const b2_import_job* jobs, int n_jobs,
+                                  int order, int flags, int32_t* has_alpha_dev) {
+  return import_impl(ctx, stream, jobs, n_jobs, order, flags, has_alpha_dev, 0.f);
+}
+
+extern "C" int b2_rgba_to_yuv420a_dithered(b2_ctx* ctx, int stream, const b2_import_job* jobs, int n_jobs,
+                                           int order, int flags, int32_t* has_alpha_dev, float dithering) {
+  return import_impl(ctx, stream, jobs, n_jobs, order, flags, has_alpha_dev, dithering);
 }

@@ -101,9 +101,10 @@ __device__ __forceinline__ uint2 lds64(uint32_t addr) {
   return v;
 }
 // RGBToY (conversion.go:56-59) as two 16x8-bit dot products; Y = byte 2 of the sum
+// rnd = YUV_HALF, or the VP8RandomBits(rg, YUV_FIX) draw of the dithered import
 template <int ORDER>
-__device__ __forceinline__ uint32_t luma_sum(uint32_t p) {
-  return __dp2a_hi(Ch<ORDER>::kHiPair, p, __dp2a_lo(Ch<ORDER>::kLoPair, p, (1u << 15) + (16u << 16)));
+__device__ __forceinline__ uint32_t luma_sum(uint32_t p, uint32_t rnd = 1u << 15) {
+  return __dp2a_hi(Ch<ORDER>::kHiPair, p, __dp2a_lo(Ch<ORDER>::kLoPair, p, rnd + (16u << 16)));
 }
 __device__ __forceinline__ uint32_t pack_b2(uint32_t s0, uint32_t s1, uint32_t s2, uint32_t s3) {
   return __byte_perm(__byte_perm(s0, s1, 0x0062), __byte_perm(s2, s3, 0x0062), 0x5410);
@@ -126,16 +127,27 @@ __device__ __forceinline__ int l2g(uint32_t s7, uint32_t lbase) {
 }
 // RGBToU / RGBToV on gamma-domain sums (conversion.go:51-69, rounding YUV_HALF<<2),
 // scaled by 64: the result is byte 3.  Inputs are <= 1020 so ClipUV never clamps.
-__device__ __forceinline__ uint32_t u_sum(int r, int g, int b) {
-  constexpr uint32_t kRnd = ((1u << 17) + (128u << 18)) << 6;
+// rnd = YUV_HALF << 2, or the VP8RandomBits(rg, YUV_FIX + 2) draw (< 2^18: still no clamp, no overflow)
+__device__ __forceinline__ uint32_t u_sum(int r, int g, int b, uint32_t rnd = 1u << 17) {
+  const uint32_t k = (rnd + (128u << 18)) << 6;
   return (uint32_t)(-9719 * 64) * (uint32_t)r + (uint32_t)(-19081 * 64) * (uint32_t)g +
-         (uint32_t)(28800 * 64) * (uint32_t)b + kRnd;
+         (uint32_t)(28800 * 64) * (uint32_t)b + k;
 }
-__device__ __forceinline__ uint32_t v_sum(int r, int g, int b) {
-  constexpr uint32_t kRnd = ((1u << 17) + (128u << 18)) << 6;
+__device__ __forceinline__ uint32_t v_sum(int r, int g, int b, uint32_t rnd = 1u << 17) {
+  const uint32_t k = (rnd + (128u << 18)) << 6;
   return (uint32_t)(28800 * 64) * (uint32_t)r + (uint32_t)(-24116 * 64) * (uint32_t)g +
-         (uint32_t)(-4684 * 64) * (uint32_t)b + kRnd;
+         (uint32_t)(-4684 * 64) * (uint32_t)b + k;
 }
+// VP8RandomBits2 (pkg/vp8/random.go:68-95) on a raw 31-bit draw
+template <int NUM_BITS>
+__device__ __forceinline__ uint32_t dither_value(uint32_t raw, int amp) {
+  int diff = (int)(raw << 1) >> (32 - NUM_BITS);   // sign-extend, 0-center
+  diff = (diff * amp) >> 8;                          // restrict range
+  return (uint32_t)(diff + (1 << (NUM_BITS - 1)));   // shift back to 0.5-center
+}
+constexpr uint32_t kDitherWarpBytes = 3 * 1024;     // three 256-entry rings of raw draws per warp
+static_assert(kSmemBytes + kFastWarps * (int)kDitherWarpBytes <= 232448 && kSmemBytes % 16 == 0 && kSplit == 1,
+              "dithered import: shared memory / one warp per row pair");
 
 // DIVIDE_BY_ALPHA (yuv.go:231) on w7 = (sum of alpha_i * linear_i) << 7; returns the
 // quotient << 7 ready for l2g().  dv = this divisor's table entry.
@@ -196,11 +208,11 @@ __device__ __forceinline__ uint32_t ring_next(uint32_t a) {
   return (a & ~kStageMask) | ((a + kStageBytes) & kStageMask);
 }
 
-template <int ORDER, bool ALPHA, bool WRITE_A, bool TABLE>
+template <int ORDER, bool ALPHA, bool WRITE_A, bool TABLE, bool DITHER>
 __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm)
 import_fast_kernel(const ImportJobDev* __restrict__ jobs, const uint32_t* __restrict__ unit_prefix,
                    uint32_t n_jobs, uint32_t uniform_units, uint32_t total_units,
-                   const uint32_t* __restrict__ tab, int32_t* __restrict__ has_alpha) {
+                   const uint32_t* __restrict__ tab, int32_t* __restrict__ has_alpha, const ImportDither dither) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
   const uint32_t tbase = (sbase + 0xffffu) & ~0xffffu;       // T
@@ -269,6 +281,30 @@ import_fast_kernel(const ImportJobDev* __restrict__ jobs, const uint32_t* __rest
     uint8_t* up = jp->u + uvo;
     uint8_t* vp = jp->v + uvo;
     uint32_t and_acc = 0xffffffffu;
+    // Dithered import: three rings of raw VP8Random draws (first luma row, second luma row,
+    // chroma row), each 128 draws per strip.  Their start windows: the row pair's own state,
+    // then width draws later, then width draws later again (a last odd row has no second
+    // luma row: its chroma draws start after the first).
+    uint32_t* const rng = reinterpret_cast<uint32_t*>(smem + kSmemBytes + warp * kDitherWarpBytes);
+    uint32_t rpos = 0;
+    if (DITHER) {
+      uint32_t* ext = rng + 512;          // scratch inside the third ring until it is filled
+      uint32_t* cw = rng + 512 + 128;
+      const uint32_t* st = dither.rng_states + (size_t)(unit / kSplit) * B2_RNG_N;
+      const uint32_t* pw = dither.rng_poly_w + (size_t)img * B2_RNG_N;
+      __syncwarp();
+      for (int i = (int)lane; i < B2_RNG_N; i += 32) { ext[i] = __ldg(st + i); cw[i] = __ldg(pw + i); }
+      __syncwarp();
+      for (int i = (int)lane; i < B2_RNG_N; i += 32) rng[(256 - B2_RNG_N) + i] = ext[i];
+      b2_rng_jump_warp(ext, cw, (int)lane);
+      for (int i = (int)lane; i < B2_RNG_N; i += 32) rng[256 + (256 - B2_RNG_N) + i] = ext[i];
+      if (has_row1) b2_rng_jump_warp(ext, cw, (int)lane);
+      const uint32_t e0 = ext[lane], e1 = ext[min((int)lane + 32, B2_RNG_N - 1)];
+      __syncwarp();
+      rng[512 + (256 - B2_RNG_N) + lane] = e0;
+      if (lane + 32 < B2_RNG_N) rng[512 + (256 - B2_RNG_N) + lane + 32] = e1;
+      __syncwarp();
+    }
 
     // Strips of 128 pixels.  Rows that are 16-byte aligned are fetched with one 16-byte
     // cp.async per lane and row; whole strips of such rows take the check-free code.  The
@@ -313,6 +349,27 @@ import_fast_kernel(const ImportJobDev* __restrict__ jobs, const uint32_t* __rest
       uint4 c0 = lds128_ring(rd);
       uint4 c1 = lds128_ring(rd + 512);
       rd = ring_next(rd);
+      uint4 dq0 = make_uint4(0, 0, 0, 0), dq1 = dq0, dq2 = dq0;
+      if (DITHER) {
+        // the next 128 draws of the three streams, 24 per step: s_n = s_(n-55) - s_(n-24) mod 2^31
+#pragma unroll
+        for (int b = 0; b < 128; b += 24) {
+          const uint32_t i = rpos + b + lane;
+          if (lane < 24 && b + (int)lane < 128) {
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+              uint32_t* r = rng + 256 * q;
+              r[i & 255u] = (r[(i - 55u) & 255u] - r[(i - 24u) & 255u]) & 0x7fffffffu;
+            }
+          }
+          __syncwarp();
+        }
+        const uint32_t o = (rpos + lane4) & 255u;
+        dq0 = *reinterpret_cast<const uint4*>(rng + o);
+        dq1 = has_row1 ? *reinterpret_cast<const uint4*>(rng + 256 + o) : dq0;
+        dq2 = *reinterpret_cast<const uint4*>(rng + 512 + o);
+        rpos = (rpos + 128u) & 255u;
+      }
       int nvalid = 4;
       if (!FULL) {
         // Last group of a row whose width is not a multiple of 4: only valid pixels were
@@ -327,8 +384,17 @@ import_fast_kernel(const ImportJobDev* __restrict__ jobs, const uint32_t* __rest
           else { c0.w = c0.z; c1.w = c1.z; }
         }
       }
-      const uint32_t yw0 = pack_b2(luma_sum<ORDER>(c0.x), luma_sum<ORDER>(c0.y), luma_sum<ORDER>(c0.z), luma_sum<ORDER>(c0.w));
-      const uint32_t yw1 = pack_b2(luma_sum<ORDER>(c1.x), luma_sum<ORDER>(c1.y), luma_sum<ORDER>(c1.z), luma_sum<ORDER>(c1.w));
+      uint32_t yw0, yw1;
+      if (DITHER) {
+        const int amp = dither.amp;
+        yw0 = pack_b2(luma_sum<ORDER>(c0.x, dither_value<16>(dq0.x, amp)), luma_sum<ORDER>(c0.y, dither_value<16>(dq0.y, amp)),
+                      luma_sum<ORDER>(c0.z, dither_value<16>(dq0.z, amp)), luma_sum<ORDER>(c0.w, dither_value<16>(dq0.w, amp)));
+        yw1 = pack_b2(luma_sum<ORDER>(c1.x, dither_value<16>(dq1.x, amp)), luma_sum<ORDER>(c1.y, dither_value<16>(dq1.y, amp)),
+                      luma_sum<ORDER>(c1.z, dither_value<16>(dq1.z, amp)), luma_sum<ORDER>(c1.w, dither_value<16>(dq1.w, amp)));
+      } else {
+        yw0 = pack_b2(luma_sum<ORDER>(c0.x), luma_sum<ORDER>(c0.y), luma_sum<ORDER>(c0.z), luma_sum<ORDER>(c0.w));
+        yw1 = pack_b2(luma_sum<ORDER>(c1.x), luma_sum<ORDER>(c1.y), luma_sum<ORDER>(c1.z), luma_sum<ORDER>(c1.w));
+      }
       uint32_t ap0 = 0xffffffffu, ap1 = 0xffffffffu;
       if (ALPHA) {
         ap0 = pack_b3(c0.x, c0.y, c0.z, c0.w);
@@ -340,8 +406,15 @@ import_fast_kernel(const ImportJobDev* __restrict__ jobs, const uint32_t* __rest
       block_sums<ORDER, ALPHA, TABLE>(gbase, dbase, c0.z, c0.w, c1.z, c1.w, __byte_perm(ap0, ap1, 0x7632), &sr1, &sg1, &sb1);
       const int r0 = l2g(sr0, lbase), gg0 = l2g(sg0, lbase), b0 = l2g(sb0, lbase);
       const int r1 = l2g(sr1, lbase), gg1 = l2g(sg1, lbase), b1 = l2g(sb1, lbase);
-      const uint32_t uu = __byte_perm(u_sum(r0, gg0, b0), u_sum(r1, gg1, b1), 0x0073);
-      const uint32_t vv = __byte_perm(v_sum(r0, gg0, b0), v_sum(r1, gg1, b1), 0x0073);
+      uint32_t uu, vv;
+      if (DITHER) {   // draws alternate u, v per chroma sample (picture_csp_enc.c.go:44-46)
+        const int amp = dither.amp;
+        uu = __byte_perm(u_sum(r0, gg0, b0, dither_value<18>(dq2.x, amp)), u_sum(r1, gg1, b1, dither_value<18>(dq2.z, amp)), 0x0073);
+        vv = __byte_perm(v_sum(r0, gg0, b0, dither_value<18>(dq2.y, amp)), v_sum(r1, gg1, b1, dither_value<18>(dq2.w, amp)), 0x0073);
+      } else {
+        uu = __byte_perm(u_sum(r0, gg0, b0), u_sum(r1, gg1, b1), 0x0073);
+        vv = __byte_perm(v_sum(r0, gg0, b0), v_sum(r1, gg1, b1), 0x0073);
+      }
       if (FULL || nvalid >= 4) {
         b2_stg_stream_u32(yp, yw0);
         b2_stg_stream_u32(yp + ystride, yw1);
@@ -378,23 +451,32 @@ import_fast_kernel(const ImportJobDev* __restrict__ jobs, const uint32_t* __rest
   }
 }
 
+template <int ORDER, bool ALPHA, bool WRITE_A, bool TABLE, bool DITHER>
+cudaError_t launch2(int grid, cudaStream_t s, const ImportJobDev* jobs, const uint32_t* unit_prefix,
+                    uint32_t n_jobs, uint32_t uniform_units, uint32_t total_units, const uint32_t* tab,
+                    int32_t* has_alpha, ImportDither dither) {
+  auto k = import_fast_kernel<ORDER, ALPHA, WRITE_A, TABLE, DITHER>;
+  const int smem = kSmemBytes + (DITHER ? kFastWarps * (int)kDitherWarpBytes : 0);
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  k<<<grid, kFastThreads, smem, s>>>(jobs, unit_prefix, n_jobs, uniform_units, total_units, tab, has_alpha, dither);
+  return cudaGetLastError();
+}
 template <int ORDER, bool ALPHA, bool WRITE_A, bool TABLE>
 cudaError_t launch1(int grid, cudaStream_t s, const ImportJobDev* jobs, const uint32_t* unit_prefix,
                     uint32_t n_jobs, uint32_t uniform_units, uint32_t total_units, const uint32_t* tab,
-                    int32_t* has_alpha) {
-  auto k = import_fast_kernel<ORDER, ALPHA, WRITE_A, TABLE>;
-  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-  if (e != cudaSuccess) return e;
-  k<<<grid, kFastThreads, kSmemBytes, s>>>(jobs, unit_prefix, n_jobs, uniform_units, total_units, tab, has_alpha);
-  return cudaGetLastError();
+                    int32_t* has_alpha, ImportDither dither) {
+  if (dither.rng_states != nullptr)
+    return launch2<ORDER, ALPHA, WRITE_A, TABLE, true>(grid, s, jobs, unit_prefix, n_jobs, uniform_units, total_units, tab, has_alpha, dither);
+  return launch2<ORDER, ALPHA, WRITE_A, TABLE, false>(grid, s, jobs, unit_prefix, n_jobs, uniform_units, total_units, tab, has_alpha, dither);
 }
 template <int ORDER, bool ALPHA, bool WRITE_A>
 cudaError_t launch(int grid, cudaStream_t s, const ImportJobDev* jobs, const uint32_t* unit_prefix,
                    uint32_t n_jobs, uint32_t uniform_units, uint32_t total_units, const uint32_t* tab,
-                   int div_table, int32_t* has_alpha) {
+                   int div_table, int32_t* has_alpha, ImportDither dither) {
   // the divide mode only matters when alpha is imported
-  if (ALPHA && div_table) return launch1<ORDER, ALPHA, WRITE_A, true>(grid, s, jobs, unit_prefix, n_jobs, uniform_units, total_units, tab, has_alpha);
-  return launch1<ORDER, ALPHA, WRITE_A, false>(grid, s, jobs, unit_prefix, n_jobs, uniform_units, total_units, tab, has_alpha);
+  if (ALPHA && div_table) return launch1<ORDER, ALPHA, WRITE_A, true>(grid, s, jobs, unit_prefix, n_jobs, uniform_units, total_units, tab, has_alpha, dither);
+  return launch1<ORDER, ALPHA, WRITE_A, false>(grid, s, jobs, unit_prefix, n_jobs, uniform_units, total_units, tab, has_alpha, dither);
 }
 
 }  // namespace
@@ -402,9 +484,10 @@ cudaError_t launch(int grid, cudaStream_t s, const ImportJobDev* jobs, const uin
 cudaError_t b2_import_fast_launch(const b2_ctx* ctx, cudaStream_t s, const ImportJobDev* jobs,
                                   const uint32_t* unit_prefix, uint32_t n_jobs,
                                   uint32_t uniform_units, uint32_t total_units, int order,
-                                  bool alpha, bool write_a, int div_table, int32_t* has_alpha) {
+                                  bool alpha, bool write_a, int div_table, int32_t* has_alpha,
+                                  ImportDither dither) {
   const int grid = b2_grid_for(ctx, kFastCtasPerSm, ((uint64_t)total_units * kSplit + kFastWarps - 1) / kFastWarps);
-#define B2_GO(O, A, W) return launch<O, A, W>(grid, s, jobs, unit_prefix, n_jobs, uniform_units, total_units, ctx->tab_dev, div_table, has_alpha)
+#define B2_GO(O, A, W) return launch<O, A, W>(grid, s, jobs, unit_prefix, n_jobs, uniform_units, total_units, ctx->tab_dev, div_table, has_alpha, dither)
   if (order == B2_ORDER_RGBA) {
     if (alpha) { if (write_a) B2_GO(0, true, true); else B2_GO(0, true, false); }
     else       { if (write_a) B2_GO(0, false, true); else B2_GO(0, false, false); }

@@ -164,13 +164,7 @@ type ImportJob struct {
 	Width, Height                  int
 }
 
-// ImportRGBA replaces dsp.WebPImportYUVAFromRGBA (pkg/libwebp/dsp/yuv.go:304-382)
-// and the has-alpha scan of picture.ImportYUVAFromRGBA (conversions.go:56) for a
-// batch.  hasAlpha addresses int32[len(jobs)] in device memory (or 0).
-func (c *Context) ImportRGBA(stream int, jobs []ImportJob, order, flags int, hasAlpha DevicePtr) error {
-	if len(jobs) == 0 {
-		return nil
-	}
+func importJobs(jobs []ImportJob) []C.b2_import_job {
 	cj := make([]C.b2_import_job, len(jobs))
 	for i, j := range jobs {
 		cj[i] = C.b2_import_job{
@@ -184,6 +178,17 @@ func (c *Context) ImportRGBA(stream int, jobs []ImportJob, order, flags int, has
 			width: C.int32_t(j.Width), height: C.int32_t(j.Height),
 		}
 	}
+	return cj
+}
+
+// ImportRGBA replaces dsp.WebPImportYUVAFromRGBA (pkg/libwebp/dsp/yuv.go:304-382)
+// and the has-alpha scan of picture.ImportYUVAFromRGBA (conversions.go:56) for a
+// batch.  hasAlpha addresses int32[len(jobs)] in device memory (or 0).
+func (c *Context) ImportRGBA(stream int, jobs []ImportJob, order, flags int, hasAlpha DevicePtr) error {
+	if len(jobs) == 0 {
+		return nil
+	}
+	cj := importJobs(jobs)
 	st := C.b2_rgba_to_yuv420a(c.h, C.int(stream), &cj[0], C.int(len(cj)), C.int(order),
 		C.int(flags), (*C.int32_t)(unsafe.Pointer(uintptr(hasAlpha))))
 	return status(c, st)
@@ -510,4 +515,16 @@ func (c *Context) ImportToARGB(stream int, jobs []ConvertJob, order int, importA
 	}
 	cj := convertJobs(jobs)
 	return status(c, C.b2_import_to_argb(c.h, C.int(stream), &cj[0], C.int(len(cj)), C.int(order), boolInt(importAlpha)))
+}
+
+// ImportRGBADithered replaces the dithered copy of the import (pkg/picture/conversions.go:
+// 122-165; ConvertRowToY / ConvertRowsToUV, pkg/libwebp/enc/picture_csp_enc.c.go:31-48;
+// VP8Random, pkg/vp8/random.go).  dithering as PictureARGBToYUVA's argument.
+func (c *Context) ImportRGBADithered(stream int, jobs []ImportJob, order, flags int, hasAlpha DevicePtr, dithering float32) error {
+	if len(jobs) == 0 {
+		return nil
+	}
+	cj := importJobs(jobs)
+	return status(c, C.b2_rgba_to_yuv420a_dithered(c.h, C.int(stream), &cj[0], C.int(len(cj)), C.int(order), C.int(flags),
+		(*C.int32_t)(unsafe.Pointer(uintptr(hasAlpha))), C.float(dithering)))
 }

@@ -188,7 +188,7 @@ def _import_argb_batch(pics, srcs, strides, b2order, step, import_alpha, ctx) ->
 
 
 def ImportRGBABatch(pics, srcs, strides, order: str = "RGBA", ctx: Context | None = None,
-                    divide_table: bool = False, chunk: int = 16) -> int:
+                    divide_table: bool = False, chunk: int = 16, dithering: float = 0.0) -> int:
     """Added batched entry point (one per part): imports srcs[i]
     (interleaved bytes, row stride strides[i]) into pics[i] as YUV420(A).
 
@@ -220,7 +220,7 @@ def ImportRGBABatch(pics, srcs, strides, order: str = "RGBA", ctx: Context | Non
         if not rest:
             return 1
         return ImportRGBABatch([pics[i] for i in rest], [srcs[i] for i in rest], [strides[i] for i in rest],
-                               order, ctx, divide_table, chunk)
+                               order, ctx, divide_table, chunk, dithering)
     # device layout per image: src rows (caller stride kept), then Y | U | V | A
     metas = []
     need = 0
@@ -261,7 +261,11 @@ def ImportRGBABatch(pics, srcs, strides, order: str = "RGBA", ctx: Context | Non
                 src = np.ascontiguousarray(srcs[i]).reshape(-1)
                 ctx._chk(lib.b2_h2d_async(hnd, s, dptr[i]["src"], src.ctypes.data, abs(strides[i]) * (h - 1) + step * w))
             arr = (_abi.ImportJob * (c1 - c0))(*jobs[c0:c1])
-            ctx._chk(lib.b2_rgba_to_yuv420a(hnd, s, arr, c1 - c0, b2order, flags, flags_ptr + 4 * c0))
+            if dithering > 0.0:  # conversions.go:122-165; one VP8Random per image, whatever the chunking
+                ctx._chk(lib.b2_rgba_to_yuv420a_dithered(hnd, s, arr, c1 - c0, b2order, flags, flags_ptr + 4 * c0,
+                                                         float(dithering)))
+            else:
+                ctx._chk(lib.b2_rgba_to_yuv420a(hnd, s, arr, c1 - c0, b2order, flags, flags_ptr + 4 * c0))
             for i in range(c0, c1):
                 w, h, uvw, uvh, ys, uvs, sz = metas[i]
                 pic = pics[i]
@@ -300,7 +304,8 @@ def WebPPictureImportBGRA(pic, bgra, bgra_stride): return _import_one(pic, bgra,
 def WebPPictureImportBGRX(pic, bgrx, bgrx_stride): return _import_one(pic, bgrx, bgrx_stride, "BGRX")
 
 
-def PictureARGBToYUVA(pic: Picture, csp: int, dithering: float = 0.0, use_iterative_conversion: int = 0):
+def PictureARGBToYUVA(pic: Picture, csp: int, dithering: float = 0.0, use_iterative_conversion: int = 0,
+                      divide_table: bool = False):
     """conversions.go:12-30: ARGB (uint32 0xAARRGGBB) -> YUV420(A).  Returns an
     error sentinel or None, like the Go function."""
     if pic is None:
@@ -311,17 +316,23 @@ def PictureARGBToYUVA(pic: Picture, csp: int, dithering: float = 0.0, use_iterat
     if (csp & WEBP_CSP_UV_MASK) != WEBP_YUV420:
         pic.SetEncodingError(ENC_ERROR_INVALID_CONFIGURATION)
         return ENC_ERROR_INVALID_CONFIGURATION
-    if dithering > 0.0 or use_iterative_conversion:
-        raise NotImplementedError("dithered / sharp-YUV import are not on the hot path (SURVEY 5, 8f-3)")
+    if use_iterative_conversion:
+        raise NotImplementedError("sharp-YUV import is not on the hot path (SURVEY 5; the sharpyuv package is absent)")
     argb = np.ascontiguousarray(pic.ARGB, np.uint32)
     stride = 4 * (pic.ARGBStride or pic.Width)
     pic.UseARGB = False  # ImportYUVAFromRGBA sets use_argb = 0 (conversions.go:59)
-    ok = ImportRGBABatch([pic], [argb.view(np.uint8)], [stride], "BGRA")
+    ok = ImportRGBABatch([pic], [argb.view(np.uint8)], [stride], "BGRA", divide_table=divide_table,
+                         dithering=max(float(dithering), 0.0))
     return None if ok else (pic.ErrorCode or ENC_ERROR_OUT_OF_MEMORY)
 
 
 def WebPPictureARGBToYUVA(pic: Picture, csp: int = WEBP_YUV420):
     return PictureARGBToYUVA(pic, csp, 0.0, 0)
+
+
+def WebPPictureARGBToYUVADithered(pic: Picture, csp: int, dithering: float):
+    """conversions.go:36-38."""
+    return PictureARGBToYUVA(pic, csp, dithering, 0)
 
 
 def YUVAToRGBABatch(pics, mode: int = _abi.MODE_BGRA, dsts=None, ctx: Context | None = None,

@@ -83,9 +83,14 @@ class ImportPipeline:
         return (2 * self.ys * self.h + 2 * self.uvs * self.uvh + 4) * self.n
 
     # execution --------------------------------------------------------------------
-    def run_device(self, stream: int = 0):
-        """One kernel launch over the resident batch (inputs already in HBM)."""
+    def run_device(self, stream: int = 0, dithering: float = 0.0):
+        """One kernel launch over the resident batch (inputs already in HBM); with
+        dithering > 0 the dithered import (skip-ahead state kernel + import kernel)."""
         c = self.ctx
+        if dithering > 0.0:
+            c._chk(c.lib.b2_rgba_to_yuv420a_dithered(c.h, stream, self._job_arr, self.n, self.order, self.flags,
+                                                     self.d_flags.ptr, float(dithering)))
+            return
         c._chk(c.lib.b2_rgba_to_yuv420a(c.h, stream, self._job_arr, self.n, self.order, self.flags,
                                         self.d_flags.ptr))
 

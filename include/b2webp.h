@@ -117,6 +117,19 @@ typedef enum b2_pixel_order {
 int b2_rgba_to_yuv420a(b2_ctx* ctx, int stream, const b2_import_job* jobs, int n_jobs,
                        int order, int flags, int32_t* has_alpha_dev);
 
+/* The dithered copy of the import: pkg/picture/conversions.go:122-165
+ * with ConvertRowToY / ConvertRowsToUV (pkg/libwebp/enc/picture_csp_enc.c.go:31-48) and
+ * VP8Random (pkg/vp8/random.go:13-95) -- the rounding constants of RGBToY / RGBToU /
+ * RGBToV become draws of ONE generator that runs through the whole image (two luma rows,
+ * then u, v per chroma sample, per row pair).  dithering in (0, 1] as
+ * PictureARGBToYUVA's argument (amp = dithering * 256; 0 or an amp of 0 = the plain
+ * import).  The generator is linear, so every row pair gets its state by skip-ahead and
+ * the image is still processed in parallel.  Preconditions of the dithered path: 4-byte
+ * pixels, source rows and Y / A planes 4-byte aligned, U / V planes 2-byte aligned
+ * (B2_ERR_INVALID_CONFIG otherwise); PictureARGBToYUVA's ARGB pictures always meet them. */
+int b2_rgba_to_yuv420a_dithered(b2_ctx* ctx, int stream, const b2_import_job* jobs, int n_jobs,
+                                int order, int flags, int32_t* has_alpha_dev, float dithering);
+
 /* ---- part 2: YUV420(+A) -> RGBA fancy upsampling -------------------------
  * Replaces WebPUpsamplers[mode] line pairs (pkg/libwebp/dsp/upsampling.c.go:
  * 43-114,275-289) driven by the whole-image schedule of WebPPictureYUVAToARGB

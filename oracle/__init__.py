@@ -369,3 +369,30 @@ def import_to_argb(src, width, height, order="RGBA", stride=None):
     ok = lib().orc_import_to_argb(C.c_void_p(base), stride, step, swap_rb, import_alpha, width, height, _p(dst), width)
     assert ok
     return dst
+
+
+def import_yuva_dithered(src: np.ndarray, width: int, height: int, dithering: float, order: str = "RGBA",
+                         stride: int | None = None, divide_mode: int = DIV_EXACT):
+    """The dithered import (conversions.go:122-165).  Returns (y,u,v,a,has_alpha)."""
+    r, g, b, a_off, step = ORDERS[order]
+    src = np.ascontiguousarray(src, np.uint8).reshape(-1)
+    if stride is None:
+        stride = step * width
+    uvw, uvh = (width + 1) >> 1, (height + 1) >> 1
+    y = np.zeros((height, width), np.uint8)
+    u = np.zeros((uvh, uvw), np.uint8)
+    v = np.zeros((uvh, uvw), np.uint8)
+    a = np.zeros((height, width), np.uint8)
+    ptr = C.c_void_p(src.ctypes.data + ((-stride) * (height - 1) if stride < 0 else 0))
+    ha = lib().orc_import_yuva_dithered(ptr, r, g, b, a_off, step, stride, width, height, _p(y), width, _p(u), _p(v),
+                                        uvw, _p(a), width, divide_mode, C.c_float(dithering))
+    if ha < 0:
+        raise ValueError("orc_import_yuva_dithered: bad arguments")
+    return y, u, v, a, bool(ha)
+
+
+def vp8_random(dithering: float, num_bits: int, n: int):
+    """First n values of VP8RandomBits(rg, num_bits) after VP8InitRandom(dithering)."""
+    out = np.zeros(n, np.int32)
+    lib().orc_vp8_random(C.c_float(dithering), num_bits, n, _p(out))
+    return out

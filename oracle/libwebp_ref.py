@@ -228,3 +228,20 @@ def import_to_argb(src: np.ndarray, width: int, height: int, order="RGBA", strid
     out = _read_argb(p)
     L.WebPPictureFree(C.byref(p))
     return out
+
+
+def argb_to_yuva_dithered(argb: np.ndarray, dithering: float):
+    """WebPPictureARGBToYUVADithered (exported) on an ARGB picture -> (y, u, v, a_or_None,
+    has_alpha).  Translucent blocks follow the binary's inverse-alpha table (DIV_TABLE)."""
+    L = lib()
+    p = _picture_argb(np.ascontiguousarray(argb, np.uint32))
+    L.WebPPictureARGBToYUVADithered.argtypes = [C.c_void_p, C.c_int, C.c_float]
+    if not L.WebPPictureARGBToYUVADithered(C.byref(p), 0, C.c_float(dithering)):   # WEBP_YUV420
+        raise ValueError("WebPPictureARGBToYUVADithered failed")
+    w, h = p.width, p.height
+    uvw, uvh = (w + 1) >> 1, (h + 1) >> 1
+    has_alpha = bool(p.colorspace & 4)
+    out = (_plane(p.y, p.y_stride, w, h), _plane(p.u, p.uv_stride, uvw, uvh), _plane(p.v, p.uv_stride, uvw, uvh),
+           _plane(p.a, p.a_stride, w, h) if has_alpha else None, has_alpha)
+    L.WebPPictureFree(C.byref(p))
+    return out

@@ -380,6 +380,138 @@ int orc_import_yuva(const uint8_t* rgb, int r_off, int g_off, int b_off,
   return has_alpha;
 }
 
+/* ---- dithered import ---------------------------------------- */
+/* pkg/vp8/random.go:13-95 (VP8Random; D. Knuth's difference-based generator).  The Go
+ * text increments the indices after testing them against the table size; the intended C
+ * semantics (upstream random_utils.h: `if (++index == VP8_RANDOM_TABLE_SIZE) index = 0`)
+ * are implemented, and pinned by the binary's WebPPictureARGBToYUVADithered. */
+#define VP8_RANDOM_DITHER_FIX 8
+#define VP8_RANDOM_TABLE_SIZE 55
+static const uint32_t kRandomTable[VP8_RANDOM_TABLE_SIZE] = {
+    0x0de15230, 0x03b31886, 0x775faccb, 0x1c88626a, 0x68385c55, 0x14b3b828, 0x4a85fef8, 0x49ddb84b,
+    0x64fcf397, 0x5c550289, 0x4a290000, 0x0d7ec1da, 0x5940b7ab, 0x5492577d, 0x4e19ca72, 0x38d38c69,
+    0x0c01ee65, 0x32a1755f, 0x5437f652, 0x5abb2c32, 0x0faa57b1, 0x73f533e7, 0x685feeda, 0x7563cce2,
+    0x6e990e83, 0x4730a7ed, 0x4fc0d9c6, 0x496b153c, 0x4f1403fa, 0x541afb0c, 0x73990b32, 0x26d7cb1c,
+    0x6fcc3706, 0x2cbb77d8, 0x75762f2a, 0x6425ccdd, 0x24b35461, 0x0a7d8715, 0x220414a8, 0x141ebf67,
+    0x56b41583, 0x73e502e3, 0x44cab16f, 0x28264d42, 0x73baaefb, 0x0a50ebed, 0x1d6ab6fb, 0x0d3ad40b,
+    0x35db3b68, 0x2b081e83, 0x77ce6b95, 0x5181e5f0, 0x78853bbc, 0x009f9494, 0x27e5ed3c};
+typedef struct {
+  int index1, index2;
+  uint32_t tab[VP8_RANDOM_TABLE_SIZE];
+  int amp;
+} VP8Random;
+/* random.go:49-63 */
+static void VP8InitRandom(VP8Random* rg, float dithering) {
+  memcpy(rg->tab, kRandomTable, sizeof(rg->tab));
+  rg->index1 = 0;
+  rg->index2 = 31;
+  rg->amp = (dithering < 0.f) ? 0
+            : (dithering > 1.f) ? (1 << VP8_RANDOM_DITHER_FIX)
+                                : (int)((1 << VP8_RANDOM_DITHER_FIX) * dithering);
+}
+/* random.go:68-95 */
+static int VP8RandomBits(VP8Random* rg, int num_bits) {
+  int diff = (int)rg->tab[rg->index1] - (int)rg->tab[rg->index2];
+  if (diff < 0) diff += (1u << 31);
+  rg->tab[rg->index1] = (uint32_t)diff;
+  if (++rg->index1 == VP8_RANDOM_TABLE_SIZE) rg->index1 = 0;
+  if (++rg->index2 == VP8_RANDOM_TABLE_SIZE) rg->index2 = 0;
+  diff = (int)((uint32_t)diff << 1) >> (32 - num_bits); /* sign-extend, 0-center */
+  diff = (diff * rg->amp) >> VP8_RANDOM_DITHER_FIX;     /* restrict range */
+  diff += 1 << (num_bits - 1);                          /* shift back to 0.5-center */
+  return diff;
+}
+/* the amp and the first n raw values of the generator, for tests of the skip-ahead */
+int orc_vp8_random(float dithering, int num_bits, int n, int32_t* out) {
+  VP8Random rg;
+  VP8InitRandom(&rg, dithering);
+  for (int i = 0; i < n; ++i) out[i] = VP8RandomBits(&rg, num_bits);
+  return rg.amp;
+}
+/* pkg/libwebp/enc/picture_csp_enc.c.go:31-39 */
+static void ConvertRowToY(const uint8_t* r_ptr, const uint8_t* g_ptr, const uint8_t* b_ptr, int step, uint8_t* dst_y,
+                          int width, VP8Random* rg) {
+  for (int i = 0, j = 0; i < width; i += 1, j += step) {
+    dst_y[i] = (uint8_t)orc_RGBToY(r_ptr[j], g_ptr[j], b_ptr[j], VP8RandomBits(rg, YUV_FIX));
+  }
+}
+/* picture_csp_enc.c.go:41-48 */
+static void ConvertRowsToUV(const uint16_t* rgb, uint8_t* dst_u, uint8_t* dst_v, int width, VP8Random* rg) {
+  for (int i = 0; i < width; i += 1, rgb += 4) {
+    const int r = rgb[0], g = rgb[1], b = rgb[2];
+    dst_u[i] = (uint8_t)orc_RGBToU(r, g, b, VP8RandomBits(rg, YUV_FIX + 2));
+    dst_v[i] = (uint8_t)orc_RGBToV(r, g, b, VP8RandomBits(rg, YUV_FIX + 2));
+  }
+}
+/*
+ * pkg/picture/conversions.go:122-165: the dithered copy of the import (dithering > 0,
+ * no iterative conversion).  Same arguments as orc_import_yuva; dst_a of an opaque image
+ * is filled with 0xff as there.  One generator runs through the whole image: two luma
+ * rows, then the chroma row of every row pair (u then v per sample).
+ */
+int orc_import_yuva_dithered(const uint8_t* rgb, int r_off, int g_off, int b_off, int a_off, int step, int rgb_stride,
+                             int width, int height, uint8_t* dst_y, int y_stride, uint8_t* dst_u, uint8_t* dst_v,
+                             int uv_stride, uint8_t* dst_a, int a_stride, int divide_mode, float dithering) {
+  const uint8_t* r_ptr = rgb + r_off;
+  const uint8_t* g_ptr = rgb + g_off;
+  const uint8_t* b_ptr = rgb + b_off;
+  const uint8_t* a_ptr = (a_off >= 0) ? rgb + a_off : NULL;
+  const int uv_width = (width + 1) >> 1;
+  int has_alpha, use_alpha, y;
+  uint16_t* tmp_rgb;
+  VP8Random rg;
+  if (width <= 0 || height <= 0) return -1;
+  if (abs(rgb_stride) < ((a_off >= 0) ? 4 : 3) * width) return -1;
+  if (a_off >= 0 && step != 4) return -1;
+  orc_init();
+  has_alpha = CheckNonOpaque(a_ptr, width, height, step, rgb_stride);
+  use_alpha = has_alpha && dst_a != NULL;
+  tmp_rgb = (uint16_t*)malloc(sizeof(uint16_t) * 4 * uv_width);
+  if (tmp_rgb == NULL) return -1;
+  VP8InitRandom(&rg, dithering);
+  for (y = 0; y < (height >> 1); ++y) {
+    int rows_have_alpha = use_alpha;
+    ConvertRowToY(r_ptr, g_ptr, b_ptr, step, dst_y, width, &rg);
+    ConvertRowToY(r_ptr + rgb_stride, g_ptr + rgb_stride, b_ptr + rgb_stride, step, dst_y + y_stride, width, &rg);
+    dst_y += 2 * y_stride;
+    if (use_alpha) {
+      rows_have_alpha &= !ExtractAlpha(a_ptr, rgb_stride, width, 2, dst_a, a_stride);
+      dst_a += 2 * a_stride;
+    } else if (dst_a != NULL) {
+      for (int i = 0; i < 2; ++i, dst_a += a_stride) memset(dst_a, 0xff, width);
+    }
+    if (!rows_have_alpha) {
+      AccumulateRGB(r_ptr, g_ptr, b_ptr, step, rgb_stride, tmp_rgb, width);
+    } else {
+      AccumulateRGBA(r_ptr, g_ptr, b_ptr, a_ptr, rgb_stride, tmp_rgb, width, divide_mode);
+    }
+    ConvertRowsToUV(tmp_rgb, dst_u, dst_v, uv_width, &rg);
+    dst_u += uv_stride;
+    dst_v += uv_stride;
+    r_ptr += 2 * rgb_stride;
+    b_ptr += 2 * rgb_stride;
+    g_ptr += 2 * rgb_stride;
+    if (use_alpha) a_ptr += 2 * rgb_stride;
+  }
+  if (height & 1) { /* extra last row */
+    int row_has_alpha = use_alpha;
+    ConvertRowToY(r_ptr, g_ptr, b_ptr, step, dst_y, width, &rg);
+    if (row_has_alpha) {
+      row_has_alpha &= !ExtractAlpha(a_ptr, 0, width, 1, dst_a, 0);
+    } else if (dst_a != NULL) {
+      memset(dst_a, 0xff, width);
+    }
+    if (!row_has_alpha) {
+      AccumulateRGB(r_ptr, g_ptr, b_ptr, step, /*rgb_stride=*/0, tmp_rgb, width);
+    } else {
+      AccumulateRGBA(r_ptr, g_ptr, b_ptr, a_ptr, /*rgb_stride=*/0, tmp_rgb, width, divide_mode);
+    }
+    ConvertRowsToUV(tmp_rgb, dst_u, dst_v, uv_width, &rg);
+  }
+  free(tmp_rgb);
+  return has_alpha;
+}
+
 /* yuv.go:74-120 (non-gamma ARGB -> Y / UV rows; row a14). */
 void orc_ConvertARGBToY(const uint32_t* argb, uint8_t* y, int width) {
   int i;

@@ -104,6 +104,39 @@ def gen_import_argb():
     print(f"{n} cases: oracle == libwebp binary for the use_argb import")
 
 
+def gen_dithered():
+    """import_dithered_libwebp160.npz: WebPPictureARGBToYUVADithered (exported by the binary;
+    pkg/picture/conversions.go:122-165 with VP8Random, pkg/vp8/random.go).  Translucent
+    blocks follow the binary's inverse-alpha table (oracle DIV_TABLE)."""
+    rng = np.random.default_rng(11)
+    store, names = {}, []
+    n = 0
+    for (w, h) in [(1, 1), (2, 2), (5, 7), (16, 9), (33, 16), (64, 33), (127, 20), (300, 11)]:
+        for kind in ("opaque", "sparse", "rand"):
+            for d in (0.05, 0.5, 1.0):
+                argb = rng.integers(0, 1 << 32, (h, w), dtype=np.uint32)
+                if kind == "opaque":
+                    argb |= 0xff000000
+                elif kind == "sparse":
+                    argb[rng.random((h, w)) < 0.7] |= 0xff000000
+                y, u, v, a, ha = ref.argb_to_yuva_dithered(argb, d)
+                oy, ou, ov, oa, oha = oracle.import_yuva_dithered(argb.view(np.uint8).reshape(h, 4 * w), w, h, d, "BGRA",
+                                                                  divide_mode=oracle.DIV_TABLE)
+                assert ha == oha and (y == oy).all() and (u == ou).all() and (v == ov).all(), (w, h, kind, d)
+                assert not ha or (a == oa).all()
+                k = f"c{n}"
+                n += 1
+                names.append(k)
+                store[f"{k}/argb"], store[f"{k}/d"], store[f"{k}/y"], store[f"{k}/u"], store[f"{k}/v"] = argb, np.float32(d), y, u, v
+                store[f"{k}/ha"] = np.bool_(ha)
+                if ha:
+                    store[f"{k}/a"] = a
+    store["names"] = np.array(names)
+    np.savez_compressed(os.path.join(HERE, "import_dithered_libwebp160.npz"), **store)
+    print(f"{n} cases: oracle == libwebp binary for the dithered import")
+
+
 if __name__ == "__main__":
     main()
     gen_import_argb()
+    gen_dithered()

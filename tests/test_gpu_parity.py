@@ -812,3 +812,48 @@ def test_picture_tools_and_argb_import_error_behaviour(gpu):
     assert lib.b2_import_to_argb(h, 0, one(cj), 1, abi.ORDER_RGBA, 1) == abi.B2_ERR_BAD_DIM
     ctx.sync()
     buf.free()
+
+
+def test_dithered_import(gpu, golden_dir):
+    """PictureARGBToYUVA with dithering (conversions.go:122-165): the libwebp vectors
+    (binary divide), then seeded pictures vs the oracle in the exact-divide mode: widths
+    over several 128-pixel strips, odd sizes, a last odd row, amp 0, and a mixed-width batch
+    in ONE call (every image runs its own generator, reached by skip-ahead per row pair)."""
+    P = gpu["picture"]
+    g = np.load(os.path.join(golden_dir, "import_dithered_libwebp160.npz"))
+    for k in g["names"]:
+        argb, d = g[f"{k}/argb"], float(g[f"{k}/d"])
+        h, w = argb.shape
+        pic = P.Picture(Width=w, Height=h, UseARGB=True, ARGB=argb.copy(), ARGBStride=w)
+        assert P.PictureARGBToYUVA(pic, P.WEBP_YUV420, d, 0, divide_table=True) is None
+        ha = bool(g[f"{k}/ha"])
+        assert (pic.Y == g[f"{k}/y"]).all() and (pic.U == g[f"{k}/u"]).all() and (pic.V == g[f"{k}/v"]).all(), k
+        assert pic.ColorSpace == (P.WEBP_YUV420A if ha else P.WEBP_YUV420)
+        if ha:
+            assert (pic.A == g[f"{k}/a"]).all(), k
+    rng = np.random.default_rng(4242)
+    sizes = [(1, 1), (3, 5), (128, 2), (129, 3), (257, 8), (640, 7), (1000, 33), (1921, 6), (64, 301)]
+    pics, srcs, exps = [], [], []
+    for i, (w, h) in enumerate(sizes):
+        argb = rng.integers(0, 1 << 32, (h, w), dtype=np.uint32)
+        if i % 3 == 0:
+            argb |= 0xff000000
+        elif i % 3 == 1:
+            argb[rng.random((h, w)) < 0.6] |= 0xff000000
+        d = [0.3, 1.0, 0.004][i % 3]
+        pic = P.Picture(Width=w, Height=h, UseARGB=True, ARGB=argb.copy(), ARGBStride=w)
+        assert P.WebPPictureARGBToYUVADithered(pic, P.WEBP_YUV420, d) is None
+        y, u, v, a, ha = oracle.import_yuva_dithered(argb.view(np.uint8).reshape(h, 4 * w), w, h, d, "BGRA")
+        assert (pic.Y == y).all(), (w, h, d, np.argwhere(pic.Y != y)[:4])
+        assert (pic.U == u).all() and (pic.V == v).all(), (w, h, d)
+        if ha:
+            assert (pic.A == a).all()
+        pics.append(P.Picture(Width=w, Height=h))
+        srcs.append(argb.view(np.uint8).reshape(h, 4 * w))
+        exps.append(oracle.import_yuva_dithered(srcs[-1], w, h, 0.7, "BGRA"))
+    assert P.ImportRGBABatch(pics, srcs, [4 * w for (w, h) in sizes], "BGRA", dithering=0.7) == 1
+    for pic, (y, u, v, a, ha) in zip(pics, exps):
+        assert (pic.Y == y).all() and (pic.U == u).all() and (pic.V == v).all()
+    # 3-byte pixels are outside the dithered path's preconditions
+    pic = P.Picture(Width=8, Height=2)
+    assert P.ImportRGBABatch([pic], [np.zeros((2, 24), np.uint8)], [24], "RGB", dithering=0.5) == 0

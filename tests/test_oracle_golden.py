@@ -229,3 +229,38 @@ def test_import_to_argb_matches_libwebp_binary(golden_dir):
         src, exp, order = g[f"{k}/src"], g[f"{k}/argb"], str(g[f"{k}/order"])
         h, w = exp.shape
         assert (oracle.import_to_argb(src, w, h, order) == exp).all(), (k, order)
+
+
+def test_dithered_import_matches_libwebp_binary(golden_dir):
+    """WebPPictureARGBToYUVADithered (conversions.go:122-165, VP8Random random.go:13-95)."""
+    g = _load(golden_dir, "import_dithered_libwebp160.npz")
+    for k in g["names"]:
+        argb, d = g[f"{k}/argb"], float(g[f"{k}/d"])
+        h, w = argb.shape
+        y, u, v, a, ha = oracle.import_yuva_dithered(argb.view(np.uint8).reshape(h, 4 * w), w, h, d, "BGRA",
+                                                     divide_mode=oracle.DIV_TABLE)
+        assert ha == bool(g[f"{k}/ha"]) and (y == g[f"{k}/y"]).all() and (u == g[f"{k}/u"]).all() and (v == g[f"{k}/v"]).all(), k
+        if ha:
+            assert (a == g[f"{k}/a"]).all(), k
+
+
+def test_vp8_random_is_the_lag_55_24_difference_generator():
+    """What the skip-ahead of the CUDA path rests on: draw n is s_n = s_(n-55) - s_(n-24)
+    mod 2^31 with the table as s_-55 .. s_-1 (random.go:68-84), returned as
+    ((s << 1) >> (32 - bits)) * amp >> 8 + (1 << (bits - 1))."""
+    n = 500
+    got = oracle.vp8_random(1.0, 16, n)
+    tab = [0x0de15230, 0x03b31886, 0x775faccb, 0x1c88626a, 0x68385c55, 0x14b3b828, 0x4a85fef8, 0x49ddb84b,
+           0x64fcf397, 0x5c550289, 0x4a290000, 0x0d7ec1da, 0x5940b7ab, 0x5492577d, 0x4e19ca72, 0x38d38c69,
+           0x0c01ee65, 0x32a1755f, 0x5437f652, 0x5abb2c32, 0x0faa57b1, 0x73f533e7, 0x685feeda, 0x7563cce2,
+           0x6e990e83, 0x4730a7ed, 0x4fc0d9c6, 0x496b153c, 0x4f1403fa, 0x541afb0c, 0x73990b32, 0x26d7cb1c,
+           0x6fcc3706, 0x2cbb77d8, 0x75762f2a, 0x6425ccdd, 0x24b35461, 0x0a7d8715, 0x220414a8, 0x141ebf67,
+           0x56b41583, 0x73e502e3, 0x44cab16f, 0x28264d42, 0x73baaefb, 0x0a50ebed, 0x1d6ab6fb, 0x0d3ad40b,
+           0x35db3b68, 0x2b081e83, 0x77ce6b95, 0x5181e5f0, 0x78853bbc, 0x009f9494, 0x27e5ed3c]
+    s = list(tab)
+    for i in range(n):
+        v = (s[-55] - s[-24]) % (1 << 31)
+        s.append(v)
+        x = (v << 1) & 0xffffffff
+        x = x - (1 << 32) if x & 0x80000000 else x
+        assert got[i] == (((x >> 16) * 256) >> 8) + (1 << 15), i

@@ -43,6 +43,10 @@ if "import" in which:
         p.fill_synthetic(0xB2000001, 0, mode)
         report(f"import {NF}x1080p alpha={name}", NF * 1920 * 1080, 6.5, timed(p.run_device))
         p.close()
+    p = ImportPipeline(ctx, NF, 1920, 1080, host=False)
+    p.fill_synthetic(0xB2000001, 0, 2)
+    report(f"import {NF}x1080p alpha=sparse DITHERED 0.5", NF * 1920 * 1080, 6.5, timed(lambda: p.run_device(0, 0.5)))
+    p.close()
     p = ImportPipeline(ctx, NF, 1920, 1080, import_alpha=False, host=False)
     p.fill_synthetic(0xB2000001, 0, 0)
     report(f"import {NF}x1080p RGBX (A written 0xff)", NF * 1920 * 1080, 6.5, timed(p.run_device))

@@ -10,8 +10,8 @@
 //     s_(n+k) = sum_j c_j s_(n+j),  c = x^k mod (x^55 + x^31 - 1) over Z / 2^31.
 // That is the skip-ahead: the host computes c for k = one row pair's draws (and for k =
 // width, used by the import kernel to reach the second luma row and the chroma row), a
-// small kernel walks every image's row pairs once (one 55 x 55 multiply-accumulate each)
-// and leaves the generator state at the start of every row pair, and the import kernel
+// pair of small kernels walks every image's row pairs (one 55 x 55 multiply-accumulate per
+// jump, two levels) and leaves the generator state at the start of every row pair, and the import kernel
 // regenerates its own draws from that state, 24 values per warp step (the shortest lag).
 #include <stdlib.h>
 #include <string.h>
@@ -68,11 +68,17 @@ namespace {
 
 struct RngTable { uint32_t v[B2_RNG_N]; };
 
-// One warp per image walks the row pairs: state <- jump(state, poly_k), storing the state
-// every row pair STARTS with (the 55 values that precede its first draw).
+// States in two levels, so that an image's ~H/2 serial jumps become H/64 + 32:
+//   level 1: one warp per image jumps kSeg row pairs at a time (poly_seg = x^(kSeg k)) and
+//            leaves the state of every kSeg-th row pair;
+//   level 2: one warp per (image, segment) walks the kSeg row pairs of its segment
+//            (poly_k = x^k), starting from the level-1 state.
+// A state = the 55 values that precede a row pair's first draw.
+constexpr int kSeg = 32;
+
 __global__ void __launch_bounds__(128)
-rng_states_kernel(const ImportJobDev* __restrict__ jobs, const uint32_t* __restrict__ unit_prefix, uint32_t n_jobs,
-                  const uint32_t* __restrict__ poly_k, uint32_t* __restrict__ states, const RngTable table) {
+rng_states_l1_kernel(const ImportJobDev* __restrict__ jobs, const uint32_t* __restrict__ unit_prefix, uint32_t n_jobs,
+                     const uint32_t* __restrict__ poly_seg, uint32_t* __restrict__ states, const RngTable table) {
   __shared__ uint32_t ext_all[4][2 * B2_RNG_N], c_all[4][B2_RNG_N];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t img = blockIdx.x * 4 + warp;
@@ -80,25 +86,57 @@ rng_states_kernel(const ImportJobDev* __restrict__ jobs, const uint32_t* __restr
   uint32_t* ext = ext_all[warp];
   uint32_t* c = c_all[warp];
   for (int i = lane; i < B2_RNG_N; i += 32) {
-    c[i] = poly_k[(size_t)img * B2_RNG_N + i];
+    c[i] = poly_seg[(size_t)img * B2_RNG_N + i];
     ext[i] = table.v[i];
   }
   __syncwarp();
   const uint32_t units = (uint32_t)((jobs[img].height + 1) >> 1);
   uint32_t* out = states + (size_t)unit_prefix[img] * B2_RNG_N;
-  for (uint32_t r = 0; r < units; ++r) {
+  for (uint32_t r = 0; r < units; r += kSeg) {
     for (int i = lane; i < B2_RNG_N; i += 32) out[(size_t)r * B2_RNG_N + i] = ext[i];
-    if (r + 1 == units) break;
+    if (r + kSeg >= units) break;
     b2_rng_jump_warp(ext, c, lane);
+  }
+}
+
+// grid.x = segments of the tallest image, grid.y = image / 4
+__global__ void __launch_bounds__(128)
+rng_states_l2_kernel(const ImportJobDev* __restrict__ jobs, const uint32_t* __restrict__ unit_prefix, uint32_t n_jobs,
+                     const uint32_t* __restrict__ poly_k, uint32_t* __restrict__ states) {
+  __shared__ uint32_t ext_all[4][2 * B2_RNG_N], c_all[4][B2_RNG_N];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t img = blockIdx.y * 4 + warp;
+  if (img >= n_jobs) return;
+  const uint32_t units = (uint32_t)((jobs[img].height + 1) >> 1);
+  const uint32_t r0 = blockIdx.x * kSeg;
+  if (r0 >= units) return;
+  uint32_t* ext = ext_all[warp];
+  uint32_t* c = c_all[warp];
+  uint32_t* out = states + (size_t)unit_prefix[img] * B2_RNG_N;
+  for (int i = lane; i < B2_RNG_N; i += 32) {
+    c[i] = poly_k[(size_t)img * B2_RNG_N + i];
+    ext[i] = out[(size_t)r0 * B2_RNG_N + i];
+  }
+  __syncwarp();
+  const uint32_t r1 = min(r0 + kSeg, units);
+  for (uint32_t r = r0 + 1; r < r1; ++r) {
+    b2_rng_jump_warp(ext, c, lane);
+    for (int i = lane; i < B2_RNG_N; i += 32) out[(size_t)r * B2_RNG_N + i] = ext[i];
   }
 }
 
 }  // namespace
 
+int b2_rng_segment_row_pairs() { return kSeg; }
+
 cudaError_t b2_rng_states_launch(cudaStream_t s, const ImportJobDev* jobs, const uint32_t* unit_prefix, uint32_t n_jobs,
-                                 const uint32_t* poly_k, uint32_t* states) {
+                                 const uint32_t* poly_k, const uint32_t* poly_seg, uint32_t max_units, uint32_t* states) {
   RngTable t;
   memcpy(t.v, kRandomTable, sizeof(t.v));
-  rng_states_kernel<<<(n_jobs + 3) / 4, 128, 0, s>>>(jobs, unit_prefix, n_jobs, poly_k, states, t);
+  rng_states_l1_kernel<<<(n_jobs + 3) / 4, 128, 0, s>>>(jobs, unit_prefix, n_jobs, poly_seg, states, t);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const dim3 grid((max_units + kSeg - 1) / kSeg, (n_jobs + 3) / 4);
+  rng_states_l2_kernel<<<grid, 128, 0, s>>>(jobs, unit_prefix, n_jobs, poly_k, states);
   return cudaGetLastError();
 }

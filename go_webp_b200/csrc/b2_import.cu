@@ -379,32 +379,40 @@ static int import_impl(b2_ctx* ctx, int stream, const b2_import_job* jobs, int n
     // (4-byte pixels, 4-byte aligned rows and planes), which PictureARGBToYUVA always meets.
     if (!tuned) return B2_ERR_INVALID_CONFIG;
     const size_t poly_bytes = sizeof(uint32_t) * B2_RNG_N * (size_t)n_jobs;
-    if (2 * poly_bytes > B2_DESC_RING_BYTES) return B2_ERR_INVALID_CONFIG;
-    uint32_t* polys = (uint32_t*)malloc(2 * poly_bytes);
+    if (3 * poly_bytes > B2_DESC_RING_BYTES) return B2_ERR_INVALID_CONFIG;
+    uint32_t* polys = (uint32_t*)malloc(3 * poly_bytes);
     if (polys == NULL) return B2_ERR_OOM;
     int last_w = -1, last_i = 0;
+    uint32_t max_units = 0;
     for (int i = 0; i < n_jobs; ++i) {
       uint32_t* pk = polys + (size_t)i * B2_RNG_N;
       uint32_t* pw = polys + (size_t)(n_jobs + i) * B2_RNG_N;
+      uint32_t* ps = polys + (size_t)(2 * n_jobs + i) * B2_RNG_N;
+      const uint32_t units_i = (uint32_t)((jobs[i].height + 1) >> 1);
+      if (units_i > max_units) max_units = units_i;
       if (jobs[i].width == last_w) {   // batches are mostly of one size
         memcpy(pk, polys + (size_t)last_i * B2_RNG_N, sizeof(uint32_t) * B2_RNG_N);
         memcpy(pw, polys + (size_t)(n_jobs + last_i) * B2_RNG_N, sizeof(uint32_t) * B2_RNG_N);
+        memcpy(ps, polys + (size_t)(2 * n_jobs + last_i) * B2_RNG_N, sizeof(uint32_t) * B2_RNG_N);
         continue;
       }
       const uint64_t w = (uint64_t)jobs[i].width;
-      b2_rng_jump_poly(2 * w + 2 * ((w + 1) >> 1), pk);   // draws of one row pair
-      b2_rng_jump_poly(w, pw);                            // draws of one luma row
+      const uint64_t k = 2 * w + 2 * ((w + 1) >> 1);
+      b2_rng_jump_poly(k, pk);                                       // draws of one row pair
+      b2_rng_jump_poly(w, pw);                                       // draws of one luma row
+      b2_rng_jump_poly(k * (uint64_t)b2_rng_segment_row_pairs(), ps);  // draws of one segment of row pairs
       last_w = jobs[i].width; last_i = i;
     }
     void* pdev = NULL;
-    st = b2_upload_desc(ctx, stream, polys, 2 * poly_bytes, &pdev);
+    st = b2_upload_desc(ctx, stream, polys, 3 * poly_bytes, &pdev);
     free(polys);
     if (st != B2_OK) return st;
     void* states = NULL;
     st = b2_stream_scratch(ctx, stream, sizeof(uint32_t) * B2_RNG_N * (size_t)utotal, &states);
     if (st != B2_OK) return st;
-    B2_CUDA(ctx, b2_rng_states_launch(s, djobs, dupre, (uint32_t)n_jobs, (const uint32_t*)pdev, (uint32_t*)states));
-    ctx->launches++;
+    B2_CUDA(ctx, b2_rng_states_launch(s, djobs, dupre, (uint32_t)n_jobs, (const uint32_t*)pdev,
+                                      (const uint32_t*)pdev + 2 * (size_t)n_jobs * B2_RNG_N, max_units, (uint32_t*)states));
+    ctx->launches += 2;
     dither.rng_states = (const uint32_t*)states;
     dither.rng_poly_w = (const uint32_t*)pdev + (size_t)n_jobs * B2_RNG_N;
     dither.amp = amp;

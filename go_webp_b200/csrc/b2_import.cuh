@@ -38,8 +38,10 @@ cudaError_t b2_import_fast_launch(const b2_ctx* ctx, cudaStream_t s, const Impor
 void b2_rng_jump_poly(uint64_t k, uint32_t* c);
 int b2_rng_amp(float dithering);
 // states[(unit_prefix[img] + r) * 55 ..] = generator window at the start of row pair r
+// poly_k = x^k (k = draws of one row pair), poly_seg = x^(k * b2_rng_segment_row_pairs())
+int b2_rng_segment_row_pairs();
 cudaError_t b2_rng_states_launch(cudaStream_t s, const ImportJobDev* jobs, const uint32_t* unit_prefix, uint32_t n_jobs,
-                                 const uint32_t* poly_k, uint32_t* states);
+                                 const uint32_t* poly_k, const uint32_t* poly_seg, uint32_t max_units, uint32_t* states);
 #ifdef __CUDACC__
 // Warp-level skip-ahead.  ext[0..54] = the 55 values preceding the next draw (room for
 // 110 words); c = x^k mod P.  On return ext[0..54] is the same window k draws later.

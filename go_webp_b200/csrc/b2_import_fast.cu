@@ -141,9 +141,10 @@ __device__ __forceinline__ uint32_t v_sum(int r, int g, int b, uint32_t rnd = 1u
 // VP8RandomBits2 (pkg/vp8/random.go:68-95) on a raw 31-bit draw
 template <int NUM_BITS>
 __device__ __forceinline__ uint32_t dither_value(uint32_t raw, int amp) {
-  int diff = (int)(raw << 1) >> (32 - NUM_BITS);   // sign-extend, 0-center
-  diff = (diff * amp) >> 8;                          // restrict range
-  return (uint32_t)(diff + (1 << (NUM_BITS - 1)));   // shift back to 0.5-center
+  int diff;                                          // sign-extend, 0-center: bits 30 .. 31-NUM_BITS of raw
+  asm("bfe.s32 %0, %1, %2, %3;" : "=r"(diff) : "r"(raw), "n"(31 - NUM_BITS), "n"(NUM_BITS));
+  // restrict range and shift back to 0.5-center: floor(x / 256) + c == floor((x + 256 c) / 256)
+  return (uint32_t)((diff * amp + (1 << (NUM_BITS - 1 + 8))) >> 8);
 }
 constexpr uint32_t kDitherWarpBytes = 3 * 1024;     // three 256-entry rings of raw draws per warp
 static_assert(kSmemBytes + kFastWarps * (int)kDitherWarpBytes <= 232448 && kSmemBytes % 16 == 0 && kSplit == 1,

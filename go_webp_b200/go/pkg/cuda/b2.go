@@ -528,3 +528,52 @@ func (c *Context) ImportRGBADithered(stream int, jobs []ImportJob, order, flags 
 	return status(c, C.b2_rgba_to_yuv420a_dithered(c.h, C.int(stream), &cj[0], C.int(len(cj)), C.int(order), C.int(flags),
 		(*C.int32_t)(unsafe.Pointer(uintptr(hasAlpha))), C.float(dithering)))
 }
+
+// AnimBlendJob is one rectangle of the animation decoder's canvas blend
+// (include/b2webp.h b2_anim_blend_job); strides in pixels.
+type AnimBlendJob struct {
+	Src, Dst             DevicePtr
+	SrcStride, DstStride int
+	Width, Height        int
+}
+
+// AnimBlendRows replaces BlendPixelRowNonPremult / BlendPixelRowPremult
+// (pkg/libwebp/demux/anim_decode.go:234-270) over whole rectangles.
+func (c *Context) AnimBlendRows(stream int, jobs []AnimBlendJob, premultiplied bool) error {
+	if len(jobs) == 0 {
+		return nil
+	}
+	cj := make([]C.b2_anim_blend_job, len(jobs))
+	for i, j := range jobs {
+		cj[i] = C.b2_anim_blend_job{
+			src: (*C.uint32_t)(unsafe.Pointer(uintptr(j.Src))), dst: (*C.uint32_t)(unsafe.Pointer(uintptr(j.Dst))),
+			src_stride: C.int32_t(j.SrcStride), dst_stride: C.int32_t(j.DstStride),
+			width: C.int32_t(j.Width), height: C.int32_t(j.Height),
+		}
+	}
+	return status(c, C.b2_anim_blend_rows(c.h, C.int(stream), &cj[0], C.int(len(cj)), boolInt(premultiplied)))
+}
+
+// AnimCompareJob is one row or column scan of the animation encoder's frame comparison.
+type AnimCompareJob struct {
+	Src, Dst         DevicePtr
+	SrcStep, DstStep int
+	Length           int
+}
+
+// AnimComparePixels replaces ComparePixelsLossless / ComparePixelsLossy
+// (pkg/libwebp/mux/anim_encode.go:318-367); result addresses int32[len(jobs)] on the device.
+func (c *Context) AnimComparePixels(stream int, jobs []AnimCompareJob, lossless bool, maxAllowedDiff int, result DevicePtr) error {
+	if len(jobs) == 0 {
+		return nil
+	}
+	cj := make([]C.b2_anim_compare_job, len(jobs))
+	for i, j := range jobs {
+		cj[i] = C.b2_anim_compare_job{
+			src: (*C.uint32_t)(unsafe.Pointer(uintptr(j.Src))), dst: (*C.uint32_t)(unsafe.Pointer(uintptr(j.Dst))),
+			src_step: C.int32_t(j.SrcStep), dst_step: C.int32_t(j.DstStep), length: C.int32_t(j.Length),
+		}
+	}
+	return status(c, C.b2_anim_compare_pixels(c.h, C.int(stream), &cj[0], C.int(len(cj)), boolInt(lossless),
+		C.int(maxAllowedDiff), (*C.int32_t)(unsafe.Pointer(uintptr(result)))))
+}

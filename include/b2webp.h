@@ -344,6 +344,34 @@ int b2_picture_blend_alpha(b2_ctx* ctx, int stream, const b2_picture_job* jobs, 
  * color & 0xffffff. */
 int b2_picture_replace_transparent(b2_ctx* ctx, int stream, const b2_picture_job* jobs, int n_jobs, uint32_t color);
 
+/* ---- next rows: animation pixel work --------------------------------
+ * Canvas blending of the animation decoder: BlendPixelRowNonPremult / BlendPixelRowPremult
+ * (pkg/libwebp/demux/anim_decode.go:195-270) over a rectangle: src (the frame just
+ * decoded into the canvas) is blended IN PLACE over dst (the previous canvas) wherever its
+ * alpha is not 0xff.  Strides in pixels.  Which rectangle to blend is the caller's
+ * decision (FindBlendRangeAtRow, anim_decode.go:272-300). */
+typedef struct b2_anim_blend_job {
+  uint32_t* src;
+  const uint32_t* dst;
+  int32_t src_stride, dst_stride;
+  int32_t width, height;
+} b2_anim_blend_job;
+int b2_anim_blend_rows(b2_ctx* ctx, int stream, const b2_anim_blend_job* jobs, int n_jobs, int premultiplied);
+
+/* Frame comparison of the animation encoder: ComparePixelsLossless / ComparePixelsLossy
+ * (pkg/libwebp/mux/anim_encode.go:318-367): result_dev[i] = 1 iff all `length` pixel pairs
+ * of job i, `src_step` / `dst_step` pixels apart, are equal (lossless) or similar within
+ * max_allowed_diff (PixelsAreSimilar :336-351).  length > 0. */
+typedef struct b2_anim_compare_job {
+  const uint32_t* src;
+  const uint32_t* dst;
+  int32_t src_step, dst_step;
+  int32_t length;
+  int32_t reserved;
+} b2_anim_compare_job;
+int b2_anim_compare_pixels(b2_ctx* ctx, int stream, const b2_anim_compare_job* jobs, int n_jobs, int lossless,
+                           int max_allowed_diff, int32_t* result_dev);
+
 /* ---- synthetic inputs (SURVEY.md 8d generator, identical to the oracle's) -
  * One uint32 per (row, word) position of n images laid out 'image_bytes'
  * apart, image ids first_img, first_img+1, ...  alpha_mode shapes the top byte

@@ -396,3 +396,21 @@ def vp8_random(dithering: float, num_bits: int, n: int):
     out = np.zeros(n, np.int32)
     lib().orc_vp8_random(C.c_float(dithering), num_bits, n, _p(out))
     return out
+
+
+# ---- animation (oracle_tools.c) ---------------------------------------
+def anim_blend_rows(src, dst, premult):
+    """BlendPixelRowNonPremult / Premult of every row of src over dst -> new src."""
+    src = np.array(src, np.uint32, order="C")
+    dst = np.ascontiguousarray(dst, np.uint32)
+    h, w = src.shape
+    lib().orc_anim_blend_rows(_p(src), w, _p(dst), w, w, h, int(premult))
+    return src
+
+
+def compare_pixels(src, src_step, dst, dst_step, length, lossless=True, max_allowed_diff=0):
+    src = np.ascontiguousarray(src, np.uint32)
+    dst = np.ascontiguousarray(dst, np.uint32)
+    if lossless:
+        return int(lib().orc_compare_pixels_lossless(_p(src), src_step, _p(dst), dst_step, length))
+    return int(lib().orc_compare_pixels_lossy(_p(src), src_step, _p(dst), dst_step, length, max_allowed_diff))

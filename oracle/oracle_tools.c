@@ -9,6 +9,7 @@
  * go-webp tree.
  */
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 /* pkg/libwebp/enc/picture_tools_enc.c.go:29-30 */
@@ -246,6 +247,81 @@ int orc_import_to_argb(const uint8_t* rgb, int rgb_stride, int step, int swap_rb
     }
     rgb += rgb_stride;
     dst += dst_stride;
+  }
+  return 1;
+}
+
+/* ---- animation: canvas blending and frame comparison ------------------ */
+/* pkg/libwebp/demux/anim_decode.go:195-203.  Pixels are uint32 with alpha in bits 24-31
+ * (CHANNEL_SHIFT(3) on little endian); the three colour channels are treated alike. */
+static uint8_t BlendChannelNonPremult(uint32_t src, uint8_t src_a, uint32_t dst, uint8_t dst_a, uint32_t scale, int shift) {
+  const uint8_t src_channel = (src >> shift) & 0xff;
+  const uint8_t dst_channel = (dst >> shift) & 0xff;
+  const uint32_t blend_unscaled = src_channel * src_a + dst_channel * dst_a;
+  return (uint8_t)((blend_unscaled * scale) >> 24);
+}
+/* anim_decode.go:205-232 */
+static uint32_t BlendPixelNonPremult(uint32_t src, uint32_t dst) {
+  const uint8_t src_a = (src >> 24) & 0xff;
+  if (src_a == 0) {
+    return dst;
+  } else {
+    const uint8_t dst_a = (dst >> 24) & 0xff;
+    const uint8_t dst_factor_a = (uint8_t)((dst_a * (256 - src_a)) >> 8);
+    const uint8_t blend_a = (uint8_t)(src_a + dst_factor_a);
+    const uint32_t scale = (1u << 24) / blend_a;
+    const uint8_t blend_r = BlendChannelNonPremult(src, src_a, dst, dst_factor_a, scale, 0);
+    const uint8_t blend_g = BlendChannelNonPremult(src, src_a, dst, dst_factor_a, scale, 8);
+    const uint8_t blend_b = BlendChannelNonPremult(src, src_a, dst, dst_factor_a, scale, 16);
+    return ((uint32_t)blend_r << 0) | ((uint32_t)blend_g << 8) | ((uint32_t)blend_b << 16) | ((uint32_t)blend_a << 24);
+  }
+}
+/* anim_decode.go:245-257 */
+static uint32_t ChannelwiseMultiply(uint32_t pix, uint32_t scale) {
+  const uint32_t mask = 0x00FF00FF;
+  const uint32_t rb = ((pix & mask) * scale) >> 8;
+  const uint32_t ag = ((pix >> 8) & mask) * scale;
+  return (rb & mask) | (ag & ~mask);
+}
+static uint32_t BlendPixelPremult(uint32_t src, uint32_t dst) {
+  const uint8_t src_a = (src >> 24) & 0xff;
+  return src + ChannelwiseMultiply(dst, 256 - src_a);
+}
+/* BlendPixelRowNonPremult / BlendPixelRowPremult (anim_decode.go:234-243, 259-270) over
+ * `rows` rows; strides in pixels.  src is blended in place over dst. */
+void orc_anim_blend_rows(uint32_t* src, int src_stride, const uint32_t* dst, int dst_stride, int width, int rows, int premult) {
+  for (int y = 0; y < rows; ++y) {
+    for (int i = 0; i < width; ++i) {
+      const uint8_t src_alpha = (src[i] >> 24) & 0xff;
+      if (src_alpha != 0xff) src[i] = premult ? BlendPixelPremult(src[i], dst[i]) : BlendPixelNonPremult(src[i], dst[i]);
+    }
+    src += src_stride;
+    dst += dst_stride;
+  }
+}
+/* pkg/libwebp/mux/anim_encode.go:318-332 */
+int orc_compare_pixels_lossless(const uint32_t* src, int src_step, const uint32_t* dst, int dst_step, int length) {
+  while (length-- > 0) {
+    if (*src != *dst) return 0;
+    src += src_step;
+    dst += dst_step;
+  }
+  return 1;
+}
+/* anim_encode.go:336-351 */
+static int PixelsAreSimilar(uint32_t src, uint32_t dst, int max_allowed_diff) {
+  const int src_a = (src >> 24) & 0xff, src_r = (src >> 16) & 0xff, src_g = (src >> 8) & 0xff, src_b = src & 0xff;
+  const int dst_a = (dst >> 24) & 0xff, dst_r = (dst >> 16) & 0xff, dst_g = (dst >> 8) & 0xff, dst_b = dst & 0xff;
+  return (src_a == dst_a) && (abs(src_r - dst_r) * dst_a <= (max_allowed_diff * 255)) &&
+         (abs(src_g - dst_g) * dst_a <= (max_allowed_diff * 255)) && (abs(src_b - dst_b) * dst_a <= (max_allowed_diff * 255));
+}
+/* anim_encode.go:355-367 */
+int orc_compare_pixels_lossy(const uint32_t* src, int src_step, const uint32_t* dst, int dst_step, int length,
+                             int max_allowed_diff) {
+  while (length-- > 0) {
+    if (!PixelsAreSimilar(*src, *dst, max_allowed_diff)) return 0;
+    src += src_step;
+    dst += dst_step;
   }
   return 1;
 }

@@ -857,3 +857,41 @@ def test_dithered_import(gpu, golden_dir):
     # 3-byte pixels are outside the dithered path's preconditions
     pic = P.Picture(Width=8, Height=2)
     assert P.ImportRGBABatch([pic], [np.zeros((2, 24), np.uint8)], [24], "RGB", dithering=0.5) == 0
+
+
+def test_anim_blend_and_compare(gpu, golden_dir):
+    """Animation pixel work: the WebPAnimDecoder vectors through
+    BlendRowsBatch (both blends in one batch each), seeded canvases vs the oracle, the row
+    functions, and ComparePixels{Lossless,Lossy} over rows and columns vs the oracle."""
+    from go_webp_b200 import anim
+    g = np.load(os.path.join(golden_dir, "anim_libwebp160.npz"))
+    for premult in (0, 1):
+        ks = [str(k) for k in g["names"] if int(g[f"{k}/premult"]) == premult]
+        outs = anim.BlendRowsBatch([g[f"{k}/src"] for k in ks], [g[f"{k}/dst"] for k in ks], bool(premult))
+        for k, o in zip(ks, outs):
+            assert (o == g[f"{k}/exp"]).all(), k
+    rng = np.random.default_rng(909)
+    for (w, h) in [(1, 1), (5, 3), (130, 9), (1027, 4), (2500, 3)]:
+        src = rng.integers(0, 1 << 32, (h, w), dtype=np.uint32)
+        dst = rng.integers(0, 1 << 32, (h, w), dtype=np.uint32)
+        src[rng.random((h, w)) < 0.3] |= 0xff000000
+        src[rng.random((h, w)) < 0.2] &= 0x00ffffff
+        for premult in (False, True):
+            o = anim.BlendRowsBatch([src], [dst], premult)[0]
+            assert (o == oracle.anim_blend_rows(src, dst, int(premult))).all(), (w, h, premult)
+    row, prev = src[0].copy(), dst[0].copy()
+    anim.BlendPixelRowNonPremult(row, prev, w - 1)
+    exp = oracle.anim_blend_rows(src[:1, :w - 1], dst[:1, :w - 1], 0)[0]
+    assert (row[:w - 1] == exp).all() and row[w - 1] == src[0, w - 1]
+    # frame comparison: rows and columns of a 64 x 48 pair of frames that differ in a rectangle
+    W, H = 64, 48
+    a = rng.integers(0, 1 << 32, (H, W), dtype=np.uint32)
+    b = a.copy()
+    b[10:20, 30:40] ^= rng.integers(0, 8, (10, 10), dtype=np.uint32) << 8     # small green differences
+    runs = [(y * W, 1, y * W, 1, W) for y in range(H)] + [(x, W, x, W, H) for x in range(W)]
+    for lossless, diff in ((True, 0), (False, 0), (False, 3), (False, 255)):
+        got = anim.ComparePixelsBatch(a, b, runs, lossless, diff)
+        exp = [oracle.compare_pixels(a.reshape(-1)[so:], ss, b.reshape(-1)[do:], ds, ln, lossless, diff) for (so, ss, do, ds, ln) in runs]
+        assert got == exp, (lossless, diff)
+    assert anim.ComparePixelsLossless(a[0], 1, a[0].copy(), 1, W) == 1
+    assert anim.ComparePixelsLossy(a[12], 1, b[12], 1, W, 0) == oracle.compare_pixels(a[12], 1, b[12], 1, W, False, 0)

@@ -264,3 +264,30 @@ def test_vp8_random_is_the_lag_55_24_difference_generator():
         x = (v << 1) & 0xffffffff
         x = x - (1 << 32) if x & 0x80000000 else x
         assert got[i] == (((x >> 16) * 256) >> 8) + (1 << 15), i
+
+
+def test_anim_blend_matches_libwebp_anim_decoder(golden_dir):
+    """BlendPixelRowNonPremult / Premult (anim_decode.go:195-270) vs WebPAnimDecoder."""
+    g = _load(golden_dir, "anim_libwebp160.npz")
+    n = 0
+    for k in g["names"]:
+        got = oracle.anim_blend_rows(g[f"{k}/src"], g[f"{k}/dst"], int(g[f"{k}/premult"]))
+        assert (got == g[f"{k}/exp"]).all(), k
+        n += 1
+    assert n >= 40
+
+
+def test_compare_pixels_known_answers():
+    """ComparePixelsLossless / Lossy (anim_encode.go:318-367)."""
+    a = np.array([0xff102030, 0x80112233, 0x00000000, 0xff000000], np.uint32)
+    assert oracle.compare_pixels(a, 1, a.copy(), 1, 4) == 1
+    b = a.copy(); b[2] = 0x00010000
+    assert oracle.compare_pixels(a, 1, b, 1, 4) == 0
+    assert oracle.compare_pixels(a, 2, b, 2, 2) == 0 and oracle.compare_pixels(a, 1, b, 1, 2) == 1
+    # lossy: alpha must match; colour differences are weighted by dst alpha
+    assert oracle.compare_pixels(a, 1, b, 1, 4, lossless=False, max_allowed_diff=0) == 1   # dst alpha 0: any colour is similar
+    c = a.copy(); c[0] = 0xff122030
+    assert oracle.compare_pixels(a, 1, c, 1, 4, lossless=False, max_allowed_diff=1) == 0
+    assert oracle.compare_pixels(a, 1, c, 1, 4, lossless=False, max_allowed_diff=2) == 1
+    d = a.copy(); d[1] = 0x81112233
+    assert oracle.compare_pixels(a, 1, d, 1, 4, lossless=False, max_allowed_diff=255) == 0

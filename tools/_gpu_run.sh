@@ -1,2 +1,1 @@
-which compute-sanitizer || ls /usr/local/cuda/bin | grep -i sanit
-timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 7 --print-limit 20 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "dithered or picture_tools or import_tuned or predictor or import_to_argb or vp8l_golden or upsample_size" > gpurun_out/memcheck_r1f.log 2>&1; echo "memcheck rc=$?"; tail -12 gpurun_out/memcheck_r1f.log
+timeout 600 python -m pytest tests -m gpu -x -q -k "anim" 2>&1 | tail -12

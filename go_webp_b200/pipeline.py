@@ -27,7 +27,7 @@ def _al(n: int, a: int = 256) -> int:
 
 class ImportPipeline:
     def __init__(self, ctx: Context, n: int, width: int, height: int, order: str = "RGBA",
-                 import_alpha: bool = True, divide_table: bool = False, chunk: int = 16,
+                 import_alpha: bool = True, divide_table: bool = False, chunk: int = 8,
                  host: bool = True):
         self.ctx, self.n, self.w, self.h = ctx, n, width, height
         self.order = {"RGBA": _abi.ORDER_RGBA, "BGRA": _abi.ORDER_BGRA}[order]

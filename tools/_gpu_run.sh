@@ -1,1 +1,1 @@
-timeout 600 python -m pytest tests -m gpu -x -q -k "anim" 2>&1 | tail -12
+timeout 600 python tools/_e2e_probe.py 2>&1 | tail -14

@@ -122,7 +122,7 @@ __device__ __forceinline__ void pixel_generic(const UpsampleJobDev& j, int r, in
   else if (ST == ST_ARGB) { d += 4 * x; d[0] = alpha; d[1] = R; d[2] = G; d[3] = B; }
   else if (ST == ST_RGB) { d += 3 * x; d[0] = R; d[1] = G; d[2] = B; }
   else if (ST == ST_BGR) { d += 3 * x; d[0] = B; d[1] = G; d[2] = R; }
-  else if (ST == ST_4444) { d += 2 * x; d[0] = (R & 0xf0) | (G >> 4); d[1] = (B & 0xf0) | 0x0f; }
+  else if (ST == ST_4444) { d += 2 * x; d[0] = (R & 0xf0) | (G >> 4); d[1] = (B & 0xf0) | (alpha >> 4); }  // EmitAlphaRGBA4444, io_dec.c.go:197-226
   else { d += 2 * x; d[0] = (R & 0xf8) | (G >> 5); d[1] = ((G << 3) & 0xe0) | (B >> 3); }
 }
 

@@ -365,7 +365,7 @@ def YUVAToRGBABatch(pics, mode: int = _abi.MODE_BGRA, dsts=None, ctx: Context | 
         w, h = pic.Width, pic.Height
         uvw, uvh = (w + 1) >> 1, (h + 1) >> 1
         ys, uvs, ds = _al(w, 16), _al(uvw, 16), _al(w * bpp, 16)
-        has_a = bool(pic.ColorSpace & WEBP_CSP_ALPHA_BIT) and bpp == 4
+        has_a = bool(pic.ColorSpace & WEBP_CSP_ALPHA_BIT) and (bpp == 4 or mode in (_abi.MODE_RGBA_4444, _abi.MODE_rgbA_4444))
         sz = dict(y=_al(ys * h), u=_al(uvs * uvh), v=_al(uvs * uvh), a=_al(ys * h) if has_a else 0, d=_al(ds * h))
         metas.append((w, h, uvw, uvh, ys, uvs, ds, has_a, sz))
         need += sum(sz.values())
@@ -423,7 +423,8 @@ def EmitFancyRGB(pic: Picture, mode: int, mb_y: int, mb_h: int, dst: np.ndarray,
         return 0
     uvw, uvh = (w + 1) >> 1, (h + 1) >> 1
     ys, uvs, ds = _al(w, 16), _al(uvw, 16), _al(w * bpp, 16)
-    has_a = bool(pic.ColorSpace & WEBP_CSP_ALPHA_BIT) and bpp == 4 and pic.A is not None
+    has_a = bool(pic.ColorSpace & WEBP_CSP_ALPHA_BIT) and (bpp == 4 or mode in (_abi.MODE_RGBA_4444, _abi.MODE_rgbA_4444)) \
+        and pic.A is not None
     sz = dict(y=_al(ys * h), u=_al(uvs * uvh), v=_al(uvs * uvh), a=_al(ys * h) if has_a else 0, d=_al(ds * h))
     ar = _arena(ctx)
     ar.reset(sum(sz.values()))

@@ -714,6 +714,20 @@ int orc_yuva_to_rgba(int mode, const uint8_t* y, int y_stride,
     const int alpha_first = (mode == MODE_ARGB || mode == MODE_Argb);
     DispatchAlpha(a, a_stride, width, height, dst + (alpha_first ? 0 : 3),
                   dst_stride);
+  } else if (a != NULL && (mode == MODE_RGBA_4444 || mode == MODE_rgbA_4444)) {
+    /* EmitAlphaRGBA4444, pkg/libwebp/decoder/io_dec.c.go:197-226 (without the
+     * premultiply, like the 4-byte modes here): the alpha nibble of the pixel takes
+     * alpha >> 4.  The 4444 writers of this path keep the upstream default byte order
+     * (rg byte first, ba byte second: what the libwebp binary pins), so the nibble is in
+     * byte 1; the Go text shows the WEBP_SWAP_16BIT_CSP build, where it is byte 0. */
+    int i, j;
+    for (j = 0; j < height; ++j) {
+      uint8_t* const alpha_dst = dst + (ptrdiff_t)j * dst_stride + 1;
+      for (i = 0; i < width; ++i) {
+        const uint32_t alpha_value = a[(ptrdiff_t)j * a_stride + i] >> 4;
+        alpha_dst[2 * i] = (uint8_t)((alpha_dst[2 * i] & 0xf0) | alpha_value);
+      }
+    }
   }
   return 1;
 }

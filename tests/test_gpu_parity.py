@@ -210,10 +210,6 @@ def test_decoder_golden_all_modes(gpu, golden_dir):
                             ColorSpace=P.WEBP_YUV420A if a.size else P.WEBP_YUV420)
             got = P.YUVAToRGBABatch([pic], mode)[0]
             exp = g[f"c{i}_m{mode}"]
-            if mode == 5 and a.size:
-                got, exp = got.copy(), exp.copy()
-                got[:, 1::2] |= 0x0f
-                exp[:, 1::2] |= 0x0f
             assert (got == exp).all(), (i, mode)
 
 

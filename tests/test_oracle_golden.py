@@ -95,7 +95,8 @@ def test_upsample_matches_libwebp_binary(golden_dir):
 def test_decoder_output_modes_match_libwebp_binary(golden_dir):
     """Pins the per-pixel writers the Go tree leaves undefined
     (pkg/libwebp/dsp/upsampling.c.go:107-114) and the alpha dispatch
-    (pkg/libwebp/decoder/io_dec.c.go:175-195) through real lossy files."""
+    (pkg/libwebp/decoder/io_dec.c.go:175-195; EmitAlphaRGBA4444 :197-226 for mode 5)
+    through real lossy files."""
     g = _load(golden_dir, "decode_libwebp160.npz")
     n = int(g["n"][0])
     for i in range(n):
@@ -106,10 +107,6 @@ def test_decoder_output_modes_match_libwebp_binary(golden_dir):
             exp = g[k + f"_m{mode}"]
             got = oracle.yuva_to_rgba(g[k + "_y"], g[k + "_u"], g[k + "_v"], a,
                                       mode=mode)
-            if mode == oracle.MODE_RGBA_4444 and a is not None:
-                # alpha nibble comes from EmitAlphaRGBA4444 (8f-2, not on the path)
-                exp = exp.copy(); got = got.copy()
-                exp[:, 1::2] |= 0x0f; got[:, 1::2] |= 0x0f
             assert (got == exp).all(), (i, mode)
 
 

@@ -1,1 +1,1 @@
-timeout 600 python tools/_e2e_probe.py 2>&1 | tail -14
+timeout 600 python -m pytest tests -m gpu -x -q -k "decoder_golden or upsample" 2>&1 | tail -8

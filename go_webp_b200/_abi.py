@@ -82,6 +82,11 @@ class AnimCompareJob(C.Structure):
                 ("length", C.c_int32), ("reserved", C.c_int32)]
 
 
+class AlphaFilterJob(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("src_stride", C.c_int32), ("dst_stride", C.c_int32),
+                ("width", C.c_int32), ("height", C.c_int32), ("filter", C.c_int32), ("reserved", C.c_int32)]
+
+
 CONVERT_UPSTREAM_16BIT = 1
 ALPHA_APPLY, ALPHA_APPLY_4444, ALPHA_MULT_ARGB, ALPHA_MULT_ROW = 0, 1, 2, 3
 
@@ -132,6 +137,8 @@ SYMBOLS = {
     "b2_import_to_argb": (C.c_int, [_ctx, C.c_int, C.POINTER(ConvertJob), C.c_int, C.c_int, C.c_int]),
     "b2_anim_blend_rows": (C.c_int, [_ctx, C.c_int, C.POINTER(AnimBlendJob), C.c_int, C.c_int]),
     "b2_anim_compare_pixels": (C.c_int, [_ctx, C.c_int, C.POINTER(AnimCompareJob), C.c_int, C.c_int, C.c_int, _vp]),
+    "b2_alpha_unfilter": (C.c_int, [_ctx, C.c_int, C.POINTER(AlphaFilterJob), C.c_int]),
+    "b2_alpha_filter": (C.c_int, [_ctx, C.c_int, C.POINTER(AlphaFilterJob), C.c_int]),
     "b2_picture_cleanup_transparent": (C.c_int, [_ctx, C.c_int, C.POINTER(PictureJob), C.c_int, C.c_int]),
     "b2_picture_blend_alpha": (C.c_int, [_ctx, C.c_int, C.POINTER(PictureJob), C.c_int, C.c_int, C.c_uint32]),
     "b2_picture_replace_transparent": (C.c_int, [_ctx, C.c_int, C.POINTER(PictureJob), C.c_int, C.c_uint32]),

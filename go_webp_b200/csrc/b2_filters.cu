@@ -1,0 +1,291 @@
+// b2_filters.cu -- alpha-plane filters:
+//   unfilters  HorizontalUnfilter_C / VerticalUnfilter_C / GradientUnfilter_C,
+//              pkg/libwebp/dsp/filters.go:130-171, applied row after row against the previous
+//              OUTPUT row as ALPHDecode / AlphaApplyFilter do (pkg/vp8/vp8l_dec.c.go:802-814)
+//   filters    DoHorizontalFilter_C / DoVerticalFilter_C / DoGradientFilter_C, filters.go:24-112
+// Planes are bytes; everything is arithmetic mod 256.
+//
+// The forward filters read only the unfiltered plane: one thread per 4 pixels.  The
+// unfilters are recurrences, restated so that they parallelise:
+//   horizontal  out[y][x] = sum_{r<=y} in[r][0] + sum_{1<=k<=x} in[y][k]: a warp per row --
+//               the column-0 sum over the rows above, then a warp scan along the row;
+//   vertical    out[y][x] = out[0][x] + sum_{1<=r<=y} in[r][x] with out[0] the horizontal
+//               prefix of row 0: a thread per 4 columns walks down the rows (whole 128-byte
+//               lines per warp), after summing row 0 up to its segment;
+//   gradient    clip(left + top - topleft) is not linear: a wavefront, one warp per image,
+//               32 rows at a time, lane r one column behind lane r-1 (top / top-left arrive
+//               by shuffle; the row above a band is read back from the output).
+#include <stdlib.h>
+
+#include "b2_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+
+struct FiltJobDev {
+  const uint8_t* src;
+  uint8_t* dst;
+  int32_t src_stride, dst_stride, width, height;
+  int32_t filter;
+  uint32_t units_x;
+};
+
+__device__ __forceinline__ int gradient_pred(int a, int b, int c) {   // GradientPredictor_C
+  const int g = a + b - c;
+  return min(max(g, 0), 255);
+}
+
+// ---- forward: unit = (row, 128-pixel segment), 4 pixels per lane --------------------
+__global__ void __launch_bounds__(kThreads, 8)
+alpha_filter_kernel(const FiltJobDev* __restrict__ jobs, const uint32_t* __restrict__ prefix, uint32_t n_jobs,
+                    uint32_t uniform, uint32_t total) {
+  const int lane = threadIdx.x & 31;
+  for (uint32_t unit = blockIdx.x * kWarps + (threadIdx.x >> 5); unit < total; unit += gridDim.x * kWarps) {
+    uint32_t local;
+    const uint32_t img = b2_find_image(prefix, n_jobs, uniform, unit, &local);
+    const FiltJobDev j = jobs[img];
+    const int y = (int)(local / j.units_x), x0 = (int)(local % j.units_x) * 128 + lane * 4;
+    const uint8_t* cur = j.src + (ptrdiff_t)y * j.src_stride;
+    const uint8_t* up = cur - j.src_stride;
+    uint8_t* dst = j.dst + (ptrdiff_t)y * j.dst_stride;
+    for (int x = x0; x < min(x0 + 4, j.width); ++x) {
+      int pred;
+      if (j.filter == 0) pred = 0;
+      else if (x == 0) pred = (y == 0) ? 0 : up[0];                        // leftmost pixel: as is / from above
+      else if (y == 0 || j.filter == 1) pred = cur[x - 1];                // top row and horizontal: from the left
+      else if (j.filter == 2) pred = up[x];
+      else pred = gradient_pred(cur[x - 1], up[x], up[x - 1]);
+      dst[x] = (uint8_t)(cur[x] - pred);
+    }
+  }
+}
+
+// bytewise inclusive prefix sum of the 4 bytes of w (mod 256 per byte)
+__device__ __forceinline__ uint32_t prefix4(uint32_t w) {
+  w = __vadd4(w, w << 8);
+  return __vadd4(w, w << 16);
+}
+
+// ---- unfilter, NONE / HORIZONTAL: a warp per row ------------------------------------
+__global__ void __launch_bounds__(kThreads, 8)
+alpha_unfilter_rows_kernel(const FiltJobDev* __restrict__ jobs, const uint32_t* __restrict__ prefix, uint32_t n_jobs,
+                           uint32_t uniform, uint32_t total) {
+  const int lane = threadIdx.x & 31;
+  for (uint32_t unit = blockIdx.x * kWarps + (threadIdx.x >> 5); unit < total; unit += gridDim.x * kWarps) {
+    uint32_t y;
+    const uint32_t img = b2_find_image(prefix, n_jobs, uniform, unit, &y);
+    const FiltJobDev j = jobs[img];
+    if (j.filter > 1) continue;                  // vertical / gradient rows are done by their own kernels
+    const uint8_t* in = j.src + (ptrdiff_t)y * j.src_stride;
+    uint8_t* out = j.dst + (ptrdiff_t)y * j.dst_stride;
+    uint32_t carry = 0;                          // value left of the current chunk (pred)
+    if (j.filter == 1 && y > 0) {                // prev[0] = sum of column 0 over the rows above
+      uint32_t s = 0;
+      for (uint32_t r = lane; r < y; r += 32) s += j.src[(ptrdiff_t)r * j.src_stride];
+#pragma unroll
+      for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      carry = s & 0xffu;
+    }
+    for (int x0 = 0; x0 < j.width; x0 += 128) {
+      const int x = x0 + lane * 4;
+      uint32_t w = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) if (x + k < j.width) w |= (uint32_t)in[x + k] << (8 * k);
+      if (j.filter == 1) {
+        uint32_t p = prefix4(w);                 // within the lane
+        uint32_t tot = p >> 24;                  // lane total, then an exclusive scan over the lanes
+        uint32_t scan = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t t = __shfl_up_sync(0xffffffffu, scan, o);
+          if (lane >= o) scan += t;
+        }
+        const uint32_t before = (scan - tot + carry) & 0xffu;
+        w = __vadd4(p, before * 0x01010101u);
+        carry = (__shfl_sync(0xffffffffu, scan, 31) + carry) & 0xffu;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) if (x + k < j.width) out[x + k] = (uint8_t)(w >> (8 * k));
+    }
+  }
+}
+
+// ---- unfilter, VERTICAL: unit = 128-column segment of an image -------------------------
+__global__ void __launch_bounds__(kThreads, 8)
+alpha_unfilter_vertical_kernel(const FiltJobDev* __restrict__ jobs, const uint32_t* __restrict__ prefix, uint32_t n_jobs,
+                               uint32_t uniform, uint32_t total) {
+  const int lane = threadIdx.x & 31;
+  for (uint32_t unit = blockIdx.x * kWarps + (threadIdx.x >> 5); unit < total; unit += gridDim.x * kWarps) {
+    uint32_t seg;
+    const uint32_t img = b2_find_image(prefix, n_jobs, uniform, unit, &seg);
+    const FiltJobDev j = jobs[img];
+    if (j.filter != 2) continue;
+    const int x = (int)seg * 128 + lane * 4;
+    // row 0: horizontal prefix; the sum of everything left of this segment first
+    uint32_t s = 0;
+    for (int k = lane; k < (int)seg * 128; k += 32) s += j.src[k];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    uint32_t w = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if (x + k < j.width) w |= (uint32_t)j.src[x + k] << (8 * k);
+    const uint32_t p = prefix4(w);
+    const uint32_t tot = p >> 24;
+    uint32_t scan = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, scan, o);
+      if (lane >= o) scan += t;
+    }
+    uint32_t acc = __vadd4(p, ((scan - tot + s) & 0xffu) * 0x01010101u);
+    const bool al4 = ((((uintptr_t)j.src | (uintptr_t)j.dst | (uintptr_t)(uint32_t)j.src_stride | (uintptr_t)(uint32_t)j.dst_stride) & 3) == 0) &&
+                     x + 4 <= j.width;
+    for (int y = 0; y < j.height; ++y) {
+      const uint8_t* in = j.src + (ptrdiff_t)y * j.src_stride + x;
+      uint8_t* out = j.dst + (ptrdiff_t)y * j.dst_stride + x;
+      if (y > 0) {
+        uint32_t v = 0;
+        if (al4) v = __ldg(reinterpret_cast<const uint32_t*>(in));
+        else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) if (x + k < j.width) v |= (uint32_t)in[k] << (8 * k);
+        }
+        acc = __vadd4(acc, v);
+      }
+      if (al4) *reinterpret_cast<uint32_t*>(out) = acc;
+      else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if (x + k < j.width) out[k] = (uint8_t)(acc >> (8 * k));
+      }
+    }
+  }
+}
+
+// ---- unfilter, GRADIENT: one warp per image ---------------------------------------------
+__global__ void __launch_bounds__(kThreads, 8)
+alpha_unfilter_gradient_kernel(const FiltJobDev* __restrict__ jobs, uint32_t n_jobs) {
+  const int lane = threadIdx.x & 31;
+  for (uint32_t img = blockIdx.x * kWarps + (threadIdx.x >> 5); img < n_jobs; img += gridDim.x * kWarps) {
+    const FiltJobDev j = jobs[img];
+    if (j.filter != 3) continue;
+    const int w = j.width, h = j.height;
+    for (int band = 0; band < h; band += 32) {
+      const int row = band + lane;
+      const bool row_ok = row < h;
+      const uint8_t* in = j.src + (ptrdiff_t)row * j.src_stride;
+      uint8_t* out = j.dst + (ptrdiff_t)row * j.dst_stride;
+      const uint8_t* above = j.dst + (ptrdiff_t)(band - 1) * j.dst_stride;   // last row of the band above (band > 0)
+      int left = 0, top_left = 0, cur_out = 0;
+      for (int k = 0; k < w + 31; ++k) {
+        const int c = k - lane;
+        // top = (row-1, c): the lane above produced it on the previous step
+        int top = __shfl_up_sync(0xffffffffu, cur_out, 1);
+        if (lane == 0) top = (band > 0 && k < w) ? (int)__ldcg(above + k) : 0;
+        if (row_ok && c >= 0 && c < w) {
+          const int v = in[c];
+          int o;
+          if (row == 0) o = (v + left) & 0xff;                        // first row: horizontal, pred 0 at c == 0
+          else if (c == 0) o = (v + top) & 0xff;                      // left = top = top_left = prev[0]
+          else o = (v + gradient_pred(left, top, top_left)) & 0xff;
+          out[c] = (uint8_t)o;
+          left = o;
+          cur_out = o;
+        }
+        top_left = top;
+      }
+      __syncwarp();
+      __threadfence_block();   // the next band's lane 0 reads this band's last row back
+    }
+  }
+}
+
+enum { KIND_FORWARD, KIND_ROWS, KIND_VERTICAL };
+
+int prepare_filt(b2_ctx* ctx, int stream, const b2_alpha_filter_job* jobs, int n_jobs, int kind, const FiltJobDev** dj,
+                 const uint32_t** dp, uint32_t* uniform, uint32_t* total, int* counts /*[4]*/) {
+  const size_t jb = (sizeof(FiltJobDev) * (size_t)n_jobs + 15) & ~(size_t)15;
+  const size_t pb = sizeof(uint32_t) * ((size_t)n_jobs + 1);
+  if (jb + pb > B2_DESC_RING_BYTES) return B2_ERR_INVALID_CONFIG;
+  uint8_t* host = (uint8_t*)calloc(1, jb + pb);
+  if (host == NULL) return B2_ERR_OOM;
+  FiltJobDev* d = (FiltJobDev*)host;
+  uint32_t* pre = (uint32_t*)(host + jb);
+  uint64_t tot = 0;
+  uint32_t uni = 0;
+  for (int i = 0; i < n_jobs; ++i) {
+    const b2_alpha_filter_job& j = jobs[i];
+    int st = B2_OK;
+    if (j.src == NULL || j.dst == NULL) st = B2_ERR_NULL;
+    else if (j.width <= 0 || j.height <= 0 || j.width > B2_MAX_DIMENSION || j.height > B2_MAX_DIMENSION) st = B2_ERR_BAD_DIM;
+    else if (j.src_stride < j.width || j.dst_stride < j.width) st = B2_ERR_BAD_DIM;
+    else if (j.filter < 0 || j.filter > 3 || (const uint8_t*)j.dst == j.src) st = B2_ERR_INVALID_CONFIG;   // WEBP_FILTER_TYPE; out of place
+    if (st != B2_OK) { free(host); return st; }
+    d[i].src = j.src; d[i].dst = j.dst; d[i].src_stride = j.src_stride; d[i].dst_stride = j.dst_stride;
+    d[i].width = j.width; d[i].height = j.height; d[i].filter = j.filter;
+    d[i].units_x = (uint32_t)((j.width + 127) / 128);
+    if (counts) counts[j.filter]++;
+    uint32_t items = 0;
+    switch (kind) {
+      case KIND_FORWARD: items = d[i].units_x * (uint32_t)j.height; break;
+      case KIND_ROWS: items = (uint32_t)j.height; break;
+      default: items = d[i].units_x; break;
+    }
+    if (i == 0) uni = items; else if (items != uni) uni = 0;
+    pre[i] = (uint32_t)tot;
+    tot += items;
+    if (tot > 0x7fffffffull) { free(host); return B2_ERR_BAD_DIM; }
+  }
+  pre[n_jobs] = (uint32_t)tot;
+  void* dev = NULL;
+  const int st = b2_upload_desc(ctx, stream, host, jb + pb, &dev);
+  free(host);
+  if (st != B2_OK) return st;
+  *dj = (const FiltJobDev*)dev; *dp = (const uint32_t*)((uint8_t*)dev + jb); *uniform = uni; *total = (uint32_t)tot;
+  return B2_OK;
+}
+
+}  // namespace
+
+#define B2_FILT_ENTRY_CHECKS          \
+  B2_CHECK_CTX(ctx, stream);          \
+  if (n_jobs < 0) return B2_ERR_INVALID_CONFIG; \
+  if (n_jobs == 0) return B2_OK;      \
+  if (jobs == NULL) return B2_ERR_NULL;
+
+extern "C" int b2_alpha_filter(b2_ctx* ctx, int stream, const b2_alpha_filter_job* jobs, int n_jobs) {
+  B2_FILT_ENTRY_CHECKS
+  const FiltJobDev* dj; const uint32_t* dp; uint32_t uni, tot;
+  const int rc = prepare_filt(ctx, stream, jobs, n_jobs, KIND_FORWARD, &dj, &dp, &uni, &tot, NULL);
+  if (rc != B2_OK) return rc;
+  alpha_filter_kernel<<<b2_grid_for(ctx, 8, (tot + kWarps - 1) / kWarps), kThreads, 0, ctx->streams[stream]>>>(dj, dp, (uint32_t)n_jobs, uni, tot);
+  ctx->launches++;
+  B2_CUDA(ctx, cudaGetLastError());
+  return B2_OK;
+}
+
+extern "C" int b2_alpha_unfilter(b2_ctx* ctx, int stream, const b2_alpha_filter_job* jobs, int n_jobs) {
+  B2_FILT_ENTRY_CHECKS
+  cudaStream_t s = ctx->streams[stream];
+  int counts[4] = {0, 0, 0, 0};
+  const FiltJobDev* dj; const uint32_t* dp; uint32_t uni, tot;
+  int rc = prepare_filt(ctx, stream, jobs, n_jobs, KIND_ROWS, &dj, &dp, &uni, &tot, counts);
+  if (rc != B2_OK) return rc;
+  if (counts[0] + counts[1] > 0) {
+    alpha_unfilter_rows_kernel<<<b2_grid_for(ctx, 8, (tot + kWarps - 1) / kWarps), kThreads, 0, s>>>(dj, dp, (uint32_t)n_jobs, uni, tot);
+    ctx->launches++;
+  }
+  if (counts[3] > 0) {
+    alpha_unfilter_gradient_kernel<<<b2_grid_for(ctx, 8, ((uint64_t)n_jobs + kWarps - 1) / kWarps), kThreads, 0, s>>>(dj, (uint32_t)n_jobs);
+    ctx->launches++;
+  }
+  if (counts[2] > 0) {
+    rc = prepare_filt(ctx, stream, jobs, n_jobs, KIND_VERTICAL, &dj, &dp, &uni, &tot, NULL);
+    if (rc != B2_OK) return rc;
+    alpha_unfilter_vertical_kernel<<<b2_grid_for(ctx, 8, (tot + kWarps - 1) / kWarps), kThreads, 0, s>>>(dj, dp, (uint32_t)n_jobs, uni, tot);
+    ctx->launches++;
+  }
+  B2_CUDA(ctx, cudaGetLastError());
+  return B2_OK;
+}

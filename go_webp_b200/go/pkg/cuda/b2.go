@@ -577,3 +577,43 @@ func (c *Context) AnimComparePixels(stream int, jobs []AnimCompareJob, lossless 
 	return status(c, C.b2_anim_compare_pixels(c.h, C.int(stream), &cj[0], C.int(len(cj)), boolInt(lossless),
 		C.int(maxAllowedDiff), (*C.int32_t)(unsafe.Pointer(uintptr(result)))))
 }
+
+// AlphaFilterJob is one alpha plane of the filter / unfilter entry points
+// (include/b2webp.h b2_alpha_filter_job); Filter is a WEBP_FILTER_TYPE.
+type AlphaFilterJob struct {
+	Src, Dst             DevicePtr
+	SrcStride, DstStride int
+	Width, Height        int
+	Filter               int
+}
+
+func alphaFilterJobs(jobs []AlphaFilterJob) []C.b2_alpha_filter_job {
+	cj := make([]C.b2_alpha_filter_job, len(jobs))
+	for i, j := range jobs {
+		cj[i] = C.b2_alpha_filter_job{
+			src: (*C.uint8_t)(unsafe.Pointer(uintptr(j.Src))), dst: (*C.uint8_t)(unsafe.Pointer(uintptr(j.Dst))),
+			src_stride: C.int32_t(j.SrcStride), dst_stride: C.int32_t(j.DstStride),
+			width: C.int32_t(j.Width), height: C.int32_t(j.Height), filter: C.int32_t(j.Filter),
+		}
+	}
+	return cj
+}
+
+// AlphaUnfilter replaces WebPUnfilters[filter] applied row after row by the alpha decoder
+// (pkg/libwebp/dsp/filters.go:130-171, pkg/vp8/vp8l_dec.c.go:802-814).
+func (c *Context) AlphaUnfilter(stream int, jobs []AlphaFilterJob) error {
+	if len(jobs) == 0 {
+		return nil
+	}
+	cj := alphaFilterJobs(jobs)
+	return status(c, C.b2_alpha_unfilter(c.h, C.int(stream), &cj[0], C.int(len(cj))))
+}
+
+// AlphaFilter replaces WebPFilters[filter] (pkg/libwebp/dsp/filters.go:24-124).
+func (c *Context) AlphaFilter(stream int, jobs []AlphaFilterJob) error {
+	if len(jobs) == 0 {
+		return nil
+	}
+	cj := alphaFilterJobs(jobs)
+	return status(c, C.b2_alpha_filter(c.h, C.int(stream), &cj[0], C.int(len(cj))))
+}

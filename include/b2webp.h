@@ -372,6 +372,25 @@ typedef struct b2_anim_compare_job {
 int b2_anim_compare_pixels(b2_ctx* ctx, int stream, const b2_anim_compare_job* jobs, int n_jobs, int lossless,
                            int max_allowed_diff, int32_t* result_dev);
 
+/* ---- next rows: alpha-plane filters ----------------------------------
+ * WEBP_FILTER_TYPE filter: 0 none, 1 horizontal, 2 vertical, 3 gradient.  Planes of bytes,
+ * strides in bytes, dst != src.  b2_alpha_unfilter = WebPUnfilters[filter] row after row
+ * against the previous output row (HorizontalUnfilter_C / VerticalUnfilter_C /
+ * GradientUnfilter_C, pkg/libwebp/dsp/filters.go:130-171, driven as ALPHDecode /
+ * AlphaApplyFilter do, pkg/vp8/vp8l_dec.c.go:802-814); b2_alpha_filter = WebPFilters[filter]
+ * on the whole plane (DoHorizontalFilter_C / DoVerticalFilter_C / DoGradientFilter_C,
+ * filters.go:24-112).  Jobs of one batch may use different filters. */
+typedef struct b2_alpha_filter_job {
+  const uint8_t* src;
+  uint8_t* dst;
+  int32_t src_stride, dst_stride;
+  int32_t width, height;
+  int32_t filter;
+  int32_t reserved;
+} b2_alpha_filter_job;
+int b2_alpha_unfilter(b2_ctx* ctx, int stream, const b2_alpha_filter_job* jobs, int n_jobs);
+int b2_alpha_filter(b2_ctx* ctx, int stream, const b2_alpha_filter_job* jobs, int n_jobs);
+
 /* ---- synthetic inputs (SURVEY.md 8d generator, identical to the oracle's) -
  * One uint32 per (row, word) position of n images laid out 'image_bytes'
  * apart, image ids first_img, first_img+1, ...  alpha_mode shapes the top byte

@@ -414,3 +414,20 @@ def compare_pixels(src, src_step, dst, dst_step, length, lossless=True, max_allo
     if lossless:
         return int(lib().orc_compare_pixels_lossless(_p(src), src_step, _p(dst), dst_step, length))
     return int(lib().orc_compare_pixels_lossy(_p(src), src_step, _p(dst), dst_step, length, max_allowed_diff))
+
+
+# ---- alpha-plane filters (oracle_tools.c) -----------------------------
+def alpha_unfilter(plane, filt):
+    plane = np.ascontiguousarray(plane, np.uint8)
+    h, w = plane.shape
+    out = np.empty_like(plane)
+    lib().orc_alpha_unfilter(int(filt), _p(plane), w, _p(out), w, w, h)
+    return out
+
+
+def alpha_filter(plane, filt):
+    plane = np.ascontiguousarray(plane, np.uint8)
+    h, w = plane.shape
+    out = np.empty_like(plane)
+    lib().orc_alpha_filter(int(filt), _p(plane), w, _p(out), w, w, h)
+    return out

@@ -8,6 +8,7 @@
  * (tests/golden/make_golden_tools.py).  File:line citations are relative to the
  * go-webp tree.
  */
+#include <stddef.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -324,4 +325,77 @@ int orc_compare_pixels_lossy(const uint32_t* src, int src_step, const uint32_t* 
     dst += dst_step;
   }
   return 1;
+}
+
+/* ---- alpha-plane filters ---------------------------------------------- */
+/* GradientPredictor_C, pkg/libwebp/dsp/filters.go (clip(a + b - c) to [0, 255]) */
+static int GradientPredictor(uint8_t a, uint8_t b, uint8_t c) {
+  const int g = a + b - c;
+  return ((g & ~0xff) == 0) ? g : (g < 0) ? 0 : 255;
+}
+/* filters.go:138-145 */
+static void HorizontalUnfilter(const uint8_t* prev, const uint8_t* in, uint8_t* out, int width) {
+  uint8_t pred = (prev == NULL) ? 0 : prev[0];
+  for (int i = 0; i < width; ++i) {
+    out[i] = (uint8_t)(pred + in[i]);
+    pred = out[i];
+  }
+}
+/* filters.go:147-155 */
+static void VerticalUnfilter(const uint8_t* prev, const uint8_t* in, uint8_t* out, int width) {
+  if (prev == NULL) {
+    HorizontalUnfilter(NULL, in, out, width);
+  } else {
+    for (int i = 0; i < width; ++i) out[i] = (uint8_t)(prev[i] + in[i]);
+  }
+}
+/* filters.go:157-171 */
+static void GradientUnfilter(const uint8_t* prev, const uint8_t* in, uint8_t* out, int width) {
+  if (prev == NULL) {
+    HorizontalUnfilter(NULL, in, out, width);
+  } else {
+    uint8_t top = prev[0], top_left = top, left = top;
+    for (int i = 0; i < width; ++i) {
+      top = prev[i]; /* need to read this first, in case prev==out */
+      left = (uint8_t)(in[i] + GradientPredictor(left, top, top_left));
+      top_left = top;
+      out[i] = left;
+    }
+  }
+}
+/* The row loop of ALPHDecode / AlphaApplyFilter (pkg/vp8/vp8l_dec.c.go:802-814): every row
+ * is unfiltered against the previous OUTPUT row.  filter: 0 none, 1 horizontal, 2 vertical,
+ * 3 gradient (WEBP_FILTER_TYPE). */
+void orc_alpha_unfilter(int filter, const uint8_t* in, int in_stride, uint8_t* out, int out_stride, int width, int height) {
+  const uint8_t* prev = NULL;
+  for (int y = 0; y < height; ++y) {
+    const uint8_t* src = in + (ptrdiff_t)y * in_stride;
+    uint8_t* dst = out + (ptrdiff_t)y * out_stride;
+    switch (filter) {
+      case 1: HorizontalUnfilter(prev, src, dst, width); break;
+      case 2: VerticalUnfilter(prev, src, dst, width); break;
+      case 3: GradientUnfilter(prev, src, dst, width); break;
+      default: memcpy(dst, src, (size_t)width); break;
+    }
+    prev = dst;
+  }
+}
+/* Forward filters: DoHorizontalFilter_C / DoVerticalFilter_C / DoGradientFilter_C
+ * (filters.go:24-112): the first row is predicted from the left (first pixel as is), the
+ * leftmost pixel of the other rows from above. */
+void orc_alpha_filter(int filter, const uint8_t* in, int in_stride, uint8_t* out, int out_stride, int width, int height) {
+  for (int y = 0; y < height; ++y) {
+    const uint8_t* cur = in + (ptrdiff_t)y * in_stride;
+    const uint8_t* up = cur - in_stride;
+    uint8_t* dst = out + (ptrdiff_t)y * out_stride;
+    if (filter == 0) { memcpy(dst, cur, (size_t)width); continue; }
+    dst[0] = (y == 0) ? cur[0] : (uint8_t)(cur[0] - up[0]);
+    for (int x = 1; x < width; ++x) {
+      int pred;
+      if (y == 0 || filter == 1) pred = cur[x - 1];
+      else if (filter == 2) pred = up[x];
+      else pred = GradientPredictor(cur[x - 1], up[x], up[x - 1]);
+      dst[x] = (uint8_t)(cur[x] - pred);
+    }
+  }
 }

@@ -891,3 +891,35 @@ def test_anim_blend_and_compare(gpu, golden_dir):
         assert got == exp, (lossless, diff)
     assert anim.ComparePixelsLossless(a[0], 1, a[0].copy(), 1, W) == 1
     assert anim.ComparePixelsLossy(a[12], 1, b[12], 1, W, 0) == oracle.compare_pixels(a[12], 1, b[12], 1, W, False, 0)
+
+
+def test_alpha_filters(gpu, golden_dir):
+    """Alpha-plane filters: the libwebp vectors (all four filters in one
+    batch), then seeded planes vs the oracle: widths over several 128-column segments, more
+    than 32 rows (several wavefront bands for the gradient), odd sizes, and
+    filter(unfilter(x)) == x."""
+    from go_webp_b200 import filters as F
+    g = np.load(os.path.join(golden_dir, "alpha_unfilter_libwebp160.npz"))
+    ks = [str(k) for k in g["names"]]
+    outs = F.AlphaUnfilterBatch([g[f"{k}/in"] for k in ks], [int(g[f"{k}/filter"]) for k in ks])
+    for k, o in zip(ks, outs):
+        assert (o == g[f"{k}/out"]).all(), (k, int(g[f"{k}/filter"]))
+    fwd = F.AlphaFilterBatch([g[f"{k}/out"] for k in ks], [int(g[f"{k}/filter"]) for k in ks])
+    for k, o in zip(ks, fwd):
+        assert (o == g[f"{k}/in"]).all(), k
+    rng = np.random.default_rng(31337)
+    planes, filts = [], []
+    for (w, h) in [(1, 1), (1, 40), (5, 3), (129, 33), (300, 70), (1000, 9), (257, 100)]:
+        for f in range(4):
+            planes.append(rng.integers(0, 256, (h, w), dtype=np.uint8))
+            filts.append(f)
+    un = F.AlphaUnfilterBatch(planes, filts)
+    for p, f, o in zip(planes, filts, un):
+        assert (o == oracle.alpha_unfilter(p, f)).all(), (p.shape, f)
+    back = F.AlphaFilterBatch(un, filts)
+    for p, f, o in zip(planes, filts, back):
+        assert (o == p).all() and (o == oracle.alpha_filter(oracle.alpha_unfilter(p, f), f)).all(), (p.shape, f)
+    data = rng.integers(0, 256, 40 * 7, dtype=np.uint8)
+    out = np.zeros_like(data)
+    F.GradientFilter_C(data, 33, 7, 40, out)
+    assert (out.reshape(7, 40)[:, :33] == oracle.alpha_filter(data.reshape(7, 40)[:, :33], 3)).all()

@@ -288,3 +288,17 @@ def test_compare_pixels_known_answers():
     assert oracle.compare_pixels(a, 1, c, 1, 4, lossless=False, max_allowed_diff=2) == 1
     d = a.copy(); d[1] = 0x81112233
     assert oracle.compare_pixels(a, 1, d, 1, 4, lossless=False, max_allowed_diff=255) == 0
+
+
+def test_alpha_unfilters_match_libwebp_streams(golden_dir):
+    """HorizontalUnfilter_C / VerticalUnfilter_C / GradientUnfilter_C (filters.go:130-171)
+    on filtered alpha planes cut out of lossy+alpha files the binary wrote, vs the alpha
+    WebPDecodeRGBA returns; the forward filters give the filtered planes back."""
+    g = _load(golden_dir, "alpha_unfilter_libwebp160.npz")
+    kinds = set()
+    for k in g["names"]:
+        f, fin, exp = int(g[f"{k}/filter"]), g[f"{k}/in"], g[f"{k}/out"]
+        kinds.add(f)
+        assert (oracle.alpha_unfilter(fin, f) == exp).all(), (k, f)
+        assert (oracle.alpha_filter(exp, f) == fin).all(), (k, f)
+    assert kinds == {0, 1, 2, 3}

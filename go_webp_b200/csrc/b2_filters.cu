@@ -88,11 +88,16 @@ alpha_unfilter_rows_kernel(const FiltJobDev* __restrict__ jobs, const uint32_t* 
       for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
       carry = s & 0xffu;
     }
+    const bool al4 = (((uintptr_t)j.src | (uintptr_t)j.dst | (uintptr_t)(uint32_t)j.src_stride | (uintptr_t)(uint32_t)j.dst_stride) & 3) == 0;
     for (int x0 = 0; x0 < j.width; x0 += 128) {
       const int x = x0 + lane * 4;
+      const bool vec = al4 && x + 4 <= j.width;
       uint32_t w = 0;
+      if (vec) w = __ldg(reinterpret_cast<const uint32_t*>(in + x));
+      else {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) if (x + k < j.width) w |= (uint32_t)in[x + k] << (8 * k);
+        for (int k = 0; k < 4; ++k) if (x + k < j.width) w |= (uint32_t)in[x + k] << (8 * k);
+      }
       if (j.filter == 1) {
         uint32_t p = prefix4(w);                 // within the lane
         uint32_t tot = p >> 24;                  // lane total, then an exclusive scan over the lanes
@@ -106,8 +111,11 @@ alpha_unfilter_rows_kernel(const FiltJobDev* __restrict__ jobs, const uint32_t* 
         w = __vadd4(p, before * 0x01010101u);
         carry = (__shfl_sync(0xffffffffu, scan, 31) + carry) & 0xffu;
       }
+      if (vec) *reinterpret_cast<uint32_t*>(out + x) = w;
+      else {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) if (x + k < j.width) out[x + k] = (uint8_t)(w >> (8 * k));
+        for (int k = 0; k < 4; ++k) if (x + k < j.width) out[x + k] = (uint8_t)(w >> (8 * k));
+      }
     }
   }
 }
@@ -142,20 +150,33 @@ alpha_unfilter_vertical_kernel(const FiltJobDev* __restrict__ jobs, const uint32
     uint32_t acc = __vadd4(p, ((scan - tot + s) & 0xffu) * 0x01010101u);
     const bool al4 = ((((uintptr_t)j.src | (uintptr_t)j.dst | (uintptr_t)(uint32_t)j.src_stride | (uintptr_t)(uint32_t)j.dst_stride) & 3) == 0) &&
                      x + 4 <= j.width;
-    for (int y = 0; y < j.height; ++y) {
-      const uint8_t* in = j.src + (ptrdiff_t)y * j.src_stride + x;
-      uint8_t* out = j.dst + (ptrdiff_t)y * j.dst_stride + x;
-      if (y > 0) {
-        uint32_t v = 0;
-        if (al4) v = __ldg(reinterpret_cast<const uint32_t*>(in));
-        else {
+    if (al4) {
+      // 8 rows of loads in flight per thread: the walk down a column is a chain of adds,
+      // the loads must not wait for one another
+      *reinterpret_cast<uint32_t*>(j.dst + x) = acc;
+      for (int y0 = 1; y0 < j.height; y0 += 8) {
+        uint32_t v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          v[q] = (y0 + q < j.height) ? __ldg(reinterpret_cast<const uint32_t*>(j.src + (ptrdiff_t)(y0 + q) * j.src_stride + x)) : 0u;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (y0 + q < j.height) {
+            acc = __vadd4(acc, v[q]);
+            *reinterpret_cast<uint32_t*>(j.dst + (ptrdiff_t)(y0 + q) * j.dst_stride + x) = acc;
+          }
+        }
+      }
+    } else {
+      for (int y = 0; y < j.height; ++y) {
+        const uint8_t* in = j.src + (ptrdiff_t)y * j.src_stride + x;
+        uint8_t* out = j.dst + (ptrdiff_t)y * j.dst_stride + x;
+        if (y > 0) {
+          uint32_t v = 0;
 #pragma unroll
           for (int k = 0; k < 4; ++k) if (x + k < j.width) v |= (uint32_t)in[k] << (8 * k);
+          acc = __vadd4(acc, v);
         }
-        acc = __vadd4(acc, v);
-      }
-      if (al4) *reinterpret_cast<uint32_t*>(out) = acc;
-      else {
 #pragma unroll
         for (int k = 0; k < 4; ++k) if (x + k < j.width) out[k] = (uint8_t)(acc >> (8 * k));
       }
@@ -164,10 +185,12 @@ alpha_unfilter_vertical_kernel(const FiltJobDev* __restrict__ jobs, const uint32
 }
 
 // ---- unfilter, GRADIENT: one warp per image ---------------------------------------------
-__global__ void __launch_bounds__(kThreads, 8)
+// (one warp per CTA: the wavefront of an image is a single dependency chain, so the images
+// are spread over as many SMs as possible and the kernel gets all the registers it wants)
+__global__ void __launch_bounds__(32)
 alpha_unfilter_gradient_kernel(const FiltJobDev* __restrict__ jobs, uint32_t n_jobs) {
   const int lane = threadIdx.x & 31;
-  for (uint32_t img = blockIdx.x * kWarps + (threadIdx.x >> 5); img < n_jobs; img += gridDim.x * kWarps) {
+  for (uint32_t img = blockIdx.x; img < n_jobs; img += gridDim.x) {
     const FiltJobDev j = jobs[img];
     if (j.filter != 3) continue;
     const int w = j.width, h = j.height;
@@ -178,22 +201,39 @@ alpha_unfilter_gradient_kernel(const FiltJobDev* __restrict__ jobs, uint32_t n_j
       uint8_t* out = j.dst + (ptrdiff_t)row * j.dst_stride;
       const uint8_t* above = j.dst + (ptrdiff_t)(band - 1) * j.dst_stride;   // last row of the band above (band > 0)
       int left = 0, top_left = 0, cur_out = 0;
-      for (int k = 0; k < w + 31; ++k) {
-        const int c = k - lane;
-        // top = (row-1, c): the lane above produced it on the previous step
-        int top = __shfl_up_sync(0xffffffffu, cur_out, 1);
-        if (lane == 0) top = (band > 0 && k < w) ? (int)__ldcg(above + k) : 0;
-        if (row_ok && c >= 0 && c < w) {
-          const int v = in[c];
-          int o;
-          if (row == 0) o = (v + left) & 0xff;                        // first row: horizontal, pred 0 at c == 0
-          else if (c == 0) o = (v + top) & 0xff;                      // left = top = top_left = prev[0]
-          else o = (v + gradient_pred(left, top, top_left)) & 0xff;
-          out[c] = (uint8_t)o;
-          left = o;
-          cur_out = o;
+      // inputs (and, for lane 0, the row above the band) are fetched 8 steps ahead: the step
+      // is a dependency chain of a shuffle and a handful of ALU operations, nothing else
+      uint32_t pre[8], apre[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int c = q - lane;
+        pre[q] = (row_ok && c >= 0 && c < w) ? in[c] : 0u;
+        apre[q] = (lane == 0 && band > 0 && q < w) ? (uint32_t)__ldcg(above + q) : 0u;
+      }
+      for (int k0 = 0; k0 < w + 31; k0 += 8) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int k = k0 + q;
+          const int c = k - lane;
+          const int v = (int)pre[q];
+          const int atop = (int)apre[q];
+          const int cn = c + 8;
+          pre[q] = (row_ok && cn >= 0 && cn < w) ? in[cn] : 0u;
+          apre[q] = (lane == 0 && band > 0 && k + 8 < w) ? (uint32_t)__ldcg(above + k + 8) : 0u;
+          // top = (row-1, c): the lane above produced it on the previous step
+          int top = __shfl_up_sync(0xffffffffu, cur_out, 1);
+          if (lane == 0) top = atop;
+          if (row_ok && c >= 0 && c < w) {
+            int o;
+            if (row == 0) o = (v + left) & 0xff;                        // first row: horizontal, pred 0 at c == 0
+            else if (c == 0) o = (v + top) & 0xff;                      // left = top = top_left = prev[0]
+            else o = (v + gradient_pred(left, top, top_left)) & 0xff;
+            out[c] = (uint8_t)o;
+            left = o;
+            cur_out = o;
+          }
+          top_left = top;
         }
-        top_left = top;
       }
       __syncwarp();
       __threadfence_block();   // the next band's lane 0 reads this band's last row back
@@ -277,7 +317,7 @@ extern "C" int b2_alpha_unfilter(b2_ctx* ctx, int stream, const b2_alpha_filter_
     ctx->launches++;
   }
   if (counts[3] > 0) {
-    alpha_unfilter_gradient_kernel<<<b2_grid_for(ctx, 8, ((uint64_t)n_jobs + kWarps - 1) / kWarps), kThreads, 0, s>>>(dj, (uint32_t)n_jobs);
+    alpha_unfilter_gradient_kernel<<<b2_grid_for(ctx, 16, (uint64_t)n_jobs), 32, 0, s>>>(dj, (uint32_t)n_jobs);
     ctx->launches++;
   }
   if (counts[2] > 0) {

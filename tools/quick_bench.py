@@ -101,3 +101,16 @@ if "tools" in which:
     report("replace transparent 8x4096^2 ARGB", 8 * 4096 * 4096, 8.0,
            timed(lambda: ctx._chk(ctx.lib.b2_picture_replace_transparent(ctx.h, 0, aj, 8, 0x112233))))
     a.close()
+if "filters" in which:
+    # alpha-plane filters on NF 1080p planes (read + write = 2 B/px)
+    n = NF
+    w, h, st = 1920, 1080, 1920
+    src = ctx.alloc(n * st * h)
+    dst = ctx.alloc(n * st * h)
+    ctx.synth_fill(src.ptr, st // 4, h, st, st * h, n, 0xB2000007, 0, 4)
+    ctx.sync()
+    for f, name in ((1, "horizontal"), (2, "vertical"), (3, "gradient")):
+        jobs = (_abi.AlphaFilterJob * n)(*[_abi.AlphaFilterJob(src.ptr + i * st * h, dst.ptr + i * st * h, st, st, w, h, f, 0) for i in range(n)])
+        report(f"alpha unfilter {name} {n}x1080p", n * w * h, 2.0, timed(lambda: ctx._chk(ctx.lib.b2_alpha_unfilter(ctx.h, 0, jobs, n)), 5))
+        report(f"alpha filter   {name} {n}x1080p", n * w * h, 2.0, timed(lambda: ctx._chk(ctx.lib.b2_alpha_filter(ctx.h, 0, jobs, n)), 5))
+    src.free(); dst.free()

@@ -146,7 +146,14 @@ constexpr int kFwdRows = 64;    // column, 4 rows per pass
 // (bits >= 2).  Two 128-bit loads (current and upper row) plus three scalar neighbours,
 // one 128-bit store.  Rows that are not 16-byte aligned take the same mapping with scalar
 // accesses.
-__global__ void __launch_bounds__(kFwdThreads, 8)
+#ifndef B2_FWD_CTAS
+#define B2_FWD_CTAS 8
+#endif
+#ifndef B2_FWD_UNROLL
+#define B2_FWD_UNROLL 1
+#endif
+constexpr int kFwdUnroll = B2_FWD_UNROLL;
+__global__ void __launch_bounds__(kFwdThreads, B2_FWD_CTAS)
 predictor_forward_kernel(const PredJobDev* __restrict__ jobs, const uint32_t* __restrict__ prefix,
                          uint32_t n_jobs, uint32_t uniform, uint32_t total_items) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -165,6 +172,7 @@ predictor_forward_kernel(const PredJobDev* __restrict__ jobs, const uint32_t* __
     const uint32_t tiles_per_row = j->tiles_per_row;
     uint32_t* __restrict__ dst = j->dst;
     const int y_end = min(h, by0 + kFwdRows);
+#pragma unroll kFwdUnroll
     for (int y = by0 + (lane >> 3); y < y_end; y += 4) {
     const size_t p0 = (size_t)y * w + x;
     const bool vec = ((w & 3) == 0) && (((((uintptr_t)a) | ((uintptr_t)j->dst)) & 15) == 0);
@@ -506,7 +514,7 @@ extern "C" int b2_vp8l_predictor_forward(b2_ctx* ctx, int stream, const b2_argb_
   PredPlan pl;
   const int st = prepare_pred(ctx, stream, jobs, n_jobs, false, &pl);
   if (st != B2_OK) return st;
-  const int grid = b2_grid_for(ctx, 8, pl.total_items);
+  const int grid = b2_grid_for(ctx, B2_FWD_CTAS, pl.total_items);
   predictor_forward_kernel<<<grid, kFwdThreads, 0, ctx->streams[stream]>>>(pl.jobs, pl.prefix, (uint32_t)n_jobs, pl.uniform, pl.total_items);
   ctx->launches++;
   B2_CUDA(ctx, cudaGetLastError());

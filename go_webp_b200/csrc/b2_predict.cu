@@ -243,9 +243,13 @@ constexpr int kInvThreads = kInvWarps * 32;
 constexpr int kInSlots = 16, kOutSlots = 8;
 constexpr int kLaneWords = 28;   // 16 in + 8 out + 4 pad; 16-byte aligned, 28 l mod 32 has period 8
 #ifndef B2_PRED_PUBLISH
-#define B2_PRED_PUBLISH 32
+#define B2_PRED_PUBLISH 16
 #endif
-constexpr int kPublish = B2_PRED_PUBLISH;   // columns between two progress publications
+constexpr int kPublish = B2_PRED_PUBLISH;
+#ifndef B2_PRED_CHUNK
+#define B2_PRED_CHUNK 16
+#endif
+constexpr int kChunk = B2_PRED_CHUNK;   // columns of the row above fetched at a time (power of two <= 32)   // columns between two progress publications
 
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
   uint32_t v;
@@ -324,18 +328,18 @@ __device__ __forceinline__ void inverse_band(const PredJobDev* __restrict__ jp, 
     constexpr bool ODD = decltype(odd_tag)::value;
     constexpr bool STEADY = decltype(steady_tag)::value;   // every lane at 1 <= c <= w-2 of an existing row > 0
     const int c = k - 2 * lane;
-    if (((k + 1) & 31) == 0 && i > 0) {          // next chunk of the row above: columns k+1 .. k+32 (uniform)
-      const uint32_t need_cols = (uint32_t)min(w, k + 33);
+    if (((k + 1) & (kChunk - 1)) == 0 && i > 0) {   // next chunk of the row above: columns k+1 .. k+kChunk (uniform)
+      const uint32_t need_cols = (uint32_t)min(w, k + 1 + kChunk);
       while (avail < need_cols) {
         avail = ld_acquire_u32(flag_up);
         if (avail < need_cols) __nanosleep(64);
       }
       const int col = k + 1 + lane;
-      upc = (col < w) ? __ldcg(up_row + col) : 0u;
+      upc = (lane < kChunk && col < w) ? __ldcg(up_row + col) : 0u;
     }
     // TR = (row-1, c+1): the lane above finished it on the previous step
     uint32_t tr = __shfl_up_sync(0xffffffffu, left, 1);
-    const uint32_t u = __shfl_sync(0xffffffffu, upc, (k + 1) & 31);
+    const uint32_t u = __shfl_sync(0xffffffffu, upc, (k + 1) & (kChunk - 1));
     tr = (lane == 0) ? u : tr;
     if (!ODD) {
       // lanes with c % 8 == 0 fetch columns c+8 .. c+15 into the other half of their ring.

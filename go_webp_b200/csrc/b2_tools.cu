@@ -79,44 +79,65 @@ cleanup_yuva_kernel(const PicJobDev* __restrict__ jobs, const uint32_t* __restri
       const int bx = base + lane;
       const int x0 = bx * 8;
       const int bw = min(8, width - x0);     // <= 0: no block for this lane
-      uint32_t a_lo[8], a_hi[8], y_lo[8], y_hi[8];
+      uint32_t a_lo[8], a_hi[8];
       int count = 0, sum = 0;
+      const int n_blk = max(bw, 0) * bh;
+      auto load_luma = [&](int r, uint32_t* lo, uint32_t* hi) {
+        const uint8_t* yp = yb + (ptrdiff_t)r * ys + x0;
+        *lo = *hi = 0u;
+        if (bw == 8 && al8) {
+          const uint2 yv = *reinterpret_cast<const uint2*>(yp);
+          *lo = yv.x; *hi = yv.y;
+        } else {
+          for (int k = 0; k < bw; ++k) {
+            const uint32_t yv = yp[k];
+            if (k < 4) *lo |= yv << (8 * k); else *hi |= yv << (8 * (k - 4));
+          }
+        }
+      };
       if (bw > 0) {
+        // alpha first: opaque and fully transparent blocks (the usual case) never touch luma
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
-          a_lo[r] = a_hi[r] = y_lo[r] = y_hi[r] = 0u;
+          a_lo[r] = a_hi[r] = 0u;
           if (r < bh) {
             const uint8_t* ap = ab + (ptrdiff_t)r * as + x0;
-            const uint8_t* yp = yb + (ptrdiff_t)r * ys + x0;
             if (bw == 8 && al8) {
               const uint2 av = *reinterpret_cast<const uint2*>(ap);
-              const uint2 yv = *reinterpret_cast<const uint2*>(yp);
-              a_lo[r] = av.x; a_hi[r] = av.y; y_lo[r] = yv.x; y_hi[r] = yv.y;
+              a_lo[r] = av.x; a_hi[r] = av.y;
             } else {
               for (int k = 0; k < bw; ++k) {
-                const uint32_t av = ap[k], yv = yp[k];
-                if (k < 4) { a_lo[r] |= av << (8 * k); y_lo[r] |= yv << (8 * k); }
-                else { a_hi[r] |= av << (8 * (k - 4)); y_hi[r] |= yv << (8 * (k - 4)); }
+                const uint32_t av = ap[k];
+                if (k < 4) a_lo[r] |= av << (8 * k); else a_hi[r] |= av << (8 * (k - 4));
               }
             }
-            // pixels with alpha != 0: count them and sum their luma (SmoothenBlock :66-76).
-            // Bytes past bw are zero alpha AND must not count as transparent pixels: they
-            // are excluded from n below, and contribute nothing here.
-            const uint32_t m_lo = __vcmpne4(a_lo[r], 0u), m_hi = __vcmpne4(a_hi[r], 0u);
-            count += (__popc(m_lo) + __popc(m_hi)) >> 3;
-            sum += (int)__dp4a(y_lo[r] & m_lo, 0x01010101u, 0u) + (int)__dp4a(y_hi[r] & m_hi, 0x01010101u, 0u);
+            // pixels with alpha != 0 (SmoothenBlock :66-76); bytes past bw are zero and are
+            // not part of n_blk
+            count += (__popc(__vcmpne4(a_lo[r], 0u)) + __popc(__vcmpne4(a_hi[r], 0u))) >> 3;
+          }
+        }
+        if (count > 0 && count < n_blk) {   // partially transparent: sum the luma of the visible pixels
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            if (r < bh) {
+              uint32_t ylo, yhi;
+              load_luma(r, &ylo, &yhi);
+              const uint32_t m_lo = __vcmpne4(a_lo[r], 0u), m_hi = __vcmpne4(a_hi[r], 0u);
+              sum += (int)__dp4a(ylo & m_lo, 0x01010101u, 0u) + (int)__dp4a(yhi & m_hi, 0x01010101u, 0u);
+            }
           }
         }
       }
-      const int n = max(bw, 0) * bh;
-      if (bw > 0 && count > 0 && count < n) {   // partially transparent: transparent pixels take the average luma
+      if (bw > 0 && count > 0 && count < n_blk) {   // partially transparent: transparent pixels take the average luma
         const uint32_t avg = (uint32_t)(sum / count) & 0xffu;
         const uint32_t avg4 = avg * 0x01010101u;
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
           if (r < bh) {
             const uint32_t m_lo = __vcmpne4(a_lo[r], 0u), m_hi = __vcmpne4(a_hi[r], 0u);
-            const uint32_t n_lo = (y_lo[r] & m_lo) | (avg4 & ~m_lo), n_hi = (y_hi[r] & m_hi) | (avg4 & ~m_hi);
+            uint32_t ylo, yhi;
+            load_luma(r, &ylo, &yhi);   // second read of the block's luma: an L1 hit
+            const uint32_t n_lo = (ylo & m_lo) | (avg4 & ~m_lo), n_hi = (yhi & m_hi) | (avg4 & ~m_hi);
             uint8_t* yp = yb + (ptrdiff_t)r * ys + x0;
             if (bw == 8 && al8) {
               *reinterpret_cast<uint2*>(yp) = make_uint2(n_lo, n_hi);

@@ -88,6 +88,15 @@ if "tools" in which:
                                      for j in p.jobs])
     report(f"cleanup transparent {NF}x1080p YUVA (binary alpha)", NF * 1920 * 1080, 3.0,
            timed(lambda: ctx._chk(ctx.lib.b2_picture_cleanup_transparent(ctx.h, 0, jobs, NF, 0))))
+    po = ImportPipeline(ctx, NF, 1920, 1080, host=False)
+    po.fill_synthetic(0xB2000001, 0, 1)
+    po.run_device()
+    ctx.sync()
+    ojobs = (_abi.PictureJob * NF)(*[_abi.PictureJob(j.y, j.u, j.v, j.a, None, j.y_stride, j.uv_stride, j.a_stride, 0, j.width, j.height)
+                                      for j in po.jobs])
+    report(f"cleanup transparent {NF}x1080p YUVA (opaque: reads A only)", NF * 1920 * 1080, 1.0,
+           timed(lambda: ctx._chk(ctx.lib.b2_picture_cleanup_transparent(ctx.h, 0, ojobs, NF, 0))))
+    po.close()
     report(f"blend alpha {NF}x1080p YUVA", NF * 1920 * 1080, 5.0,
            timed(lambda: ctx._chk(ctx.lib.b2_picture_blend_alpha(ctx.h, 0, jobs, NF, 0, 0x336699))))
     p.close()

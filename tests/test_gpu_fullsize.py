@@ -236,3 +236,46 @@ def test_mixed_pipeline_device_resident(env):
         go = ctx.d2h(p.d_out.ptr + p.off["src"][i], 4 * w * h).view(np.uint32).reshape(h, w)
         assert (go == oracle.add_green(oracle.color_space_inverse(src, codes, 5))).all()
     p.close()
+
+
+@pytest.mark.parametrize("size", [(16383, 9), (10, 16383)])
+def test_maximum_dimension_next_rows(env, size):
+    """WEBP_MAX_DIMENSION in either direction through the 8f-3 / 8f-4 entry points: dithered
+    import, picture cleanup / blend, use_argb import, animation blend, alpha filters."""
+    from go_webp_b200 import anim, filters as F, picture as P, picture_tools as T
+    w, h = size
+    rng = np.random.default_rng(w + h)
+    argb = rng.integers(0, 1 << 32, (h, w), dtype=np.uint32)
+    argb[rng.random((h, w)) < 0.5] |= 0xff000000
+    pic = P.Picture(Width=w, Height=h, UseARGB=True, ARGB=argb.copy(), ARGBStride=w)
+    assert P.WebPPictureARGBToYUVADithered(pic, P.WEBP_YUV420, 0.8) is None
+    y, u, v, a, ha = oracle.import_yuva_dithered(argb.view(np.uint8).reshape(h, 4 * w), w, h, 0.8, "BGRA")
+    assert (pic.Y == y).all() and (pic.U == u).all() and (pic.V == v).all() and (pic.A == a).all()
+    bw, bh = (w + 7) // 8, (h + 7) // 8
+    al = rng.integers(1, 256, (h, w), dtype=np.uint8)
+    al[np.kron(rng.random((bh, bw)) < 0.7, np.ones((8, 8), bool))[:h, :w]] = 0
+    al[rng.random((h, w)) < 0.05] = 0
+    py = P.Picture(Width=w, Height=h, ColorSpace=P.WEBP_YUV420A, Y=y.copy(), U=u.copy(), V=v.copy(), A=al.copy())
+    pa = P.Picture(Width=w, Height=h, UseARGB=True, ARGB=(argb & 0xffffff) | (al.astype(np.uint32) << 24), ARGBStride=w)
+    src_argb = pa.ARGB.copy()
+    T.WebPCleanupTransparentAreaBatch([py, pa])
+    ey, eu, ev = oracle.cleanup_transparent_yuva(y, u, v, al)
+    assert (py.Y == ey).all() and (py.U == eu).all() and (py.V == ev).all()
+    assert (pa.ARGB == oracle.cleanup_transparent_argb(src_argb)).all()
+    T.WebPBlendAlphaBatch([py, pa], 0x204060)
+    by, bu, bv, ba = oracle.blend_alpha_yuva(ey, eu, ev, al, 0x204060)
+    assert (py.Y == by).all() and (py.U == bu).all() and (py.V == bv).all() and (py.A == 255).all()
+    assert (pa.ARGB == oracle.blend_alpha_argb(oracle.cleanup_transparent_argb(src_argb), 0x204060)).all()
+    rgb = rng.integers(0, 256, (h, 3 * w), dtype=np.uint8)
+    pr = P.Picture(Width=w, Height=h, UseARGB=True)
+    assert P.WebPPictureImportBGR(pr, rgb, 3 * w) == 1
+    assert (pr.ARGB == oracle.import_to_argb(rgb, w, h, "BGR")).all()
+    dst = rng.integers(0, 1 << 32, (h, w), dtype=np.uint32)
+    for premult in (False, True):
+        assert (anim.BlendRowsBatch([src_argb], [dst], premult)[0] == oracle.anim_blend_rows(src_argb, dst, int(premult))).all()
+    planes = [al] * 4
+    un = F.AlphaUnfilterBatch(planes, [0, 1, 2, 3])
+    for f, o in enumerate(un):
+        assert (o == oracle.alpha_unfilter(al, f)).all(), f
+    for f, o in enumerate(F.AlphaFilterBatch(un, [0, 1, 2, 3])):
+        assert (o == al).all(), f

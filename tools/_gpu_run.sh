@@ -1,2 +1,1 @@
-timeout 600 python -m pytest tests -m gpu -x -q -k "picture_tools" 2>&1 | tail -2
-timeout 300 python tools/quick_bench.py tools 2>&1 | tail -7
+timeout 900 python -m pytest tests -m gpu -x -q -k "maximum_dimension" 2>&1 | tail -12

@@ -1,0 +1,259 @@
+// b2_rescale.cu -- the fixed-point rescaler:
+//   WebPRescalerInit / Import / Export   pkg/libwebp/utils/rescaler_utils.c.go:31-158
+//   ImportRowExpand / ImportRowShrink / ExportRowExpand / ExportRowShrink
+//                                        pkg/libwebp/dsp/rescaler.c.go:39-197
+// driven over a whole plane as RescalePlane does (pkg/libwebp/enc/picture_rescale_enc.c.go:
+// 125-136; the decoder's EmitRescaled* loops feed the same machine row batch by row batch).
+//
+// The reference is a streaming state machine: rows are imported one by one into `frow`,
+// accumulated into `irow`, and exported whenever the vertical accumulator runs out.  What
+// carries from one output to the next -- horizontally the fractional start of the next
+// pixel, vertically the fractional start of the next row -- is a function of the LAST input
+// sample and of the accumulator only, never of the running sums.  So every output sample is
+// an independent function of a small rectangle of input samples once the accumulator walks
+// are known: the host replays the two integer walks (O(width + height), no pixel work) into
+// an x table and a y table, and one kernel computes every output sample from them.
+#include <stdlib.h>
+#include <string.h>
+
+#include <map>
+#include <tuple>
+#include <vector>
+
+#include "b2_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr uint64_t kOne = 1ull << 32;
+constexpr uint64_t kRounder = kOne >> 1;
+
+struct XEnt { int32_t a, b, accum; };                 // expand: left, right sample; shrink: [a, b) consumed; accum after
+struct YEnt { int32_t prev_last, last, y_accum; uint32_t prev_yscale, yscale; };   // last < 0: row never exported
+
+struct RescaleJobDev {
+  const uint8_t* src;
+  uint8_t* dst;
+  int32_t src_stride, dst_stride, dst_width, dst_height, num_channels;
+  int32_t x_expand, y_expand, x_add, x_sub, y_sub;
+  uint32_t fx_scale, fy_scale, fxy_scale;
+  uint32_t xtab, ytab;   // entry offsets into the table pools
+  uint32_t units_x;
+};
+
+__device__ __forceinline__ uint32_t mult_fix(uint32_t x, uint32_t y) { return (uint32_t)(((uint64_t)x * y + kRounder) >> 32); }
+__device__ __forceinline__ uint32_t mult_fix_floor(uint32_t x, uint32_t y) { return (uint32_t)(((uint64_t)x * y) >> 32); }
+
+// frow[xo] of source row `row` (rescaler.c.go:39-105), c = channel
+__device__ __forceinline__ uint32_t frow_at(const RescaleJobDev& j, const XEnt* __restrict__ xt, const uint8_t* __restrict__ row,
+                                            int xo, int c) {
+  const int ch = j.num_channels;
+  const XEnt e = xt[xo];
+  if (j.x_expand) {
+    const uint32_t left = row[e.a * ch + c], right = row[e.b * ch + c];
+    return right * (uint32_t)j.x_add + (left - right) * (uint32_t)e.accum;
+  }
+  uint32_t sum = 0;
+  if (xo > 0) {   // fractional start left by the previous output sample
+    const XEnt p = xt[xo - 1];
+    sum = mult_fix((uint32_t)row[(p.b - 1) * ch + c] * (uint32_t)(-p.accum), j.fx_scale);
+  }
+  uint32_t base = 0;
+  for (int xi = e.a; xi < e.b; ++xi) {
+    base = row[xi * ch + c];
+    sum += base;
+  }
+  return sum * (uint32_t)j.x_sub - base * (uint32_t)(-e.accum);
+}
+
+// unit = (job, output row, 256 output samples); a thread per output sample (x_out * channels + c)
+__global__ void __launch_bounds__(kThreads, 8)
+rescale_kernel(const RescaleJobDev* __restrict__ jobs, const uint32_t* __restrict__ prefix, uint32_t n_jobs, uint32_t uniform,
+               uint32_t total, const XEnt* __restrict__ xpool, const YEnt* __restrict__ ypool) {
+  for (uint32_t unit = blockIdx.x; unit < total; unit += gridDim.x) {
+    uint32_t local;
+    const uint32_t img = b2_find_image(prefix, n_jobs, uniform, unit, &local);
+    const RescaleJobDev j = jobs[img];
+    const int dy = (int)(local / j.units_x);
+    const int s = (int)(local % j.units_x) * kThreads + (int)threadIdx.x;
+    const int ch = j.num_channels;
+    if (s >= j.dst_width * ch) continue;
+    const int xo = s / ch, c = s - xo * ch;
+    const XEnt* __restrict__ xt = xpool + j.xtab;
+    const YEnt e = ypool[j.ytab + dy];
+    if (e.last < 0) continue;                     // the state machine never exports this row
+    const uint8_t* last_row = j.src + (ptrdiff_t)e.last * j.src_stride;
+    uint32_t v;
+    if (j.y_expand) {                             // ExportRowExpand, rescaler.c.go:110-136
+      const uint32_t f = frow_at(j, xt, last_row, xo, c);
+      uint32_t J = f;
+      if (e.y_accum != 0) {
+        const uint32_t i = (e.last > 0) ? frow_at(j, xt, last_row - j.src_stride, xo, c) : 0u;   // irow = the previous row's frow
+        const uint32_t B = (uint32_t)(((uint64_t)(uint32_t)(-e.y_accum) << 32) / (uint32_t)j.y_sub);
+        const uint32_t A = (uint32_t)(kOne - B);
+        J = (uint32_t)(((uint64_t)A * f + (uint64_t)B * i + kRounder) >> 32);
+      }
+      v = mult_fix(J, j.fy_scale);
+    } else {                                      // rows accumulated since the previous export (+ its fractional rest)
+      uint32_t irow = 0;
+      if (e.prev_last >= 0 && e.prev_yscale != 0u)
+        irow = mult_fix_floor(frow_at(j, xt, j.src + (ptrdiff_t)e.prev_last * j.src_stride, xo, c), e.prev_yscale);
+      uint32_t f = 0;
+      for (int r = e.prev_last + 1; r <= e.last; ++r) {
+        f = frow_at(j, xt, j.src + (ptrdiff_t)r * j.src_stride, xo, c);
+        irow += f;
+      }
+      if (j.fxy_scale == 0u) {                    // special case, rescaler.c.go:184-191
+        v = irow & 0xffu;
+        j.dst[(ptrdiff_t)dy * j.dst_stride + s] = (uint8_t)v;
+        continue;
+      }
+      if (e.yscale != 0u) v = mult_fix(irow - mult_fix_floor(f, e.yscale), j.fxy_scale);   // ExportRowShrink :138-163
+      else v = mult_fix(irow, j.fxy_scale);
+    }
+    j.dst[(ptrdiff_t)dy * j.dst_stride + s] = (uint8_t)min(v, 255u);
+  }
+}
+
+struct Geometry {
+  int x_expand, y_expand, x_add, x_sub, y_add, y_sub;
+  uint32_t fx_scale, fy_scale, fxy_scale;
+};
+
+// WebPRescalerInit, rescaler_utils.c.go:31-86
+Geometry init_geometry(int sw, int sh, int dw, int dh) {
+  Geometry g;
+  g.x_expand = sw < dw;
+  g.y_expand = sh < dh;
+  g.x_add = g.x_expand ? (dw - 1) : sw;
+  g.x_sub = g.x_expand ? (sw - 1) : dw;
+  g.fx_scale = g.x_expand ? 0u : (uint32_t)(kOne / (uint64_t)g.x_sub);
+  g.y_add = g.y_expand ? (sh - 1) : sh;
+  g.y_sub = g.y_expand ? (dh - 1) : dh;
+  g.fxy_scale = 0;
+  if (!g.y_expand) {
+    const uint64_t ratio = ((uint64_t)dh * kOne) / ((uint64_t)g.x_add * (uint64_t)g.y_add);
+    g.fxy_scale = (ratio != (uint32_t)ratio) ? 0u : (uint32_t)ratio;
+    g.fy_scale = (uint32_t)(kOne / (uint64_t)g.y_sub);
+  } else {
+    g.fy_scale = (uint32_t)(kOne / (uint64_t)g.x_add);
+  }
+  return g;
+}
+
+// the horizontal accumulator walk of ImportRowExpand / ImportRowShrink
+void build_xtab(const Geometry& g, int sw, int dw, std::vector<XEnt>* out) {
+  if (g.x_expand) {
+    int x_in = 0, accum = g.x_add;
+    int left = 0, right = (sw > 1) ? 1 : 0;
+    x_in = right;
+    for (int xo = 0;; ) {
+      out->push_back(XEnt{left, right, accum});
+      if (++xo >= dw) break;
+      accum -= g.x_sub;
+      if (accum < 0) {
+        left = right;
+        x_in += 1;
+        right = x_in;
+        accum += g.x_add;
+      }
+    }
+  } else {
+    int x_in = 0, accum = 0;
+    for (int xo = 0; xo < dw; ++xo) {
+      const int begin = x_in;
+      accum += g.x_add;
+      while (accum > 0) { accum -= g.x_sub; ++x_in; }
+      out->push_back(XEnt{begin, x_in, accum});
+    }
+  }
+}
+
+// the vertical walk of WebPRescalerImport / WebPRescalerExport (rescaler_utils.c.go:119-158)
+void build_ytab(const Geometry& g, int sh, int dh, std::vector<YEnt>* out) {
+  const size_t first = out->size();
+  out->resize(first + (size_t)dh, YEnt{-1, -1, 0, 0u, 0u});
+  int y_accum = g.y_expand ? g.y_sub : g.y_add;
+  int src_y = 0, dst_y = 0, last = -1, prev_last = -1;
+  uint32_t prev_yscale = 0;
+  while (src_y < sh) {
+    while (src_y < sh && !(dst_y < dh && y_accum <= 0)) {
+      last = src_y++;
+      y_accum -= g.y_sub;
+    }
+    while (dst_y < dh && y_accum <= 0) {
+      const uint32_t yscale = g.y_expand ? 0u : g.fy_scale * (uint32_t)(-y_accum);
+      (*out)[first + (size_t)dst_y] = YEnt{prev_last, last, y_accum, prev_yscale, yscale};
+      prev_last = last;
+      prev_yscale = yscale;
+      y_accum += g.y_add;
+      ++dst_y;
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int b2_rescale_planes(b2_ctx* ctx, int stream, const b2_rescale_job* jobs, int n_jobs) {
+  B2_CHECK_CTX(ctx, stream);
+  if (n_jobs < 0) return B2_ERR_INVALID_CONFIG;
+  if (n_jobs == 0) return B2_OK;
+  if (jobs == NULL) return B2_ERR_NULL;
+  std::vector<RescaleJobDev> dj((size_t)n_jobs);
+  std::vector<uint32_t> pre((size_t)n_jobs + 1);
+  std::vector<XEnt> xpool;
+  std::vector<YEnt> ypool;
+  std::map<std::tuple<int, int, int, int>, std::pair<uint32_t, uint32_t>> seen;   // geometry -> table offsets
+  uint64_t tot = 0;
+  uint32_t uni = 0;
+  for (int i = 0; i < n_jobs; ++i) {
+    const b2_rescale_job& j = jobs[i];
+    if (j.src == NULL || j.dst == NULL) return B2_ERR_NULL;
+    if (j.src_width <= 0 || j.src_height <= 0 || j.dst_width <= 0 || j.dst_height <= 0 || j.src_width > B2_MAX_DIMENSION ||
+        j.src_height > B2_MAX_DIMENSION || j.dst_width > B2_MAX_DIMENSION || j.dst_height > B2_MAX_DIMENSION) return B2_ERR_BAD_DIM;
+    if (j.num_channels < 1 || j.num_channels > 4) return B2_ERR_INVALID_CONFIG;
+    if (j.src_stride < j.src_width * j.num_channels || j.dst_stride < j.dst_width * j.num_channels) return B2_ERR_BAD_DIM;
+    const Geometry g = init_geometry(j.src_width, j.src_height, j.dst_width, j.dst_height);
+    const auto key = std::make_tuple(j.src_width, j.src_height, j.dst_width, j.dst_height);
+    auto it = seen.find(key);
+    if (it == seen.end()) {
+      const uint32_t xo = (uint32_t)xpool.size(), yo = (uint32_t)ypool.size();
+      build_xtab(g, j.src_width, j.dst_width, &xpool);
+      build_ytab(g, j.src_height, j.dst_height, &ypool);
+      it = seen.emplace(key, std::make_pair(xo, yo)).first;
+    }
+    RescaleJobDev& d = dj[(size_t)i];
+    d.src = j.src; d.dst = j.dst; d.src_stride = j.src_stride; d.dst_stride = j.dst_stride;
+    d.dst_width = j.dst_width; d.dst_height = j.dst_height; d.num_channels = j.num_channels;
+    d.x_expand = g.x_expand; d.y_expand = g.y_expand; d.x_add = g.x_add; d.x_sub = g.x_sub; d.y_sub = g.y_sub;
+    d.fx_scale = g.fx_scale; d.fy_scale = g.fy_scale; d.fxy_scale = g.fxy_scale;
+    d.xtab = it->second.first; d.ytab = it->second.second;
+    d.units_x = (uint32_t)((j.dst_width * j.num_channels + kThreads - 1) / kThreads);
+    const uint32_t items = d.units_x * (uint32_t)j.dst_height;
+    if (i == 0) uni = items; else if (items != uni) uni = 0;
+    pre[(size_t)i] = (uint32_t)tot;
+    tot += items;
+    if (tot > 0x7fffffffull) return B2_ERR_BAD_DIM;
+  }
+  pre[(size_t)n_jobs] = (uint32_t)tot;
+  const size_t jb = (sizeof(RescaleJobDev) * (size_t)n_jobs + 15) & ~(size_t)15;
+  const size_t pb = (sizeof(uint32_t) * ((size_t)n_jobs + 1) + 15) & ~(size_t)15;
+  const size_t xb = (sizeof(XEnt) * xpool.size() + 15) & ~(size_t)15;
+  const size_t yb = sizeof(YEnt) * ypool.size();
+  if (jb + pb + xb + yb > B2_DESC_RING_BYTES) return B2_ERR_INVALID_CONFIG;   // too many distinct geometries for one call
+  std::vector<uint8_t> host(jb + pb + xb + yb);
+  memcpy(host.data(), dj.data(), sizeof(RescaleJobDev) * (size_t)n_jobs);
+  memcpy(host.data() + jb, pre.data(), sizeof(uint32_t) * ((size_t)n_jobs + 1));
+  memcpy(host.data() + jb + pb, xpool.data(), sizeof(XEnt) * xpool.size());
+  memcpy(host.data() + jb + pb + xb, ypool.data(), yb);
+  void* dev = NULL;
+  const int st = b2_upload_desc(ctx, stream, host.data(), host.size(), &dev);
+  if (st != B2_OK) return st;
+  const uint8_t* base = (const uint8_t*)dev;
+  rescale_kernel<<<b2_grid_for(ctx, 8, tot), kThreads, 0, ctx->streams[stream]>>>(
+      (const RescaleJobDev*)base, (const uint32_t*)(base + jb), (uint32_t)n_jobs, uni, (uint32_t)tot,
+      (const XEnt*)(base + jb + pb), (const YEnt*)(base + jb + pb + xb));
+  ctx->launches++;
+  B2_CUDA(ctx, cudaGetLastError());
+  return B2_OK;
+}

@@ -617,3 +617,30 @@ func (c *Context) AlphaFilter(stream int, jobs []AlphaFilterJob) error {
 	cj := alphaFilterJobs(jobs)
 	return status(c, C.b2_alpha_filter(c.h, C.int(stream), &cj[0], C.int(len(cj))))
 }
+
+// RescaleJob is one plane of the rescaler (include/b2webp.h b2_rescale_job); strides in bytes.
+type RescaleJob struct {
+	Src, Dst                         DevicePtr
+	SrcWidth, SrcHeight, SrcStride   int
+	DstWidth, DstHeight, DstStride   int
+	NumChannels                      int
+}
+
+// RescalePlanes replaces RescalePlane (pkg/libwebp/enc/picture_rescale_enc.c.go:125-136):
+// WebPRescalerInit / Import / Export with the import / export row functions of
+// pkg/libwebp/dsp/rescaler.c.go.
+func (c *Context) RescalePlanes(stream int, jobs []RescaleJob) error {
+	if len(jobs) == 0 {
+		return nil
+	}
+	cj := make([]C.b2_rescale_job, len(jobs))
+	for i, j := range jobs {
+		cj[i] = C.b2_rescale_job{
+			src: (*C.uint8_t)(unsafe.Pointer(uintptr(j.Src))), dst: (*C.uint8_t)(unsafe.Pointer(uintptr(j.Dst))),
+			src_width: C.int32_t(j.SrcWidth), src_height: C.int32_t(j.SrcHeight), src_stride: C.int32_t(j.SrcStride),
+			dst_width: C.int32_t(j.DstWidth), dst_height: C.int32_t(j.DstHeight), dst_stride: C.int32_t(j.DstStride),
+			num_channels: C.int32_t(j.NumChannels),
+		}
+	}
+	return status(c, C.b2_rescale_planes(c.h, C.int(stream), &cj[0], C.int(len(cj))))
+}

@@ -1,0 +1,87 @@
+"""Host-side mirror of the rescaler: RescalePlane (pkg/libwebp/enc/
+picture_rescale_enc.c.go:125-136) over WebPRescalerImport / WebPRescalerExport
+(pkg/libwebp/utils/rescaler_utils.c.go:119-158), WebPRescalerGetScaledDimensions (:88-113)
+and the YUV branch of WebPPictureRescale (:149-200, pictures without alpha), plus one added
+batched entry point.  The work happens in b2_rescale.cu through the C ABI (no CPU fallback)."""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _abi
+from .device import Context
+from .picture import (ENC_ERROR_BAD_DIMENSION, ENC_ERROR_OUT_OF_MEMORY, Picture, _al, _arena, _STATUS_TO_ENC,
+                      default_context)
+from ._abi import B2Error
+
+
+def WebPRescalerGetScaledDimensions(src_width: int, src_height: int, scaled_width: int, scaled_height: int):
+    """rescaler_utils.c.go:88-113: returns (ok, width, height); a 0 dimension follows the ratio."""
+    width, height = scaled_width, scaled_height
+    max_size = (2**31 - 1) // 2
+    if width == 0 and src_height > 0:
+        width = (src_width * height + src_height - 1) // src_height
+    if height == 0 and src_width > 0:
+        height = (src_height * width + src_width - 1) // src_width
+    if width <= 0 or height <= 0 or width > max_size or height > max_size:
+        return 0, scaled_width, scaled_height
+    return 1, width, height
+
+
+def RescalePlanesBatch(planes, sizes, num_channels: int = 1, ctx: Context | None = None):
+    """Added batched entry point: planes[i] (uint8 [h, w * num_channels]) rescaled to
+    sizes[i] = (dst_width, dst_height).  Returns the list of outputs."""
+    ctx = ctx or default_context()
+    lib, hnd = ctx.lib, ctx.h
+    n = len(planes)
+    if n == 0:
+        return []
+    metas, need = [], 0
+    for p, (dw, dh) in zip(planes, sizes):
+        h, wc = p.shape
+        ss, ds = _al(wc, 16), _al(dw * num_channels, 16)
+        metas.append((wc // num_channels, h, ss, dw, dh, ds))
+        need += _al(ss * h) + _al(ds * dh)
+    ar = _arena(ctx)
+    ar.reset(need)
+    jobs, ptrs = [], []
+    for (w, h, ss, dw, dh, ds), p in zip(metas, planes):
+        ps, pd = ar.take(ss * h), ar.take(ds * dh)
+        p = np.ascontiguousarray(p, np.uint8)
+        ctx._chk(lib.b2_h2d_2d_async(hnd, 0, ps, ss, p.ctypes.data, w * num_channels, w * num_channels, h))
+        jobs.append(_abi.RescaleJob(ps, pd, w, h, ss, dw, dh, ds, num_channels, 0))
+        ptrs.append(pd)
+    arr = (_abi.RescaleJob * n)(*jobs)
+    ctx._chk(lib.b2_rescale_planes(hnd, 0, arr, n))
+    outs = []
+    for (w, h, ss, dw, dh, ds), pd in zip(metas, ptrs):
+        o = np.empty((dh, dw * num_channels), np.uint8)
+        ctx._chk(lib.b2_d2h_2d_async(hnd, 0, o.ctypes.data, dw * num_channels, pd, ds, dw * num_channels, dh))
+        outs.append(o)
+    ctx.sync()
+    return outs
+
+
+def RescalePlane(src: np.ndarray, dst_width: int, dst_height: int, num_channels: int = 1) -> np.ndarray:
+    """picture_rescale_enc.c.go:125-136."""
+    return RescalePlanesBatch([src], [(dst_width, dst_height)], num_channels)[0]
+
+
+def WebPPictureRescale(pic: Picture, width: int, height: int) -> int:
+    """picture_rescale_enc.c.go:149-200 for YUV420 pictures without alpha (the ARGB and
+    alpha branches premultiply around the same RescalePlane calls: not mirrored here)."""
+    if pic is None:
+        return 0
+    ok, width, height = WebPRescalerGetScaledDimensions(pic.Width, pic.Height, width, height)
+    if not ok:
+        return pic.SetEncodingError(ENC_ERROR_BAD_DIMENSION)
+    if pic.UseARGB or pic.A is not None:
+        raise NotImplementedError("WebPPictureRescale: only the YUV420 branch without alpha is mirrored")
+    halve = lambda x: (x + 1) >> 1  # noqa: E731
+    try:
+        y = RescalePlane(pic.Y, width, height)
+        u, v = RescalePlanesBatch([pic.U, pic.V], [(halve(width), halve(height))] * 2)
+    except B2Error as e:
+        return pic.SetEncodingError(_STATUS_TO_ENC.get(e.status, ENC_ERROR_OUT_OF_MEMORY))
+    pic.Y, pic.U, pic.V = y, u, v
+    pic.Width, pic.Height, pic.YStride, pic.UVStride = width, height, width, halve(width)
+    return 1

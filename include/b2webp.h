@@ -391,6 +391,21 @@ typedef struct b2_alpha_filter_job {
 int b2_alpha_unfilter(b2_ctx* ctx, int stream, const b2_alpha_filter_job* jobs, int n_jobs);
 int b2_alpha_filter(b2_ctx* ctx, int stream, const b2_alpha_filter_job* jobs, int n_jobs);
 
+/* The fixed-point rescaler: WebPRescalerInit / Import / Export
+ * (pkg/libwebp/utils/rescaler_utils.c.go:31-158) with WebPRescalerImportRow{Expand,Shrink}
+ * and WebPRescalerExportRow{Expand,Shrink} (pkg/libwebp/dsp/rescaler.c.go:39-197) over a
+ * whole plane of num_channels interleaved byte channels, as RescalePlane drives them
+ * (pkg/libwebp/enc/picture_rescale_enc.c.go:125-136).  Strides in bytes, dst != src. */
+typedef struct b2_rescale_job {
+  const uint8_t* src;
+  uint8_t* dst;
+  int32_t src_width, src_height, src_stride;
+  int32_t dst_width, dst_height, dst_stride;
+  int32_t num_channels; /* 1..4 */
+  int32_t reserved;
+} b2_rescale_job;
+int b2_rescale_planes(b2_ctx* ctx, int stream, const b2_rescale_job* jobs, int n_jobs);
+
 /* ---- synthetic inputs (SURVEY.md 8d generator, identical to the oracle's) -
  * One uint32 per (row, word) position of n images laid out 'image_bytes'
  * apart, image ids first_img, first_img+1, ...  alpha_mode shapes the top byte

@@ -431,3 +431,15 @@ def alpha_filter(plane, filt):
     out = np.empty_like(plane)
     lib().orc_alpha_filter(int(filt), _p(plane), w, _p(out), w, w, h)
     return out
+
+
+# ---- rescaler (oracle_tools.c) ----------------------------------------
+def rescale_plane(plane, dst_width, dst_height, num_channels=1):
+    """RescalePlane: plane uint8 [h, w * num_channels] -> [dst_height, dst_width * num_channels]."""
+    plane = np.ascontiguousarray(plane, np.uint8)
+    h, wc = plane.shape
+    w = wc // num_channels
+    out = np.zeros((dst_height, dst_width * num_channels), np.uint8)
+    ok = lib().orc_rescale_plane(_p(plane), w, h, wc, _p(out), dst_width, dst_height, dst_width * num_channels, num_channels)
+    assert ok
+    return out

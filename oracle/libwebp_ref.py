@@ -245,3 +245,23 @@ def argb_to_yuva_dithered(argb: np.ndarray, dithering: float):
            _plane(p.a, p.a_stride, w, h) if has_alpha else None, has_alpha)
     L.WebPPictureFree(C.byref(p))
     return out
+
+
+def picture_rescale_yuv(y, u, v, width, height):
+    """WebPPictureRescale (exported) on a YUV420 picture without alpha -> (y, u, v)."""
+    L = lib()
+    h, w = y.shape
+    p = WebPPicture()
+    assert L.WebPPictureInitInternal(C.byref(p), 0x0210)
+    p.width, p.height, p.use_argb, p.colorspace = w, h, 0, 0
+    assert L.WebPPictureAlloc(C.byref(p))
+    for ptr, stride, arr in ((p.y, p.y_stride, y), (p.u, p.uv_stride, u), (p.v, p.uv_stride, v)):
+        hh, ww = arr.shape
+        buf = (C.c_uint8 * (stride * hh)).from_address(ptr)
+        np.frombuffer(buf, np.uint8).reshape(hh, stride)[:, :ww] = arr
+    if not L.WebPPictureRescale(C.byref(p), width, height):
+        raise ValueError("WebPPictureRescale failed")
+    uvw, uvh = (p.width + 1) >> 1, (p.height + 1) >> 1
+    out = (_plane(p.y, p.y_stride, p.width, p.height), _plane(p.u, p.uv_stride, uvw, uvh), _plane(p.v, p.uv_stride, uvw, uvh))
+    L.WebPPictureFree(C.byref(p))
+    return out

@@ -399,3 +399,192 @@ void orc_alpha_filter(int filter, const uint8_t* in, int in_stride, uint8_t* out
     }
   }
 }
+
+/* ---- rescaler ---------------------------------------------------------- */
+/* pkg/libwebp/utils/rescaler_utils.h.go (WebPRescaler, WEBP_RESCALER_RFIX = 32) */
+typedef uint32_t rescaler_t;
+#define RS_RFIX 32
+#define RS_ONE (1ull << RS_RFIX)
+#define RS_FRAC(x, y) ((uint32_t)(((uint64_t)(x) << RS_RFIX) / (y)))
+#define RS_ROUNDER (RS_ONE >> 1)
+#define RS_MULT_FIX(x, y) (((uint64_t)(x) * (y) + RS_ROUNDER) >> RS_RFIX)
+#define RS_MULT_FIX_FLOOR(x, y) (((uint64_t)(x) * (y)) >> RS_RFIX)
+typedef struct {
+  int x_expand, y_expand, num_channels;
+  uint32_t fx_scale, fy_scale, fxy_scale;
+  int y_accum, y_add, y_sub, x_add, x_sub;
+  int src_width, src_height, dst_width, dst_height, src_y, dst_y;
+  uint8_t* dst;
+  int dst_stride;
+  rescaler_t *irow, *frow;
+} Rescaler;
+/* pkg/libwebp/utils/rescaler_utils.c.go:31-86 */
+static void RescalerInit(Rescaler* r, int src_width, int src_height, uint8_t* dst, int dst_width, int dst_height,
+                         int dst_stride, int num_channels, rescaler_t* work) {
+  const int x_add = src_width, x_sub = dst_width, y_add = src_height, y_sub = dst_height;
+  r->x_expand = (src_width < dst_width);
+  r->y_expand = (src_height < dst_height);
+  r->src_width = src_width; r->src_height = src_height; r->dst_width = dst_width; r->dst_height = dst_height;
+  r->src_y = 0; r->dst_y = 0; r->dst = dst; r->dst_stride = dst_stride; r->num_channels = num_channels;
+  r->irow = work;
+  r->frow = work + num_channels * dst_width;
+  memset(work, 0, sizeof(*work) * 2 * (size_t)dst_width * num_channels);
+  r->x_add = r->x_expand ? (x_sub - 1) : x_add;
+  r->x_sub = r->x_expand ? (x_add - 1) : x_sub;
+  r->fx_scale = 0;
+  if (!r->x_expand) r->fx_scale = RS_FRAC(1, r->x_sub);
+  r->y_add = r->y_expand ? (y_add - 1) : y_add;
+  r->y_sub = r->y_expand ? (y_sub - 1) : y_sub;
+  r->y_accum = r->y_expand ? r->y_sub : r->y_add;
+  r->fxy_scale = 0;
+  if (!r->y_expand) {
+    const uint64_t num = (uint64_t)dst_height * RS_ONE;
+    const uint64_t den = (uint64_t)r->x_add * r->y_add;
+    const uint64_t ratio = num / den;
+    r->fxy_scale = (ratio != (uint32_t)ratio) ? 0 : (uint32_t)ratio;
+    r->fy_scale = RS_FRAC(1, r->y_sub);
+  } else {
+    r->fy_scale = RS_FRAC(1, r->x_add);
+  }
+}
+/* pkg/libwebp/dsp/rescaler.c.go:39-69 */
+static void ImportRowExpand(Rescaler* wrk, const uint8_t* src) {
+  const int x_stride = wrk->num_channels, x_out_max = wrk->dst_width * wrk->num_channels;
+  for (int channel = 0; channel < x_stride; ++channel) {
+    int x_in = channel, x_out = channel;
+    int accum = wrk->x_add;
+    rescaler_t left = (rescaler_t)src[x_in];
+    rescaler_t right = (wrk->src_width > 1) ? (rescaler_t)src[x_in + x_stride] : left;
+    x_in += x_stride;
+    while (1) {
+      wrk->frow[x_out] = right * wrk->x_add + (left - right) * accum;
+      x_out += x_stride;
+      if (x_out >= x_out_max) break;
+      accum -= wrk->x_sub;
+      if (accum < 0) {
+        left = right;
+        x_in += x_stride;
+        right = (rescaler_t)src[x_in];
+        accum += wrk->x_add;
+      }
+    }
+  }
+}
+/* rescaler.c.go:71-105 */
+static void ImportRowShrink(Rescaler* wrk, const uint8_t* src) {
+  const int x_stride = wrk->num_channels, x_out_max = wrk->dst_width * wrk->num_channels;
+  for (int channel = 0; channel < x_stride; ++channel) {
+    int x_in = channel, x_out = channel;
+    uint32_t sum = 0;
+    int accum = 0;
+    while (x_out < x_out_max) {
+      uint32_t base = 0;
+      accum += wrk->x_add;
+      while (accum > 0) {
+        accum -= wrk->x_sub;
+        base = src[x_in];
+        sum += base;
+        x_in += x_stride;
+      }
+      {
+        const rescaler_t frac = base * (-accum);
+        wrk->frow[x_out] = sum * wrk->x_sub - frac;
+        sum = (int)RS_MULT_FIX(frac, wrk->fx_scale);
+      }
+      x_out += x_stride;
+    }
+  }
+}
+/* rescaler.c.go:110-136 */
+static void ExportRowExpand(Rescaler* wrk) {
+  uint8_t* dst = wrk->dst;
+  const int x_out_max = wrk->dst_width * wrk->num_channels;
+  if (wrk->y_accum == 0) {
+    for (int x_out = 0; x_out < x_out_max; ++x_out) {
+      const uint32_t J = wrk->frow[x_out];
+      const int v = (int)RS_MULT_FIX(J, wrk->fy_scale);
+      dst[x_out] = (v > 255) ? 255u : (uint8_t)v;
+    }
+  } else {
+    const uint32_t B = RS_FRAC(-wrk->y_accum, wrk->y_sub);
+    const uint32_t A = (uint32_t)(RS_ONE - B);
+    for (int x_out = 0; x_out < x_out_max; ++x_out) {
+      const uint64_t I = (uint64_t)A * wrk->frow[x_out] + (uint64_t)B * wrk->irow[x_out];
+      const uint32_t J = (uint32_t)((I + RS_ROUNDER) >> RS_RFIX);
+      const int v = (int)RS_MULT_FIX(J, wrk->fy_scale);
+      dst[x_out] = (v > 255) ? 255u : (uint8_t)v;
+    }
+  }
+}
+/* rescaler.c.go:138-163 */
+static void ExportRowShrink(Rescaler* wrk) {
+  uint8_t* dst = wrk->dst;
+  const int x_out_max = wrk->dst_width * wrk->num_channels;
+  const uint32_t yscale = wrk->fy_scale * (-wrk->y_accum);
+  if (yscale) {
+    for (int x_out = 0; x_out < x_out_max; ++x_out) {
+      const uint32_t frac = (uint32_t)RS_MULT_FIX_FLOOR(wrk->frow[x_out], yscale);
+      const int v = (int)RS_MULT_FIX(wrk->irow[x_out] - frac, wrk->fxy_scale);
+      dst[x_out] = (v > 255) ? 255u : (uint8_t)v;
+      wrk->irow[x_out] = frac;
+    }
+  } else {
+    for (int x_out = 0; x_out < x_out_max; ++x_out) {
+      const int v = (int)RS_MULT_FIX(wrk->irow[x_out], wrk->fxy_scale);
+      dst[x_out] = (v > 255) ? 255u : (uint8_t)v;
+      wrk->irow[x_out] = 0;
+    }
+  }
+}
+/* rescaler.c.go:178-197 + rescaler_utils.h (HasPendingOutput = !OutputDone && y_accum <= 0) */
+static int HasPendingOutput(const Rescaler* r) { return r->dst_y < r->dst_height && r->y_accum <= 0; }
+static void ExportRow(Rescaler* wrk) {
+  if (wrk->y_accum <= 0) {
+    if (wrk->y_expand) {
+      ExportRowExpand(wrk);
+    } else if (wrk->fxy_scale) {
+      ExportRowShrink(wrk);
+    } else { /* special case */
+      for (int i = 0; i < wrk->num_channels * wrk->dst_width; ++i) {
+        wrk->dst[i] = (uint8_t)wrk->irow[i];
+        wrk->irow[i] = 0;
+      }
+    }
+    wrk->y_accum += wrk->y_add;
+    wrk->dst += wrk->dst_stride;
+    ++wrk->dst_y;
+  }
+}
+/* RescalePlane (pkg/libwebp/enc/picture_rescale_enc.c.go:125-136) over WebPRescalerImport /
+ * WebPRescalerExport (rescaler_utils.c.go:119-158). */
+int orc_rescale_plane(const uint8_t* src, int src_width, int src_height, int src_stride, uint8_t* dst, int dst_width,
+                      int dst_height, int dst_stride, int num_channels) {
+  Rescaler r;
+  rescaler_t* work = (rescaler_t*)malloc(sizeof(rescaler_t) * 2 * (size_t)dst_width * num_channels);
+  int y = 0;
+  if (work == NULL) return 0;
+  RescalerInit(&r, src_width, src_height, dst, dst_width, dst_height, dst_stride, num_channels, work);
+  while (y < src_height) {
+    int num_lines = src_height - y, total_imported = 0;
+    const uint8_t* s = src + (ptrdiff_t)y * src_stride;
+    while (total_imported < num_lines && !HasPendingOutput(&r)) {
+      if (r.y_expand) {
+        rescaler_t* const tmp = r.irow;
+        r.irow = r.frow;
+        r.frow = tmp;
+      }
+      if (!r.x_expand) ImportRowShrink(&r, s); else ImportRowExpand(&r, s);
+      if (!r.y_expand) {
+        for (int x = 0; x < r.num_channels * r.dst_width; ++x) r.irow[x] += r.frow[x];
+      }
+      ++r.src_y;
+      s += src_stride;
+      ++total_imported;
+      r.y_accum -= r.y_sub;
+    }
+    y += total_imported;
+    while (HasPendingOutput(&r)) ExportRow(&r);
+  }
+  free(work);
+  return 1;
+}

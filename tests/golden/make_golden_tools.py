@@ -1,6 +1,8 @@
 """Generate tests/golden/tools_libwebp160.npz: WebPCleanupTransparentArea and
 WebPBlendAlpha (both exported by the libwebp 1.6.0 binary) on YUVA and ARGB pictures,
-and tests/golden/import_argb_libwebp160.npz: the use_argb branch of WebPPictureImport*.
+tests/golden/import_argb_libwebp160.npz: the use_argb branch of WebPPictureImport*,
+import_dithered_libwebp160.npz (WebPPictureARGBToYUVADithered) and rescale_libwebp160.npz
+(WebPPictureRescale).
 
     python tests/golden/make_golden_tools.py
 
@@ -136,7 +138,33 @@ def gen_dithered():
     print(f"{n} cases: oracle == libwebp binary for the dithered import")
 
 
+def gen_rescale():
+    """rescale_libwebp160.npz: WebPPictureRescale (exported) on YUV420 pictures without
+    alpha: RescalePlane on the Y, U and V planes (pkg/libwebp/enc/picture_rescale_enc.c.go:
+    125-136, 149-200), every combination of horizontal / vertical expansion and shrinking."""
+    rng = np.random.default_rng(3)
+    store, names = {}, []
+    n = 0
+    for (w, h, dw, dh) in [(64, 48, 32, 24), (64, 48, 100, 70), (33, 17, 20, 40), (50, 50, 50, 50), (7, 9, 3, 2), (3, 2, 9, 11),
+                           (100, 3, 37, 3), (1, 1, 5, 5), (20, 30, 1, 1), (120, 80, 119, 81), (16, 16, 17, 15), (300, 40, 77, 111),
+                           (2, 64, 2, 64), (1, 40, 2, 40)]:
+        y = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        u = rng.integers(0, 256, ((h + 1) // 2, (w + 1) // 2), dtype=np.uint8)
+        v = rng.integers(0, 256, ((h + 1) // 2, (w + 1) // 2), dtype=np.uint8)
+        ey, eu, ev = ref.picture_rescale_yuv(y, u, v, dw, dh)
+        for src, exp in ((y, ey), (u, eu), (v, ev)):
+            assert (oracle.rescale_plane(src, exp.shape[1], exp.shape[0]) == exp).all(), (w, h, dw, dh)
+            k = f"c{n}"
+            n += 1
+            names.append(k)
+            store[f"{k}/src"], store[f"{k}/dst"] = src, exp
+    store["names"] = np.array(names)
+    np.savez_compressed(os.path.join(HERE, "rescale_libwebp160.npz"), **store)
+    print(f"{n} planes: oracle == libwebp binary for the rescaler")
+
+
 if __name__ == "__main__":
     main()
     gen_import_argb()
     gen_dithered()
+    gen_rescale()

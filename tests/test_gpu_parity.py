@@ -923,3 +923,32 @@ def test_alpha_filters(gpu, golden_dir):
     out = np.zeros_like(data)
     F.GradientFilter_C(data, 33, 7, 40, out)
     assert (out.reshape(7, 40)[:, :33] == oracle.alpha_filter(data.reshape(7, 40)[:, :33], 3)).all()
+
+
+def test_rescaler(gpu, golden_dir):
+    """The rescaler: the WebPPictureRescale vectors in one batch (all mixes of
+    horizontal / vertical expansion and shrinking, identity, 1-pixel sources), seeded planes
+    with 1, 3 and 4 interleaved channels vs the oracle, WebPPictureRescale on a picture."""
+    from go_webp_b200 import rescaler as R
+    P = gpu["picture"]
+    g = np.load(os.path.join(golden_dir, "rescale_libwebp160.npz"))
+    ks = [str(k) for k in g["names"]]
+    outs = R.RescalePlanesBatch([g[f"{k}/src"] for k in ks], [g[f"{k}/dst"].shape[::-1] for k in ks])
+    for k, o in zip(ks, outs):
+        assert (o == g[f"{k}/dst"]).all(), k
+    rng = np.random.default_rng(2718)
+    for ch in (1, 3, 4):
+        for (w, h, dw, dh) in [(640, 360, 213, 120), (100, 80, 333, 201), (257, 3, 64, 9), (31, 200, 90, 41), (500, 20, 500, 7)]:
+            src = rng.integers(0, 256, (h, w * ch), dtype=np.uint8)
+            o = R.RescalePlane(src, dw, dh, ch)
+            e = oracle.rescale_plane(src, dw, dh, ch)
+            assert (o == e).all(), (ch, w, h, dw, dh, np.argwhere(o != e)[:3])
+    y = rng.integers(0, 256, (90, 160), dtype=np.uint8)
+    u = rng.integers(0, 256, (45, 80), dtype=np.uint8)
+    v = rng.integers(0, 256, (45, 80), dtype=np.uint8)
+    pic = P.Picture(Width=160, Height=90, Y=y, U=u, V=v)
+    assert R.WebPPictureRescale(pic, 64, 0) == 1          # height follows the ratio
+    assert (pic.Width, pic.Height) == (64, 36)
+    assert (pic.Y == oracle.rescale_plane(y, 64, 36)).all() and (pic.U == oracle.rescale_plane(u, 32, 18)).all()
+    assert (pic.V == oracle.rescale_plane(v, 32, 18)).all()
+    assert R.WebPPictureRescale(P.Picture(Width=4, Height=4, Y=y[:4, :4], U=u[:2, :2], V=v[:2, :2]), 0, 0) == 0

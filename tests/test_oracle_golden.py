@@ -302,3 +302,15 @@ def test_alpha_unfilters_match_libwebp_streams(golden_dir):
         assert (oracle.alpha_unfilter(fin, f) == exp).all(), (k, f)
         assert (oracle.alpha_filter(exp, f) == fin).all(), (k, f)
     assert kinds == {0, 1, 2, 3}
+
+
+def test_rescaler_matches_libwebp_binary(golden_dir):
+    """RescalePlane (WebPRescaler import / export rows, rescaler.c.go:39-197) vs
+    WebPPictureRescale on the Y, U and V planes of pictures the binary rescaled."""
+    g = _load(golden_dir, "rescale_libwebp160.npz")
+    n = 0
+    for k in g["names"]:
+        src, dst = g[f"{k}/src"], g[f"{k}/dst"]
+        assert (oracle.rescale_plane(src, dst.shape[1], dst.shape[0]) == dst).all(), k
+        n += 1
+    assert n >= 40

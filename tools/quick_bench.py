@@ -123,3 +123,16 @@ if "filters" in which:
         report(f"alpha unfilter {name} {n}x1080p", n * w * h, 2.0, timed(lambda: ctx._chk(ctx.lib.b2_alpha_unfilter(ctx.h, 0, jobs, n)), 5))
         report(f"alpha filter   {name} {n}x1080p", n * w * h, 2.0, timed(lambda: ctx._chk(ctx.lib.b2_alpha_filter(ctx.h, 0, jobs, n)), 5))
     src.free(); dst.free()
+if "rescale" in which:
+    # rescaler: NF luma planes 3840x2160 -> 1920x1080 (shrink both ways) and 1920x1080 -> 3840x2160 (expand)
+    n = min(NF, 64)
+    for (w, h, dw, dh) in ((3840, 2160, 1920, 1080), (1920, 1080, 3840, 2160), (1920, 1080, 1280, 720)):
+        src = ctx.alloc(n * w * h)
+        dst = ctx.alloc(n * dw * dh)
+        ctx.synth_fill(src.ptr, w // 4, h, w, w * h, n, 0xB2000008, 0, 4)
+        ctx.sync()
+        jobs = (_abi.RescaleJob * n)(*[_abi.RescaleJob(src.ptr + i * w * h, dst.ptr + i * dw * dh, w, h, w, dw, dh, dw, 1, 0) for i in range(n)])
+        ms = timed(lambda: ctx._chk(ctx.lib.b2_rescale_planes(ctx.h, 0, jobs, n)), 5)
+        print(f"rescale {n} x {w}x{h} -> {dw}x{dh}: {n * w * h / ms / 1e3:9.0f} Mpx/s in, {n * (w * h + dw * dh) / ms / 1e6:7.0f} GB/s "
+              f"({n * (w * h + dw * dh) / ms / 1e6 / PEAK:.3f} of measured peak)")
+        src.free(); dst.free()

@@ -29,7 +29,8 @@ constexpr uint64_t kOne = 1ull << 32;
 constexpr uint64_t kRounder = kOne >> 1;
 
 struct XEnt { int32_t a, b, accum; };                 // expand: left, right sample; shrink: [a, b) consumed; accum after
-struct YEnt { int32_t prev_last, last, y_accum; uint32_t prev_yscale, yscale; };   // last < 0: row never exported
+struct YEnt { int32_t prev_last, last, y_accum; uint32_t prev_yscale, yscale; };   // last < 0: row never exported;
+                                                                                   // expand: yscale holds B = FRAC(-y_accum, y_sub)
 
 struct RescaleJobDev {
   const uint8_t* src;
@@ -66,52 +67,72 @@ __device__ __forceinline__ uint32_t frow_at(const RescaleJobDev& j, const XEnt* 
   return sum * (uint32_t)j.x_sub - base * (uint32_t)(-e.accum);
 }
 
-// unit = (job, output row, 256 output samples); a thread per output sample (x_out * channels + c)
+// one output sample: row dy, sample s = x_out * channels + c
+__device__ __forceinline__ uint32_t rescale_sample(const RescaleJobDev& j, const XEnt* __restrict__ xt, const YEnt& e, int xo, int c) {
+  const uint8_t* last_row = j.src + (ptrdiff_t)e.last * j.src_stride;
+  if (j.y_expand) {                               // ExportRowExpand, rescaler.c.go:110-136
+    const uint32_t f = frow_at(j, xt, last_row, xo, c);
+    uint32_t J = f;
+    if (e.y_accum != 0) {
+      const uint32_t i = (e.last > 0) ? frow_at(j, xt, last_row - j.src_stride, xo, c) : 0u;   // irow = the previous row's frow
+      const uint32_t B = e.yscale;   // WEBP_RESCALER_FRAC(-y_accum, y_sub), from the host
+      const uint32_t A = (uint32_t)(kOne - B);
+      J = (uint32_t)(((uint64_t)A * f + (uint64_t)B * i + kRounder) >> 32);
+    }
+    return min(mult_fix(J, j.fy_scale), 255u);
+  }
+  // rows accumulated since the previous export (+ its fractional rest)
+  uint32_t irow = 0;
+  if (e.prev_last >= 0 && e.prev_yscale != 0u)
+    irow = mult_fix_floor(frow_at(j, xt, j.src + (ptrdiff_t)e.prev_last * j.src_stride, xo, c), e.prev_yscale);
+  uint32_t f = 0;
+  for (int r = e.prev_last + 1; r <= e.last; ++r) {
+    f = frow_at(j, xt, j.src + (ptrdiff_t)r * j.src_stride, xo, c);
+    irow += f;
+  }
+  if (j.fxy_scale == 0u) return irow & 0xffu;     // special case, rescaler.c.go:184-191
+  if (e.yscale != 0u) return min(mult_fix(irow - mult_fix_floor(f, e.yscale), j.fxy_scale), 255u);   // ExportRowShrink :138-163
+  return min(mult_fix(irow, j.fxy_scale), 255u);
+}
+
+// unit = (job, output row, 1024 output samples); a thread computes 4 consecutive samples
+constexpr int kPerThread = 4;
 __global__ void __launch_bounds__(kThreads, 8)
 rescale_kernel(const RescaleJobDev* __restrict__ jobs, const uint32_t* __restrict__ prefix, uint32_t n_jobs, uint32_t uniform,
                uint32_t total, const XEnt* __restrict__ xpool, const YEnt* __restrict__ ypool) {
+  __shared__ RescaleJobDev sj;
+  __shared__ YEnt se;
   for (uint32_t unit = blockIdx.x; unit < total; unit += gridDim.x) {
     uint32_t local;
     const uint32_t img = b2_find_image(prefix, n_jobs, uniform, unit, &local);
-    const RescaleJobDev j = jobs[img];
-    const int dy = (int)(local / j.units_x);
-    const int s = (int)(local % j.units_x) * kThreads + (int)threadIdx.x;
-    const int ch = j.num_channels;
-    if (s >= j.dst_width * ch) continue;
-    const int xo = s / ch, c = s - xo * ch;
-    const XEnt* __restrict__ xt = xpool + j.xtab;
-    const YEnt e = ypool[j.ytab + dy];
-    if (e.last < 0) continue;                     // the state machine never exports this row
-    const uint8_t* last_row = j.src + (ptrdiff_t)e.last * j.src_stride;
-    uint32_t v;
-    if (j.y_expand) {                             // ExportRowExpand, rescaler.c.go:110-136
-      const uint32_t f = frow_at(j, xt, last_row, xo, c);
-      uint32_t J = f;
-      if (e.y_accum != 0) {
-        const uint32_t i = (e.last > 0) ? frow_at(j, xt, last_row - j.src_stride, xo, c) : 0u;   // irow = the previous row's frow
-        const uint32_t B = (uint32_t)(((uint64_t)(uint32_t)(-e.y_accum) << 32) / (uint32_t)j.y_sub);
-        const uint32_t A = (uint32_t)(kOne - B);
-        J = (uint32_t)(((uint64_t)A * f + (uint64_t)B * i + kRounder) >> 32);
-      }
-      v = mult_fix(J, j.fy_scale);
-    } else {                                      // rows accumulated since the previous export (+ its fractional rest)
-      uint32_t irow = 0;
-      if (e.prev_last >= 0 && e.prev_yscale != 0u)
-        irow = mult_fix_floor(frow_at(j, xt, j.src + (ptrdiff_t)e.prev_last * j.src_stride, xo, c), e.prev_yscale);
-      uint32_t f = 0;
-      for (int r = e.prev_last + 1; r <= e.last; ++r) {
-        f = frow_at(j, xt, j.src + (ptrdiff_t)r * j.src_stride, xo, c);
-        irow += f;
-      }
-      if (j.fxy_scale == 0u) {                    // special case, rescaler.c.go:184-191
-        v = irow & 0xffu;
-        j.dst[(ptrdiff_t)dy * j.dst_stride + s] = (uint8_t)v;
-        continue;
-      }
-      if (e.yscale != 0u) v = mult_fix(irow - mult_fix_floor(f, e.yscale), j.fxy_scale);   // ExportRowShrink :138-163
-      else v = mult_fix(irow, j.fxy_scale);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      sj = jobs[img];
+      se = ypool[sj.ytab + local / sj.units_x];
     }
-    j.dst[(ptrdiff_t)dy * j.dst_stride + s] = (uint8_t)min(v, 255u);
+    __syncthreads();
+    const RescaleJobDev& j = sj;
+    const YEnt& e = se;
+    if (e.last < 0) continue;                     // the state machine never exports this row
+    const int dy = (int)(local / j.units_x);
+    const int s0 = ((int)(local % j.units_x) * kThreads + (int)threadIdx.x) * kPerThread;
+    const int ch = j.num_channels, n_s = j.dst_width * ch;
+    if (s0 >= n_s) continue;
+    const XEnt* __restrict__ xt = xpool + j.xtab;
+    uint8_t* out = j.dst + (ptrdiff_t)dy * j.dst_stride + s0;
+    uint32_t v[kPerThread];
+    int xo = s0 / ch, c = s0 - xo * ch;
+#pragma unroll
+    for (int k = 0; k < kPerThread; ++k) {
+      v[k] = (s0 + k < n_s) ? rescale_sample(j, xt, e, xo, c) : 0u;
+      if (++c == ch) { c = 0; ++xo; }
+    }
+    if (s0 + kPerThread <= n_s && (((uintptr_t)out) & 3) == 0) {
+      *reinterpret_cast<uint32_t*>(out) = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
+    } else {
+#pragma unroll
+      for (int k = 0; k < kPerThread; ++k) if (s0 + k < n_s) out[k] = (uint8_t)v[k];
+    }
   }
 }
 
@@ -182,7 +203,8 @@ void build_ytab(const Geometry& g, int sh, int dh, std::vector<YEnt>* out) {
       y_accum -= g.y_sub;
     }
     while (dst_y < dh && y_accum <= 0) {
-      const uint32_t yscale = g.y_expand ? 0u : g.fy_scale * (uint32_t)(-y_accum);
+      const uint32_t yscale = g.y_expand ? ((y_accum != 0) ? (uint32_t)(((uint64_t)(uint32_t)(-y_accum) << 32) / (uint64_t)g.y_sub) : 0u)
+                                         : g.fy_scale * (uint32_t)(-y_accum);
       (*out)[first + (size_t)dst_y] = YEnt{prev_last, last, y_accum, prev_yscale, yscale};
       prev_last = last;
       prev_yscale = yscale;
@@ -228,7 +250,7 @@ extern "C" int b2_rescale_planes(b2_ctx* ctx, int stream, const b2_rescale_job* 
     d.x_expand = g.x_expand; d.y_expand = g.y_expand; d.x_add = g.x_add; d.x_sub = g.x_sub; d.y_sub = g.y_sub;
     d.fx_scale = g.fx_scale; d.fy_scale = g.fy_scale; d.fxy_scale = g.fxy_scale;
     d.xtab = it->second.first; d.ytab = it->second.second;
-    d.units_x = (uint32_t)((j.dst_width * j.num_channels + kThreads - 1) / kThreads);
+    d.units_x = (uint32_t)((j.dst_width * j.num_channels + kThreads * kPerThread - 1) / (kThreads * kPerThread));
     const uint32_t items = d.units_x * (uint32_t)j.dst_height;
     if (i == 0) uni = items; else if (items != uni) uni = 0;
     pre[(size_t)i] = (uint32_t)tot;

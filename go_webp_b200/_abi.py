@@ -87,6 +87,11 @@ class AlphaFilterJob(C.Structure):
                 ("width", C.c_int32), ("height", C.c_int32), ("filter", C.c_int32), ("reserved", C.c_int32)]
 
 
+class AlphaDequantJob(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("src_stride", C.c_int32), ("dst_stride", C.c_int32),
+                ("width", C.c_int32), ("height", C.c_int32), ("strength", C.c_int32), ("reserved", C.c_int32)]
+
+
 class RescaleJob(C.Structure):
     _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("src_width", C.c_int32), ("src_height", C.c_int32),
                 ("src_stride", C.c_int32), ("dst_width", C.c_int32), ("dst_height", C.c_int32), ("dst_stride", C.c_int32),
@@ -146,6 +151,7 @@ SYMBOLS = {
     "b2_alpha_unfilter": (C.c_int, [_ctx, C.c_int, C.POINTER(AlphaFilterJob), C.c_int]),
     "b2_alpha_filter": (C.c_int, [_ctx, C.c_int, C.POINTER(AlphaFilterJob), C.c_int]),
     "b2_rescale_planes": (C.c_int, [_ctx, C.c_int, C.POINTER(RescaleJob), C.c_int]),
+    "b2_alpha_dequantize_levels": (C.c_int, [_ctx, C.c_int, C.POINTER(AlphaDequantJob), C.c_int, C.c_int]),
     "b2_picture_cleanup_transparent": (C.c_int, [_ctx, C.c_int, C.POINTER(PictureJob), C.c_int, C.c_int]),
     "b2_picture_blend_alpha": (C.c_int, [_ctx, C.c_int, C.POINTER(PictureJob), C.c_int, C.c_int, C.c_uint32]),
     "b2_picture_replace_transparent": (C.c_int, [_ctx, C.c_int, C.POINTER(PictureJob), C.c_int, C.c_uint32]),

@@ -1,0 +1,280 @@
+// b2_dequant.cu -- alpha level smoothing: WebPDequantizeLevels
+// (pkg/libwebp/utils/quant_levels_dec_utils.c.go:259-286), which ALPHDecode runs over the
+// decoded alpha plane when the ALPH chunk says its levels were quantised and the caller asked
+// for alpha dithering (pkg/libwebp/decoder/alpha_dec.go:198-203).
+//
+// The reference streams rows through a ring of cumulative sums (VFilter :86-111, HFilter
+// :115-136, all modulo 2^16).  Restated per pixel: with cs[k] the sum of column k over rows
+// y-r .. y+r (rows above the plane replicate row 0; the last r rows of the plane are never
+// emitted, so rows below it are never needed), the box value of pixel x is
+//     x <= r      : sum cs[0 .. x+r-1] + sum cs[0 .. r-x]          (the reference's left mirror)
+//     x >= w - r  : sum cs[2w-1-r-x .. w-1] + sum cs[x-r .. w-1]   (right mirror)
+//     otherwise   : sum cs[x-r .. x+r]
+// at most (2r+1)^2 * 255 < 2^16, so the modulo never bites.  average = (box * scale) >> 16,
+// then ApplyFilter (:139-157) through the correction table (InitCorrectionLUT :162-184) built
+// from the smallest distance between two used levels (CountLevels :186-219).
+//
+// Three launches: used-level bitmap per plane (256 bits, atomicOr), one thread per plane
+// turning it into min / max / min distance / count, then the smoother: a warp owns 120
+// output columns x 32 rows, each lane keeps the vertical sums of its 4 columns in registers
+// (sliding down the band), neighbours' sums come by shuffle (r <= 4: one lane each side, the
+// two outer lanes of a warp are halo only), the correction table sits in shared memory.
+// Out of place: the reference filters in place, but it reads row y+r before it writes row y,
+// so reading the untouched source is the same computation.
+#include <stdlib.h>
+
+#include "b2_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256, kWarps = kThreads / 32;
+constexpr int kTileCols = 120;   // output columns per warp (lanes 1..30 x 4)
+constexpr int kBandRows = 32;
+constexpr int kLfix = 2, kFix = 16;
+constexpr int kLutSize = (1 << (8 + kLfix)) - 1;
+
+struct DqJobDev {
+  const uint8_t* src;
+  uint8_t* dst;
+  int32_t src_stride, dst_stride, width, height, radius;
+  uint32_t tiles_x, units;
+};
+struct DqStats {          // per plane: 8 words of used-level bits, then CountLevels' results
+  uint32_t used[8];
+  int32_t min, max, min_dist, num_levels;
+};
+
+// 4 bytes of row 'row' at columns x0 .. x0+3.  Columns outside the plane are mirrored about
+// its edges (column -1-k for k < 0, 2w-1-k for k >= w; zero where that falls outside too):
+// the extension on which the reference's edge sums become plain windows (see the smoother).
+__device__ __forceinline__ uint32_t load4(const DqJobDev& j, int row, int x0) {
+  const uint8_t* p = j.src + (size_t)row * j.src_stride;
+  if (x0 >= 0 && x0 + 3 < j.width && (((uintptr_t)(p + x0)) & 3) == 0) return __ldg((const uint32_t*)(p + x0));
+  uint32_t v = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    int c = x0 + k;
+    c = c < 0 ? -1 - c : (c >= j.width ? 2 * j.width - 1 - c : c);
+    if (c >= 0 && c < j.width) v |= (uint32_t)__ldg(p + c) << (8 * k);
+  }
+  return v;
+}
+
+__global__ void __launch_bounds__(kThreads)
+dq_levels_kernel(const DqJobDev* __restrict__ jobs, DqStats* __restrict__ stats) {
+  __shared__ uint8_t flag[256];
+  const DqJobDev j = jobs[blockIdx.y];
+  if (j.radius == 0) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  flag[threadIdx.x] = 0;
+  __syncthreads();
+  for (int row = blockIdx.x * kWarps + warp; row < j.height; row += gridDim.x * kWarps) {
+    uint32_t last = 0;
+    bool fresh = true;
+    for (int x0 = lane * 4; x0 < j.width; x0 += 128) {
+      const uint32_t v = load4(j, row, x0);
+      if (!fresh && v == last) continue;   // flat runs: nothing new to flag
+      last = v;
+      fresh = false;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (x0 + k < j.width) flag[(v >> (8 * k)) & 0xff] = 1;
+    }
+  }
+  __syncthreads();
+  const uint32_t bits = __ballot_sync(0xffffffffu, flag[threadIdx.x] != 0);
+  if (lane == 0 && bits) atomicOr(&stats[blockIdx.y].used[warp], bits);
+}
+
+__global__ void dq_finalize_kernel(DqStats* __restrict__ stats, uint32_t n_jobs) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_jobs) return;
+  DqStats& s = stats[i];
+  int mn = 255, mx = 0, n = 0, last = -1, dist = 255;
+#pragma unroll
+  for (int word = 0; word < 8; ++word) {
+    uint32_t bits = s.used[word];
+    while (bits) {
+      const int v = word * 32 + __ffs(bits) - 1;
+      bits &= bits - 1;
+      ++n;
+      if (v < mn) mn = v;
+      mx = v;
+      if (last >= 0 && v - last < dist) dist = v - last;
+      last = v;
+    }
+  }
+  if (mx - mn < dist) dist = mx - mn;
+  s.min = mn; s.max = mx; s.min_dist = dist; s.num_levels = n;
+}
+
+template <int DFIX>
+__global__ void __launch_bounds__(kThreads)
+dq_smooth_kernel(const DqJobDev* __restrict__ jobs, const DqStats* __restrict__ stats) {
+  __shared__ int16_t lut[2 * kLutSize + 1];
+  const DqJobDev j = jobs[blockIdx.y];
+  if (blockIdx.x * kWarps >= j.units) return;
+  const int vmin = stats[blockIdx.y].min, vmax = stats[blockIdx.y].max;
+  const bool active = j.radius > 0 && stats[blockIdx.y].num_levels > 2;
+  if (active) {   // InitCorrectionLUT
+    const int threshold1 = stats[blockIdx.y].min_dist << kLfix;
+    const int threshold2 = (3 * threshold1) >> 2;
+    const int max_threshold = threshold2 << DFIX;
+    const int delta = threshold1 - threshold2;
+    for (int i = threadIdx.x; i <= kLutSize; i += kThreads) {
+      int c = 0;
+      if (i > 0) {
+        c = (i <= threshold2) ? (i << DFIX) : (i < threshold1) ? max_threshold * (threshold1 - i) / delta : 0;
+        c >>= kLfix;
+      }
+      lut[kLutSize + i] = (int16_t)c;
+      lut[kLutSize - i] = (int16_t)-c;
+    }
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t unit = blockIdx.x * kWarps + warp;
+  if (unit >= j.units) return;
+  const int w = j.width, h = j.height, r = j.radius;
+  const int x0 = (int)(unit % j.tiles_x) * kTileCols - 4 + 4 * lane;
+  const int yb = (int)(unit / j.tiles_x) * kBandRows, ye = min(yb + kBandRows, h);
+  const bool writer = lane >= 1 && lane <= 30 && x0 < w;
+  const int filt_end = active ? h - r : 0;          // rows [0, filt_end) are smoothed
+  const uint32_t scale = (1u << (kFix + kLfix)) / (uint32_t)((2 * r + 1) * (2 * r + 1));
+  const uint32_t m2 = r >= 2 ? ~0u : 0u, m3 = r >= 3 ? ~0u : 0u, m4 = r >= 4 ? ~0u : 0u;
+
+  uint32_t cs[4] = {0, 0, 0, 0};
+  if (yb < filt_end) {
+    for (int k = -r; k <= r; ++k) {
+      const uint32_t v = load4(j, max(yb + k, 0), x0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) cs[q] += (v >> (8 * q)) & 0xff;
+    }
+  }
+  for (int y = yb; y < ye; ++y) {
+    const uint32_t pix = load4(j, y, x0);
+    uint32_t out = pix;
+    if (y < filt_end) {                              // warp-uniform
+      if (y > yb) {
+        const uint32_t a = load4(j, y + r, x0), s = load4(j, max(y - 1 - r, 0), x0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) cs[q] += ((a >> (8 * q)) & 0xff) - ((s >> (8 * q)) & 0xff);
+      }
+      const uint32_t p0 = cs[0] | (cs[1] << 16), p1 = cs[2] | (cs[3] << 16);
+      const uint32_t l0 = __shfl_up_sync(0xffffffffu, p0, 1), l1 = __shfl_up_sync(0xffffffffu, p1, 1);
+      const uint32_t r0 = __shfl_down_sync(0xffffffffu, p0, 1), r1 = __shfl_down_sync(0xffffffffu, p1, 1);
+      if (writer) {
+        const uint32_t v[12] = {l0 & 0xffff, l0 >> 16, l1 & 0xffff, l1 >> 16, cs[0], cs[1], cs[2], cs[3],
+                                r0 & 0xffff, r0 >> 16, r1 & 0xffff, r1 >> 16};
+        // plain (2r+1)-wide windows on the mirrored extension ...
+        uint32_t box[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          box[q] = v[3 + q] + v[4 + q] + v[5 + q] + ((v[2 + q] + v[6 + q]) & m2) + ((v[1 + q] + v[7 + q]) & m3) +
+                   ((v[q] + v[8 + q]) & m4);
+        // ... which is the reference's right mirror exactly; its left mirror takes column r-x
+        // instead of column x+r (sum cs[0..x+r-1] + sum cs[0..r-x]): both lie in v[0..11]
+        if (x0 <= r) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int x = x0 + q;
+            if (x <= r) {
+              const int ia = r - x - x0 + 4, ib = x + r - x0 + 4;
+              uint32_t add = 0, sub = 0;
+#pragma unroll
+              for (int i = 0; i < 12; ++i) {
+                add = (i == ia) ? v[i] : add;
+                sub = (i == ib) ? v[i] : sub;
+              }
+              box[q] += add - sub;
+            }
+          }
+        }
+        const uint64_t kDither = 0x5d7f91b36e4ca280ull;   // kOrderedDither (:39-44), nibble row * 4 + col
+        out = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int pv = (int)((pix >> (8 * q)) & 0xff);
+          int res = pv;
+          if (pv < vmax && pv > vmin) {
+            const int avg = (int)(((box[q] & 0xffff) * scale) >> kFix);
+            int c = (pv << DFIX) + lut[kLutSize + avg - (pv << kLfix)];
+            if (DFIX) c += (int)((kDither >> (4 * ((((y + r) & 3) << 2) + ((x0 + q) & 3)))) & 15);
+            res = c < 0 ? 0 : (c >= (256 << DFIX)) ? 255 : (c >> DFIX);
+          }
+          out |= (uint32_t)res << (8 * q);
+        }
+      }
+    }
+    if (writer) {
+      uint8_t* d = j.dst + (size_t)y * j.dst_stride + x0;
+      if (x0 + 3 < w && (((uintptr_t)d) & 3) == 0) {
+        *(uint32_t*)d = out;
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (x0 + q < w) d[q] = (uint8_t)(out >> (8 * q));
+      }
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int b2_alpha_dequantize_levels(b2_ctx* ctx, int stream, const b2_alpha_dequant_job* jobs, int n_jobs,
+                                          int ordered_dither) {
+  B2_CHECK_CTX(ctx, stream);
+  if (n_jobs < 0 || n_jobs > 65535) return B2_ERR_INVALID_CONFIG;
+  if (n_jobs == 0) return B2_OK;
+  if (jobs == NULL) return B2_ERR_NULL;
+  const size_t jb = sizeof(DqJobDev) * (size_t)n_jobs;
+  if (jb > B2_DESC_RING_BYTES) return B2_ERR_INVALID_CONFIG;
+  DqJobDev* d = (DqJobDev*)calloc(1, jb);
+  if (d == NULL) return B2_ERR_OOM;
+  uint32_t max_units = 0, max_rows = 0;
+  bool any = false;
+  for (int i = 0; i < n_jobs; ++i) {
+    const b2_alpha_dequant_job& j = jobs[i];
+    int st = B2_OK;
+    if (j.src == NULL || j.dst == NULL) st = B2_ERR_NULL;
+    else if (j.width <= 0 || j.height <= 0 || j.width > B2_MAX_DIMENSION || j.height > B2_MAX_DIMENSION) st = B2_ERR_BAD_DIM;
+    else if (j.src_stride < j.width || j.dst_stride < j.width) st = B2_ERR_BAD_DIM;
+    else if (j.strength < 0 || j.strength > 100 || (const uint8_t*)j.dst == j.src) st = B2_ERR_INVALID_CONFIG;   // :263; out of place
+    if (st != B2_OK) { free(d); return st; }
+    int radius = 4 * j.strength / 100;                                  // :260-273
+    if (2 * radius + 1 > j.width) radius = (j.width - 1) >> 1;
+    if (2 * radius + 1 > j.height) radius = (j.height - 1) >> 1;
+    d[i].src = j.src; d[i].dst = j.dst; d[i].src_stride = j.src_stride; d[i].dst_stride = j.dst_stride;
+    d[i].width = j.width; d[i].height = j.height; d[i].radius = radius;
+    d[i].tiles_x = (uint32_t)((j.width + kTileCols - 1) / kTileCols);
+    d[i].units = d[i].tiles_x * (uint32_t)((j.height + kBandRows - 1) / kBandRows);
+    if (d[i].units > max_units) max_units = d[i].units;
+    if (radius > 0) { any = true; if ((uint32_t)j.height > max_rows) max_rows = (uint32_t)j.height; }
+  }
+  void* dev = NULL;
+  int st = b2_upload_desc(ctx, stream, d, jb, &dev);
+  free(d);
+  if (st != B2_OK) return st;
+  void* sp = NULL;
+  st = b2_stream_scratch(ctx, stream, sizeof(DqStats) * (size_t)n_jobs, &sp);
+  if (st != B2_OK) return st;
+  cudaStream_t s = ctx->streams[stream];
+  const DqJobDev* dj = (const DqJobDev*)dev;
+  DqStats* ds = (DqStats*)sp;
+  B2_CUDA(ctx, cudaMemsetAsync(ds, 0, sizeof(DqStats) * (size_t)n_jobs, s));
+  if (any) {
+    uint32_t gx = (max_rows + kWarps - 1) / kWarps;
+    const uint32_t cap = (uint32_t)(ctx->sm_count * 8 + n_jobs - 1) / (uint32_t)n_jobs;
+    if (gx > cap) gx = cap;
+    if (gx < 1) gx = 1;
+    dq_levels_kernel<<<dim3(gx, (unsigned)n_jobs), kThreads, 0, s>>>(dj, ds);
+    dq_finalize_kernel<<<(n_jobs + 63) / 64, 64, 0, s>>>(ds, (uint32_t)n_jobs);
+    ctx->launches += 2;
+  }
+  const dim3 grid((max_units + kWarps - 1) / kWarps, (unsigned)n_jobs);
+  if (ordered_dither) dq_smooth_kernel<4><<<grid, kThreads, 0, s>>>(dj, ds);
+  else dq_smooth_kernel<0><<<grid, kThreads, 0, s>>>(dj, ds);
+  ctx->launches++;
+  B2_CUDA(ctx, cudaGetLastError());
+  return B2_OK;
+}

@@ -46,6 +46,57 @@ def _run(planes, filters, unfilter: bool, ctx: Context | None):
     return outs
 
 
+def DequantizeLevelsBatch(planes, strengths, ordered_dither: bool = True, ctx: Context | None = None,
+                          row_align: int = 16):
+    """Added batched entry point: WebPDequantizeLevels on every plane (uint8 [h, w]) with
+    strengths[i] in [0, 100] -> new planes.  ordered_dither=True is the Go file as written
+    (DFIX = 4, quant_levels_dec_utils.c.go:36-45); False is the stock libwebp build.
+    row_align: alignment of the device row stride (1 = tightly packed rows)."""
+    ctx = ctx or default_context()
+    lib, hnd = ctx.lib, ctx.h
+    n = len(planes)
+    if n == 0:
+        return []
+    metas, need = [], 0
+    for p in planes:
+        h, w = p.shape
+        st = _al(w, row_align)
+        metas.append((w, h, st))
+        need += 2 * _al(st * h)
+    ar = _arena(ctx)
+    ar.reset(need)
+    jobs, outs_ptr = [], []
+    for (w, h, st), p, strength in zip(metas, planes, strengths):
+        ps, pd = ar.take(st * h), ar.take(st * h)
+        p = np.ascontiguousarray(p, np.uint8)
+        ctx._chk(lib.b2_h2d_2d_async(hnd, 0, ps, st, p.ctypes.data, w, w, h))
+        jobs.append(_abi.AlphaDequantJob(ps, pd, st, st, w, h, int(strength), 0))
+        outs_ptr.append(pd)
+    arr = (_abi.AlphaDequantJob * n)(*jobs)
+    ctx._chk(lib.b2_alpha_dequantize_levels(hnd, 0, arr, n, int(bool(ordered_dither))))
+    outs = []
+    for (w, h, st), pd in zip(metas, outs_ptr):
+        o = np.empty((h, w), np.uint8)
+        ctx._chk(lib.b2_d2h_2d_async(hnd, 0, o.ctypes.data, w, pd, st, w, h))
+        outs.append(o)
+    ctx.sync()
+    return outs
+
+
+def WebPDequantizeLevels(data: np.ndarray, width: int, height: int, stride: int, strength: int,
+                         ordered_dither: bool = True) -> bool:
+    """quant_levels_dec_utils.c.go:259-286: smooths the alpha plane `data` (flat uint8, row
+    stride `stride`) in place; False for a strength outside [0, 100] or an empty plane."""
+    if strength < 0 or strength > 100 or data is None or width <= 0 or height <= 0:
+        return False
+    flat = np.asarray(data).reshape(-1)
+    plane = np.stack([flat[y * stride:y * stride + width] for y in range(height)])
+    out = DequantizeLevelsBatch([plane], [strength], ordered_dither)[0]
+    for y in range(height):
+        flat[y * stride:y * stride + width] = out[y]
+    return True
+
+
 def AlphaUnfilterBatch(planes, filters, ctx: Context | None = None):
     """Added batched entry point: planes[i] (uint8 [h, w], the filtered alpha plane the ALPH
     chunk decodes to) unfiltered with WebPUnfilters[filters[i]] exactly as the row loop of

@@ -391,6 +391,24 @@ typedef struct b2_alpha_filter_job {
 int b2_alpha_unfilter(b2_ctx* ctx, int stream, const b2_alpha_filter_job* jobs, int n_jobs);
 int b2_alpha_filter(b2_ctx* ctx, int stream, const b2_alpha_filter_job* jobs, int n_jobs);
 
+/* Alpha level smoothing: WebPDequantizeLevels
+ * (pkg/libwebp/utils/quant_levels_dec_utils.c.go:259-286) as ALPHDecode calls it on the
+ * decoded plane (pkg/libwebp/decoder/alpha_dec.go:198-203): radius = 4 * strength / 100
+ * clamped to the plane, nothing happens with fewer than 3 used levels; strength outside
+ * [0, 100] is B2_ERR_INVALID_CONFIG (the reference returns false).  The reference works in
+ * place; here dst != src (the result is the same, see b2_dequant.cu).  ordered_dither = 1
+ * is the Go file as written (DFIX = 4 and the 4x4 ordered dither, :36-45, :147-148);
+ * 0 is the stock libwebp build it was transliterated from (USE_DITHERING undefined). */
+typedef struct b2_alpha_dequant_job {
+  const uint8_t* src;
+  uint8_t* dst;
+  int32_t src_stride, dst_stride;
+  int32_t width, height;
+  int32_t strength;
+  int32_t reserved;
+} b2_alpha_dequant_job;
+int b2_alpha_dequantize_levels(b2_ctx* ctx, int stream, const b2_alpha_dequant_job* jobs, int n_jobs, int ordered_dither);
+
 /* The fixed-point rescaler: WebPRescalerInit / Import / Export
  * (pkg/libwebp/utils/rescaler_utils.c.go:31-158) with WebPRescalerImportRow{Expand,Shrink}
  * and WebPRescalerExportRow{Expand,Shrink} (pkg/libwebp/dsp/rescaler.c.go:39-197) over a

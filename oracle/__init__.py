@@ -443,3 +443,13 @@ def rescale_plane(plane, dst_width, dst_height, num_channels=1):
     ok = lib().orc_rescale_plane(_p(plane), w, h, wc, _p(out), dst_width, dst_height, dst_width * num_channels, num_channels)
     assert ok
     return out
+
+
+def dequantize_levels(plane, strength, ordered_dither=False):
+    """WebPDequantizeLevels on an alpha plane -> new plane.  ordered_dither: the Go file's
+    DFIX = 4 branch; False is the stock libwebp build (DFIX = 0)."""
+    plane = np.array(plane, np.uint8, order="C")
+    h, w = plane.shape
+    ok = lib().orc_dequantize_levels(_p(plane), w, h, w, int(strength), int(bool(ordered_dither)))
+    assert ok
+    return plane

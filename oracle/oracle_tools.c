@@ -588,3 +588,177 @@ int orc_rescale_plane(const uint8_t* src, int src_width, int src_height, int src
   free(work);
   return 1;
 }
+
+/* ---- alpha level smoothing --------------------------------------------- */
+/* WebPDequantizeLevels, pkg/libwebp/utils/quant_levels_dec_utils.c.go:30-286: a sliding
+ * (2r+1)^2 box average (vertical sums with replicated rows, horizontal sums on cumulative
+ * columns with mirroring), a correction look-up that pulls each level towards the local
+ * average by at most the smallest gap between two used levels, ordered dithering. */
+#define DQ_FIX 16
+#define DQ_LFIX 2
+#define DQ_LUT_SIZE ((1 << (8 + DQ_LFIX)) - 1)
+#define DQ_DSIZE 4
+/* The Go file keeps the ordered-dither branch of the C source (DFIX = 4, :36-45); the stock
+ * libwebp build leaves USE_DITHERING undefined (DFIX = 0, no dither).  `dfix` selects: 4 is
+ * the reference as written, 0 is what the libwebp 1.6.0 binary runs (the pinned variant);
+ * the two differ in this constant and the dither add only. */
+static const uint8_t kOrderedDither[DQ_DSIZE][DQ_DSIZE] = {{0, 8, 2, 10}, {12, 4, 14, 6}, {3, 11, 1, 9}, {15, 7, 13, 5}};
+typedef struct {
+  int width, height, stride, row;
+  uint8_t* src;
+  uint8_t* dst;
+  int radius, scale;
+  uint16_t *start, *cur, *end, *top, *average;
+  int num_levels, min, max, min_level_dist;
+  int16_t* correction;
+  int dfix;
+} SmoothParams;
+static uint8_t dq_clip_8b(int v, int dfix) {
+  const int mask = (int)(~0u << (8 + dfix));
+  return (!(v & mask)) ? (uint8_t)(v >> dfix) : (v < 0) ? 0u : 255u;
+}
+/* quant_levels_dec_utils.c.go:86-111 */
+static void DqVFilter(SmoothParams* p) {
+  const uint8_t* src = p->src;
+  const int w = p->width;
+  uint16_t* const cur = p->cur;
+  const uint16_t* const top = p->top;
+  uint16_t* const out = p->end;
+  uint16_t sum = 0; /* all arithmetic is modulo 16bit */
+  for (int x = 0; x < w; ++x) {
+    uint16_t new_value;
+    sum += src[x];
+    new_value = top[x] + sum;
+    out[x] = new_value - cur[x]; /* vertical sum of 'r' pixels. */
+    cur[x] = new_value;
+  }
+  p->top = p->cur;
+  p->cur += w;
+  if (p->cur == p->end) p->cur = p->start; /* roll-over */
+  if (p->row >= 0 && p->row < p->height - 1) p->src += p->stride;
+}
+/* :115-136 */
+static void DqHFilter(SmoothParams* p) {
+  const uint16_t* const in = p->end;
+  uint16_t* const out = p->average;
+  const uint32_t scale = p->scale;
+  const int w = p->width, r = p->radius;
+  int x;
+  for (x = 0; x <= r; ++x) { /* left mirroring */
+    const uint16_t delta = in[x + r - 1] + in[r - x];
+    out[x] = (delta * scale) >> DQ_FIX;
+  }
+  for (; x < w - r; ++x) { /* bulk middle run */
+    const uint16_t delta = in[x + r] - in[x - r - 1];
+    out[x] = (delta * scale) >> DQ_FIX;
+  }
+  for (; x < w; ++x) { /* right mirroring */
+    const uint16_t delta = 2 * in[w - 1] - in[2 * w - 2 - r - x] - in[x - r - 1];
+    out[x] = (delta * scale) >> DQ_FIX;
+  }
+}
+/* :139-157 */
+static void DqApplyFilter(SmoothParams* p) {
+  const uint16_t* const average = p->average;
+  const int w = p->width;
+  const int16_t* const correction = p->correction + DQ_LUT_SIZE;
+  const uint8_t* const dither = kOrderedDither[p->row % DQ_DSIZE];
+  uint8_t* const dst = p->dst;
+  for (int x = 0; x < w; ++x) {
+    const int v = dst[x];
+    if (v < p->max && v > p->min) {
+      const int c = (v << p->dfix) + correction[average[x] - (v << DQ_LFIX)];
+      dst[x] = dq_clip_8b(c + (p->dfix ? dither[x % DQ_DSIZE] : 0), p->dfix);
+    }
+  }
+  p->dst += p->stride;
+}
+/* :162-184 */
+static void DqInitCorrectionLUT(int16_t* lut_ptr, int min_dist, int dfix) {
+  const int threshold1 = min_dist << DQ_LFIX;
+  const int threshold2 = (3 * threshold1) >> 2;
+  const int max_threshold = threshold2 << dfix;
+  const int delta = threshold1 - threshold2;
+  int16_t* const lut = lut_ptr + DQ_LUT_SIZE;
+  for (int i = 1; i <= DQ_LUT_SIZE; ++i) {
+    int c = (i <= threshold2) ? (i << dfix) : (i < threshold1) ? max_threshold * (threshold1 - i) / delta : 0;
+    c >>= DQ_LFIX;
+    lut[+i] = (int16_t)+c;
+    lut[-i] = (int16_t)-c;
+  }
+  lut[0] = 0;
+}
+/* :186-219 */
+static void DqCountLevels(SmoothParams* p) {
+  uint8_t used_levels[256] = {0};
+  const uint8_t* data = p->src;
+  p->min = 255;
+  p->max = 0;
+  for (int j = 0; j < p->height; ++j) {
+    for (int i = 0; i < p->width; ++i) {
+      const int v = data[i];
+      if (v < p->min) p->min = v;
+      if (v > p->max) p->max = v;
+      used_levels[v] = 1;
+    }
+    data += p->stride;
+  }
+  p->min_level_dist = p->max - p->min;
+  int last_level = -1;
+  for (int i = 0; i < 256; ++i) {
+    if (used_levels[i]) {
+      ++p->num_levels;
+      if (last_level >= 0) {
+        const int level_dist = i - last_level;
+        if (level_dist < p->min_level_dist) p->min_level_dist = level_dist;
+      }
+      last_level = i;
+    }
+  }
+}
+/* :222-286 (InitParams + WebPDequantizeLevels), in place on data */
+int orc_dequantize_levels(uint8_t* data, int width, int height, int stride, int strength, int ordered_dither) {
+  int radius = 4 * strength / 100;
+  if (strength < 0 || strength > 100) return 0;
+  if (data == NULL || width <= 0 || height <= 0) return 0;
+  if (2 * radius + 1 > width) radius = (width - 1) >> 1;
+  if (2 * radius + 1 > height) radius = (height - 1) >> 1;
+  if (radius > 0) {
+    SmoothParams p;
+    const int R = 2 * radius + 1;
+    memset(&p, 0, sizeof(p));
+    uint16_t* scratch = (uint16_t*)calloc((size_t)(R + 1) * width + width, sizeof(uint16_t));
+    int16_t* lut = (int16_t*)calloc(1 + 2 * DQ_LUT_SIZE, sizeof(int16_t));
+    if (scratch == NULL || lut == NULL) { free(scratch); free(lut); return 0; }
+    p.start = scratch;
+    p.cur = p.start;
+    p.end = p.start + R * width;
+    p.top = p.end - width;
+    memset(p.top, 0, width * sizeof(*p.top));
+    p.width = width;
+    p.average = scratch + (size_t)(R + 1) * width;
+    p.height = height;
+    p.stride = stride;
+    p.src = data;
+    p.dst = data;
+    p.radius = radius;
+    p.scale = (1 << (DQ_FIX + DQ_LFIX)) / (R * R);
+    p.row = -radius;
+    p.dfix = ordered_dither ? 4 : 0;
+    DqCountLevels(&p);
+    p.correction = lut;
+    DqInitCorrectionLUT(p.correction, p.min_level_dist, p.dfix);
+    if (p.num_levels > 2) {
+      for (; p.row < p.height; ++p.row) {
+        DqVFilter(&p);
+        if (p.row >= p.radius) {
+          DqHFilter(&p);
+          DqApplyFilter(&p);
+        }
+      }
+    }
+    free(scratch);
+    free(lut);
+  }
+  return 1;
+}

@@ -925,6 +925,47 @@ def test_alpha_filters(gpu, golden_dir):
     assert (out.reshape(7, 40)[:, :33] == oracle.alpha_filter(data.reshape(7, 40)[:, :33], 3)).all()
 
 
+def test_alpha_level_smoothing(gpu, golden_dir):
+    """WebPDequantizeLevels: the libwebp decoder vectors in one batch (stock
+    build, no dither), the same planes with the Go file's ordered dither vs the oracle, then
+    seeded quantised planes: several 120-column tiles and 32-row bands, widths around the tile
+    edge, radius clamped by a thin plane, unaligned rows, two-level planes (copied), strength
+    0 (copied), mixed strengths in one batch."""
+    from go_webp_b200 import filters as F
+    g = np.load(os.path.join(golden_dir, "alpha_dequant_libwebp160.npz"))
+    ks = [str(k) for k in g["names"]]
+    ins, strengths = [g[f"{k}/in"] for k in ks], [int(g[f"{k}/strength"]) for k in ks]
+    outs = F.DequantizeLevelsBatch(ins, strengths, ordered_dither=False)
+    for k, o in zip(ks, outs):
+        assert (o == g[f"{k}/out"]).all(), k
+    outs = F.DequantizeLevelsBatch(ins, strengths, ordered_dither=True)
+    for k, p, s, o in zip(ks, ins, strengths, outs):
+        assert (o == oracle.dequantize_levels(p, s, True)).all(), k
+    rng = np.random.default_rng(4242)
+    planes, strengths = [], []
+    for (w, h) in [(1, 1), (2, 9), (3, 3), (9, 2), (119, 33), (120, 64), (121, 65), (124, 31), (240, 40), (245, 97), (1000, 70), (333, 200)]:
+        yy, xx = np.mgrid[0:h, 0:w]
+        base = (128 + 90 * np.sin(xx / 23.0 + 1) * np.cos(yy / 17.0) + rng.integers(-6, 7, (h, w))).clip(0, 255)
+        for q, s in [(17, 100), (40, 60), (8, 30), (64, 100), (17, 0), (255, 100)]:
+            planes.append(((base // q) * q).astype(np.uint8))
+            strengths.append(s)
+    for dither in (False, True):
+        for align in (16, 1):
+            outs = F.DequantizeLevelsBatch(planes, strengths, ordered_dither=dither, row_align=align)
+            for p, s, o in zip(planes, strengths, outs):
+                assert (o == oracle.dequantize_levels(p, s, dither)).all(), (p.shape, s, dither, align)
+    data = np.ascontiguousarray(planes[40]).copy()
+    h, w = data.shape
+    flat = data.reshape(-1)
+    assert F.WebPDequantizeLevels(flat, w - 3, h, w, 100)
+    exp = data.copy()
+    exp[:, :w - 3] = oracle.dequantize_levels(planes[40][:, :w - 3], 100, True)
+    assert (flat.reshape(h, w) == exp).all()
+    assert not F.WebPDequantizeLevels(flat, w, h, w, 101)
+    with pytest.raises(Exception):
+        F.DequantizeLevelsBatch([planes[0]], [-1])
+
+
 def test_rescaler(gpu, golden_dir):
     """The rescaler: the WebPPictureRescale vectors in one batch (all mixes of
     horizontal / vertical expansion and shrinking, identity, 1-pixel sources), seeded planes

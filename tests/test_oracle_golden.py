@@ -304,6 +304,28 @@ def test_alpha_unfilters_match_libwebp_streams(golden_dir):
     assert kinds == {0, 1, 2, 3}
 
 
+def test_level_smoothing_matches_libwebp_decoder(golden_dir):
+    """WebPDequantizeLevels (quant_levels_dec_utils.c.go:259-286) vs WebPDecode with
+    alpha_dithering_strength on files the binary wrote with quantised alpha levels (the stock
+    build: no ordered dither).  The Go file's dither branch differs in DFIX and the dither
+    add only; checked here for the structural properties that follow."""
+    g = _load(golden_dir, "alpha_dequant_libwebp160.npz")
+    changed = 0
+    for k in g["names"]:
+        s, fin, exp = int(g[f"{k}/strength"]), g[f"{k}/in"], g[f"{k}/out"]
+        assert (oracle.dequantize_levels(fin, s) == exp).all(), (k, s)
+        changed += int((fin != exp).any())
+        d = oracle.dequantize_levels(fin, s, ordered_dither=True)
+        r = min(4 * s // 100, (fin.shape[1] - 1) >> 1, (fin.shape[0] - 1) >> 1)
+        if r > 0:   # last r rows, the lowest and the highest level are never touched
+            assert (d[fin.shape[0] - r:] == fin[fin.shape[0] - r:]).all()
+        assert (d[(fin == fin.min()) | (fin == fin.max())] == fin[(fin == fin.min()) | (fin == fin.max())]).all()
+        assert np.abs(d.astype(int) - exp.astype(int)).max() <= 1     # 4 extra fraction bits + dither < 1 level
+    assert changed >= 60
+    two = np.where(np.arange(64)[None, :] > 31, 200, 10).astype(np.uint8).repeat(16, 0)
+    assert (oracle.dequantize_levels(two, 100) == two).all()          # two levels: untouched (:279)
+
+
 def test_rescaler_matches_libwebp_binary(golden_dir):
     """RescalePlane (WebPRescaler import / export rows, rescaler.c.go:39-197) vs
     WebPPictureRescale on the Y, U and V planes of pictures the binary rescaled."""

@@ -136,3 +136,25 @@ if "rescale" in which:
         print(f"rescale {n} x {w}x{h} -> {dw}x{dh}: {n * w * h / ms / 1e3:9.0f} Mpx/s in, {n * (w * h + dw * dh) / ms / 1e6:7.0f} GB/s "
               f"({n * (w * h + dw * dh) / ms / 1e6 / PEAK:.3f} of measured peak)")
         src.free(); dst.free()
+if "dequant" in which:
+    # alpha level smoothing on NF 1080p planes (3 B/px: the level scan reads the plane, the smoother reads + writes it)
+    import numpy as np
+    n = NF
+    w, h, st = 1920, 1080, 1920
+    src = ctx.alloc(n * st * h)
+    dst = ctx.alloc(n * st * h)
+    yy, xx = np.mgrid[0:h, 0:w]
+    smooth = ((128 + 100 * np.sin(xx / 90.0) * np.cos(yy / 70.0)).astype(np.int64) // 16 * 16).astype(np.uint8)
+    for name in ("random bytes", "smooth, 16 levels apart"):
+        if name == "random bytes":
+            ctx.synth_fill(src.ptr, st // 4, h, st, st * h, n, 0xB2000009, 0, 4)
+        else:
+            for i in range(n):
+                ctx._chk(ctx.lib.b2_h2d_2d_async(ctx.h, 0, src.ptr + i * st * h, st, smooth.ctypes.data, w, w, h))
+        ctx.sync()
+        for strength in (100, 50):
+            jobs = (_abi.AlphaDequantJob * n)(*[_abi.AlphaDequantJob(src.ptr + i * st * h, dst.ptr + i * st * h, st, st, w, h, strength, 0) for i in range(n)])
+            for dither in (1, 0):
+                report(f"level smoothing {n}x1080p {name} s={strength} dither={dither}", n * w * h, 3.0,
+                       timed(lambda: ctx._chk(ctx.lib.b2_alpha_dequantize_levels(ctx.h, 0, jobs, n, dither)), 5))
+    src.free(); dst.free()

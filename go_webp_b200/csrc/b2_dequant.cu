@@ -10,6 +10,8 @@
 //     x <= r      : sum cs[0 .. x+r-1] + sum cs[0 .. r-x]          (the reference's left mirror)
 //     x >= w - r  : sum cs[2w-1-r-x .. w-1] + sum cs[x-r .. w-1]   (right mirror)
 //     otherwise   : sum cs[x-r .. x+r]
+// i.e. with cs mirrored about both edges (column -1-k for k < 0, 2w-1-k for k >= w) a plain
+// window centred on x, except that columns x <= r take the window centred on max(x-1, 0)
 // at most (2r+1)^2 * 255 < 2^16, so the modulo never bites.  average = (box * scale) >> 16,
 // then ApplyFilter (:139-157) through the correction table (InitCorrectionLUT :162-184) built
 // from the smallest distance between two used levels (CountLevels :186-219).
@@ -44,20 +46,34 @@ struct DqStats {          // per plane: 8 words of used-level bits, then CountLe
   int32_t min, max, min_dist, num_levels;
 };
 
-// 4 bytes of row 'row' at columns x0 .. x0+3.  Columns outside the plane are mirrored about
-// its edges (column -1-k for k < 0, 2w-1-k for k >= w; zero where that falls outside too):
-// the extension on which the reference's edge sums become plain windows (see the smoother).
-__device__ __forceinline__ uint32_t load4(const DqJobDev& j, int row, int x0) {
-  const uint8_t* p = j.src + (size_t)row * j.src_stride;
-  if (x0 >= 0 && x0 + 3 < j.width && (((uintptr_t)(p + x0)) & 3) == 0) return __ldg((const uint32_t*)(p + x0));
+// 4 bytes of row 'row' at columns x0 .. x0+3, any alignment.  Columns outside the plane are
+// mirrored about its edges (column -1-k for k < 0, 2w-1-k for k >= w; zero where that falls
+// outside too): the extension on which the reference's edge sums become plain windows.
+__device__ __noinline__ uint32_t load4_edge(const uint8_t* __restrict__ p, int width, int x0) {
   uint32_t v = 0;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     int c = x0 + k;
-    c = c < 0 ? -1 - c : (c >= j.width ? 2 * j.width - 1 - c : c);
-    if (c >= 0 && c < j.width) v |= (uint32_t)__ldg(p + c) << (8 * k);
+    c = c < 0 ? -1 - c : (c >= width ? 2 * width - 1 - c : c);
+    if (c >= 0 && c < width) v |= (uint32_t)__ldg(p + c) << (8 * k);
   }
   return v;
+}
+
+// Used-level bits of one plane: flags in shared memory, one ballot per warp at the end.
+// Alpha planes are mostly flat: a word equal to the previous one, or made of one byte value,
+// costs one store or none.
+__device__ __forceinline__ void flag_word(uint8_t* flag, uint32_t v, uint32_t& last, bool& have) {
+  if (have && v == last) return;
+  last = v;
+  have = true;
+  const uint32_t b0 = v & 0xff;
+  flag[b0] = 1;
+  if (v != b0 * 0x01010101u) {
+    flag[(v >> 8) & 0xff] = 1;
+    flag[(v >> 16) & 0xff] = 1;
+    flag[v >> 24] = 1;
+  }
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -69,17 +85,22 @@ dq_levels_kernel(const DqJobDev* __restrict__ jobs, DqStats* __restrict__ stats)
   flag[threadIdx.x] = 0;
   __syncthreads();
   for (int row = blockIdx.x * kWarps + warp; row < j.height; row += gridDim.x * kWarps) {
-    uint32_t last = 0;
-    bool fresh = true;
-    for (int x0 = lane * 4; x0 < j.width; x0 += 128) {
-      const uint32_t v = load4(j, row, x0);
-      if (!fresh && v == last) continue;   // flat runs: nothing new to flag
-      last = v;
-      fresh = false;
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (x0 + k < j.width) flag[(v >> (8 * k)) & 0xff] = 1;
+    const uint8_t* p = j.src + (size_t)row * j.src_stride;
+    int x = 0;
+    if ((((uintptr_t)p) & 15) == 0) {
+      const int nvec = j.width >> 4;
+      uint32_t last = 0;
+      bool have = false;
+      for (int i = lane; i < nvec; i += 32) {
+        const uint4 v = b2_ldg_stream_v4(p + 16 * i);
+        flag_word(flag, v.x, last, have);
+        flag_word(flag, v.y, last, have);
+        flag_word(flag, v.z, last, have);
+        flag_word(flag, v.w, last, have);
+      }
+      x = nvec << 4;
     }
+    for (x += lane; x < j.width; x += 32) flag[__ldg(p + x)] = 1;
   }
   __syncthreads();
   const uint32_t bits = __ballot_sync(0xffffffffu, flag[threadIdx.x] != 0);
@@ -140,75 +161,80 @@ dq_smooth_kernel(const DqJobDev* __restrict__ jobs, const DqStats* __restrict__ 
   const int yb = (int)(unit / j.tiles_x) * kBandRows, ye = min(yb + kBandRows, h);
   const bool writer = lane >= 1 && lane <= 30 && x0 < w;
   const int filt_end = active ? h - r : 0;          // rows [0, filt_end) are smoothed
-  const uint32_t scale = (1u << (kFix + kLfix)) / (uint32_t)((2 * r + 1) * (2 * r + 1));
+  const uint32_t scale16 = ((1u << (kFix + kLfix)) / (uint32_t)((2 * r + 1) * (2 * r + 1))) << 16;   // average = umulhi(box, scale16)
   const uint32_t m2 = r >= 2 ? ~0u : 0u, m3 = r >= 3 ? ~0u : 0u, m4 = r >= 4 ? ~0u : 0u;
+  const bool inside = x0 >= 0 && x0 + 3 < w;
+  const bool fast_src = inside && ((((uintptr_t)(j.src + x0)) | (uint32_t)j.src_stride) & 3) == 0;
+  const bool fast_dst = inside && ((((uintptr_t)(j.dst + x0)) | (uint32_t)j.dst_stride) & 3) == 0;
+  auto ld = [&](int row) -> uint32_t {
+    const uint8_t* p = j.src + (size_t)row * j.src_stride;
+    return fast_src ? __ldg((const uint32_t*)(p + x0)) : load4_edge(p, w, x0);
+  };
+  // keep = vmin < v < vmax as one unsigned compare
+  const uint32_t keep_lo = (uint32_t)(vmin + 1), keep_span = (uint32_t)(vmax - vmin - 1);
+  const uint32_t lut_mid = (uint32_t)__cvta_generic_to_shared(lut) + 2u * kLutSize;
 
-  uint32_t cs[4] = {0, 0, 0, 0};
+  // vertical sums of my 4 columns, two 16-bit fields per word (fields stay below 2^16)
+  uint32_t cs01 = 0, cs23 = 0;
   if (yb < filt_end) {
     for (int k = -r; k <= r; ++k) {
-      const uint32_t v = load4(j, max(yb + k, 0), x0);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) cs[q] += (v >> (8 * q)) & 0xff;
+      const uint32_t v = ld(max(yb + k, 0));
+      cs01 += __byte_perm(v, 0, 0x4140);
+      cs23 += __byte_perm(v, 0, 0x4342);
     }
   }
   for (int y = yb; y < ye; ++y) {
-    const uint32_t pix = load4(j, y, x0);
+    const uint32_t pix = ld(y);
     uint32_t out = pix;
     if (y < filt_end) {                              // warp-uniform
       if (y > yb) {
-        const uint32_t a = load4(j, y + r, x0), s = load4(j, max(y - 1 - r, 0), x0);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) cs[q] += ((a >> (8 * q)) & 0xff) - ((s >> (8 * q)) & 0xff);
+        const uint32_t a = ld(y + r), s = ld(max(y - 1 - r, 0));
+        cs01 += __byte_perm(a, 0, 0x4140) - __byte_perm(s, 0, 0x4140);
+        cs23 += __byte_perm(a, 0, 0x4342) - __byte_perm(s, 0, 0x4342);
       }
-      const uint32_t p0 = cs[0] | (cs[1] << 16), p1 = cs[2] | (cs[3] << 16);
-      const uint32_t l0 = __shfl_up_sync(0xffffffffu, p0, 1), l1 = __shfl_up_sync(0xffffffffu, p1, 1);
-      const uint32_t r0 = __shfl_down_sync(0xffffffffu, p0, 1), r1 = __shfl_down_sync(0xffffffffu, p1, 1);
+      // column pairs at even offsets from x0 - 4 (P) and at odd offsets (Q)
+      const uint32_t P0 = __shfl_up_sync(0xffffffffu, cs01, 1), P1 = __shfl_up_sync(0xffffffffu, cs23, 1);
+      const uint32_t P4 = __shfl_down_sync(0xffffffffu, cs01, 1), P5 = __shfl_down_sync(0xffffffffu, cs23, 1);
       if (writer) {
-        const uint32_t v[12] = {l0 & 0xffff, l0 >> 16, l1 & 0xffff, l1 >> 16, cs[0], cs[1], cs[2], cs[3],
-                                r0 & 0xffff, r0 >> 16, r1 & 0xffff, r1 >> 16};
-        // plain (2r+1)-wide windows on the mirrored extension ...
-        uint32_t box[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          box[q] = v[3 + q] + v[4 + q] + v[5 + q] + ((v[2 + q] + v[6 + q]) & m2) + ((v[1 + q] + v[7 + q]) & m3) +
-                   ((v[q] + v[8 + q]) & m4);
-        // ... which is the reference's right mirror exactly; its left mirror takes column r-x
-        // instead of column x+r (sum cs[0..x+r-1] + sum cs[0..r-x]): both lie in v[0..11]
+        const uint32_t P2 = cs01, P3 = cs23;
+        const uint32_t Q0 = __byte_perm(P0, P1, 0x5432), Q1 = __byte_perm(P1, P2, 0x5432), Q2 = __byte_perm(P2, P3, 0x5432),
+                       Q3 = __byte_perm(P3, P4, 0x5432), Q4 = __byte_perm(P4, P5, 0x5432);
+        // plain (2r+1)-wide windows on the mirrored extension: outputs 0,1 centred on offsets 4,5; 2,3 on 6,7
+        uint32_t box01 = P2 + Q1 + Q2 + ((P1 + P3) & m2) + ((Q0 + Q3) & m3) + ((P0 + P4) & m4);
+        uint32_t box23 = P3 + Q2 + Q3 + ((P2 + P4) & m2) + ((Q1 + Q4) & m3) + ((P1 + P5) & m4);
+        // ... which is the reference's right mirror exactly; its left mirror (sum cs[0..x+r-1] +
+        // sum cs[0..r-x] for x <= r) is the window centred on max(x-1, 0): only the lanes at
+        // columns 0 and, for r = 4, 4 of the plane re-arrange their sums.
         if (x0 <= r) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int x = x0 + q;
-            if (x <= r) {
-              const int ia = r - x - x0 + 4, ib = x + r - x0 + 4;
-              uint32_t add = 0, sub = 0;
-#pragma unroll
-              for (int i = 0; i < 12; ++i) {
-                add = (i == ia) ? v[i] : add;
-                sub = (i == ib) ? v[i] : sub;
-              }
-              box[q] += add - sub;
-            }
+          if (x0 == 0) {
+            const uint32_t n0 = box01 & 0xffff, n1 = box01 >> 16, n2 = box23 & 0xffff, n3 = box23 >> 16;
+            box01 = n0 | (n0 << 16);
+            box23 = (r >= 2 ? n1 : n2) | ((r >= 3 ? n2 : n3) << 16);
+          } else {   // column 4 takes the window centred on 3: columns -1 (= 0) .. 7
+            const uint32_t t = P0 + P1 + P2 + P3;
+            box01 = (box01 & 0xffff0000u) | ((t & 0xffff) + (t >> 16) + (P0 & 0xffff));
           }
         }
-        const uint64_t kDither = 0x5d7f91b36e4ca280ull;   // kOrderedDither (:39-44), nibble row * 4 + col
-        out = 0;
+        const uint32_t drow = DFIX ? (uint32_t)(0x5d7f91b36e4ca280ull >> (16 * ((y + r) & 3))) : 0u;   // kOrderedDither row (:39-44), a nibble per column
+        uint32_t res[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const int pv = (int)((pix >> (8 * q)) & 0xff);
-          int res = pv;
-          if (pv < vmax && pv > vmin) {
-            const int avg = (int)(((box[q] & 0xffff) * scale) >> kFix);
-            int c = (pv << DFIX) + lut[kLutSize + avg - (pv << kLfix)];
-            if (DFIX) c += (int)((kDither >> (4 * ((((y + r) & 3) << 2) + ((x0 + q) & 3)))) & 15);
-            res = c < 0 ? 0 : (c >= (256 << DFIX)) ? 255 : (c >> DFIX);
-          }
-          out |= (uint32_t)res << (8 * q);
+          const uint32_t box = (q & 1) ? ((q < 2 ? box01 : box23) >> 16) : ((q < 2 ? box01 : box23) & 0xffff);
+          const uint32_t pv = (pix >> (8 * q)) & 0xff;
+          const uint32_t avg = __umulhi(box, scale16);
+          int corr;
+          asm volatile("ld.shared.s16 %0, [%1];" : "=r"(corr) : "r"(lut_mid + 2u * avg - 8u * pv));
+          int c = (int)(pv << DFIX) + corr;
+          if (DFIX) c += (int)((drow >> (4 * q)) & 15);
+          c = min(max(c, 0), (256 << DFIX) - 1) >> DFIX;
+          res[q] = (pv - keep_lo < keep_span) ? (uint32_t)c : pv;
         }
+        out = res[0] | (res[1] << 8) | (res[2] << 16) | (res[3] << 24);
       }
     }
     if (writer) {
       uint8_t* d = j.dst + (size_t)y * j.dst_stride + x0;
-      if (x0 + 3 < w && (((uintptr_t)d) & 3) == 0) {
+      if (fast_dst) {
         *(uint32_t*)d = out;
       } else {
 #pragma unroll

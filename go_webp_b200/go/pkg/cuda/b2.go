@@ -644,3 +644,31 @@ func (c *Context) RescalePlanes(stream int, jobs []RescaleJob) error {
 	}
 	return status(c, C.b2_rescale_planes(c.h, C.int(stream), &cj[0], C.int(len(cj))))
 }
+
+// AlphaDequantJob is one alpha plane of a DequantizeLevels batch (device pointers, strides in
+// bytes, Dst != Src).
+type AlphaDequantJob struct {
+	Src, Dst             DevicePtr
+	SrcStride, DstStride int
+	Width, Height        int
+	Strength             int // options.alpha_dithering_strength, 0..100
+}
+
+// DequantizeLevels replaces WebPDequantizeLevels
+// (pkg/libwebp/utils/quant_levels_dec_utils.c.go:259-286) as ALPHDecode calls it on the decoded
+// alpha plane (pkg/libwebp/decoder/alpha_dec.go:198-203).  orderedDither = true is this
+// tree's text (DFIX = 4 with the 4x4 dither table); false is the stock libwebp build.
+func (c *Context) DequantizeLevels(stream int, jobs []AlphaDequantJob, orderedDither bool) error {
+	if len(jobs) == 0 {
+		return nil
+	}
+	cj := make([]C.b2_alpha_dequant_job, len(jobs))
+	for i, j := range jobs {
+		cj[i] = C.b2_alpha_dequant_job{
+			src: (*C.uint8_t)(unsafe.Pointer(uintptr(j.Src))), dst: (*C.uint8_t)(unsafe.Pointer(uintptr(j.Dst))),
+			src_stride: C.int32_t(j.SrcStride), dst_stride: C.int32_t(j.DstStride),
+			width: C.int32_t(j.Width), height: C.int32_t(j.Height), strength: C.int32_t(j.Strength),
+		}
+	}
+	return status(c, C.b2_alpha_dequantize_levels(c.h, C.int(stream), &cj[0], C.int(len(cj)), boolInt(orderedDither)))
+}

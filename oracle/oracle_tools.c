@@ -5,8 +5,10 @@
  *
  * TEST INFRASTRUCTURE ONLY (see oracle.c).  Pinned against the libwebp 1.6.0 binary,
  * which exports WebPCleanupTransparentArea and WebPBlendAlpha
- * (tests/golden/make_golden_tools.py).  File:line citations are relative to the
- * go-webp tree.
+ * (tests/golden/make_golden_tools.py).  Later sections carry their own pin in their
+ * headers (animation: WebPAnimDecoder; alpha filters: ALPH chunks of real files; rescaler:
+ * WebPPictureRescale; level smoothing: WebPDecode with alpha_dithering_strength, stock
+ * DFIX = 0 build).  File:line citations are relative to the go-webp tree.
  */
 #include <stddef.h>
 #include <stdint.h>
@@ -601,7 +603,8 @@ int orc_rescale_plane(const uint8_t* src, int src_width, int src_height, int src
 /* The Go file keeps the ordered-dither branch of the C source (DFIX = 4, :36-45); the stock
  * libwebp build leaves USE_DITHERING undefined (DFIX = 0, no dither).  `dfix` selects: 4 is
  * the reference as written, 0 is what the libwebp 1.6.0 binary runs (the pinned variant);
- * the two differ in this constant and the dither add only. */
+ * the two differ in this constant and the dither add only.  PINNED (dfix = 0) against
+ * WebPDecode of files with quantised alpha levels: tests/golden/make_golden_dequant.py. */
 static const uint8_t kOrderedDither[DQ_DSIZE][DQ_DSIZE] = {{0, 8, 2, 10}, {12, 4, 14, 6}, {3, 11, 1, 9}, {15, 7, 13, 5}};
 typedef struct {
   int width, height, stride, row;

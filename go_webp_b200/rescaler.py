@@ -1,7 +1,7 @@
 """Host-side mirror of the rescaler: RescalePlane (pkg/libwebp/enc/
 picture_rescale_enc.c.go:125-136) over WebPRescalerImport / WebPRescalerExport
 (pkg/libwebp/utils/rescaler_utils.c.go:119-158), WebPRescalerGetScaledDimensions (:88-113)
-and the YUV branch of WebPPictureRescale (:149-200, pictures without alpha), plus one added
+and WebPPictureRescale (:149-220: YUV420 with or without alpha, ARGB), plus one added
 batched entry point.  The work happens in b2_rescale.cu through the C ABI (no CPU fallback)."""
 from __future__ import annotations
 
@@ -67,21 +67,40 @@ def RescalePlane(src: np.ndarray, dst_width: int, dst_height: int, num_channels:
 
 
 def WebPPictureRescale(pic: Picture, width: int, height: int) -> int:
-    """picture_rescale_enc.c.go:149-200 for YUV420 pictures without alpha (the ARGB and
-    alpha branches premultiply around the same RescalePlane calls: not mirrored here)."""
+    """picture_rescale_enc.c.go:149-220.  YUV420: alpha (if any) is rescaled first, luma is
+    premultiplied by the source alpha (AlphaMultiplyY :143-147), Y / U / V are rescaled, luma
+    is divided by the new alpha.  ARGB: premultiply (AlphaMultiplyARGB :138-141), 4-channel
+    rescale, un-premultiply."""
+    from . import dsp
     if pic is None:
         return 0
-    ok, width, height = WebPRescalerGetScaledDimensions(pic.Width, pic.Height, width, height)
+    prev_w, prev_h = pic.Width, pic.Height
+    ok, width, height = WebPRescalerGetScaledDimensions(prev_w, prev_h, width, height)
     if not ok:
         return pic.SetEncodingError(ENC_ERROR_BAD_DIMENSION)
-    if pic.UseARGB or pic.A is not None:
-        raise NotImplementedError("WebPPictureRescale: only the YUV420 branch without alpha is mirrored")
     halve = lambda x: (x + 1) >> 1  # noqa: E731
     try:
-        y = RescalePlane(pic.Y, width, height)
-        u, v = RescalePlanesBatch([pic.U, pic.V], [(halve(width), halve(height))] * 2)
+        if not pic.UseARGB:
+            crop = lambda p, w, h: np.ascontiguousarray(np.asarray(p)[:h, :w])  # noqa: E731
+            y, u, v = crop(pic.Y, prev_w, prev_h), crop(pic.U, halve(prev_w), halve(prev_h)), crop(pic.V, halve(prev_w), halve(prev_h))
+            a2 = None
+            if pic.A is not None:
+                a = crop(pic.A, prev_w, prev_h)
+                y = dsp.WebPMultRows(y, a, prev_w, prev_h, 0)
+                y2, a2 = RescalePlanesBatch([y, a], [(width, height)] * 2)
+                y2 = dsp.WebPMultRows(y2, a2, width, height, 1)
+            else:
+                y2 = RescalePlane(y, width, height)
+            u2, v2 = RescalePlanesBatch([u, v], [(halve(width), halve(height))] * 2)
+            pic.Y, pic.U, pic.V, pic.A = y2, u2, v2, a2
+            pic.YStride, pic.UVStride, pic.AStride = width, halve(width), (width if a2 is not None else 0)
+        else:
+            argb = np.ascontiguousarray(np.asarray(pic.ARGB, np.uint32)[:prev_h, :prev_w])
+            pre = np.ascontiguousarray(dsp.WebPMultARGBRows(argb, prev_w, prev_h, 0))
+            out = RescalePlane(pre.view(np.uint8).reshape(prev_h, 4 * prev_w), width, height, 4)
+            pic.ARGB = dsp.WebPMultARGBRows(np.ascontiguousarray(out).view(np.uint32).reshape(height, width), width, height, 1)
+            pic.ARGBStride = width
     except B2Error as e:
         return pic.SetEncodingError(_STATUS_TO_ENC.get(e.status, ENC_ERROR_OUT_OF_MEMORY))
-    pic.Y, pic.U, pic.V = y, u, v
-    pic.Width, pic.Height, pic.YStride, pic.UVStride = width, height, width, halve(width)
+    pic.Width, pic.Height = width, height
     return 1

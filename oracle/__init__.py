@@ -445,6 +445,23 @@ def rescale_plane(plane, dst_width, dst_height, num_channels=1):
     return out
 
 
+def picture_rescale_yuva(y, u, v, a, width, height):
+    """WebPPictureRescale, YUV420 branch with alpha (picture_rescale_enc.c.go:174-194):
+    alpha first, luma premultiplied by the source alpha, rescaled, divided by the new alpha."""
+    hw, hh = (width + 1) >> 1, (height + 1) >> 1
+    a2 = rescale_plane(a, width, height)
+    y2 = rescale_plane(mult_rows(y, a, 0), width, height)
+    return mult_rows(y2, a2, 1), rescale_plane(u, hw, hh), rescale_plane(v, hw, hh), a2
+
+
+def picture_rescale_argb(argb, width, height):
+    """WebPPictureRescale, ARGB branch (picture_rescale_enc.c.go:196-212)."""
+    pre = np.ascontiguousarray(mult_argb_rows(argb, 0))
+    h, w = pre.shape
+    out = rescale_plane(pre.view(np.uint8).reshape(h, 4 * w), width, height, 4)
+    return mult_argb_rows(np.ascontiguousarray(out).view(np.uint32).reshape(height, width), 1)
+
+
 def dequantize_levels(plane, strength, ordered_dither=False):
     """WebPDequantizeLevels on an alpha plane -> new plane.  ordered_dither: the Go file's
     DFIX = 4 branch; False is the stock libwebp build (DFIX = 0)."""

@@ -265,3 +265,27 @@ def picture_rescale_yuv(y, u, v, width, height):
     out = (_plane(p.y, p.y_stride, p.width, p.height), _plane(p.u, p.uv_stride, uvw, uvh), _plane(p.v, p.uv_stride, uvw, uvh))
     L.WebPPictureFree(C.byref(p))
     return out
+
+
+def picture_rescale_yuva(y, u, v, a, width, height):
+    """WebPPictureRescale on a YUV420A picture (alpha rescaled first, luma premultiplied
+    around its rescale, picture_rescale_enc.c.go:174-194) -> (y, u, v, a)."""
+    L = lib()
+    p = _picture_yuva(y, u, v, a)
+    if not L.WebPPictureRescale(C.byref(p), width, height):
+        raise ValueError("WebPPictureRescale failed")
+    out = _read_yuva(p)
+    L.WebPPictureFree(C.byref(p))
+    return out
+
+
+def picture_rescale_argb(argb, width, height):
+    """WebPPictureRescale on an ARGB picture (premultiply, 4-channel rescale, un-premultiply,
+    picture_rescale_enc.c.go:196-212) -> argb."""
+    L = lib()
+    p = _picture_argb(argb)
+    if not L.WebPPictureRescale(C.byref(p), width, height):
+        raise ValueError("WebPPictureRescale failed")
+    out = _read_argb(p)
+    L.WebPPictureFree(C.byref(p))
+    return out

@@ -163,8 +163,48 @@ def gen_rescale():
     print(f"{n} planes: oracle == libwebp binary for the rescaler")
 
 
+def gen_rescale_alpha():
+    """rescale_alpha_libwebp160.npz: WebPPictureRescale on YUV420A and ARGB pictures: the
+    premultiplying branches around RescalePlane (picture_rescale_enc.c.go:138-147, 174-212:
+    WebPMultRows / WebPMultARGBRows before, their inverses after)."""
+    rng = np.random.default_rng(5)
+    store, names = {}, []
+    n = 0
+    for (w, h, dw, dh) in [(64, 48, 32, 24), (40, 30, 90, 70), (33, 17, 20, 40), (7, 9, 3, 2), (3, 2, 9, 11), (1, 1, 4, 4),
+                           (120, 80, 119, 81), (50, 20, 50, 20)]:
+        for alpha_kind in ("random", "binary", "smooth"):
+            yy, xx = np.mgrid[0:h, 0:w]
+            a = {"random": rng.integers(0, 256, (h, w)), "binary": rng.integers(0, 2, (h, w)) * 255,
+                 "smooth": (xx * 255) // max(1, w - 1) + 0 * yy}[alpha_kind].astype(np.uint8)
+            y = rng.integers(0, 256, (h, w), dtype=np.uint8)
+            u = rng.integers(0, 256, ((h + 1) // 2, (w + 1) // 2), dtype=np.uint8)
+            v = rng.integers(0, 256, ((h + 1) // 2, (w + 1) // 2), dtype=np.uint8)
+            exp = ref.picture_rescale_yuva(y, u, v, a, dw, dh)
+            got = oracle.picture_rescale_yuva(y, u, v, a, dw, dh)
+            for e, g_ in zip(exp, got):
+                assert (e == g_).all(), ("yuva", w, h, dw, dh, alpha_kind)
+            argb = rng.integers(0, 2**32, (h, w), dtype=np.uint32)
+            argb = (argb & 0x00ffffff) | (a.astype(np.uint32) << 24)
+            eargb = ref.picture_rescale_argb(argb, dw, dh)
+            assert (oracle.picture_rescale_argb(argb, dw, dh) == eargb).all(), ("argb", w, h, dw, dh, alpha_kind)
+            if w * h > 3200 and alpha_kind != "random":
+                continue   # checked above, not stored (fixture size)
+            k = f"c{n}"
+            n += 1
+            names.append(k)
+            for nm, arr in zip("yuva", (y, u, v, a)):
+                store[f"{k}/{nm}"] = arr
+            for nm, arr in zip("yuva", exp):
+                store[f"{k}/out_{nm}"] = arr
+            store[f"{k}/argb"], store[f"{k}/out_argb"] = argb, eargb
+    store["names"] = np.array(names)
+    np.savez_compressed(os.path.join(HERE, "rescale_alpha_libwebp160.npz"), **store)
+    print(f"{n} pictures (YUVA + ARGB each): oracle == libwebp binary for WebPPictureRescale with alpha")
+
+
 if __name__ == "__main__":
     main()
     gen_import_argb()
     gen_dithered()
     gen_rescale()
+    gen_rescale_alpha()

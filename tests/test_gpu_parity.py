@@ -993,3 +993,16 @@ def test_rescaler(gpu, golden_dir):
     assert (pic.Y == oracle.rescale_plane(y, 64, 36)).all() and (pic.U == oracle.rescale_plane(u, 32, 18)).all()
     assert (pic.V == oracle.rescale_plane(v, 32, 18)).all()
     assert R.WebPPictureRescale(P.Picture(Width=4, Height=4, Y=y[:4, :4], U=u[:2, :2], V=v[:2, :2]), 0, 0) == 0
+    # the premultiplying branches (YUV420A, ARGB) against what the libwebp binary returned
+    g = np.load(os.path.join(golden_dir, "rescale_alpha_libwebp160.npz"))
+    for k in [str(k) for k in g["names"]]:
+        h, w = g[f"{k}/y"].shape
+        dh, dw = g[f"{k}/out_y"].shape
+        pic = P.Picture(Width=w, Height=h, Y=g[f"{k}/y"], U=g[f"{k}/u"], V=g[f"{k}/v"], A=g[f"{k}/a"], ColorSpace=P.WEBP_YUV420A)
+        assert R.WebPPictureRescale(pic, dw, dh) == 1
+        for got, nm in ((pic.Y, "y"), (pic.U, "u"), (pic.V, "v"), (pic.A, "a")):
+            assert (got == g[f"{k}/out_{nm}"]).all(), (k, nm)
+        pic = P.Picture(Width=w, Height=h, UseARGB=True, ARGB=g[f"{k}/argb"], ARGBStride=w)
+        assert R.WebPPictureRescale(pic, dw, dh) == 1
+        assert (pic.ARGB == g[f"{k}/out_argb"]).all(), (k, "argb")
+        assert (pic.Width, pic.Height, pic.ARGBStride) == (dw, dh, dw)

@@ -304,6 +304,19 @@ def test_alpha_unfilters_match_libwebp_streams(golden_dir):
     assert kinds == {0, 1, 2, 3}
 
 
+def test_picture_rescale_with_alpha_matches_libwebp_binary(golden_dir):
+    """WebPPictureRescale's premultiplying branches (picture_rescale_enc.c.go:138-147,
+    174-212) on YUV420A and ARGB pictures vs what the binary returned."""
+    g = _load(golden_dir, "rescale_alpha_libwebp160.npz")
+    for k in g["names"]:
+        dh, dw = g[f"{k}/out_y"].shape
+        got = oracle.picture_rescale_yuva(g[f"{k}/y"], g[f"{k}/u"], g[f"{k}/v"], g[f"{k}/a"], dw, dh)
+        for o, nm in zip(got, "yuva"):
+            assert (o == g[f"{k}/out_{nm}"]).all(), (k, nm)
+        assert (oracle.picture_rescale_argb(g[f"{k}/argb"], dw, dh) == g[f"{k}/out_argb"]).all(), k
+    assert len(g["names"]) >= 20
+
+
 def test_level_smoothing_matches_libwebp_decoder(golden_dir):
     """WebPDequantizeLevels (quant_levels_dec_utils.c.go:259-286) vs WebPDecode with
     alpha_dithering_strength on files the binary wrote with quantised alpha levels (the stock

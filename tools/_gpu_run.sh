@@ -1,2 +1,1 @@
-timeout 600 python -m pytest tests -m gpu -x -q -k "level_smoothing" 2>&1 | tail -5
-timeout 300 python tools/quick_bench.py dequant 2>&1 | tail -10
+timeout 600 python -m pytest tests -m gpu -x -q -k "rescaler or level_smoothing" 2>&1 | tail -12

@@ -28,7 +28,8 @@ constexpr int kThreads = 256;
 constexpr uint64_t kOne = 1ull << 32;
 constexpr uint64_t kRounder = kOne >> 1;
 
-struct XEnt { int32_t a, b, accum; };                 // expand: left, right sample; shrink: [a, b) consumed; accum after
+struct __align__(16) XEnt { int32_t a, b, accum, pad; };   // expand: left, right sample; shrink: [a, b) consumed; accum after
+                                                           // (16 bytes: one 128-bit load per entry, consecutive lanes = consecutive entries)
 struct YEnt { int32_t prev_last, last, y_accum; uint32_t prev_yscale, yscale; };   // last < 0: row never exported;
                                                                                    // expand: yscale holds B = FRAC(-y_accum, y_sub)
 
@@ -95,9 +96,9 @@ __device__ __forceinline__ uint32_t rescale_sample(const RescaleJobDev& j, const
   return min(mult_fix(irow, j.fxy_scale), 255u);
 }
 
-// unit = (job, output row, 1024 output samples); a thread computes 4 consecutive samples
+// unit = (job, output row, 1024 output samples); a thread computes 4 samples
 constexpr int kPerThread = 4;
-__global__ void __launch_bounds__(kThreads, 8)
+__global__ void __launch_bounds__(kThreads, 4)
 rescale_kernel(const RescaleJobDev* __restrict__ jobs, const uint32_t* __restrict__ prefix, uint32_t n_jobs, uint32_t uniform,
                uint32_t total, const XEnt* __restrict__ xpool, const YEnt* __restrict__ ypool) {
   __shared__ RescaleJobDev sj;
@@ -111,27 +112,22 @@ rescale_kernel(const RescaleJobDev* __restrict__ jobs, const uint32_t* __restric
       se = ypool[sj.ytab + local / sj.units_x];
     }
     __syncthreads();
-    const RescaleJobDev& j = sj;
-    const YEnt& e = se;
+    const RescaleJobDev j = sj;   // by value: the byte stores below could alias shared memory and force reloads
+    const YEnt e = se;
     if (e.last < 0) continue;                     // the state machine never exports this row
     const int dy = (int)(local / j.units_x);
-    const int s0 = ((int)(local % j.units_x) * kThreads + (int)threadIdx.x) * kPerThread;
+    // consecutive lanes take consecutive samples (table entries and source bytes coalesce);
+    // a thread's 4 samples are kThreads apart
+    const int sbase = (int)(local % j.units_x) * kThreads * kPerThread + (int)threadIdx.x;
     const int ch = j.num_channels, n_s = j.dst_width * ch;
-    if (s0 >= n_s) continue;
     const XEnt* __restrict__ xt = xpool + j.xtab;
-    uint8_t* out = j.dst + (ptrdiff_t)dy * j.dst_stride + s0;
-    uint32_t v[kPerThread];
-    int xo = s0 / ch, c = s0 - xo * ch;
+    uint8_t* out = j.dst + (ptrdiff_t)dy * j.dst_stride;
 #pragma unroll
     for (int k = 0; k < kPerThread; ++k) {
-      v[k] = (s0 + k < n_s) ? rescale_sample(j, xt, e, xo, c) : 0u;
-      if (++c == ch) { c = 0; ++xo; }
-    }
-    if (s0 + kPerThread <= n_s && (((uintptr_t)out) & 3) == 0) {
-      *reinterpret_cast<uint32_t*>(out) = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
-    } else {
-#pragma unroll
-      for (int k = 0; k < kPerThread; ++k) if (s0 + k < n_s) out[k] = (uint8_t)v[k];
+      const int s = sbase + k * kThreads;
+      if (s >= n_s) break;
+      const int xo = (ch == 1) ? s : s / ch, c = s - xo * ch;
+      out[s] = (uint8_t)rescale_sample(j, xt, e, xo, c);
     }
   }
 }
@@ -169,7 +165,7 @@ void build_xtab(const Geometry& g, int sw, int dw, std::vector<XEnt>* out) {
     int left = 0, right = (sw > 1) ? 1 : 0;
     x_in = right;
     for (int xo = 0;; ) {
-      out->push_back(XEnt{left, right, accum});
+      out->push_back(XEnt{left, right, accum, 0});
       if (++xo >= dw) break;
       accum -= g.x_sub;
       if (accum < 0) {
@@ -185,7 +181,7 @@ void build_xtab(const Geometry& g, int sw, int dw, std::vector<XEnt>* out) {
       const int begin = x_in;
       accum += g.x_add;
       while (accum > 0) { accum -= g.x_sub; ++x_in; }
-      out->push_back(XEnt{begin, x_in, accum});
+      out->push_back(XEnt{begin, x_in, accum, 0});
     }
   }
 }
@@ -272,7 +268,7 @@ extern "C" int b2_rescale_planes(b2_ctx* ctx, int stream, const b2_rescale_job* 
   const int st = b2_upload_desc(ctx, stream, host.data(), host.size(), &dev);
   if (st != B2_OK) return st;
   const uint8_t* base = (const uint8_t*)dev;
-  rescale_kernel<<<b2_grid_for(ctx, 8, tot), kThreads, 0, ctx->streams[stream]>>>(
+  rescale_kernel<<<b2_grid_for(ctx, 4, tot), kThreads, 0, ctx->streams[stream]>>>(
       (const RescaleJobDev*)base, (const uint32_t*)(base + jb), (uint32_t)n_jobs, uni, (uint32_t)tot,
       (const XEnt*)(base + jb + pb), (const YEnt*)(base + jb + pb + xb));
   ctx->launches++;

@@ -1,3 +1,2 @@
-timeout 600 python bench.py > gpurun_out/b1.json 2> gpurun_out/b1.err; python -c "import json; d=json.loads(open('gpurun_out/b1.json').read().strip().splitlines()[-1]); print(d['value'], d['clocks'])"
-B2_CLOCKS=smi timeout 600 python bench.py > gpurun_out/b2.json 2> gpurun_out/b2.err; python -c "import json; d=json.loads(open('gpurun_out/b2.json').read().strip().splitlines()[-1]); print(d['value'], d['clocks'])"
-tail -3 gpurun_out/b2.err
+timeout 600 python -m pytest tests -m gpu -x -q -k "rescaler or maximum_dimension" 2>&1 | tail -5
+timeout 300 python tools/quick_bench.py rescale 2>&1 | tail -4

@@ -49,17 +49,16 @@ __device__ __forceinline__ uint32_t mult_fix_floor(uint32_t x, uint32_t y) { ret
 // frow[xo] of source row `row` (rescaler.c.go:39-105), c = channel
 // XE / YE / CH: compile-time x_expand / y_expand / num_channels of a batch whose jobs all agree (-1: read the job)
 template <int XE, int CH>
-__device__ __forceinline__ uint32_t frow_at(const RescaleJobDev& j, const XEnt* __restrict__ xt, const uint8_t* __restrict__ row,
+// e = the x-table entry of output sample xo, p = the entry of xo - 1 (shrinking only)
+__device__ __forceinline__ uint32_t frow_at(const RescaleJobDev& j, const XEnt& e, const XEnt& p, const uint8_t* __restrict__ row,
                                             int xo, int c) {
   const int ch = CH > 0 ? CH : j.num_channels;
-  const XEnt e = xt[xo];
   if (XE < 0 ? j.x_expand : XE) {
     const uint32_t left = row[e.a * ch + c], right = row[e.b * ch + c];
     return right * (uint32_t)j.x_add + (left - right) * (uint32_t)e.accum;
   }
   uint32_t sum = 0;
   if (xo > 0) {   // fractional start left by the previous output sample
-    const XEnt p = xt[xo - 1];
     sum = mult_fix((uint32_t)row[(p.b - 1) * ch + c] * (uint32_t)(-p.accum), j.fx_scale);
   }
   uint32_t base = 0;
@@ -72,13 +71,13 @@ __device__ __forceinline__ uint32_t frow_at(const RescaleJobDev& j, const XEnt* 
 
 // one output sample: row dy, sample s = x_out * channels + c
 template <int XE, int YE, int CH>
-__device__ __forceinline__ uint32_t rescale_sample(const RescaleJobDev& j, const XEnt* __restrict__ xt, const YEnt& e, int xo, int c) {
+__device__ __forceinline__ uint32_t rescale_sample(const RescaleJobDev& j, const XEnt& ex, const XEnt& px, const YEnt& e, int xo, int c) {
   const uint8_t* last_row = j.src + (ptrdiff_t)e.last * j.src_stride;
   if (YE < 0 ? j.y_expand : YE) {                               // ExportRowExpand, rescaler.c.go:110-136
-    const uint32_t f = frow_at<XE, CH>(j, xt, last_row, xo, c);
+    const uint32_t f = frow_at<XE, CH>(j, ex, px, last_row, xo, c);
     uint32_t J = f;
     if (e.y_accum != 0) {
-      const uint32_t i = (e.last > 0) ? frow_at<XE, CH>(j, xt, last_row - j.src_stride, xo, c) : 0u;   // irow = the previous row's frow
+      const uint32_t i = (e.last > 0) ? frow_at<XE, CH>(j, ex, px, last_row - j.src_stride, xo, c) : 0u;   // irow = the previous row's frow
       const uint32_t B = e.yscale;   // WEBP_RESCALER_FRAC(-y_accum, y_sub), from the host
       const uint32_t A = (uint32_t)(kOne - B);
       J = (uint32_t)(((uint64_t)A * f + (uint64_t)B * i + kRounder) >> 32);
@@ -88,10 +87,10 @@ __device__ __forceinline__ uint32_t rescale_sample(const RescaleJobDev& j, const
   // rows accumulated since the previous export (+ its fractional rest)
   uint32_t irow = 0;
   if (e.prev_last >= 0 && e.prev_yscale != 0u)
-    irow = mult_fix_floor(frow_at<XE, CH>(j, xt, j.src + (ptrdiff_t)e.prev_last * j.src_stride, xo, c), e.prev_yscale);
+    irow = mult_fix_floor(frow_at<XE, CH>(j, ex, px, j.src + (ptrdiff_t)e.prev_last * j.src_stride, xo, c), e.prev_yscale);
   uint32_t f = 0;
   for (int r = e.prev_last + 1; r <= e.last; ++r) {
-    f = frow_at<XE, CH>(j, xt, j.src + (ptrdiff_t)r * j.src_stride, xo, c);
+    f = frow_at<XE, CH>(j, ex, px, j.src + (ptrdiff_t)r * j.src_stride, xo, c);
     irow += f;
   }
   if (j.fxy_scale == 0u) return irow & 0xffu;     // special case, rescaler.c.go:184-191
@@ -99,33 +98,62 @@ __device__ __forceinline__ uint32_t rescale_sample(const RescaleJobDev& j, const
   return min(mult_fix(irow, j.fxy_scale), 255u);
 }
 
-// unit = (job, output row, 1024 output samples); a thread computes 4 samples
+// unit = (job, group of output rows, 1024 output samples); a thread computes 4 samples of
+// every row of the group with the x-table entries it loaded once.  Vertical expansion takes
+// 8 rows per unit (neighbouring output rows share their source rows), the others one.
 constexpr int kPerThread = 4;
+__host__ __device__ constexpr int rows_per_unit(int ye) { return ye == 1 ? 8 : 1; }
 template <int XE, int YE, int CH>
-__global__ void __launch_bounds__(kThreads, (CH > 0 && XE == 1) ? 6 : 4)
+__global__ void __launch_bounds__(kThreads, 4)
 rescale_kernel(const RescaleJobDev* __restrict__ jobs, const uint32_t* __restrict__ prefix, uint32_t n_jobs, uint32_t uniform,
                uint32_t total, const XEnt* __restrict__ xpool, const YEnt* __restrict__ ypool) {
   for (uint32_t unit = blockIdx.x; unit < total; unit += gridDim.x) {
     uint32_t local;
     const uint32_t img = b2_find_image(prefix, n_jobs, uniform, unit, &local);
-    // every thread reads the job and the row entry itself (uniform addresses: one broadcast
+    // every thread reads the job and the row entries itself (uniform addresses: one broadcast
     // transaction per warp, L1 hits after the first): no barrier, warps run ahead independently
     const RescaleJobDev j = jobs[img];
-    const YEnt e = ypool[j.ytab + local / j.units_x];
-    if (e.last < 0) continue;                     // the state machine never exports this row
-    const int dy = (int)(local / j.units_x);
     // consecutive lanes take consecutive samples (table entries and source bytes coalesce);
     // a thread's 4 samples are kThreads apart
     const int sbase = (int)(local % j.units_x) * kThreads * kPerThread + (int)threadIdx.x;
     const int ch = CH > 0 ? CH : j.num_channels, n_s = j.dst_width * ch;
+    if (sbase >= n_s) continue;
     const XEnt* __restrict__ xt = xpool + j.xtab;
-    uint8_t* out = j.dst + (ptrdiff_t)dy * j.dst_stride;
+    constexpr int kRowsPerUnit = rows_per_unit(YE);
+    const int dy0 = (int)(local / j.units_x) * kRowsPerUnit, dy1 = min(dy0 + kRowsPerUnit, j.dst_height);
+    if (kRowsPerUnit == 1) {       // one row: entries are used once, keep one sample's worth in registers
+      const YEnt e = ypool[j.ytab + dy0];
+      if (e.last < 0) continue;                     // the state machine never exports this row
+      uint8_t* out = j.dst + (ptrdiff_t)dy0 * j.dst_stride;
+#pragma unroll
+      for (int k = 0; k < kPerThread; ++k) {
+        const int s = sbase + k * kThreads;
+        if (s >= n_s) break;
+        const int xo = (ch == 1) ? s : s / ch, c = s - xo * ch;
+        out[s] = (uint8_t)rescale_sample<XE, YE, CH>(j, xt[xo], xt[max(xo - 1, 0)], e, xo, c);
+      }
+      continue;
+    }
+    XEnt ex[kPerThread], px[kPerThread];
+    int xo[kPerThread], c[kPerThread];
 #pragma unroll
     for (int k = 0; k < kPerThread; ++k) {
-      const int s = sbase + k * kThreads;
-      if (s >= n_s) break;
-      const int xo = (ch == 1) ? s : s / ch, c = s - xo * ch;
-      out[s] = (uint8_t)rescale_sample<XE, YE, CH>(j, xt, e, xo, c);
+      const int s = min(sbase + k * kThreads, n_s - 1);
+      xo[k] = (ch == 1) ? s : s / ch;
+      c[k] = s - xo[k] * ch;
+      ex[k] = xt[xo[k]];
+      px[k] = xt[max(xo[k] - 1, 0)];
+    }
+    for (int dy = dy0; dy < dy1; ++dy) {
+      const YEnt e = ypool[j.ytab + dy];
+      if (e.last < 0) continue;
+      uint8_t* out = j.dst + (ptrdiff_t)dy * j.dst_stride;
+#pragma unroll
+      for (int k = 0; k < kPerThread; ++k) {
+        const int s = sbase + k * kThreads;
+        if (s >= n_s) break;
+        out[s] = (uint8_t)rescale_sample<XE, YE, CH>(j, ex[k], px[k], e, xo[k], c[k]);
+      }
     }
   }
 }
@@ -245,7 +273,14 @@ extern "C" int b2_rescale_planes(b2_ctx* ctx, int stream, const b2_rescale_job* 
     d.fx_scale = g.fx_scale; d.fy_scale = g.fy_scale; d.fxy_scale = g.fxy_scale;
     d.xtab = it->second.first; d.ytab = it->second.second;
     d.units_x = (uint32_t)((j.dst_width * j.num_channels + kThreads * kPerThread - 1) / (kThreads * kPerThread));
-    const uint32_t items = d.units_x * (uint32_t)j.dst_height;
+  }
+  // batches whose jobs all share the direction and have one channel take a specialised instantiation
+  int cls = dj[0].num_channels == 1 ? (dj[0].x_expand * 2 + dj[0].y_expand) : -1;
+  for (int i = 1; i < n_jobs && cls >= 0; ++i)
+    if (dj[(size_t)i].num_channels != 1 || dj[(size_t)i].x_expand * 2 + dj[(size_t)i].y_expand != cls) cls = -1;
+  const int rows = rows_per_unit(cls < 0 ? -1 : (cls & 1));
+  for (int i = 0; i < n_jobs; ++i) {
+    const uint32_t items = dj[(size_t)i].units_x * (uint32_t)((dj[(size_t)i].dst_height + rows - 1) / rows);
     if (i == 0) uni = items; else if (items != uni) uni = 0;
     pre[(size_t)i] = (uint32_t)tot;
     tot += items;
@@ -266,12 +301,8 @@ extern "C" int b2_rescale_planes(b2_ctx* ctx, int stream, const b2_rescale_job* 
   const int st = b2_upload_desc(ctx, stream, host.data(), host.size(), &dev);
   if (st != B2_OK) return st;
   const uint8_t* base = (const uint8_t*)dev;
-  // batches whose jobs all share the direction and have one channel take a specialised instantiation
-  int cls = dj[0].num_channels == 1 ? (dj[0].x_expand * 2 + dj[0].y_expand) : -1;
-  for (int i = 1; i < n_jobs && cls >= 0; ++i)
-    if (dj[(size_t)i].num_channels != 1 || dj[(size_t)i].x_expand * 2 + dj[(size_t)i].y_expand != cls) cls = -1;
 #define B2_RESCALE_LAUNCH(XE, YE, CH)                                                                            \
-  rescale_kernel<XE, YE, CH><<<b2_grid_for(ctx, ((CH) > 0 && (XE) == 1) ? 6 : 4, tot), kThreads, 0, ctx->streams[stream]>>>( \
+  rescale_kernel<XE, YE, CH><<<b2_grid_for(ctx, 4, tot), kThreads, 0, ctx->streams[stream]>>>( \
       (const RescaleJobDev*)base, (const uint32_t*)(base + jb), (uint32_t)n_jobs, uni, (uint32_t)tot,             \
       (const XEnt*)(base + jb + pb), (const YEnt*)(base + jb + pb + xb))
   switch (cls) {

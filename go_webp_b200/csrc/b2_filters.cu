@@ -184,33 +184,62 @@ alpha_unfilter_vertical_kernel(const FiltJobDev* __restrict__ jobs, const uint32
   }
 }
 
-// ---- unfilter, GRADIENT: one warp per image ---------------------------------------------
-// (one warp per CTA: the wavefront of an image is a single dependency chain, so the images
-// are spread over as many SMs as possible and the kernel gets all the registers it wants)
-__global__ void __launch_bounds__(32)
+// ---- unfilter, GRADIENT: one CTA per image, its warps pipelined down the bands ------------
+// A band of 32 rows is a wavefront inside one warp (lane = row, one column of skew per row).
+// Band b needs the last row of band b-1 one column ahead of its own lane 0, so the bands of an
+// image run as a pipeline: warp w takes bands w, w + kGradWarps, ...; after every 8 steps it
+// publishes how many columns of its band's last row are final (band * 2^14 + columns, one
+// word per warp in shared memory, monotonic), and the warp below waits for the columns it is
+// about to read.  The last row itself travels through global memory (written by lane 31,
+// CTA-scope fence, flag; read back by lane 0 with volatile loads after its own fence).
+constexpr int kGradWarps = 16;
+__global__ void __launch_bounds__(32 * kGradWarps)
 alpha_unfilter_gradient_kernel(const FiltJobDev* __restrict__ jobs, uint32_t n_jobs) {
-  const int lane = threadIdx.x & 31;
+  __shared__ volatile int progress[kGradWarps];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (uint32_t img = blockIdx.x; img < n_jobs; img += gridDim.x) {
     const FiltJobDev j = jobs[img];
+    __syncthreads();                 // the previous image's flags are no longer read
+    if (lane == 0) progress[warp] = 0;
+    __syncthreads();
     if (j.filter != 3) continue;
     const int w = j.width, h = j.height;
-    for (int band = 0; band < h; band += 32) {
+    const int producer = (warp + kGradWarps - 1) % kGradWarps;
+    for (int bi = warp; bi * 32 < h; bi += kGradWarps) {
+      const int band = bi * 32;
       const int row = band + lane;
       const bool row_ok = row < h;
       const uint8_t* in = j.src + (ptrdiff_t)row * j.src_stride;
       uint8_t* out = j.dst + (ptrdiff_t)row * j.dst_stride;
       const uint8_t* above = j.dst + (ptrdiff_t)(band - 1) * j.dst_stride;   // last row of the band above (band > 0)
+      const int need_base = (bi - 1) << 14;
+      auto wait_for = [&](int columns) {   // columns of the row above that must be final
+        if (band > 0) {
+          if (lane == 0) {
+            const int need = need_base + min(columns, w);
+            while (progress[producer] < need) {}
+            __threadfence_block();
+          }
+          __syncwarp();
+        }
+      };
       int left = 0, top_left = 0, cur_out = 0;
+      // a lane touches a different row than its neighbours, so every access costs the L1 one
+      // sector per lane: outputs leave as aligned 32-bit words (a quarter of the lanes per step)
+      const bool packed = ((((uintptr_t)j.dst) | (uint32_t)j.dst_stride) & 3) == 0;
+      uint32_t acc = 0;
       // inputs (and, for lane 0, the row above the band) are fetched 8 steps ahead: the step
       // is a dependency chain of a shuffle and a handful of ALU operations, nothing else
       uint32_t pre[8], apre[8];
+      wait_for(8);
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const int c = q - lane;
         pre[q] = (row_ok && c >= 0 && c < w) ? in[c] : 0u;
-        apre[q] = (lane == 0 && band > 0 && q < w) ? (uint32_t)__ldcg(above + q) : 0u;
+        apre[q] = (lane == 0 && band > 0 && q < w) ? (uint32_t)*(const volatile uint8_t*)(above + q) : 0u;
       }
       for (int k0 = 0; k0 < w + 31; k0 += 8) {
+        wait_for(k0 + 16);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const int k = k0 + q;
@@ -219,7 +248,7 @@ alpha_unfilter_gradient_kernel(const FiltJobDev* __restrict__ jobs, uint32_t n_j
           const int atop = (int)apre[q];
           const int cn = c + 8;
           pre[q] = (row_ok && cn >= 0 && cn < w) ? in[cn] : 0u;
-          apre[q] = (lane == 0 && band > 0 && k + 8 < w) ? (uint32_t)__ldcg(above + k + 8) : 0u;
+          apre[q] = (lane == 0 && band > 0 && k + 8 < w) ? (uint32_t)*(const volatile uint8_t*)(above + k + 8) : 0u;
           // top = (row-1, c): the lane above produced it on the previous step
           int top = __shfl_up_sync(0xffffffffu, cur_out, 1);
           if (lane == 0) top = atop;
@@ -228,15 +257,27 @@ alpha_unfilter_gradient_kernel(const FiltJobDev* __restrict__ jobs, uint32_t n_j
             if (row == 0) o = (v + left) & 0xff;                        // first row: horizontal, pred 0 at c == 0
             else if (c == 0) o = (v + top) & 0xff;                      // left = top = top_left = prev[0]
             else o = (v + gradient_pred(left, top, top_left)) & 0xff;
-            out[c] = (uint8_t)o;
+            acc = (acc >> 8) | ((uint32_t)o << 24);
+            if (!packed) {
+              out[c] = (uint8_t)o;
+            } else if ((c & 3) == 3) {
+              *(uint32_t*)(out + c - 3) = acc;
+            } else if (c == w - 1) {                                     // ragged end of the row
+              const uint32_t tail = acc >> (8 * (3 - (c & 3)));
+              for (int t = 0; t <= (c & 3); ++t) out[c - (c & 3) + t] = (uint8_t)(tail >> (8 * t));
+            }
             left = o;
             cur_out = o;
           }
           top_left = top;
         }
+        if (lane == 31) {            // columns 0 .. k0 + 7 - 31 of the band's last row are written
+          int done = min(max(k0 + 8 - 31, 0), w);
+          if (packed && done < w) done &= ~3;   // whole words only have left the registers
+          __threadfence_block();   // producer and consumer share the CTA; the row is read back with volatile loads
+          progress[warp] = (bi << 14) + done;
+        }
       }
-      __syncwarp();
-      __threadfence_block();   // the next band's lane 0 reads this band's last row back
     }
   }
 }
@@ -317,7 +358,7 @@ extern "C" int b2_alpha_unfilter(b2_ctx* ctx, int stream, const b2_alpha_filter_
     ctx->launches++;
   }
   if (counts[3] > 0) {
-    alpha_unfilter_gradient_kernel<<<b2_grid_for(ctx, 16, (uint64_t)n_jobs), 32, 0, s>>>(dj, (uint32_t)n_jobs);
+    alpha_unfilter_gradient_kernel<<<b2_grid_for(ctx, 2, (uint64_t)n_jobs), 32 * kGradWarps, 0, s>>>(dj, (uint32_t)n_jobs);
     ctx->launches++;
   }
   if (counts[2] > 0) {

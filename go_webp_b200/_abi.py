@@ -99,7 +99,7 @@ class RescaleJob(C.Structure):
 
 
 CONVERT_UPSTREAM_16BIT = 1
-ALPHA_APPLY, ALPHA_APPLY_4444, ALPHA_MULT_ARGB, ALPHA_MULT_ROW = 0, 1, 2, 3
+ALPHA_APPLY, ALPHA_APPLY_4444, ALPHA_MULT_ARGB, ALPHA_MULT_ROW, ALPHA_DISPATCH = 0, 1, 2, 3, 4
 
 # every symbol include/b2webp.h declares: name -> (restype, argtypes)
 _vp = C.c_void_p

@@ -181,7 +181,7 @@ import_argb_kernel(const ConvJobDev* __restrict__ jobs, const uint32_t* __restri
 }
 
 // ---- alpha multiplies (in place) ----------------------------------------------------
-enum { AM_APPLY = 0, AM_APPLY_4444 = 1, AM_MULT_ARGB = 2, AM_MULT_ROW = 3 };
+enum { AM_APPLY = 0, AM_APPLY_4444 = 1, AM_MULT_ARGB = 2, AM_MULT_ROW = 3, AM_DISPATCH = 4 };
 #define MFIX 24
 // Mult / GetScale, alpha_processing.go:17-31
 __device__ __forceinline__ uint32_t mult_scale(uint32_t a, bool inverse) {
@@ -224,6 +224,10 @@ alpha_multiply_kernel(const ConvJobDev* __restrict__ jobs, const uint32_t* __res
           }
         }
       }
+    } else if (kind == AM_DISPATCH) {  // DispatchAlpha_C (alpha_processing.go:165-180): alpha plane u -> alpha byte, flag = alpha_first
+      uint8_t* d = j.dst + (ptrdiff_t)y * j.dst_stride + x0 * 4 + (flag ? 0 : 3);
+      const uint8_t* al = j.u + (ptrdiff_t)y * j.uv_stride + x0;
+      for (int k = 0; k < nv; ++k) d[4 * k] = al[k];
     } else {  // WebPMultRow_C: plane dst, alpha plane u, flag = inverse
       uint8_t* d = j.dst + (ptrdiff_t)y * j.dst_stride + x0;
       const uint8_t* al = j.u + (ptrdiff_t)y * j.uv_stride + x0;
@@ -330,10 +334,10 @@ extern "C" int b2_vp8l_convert_from_bgra(b2_ctx* ctx, int stream, const b2_conve
 
 extern "C" int b2_alpha_multiply(b2_ctx* ctx, int stream, const b2_convert_job* jobs, int n_jobs, int kind, int flag) {
   B2_CONV_ENTRY_CHECKS
-  if (kind < 0 || kind > 3) return B2_ERR_INVALID_CONFIG;
-  const int bpp = (kind == B2_ALPHA_APPLY || kind == B2_ALPHA_MULT_ARGB) ? 4 : (kind == B2_ALPHA_APPLY_4444 ? 2 : 1);
+  if (kind < 0 || kind > 4) return B2_ERR_INVALID_CONFIG;
+  const int bpp = (kind == B2_ALPHA_APPLY || kind == B2_ALPHA_MULT_ARGB || kind == B2_ALPHA_DISPATCH) ? 4 : (kind == B2_ALPHA_APPLY_4444 ? 2 : 1);
   const ConvJobDev* dj; const uint32_t* dp; uint32_t uni, tot;
-  const int rc = prepare_conv(ctx, stream, jobs, n_jobs, kind == B2_ALPHA_MULT_ROW, bpp, &dj, &dp, &uni, &tot);
+  const int rc = prepare_conv(ctx, stream, jobs, n_jobs, kind == B2_ALPHA_MULT_ROW || kind == B2_ALPHA_DISPATCH, bpp, &dj, &dp, &uni, &tot);
   if (rc != B2_OK) return rc;
   alpha_multiply_kernel<<<b2_grid_for(ctx, 8, (tot + kWarps - 1) / kWarps), kThreads, 0, ctx->streams[stream]>>>(
       dj, dp, (uint32_t)n_jobs, uni, tot, kind, flag ? 1 : 0);

@@ -312,6 +312,15 @@ def WebPMultRows(ptr: np.ndarray, alpha: np.ndarray, width: int, num_rows: int, 
                     0, (num_rows, width), np.uint8, (_abi.ALPHA_MULT_ROW, int(inverse)))
 
 
+def WebPDispatchAlpha(alpha: np.ndarray, width: int, height: int, dst: np.ndarray, dst_stride: int, alpha_first: int = 0) -> np.ndarray:
+    """DispatchAlpha_C (alpha_processing.go:165-180) as ExportAlpha / EmitAlphaRGB call it: the
+    alpha plane written into the alpha byte of the 4-byte pixels of dst; returns the new dst."""
+    buf = np.ascontiguousarray(dst, np.uint8).reshape(height, dst_stride)
+    al = np.ascontiguousarray(alpha, np.uint8).reshape(height, width)
+    return _convert("b2_alpha_multiply", [buf, al], lambda p, po: _abi.ConvertJob(None, p[1], None, po, 0, width, dst_stride, width, height, 0),
+                    0, (height, dst_stride), np.uint8, (_abi.ALPHA_DISPATCH, int(alpha_first)))
+
+
 def WebPSamplerProcessPlane(y: np.ndarray, u: np.ndarray, v: np.ndarray, mode: int) -> np.ndarray:
     """dsp/yuv.go:47-58 with WebPSamplers[mode] (== EmitSampledRGB, io_dec.c.go:53-59):
     point-sampled chroma, y [h, w], u/v [ceil(h/2), ceil(w/2)] -> bytes [h, w*bpp]."""

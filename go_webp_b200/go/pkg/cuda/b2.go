@@ -422,7 +422,8 @@ func (c *Context) ConvertFromBGRA(stream int, jobs []ConvertJob, mode, flags int
 }
 
 // AlphaMultiply replaces ApplyAlphaMultiply_C / ..4444_C / WebPMultARGBRow_C / WebPMultRow_C
-// (pkg/libwebp/dsp/alpha_processing.go:17-163); kind is one of the B2_ALPHA_* values.
+// (pkg/libwebp/dsp/alpha_processing.go:17-163) and, with kind = C.B2_ALPHA_DISPATCH,
+// DispatchAlpha_C (:165-180); kind is one of the B2_ALPHA_* values.
 func (c *Context) AlphaMultiply(stream int, jobs []ConvertJob, kind, flag int) error {
 	if len(jobs) == 0 {
 		return nil

@@ -104,3 +104,48 @@ def WebPPictureRescale(pic: Picture, width: int, height: int) -> int:
         return pic.SetEncodingError(_STATUS_TO_ENC.get(e.status, ENC_ERROR_OUT_OF_MEMORY))
     pic.Width, pic.Height = width, height
     return 1
+
+
+_ALPHA_BYTE = {_abi.MODE_RGBA: 3, _abi.MODE_BGRA: 3, _abi.MODE_ARGB: 0, _abi.MODE_rgbA: 3, _abi.MODE_bgrA: 3, _abi.MODE_Argb: 0}
+_PREMULTIPLIED = (_abi.MODE_rgbA, _abi.MODE_bgrA, _abi.MODE_Argb)
+
+
+def EmitRescaledRGB(y: np.ndarray, u: np.ndarray, v: np.ndarray, a: np.ndarray | None, scaled_width: int, scaled_height: int,
+                    mode: int) -> np.ndarray:
+    """The decoder's rescaled RGB output over a whole picture (io_dec.c.go:361-515; the row
+    batches of EmitRescaledRGB feed the same streaming rescalers, so the result is the same):
+    InitRGBRescaler's three rescalers (Y to the output size, U and V from half size straight
+    to the output size, :476-478), WebPYUV444Converters[mode] per exported row (ExportRGB
+    :361-381), then EmitRescaledAlphaRGB / ExportAlpha (:405-430): the rescaled alpha through
+    WebPDispatchAlpha and, for premultiplied modes, WebPApplyAlphaMultiply.  Returns
+    uint8 [scaled_height, scaled_width * bpp]."""
+    from . import dsp
+    ys = RescalePlane(y, scaled_width, scaled_height)
+    us, vs = RescalePlanesBatch([u, v], [(scaled_width, scaled_height)] * 2)
+    out = dsp.WebPYUV444ToRGB(ys, us, vs, mode)
+    if a is not None and mode in _ALPHA_BYTE:
+        alpha_first = int(_ALPHA_BYTE[mode] == 0)
+        a_s = RescalePlane(a, scaled_width, scaled_height)
+        out = dsp.WebPDispatchAlpha(a_s, scaled_width, scaled_height, out, 4 * scaled_width, alpha_first)
+        if mode in _PREMULTIPLIED:
+            out = dsp.WebPApplyAlphaMultiply(out, alpha_first, scaled_width, scaled_height, 4 * scaled_width)
+    return out
+
+
+def EmitRescaledYUV(y: np.ndarray, u: np.ndarray, v: np.ndarray, a: np.ndarray | None, scaled_width: int, scaled_height: int):
+    """EmitRescaledYUV + EmitRescaledAlphaYUV over a whole picture (io_dec.c.go:244-281) for a
+    MODE_YUVA output: luma premultiplied by the source alpha before its rescale, divided by
+    the rescaled alpha after; an absent alpha plane is delivered opaque (:272-276).
+    Returns (y, u, v, a)."""
+    from . import dsp
+    h, w = y.shape
+    halve = lambda x: (x + 1) >> 1  # noqa: E731
+    if a is not None:
+        y = dsp.WebPMultRows(y, a, w, h, 0)
+        ys, a_s = RescalePlanesBatch([y, a], [(scaled_width, scaled_height)] * 2)
+        ys = dsp.WebPMultRows(ys, a_s, scaled_width, scaled_height, 1)
+    else:
+        ys = RescalePlane(y, scaled_width, scaled_height)
+        a_s = np.full((scaled_height, scaled_width), 255, np.uint8)
+    us, vs = RescalePlanesBatch([u, v], [(halve(scaled_width), halve(scaled_height))] * 2)
+    return ys, us, vs, a_s

@@ -218,7 +218,7 @@ int b2_vp8l_predictor_forward(b2_ctx* ctx, int stream, const b2_argb_job* jobs, 
  * One job layout for the three entry points (DEVICE pointers, signed strides). */
 typedef struct b2_convert_job {
   const void* src;     /* uint32 0xAARRGGBB pixels (convert) or the Y plane (point samplers); unused by alpha multiply */
-  const uint8_t* u;    /* U plane (samplers) or the alpha plane (B2_ALPHA_MULT_ROW) */
+  const uint8_t* u;    /* U plane (samplers) or the alpha plane (B2_ALPHA_MULT_ROW, B2_ALPHA_DISPATCH) */
   const uint8_t* v;    /* V plane (samplers) */
   uint8_t* dst;        /* output bytes; the in-place buffer for alpha multiply */
   int32_t src_stride;  /* pixels for uint32 sources, bytes for planes */
@@ -241,8 +241,12 @@ int b2_vp8l_convert_from_bgra(b2_ctx* ctx, int stream, const b2_convert_job* job
  *   B2_ALPHA_APPLY       ApplyAlphaMultiply_C :110-126, 4 bytes/pixel, flag = alpha_first
  *   B2_ALPHA_APPLY_4444  ApplyAlphaMultiply4444_C :141-163, 2 bytes/pixel, flag = rg_byte_pos
  *   B2_ALPHA_MULT_ARGB   WebPMultARGBRow_C / WebPMultARGBRows :33-52,73-79, uint32 pixels, flag = inverse
- *   B2_ALPHA_MULT_ROW    WebPMultRow_C / WebPMultRows :54-67,81-89, plane dst with alpha plane u, flag = inverse */
-enum { B2_ALPHA_APPLY = 0, B2_ALPHA_APPLY_4444 = 1, B2_ALPHA_MULT_ARGB = 2, B2_ALPHA_MULT_ROW = 3 };
+ *   B2_ALPHA_MULT_ROW    WebPMultRow_C / WebPMultRows :54-67,81-89, plane dst with alpha plane u, flag = inverse
+ *   B2_ALPHA_DISPATCH    WebPDispatchAlpha = DispatchAlpha_C :165-180 as ExportAlpha uses it
+ *                        (pkg/libwebp/decoder/io_dec.c.go:405-430): alpha plane u into the alpha byte of 4-byte
+ *                        pixels, flag = alpha_first.  Its "non opaque" return value only gates the premultiply
+ *                        that follows, which leaves opaque pixels alone: not reported */
+enum { B2_ALPHA_APPLY = 0, B2_ALPHA_APPLY_4444 = 1, B2_ALPHA_MULT_ARGB = 2, B2_ALPHA_MULT_ROW = 3, B2_ALPHA_DISPATCH = 4 };
 int b2_alpha_multiply(b2_ctx* ctx, int stream, const b2_convert_job* jobs, int n_jobs, int kind, int flag);
 
 /* Point-sampled YUV420 -> RGB: WebPSamplers[mode] driven by WebPSamplerProcessPlane

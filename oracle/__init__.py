@@ -462,6 +462,24 @@ def picture_rescale_argb(argb, width, height):
     return mult_argb_rows(np.ascontiguousarray(out).view(np.uint32).reshape(height, width), 1)
 
 
+def emit_rescaled_rgb(y, u, v, a, width, height, mode):
+    """The decoder's rescaled RGB output over a whole picture (io_dec.c.go:361-515): Y to the
+    output size, U / V from half size to the output size (InitRGBRescaler :476-478),
+    WebPYUV444Converters per row (ExportRGB :361-381), the rescaled alpha dispatched into the
+    alpha byte and WebPApplyAlphaMultiply for premultiplied modes (ExportAlpha :405-430).
+    a = None or a mode without alpha: the converter's 0xff stays."""
+    ys, us, vs = rescale_plane(y, width, height), rescale_plane(u, width, height), rescale_plane(v, width, height)
+    out = yuv444_to_rgb(ys, us, vs, mode)
+    alpha_modes = {1: 3, 3: 3, 4: 0, 7: 3, 8: 3, 9: 0}     # mode -> alpha byte (RGBA BGRA ARGB rgbA bgrA Argb)
+    if a is not None and mode in alpha_modes:
+        a_s = rescale_plane(a, width, height)
+        out = out.copy()
+        out[:, alpha_modes[mode]::4] = a_s
+        if mode in (7, 8, 9) and (a_s != 255).any():
+            out = apply_alpha_multiply(out, int(alpha_modes[mode] == 0))
+    return out
+
+
 def dequantize_levels(plane, strength, ordered_dither=False):
     """WebPDequantizeLevels on an alpha plane -> new plane.  ordered_dither: the Go file's
     DFIX = 4 branch; False is the stock libwebp build (DFIX = 0)."""

@@ -241,7 +241,8 @@ def test_mixed_pipeline_device_resident(env):
 @pytest.mark.parametrize("size", [(16383, 9), (10, 16383)])
 def test_maximum_dimension_next_rows(env, size):
     """WEBP_MAX_DIMENSION in either direction through the 8f-3 / 8f-4 entry points: dithered
-    import, picture cleanup / blend, use_argb import, animation blend, alpha filters."""
+    import, picture cleanup / blend, use_argb import, animation blend, alpha filters, alpha
+    level smoothing."""
     from go_webp_b200 import anim, filters as F, picture as P, picture_tools as T
     w, h = size
     rng = np.random.default_rng(w + h)
@@ -279,3 +280,7 @@ def test_maximum_dimension_next_rows(env, size):
         assert (o == oracle.alpha_unfilter(al, f)).all(), f
     for f, o in enumerate(F.AlphaFilterBatch(un, [0, 1, 2, 3])):
         assert (o == al).all(), f
+    q = ((al // 24) * 24).astype(np.uint8)                  # quantised levels, many tiles / bands
+    assert (F.DequantizeLevelsBatch([q], [100], ordered_dither=False)[0] == oracle.dequantize_levels(q, 100, False)).all()
+    d = F.DequantizeLevelsBatch([q, al], [55, 100], ordered_dither=True)
+    assert (d[0] == oracle.dequantize_levels(q, 55, True)).all() and (d[1] == oracle.dequantize_levels(al, 100, True)).all()

@@ -925,6 +925,30 @@ def test_alpha_filters(gpu, golden_dir):
     assert (out.reshape(7, 40)[:, :33] == oracle.alpha_filter(data.reshape(7, 40)[:, :33], 3)).all()
 
 
+def test_rescaled_decoder_output(gpu, golden_dir):
+    """EmitRescaledRGB / EmitRescaledYUV (io_dec.c.go:232-515) on the planes the libwebp decoder
+    emitted, vs what the same decoder returned with options.use_scaling: eight RGB-family
+    modes (alpha dispatched, premultiplied variants) and MODE_YUVA; plus WebPDispatchAlpha on
+    a seeded buffer with the alpha byte first and last."""
+    from go_webp_b200 import _abi, dsp as D, rescaler as R
+    g = np.load(os.path.join(golden_dir, "rescaled_decode_libwebp160.npz"))
+    for k in [str(k) for k in g["names"]]:
+        y, u, v, a = (g[f"{k}/{nm}"] for nm in "yuva")
+        dw, dh = (int(t) for t in g[f"{k}/size"])
+        for mode in (_abi.MODE_RGB, _abi.MODE_RGBA, _abi.MODE_BGR, _abi.MODE_BGRA, _abi.MODE_ARGB, _abi.MODE_rgbA, _abi.MODE_bgrA, _abi.MODE_Argb):
+            got = R.EmitRescaledRGB(y, u, v, a, dw, dh, mode)
+            assert (got == g[f"{k}/rgb{mode}"]).all(), (k, mode)
+        for got, nm in zip(R.EmitRescaledYUV(y, u, v, a, dw, dh), "yuva"):
+            assert (got == g[f"{k}/out_{nm}"]).all(), (k, nm)
+    rng = np.random.default_rng(77)
+    buf = rng.integers(0, 256, (37, 4 * 131 + 8), dtype=np.uint8)
+    al = rng.integers(0, 256, (37, 131), dtype=np.uint8)
+    for first in (0, 1):
+        exp = buf.copy()
+        exp[:, (0 if first else 3):4 * 131:4] = al
+        assert (D.WebPDispatchAlpha(al, 131, 37, buf, 4 * 131 + 8, first) == exp).all()
+
+
 def test_alpha_level_smoothing(gpu, golden_dir):
     """WebPDequantizeLevels: the libwebp decoder vectors in one batch (stock
     build, no dither), the same planes with the Go file's ordered dither vs the oracle, then

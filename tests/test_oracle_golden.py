@@ -317,6 +317,19 @@ def test_picture_rescale_with_alpha_matches_libwebp_binary(golden_dir):
     assert len(g["names"]) >= 20
 
 
+def test_rescaled_decoder_output_matches_libwebp_decoder(golden_dir):
+    """EmitRescaledRGB / EmitRescaledYUV as whole-picture compositions (io_dec.c.go:232-515)
+    vs WebPDecode with options.use_scaling, on the planes the same decoder emitted."""
+    g = _load(golden_dir, "rescaled_decode_libwebp160.npz")
+    for k in g["names"]:
+        y, u, v, a = (g[f"{k}/{nm}"] for nm in "yuva")
+        dw, dh = (int(t) for t in g[f"{k}/size"])
+        for mode in (0, 1, 2, 3, 4, 7, 8, 9):
+            assert (oracle.emit_rescaled_rgb(y, u, v, a, dw, dh, mode) == g[f"{k}/rgb{mode}"]).all(), (k, mode)
+        for got, nm in zip(oracle.picture_rescale_yuva(y, u, v, a, dw, dh), "yuva"):
+            assert (got == g[f"{k}/out_{nm}"]).all(), (k, nm)
+
+
 def test_level_smoothing_matches_libwebp_decoder(golden_dir):
     """WebPDequantizeLevels (quant_levels_dec_utils.c.go:259-286) vs WebPDecode with
     alpha_dithering_strength on files the binary wrote with quantised alpha levels (the stock

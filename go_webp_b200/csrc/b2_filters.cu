@@ -37,7 +37,23 @@ __device__ __forceinline__ int gradient_pred(int a, int b, int c) {   // Gradien
   return min(max(g, 0), 255);
 }
 
-// ---- forward: unit = (row, 128-pixel segment), 4 pixels per lane --------------------
+// ---- forward: unit = (row, 512-pixel segment), 16 pixels per lane ------------------
+constexpr int kFwdLane = 16, kFwdUnit = 32 * kFwdLane;
+
+// predictions for the 4 pixels of word c: left = the byte before them, t = the word above,
+// up_left = the byte before that one
+__device__ __forceinline__ uint32_t filter_pred4(int filter, bool top_row, uint32_t c, uint32_t left, uint32_t t, uint32_t up_left) {
+  if (filter == 0) return 0u;
+  if (top_row || filter == 1) return (c << 8) | left;      // top row and horizontal: from the left
+  if (filter == 2) return t;
+  const uint32_t l4 = (c << 8) | left, tl4 = (t << 8) | up_left;
+  uint32_t pred = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    pred |= (uint32_t)gradient_pred((int)((l4 >> (8 * k)) & 0xff), (int)((t >> (8 * k)) & 0xff), (int)((tl4 >> (8 * k)) & 0xff)) << (8 * k);
+  return pred;
+}
+
 __global__ void __launch_bounds__(kThreads, 8)
 alpha_filter_kernel(const FiltJobDev* __restrict__ jobs, const uint32_t* __restrict__ prefix, uint32_t n_jobs,
                     uint32_t uniform, uint32_t total) {
@@ -46,11 +62,45 @@ alpha_filter_kernel(const FiltJobDev* __restrict__ jobs, const uint32_t* __restr
     uint32_t local;
     const uint32_t img = b2_find_image(prefix, n_jobs, uniform, unit, &local);
     const FiltJobDev j = jobs[img];
-    const int y = (int)(local / j.units_x), x0 = (int)(local % j.units_x) * 128 + lane * 4;
+    const uint32_t fwd_units = (uint32_t)((j.width + kFwdUnit - 1) / kFwdUnit);
+    const int y = (int)(local / fwd_units), x0 = (int)(local % fwd_units) * kFwdUnit + lane * kFwdLane;
     const uint8_t* cur = j.src + (ptrdiff_t)y * j.src_stride;
     const uint8_t* up = cur - j.src_stride;
     uint8_t* dst = j.dst + (ptrdiff_t)y * j.dst_stride;
-    for (int x = x0; x < min(x0 + 4, j.width); ++x) {
+    // whole words when the rows are 4-byte aligned: the left / upper-left neighbours of a
+    // lane's first pixel are the last bytes of the previous lane's words (one shuffle each)
+    const bool aligned = (((((uintptr_t)j.src) | (uintptr_t)j.dst) | (uint32_t)j.src_stride | (uint32_t)j.dst_stride) & 3) == 0;
+    const bool vec = aligned && x0 + kFwdLane <= j.width;
+    const bool use_up = y > 0 && j.filter >= 2;
+    uint32_t c[4] = {0, 0, 0, 0}, t[4] = {0, 0, 0, 0};
+    if (vec) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) c[q] = __ldg((const uint32_t*)(cur + x0) + q);
+      if (use_up) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) t[q] = __ldg((const uint32_t*)(up + x0) + q);
+      }
+    }
+    uint32_t left = __shfl_up_sync(0xffffffffu, c[3] >> 24, 1), up_left = __shfl_up_sync(0xffffffffu, t[3] >> 24, 1);
+    if (vec) {
+      if (lane == 0) {
+        left = x0 > 0 ? cur[x0 - 1] : 0u;
+        up_left = (x0 > 0 && use_up) ? up[x0 - 1] : 0u;
+      }
+      uint32_t o[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint32_t pred = filter_pred4(j.filter, y == 0, c[q], left, t[q], up_left);
+        if (q == 0 && x0 == 0 && j.filter != 0) pred = (pred & 0xffffff00u) | (y == 0 ? 0u : (uint32_t)up[0]);   // leftmost pixel: as is / from above
+        o[q] = __vsub4(c[q], pred);
+        left = c[q] >> 24;
+        up_left = t[q] >> 24;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) *((uint32_t*)(dst + x0) + q) = o[q];
+      continue;
+    }
+    for (int x = x0; x < min(x0 + kFwdLane, j.width); ++x) {
       int pred;
       if (j.filter == 0) pred = 0;
       else if (x == 0) pred = (y == 0) ? 0 : up[0];                        // leftmost pixel: as is / from above
@@ -309,7 +359,7 @@ int prepare_filt(b2_ctx* ctx, int stream, const b2_alpha_filter_job* jobs, int n
     if (counts) counts[j.filter]++;
     uint32_t items = 0;
     switch (kind) {
-      case KIND_FORWARD: items = d[i].units_x * (uint32_t)j.height; break;
+      case KIND_FORWARD: items = (uint32_t)((j.width + kFwdUnit - 1) / kFwdUnit) * (uint32_t)j.height; break;
       case KIND_ROWS: items = (uint32_t)j.height; break;
       default: items = d[i].units_x; break;
     }

@@ -1,1 +1,2 @@
-timeout 600 python -m pytest tests -m gpu -x -q -k "rescaled_decoder or output_conversions or alpha_mult or convert" 2>&1 | tail -8
+timeout 300 python -m pytest tests -m gpu -x -q -k "alpha_filters or maximum_dimension" 2>&1 | tail -3
+timeout 300 python tools/quick_bench.py filters 2>&1 | tail -6

@@ -93,6 +93,58 @@ __device__ __forceinline__ uint32_t pack_px(int st, bool premult, uint32_t a, ui
   if (st == ST_BGRA) return b | (g << 8) | (r << 16) | (a << 24);
   return a | (r << 8) | (g << 16) | (b << 24);  // ST_ARGB
 }
+// Four consecutive pixels into 'st' byte order at d: whole words when d allows it (16, 12 or 8
+// bytes per lane: one 128-bit, three 32-bit or one 64-bit store), else byte by byte.
+__device__ __forceinline__ void store_px4(int st, bool premult, bool upstream16, const uint32_t* a, const uint32_t* r,
+                                          const uint32_t* g, const uint32_t* b, uint8_t* d) {
+  if ((((uintptr_t)d) & 3) != 0) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) store_px(st, premult, upstream16, a[k], r[k], g[k], b[k], d + k * bpp_of(st));
+    return;
+  }
+  if (st == ST_4444 || st == ST_565) {
+    uint32_t v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      uint32_t hi, lo;   // hi = the RG byte, lo = the BA / GB byte
+      if (st == ST_4444) {
+        hi = (r[k] & 0xf0) | (g[k] >> 4); lo = (b[k] & 0xf0) | (a[k] >> 4);
+        if (premult) premul4444(&hi, &lo);
+      } else {
+        hi = (r[k] & 0xf8) | (g[k] >> 5); lo = ((g[k] << 3) & 0xe0) | (b[k] >> 3);
+      }
+      v[k] = upstream16 ? ((hi & 0xff) | ((lo & 0xff) << 8)) : ((lo & 0xff) | ((hi & 0xff) << 8));
+    }
+    uint32_t* o = (uint32_t*)d;
+    o[0] = v[0] | (v[1] << 16);
+    o[1] = v[2] | (v[3] << 16);
+    return;
+  }
+  if (st == ST_RGB || st == ST_BGR) {
+    uint32_t c0[4], c2[4];   // first and third byte of a pixel
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      c0[k] = (st == ST_RGB) ? r[k] : b[k];
+      c2[k] = (st == ST_RGB) ? b[k] : r[k];
+    }
+    uint32_t* o = (uint32_t*)d;
+    o[0] = c0[0] | (g[0] << 8) | (c2[0] << 16) | (c0[1] << 24);
+    o[1] = g[1] | (c2[1] << 8) | (c0[2] << 16) | (g[2] << 24);
+    o[2] = c2[2] | (c0[3] << 8) | (g[3] << 16) | (c2[3] << 24);
+    return;
+  }
+  uint4 q;
+  q.x = pack_px(st, premult, a[0], r[0], g[0], b[0]);
+  q.y = pack_px(st, premult, a[1], r[1], g[1], b[1]);
+  q.z = pack_px(st, premult, a[2], r[2], g[2], b[2]);
+  q.w = pack_px(st, premult, a[3], r[3], g[3], b[3]);
+  if ((((uintptr_t)d) & 15) == 0) {
+    b2_stg_stream_v4(d, q);
+  } else {
+    uint32_t* o = (uint32_t*)d;
+    o[0] = q.x; o[1] = q.y; o[2] = q.z; o[3] = q.w;
+  }
+}
 
 // Common item walk: a warp takes 128 pixels of one row, a lane 4 of them.
 #define B2_CONV_ITEM_PROLOGUE                                                                        \
@@ -130,6 +182,11 @@ convert_from_bgra_kernel(const ConvJobDev* __restrict__ jobs, const uint32_t* __
       o.z = pack_px(st, premult, p[2] >> 24, (p[2] >> 16) & 0xff, (p[2] >> 8) & 0xff, p[2] & 0xff);
       o.w = pack_px(st, premult, p[3] >> 24, (p[3] >> 16) & 0xff, (p[3] >> 8) & 0xff, p[3] & 0xff);
       b2_stg_stream_v4(d, o);
+    } else if (nv == 4) {
+      uint32_t a4[4], r4[4], g4[4], b4[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { a4[k] = p[k] >> 24; r4[k] = (p[k] >> 16) & 0xff; g4[k] = (p[k] >> 8) & 0xff; b4[k] = p[k] & 0xff; }
+      store_px4(st, premult, upstream16, a4, r4, g4, b4, d);
     } else {
 #pragma unroll
       for (int k = 0; k < 4; ++k)
@@ -195,6 +252,21 @@ alpha_multiply_kernel(const ConvJobDev* __restrict__ jobs, const uint32_t* __res
   B2_CONV_ITEM_PROLOGUE
     if (kind == AM_APPLY) {  // ApplyAlphaMultiply_C: 4 bytes per pixel, flag = alpha_first
       uint8_t* d = j.dst + (ptrdiff_t)y * j.dst_stride + x0 * 4;
+      if (nv == 4 && (((uintptr_t)d) & 15) == 0) {   // a pixel per word
+        uint4 q = *(const uint4*)d;
+        uint32_t px[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t a = flag ? (px[k] & 0xff) : (px[k] >> 24);
+          if (a != 0xff) {
+            const int sh = flag ? 8 : 0;
+            const uint32_t c0 = premul((px[k] >> sh) & 0xff, a), c1 = premul((px[k] >> (sh + 8)) & 0xff, a), c2 = premul((px[k] >> (sh + 16)) & 0xff, a);
+            px[k] = flag ? (a | (c0 << 8) | (c1 << 16) | (c2 << 24)) : (c0 | (c1 << 8) | (c2 << 16) | (a << 24));
+          }
+        }
+        *(uint4*)d = make_uint4(px[0], px[1], px[2], px[3]);
+        continue;
+      }
       for (int k = 0; k < nv; ++k) {
         uint8_t* px = d + 4 * k;
         const uint32_t a = px[flag ? 0 : 3];
@@ -227,10 +299,38 @@ alpha_multiply_kernel(const ConvJobDev* __restrict__ jobs, const uint32_t* __res
     } else if (kind == AM_DISPATCH) {  // DispatchAlpha_C (alpha_processing.go:165-180): alpha plane u -> alpha byte, flag = alpha_first
       uint8_t* d = j.dst + (ptrdiff_t)y * j.dst_stride + x0 * 4 + (flag ? 0 : 3);
       const uint8_t* al = j.u + (ptrdiff_t)y * j.uv_stride + x0;
+      uint8_t* dw = j.dst + (ptrdiff_t)y * j.dst_stride + x0 * 4;
+      if (nv == 4 && (((uintptr_t)dw) & 15) == 0 && (((uintptr_t)al) & 3) == 0) {   // the lane owns these 4 pixels: whole words
+        const uint32_t aw = __ldg((const uint32_t*)al);
+        uint4 q = *(const uint4*)dw;
+        uint32_t px[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t a = (aw >> (8 * k)) & 0xff;
+          px[k] = flag ? ((px[k] & 0xffffff00u) | a) : ((px[k] & 0x00ffffffu) | (a << 24));
+        }
+        *(uint4*)dw = make_uint4(px[0], px[1], px[2], px[3]);
+        continue;
+      }
       for (int k = 0; k < nv; ++k) d[4 * k] = al[k];
     } else {  // WebPMultRow_C: plane dst, alpha plane u, flag = inverse
       uint8_t* d = j.dst + (ptrdiff_t)y * j.dst_stride + x0;
       const uint8_t* al = j.u + (ptrdiff_t)y * j.uv_stride + x0;
+      if (nv == 4 && (((uintptr_t)d | (uintptr_t)al) & 3) == 0) {
+        const uint32_t aw = __ldg((const uint32_t*)al);
+        if (aw != 0xffffffffu) {
+          const uint32_t dw = *(const uint32_t*)d;
+          uint32_t o = 0;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t a = (aw >> (8 * k)) & 0xff, v = (dw >> (8 * k)) & 0xff;
+            const uint32_t r = (a == 255) ? v : (a == 0) ? 0u : (mult_fix(v, mult_scale(a, flag != 0)) & 0xff);
+            o |= r << (8 * k);
+          }
+          *(uint32_t*)d = o;
+        }
+        continue;
+      }
       for (int k = 0; k < nv; ++k) {
         const uint32_t a = al[k];
         if (a != 255) d[k] = (a == 0) ? 0 : (uint8_t)mult_fix(d[k], mult_scale(a, flag != 0));
@@ -260,6 +360,32 @@ yuv_point_kernel(const ConvJobDev* __restrict__ jobs, const uint32_t* __restrict
     const uint8_t* vr = j.v + crow;
     const int bpp = bpp_of(st);
     uint8_t* d = j.dst + (ptrdiff_t)y * j.dst_stride + x0 * bpp;
+    if (nv == 4) {   // whole words in (x0 is a multiple of 4: its chroma pair starts at x0 / 2), whole words out
+      const uint32_t yw = ((((uintptr_t)yr) & 3) == 0) ? __ldg((const uint32_t*)yr)
+                                                       : (uint32_t)yr[0] | ((uint32_t)yr[1] << 8) | ((uint32_t)yr[2] << 16) | ((uint32_t)yr[3] << 24);
+      uint32_t uw, vw;   // the 4 chroma samples of the 4 pixels, one per byte
+      if (YUV444) {
+        const uint8_t* up = ur + x0;
+        const uint8_t* vp = vr + x0;
+        uw = ((((uintptr_t)up) & 3) == 0) ? __ldg((const uint32_t*)up) : (uint32_t)up[0] | ((uint32_t)up[1] << 8) | ((uint32_t)up[2] << 16) | ((uint32_t)up[3] << 24);
+        vw = ((((uintptr_t)vp) & 3) == 0) ? __ldg((const uint32_t*)vp) : (uint32_t)vp[0] | ((uint32_t)vp[1] << 8) | ((uint32_t)vp[2] << 16) | ((uint32_t)vp[3] << 24);
+      } else {
+        const uint8_t* up = ur + (x0 >> 1);
+        const uint8_t* vp = vr + (x0 >> 1);
+        const uint32_t u2 = ((((uintptr_t)up) & 1) == 0) ? (uint32_t)__ldg((const uint16_t*)up) : (uint32_t)up[0] | ((uint32_t)up[1] << 8);
+        const uint32_t v2 = ((((uintptr_t)vp) & 1) == 0) ? (uint32_t)__ldg((const uint16_t*)vp) : (uint32_t)vp[0] | ((uint32_t)vp[1] << 8);
+        uw = __byte_perm(u2, 0, 0x1100);   // row_func: two pixels share a sample (yuv.go:24-30)
+        vw = __byte_perm(v2, 0, 0x1100);
+      }
+      uint32_t a4[4], r4[4], g4[4], b4[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        a4[k] = 0xff;
+        yuv_rgb((yw >> (8 * k)) & 0xff, (uw >> (8 * k)) & 0xff, (vw >> (8 * k)) & 0xff, &r4[k], &g4[k], &b4[k]);
+      }
+      store_px4(st, false, true, a4, r4, g4, b4, d);
+      continue;
+    }
     for (int k = 0; k < nv; ++k) {
       const int cx = YUV444 ? (x0 + k) : ((x0 + k) >> 1);  // row_func: two pixels share a sample (yuv.go:24-30)
       uint32_t r, g, b;

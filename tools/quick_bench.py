@@ -158,3 +158,41 @@ if "dequant" in which:
                 report(f"level smoothing {n}x1080p {name} s={strength} dither={dither}", n * w * h, 3.0,
                        timed(lambda: ctx._chk(ctx.lib.b2_alpha_dequantize_levels(ctx.h, 0, jobs, n, dither)), 5))
     src.free(); dst.free()
+if "convert" in which:
+    # output conversions (8f-2) on NF 1080p pictures: ARGB words in, packed bytes out; alpha multiplies in place;
+    # point-sampled and 4:4:4 YUV -> RGBA; the use_argb import (RGBA bytes -> ARGB words); animation blend
+    n = NF
+    w, h = 1920, 1080
+    argb = ctx.alloc(n * 4 * w * h)
+    out = ctx.alloc(n * 4 * w * h)
+    yp = ctx.alloc(n * w * h)
+    up = ctx.alloc(n * w * h)
+    vp = ctx.alloc(n * w * h)
+    ctx.synth_fill(argb.ptr, w, h, 4 * w, 4 * w * h, n, 0xB200000A, 0, 0)
+    for pl, tag in ((yp, 1), (up, 2), (vp, 3)):
+        ctx.synth_fill(pl.ptr, w // 4, h, w, w * h, n, 0xB200000A + tag, 0, 4)
+    ctx.sync()
+    CJ = _abi.ConvertJob
+    for mode, name, bpp in ((_abi.MODE_RGBA, "RGBA", 4), (_abi.MODE_RGB, "RGB", 3), (_abi.MODE_RGB_565, "RGB565", 2), (_abi.MODE_rgbA, "rgbA (premultiplied)", 4)):
+        jobs = (CJ * n)(*[CJ(argb.ptr + i * 4 * w * h, None, None, out.ptr + i * 4 * w * h, w, 0, bpp * w, w, h, 0) for i in range(n)])
+        report(f"VP8LConvertFromBGRA -> {name} {n}x1080p", n * w * h, 4.0 + bpp,
+               timed(lambda: ctx._chk(ctx.lib.b2_vp8l_convert_from_bgra(ctx.h, 0, jobs, n, mode, 0)), 5))
+    jobs = (CJ * n)(*[CJ(None, None, None, argb.ptr + i * 4 * w * h, 0, 0, 4 * w, w, h, 0) for i in range(n)])
+    report(f"WebPApplyAlphaMultiply (in place) {n}x1080p", n * w * h, 8.0, timed(lambda: ctx._chk(ctx.lib.b2_alpha_multiply(ctx.h, 0, jobs, n, _abi.ALPHA_APPLY, 0)), 5))
+    report(f"WebPMultARGBRows (in place) {n}x1080p", n * w * h, 8.0, timed(lambda: ctx._chk(ctx.lib.b2_alpha_multiply(ctx.h, 0, jobs, n, _abi.ALPHA_MULT_ARGB, 0)), 5))
+    jobs = (CJ * n)(*[CJ(None, up.ptr + i * w * h, None, yp.ptr + i * w * h, 0, w, w, w, h, 0) for i in range(n)])
+    report(f"WebPMultRows (plane, in place) {n}x1080p", n * w * h, 3.0, timed(lambda: ctx._chk(ctx.lib.b2_alpha_multiply(ctx.h, 0, jobs, n, _abi.ALPHA_MULT_ROW, 0)), 5))
+    jobs = (CJ * n)(*[CJ(None, up.ptr + i * w * h, None, out.ptr + i * 4 * w * h, 0, w, 4 * w, w, h, 0) for i in range(n)])
+    report(f"WebPDispatchAlpha {n}x1080p", n * w * h, 2.0, timed(lambda: ctx._chk(ctx.lib.b2_alpha_multiply(ctx.h, 0, jobs, n, _abi.ALPHA_DISPATCH, 0)), 5))
+    jobs = (CJ * n)(*[CJ(yp.ptr + i * w * h, up.ptr + i * w * h, vp.ptr + i * w * h, out.ptr + i * 4 * w * h, w, w, 4 * w, w, h, 0) for i in range(n)])
+    report(f"YUV444 -> RGBA {n}x1080p", n * w * h, 7.0, timed(lambda: ctx._chk(ctx.lib.b2_yuv_to_rgb_point(ctx.h, 0, jobs, n, _abi.MODE_RGBA, 1)), 5))
+    jobs = (CJ * n)(*[CJ(yp.ptr + i * w * h, up.ptr + i * w * h, vp.ptr + i * w * h, out.ptr + i * 4 * w * h, w, w // 2, 4 * w, w, h, 0) for i in range(n)])
+    report(f"point-sampled YUV420 -> RGBA {n}x1080p", n * w * h, 5.5, timed(lambda: ctx._chk(ctx.lib.b2_yuv_to_rgb_point(ctx.h, 0, jobs, n, _abi.MODE_RGBA, 0)), 5))
+    jobs = (CJ * n)(*[CJ(argb.ptr + i * 4 * w * h, None, None, out.ptr + i * 4 * w * h, 4 * w, 0, 4 * w, w, h, 0) for i in range(n)])
+    report(f"import RGBA -> ARGB (use_argb) {n}x1080p", n * w * h, 8.0, timed(lambda: ctx._chk(ctx.lib.b2_import_to_argb(ctx.h, 0, jobs, n, _abi.ORDER_RGBA, 1)), 5))
+    AB = _abi.AnimBlendJob
+    jobs = (AB * n)(*[AB(argb.ptr + i * 4 * w * h, out.ptr + i * 4 * w * h, w, w, w, h) for i in range(n)])
+    for premult in (0, 1):
+        report(f"anim blend rows premult={premult} {n}x1080p", n * w * h, 12.0, timed(lambda: ctx._chk(ctx.lib.b2_anim_blend_rows(ctx.h, 0, jobs, n, premult)), 5))
+    for b in (argb, out, yp, up, vp):
+        b.free()

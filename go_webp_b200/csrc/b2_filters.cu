@@ -118,53 +118,85 @@ __device__ __forceinline__ uint32_t prefix4(uint32_t w) {
   return __vadd4(w, w << 16);
 }
 
-// ---- unfilter, NONE / HORIZONTAL: a warp per row ------------------------------------
+// ---- unfilter, NONE / HORIZONTAL: a warp per group of 8 rows -------------------------
+// A row is a bytewise running sum started from prev[0] = the sum of column 0 over the rows
+// above (each row's first output is the next row's start).  The warp sums column 0 down to
+// its first row once and carries it from row to row; along a row every lane takes 16 bytes
+// (prefix inside the lane with packed adds, one scan of the lane totals per 512 bytes).
+constexpr int kRowsPerWarp = 8;
 __global__ void __launch_bounds__(kThreads, 8)
 alpha_unfilter_rows_kernel(const FiltJobDev* __restrict__ jobs, const uint32_t* __restrict__ prefix, uint32_t n_jobs,
                            uint32_t uniform, uint32_t total) {
   const int lane = threadIdx.x & 31;
   for (uint32_t unit = blockIdx.x * kWarps + (threadIdx.x >> 5); unit < total; unit += gridDim.x * kWarps) {
-    uint32_t y;
-    const uint32_t img = b2_find_image(prefix, n_jobs, uniform, unit, &y);
+    uint32_t group;
+    const uint32_t img = b2_find_image(prefix, n_jobs, uniform, unit, &group);
     const FiltJobDev j = jobs[img];
     if (j.filter > 1) continue;                  // vertical / gradient rows are done by their own kernels
-    const uint8_t* in = j.src + (ptrdiff_t)y * j.src_stride;
-    uint8_t* out = j.dst + (ptrdiff_t)y * j.dst_stride;
-    uint32_t carry = 0;                          // value left of the current chunk (pred)
-    if (j.filter == 1 && y > 0) {                // prev[0] = sum of column 0 over the rows above
+    const int y0 = (int)group * kRowsPerWarp, y1 = min(y0 + kRowsPerWarp, j.height);
+    uint32_t col0 = 0;                           // sum of column 0 over the rows above y
+    if (j.filter == 1 && y0 > 0) {
       uint32_t s = 0;
-      for (uint32_t r = lane; r < y; r += 32) s += j.src[(ptrdiff_t)r * j.src_stride];
+      for (int r = lane; r < y0; r += 32) s += j.src[(ptrdiff_t)r * j.src_stride];
 #pragma unroll
       for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      carry = s & 0xffu;
+      col0 = s;
     }
-    const bool al4 = (((uintptr_t)j.src | (uintptr_t)j.dst | (uintptr_t)(uint32_t)j.src_stride | (uintptr_t)(uint32_t)j.dst_stride) & 3) == 0;
-    for (int x0 = 0; x0 < j.width; x0 += 128) {
-      const int x = x0 + lane * 4;
-      const bool vec = al4 && x + 4 <= j.width;
-      uint32_t w = 0;
-      if (vec) w = __ldg(reinterpret_cast<const uint32_t*>(in + x));
-      else {
+    const uintptr_t bits = (uintptr_t)j.src | (uintptr_t)j.dst | (uintptr_t)(uint32_t)j.src_stride | (uintptr_t)(uint32_t)j.dst_stride;
+    const bool al4 = (bits & 3) == 0, al16 = (bits & 15) == 0;
+    for (int y = y0; y < y1; ++y) {
+      const uint8_t* in = j.src + (ptrdiff_t)y * j.src_stride;
+      uint8_t* out = j.dst + (ptrdiff_t)y * j.dst_stride;
+      uint32_t carry = col0 & 0xffu;             // value left of the current chunk (pred)
+      col0 += in[0];
+      for (int x0 = 0; x0 < j.width; x0 += 512) {
+        const int x = x0 + lane * 16;
+        const bool vec16 = al16 && x + 16 <= j.width;
+        uint32_t w[4] = {0, 0, 0, 0};
+        if (vec16) {
+          const uint4 q = __ldg(reinterpret_cast<const uint4*>(in + x));
+          w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w;
+        } else {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) if (x + k < j.width) w |= (uint32_t)in[x + k] << (8 * k);
-      }
-      if (j.filter == 1) {
-        uint32_t p = prefix4(w);                 // within the lane
-        uint32_t tot = p >> 24;                  // lane total, then an exclusive scan over the lanes
-        uint32_t scan = tot;
+          for (int q = 0; q < 4; ++q) {
+            const int xq = x + 4 * q;
+            if (al4 && xq + 4 <= j.width) w[q] = __ldg(reinterpret_cast<const uint32_t*>(in + xq));
+            else {
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const uint32_t t = __shfl_up_sync(0xffffffffu, scan, o);
-          if (lane >= o) scan += t;
+              for (int k = 0; k < 4; ++k) if (xq + k < j.width) w[q] |= (uint32_t)in[xq + k] << (8 * k);
+            }
+          }
         }
-        const uint32_t before = (scan - tot + carry) & 0xffu;
-        w = __vadd4(p, before * 0x01010101u);
-        carry = (__shfl_sync(0xffffffffu, scan, 31) + carry) & 0xffu;
-      }
-      if (vec) *reinterpret_cast<uint32_t*>(out + x) = w;
-      else {
+        if (j.filter == 1) {
+          uint32_t p[4];
+          p[0] = prefix4(w[0]);                  // within the lane
 #pragma unroll
-        for (int k = 0; k < 4; ++k) if (x + k < j.width) out[x + k] = (uint8_t)(w >> (8 * k));
+          for (int q = 1; q < 4; ++q) p[q] = __vadd4(prefix4(w[q]), (p[q - 1] >> 24) * 0x01010101u);
+          const uint32_t tot = p[3] >> 24;       // lane total, then an exclusive scan over the lanes
+          uint32_t scan = tot;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, scan, o);
+            if (lane >= o) scan += t;
+          }
+          const uint32_t before = ((scan - tot + carry) & 0xffu) * 0x01010101u;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) w[q] = __vadd4(p[q], before);
+          carry = (__shfl_sync(0xffffffffu, scan, 31) + carry) & 0xffu;
+        }
+        if (vec16) {
+          *reinterpret_cast<uint4*>(out + x) = make_uint4(w[0], w[1], w[2], w[3]);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int xq = x + 4 * q;
+            if (al4 && xq + 4 <= j.width) *reinterpret_cast<uint32_t*>(out + xq) = w[q];
+            else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) if (xq + k < j.width) out[xq + k] = (uint8_t)(w[q] >> (8 * k));
+            }
+          }
+        }
       }
     }
   }
@@ -360,7 +392,7 @@ int prepare_filt(b2_ctx* ctx, int stream, const b2_alpha_filter_job* jobs, int n
     uint32_t items = 0;
     switch (kind) {
       case KIND_FORWARD: items = (uint32_t)((j.width + kFwdUnit - 1) / kFwdUnit) * (uint32_t)j.height; break;
-      case KIND_ROWS: items = (uint32_t)j.height; break;
+      case KIND_ROWS: items = (uint32_t)((j.height + kRowsPerWarp - 1) / kRowsPerWarp); break;
       default: items = d[i].units_x; break;
     }
     if (i == 0) uni = items; else if (items != uni) uni = 0;

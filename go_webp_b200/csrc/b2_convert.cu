@@ -284,6 +284,25 @@ alpha_multiply_kernel(const ConvJobDev* __restrict__ jobs, const uint32_t* __res
       }
     } else if (kind == AM_MULT_ARGB) {  // WebPMultARGBRow_C, flag = inverse
       uint32_t* d = (uint32_t*)(j.dst + (ptrdiff_t)y * j.dst_stride) + x0;
+      if (nv == 4 && (((uintptr_t)d) & 15) == 0) {   // one 128-bit access each way
+        const uint4 q = *(const uint4*)d;
+        uint32_t px[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t argb = px[k];
+          if (argb < 0xff000000u) {
+            if (argb <= 0x00ffffffu) {
+              px[k] = 0;
+            } else {
+              const uint32_t scale = mult_scale(argb >> 24, flag != 0);
+              px[k] = (argb & 0xff000000u) | mult_fix(argb & 0xff, scale) | (mult_fix((argb >> 8) & 0xff, scale) << 8) |
+                      (mult_fix((argb >> 16) & 0xff, scale) << 16);
+            }
+          }
+        }
+        *(uint4*)d = make_uint4(px[0], px[1], px[2], px[3]);
+        continue;
+      }
       for (int k = 0; k < nv; ++k) {
         const uint32_t argb = d[k];
         if (argb < 0xff000000u) {

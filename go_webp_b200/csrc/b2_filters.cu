@@ -203,7 +203,7 @@ alpha_unfilter_rows_kernel(const FiltJobDev* __restrict__ jobs, const uint32_t* 
 }
 
 // ---- unfilter, VERTICAL: unit = 128-column segment of an image -------------------------
-__global__ void __launch_bounds__(kThreads, 8)
+__global__ void __launch_bounds__(kThreads, 4)
 alpha_unfilter_vertical_kernel(const FiltJobDev* __restrict__ jobs, const uint32_t* __restrict__ prefix, uint32_t n_jobs,
                                uint32_t uniform, uint32_t total) {
   const int lane = threadIdx.x & 31;
@@ -233,16 +233,17 @@ alpha_unfilter_vertical_kernel(const FiltJobDev* __restrict__ jobs, const uint32
     const bool al4 = ((((uintptr_t)j.src | (uintptr_t)j.dst | (uintptr_t)(uint32_t)j.src_stride | (uintptr_t)(uint32_t)j.dst_stride) & 3) == 0) &&
                      x + 4 <= j.width;
     if (al4) {
-      // 8 rows of loads in flight per thread: the walk down a column is a chain of adds,
+      // 16 rows of loads in flight per thread: the walk down a column is a chain of adds,
       // the loads must not wait for one another
+      constexpr int kInFlight = 16;
       *reinterpret_cast<uint32_t*>(j.dst + x) = acc;
-      for (int y0 = 1; y0 < j.height; y0 += 8) {
-        uint32_t v[8];
+      for (int y0 = 1; y0 < j.height; y0 += kInFlight) {
+        uint32_t v[kInFlight];
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
+        for (int q = 0; q < kInFlight; ++q)
           v[q] = (y0 + q < j.height) ? __ldg(reinterpret_cast<const uint32_t*>(j.src + (ptrdiff_t)(y0 + q) * j.src_stride + x)) : 0u;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
+        for (int q = 0; q < kInFlight; ++q) {
           if (y0 + q < j.height) {
             acc = __vadd4(acc, v[q]);
             *reinterpret_cast<uint32_t*>(j.dst + (ptrdiff_t)(y0 + q) * j.dst_stride + x) = acc;

@@ -29,7 +29,7 @@ struct ConvJobDev {
   int32_t uv_stride;
   int32_t dst_stride;  // bytes
   int32_t width, height;
-  uint32_t chunks_x;   // 128-pixel chunks per row
+  uint32_t chunks_x;   // kItemPx-pixel chunks per row
 };
 
 enum {  // canonical store modes
@@ -146,7 +146,7 @@ __device__ __forceinline__ void store_px4(int st, bool premult, bool upstream16,
   }
 }
 
-// Common item walk: a warp takes 128 pixels of one row, a lane 4 of them.
+// Item walk of the ARGB converters: a warp takes 128 pixels of one row, a lane 4 of them.
 #define B2_CONV_ITEM_PROLOGUE                                                                        \
   const int lane = threadIdx.x & 31;                                                                 \
   const uint32_t warp = threadIdx.x >> 5;                                                            \
@@ -157,6 +157,22 @@ __device__ __forceinline__ void store_px4(int st, bool premult, bool upstream16,
     const uint32_t y = local / j.chunks_x;                                                           \
     const int x0 = (int)(local - y * j.chunks_x) * 128 + lane * 4;                                   \
     if (x0 >= j.width) continue;                                                                     \
+    const int nv = min(4, j.width - x0);
+
+// Item walk of the in-place multiplies and the YUV converters: a warp takes kItemPx pixels of one row, 128 at a time, a lane 4 of them
+// (the item's image lookup and job descriptor are paid once per kItemPx pixels).
+constexpr int kItemPx = 512;   // the in-place multiplies and the YUV converters; the ARGB converters keep 128 (registers)
+#define B2_CONV_ITEM_PROLOGUE_WIDE(ITEM_PX)                                                                        \
+  const int lane = threadIdx.x & 31;                                                                 \
+  const uint32_t warp = threadIdx.x >> 5;                                                            \
+  for (uint32_t item = blockIdx.x * kWarps + warp; item < total_items; item += gridDim.x * kWarps) { \
+    uint32_t local;                                                                                  \
+    const uint32_t img = b2_find_image(prefix, n_jobs, uniform, item, &local);                       \
+    const ConvJobDev j = jobs[img];                                                                  \
+    const uint32_t y = local / j.chunks_x;                                                           \
+    const int xc = (int)(local - y * j.chunks_x) * (ITEM_PX);                                        \
+    const int xe = min(xc + (ITEM_PX), j.width);                                                     \
+    for (int x0 = xc + lane * 4; x0 < xe; x0 += 128) {                                               \
     const int nv = min(4, j.width - x0);
 
 // ---- VP8LConvertFromBGRA ----------------------------------------------------------
@@ -249,7 +265,7 @@ __device__ __forceinline__ uint32_t mult_fix(uint32_t x, uint32_t scale) { retur
 __global__ void __launch_bounds__(kThreads, 8)
 alpha_multiply_kernel(const ConvJobDev* __restrict__ jobs, const uint32_t* __restrict__ prefix, uint32_t n_jobs,
                       uint32_t uniform, uint32_t total_items, int kind, int flag) {
-  B2_CONV_ITEM_PROLOGUE
+  B2_CONV_ITEM_PROLOGUE_WIDE(kItemPx)
     if (kind == AM_APPLY) {  // ApplyAlphaMultiply_C: 4 bytes per pixel, flag = alpha_first
       uint8_t* d = j.dst + (ptrdiff_t)y * j.dst_stride + x0 * 4;
       if (nv == 4 && (((uintptr_t)d) & 15) == 0) {   // a pixel per word
@@ -355,6 +371,7 @@ alpha_multiply_kernel(const ConvJobDev* __restrict__ jobs, const uint32_t* __res
         if (a != 255) d[k] = (a == 0) ? 0 : (uint8_t)mult_fix(d[k], mult_scale(a, flag != 0));
       }
     }
+    }
   }
 }
 
@@ -368,10 +385,10 @@ __device__ __forceinline__ void yuv_rgb(uint32_t y, uint32_t u, uint32_t v, uint
   *r = (uint32_t)min(max(r6, 0), 255); *g = (uint32_t)min(max(g6, 0), 255); *b = (uint32_t)min(max(b6, 0), 255);
 }
 template <bool YUV444>
-__global__ void __launch_bounds__(kThreads, 8)
+__global__ void __launch_bounds__(kThreads, 4)
 yuv_point_kernel(const ConvJobDev* __restrict__ jobs, const uint32_t* __restrict__ prefix, uint32_t n_jobs,
                  uint32_t uniform, uint32_t total_items, int st) {
-  B2_CONV_ITEM_PROLOGUE
+  B2_CONV_ITEM_PROLOGUE_WIDE(kItemPx)
     const uint8_t* yr = (const uint8_t*)j.src + (ptrdiff_t)y * j.src_stride + x0;
     // WebPSamplerProcessPlane advances u/v after every odd row (yuv.go:52-55): chroma row y >> 1
     const ptrdiff_t crow = (ptrdiff_t)(YUV444 ? y : (y >> 1)) * j.uv_stride;
@@ -413,10 +430,11 @@ yuv_point_kernel(const ConvJobDev* __restrict__ jobs, const uint32_t* __restrict
       else if (st == ST_565) { d[2 * k] = (uint8_t)((r & 0xf8) | (g >> 5)); d[2 * k + 1] = (uint8_t)(((g << 3) & 0xe0) | (b >> 3)); }
       else store_px(st, false, true, 0xff, r, g, b, d + k * bpp);
     }
+    }
   }
 }
 
-int prepare_conv(b2_ctx* ctx, int stream, const b2_convert_job* jobs, int n_jobs, bool need_uv, int min_dst_bpp,
+int prepare_conv(b2_ctx* ctx, int stream, const b2_convert_job* jobs, int n_jobs, bool need_uv, int min_dst_bpp, int item_px,
                  const ConvJobDev** dj, const uint32_t** dp, uint32_t* uniform, uint32_t* total) {
   const size_t jb = (sizeof(ConvJobDev) * (size_t)n_jobs + 15) & ~(size_t)15;
   const size_t pb = sizeof(uint32_t) * ((size_t)n_jobs + 1);
@@ -437,7 +455,7 @@ int prepare_conv(b2_ctx* ctx, int stream, const b2_convert_job* jobs, int n_jobs
     d[i].src = j.src; d[i].u = j.u; d[i].v = j.v; d[i].dst = j.dst;
     d[i].src_stride = j.src_stride; d[i].uv_stride = j.uv_stride; d[i].dst_stride = j.dst_stride;
     d[i].width = j.width; d[i].height = j.height;
-    d[i].chunks_x = (uint32_t)((j.width + 127) / 128);
+    d[i].chunks_x = (uint32_t)((j.width + item_px - 1) / item_px);
     const uint32_t items = d[i].chunks_x * (uint32_t)j.height;
     if (i == 0) uni = items; else if (items != uni) uni = 0;
     pre[i] = (uint32_t)tot;
@@ -468,7 +486,7 @@ extern "C" int b2_vp8l_convert_from_bgra(b2_ctx* ctx, int stream, const b2_conve
   if (st < 0) return B2_ERR_INVALID_CONFIG;
   for (int i = 0; i < n_jobs; ++i) if (jobs[i].src == NULL) return B2_ERR_NULL;
   const ConvJobDev* dj; const uint32_t* dp; uint32_t uni, tot;
-  const int rc = prepare_conv(ctx, stream, jobs, n_jobs, false, bpp_of(st), &dj, &dp, &uni, &tot);
+  const int rc = prepare_conv(ctx, stream, jobs, n_jobs, false, bpp_of(st), 128, &dj, &dp, &uni, &tot);
   if (rc != B2_OK) return rc;
   convert_from_bgra_kernel<<<b2_grid_for(ctx, 8, (tot + kWarps - 1) / kWarps), kThreads, 0, ctx->streams[stream]>>>(
       dj, dp, (uint32_t)n_jobs, uni, tot, st, premult ? 1 : 0, (flags & B2_CONVERT_UPSTREAM_16BIT) ? 1 : 0);
@@ -482,7 +500,7 @@ extern "C" int b2_alpha_multiply(b2_ctx* ctx, int stream, const b2_convert_job* 
   if (kind < 0 || kind > 4) return B2_ERR_INVALID_CONFIG;
   const int bpp = (kind == B2_ALPHA_APPLY || kind == B2_ALPHA_MULT_ARGB || kind == B2_ALPHA_DISPATCH) ? 4 : (kind == B2_ALPHA_APPLY_4444 ? 2 : 1);
   const ConvJobDev* dj; const uint32_t* dp; uint32_t uni, tot;
-  const int rc = prepare_conv(ctx, stream, jobs, n_jobs, kind == B2_ALPHA_MULT_ROW || kind == B2_ALPHA_DISPATCH, bpp, &dj, &dp, &uni, &tot);
+  const int rc = prepare_conv(ctx, stream, jobs, n_jobs, kind == B2_ALPHA_MULT_ROW || kind == B2_ALPHA_DISPATCH, bpp, kItemPx, &dj, &dp, &uni, &tot);
   if (rc != B2_OK) return rc;
   alpha_multiply_kernel<<<b2_grid_for(ctx, 8, (tot + kWarps - 1) / kWarps), kThreads, 0, ctx->streams[stream]>>>(
       dj, dp, (uint32_t)n_jobs, uni, tot, kind, flag ? 1 : 0);
@@ -498,7 +516,7 @@ extern "C" int b2_yuv_to_rgb_point(b2_ctx* ctx, int stream, const b2_convert_job
   if (st < 0) return B2_ERR_INVALID_CONFIG;
   for (int i = 0; i < n_jobs; ++i) if (jobs[i].src == NULL || jobs[i].v == NULL) return B2_ERR_NULL;
   const ConvJobDev* dj; const uint32_t* dp; uint32_t uni, tot;
-  const int rc = prepare_conv(ctx, stream, jobs, n_jobs, true, bpp_of(st), &dj, &dp, &uni, &tot);
+  const int rc = prepare_conv(ctx, stream, jobs, n_jobs, true, bpp_of(st), kItemPx, &dj, &dp, &uni, &tot);
   if (rc != B2_OK) return rc;
   const int grid = b2_grid_for(ctx, 8, (tot + kWarps - 1) / kWarps);
   if (yuv444) yuv_point_kernel<true><<<grid, kThreads, 0, ctx->streams[stream]>>>(dj, dp, (uint32_t)n_jobs, uni, tot, st);
@@ -520,7 +538,7 @@ extern "C" int b2_import_to_argb(b2_ctx* ctx, int stream, const b2_convert_job* 
     if (jobs[i].width > 0 && st < (int64_t)step * jobs[i].width) return B2_ERR_BAD_DIM;
   }
   const ConvJobDev* dj; const uint32_t* dp; uint32_t uni, tot;
-  const int rc = prepare_conv(ctx, stream, jobs, n_jobs, false, 4, &dj, &dp, &uni, &tot);
+  const int rc = prepare_conv(ctx, stream, jobs, n_jobs, false, 4, 128, &dj, &dp, &uni, &tot);
   if (rc != B2_OK) return rc;
   import_argb_kernel<<<b2_grid_for(ctx, 8, (tot + kWarps - 1) / kWarps), kThreads, 0, ctx->streams[stream]>>>(
       dj, dp, (uint32_t)n_jobs, uni, tot, order, import_alpha ? 1 : 0);

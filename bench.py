@@ -340,6 +340,32 @@ def other_kernels(ctx, peak, steps):
         out[name] = {"frames": 64, "mpixel_per_s": px / ms / 1e3, "bytes_per_px": bpp,
                      "gbs": px * bpp / ms / 1e6, "frac": px * bpp / ms / 1e6 / peak}
         ap.close()
+    # the 8f-4 rows on 128 alpha / luma planes of 1080p (2 B/px; level smoothing 3: its level scan reads the plane too)
+    n, st = 128, W
+    src, dst = ctx.alloc(n * st * H), ctx.alloc(4 * n * st * H)
+    ctx.synth_fill(src.ptr, st // 4, H, st, st * H, n, SEED + 7, 0, 4)
+    ctx.sync()
+    k5 = max(3, min(steps, 5))
+
+    def row(name, px, bpp, fn, extra=None):
+        ms = timed(fn, k5)
+        out[name] = {"frames": n, "mpixel_per_s": px / ms / 1e3, "bytes_per_px": bpp, "gbs": px * bpp / ms / 1e6,
+                     "frac": px * bpp / ms / 1e6 / peak}
+        if extra:
+            out[name].update(extra)
+
+    for f, fname in ((1, "horizontal"), (2, "vertical"), (3, "gradient")):
+        fj = (_abi.AlphaFilterJob * n)(*[_abi.AlphaFilterJob(src.ptr + i * st * H, dst.ptr + i * st * H, st, st, W, H, f, 0) for i in range(n)])
+        row(f"alpha_unfilter_{fname}_1080p", n * W * H, 2.0, lambda: ctx._chk(ctx.lib.b2_alpha_unfilter(ctx.h, 0, fj, n)))
+        row(f"alpha_filter_{fname}_1080p", n * W * H, 2.0, lambda: ctx._chk(ctx.lib.b2_alpha_filter(ctx.h, 0, fj, n)))
+    dj = (_abi.AlphaDequantJob * n)(*[_abi.AlphaDequantJob(src.ptr + i * st * H, dst.ptr + i * st * H, st, st, W, H, 100, 0) for i in range(n)])
+    row("alpha_level_smoothing_1080p", n * W * H, 3.0, lambda: ctx._chk(ctx.lib.b2_alpha_dequantize_levels(ctx.h, 0, dj, n, 1)))
+    rj = (_abi.RescaleJob * n)(*[_abi.RescaleJob(src.ptr + i * st * H, dst.ptr + i * 4 * st * H, W, H, st, 2 * W, 2 * H, 2 * W, 1, 0) for i in range(n)])
+    row("rescale_1080p_to_4k_luma", n * W * H, 5.0, lambda: ctx._chk(ctx.lib.b2_rescale_planes(ctx.h, 0, rj, n)), {"note": "Mpx/s of input; 1 B in + 4 B out per input pixel"})
+    rj2 = (_abi.RescaleJob * n)(*[_abi.RescaleJob(src.ptr + i * st * H, dst.ptr + i * st * H, W, H, st, 1280, 720, 1280, 1, 0) for i in range(n)])
+    row("rescale_1080p_to_720p_luma", n * W * H, 1.0 + 1280 * 720 / (W * H), lambda: ctx._chk(ctx.lib.b2_rescale_planes(ctx.h, 0, rj2, n)), {"note": "Mpx/s of input"})
+    src.free()
+    dst.free()
     return out
 
 

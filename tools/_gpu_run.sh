@@ -1,2 +1,4 @@
-timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
-B2_FRAMES=64 timeout 300 python tools/quick_bench.py convert 2>&1 | tail -13
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 900 python bench.py > gpurun_out/r01h_bench.json 2> gpurun_out/r01h_bench.err; echo bench rc=$?
+tail -c 300 gpurun_out/r01h_bench.err
+B2_FRAMES=128 timeout 600 python tools/quick_bench.py dequant filters rescale convert > gpurun_out/r01h_quick_next_rows.txt 2>&1; echo quick rc=$?

@@ -1,4 +1,2 @@
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-timeout 900 python bench.py > gpurun_out/r01h_bench.json 2> gpurun_out/r01h_bench.err; echo bench rc=$?
-tail -c 300 gpurun_out/r01h_bench.err
-B2_FRAMES=128 timeout 600 python tools/quick_bench.py dequant filters rescale convert > gpurun_out/r01h_quick_next_rows.txt 2>&1; echo quick rc=$?
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/r01h_bench_n2.json 2> gpurun_out/r01h_bench_n2.err; echo rc=$?
+tail -c 400 gpurun_out/r01h_bench_n2.err

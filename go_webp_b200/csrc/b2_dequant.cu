@@ -195,7 +195,12 @@ dq_smooth_kernel(const DqJobDev* __restrict__ jobs, const DqStats* __restrict__ 
       // column pairs at even offsets from x0 - 4 (P) and at odd offsets (Q)
       const uint32_t P0 = __shfl_up_sync(0xffffffffu, cs01, 1), P1 = __shfl_up_sync(0xffffffffu, cs23, 1);
       const uint32_t P4 = __shfl_down_sync(0xffffffffu, cs01, 1), P5 = __shfl_down_sync(0xffffffffu, cs23, 1);
-      if (writer) {
+      // pixels at the lowest or the highest level are never touched (:143): a lane whose four
+      // pixels are all there (the flat opaque / transparent areas of a real alpha plane) is done
+      bool touched = false;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) touched |= (((pix >> (8 * q)) & 0xff) - keep_lo) < keep_span;
+      if (writer && touched) {
         const uint32_t P2 = cs01, P3 = cs23;
         const uint32_t Q0 = __byte_perm(P0, P1, 0x5432), Q1 = __byte_perm(P1, P2, 0x5432), Q2 = __byte_perm(P2, P3, 0x5432),
                        Q3 = __byte_perm(P3, P4, 0x5432), Q4 = __byte_perm(P4, P5, 0x5432);

@@ -145,12 +145,15 @@ if "dequant" in which:
     dst = ctx.alloc(n * st * h)
     yy, xx = np.mgrid[0:h, 0:w]
     smooth = ((128 + 100 * np.sin(xx / 90.0) * np.cos(yy / 70.0)).astype(np.int64) // 16 * 16).astype(np.uint8)
-    for name in ("random bytes", "smooth, 16 levels apart"):
+    edge = (np.clip((xx - 900) * 2 + 0 * yy, 0, 255) // 16 * 16).astype(np.uint8)   # opaque | 128-column ramp | transparent
+    edge[edge >= 240] = 255
+    for name in ("random bytes", "smooth, 16 levels apart", "flat with a soft edge"):
         if name == "random bytes":
             ctx.synth_fill(src.ptr, st // 4, h, st, st * h, n, 0xB2000009, 0, 4)
         else:
+            host = smooth if name.startswith("smooth") else edge
             for i in range(n):
-                ctx._chk(ctx.lib.b2_h2d_2d_async(ctx.h, 0, src.ptr + i * st * h, st, smooth.ctypes.data, w, w, h))
+                ctx._chk(ctx.lib.b2_h2d_2d_async(ctx.h, 0, src.ptr + i * st * h, st, host.ctypes.data, w, w, h))
         ctx.sync()
         for strength in (100, 50):
             jobs = (_abi.AlphaDequantJob * n)(*[_abi.AlphaDequantJob(src.ptr + i * st * h, dst.ptr + i * st * h, st, st, w, h, strength, 0) for i in range(n)])

@@ -413,11 +413,25 @@ yuv_point_kernel(const ConvJobDev* __restrict__ jobs, const uint32_t* __restrict
         uw = __byte_perm(u2, 0, 0x1100);   // row_func: two pixels share a sample (yuv.go:24-30)
         vw = __byte_perm(v2, 0, 0x1100);
       }
-      uint32_t a4[4], r4[4], g4[4], b4[4];
+      uint32_t a4[4] = {0xff, 0xff, 0xff, 0xff}, r4[4], g4[4], b4[4];
+      if (YUV444) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        a4[k] = 0xff;
-        yuv_rgb((yw >> (8 * k)) & 0xff, (uw >> (8 * k)) & 0xff, (vw >> (8 * k)) & 0xff, &r4[k], &g4[k], &b4[k]);
+        for (int k = 0; k < 4; ++k)
+          yuv_rgb((yw >> (8 * k)) & 0xff, (uw >> (8 * k)) & 0xff, (vw >> (8 * k)) & 0xff, &r4[k], &g4[k], &b4[k]);
+      } else {   // two pixels per chroma sample: its three terms once (the same integer sums as yuv_rgb)
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+          const uint32_t u = (uw >> (16 * p)) & 0xff, v = (vw >> (16 * p)) & 0xff;
+          const int cr = ((int)(v * 26149u) >> 8) - 14234, cg = 8708 - ((int)(u * 6419u) >> 8) - ((int)(v * 13320u) >> 8),
+                    cb = ((int)(u * 33050u) >> 8) - 17685;
+#pragma unroll
+          for (int k = 2 * p; k < 2 * p + 2; ++k) {
+            const int yy = (int)(((yw >> (8 * k)) & 0xff) * 19077u) >> 8;
+            r4[k] = (uint32_t)min(max((yy + cr) >> 6, 0), 255);
+            g4[k] = (uint32_t)min(max((yy + cg) >> 6, 0), 255);
+            b4[k] = (uint32_t)min(max((yy + cb) >> 6, 0), 255);
+          }
+        }
       }
       store_px4(st, false, true, a4, r4, g4, b4, d);
       continue;

@@ -1,2 +1,2 @@
-timeout 600 python -m pytest tests -m gpu -x -q -k "level_smoothing or maximum_dimension" 2>&1 | tail -2
-timeout 300 python tools/quick_bench.py dequant 2>&1 | tail -12
+timeout 600 python -m pytest tests -m gpu -x -q -k "conversion or convert or sampler or rescaled or output" 2>&1 | tail -2
+B2_FRAMES=64 timeout 300 python tools/quick_bench.py convert 2>&1 | grep -i "yuv"

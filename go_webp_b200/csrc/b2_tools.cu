@@ -53,7 +53,7 @@ __device__ __forceinline__ int carry_out(uint32_t tmask, int base, int carry, in
 
 // ---- WebPCleanupTransparentArea, YUVA form ------------------------------------------
 // unit = one band of 8 rows (the last band may be shorter: SmoothenBlock only, :173-181)
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, 5)
 cleanup_yuva_kernel(const PicJobDev* __restrict__ jobs, const uint32_t* __restrict__ prefix, uint32_t n_jobs,
                     uint32_t uniform, uint32_t total) {
   const int lane = threadIdx.x & 31;
@@ -439,7 +439,7 @@ extern "C" int b2_picture_cleanup_transparent(b2_ctx* ctx, int stream, const b2_
   if (tot == 0) return B2_OK;   // images lower than one block row: nothing to clean
   const int grid = b2_grid_for(ctx, 4, (tot + kWarps - 1) / kWarps);
   if (use_argb) cleanup_argb_kernel<<<grid, kThreads, 0, ctx->streams[stream]>>>(dj, dp, (uint32_t)n_jobs, uni, tot);
-  else cleanup_yuva_kernel<<<grid, kThreads, 0, ctx->streams[stream]>>>(dj, dp, (uint32_t)n_jobs, uni, tot);
+  else cleanup_yuva_kernel<<<b2_grid_for(ctx, 5, (tot + kWarps - 1) / kWarps), kThreads, 0, ctx->streams[stream]>>>(dj, dp, (uint32_t)n_jobs, uni, tot);
   ctx->launches++;
   B2_CUDA(ctx, cudaGetLastError());
   return B2_OK;

@@ -402,7 +402,8 @@ int b2_alpha_filter(b2_ctx* ctx, int stream, const b2_alpha_filter_job* jobs, in
  * [0, 100] is B2_ERR_INVALID_CONFIG (the reference returns false).  The reference works in
  * place; here dst != src (the result is the same, see b2_dequant.cu).  ordered_dither = 1
  * is the Go file as written (DFIX = 4 and the 4x4 ordered dither, :36-45, :147-148);
- * 0 is the stock libwebp build it was transliterated from (USE_DITHERING undefined). */
+ * 0 is the stock libwebp build it was transliterated from (USE_DITHERING undefined).
+ * At most 65535 planes per call (B2_ERR_INVALID_CONFIG beyond). */
 typedef struct b2_alpha_dequant_job {
   const uint8_t* src;
   uint8_t* dst;

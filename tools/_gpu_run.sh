@@ -1,5 +1,2 @@
-timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-timeout 900 python bench.py > gpurun_out/r01h_bench.json 2> gpurun_out/r01h_bench.err; echo bench rc=$?
-timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r01h_bench_reference_arm.json 2>> gpurun_out/r01h_bench.err; echo ref rc=$?
-B2_FRAMES=128 timeout 600 python tools/quick_bench.py dequant filters rescale convert tools > gpurun_out/r01h_quick_next_rows.txt 2>&1; echo quick rc=$?
+timeout 600 python -m pytest tests -m gpu -x -q -k "rescale" 2>&1 | tail -2
+B2_FRAMES=64 timeout 300 python tools/quick_bench.py rescale 2>&1 | tail -3

@@ -306,6 +306,71 @@ alpha_unfilter_gradient_kernel(const FiltJobDev* __restrict__ jobs, uint32_t n_j
           __syncwarp();
         }
       };
+      const bool words = ((((uintptr_t)j.src | (uintptr_t)j.dst) | (uint32_t)j.src_stride | (uint32_t)j.dst_stride) & 3) == 0;
+      if (words) {
+        // Aligned rows: the skew between rows is one 4-pixel word instead of one pixel, so that
+        // every lane is at a word boundary at the same time.  Quad step q: lane l takes word
+        // m = q - l of its row; the word above it is lane l-1's output of the previous quad step
+        // (one shuffle per 4 pixels), the pixel above-left the last byte of the word before that.
+        // Inputs and (lane 0) the row above are whole words fetched 8 quad steps ahead.
+        const int nq = (w + 3) >> 2;
+        auto in_word = [&](int m) -> uint32_t {
+          if (!row_ok || m < 0 || m >= nq) return 0u;
+          if (4 * m + 4 <= w) return __ldg((const uint32_t*)in + m);
+          uint32_t v = 0;
+          for (int t = 0; 4 * m + t < w; ++t) v |= (uint32_t)in[4 * m + t] << (8 * t);
+          return v;
+        };
+        auto above_word = [&](int m) -> uint32_t {
+          if (lane != 0 || band == 0 || m < 0 || m >= nq) return 0u;
+          if (4 * m + 4 <= w) return *((const volatile uint32_t*)above + m);
+          uint32_t v = 0;
+          for (int t = 0; 4 * m + t < w; ++t) v |= (uint32_t)*(const volatile uint8_t*)(above + 4 * m + t) << (8 * t);
+          return v;
+        };
+        uint32_t inq[8], abq[8];
+        wait_for(32);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) { inq[t] = in_word(t - lane); abq[t] = above_word(t); }
+        uint32_t my_out = 0, left = 0, tl = 0;
+        for (int q0 = 0; q0 < nq + 31; q0 += 8) {
+          wait_for(4 * (q0 + 16));
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const int q = q0 + t, m = q - lane;
+            const uint32_t vin = inq[t];
+            uint32_t topw = __shfl_up_sync(0xffffffffu, my_out, 1);
+            if (lane == 0) topw = abq[t];
+            inq[t] = in_word(m + 8);
+            abq[t] = above_word(q + 8);
+            if (row_ok && m >= 0 && m < nq) {
+              uint32_t outw = 0;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int c = 4 * m + k;
+                const int v = (int)((vin >> (8 * k)) & 0xff), top = (int)((topw >> (8 * k)) & 0xff);
+                const int tlk = (k == 0) ? (int)tl : (int)((topw >> (8 * (k - 1))) & 0xff);
+                int o;
+                if (row == 0) o = (v + (int)left) & 0xff;                  // first row: horizontal, pred 0 at c == 0
+                else if (c == 0) o = (v + top) & 0xff;                     // left = top = top_left = prev[0]
+                else o = (v + gradient_pred((int)left, top, tlk)) & 0xff;
+                if (c < w) left = (uint32_t)o;
+                outw |= (uint32_t)o << (8 * k);
+              }
+              tl = topw >> 24;
+              if (4 * m + 4 <= w) *((uint32_t*)out + m) = outw;
+              else for (int t2 = 0; 4 * m + t2 < w; ++t2) out[4 * m + t2] = (uint8_t)(outw >> (8 * t2));
+              my_out = outw;
+            }
+          }
+          if (lane == 31) {            // words 0 .. q0 + 7 - 31 of the band's last row are written
+            const int done = min(max(4 * (q0 + 8 - 31), 0), w);
+            __threadfence_block();
+            progress[warp] = (bi << 14) + done;
+          }
+        }
+        continue;
+      }
       int left = 0, top_left = 0, cur_out = 0;
       // a lane touches a different row than its neighbours, so every access costs the L1 one
       // sector per lane: outputs leave as aligned 32-bit words (a quarter of the lanes per step)

@@ -1,2 +1,2 @@
-timeout 600 python -m pytest tests -m gpu -x -q -k "rescale" 2>&1 | tail -2
-B2_FRAMES=64 timeout 300 python tools/quick_bench.py rescale 2>&1 | tail -3
+timeout 300 python -m pytest tests -m gpu -x -q -k "alpha_filters or maximum_dimension or golden" 2>&1 | tail -3
+timeout 120 python tools/quick_bench.py filters 2>&1 | grep gradient

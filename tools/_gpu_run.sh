@@ -1,2 +1,3 @@
-timeout 300 python -m pytest tests -m gpu -x -q -k "alpha_filters or maximum_dimension or golden" 2>&1 | tail -3
-timeout 120 python tools/quick_bench.py filters 2>&1 | grep gradient
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 600 python bench.py --steps 10 --warmup 3 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['value'], d['roofline']['frac'], d['clocks'])"

@@ -98,6 +98,25 @@ class RescaleJob(C.Structure):
                 ("num_channels", C.c_int32), ("reserved", C.c_int32)]
 
 
+class ImportHost(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("y", C.c_void_p), ("u", C.c_void_p), ("v", C.c_void_p), ("a", C.c_void_p),
+                ("y_stride", C.c_int32), ("uv_stride", C.c_int32), ("a_stride", C.c_int32), ("reserved", C.c_int32)]
+
+
+class UpsampleHost(C.Structure):
+    _fields_ = [("y", C.c_void_p), ("u", C.c_void_p), ("v", C.c_void_p), ("a", C.c_void_p), ("dst", C.c_void_p),
+                ("y_stride", C.c_int32), ("uv_stride", C.c_int32), ("a_stride", C.c_int32), ("dst_stride", C.c_int32)]
+
+
+class ArgbHost(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("data", C.c_void_p),
+                ("src_bytes", C.c_size_t), ("dst_bytes", C.c_size_t), ("data_bytes", C.c_size_t)]
+
+
+VP8L_OPS = {"add_green": 0, "sub_green": 1, "color_inverse": 2, "color_forward": 3, "inverse_chain": 4,
+            "forward_chain": 5, "color_index_inverse": 6, "bundle_color_map": 7, "predictor_inverse": 8,
+            "predictor_forward": 9}
+
 CONVERT_UPSTREAM_16BIT = 1
 ALPHA_APPLY, ALPHA_APPLY_4444, ALPHA_MULT_ARGB, ALPHA_MULT_ROW, ALPHA_DISPATCH = 0, 1, 2, 3, 4
 
@@ -128,6 +147,12 @@ SYMBOLS = {
     "b2_sync": (C.c_int, [_ctx, C.c_int]),
     "b2_event_record": (C.c_int, [_ctx, C.c_int, C.c_int]),
     "b2_event_elapsed_ms": (C.c_int, [_ctx, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "b2_event_sync": (C.c_int, [_ctx, C.c_int]),
+    "b2_copy_stats": (C.c_int, [_ctx, C.POINTER(C.c_uint64)]),
+    "b2_import_batch_staged": (C.c_int, [_ctx, C.POINTER(ImportJob), C.POINTER(ImportHost), C.c_int, C.c_int, C.c_int,
+                                         C.c_int, C.c_float, _vp]),
+    "b2_upsample_batch_staged": (C.c_int, [_ctx, C.POINTER(UpsampleJob), C.POINTER(UpsampleHost), C.c_int, C.c_int, C.c_int]),
+    "b2_vp8l_batch_staged": (C.c_int, [_ctx, C.c_int, C.POINTER(ArgbJob), C.POINTER(ArgbHost), C.c_int, C.c_int]),
     "b2_rgba_to_yuv420a": (C.c_int, [_ctx, C.c_int, C.POINTER(ImportJob), C.c_int, C.c_int, C.c_int, _vp]),
     "b2_rgba_to_yuv420a_dithered": (C.c_int, [_ctx, C.c_int, C.POINTER(ImportJob), C.c_int, C.c_int, C.c_int, _vp, C.c_float]),
     "b2_yuv420a_to_rgba_fancy": (C.c_int, [_ctx, C.c_int, C.POINTER(UpsampleJob), C.c_int, C.c_int]),
@@ -183,7 +208,7 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)  # AttributeError if the export is missing
             fn.restype = res
             fn.argtypes = args
-        if lib.b2_abi_version() != 0x0104:
+        if lib.b2_abi_version() != 0x0105:
             raise ImportError("libb2webp.so ABI version mismatch; rebuild")
         _LIB = lib
     return _LIB

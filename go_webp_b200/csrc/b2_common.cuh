@@ -13,6 +13,8 @@
 #define B2_EVENT_SLOTS 32
 // Staging ring for batch descriptors (pinned host + device mirror) per stream.
 #define B2_DESC_RING_BYTES (4u << 20)
+// Events of the host-staged entry points (b2_staged.cu): one per chunk in flight.
+#define B2_STAGED_EVENTS 24
 
 struct b2_ctx {
   int device;
@@ -30,6 +32,13 @@ struct b2_ctx {
   void* scratch[B2_MAX_STREAMS];
   size_t scratch_bytes[B2_MAX_STREAMS];
   uint64_t launches;
+  // copies issued through the ABI (b2_copy_stats): calls and bytes per direction
+  uint64_t h2d_calls, h2d_bytes, d2h_calls, d2h_bytes;
+  // host-staged entry points: has-alpha flags (device + pinned mirror), per-chunk events
+  int32_t* flags_dev;
+  int32_t* flags_host;
+  size_t flags_cap;
+  cudaEvent_t staged_ev[B2_STAGED_EVENTS];
   char err[256];
 };
 

@@ -126,6 +126,9 @@ extern "C" void b2_ctx_destroy(b2_ctx* ctx) {
   }
   for (int i = 0; i < B2_EVENT_SLOTS; ++i) if (ctx->events[i]) (void)cudaEventDestroy(ctx->events[i]);
   if (ctx->tab_dev) (void)cudaFree(ctx->tab_dev);
+  if (ctx->flags_dev) (void)cudaFree(ctx->flags_dev);
+  if (ctx->flags_host) (void)cudaFreeHost(ctx->flags_host);
+  for (int i = 0; i < B2_STAGED_EVENTS; ++i) if (ctx->staged_ev[i]) (void)cudaEventDestroy(ctx->staged_ev[i]);
   free(ctx);
 }
 
@@ -207,6 +210,7 @@ extern "C" int b2_h2d_async(b2_ctx* ctx, int stream, void* dst_dev, const void* 
   if (bytes == 0) return B2_OK;
   if (dst_dev == NULL || src_host == NULL) return B2_ERR_NULL;
   B2_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->streams[stream]));
+  ctx->h2d_calls++; ctx->h2d_bytes += bytes;
   return B2_OK;
 }
 extern "C" int b2_d2h_async(b2_ctx* ctx, int stream, void* dst_host, const void* src_dev, size_t bytes) {
@@ -214,6 +218,7 @@ extern "C" int b2_d2h_async(b2_ctx* ctx, int stream, void* dst_host, const void*
   if (bytes == 0) return B2_OK;
   if (dst_host == NULL || src_dev == NULL) return B2_ERR_NULL;
   B2_CUDA(ctx, cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->streams[stream]));
+  ctx->d2h_calls++; ctx->d2h_bytes += bytes;
   return B2_OK;
 }
 extern "C" int b2_h2d_2d_async(b2_ctx* ctx, int stream, void* dst_dev, size_t dst_pitch,
@@ -223,6 +228,7 @@ extern "C" int b2_h2d_2d_async(b2_ctx* ctx, int stream, void* dst_dev, size_t ds
   if (dst_dev == NULL || src_host == NULL) return B2_ERR_NULL;
   B2_CUDA(ctx, cudaMemcpy2DAsync(dst_dev, dst_pitch, src_host, src_pitch, width_bytes, rows,
                                  cudaMemcpyHostToDevice, ctx->streams[stream]));
+  ctx->h2d_calls++; ctx->h2d_bytes += width_bytes * rows;
   return B2_OK;
 }
 extern "C" int b2_d2h_2d_async(b2_ctx* ctx, int stream, void* dst_host, size_t dst_pitch,
@@ -232,6 +238,7 @@ extern "C" int b2_d2h_2d_async(b2_ctx* ctx, int stream, void* dst_host, size_t d
   if (dst_host == NULL || src_dev == NULL) return B2_ERR_NULL;
   B2_CUDA(ctx, cudaMemcpy2DAsync(dst_host, dst_pitch, src_dev, src_pitch, width_bytes, rows,
                                  cudaMemcpyDeviceToHost, ctx->streams[stream]));
+  ctx->d2h_calls++; ctx->d2h_bytes += width_bytes * rows;
   return B2_OK;
 }
 extern "C" int b2_memset_async(b2_ctx* ctx, int stream, void* dst_dev, int value, size_t bytes) {

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define B2_ABI_VERSION 0x0104
+#define B2_ABI_VERSION 0x0105
 
 typedef enum b2_status {
   B2_OK = 0,
@@ -77,6 +77,12 @@ int b2_sync(b2_ctx* ctx, int stream);
 /* CUDA-event stopwatch on a context stream (slots 0..31). */
 int b2_event_record(b2_ctx* ctx, int stream, int slot);
 int b2_event_elapsed_ms(b2_ctx* ctx, int slot_start, int slot_stop, float* ms);
+/* Blocks the host until the event in 'slot' has happened. */
+int b2_event_sync(b2_ctx* ctx, int slot);
+/* Copies issued through this context so far: out = {H2D calls, H2D bytes, D2H calls,
+ * D2H bytes}.  What a caller uses to check that chained calls on device-resident
+ * pictures do not touch the host in between. */
+int b2_copy_stats(const b2_ctx* ctx, uint64_t out[4]);
 
 /* ---- part 1: RGBA -> YUV420(+A) import ----------------------------------
  * Replaces the row loop of dsp.WebPImportYUVAFromRGBA /
@@ -428,6 +434,63 @@ typedef struct b2_rescale_job {
   int32_t reserved;
 } b2_rescale_job;
 int b2_rescale_planes(b2_ctx* ctx, int stream, const b2_rescale_job* jobs, int n_jobs);
+
+/* ---- host-staged batch entry points -------------------------------------------------
+ * What the added batched Go entry points bind (picture.ImportRGBABatch,
+ * picture.YUVAToRGBABatch, dsp.VP8LInverseTransformBatch): the whole
+ * host -> device -> kernel -> host pipeline of a batch in one synchronous call.  'jobs'
+ * is the same DEVICE-side job array the resident entry points take (the device planes of
+ * pkg/picture's device-resident pictures, or library scratch), 'host' the matching HOST
+ * buffers, entry by entry.  The batch is cut into chunks of 'chunk' jobs that go round the
+ * context's streams, so the H2D copy of one chunk, the kernel of another and the D2H copy of
+ * a third overlap.  A NULL host pointer skips that copy: inputs already resident are not
+ * sent again, outputs that stay on the device for the next call are not brought back.
+ * Host buffers should be pinned (b2_pinned_alloc / b2_host_register); pageable memory
+ * works but is staged by the driver.  Host planes are top-down (positive strides, in
+ * bytes); contiguous ranges are merged into single copies. */
+typedef struct b2_import_host {
+  const uint8_t* src; /* pixel (0,0) of the host image; rows job.src_stride apart (signed) */
+  uint8_t* y;
+  uint8_t* u;
+  uint8_t* v;
+  uint8_t* a;         /* copied back only when the picture turns out to have alpha (conversions.go:56-58) */
+  int32_t y_stride, uv_stride, a_stride;
+  int32_t reserved;
+} b2_import_host;
+/* Per image enc.Import -> picture.ImportYUVAFromRGBA (pkg/libwebp/enc/picture_csp_enc.c.go:123-137,
+ * pkg/picture/conversions.go:50-165).  has_alpha_host: int32[n_jobs], may be NULL.
+ * dithering > 0 selects the dithered import. */
+int b2_import_batch_staged(b2_ctx* ctx, const b2_import_job* jobs, const b2_import_host* host, int n_jobs,
+                           int order, int flags, int chunk, float dithering, int32_t* has_alpha_host);
+
+typedef struct b2_upsample_host {
+  const uint8_t* y;
+  const uint8_t* u;
+  const uint8_t* v;
+  const uint8_t* a;
+  uint8_t* dst;
+  int32_t y_stride, uv_stride, a_stride, dst_stride;
+} b2_upsample_host;
+/* Per image WebPPictureYUVAToARGB / EmitFancyRGB (picture_csp_enc.c.go:62-118, io_dec.c.go:65-115);
+ * only the rows [row_begin, row_end) a job produces are copied back. */
+int b2_upsample_batch_staged(b2_ctx* ctx, const b2_upsample_job* jobs, const b2_upsample_host* host, int n_jobs,
+                             int mode, int chunk);
+
+typedef struct b2_argb_host {
+  const void* src;  /* src_bytes of pixels (or indices for the bundle) */
+  void* dst;
+  const void* data; /* tile codes / palette / mode image */
+  size_t src_bytes, dst_bytes, data_bytes;
+} b2_argb_host;
+typedef enum b2_vp8l_op {
+  B2_VP8L_ADD_GREEN = 0, B2_VP8L_SUB_GREEN = 1, B2_VP8L_COLOR_INVERSE = 2, B2_VP8L_COLOR_FORWARD = 3,
+  B2_VP8L_INVERSE_CHAIN = 4, B2_VP8L_FORWARD_CHAIN = 5, B2_VP8L_COLOR_INDEX_INVERSE = 6,
+  B2_VP8L_BUNDLE_COLOR_MAP = 7, B2_VP8L_PREDICTOR_INVERSE = 8, B2_VP8L_PREDICTOR_FORWARD = 9
+} b2_vp8l_op;
+/* One step of VP8LInverseTransform / ApplyInverseTransforms (lossless.go:511-547,
+ * pkg/vp8/vp8l_dec.c.go:710-729) or its forward counterpart over a batch of images. */
+int b2_vp8l_batch_staged(b2_ctx* ctx, int op, const b2_argb_job* jobs, const b2_argb_host* host, int n_jobs,
+                         int chunk);
 
 /* ---- synthetic inputs (SURVEY.md 8d generator, identical to the oracle's) -
  * One uint32 per (row, word) position of n images laid out 'image_bytes'

@@ -1,18 +1,22 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the go-webp pixel hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config 1|2|3|4]
 
-Workload (BASELINE.json configs[1]): a batch of 256 synthetic 1920x1080 RGBA
-frames per GPU, RGBA -> YUV420(+A) import.  A "step" is one pass of the import
-kernel over the resident batch (one kernel launch).  Weak scaling: every rank
-owns its own 256-frame batch, no data-path collective (images are independent).
+Headline workload (BASELINE.json configs[1], --config 1): a batch of 256 synthetic
+1920x1080 RGBA frames per GPU, RGBA -> YUV420(+A) import.  A "step" is one pass of the
+import kernel over the resident batch (one kernel launch).  Weak scaling: every rank owns
+its own 256-frame batch, no data-path collective (images are independent).
 
-Prints ONE JSON line (rank 0).  `value` is device-resident throughput (inputs in
-HBM before the timed region); `e2e` is the same metric through the batched
-public entry point (go_webp_b200.pipeline.ImportPipeline.run) with pinned HOST
-buffers, H2D and D2H inside the timed region.  `roofline` is for the import
-kernel; `cpu_baseline` is the CPU oracle port timed on this box's host cores.
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput (inputs in HBM
+before the timed region); `e2e` is the same metric through the drop-in batched entry point
+picture.ImportRGBABatch (-> b2_import_batch_staged) with pinned HOST buffers, H2D and D2H
+inside the timed region, next to the box's own copy ceiling measured in the same run.
+`roofline` is for the import kernel; `cpu_baseline` is the CPU oracle port timed on this
+box's host cores.  `other_configs` carries, at EVERY N and from every rank's share, the
+other BASELINE configs: [2] VP8L chains on 64 x 4096^2, [3] 1024 x 4K fancy upsample sharded
+by image (strong scaling), [4] the mixed-size batch, LPT by calibrated time -- each with its
+own device-resident and end-to-end figure.  --config k makes config k the headline.
 """
 from __future__ import annotations
 
@@ -228,42 +232,82 @@ def host_threads() -> int:
         return max(1, os.cpu_count() or 1)
 
 
-def run_reference(args):
-    """--impl reference: the CPU implementation of the path on the host cores.
-    The Go reference does not compile and no Go toolchain exists (DESIGN.md), so
-    this is the oracle port, with all host threads, on the same config/metric."""
-    rank, world, _ = dist_env()
-    if rank != 0:
-        return 0
-    import oracle
-    oracle.build()
-    T = host_threads()
-    alpha_mode = ALPHA_MODES[args.alpha]
-    # bounded sample per step: sized from a probe so (K+W) steps take ~2 minutes at most
-    probe_frames = max(T, 8)
-    rate, dt = cpu_import_rate(probe_frames, T, alpha_mode)
-    budget = 100.0 / max(1, args.steps + args.warmup)
-    frames = int(min(args.frames, max(T, rate * 1e6 * min(budget, 4.0) / (W * H))))
-    for _ in range(args.warmup):
-        cpu_import_rate(frames, T, alpha_mode)
-    t = 0.0
-    for _ in range(args.steps):
-        t += cpu_import_rate(frames, T, alpha_mode)[1]
-    value = frames * W * H * args.steps / t / 1e6
-    sample = f"{frames} of {args.frames} 1080p frames per step, one image per task"
-    line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "Mpixel/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
-        "data": "synthetic", "config": workload_config(args),
-        "cpu_baseline": {"value": value, "unit": "Mpixel/s", "cores": T, "kind": "port", "sample": sample,
-                         "note": "gcc -O2 C restatement of the reference (oracle/oracle.c); Go reference "
-                                 "cannot be built: GOMAXPROCS n/a"},
-        "e2e": {"value": value, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    }
-    print(json.dumps(line))
-    return 0
+class Dist:
+    """torch.distributed plumbing: barrier + max / sum / gather over ranks (NCCL; no data-path use)."""
+
+    def __init__(self):
+        self.rank, self.world, self.local = dist_env()
+        import torch
+        self.torch = torch
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            import torch.distributed as dist
+            self.dist = dist
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def _red(self, x, op):
+        if self.world == 1:
+            return float(x)
+        t = self.torch.tensor([float(x)], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    def max(self, x):
+        return self._red(x, self.dist.ReduceOp.MAX if self.world > 1 else None)
+
+    def sum(self, x):
+        return self._red(x, self.dist.ReduceOp.SUM if self.world > 1 else None)
+
+    def gather(self, x):
+        if self.world == 1:
+            return [float(x)]
+        t = self.torch.zeros(self.world, dtype=self.torch.float64, device="cuda")
+        t[self.rank] = float(x)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return [float(v) for v in t.tolist()]
+
+    def bcast_list(self, values):
+        """rank 0's list of floats to everyone (the calibrated cost model of configs[4])."""
+        if self.world == 1:
+            return list(values)
+        t = self.torch.tensor(list(values), dtype=self.torch.float64, device="cuda")
+        self.dist.broadcast(t, 0)
+        return [float(v) for v in t.tolist()]
+
+    def close(self):
+        if self.world > 1:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def timed_device(ctx, D, run, steps, warm=3, slots=(6, 7)):
+    """ms per call of run() on stream 0: CUDA events, barrier + synchronize on both sides, max over ranks."""
+    for _ in range(warm):
+        run()
+    D.barrier()
+    ctx.event_record(slots[0])
+    for _ in range(steps):
+        run()
+    ctx.event_record(slots[1])
+    D.barrier()
+    return D.max(ctx.elapsed_ms(slots[0], slots[1]) / steps)
+
+
+def timed_wall(D, run, steps, warm=1):
+    """seconds per call of a synchronous host-level call (the end-to-end entry points), max over ranks."""
+    for _ in range(warm):
+        run()
+    D.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        run()
+    D.barrier()
+    return D.max((time.perf_counter() - t0) / steps)
 
 
 def workload_config(args):
@@ -273,6 +317,262 @@ def workload_config(args):
             "partition": "images sharded by rank, no collective",
             "l2": "input batch (2.1 GB) and outputs (1.3 GB) are >> 126 MB L2; no flush needed",
             "seed": hex(SEED)}
+
+
+# ---- BASELINE configs[2], [3], [4]: every rank's share, device-resident and end to end ------------
+def config3_upsample(ctx, D, peak, steps, total_frames=1024, e2e_frames=32):
+    """configs[3]: 1024 x 3840x2160 YUV420 -> RGBA fancy upsampling sharded by image over the ranks
+    (strong scaling: 1024 / N frames per GPU).  e2e = picture.YUVAToRGBABatch on pinned planes."""
+    from go_webp_b200 import _abi, picture
+    from go_webp_b200.partition import contiguous_shard
+    from go_webp_b200.pipeline import UpsamplePipeline
+    w, h = 3840, 2160
+    mine = contiguous_shard(total_frames, D.world, D.rank)
+    n = len(mine)
+    up = UpsamplePipeline(ctx, n, w, h, _abi.MODE_RGBA, host=False)
+    up.fill_synthetic(0xB2000004, first_img=mine.start)
+    ms = timed_device(ctx, D, up.run_device, max(3, min(steps, 10)))
+    up.close()
+    px = total_frames * w * h
+    out = {"workload": f"configs[3]: {total_frames} x {w}x{h} YUV420 -> RGBA fancy upsample, {n} frames on this rank "
+                       f"(image-sharded, strong scaling)", "n_gpus": D.world, "scaling": "strong",
+           "value": px / ms / 1e3, "unit": "Mpixel/s", "ms_per_step": ms,
+           "roofline": {"bound": "hbm", "bytes_per_px": 5.5, "achieved": n * w * h * 5.5 / ms / 1e6, "peak": peak,
+                        "frac": n * w * h * 5.5 / ms / 1e6 / peak, "unit": "GB/s", "per": "GPU"}}
+    # end to end through the drop-in entry point: pinned Y/U/V in, pinned RGBA out, a bounded sample per rank
+    m = min(e2e_frames, n)
+    pics = [picture.Picture(Width=w, Height=h) for _ in range(m)]
+    picture.AllocResidentBatch(pics, "yuva", ctx)
+    for i, pic in enumerate(pics):   # synthetic planes straight into the pinned mirrors, then device copies dropped
+        mem = pic.memory_
+        ctx.synth_fill(mem.dev("y"), mem.ys // 4, h, mem.ys, mem.ys * h, 1, 0xB2000004, mine.start + i, 1)
+        ctx.synth_fill(mem.dev("u"), mem.uvs // 4, mem.uvh, mem.uvs, mem.uvs * mem.uvh, 1, 0xB2000004, mine.start + i, 2)
+        ctx.synth_fill(mem.dev("v"), mem.uvs // 4, mem.uvh, mem.uvs, mem.uvs * mem.uvh, 1, 0xB2000004, mine.start + i, 3)
+        mem.dev_valid = True
+        mem.download(with_alpha=False)
+    dst = picture.PinnedBytes(m * 4 * w * h, ctx)
+    dsts = [dst.array[i * 4 * w * h:(i + 1) * 4 * w * h].reshape(h, 4 * w) for i in range(m)]
+
+    def run():
+        for pic in pics:
+            pic.memory_.dev_valid = False     # host planes are the source of truth: upload every step
+        assert picture.YUVAToRGBABatch(pics, _abi.MODE_RGBA, dsts, ctx, chunk=4) is not None
+    for pic in pics:
+        pic.ColorSpace = picture.WEBP_YUV420
+    t = timed_wall(D, run, 2)
+    agg_px = D.sum(m * w * h)
+    out["e2e"] = {"value": agg_px / t / 1e6, "unit": "Mpixel/s", "api": "picture.YUVAToRGBABatch (b2_upsample_batch_staged)",
+                  "sample": f"{m} frames per rank per step", "h2d_bytes_per_step": int(m * w * h * 1.5),
+                  "d2h_bytes_per_step": m * w * h * 4}
+    for pic in pics:
+        picture.WebPPictureFree(pic)
+    return out
+
+
+def config2_vp8l(ctx, D, peak, steps, total_images=64, e2e_images=16):
+    """configs[2]: VP8L inverse chains on 64 x 4096x4096 ARGB images sharded over the ranks: fused
+    cross-colour^-1 + add-green (32x32 tiles), 8-bit and 2-bit colour indexing, and the full
+    predictor + cross-colour + add-green chain.  e2e = b2_vp8l_batch_staged with pinned buffers."""
+    from go_webp_b200.partition import contiguous_shard
+    from go_webp_b200.pipeline import ArgbPipeline
+    w = h = 4096
+    mine = contiguous_shard(total_images, D.world, D.rank)
+    n = len(mine)
+    out = {"workload": f"configs[2]: {total_images} x {w}x{h} ARGB, {n} images on this rank", "n_gpus": D.world,
+           "scaling": "strong", "kernels": {}}
+    k = max(3, min(steps, 10))
+    for op, bits, bpp, name in [("inverse_chain", 5, 8.0039, "crosscolor_inv_addgreen_fused"),
+                                ("color_index_inverse", 0, 8.0, "color_index_8bit"),
+                                ("color_index_inverse", 2, 5.0, "color_index_2bit"),
+                                ("predictor_inverse", 5, 8.0039, "predictor_inverse")]:
+        ap = ArgbPipeline(ctx, n, w, h, op, bits, host=(name == "crosscolor_inv_addgreen_fused"), host_images=e2e_images)
+        ap.fill_synthetic(0xB2000003, first_img=mine.start)
+        ms = timed_device(ctx, D, ap.run_device, k if op != "predictor_inverse" else 3)
+        px = total_images * w * h
+        out["kernels"][name] = {"mpixel_per_s": px / ms / 1e3, "ms_per_step": ms, "bytes_per_px": bpp,
+                                "frac": n * w * h * bpp / ms / 1e6 / peak}
+        if ap.host:
+            m = ap.host_images
+            t = timed_wall(D, ap.run, 2)
+            out["e2e"] = {"value": D.sum(m * w * h) / t / 1e6, "unit": "Mpixel/s",
+                          "api": "b2_vp8l_batch_staged(B2_VP8L_INVERSE_CHAIN) = dsp.VP8LInverseTransformBatch's call, pinned buffers",
+                          "sample": f"{m} images per rank per step", "h2d_bytes_per_step": ap.h2d_bytes, "d2h_bytes_per_step": ap.d2h_bytes}
+        ap.close()
+    kk = out["kernels"]["crosscolor_inv_addgreen_fused"]
+    out.update({"value": kk["mpixel_per_s"], "unit": "Mpixel/s", "ms_per_step": kk["ms_per_step"],
+                "roofline": {"bound": "hbm", "bytes_per_px": 8.0039, "frac": kk["frac"], "peak": peak, "unit": "GB/s", "per": "GPU"}})
+    return out
+
+
+def config4_mixed(ctx, D, peak, steps, n_images=256):
+    """configs[4]: 256 images, 64x64 .. 8192x8192 with odd widths / heights, full pixel pipeline (import ->
+    fancy upsample -> VP8L inverse chain), LPT-partitioned over the ranks by CALIBRATED TIME: one warm-up
+    pass times each (width class, size class) group of the batch, cost = bytes / rate(group)."""
+    from go_webp_b200 import partition
+    from go_webp_b200.pipeline import MixedPipeline, mixed_sizes
+    sizes = mixed_sizes(n_images, 0xB2000005)
+    groups = [partition.size_class(w_, h_) for (w_, h_) in sizes]
+    rates = {}
+    if D.rank == 0:
+        for g in sorted(set(groups)):
+            sub = [s for s, gg in zip(sizes, groups) if gg == g]
+            p = MixedPipeline(ctx, sub)
+            p.fill_synthetic(0xB2000005)
+            for _ in range(2):
+                p.run_device()
+            ctx.sync()
+            ctx.event_record(8)
+            for _ in range(3):
+                p.run_device()
+            ctx.event_record(9)
+            ctx.sync()
+            rates[g] = p.algorithmic_bytes() / (ctx.elapsed_ms(8, 9) / 3)
+            p.close()
+    keys = sorted(set(groups))
+    vals = D.bcast_list([rates.get(g, 0.0) for g in keys])
+    rates = dict(zip(keys, vals))
+    costs = partition.calibrated_costs(sizes, rates)
+    parts = partition.lpt_partition(costs, D.world)
+    mine = [sizes[i] for i in parts[D.rank]]
+    p = MixedPipeline(ctx, mine)
+    p.fill_synthetic(0xB2000005)
+    k = max(3, min(steps, 10))
+    for _ in range(3):
+        p.run_device()
+    D.barrier()
+    ctx.event_record(8)
+    for _ in range(k):
+        p.run_device()
+    ctx.event_record(9)
+    D.barrier()
+    my_ms = ctx.elapsed_ms(8, 9) / k
+    per_gpu = D.gather(my_ms)
+    ms = max(per_gpu)
+    px = D.sum(p.pixels)
+    by = D.sum(p.algorithmic_bytes())
+    out = {"workload": f"configs[4]: {n_images} mixed-size images (64x64..8192x8192, odd sizes), import -> fancy upsample -> "
+                       f"cross-colour^-1 + add-green, 3 launches per pass over the rank's share", "n_gpus": D.world,
+           "scaling": "strong", "value": px / ms / 1e3, "unit": "Mpixel/s", "ms_per_step": ms,
+           "per_gpu_ms": per_gpu, "imbalance_max_over_mean": ms * D.world / sum(per_gpu),
+           "partition": "LPT on calibrated time (bytes / measured rate of the image's width-alignment x size class)",
+           "roofline": {"bound": "hbm", "achieved": by / D.world / ms / 1e6, "peak": peak, "unit": "GB/s",
+                        "frac": by / D.world / ms / 1e6 / peak, "per": "GPU (mean share / slowest rank)"}}
+    p.close()
+    return out
+
+
+def config1_import(ctx, D, args, peak, peak_src, sampler):
+    from go_webp_b200 import picture
+    from go_webp_b200.pipeline import ImportPipeline
+    alpha_mode = ALPHA_MODES[args.alpha]
+    rank, world = D.rank, D.world
+    pipe = ImportPipeline(ctx, args.frames, W, H, "RGBA", import_alpha=True, chunk=16, host=True)
+    pipe.fill_synthetic(SEED, first_img=rank * args.frames, alpha_mode=alpha_mode, to_host=True)
+    t_load0 = time.perf_counter()
+    for _ in range(args.warmup):
+        pipe.run_device()
+    D.barrier()
+    launches0 = ctx.launches
+    t0 = time.perf_counter()
+    ctx.event_record(0)
+    for _ in range(args.steps):
+        pipe.run_device()
+    ctx.event_record(1)
+    D.barrier()
+    t1 = time.perf_counter()
+    launches = ctx.launches - launches0
+    ms = D.max(ctx.elapsed_ms(0, 1))
+    extra = None
+    if sampler.count_between(t_load0, t1) < 3:   # keep the same kernel running (untimed) until the sampler has seen it
+        e0 = time.perf_counter()
+        while time.perf_counter() - e0 < 0.5:
+            for _ in range(10):
+                pipe.run_device()
+            ctx.sync()
+        extra = (e0, time.perf_counter())
+    clocks = sampler.summary(t0, t1, t_load0, extra)
+    px_step = world * args.frames * W * H
+    ms_step = ms / args.steps
+    value = px_step / ms_step / 1e3  # Mpixel/s
+    gbs_rank = args.frames * W * H * IMPORT_BYTES_PER_PX / ms_step / 1e6
+
+    # sustained: the same launch back to back for >= 2 s, with the clock record of that window
+    sustained = None
+    if not args.no_extras:
+        n_loop = int(2200.0 / ms_step) + 1
+        D.barrier()
+        ts0 = time.perf_counter()
+        ctx.event_record(2)
+        for _ in range(n_loop):
+            pipe.run_device()
+        ctx.event_record(3)
+        D.barrier()
+        ts1 = time.perf_counter()
+        sms = D.max(ctx.elapsed_ms(2, 3)) / n_loop
+        sustained = {"seconds": sms * n_loop / 1e3, "launches": n_loop, "ms_per_step": sms, "value": px_step / sms / 1e3,
+                     "frac": args.frames * W * H * IMPORT_BYTES_PER_PX / sms / 1e6 / peak,
+                     "clocks": sampler.summary(ts0, ts1, ts0)}
+
+    # parity spot check against the oracle (outside every timed region)
+    parity = "skipped"
+    if rank == 0:
+        import oracle
+        oracle.build()
+        ok = True
+        for i in (0, args.frames - 1):
+            src = oracle.synth_u32(SEED, rank * args.frames + i, 0, W, H, alpha_mode).view(np.uint8)
+            ey, eu, ev, ea, eha = oracle.import_yuva(src, W, H, "RGBA")
+            gy, gu, gv, ga, gha = pipe.device_planes(i)
+            ok &= bool((gy == ey).all() and (gu == eu).all() and (gv == ev).all() and (ga == ea).all() and gha == eha)
+        parity = "bit-exact vs oracle on frames 0 and %d" % (args.frames - 1) if ok else "MISMATCH"
+
+    # end to end through the drop-in entry point: pinned host sources -> picture.ImportRGBABatch -> pinned planes
+    e2e_steps = max(2, min(args.steps, 8))
+    pics = [picture.Picture(Width=W, Height=H) for _ in range(args.frames)]
+    srcs = [pipe.src_view(i) for i in range(args.frames)]
+    strides = [4 * W] * args.frames
+    s0 = ctx.copy_stats()
+    run_api = lambda: picture.ImportRGBABatch(pics, srcs, strides, "RGBA", ctx, chunk=16)  # noqa: E731
+    assert run_api() == 1
+    s1 = ctx.copy_stats()
+    te = timed_wall(D, run_api, e2e_steps, warm=1)
+    e2e_value = px_step / te / 1e6
+    tp = timed_wall(D, pipe.run, e2e_steps, warm=1)           # the bench-shaped twin, for comparison
+    tc = timed_wall(D, pipe.run_copies_only, e2e_steps, warm=1)  # the same copies with no kernel: this box's ceiling
+    h2d, d2h = s1["h2d_bytes"] - s0["h2d_bytes"], s1["d2h_bytes"] - s0["d2h_bytes"]
+    if rank == 0 and parity != "MISMATCH":
+        y, u, v, a, ha = pipe.planes(0)
+        gy, gu, gv, ga, gha = pipe.device_planes(0)
+        p0 = pics[0]
+        if not ((y == gy).all() and (u == gu).all() and (v == gv).all() and ha == gha and (p0.Y == gy).all()
+                and (p0.U == gu).all() and (p0.V == gv).all() and (p0.A is not None) == gha and (not gha or (p0.A == ga).all())):
+            parity = "MISMATCH (e2e)"
+    ceiling_gbs = world * (pipe.h2d_bytes + pipe.d2h_bytes) / tc / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload_config(args),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "Mpixel/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "api": "go_webp_b200.picture.ImportRGBABatch (drop-in batched entry point -> "
+                                           "b2_import_batch_staged; pinned sources, device-resident pictures with pinned mirrors)",
+                "pipeline_value": px_step / tp / 1e6, "pipeline_api": "pipeline.ImportPipeline.run (bench-shaped twin)",
+                "gbs": world * (h2d + d2h) / te / 1e9,
+                "ceiling_gbs": ceiling_gbs, "frac_of_ceiling": world * (h2d + d2h) / te / 1e9 / ceiling_gbs,
+                "ceiling": "the same H2D + D2H copies of this step with no kernel, all ranks at once (live; "
+                           "profiles/r02_pcie_ceiling.md has the bare-CUDA microbenchmark of the box)"},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "achieved": gbs_rank, "peak": peak, "unit": "GB/s",
+                     "frac": gbs_rank / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
+                     "kernel": "import_fast_kernel<RGBA,alpha>", "algorithmic_bytes_per_px": IMPORT_BYTES_PER_PX,
+                     "frac_of_8000_nominal": gbs_rank / 8000.0, "per": "GPU (rank 0 step time = max over ranks)"},
+        "parity": parity,
+    }
+    if sustained:
+        line["sustained"] = sustained
+    for pic in pics:
+        picture.WebPPictureFree(pic)
+    return line, pipe
 
 
 def other_kernels(ctx, peak, steps):
@@ -340,6 +640,16 @@ def other_kernels(ctx, peak, steps):
         out[name] = {"frames": 64, "mpixel_per_s": px / ms / 1e3, "bytes_per_px": bpp,
                      "gbs": px * bpp / ms / 1e6, "frac": px * bpp / ms / 1e6 / peak}
         ap.close()
+    from go_webp_b200.pipeline import PalettePipeline
+    for psize, bpp, name in [(256, 8.0, "vp8l_apply_palette_256_colours_8bit"), (16, 4.5, "vp8l_apply_palette_16_colours_4bit"),
+                             (4, 4.25, "vp8l_apply_palette_4_colours_2bit"), (2, 4.125, "vp8l_apply_palette_2_colours_1bit")]:
+        pp = PalettePipeline(ctx, 64, 4096, 4096, psize)   # colour -> packed index: 4 B/px in, 4 / 2^xbits out
+        pp.fill_synthetic(0xB2000003)
+        ms = timed(pp.run_device, k)
+        px = 64 * 4096 * 4096
+        out[name] = {"frames": 64, "mpixel_per_s": px / ms / 1e3, "bytes_per_px": bpp,
+                     "gbs": px * bpp / ms / 1e6, "frac": px * bpp / ms / 1e6 / peak}
+        pp.close()
     # the 8f-4 rows on 128 alpha / luma planes of 1080p (2 B/px; level smoothing 3: its level scan reads the plane too)
     n, st = 128, W
     src, dst = ctx.alloc(n * st * H), ctx.alloc(4 * n * st * H)
@@ -369,6 +679,63 @@ def other_kernels(ctx, peak, steps):
     return out
 
 
+def cpu_baseline_block(args, alpha_mode):
+    T = host_threads()
+    n_cpu = int(min(args.frames, max(2 * T, 64)))
+    # ~25 s of CPU work: passes over the sample for 1.5 s of wall time on all host threads
+    rate, dt = cpu_import_rate(n_cpu, T, alpha_mode, min_seconds=max(1.5, 24.0 / T))
+    rate1, _ = cpu_import_rate(4, 1, alpha_mode, min_seconds=1.0)
+    srate, _ = cpu_import_rate(n_cpu, T, alpha_mode, scalar=True, min_seconds=1.0)
+    srate1, _ = cpu_import_rate(4, 1, alpha_mode, scalar=True, min_seconds=1.0)
+    return {
+        "value": rate, "unit": "Mpixel/s", "cores": T, "kind": "port",
+        "sample": f"{n_cpu} of {args.frames} frames, one image per task, repeated for {dt:.2f} s wall "
+                  f"({dt * T:.0f} core-seconds) after one untimed pass",
+        "single_thread": rate1, "libwebp160_simd_all_threads": libwebp_import_rate(n_cpu, T, alpha_mode),
+        "scalar_no_vectorize_all_threads": srate, "scalar_no_vectorize_single_thread": srate1,
+        "note": "oracle/oracle.c (gcc -O2) restating the reference; scalar_no_vectorize_* is the same source built "
+                "-O2 -fno-tree-vectorize (the 'Go-equivalent scalar' figure of BASELINE.md 3); the Go reference does "
+                "not compile and no Go toolchain exists here: GOMAXPROCS n/a"}
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation of the path on the host cores.
+    The Go reference does not compile and no Go toolchain exists (DESIGN.md), so
+    this is the oracle port, with all host threads, on the same config/metric."""
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return 0
+    import oracle
+    oracle.build()
+    T = host_threads()
+    alpha_mode = ALPHA_MODES[args.alpha]
+    # bounded sample per step: sized from a probe so (K+W) steps take ~2 minutes at most
+    probe_frames = max(T, 8)
+    rate, dt = cpu_import_rate(probe_frames, T, alpha_mode)
+    budget = 100.0 / max(1, args.steps + args.warmup)
+    frames = int(min(args.frames, max(T, rate * 1e6 * min(budget, 4.0) / (W * H))))
+    for _ in range(args.warmup):
+        cpu_import_rate(frames, T, alpha_mode)
+    t = 0.0
+    for _ in range(args.steps):
+        t += cpu_import_rate(frames, T, alpha_mode)[1]
+    value = frames * W * H * args.steps / t / 1e6
+    sample = f"{frames} of {args.frames} 1080p frames per step, one image per task"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "Mpixel/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic", "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": "Mpixel/s", "cores": T, "kind": "port", "sample": sample,
+                         "note": "gcc -O2 C restatement of the reference (oracle/oracle.c); Go reference "
+                                 "cannot be built: GOMAXPROCS n/a"},
+        "e2e": {"value": value, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -377,130 +744,24 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=256)
     ap.add_argument("--alpha", default="sparse", choices=sorted(ALPHA_MODES))
-    ap.add_argument("--no-extras", action="store_true", help="skip other kernels / cpu baseline")
+    ap.add_argument("--config", type=int, default=1, choices=[1, 2, 3, 4],
+                    help="BASELINE.json configs[k] as the headline of the line (default 1)")
+    ap.add_argument("--no-extras", action="store_true", help="skip other kernels / other configs / cpu baseline")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)  # timing rule: W >= 3
     if args.impl == "reference":
         return run_reference(args)
 
-    rank, world, local = dist_env()
-    import torch
-    import torch.distributed as dist
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    from go_webp_b200 import _abi
+    D = Dist()
     from go_webp_b200.device import Context
-    from go_webp_b200.pipeline import ImportPipeline
-
     peak, peak_src = hbm_peak()
-    ctx = Context(local, n_streams=4)
-    alpha_mode = ALPHA_MODES[args.alpha]
-    pipe = ImportPipeline(ctx, args.frames, W, H, "RGBA", import_alpha=True, chunk=16, host=True)
-    pipe.fill_synthetic(SEED, first_img=rank * args.frames, alpha_mode=alpha_mode, to_host=True)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    sampler = ClockSampler(local)
+    ctx = Context(D.local, n_streams=4)
+    sampler = ClockSampler(D.local)
     sampler.start()
-    t_load0 = time.perf_counter()
-    for _ in range(args.warmup):
-        pipe.run_device()
-    barrier()
-    launches0 = ctx.launches
-    t0 = time.perf_counter()
-    ctx.event_record(0)
-    for _ in range(args.steps):
-        pipe.run_device()
-    ctx.event_record(1)
-    barrier()
-    t1 = time.perf_counter()
-    launches = ctx.launches - launches0
-    ms = ctx.elapsed_ms(0, 1)
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    extra = None
-    if sampler.count_between(t_load0, t1) < 3:   # keep the same kernel running (untimed) until the sampler has seen it
-        e0 = time.perf_counter()
-        while time.perf_counter() - e0 < 0.5:
-            for _ in range(10):
-                pipe.run_device()
-            ctx.sync()
-        extra = (e0, time.perf_counter())
-    clocks = sampler.summary(t0, t1, t_load0, extra)
-    px_step = world * args.frames * W * H
-    ms_step = ms / args.steps
-    value = px_step / ms_step / 1e3  # Mpixel/s
-    gbs_rank = args.frames * W * H * IMPORT_BYTES_PER_PX / ms_step / 1e6
-
-    # parity spot check against the oracle (outside every timed region)
-    parity = "skipped"
-    if rank == 0:
-        import oracle
-        oracle.build()
-        ok = True
-        for i in (0, args.frames - 1):
-            src = oracle.synth_u32(SEED, rank * args.frames + i, 0, W, H, alpha_mode).view(np.uint8)
-            ey, eu, ev, ea, eha = oracle.import_yuva(src, W, H, "RGBA")
-            gy, gu, gv, ga, gha = pipe.device_planes(i)
-            ok &= bool((gy == ey).all() and (gu == eu).all() and (gv == ev).all() and (ga == ea).all() and gha == eha)
-        parity = "bit-exact vs oracle on frames 0 and %d" % (args.frames - 1) if ok else "MISMATCH"
-
-    # end to end: pinned host -> device -> kernel -> pinned host, every step
-    e2e_steps = max(2, min(args.steps, 8))
-    pipe.run()
-    barrier()
-    te0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        pipe.run()
-    barrier()
-    te = time.perf_counter() - te0
-    if world > 1:
-        t = torch.tensor([te], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        te = float(t.item())
-    e2e_value = px_step * e2e_steps / te / 1e6
-    if rank == 0 and parity != "MISMATCH":
-        y, u, v, a, ha = pipe.planes(0)
-        gy, gu, gv, ga, gha = pipe.device_planes(0)
-        if not ((y == gy).all() and (u == gu).all() and (v == gv).all() and ha == gha):
-            parity = "MISMATCH (e2e)"
-    sampler.stop_flag = True
-
-    line = {
-        "metric": METRIC, "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload_config(args),
-        "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "Mpixel/s", "h2d_bytes_per_step": pipe.h2d_bytes,
-                "d2h_bytes_per_step": pipe.d2h_bytes, "steps": e2e_steps,
-                "api": "go_webp_b200.pipeline.ImportPipeline.run (pinned host buffers, 4 streams)"},
-        "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "achieved": gbs_rank, "peak": peak, "unit": "GB/s",
-                     "frac": gbs_rank / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
-                     "kernel": "import_kernel<RGBA,alpha>", "algorithmic_bytes_per_px": IMPORT_BYTES_PER_PX,
-                     "frac_of_8000_nominal": gbs_rank / 8000.0, "per": "GPU (rank 0 step time = max over ranks)"},
-        "parity": parity,
-    }
-    if rank == 0 and world == 1 and not args.no_extras:
-        T = host_threads()
-        n_cpu = int(min(args.frames, max(2 * T, 64)))
-        # ~25 s of CPU work: passes over the sample for 1.5 s of wall time on all host threads
-        rate, dt = cpu_import_rate(n_cpu, T, alpha_mode, min_seconds=max(1.5, 24.0 / T))
-        rate1, _ = cpu_import_rate(4, 1, alpha_mode, min_seconds=1.0)
-        line["cpu_baseline"] = {
-            "value": rate, "unit": "Mpixel/s", "cores": T, "kind": "port",
-            "sample": f"{n_cpu} of {args.frames} frames, one image per task, repeated for {dt:.2f} s wall "
-                      f"({dt * T:.0f} core-seconds) after one untimed pass",
-            "single_thread": rate1, "libwebp160_simd_all_threads": libwebp_import_rate(n_cpu, T, alpha_mode),
-            "note": "oracle/oracle.c (gcc -O2) restating the reference; the Go reference does not compile "
-                    "and no Go toolchain exists here: GOMAXPROCS n/a"}
+    line, pipe = config1_import(ctx, D, args, peak, peak_src, sampler)
+    alpha_mode = ALPHA_MODES[args.alpha]
+    if D.rank == 0 and D.world == 1 and not args.no_extras:
+        line["cpu_baseline"] = cpu_baseline_block(args, alpha_mode)
         alpha_mixes = {}
         for name, am in ALPHA_MODES.items():
             pipe.fill_synthetic(SEED, first_img=0, alpha_mode=am)
@@ -516,13 +777,31 @@ def main():
             alpha_mixes[name] = {"mpixel_per_s": args.frames * W * H / m / 1e3,
                                  "frac": args.frames * W * H * IMPORT_BYTES_PER_PX / m / 1e6 / peak}
         line["alpha_mixes"] = alpha_mixes
-        pipe.close()
-        line["other_kernels"] = other_kernels(ctx, peak, args.steps)
-    if rank == 0:
+    pipe.close()
+    sampler.stop_flag = True
+    if not args.no_extras:
+        others = {}
+        for name, fn in (("configs[3]", config3_upsample), ("configs[2]", config2_vp8l), ("configs[4]", config4_mixed)):
+            try:
+                others[name] = fn(ctx, D, peak, args.steps)
+            except Exception as e:   # a failed side config must not take the headline down
+                others[name] = {"error": repr(e)[:300]}
+                D.barrier()
+        line["other_configs"] = others
+        k = f"configs[{args.config}]"
+        if args.config != 1 and "error" not in others.get(k, {"error": 1}):
+            o = others[k]
+            line["headline_config"] = k
+            line["configs[1]"] = {key: line[key] for key in ("value", "ms_per_step", "e2e", "roofline", "config", "scaling")}
+            line.update({"value": o["value"], "ms_per_step": o["ms_per_step"], "scaling": o["scaling"],
+                         "config": {"workload": o["workload"]}, "roofline": o["roofline"]})
+            if "e2e" in o:
+                line["e2e"] = o["e2e"]
+        if D.rank == 0 and D.world == 1:
+            line["other_kernels"] = other_kernels(ctx, peak, args.steps)
+    if D.rank == 0:
         print(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    D.close()
     return 0
 
 

@@ -98,6 +98,12 @@ class RescaleJob(C.Structure):
                 ("num_channels", C.c_int32), ("reserved", C.c_int32)]
 
 
+class PaletteJob(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("palette", C.c_void_p), ("src_stride", C.c_int32),
+                ("dst_stride", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("palette_size", C.c_int32),
+                ("xbits", C.c_int32)]
+
+
 class ImportHost(C.Structure):
     _fields_ = [("src", C.c_void_p), ("y", C.c_void_p), ("u", C.c_void_p), ("v", C.c_void_p), ("a", C.c_void_p),
                 ("y_stride", C.c_int32), ("uv_stride", C.c_int32), ("a_stride", C.c_int32), ("reserved", C.c_int32)]
@@ -164,6 +170,7 @@ SYMBOLS = {
     "b2_vp8l_forward_chain": (C.c_int, [_ctx, C.c_int, C.POINTER(ArgbJob), C.c_int]),
     "b2_vp8l_color_index_inverse": (C.c_int, [_ctx, C.c_int, C.POINTER(ArgbJob), C.c_int]),
     "b2_vp8l_bundle_color_map": (C.c_int, [_ctx, C.c_int, C.POINTER(ArgbJob), C.c_int]),
+    "b2_vp8l_apply_palette": (C.c_int, [_ctx, C.c_int, C.POINTER(PaletteJob), C.c_int]),
     "b2_vp8l_predictor_inverse": (C.c_int, [_ctx, C.c_int, C.POINTER(ArgbJob), C.c_int]),
     "b2_vp8l_predictor_forward": (C.c_int, [_ctx, C.c_int, C.POINTER(ArgbJob), C.c_int]),
     "b2_vp8l_convert_from_bgra": (C.c_int, [_ctx, C.c_int, C.POINTER(ConvertJob), C.c_int, C.c_int, C.c_int]),

@@ -116,6 +116,7 @@ extern "C" int b2_import_batch_staged(b2_ctx* ctx, const b2_import_job* jobs, co
   const int ns = ctx->n_streams;
   const int bpp = bytes_per_pixel(order);
   const int n_chunks = (n_jobs + chunk - 1) / chunk;
+  const int lag = ns < B2_STAGED_EVENTS ? ns : B2_STAGED_EVENTS;   // a multiple of ns keeps a chunk's waves on one stream
   CopyList cl;
   // second wave of one chunk: its flags are on the host -> copy back the alpha planes of
   // the pictures that turned out to have alpha (conversions.go:56-58 drops the others)
@@ -134,7 +135,9 @@ extern "C" int b2_import_batch_staged(b2_ctx* ctx, const b2_import_job* jobs, co
   for (int k = 0; k < n_chunks; ++k) {
     const int s = k % ns;
     const int c0 = k * chunk, c1 = (c0 + chunk < n_jobs) ? c0 + chunk : n_jobs, m = c1 - c0;
-    if (k >= B2_STAGED_EVENTS && (st = finish(k - B2_STAGED_EVENTS)) != B2_OK) return st;
+    // the alpha planes of chunk k - lag go out BEFORE this chunk's work is queued behind them on the
+    // same stream: the host stays 'lag' chunks ahead of the device, the D2H engine never idles
+    if (k >= lag && (st = finish(k - lag)) != B2_OK) return st;
     for (int i = c0; i < c1; ++i) {
       const b2_import_job& j = jobs[i];
       if (host[i].src != NULL) {
@@ -148,6 +151,7 @@ extern "C" int b2_import_batch_staged(b2_ctx* ctx, const b2_import_job* jobs, co
     else st = b2_rgba_to_yuv420a(ctx, s, jobs + c0, m, order, flags, ctx->flags_dev + c0);
     if (st != B2_OK) return st;
     B2_CUDA(ctx, cudaMemcpyAsync(ctx->flags_host + c0, ctx->flags_dev + c0, sizeof(int32_t) * m, cudaMemcpyDeviceToHost, ctx->streams[s]));
+    ctx->d2h_calls++; ctx->d2h_bytes += sizeof(int32_t) * m;
     B2_CUDA(ctx, cudaEventRecord(ctx->staged_ev[k % B2_STAGED_EVENTS], ctx->streams[s]));
     for (int i = c0; i < c1; ++i) {
       const b2_import_job& j = jobs[i];
@@ -161,7 +165,7 @@ extern "C" int b2_import_batch_staged(b2_ctx* ctx, const b2_import_job* jobs, co
     }
     if ((st = cl.issue(ctx, s, cudaMemcpyDeviceToHost)) != B2_OK) return st;
   }
-  for (int k = (n_chunks > B2_STAGED_EVENTS ? n_chunks - B2_STAGED_EVENTS : 0); k < n_chunks; ++k) {
+  for (int k = (n_chunks > lag ? n_chunks - lag : 0); k < n_chunks; ++k) {
     if ((st = finish(k)) != B2_OK) return st;
   }
   for (int i = 0; i < ns; ++i) B2_CUDA(ctx, cudaStreamSynchronize(ctx->streams[i]));

@@ -95,6 +95,12 @@ class Context:
     def launches(self) -> int:
         return int(self.lib.b2_launch_count(self.h))
 
+    def copy_stats(self) -> dict:
+        """Copies issued through this context so far (calls and bytes per direction)."""
+        out = (C.c_uint64 * 4)()
+        self._chk(self.lib.b2_copy_stats(self.h, out))
+        return {"h2d_calls": int(out[0]), "h2d_bytes": int(out[1]), "d2h_calls": int(out[2]), "d2h_bytes": int(out[3])}
+
     def alloc(self, nbytes: int) -> DevBuf:
         return DevBuf(self, nbytes)
 

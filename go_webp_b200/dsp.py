@@ -45,13 +45,15 @@ class VP8LImage:
     height: int
 
 
-def _run(op: str, items, ctx: Context | None = None, chunk: int = 8):
+def _run(op: str, items, ctx: Context | None = None, chunk: int = 4):
     """items: list of (src u32/u8 array, out_shape, data array or None, width, height, bits).
-    Returns the list of uint32 outputs.  Chunks are pipelined over the streams."""
+    Returns the list of uint32 outputs.  One b2_vp8l_batch_staged call: chunks are pipelined
+    over the streams (H2D, kernel and D2H of different chunks overlap)."""
     ctx = ctx or default_context()
     n = len(items)
-    need = 0
-    metas = []
+    if n == 0:
+        return []
+    metas, need = [], 0
     for (src, oshape, data, w, h, bits) in items:
         src = np.ascontiguousarray(src)
         data = None if data is None else np.ascontiguousarray(data, np.uint32)
@@ -61,28 +63,21 @@ def _run(op: str, items, ctx: Context | None = None, chunk: int = 8):
         need += sum(sz)
     ar = _arena(ctx)
     ar.reset(need)
-    lib, hnd, ns = ctx.lib, ctx.h, ctx.n_streams
-    fn = getattr(lib, "b2_vp8l_" + op)
-    outs, jobs, ptrs = [], [], []
-    for (src, data, ob, sz), (_, oshape, _, w, h, bits) in zip(metas, items):
-        ps, pd = ar.take(sz[0]), ar.take(sz[1])
-        pt = ar.take(sz[2]) if sz[2] else None
-        ptrs.append((ps, pd, pt))
-        jobs.append(_abi.ArgbJob(ps, pd, pt, w, h, bits, 0))
-        outs.append(np.empty(oshape, np.uint32))
-    for c0 in range(0, n, chunk):
-        c1 = min(n, c0 + chunk)
-        s = (c0 // chunk) % ns
-        for i in range(c0, c1):
-            src, data, ob, sz = metas[i]
-            ctx._chk(lib.b2_h2d_async(hnd, s, ptrs[i][0], src.ctypes.data, src.nbytes))
-            if data is not None:
-                ctx._chk(lib.b2_h2d_async(hnd, s, ptrs[i][2], data.ctypes.data, data.nbytes))
-        arr = (_abi.ArgbJob * (c1 - c0))(*jobs[c0:c1])
-        ctx._chk(fn(hnd, s, arr, c1 - c0))
-        for i in range(c0, c1):
-            ctx._chk(lib.b2_d2h_async(hnd, s, outs[i].ctypes.data, ptrs[i][1], metas[i][2]))
-    ctx.sync()
+    jobs = (_abi.ArgbJob * n)()
+    hosts = (_abi.ArgbHost * n)()
+    outs = []
+    for i, ((src, data, ob, sz), (_, oshape, _, w, h, bits)) in enumerate(zip(metas, items)):
+        j, hh = jobs[i], hosts[i]
+        j.src, j.dst = ar.take(sz[0]), ar.take(sz[1])
+        j.data = ar.take(sz[2]) if sz[2] else None
+        j.width, j.height, j.bits = w, h, bits
+        o = np.empty(oshape, np.uint32)
+        outs.append(o)
+        hh.src, hh.src_bytes = src.ctypes.data, src.nbytes
+        hh.dst, hh.dst_bytes = o.ctypes.data, ob
+        if data is not None:
+            hh.data, hh.data_bytes = data.ctypes.data, data.nbytes
+    ctx._chk(ctx.lib.b2_vp8l_batch_staged(ctx.h, _abi.VP8L_OPS[op], jobs, hosts, n, chunk))
     return outs
 
 
@@ -361,6 +356,58 @@ def VP8LBundleColorMap(row: np.ndarray, width: int, xbits: int) -> np.ndarray:
     return _run("bundle_color_map", [(idx, (h, ow), None, width, h, xbits)])[0]
 
 
+def PaletteXBits(palette_size: int) -> int:
+    """MapImageFromPalette's packing rule (pkg/vp8/vp8l_encoder.go:1229-1233)."""
+    if palette_size <= 4:
+        return 3 if palette_size <= 2 else 2
+    return 1 if palette_size <= 16 else 0
+
+
+def ApplyPaletteBatch(items, ctx: Context | None = None):
+    """Added batched form of ApplyPalette: items = [(src [h, w] uint32, palette, xbits), ...];
+    returns the packed index images ([h, ceil(w / 2^xbits)] uint32).  One launch per xbits
+    value present; lookup and VP8LBundleColorMap are one pass on the device."""
+    ctx = ctx or default_context()
+    n = len(items)
+    if n == 0:
+        return []
+    metas, need = [], 0
+    for (src, palette, xbits) in items:
+        src = np.ascontiguousarray(src, np.uint32)
+        pal = np.ascontiguousarray(palette, np.uint32).reshape(-1)
+        h, w = src.shape
+        ow = VP8LSubSampleSize(w, xbits)
+        metas.append((src, pal, h, w, ow))
+        need += _al(src.nbytes) + _al(4 * ow * h) + _al(pal.nbytes)
+    ar = _arena(ctx)
+    ar.reset(need)
+    jobs = (_abi.PaletteJob * n)()
+    outs, dptr = [], []
+    for i, ((src, pal, h, w, ow), (_, _, xbits)) in enumerate(zip(metas, items)):
+        j = jobs[i]
+        j.src, j.dst, j.palette = ar.take(src.nbytes), ar.take(4 * ow * h), ar.take(pal.nbytes)
+        j.src_stride, j.dst_stride, j.width, j.height, j.palette_size, j.xbits = w, ow, w, h, pal.size, xbits
+        ctx._chk(ctx.lib.b2_h2d_async(ctx.h, 0, j.src, src.ctypes.data, src.nbytes))
+        ctx._chk(ctx.lib.b2_h2d_async(ctx.h, 0, j.palette, pal.ctypes.data, pal.nbytes))
+        outs.append(np.empty((h, ow), np.uint32))
+        dptr.append(j.dst)
+    ctx._chk(ctx.lib.b2_vp8l_apply_palette(ctx.h, 0, jobs, n))
+    for o, p in zip(outs, dptr):
+        ctx._chk(ctx.lib.b2_d2h_async(ctx.h, 0, o.ctypes.data, p, o.nbytes))
+    ctx.sync()
+    return outs
+
+
+def ApplyPalette(src: np.ndarray, src_stride: int, palette: np.ndarray, palette_size: int, width: int, height: int,
+                 xbits: int) -> np.ndarray:
+    """ApplyPalette (pkg/vp8/vp8l_encoder.go:1149-1212): src = ARGB rows src_stride pixels apart;
+    returns dst ([height, VP8LSubSampleSize(width, xbits)] uint32, the packed palette indices)."""
+    rows = np.ascontiguousarray(src, np.uint32).reshape(-1)[:src_stride * (height - 1) + width]
+    img = np.lib.stride_tricks.as_strided(rows, (height, width), (4 * src_stride, 4))
+    pal = np.ascontiguousarray(palette, np.uint32).reshape(-1)[:palette_size]
+    return ApplyPaletteBatch([(img, pal, xbits)])[0]
+
+
 def VP8LInverseTransform(transform: VP8LTransform, row_start: int, row_end: int, in_rows: np.ndarray) -> np.ndarray:
     """lossless.go:511-547 for rows [row_start,row_end) of one transform; 'in_rows'
     holds exactly those rows.  Out-of-place (the in-place colour-index trick of
@@ -395,50 +442,79 @@ def VP8LInverseTransform(transform: VP8LTransform, row_start: int, row_end: int,
     raise ValueError("unknown transform type")
 
 
-def VP8LInverseTransformBatch(imgs, chain, ctx: Context | None = None):
+def _plan_chain(c):
+    """ApplyInverseTransforms order (vp8l_dec.c.go:710-729): last read, first applied; a
+    cross-colour transform directly followed by add-green becomes the fused kernel."""
+    steps, k, c = [], 0, list(c)
+    while k < len(c):
+        t = c[-1 - k]
+        nxt = c[-2 - k] if k + 1 < len(c) else None
+        if t.vtype == CROSS_COLOR_TRANSFORM and nxt is not None and nxt.vtype == SUBTRACT_GREEN_TRANSFORM:
+            steps.append(("inverse_chain", t))
+            k += 2
+            continue
+        op = {CROSS_COLOR_TRANSFORM: "color_inverse", SUBTRACT_GREEN_TRANSFORM: "add_green",
+              COLOR_INDEXING_TRANSFORM: "color_index_inverse", PREDICTOR_TRANSFORM: "predictor_inverse"}.get(t.vtype)
+        if op is None:
+            raise ValueError("unknown transform type")
+        steps.append((op, t))
+        k += 1
+    return steps
+
+
+def VP8LInverseTransformBatch(imgs, chain, ctx: Context | None = None, chunk: int = 4):
     """Added batched entry point for part 3 (SURVEY 8b).  imgs: list[VP8LImage];
     chain: list (per image) of the transforms in READ order (ReadTransform,
     vp8l_dec.c.go:1221-1269); they are applied last-read-first exactly like
     ApplyInverseTransforms (vp8l_dec.c.go:710-729).  A cross-colour transform
-    directly followed by add-green is run as the fused single-pass kernel."""
+    directly followed by add-green is run as the fused single-pass kernel.  The pixels
+    cross PCIe twice, whatever the length of the chain: decoded pixels up with the first
+    step, final pixels down with the last; everything in between stays on the device
+    (two ping-pong buffers per image)."""
     ctx = ctx or default_context()
+    n = len(imgs)
     cur = [np.ascontiguousarray(im.pixels, np.uint32) for im in imgs]
-    chain = [list(c) for c in chain]
-    depth = max((len(c) for c in chain), default=0)
-    # step k applies chain[i][-1-k]; group images by the op of this step
+    plans = [_plan_chain(c) for c in chain]
+    if n == 0:
+        return cur
+    sizes, need = [], 0
+    for im, src, plan in zip(imgs, cur, plans):
+        full = max([4 * t.xsize * t.ysize for _, t in plan] + [src.nbytes])
+        dsz = [_al(np.asarray(t.data).size * 4) if t.data is not None else 0 for _, t in plan]
+        sizes.append((_al(full), dsz))
+        need += 2 * _al(full) + sum(dsz)
+    ar = _arena(ctx)
+    ar.reset(need)
+    bufs, dptr, hdata = [], [], []
+    for (full, dsz), plan in zip(sizes, plans):
+        bufs.append([ar.take(full), ar.take(full)])
+        dptr.append([ar.take(z) if z else None for z in dsz])
+        hdata.append([np.ascontiguousarray(t.data, np.uint32) if t.data is not None else None for _, t in plan])
+    outs = list(cur)
+    depth = max((len(p) for p in plans), default=0)
     for k in range(depth):
         groups: dict[str, list] = {}
-        for i, c in enumerate(chain):
-            if k >= len(c) or c[-1 - k] is None:
-                continue
-            t = c[-1 - k]
-            if t.vtype == CROSS_COLOR_TRANSFORM and k + 1 < len(c) and c[-2 - k] is not None \
-                    and c[-2 - k].vtype == SUBTRACT_GREEN_TRANSFORM:
-                groups.setdefault("inverse_chain", []).append((i, t))
-                c[-2 - k] = None  # consumed by the fused kernel
-            elif t.vtype == CROSS_COLOR_TRANSFORM:
-                groups.setdefault("color_inverse", []).append((i, t))
-            elif t.vtype == SUBTRACT_GREEN_TRANSFORM:
-                groups.setdefault("add_green", []).append((i, t))
-            elif t.vtype == COLOR_INDEXING_TRANSFORM:
-                groups.setdefault("color_index_inverse", []).append((i, t))
-            elif t.vtype == PREDICTOR_TRANSFORM:
-                groups.setdefault("predictor_inverse", []).append((i, t))
-            else:
-                raise ValueError("unknown transform type")
+        for i, plan in enumerate(plans):
+            if k < len(plan):
+                groups.setdefault(plan[k][0], []).append(i)
         for op, members in groups.items():
-            items = []
-            for i, t in members:
-                w, h = t.xsize, t.ysize
-                if op == "color_index_inverse":
-                    sw = VP8LSubSampleSize(w, t.bits)
-                    items.append((cur[i].reshape(h, sw), (h, w), t.data, w, h, t.bits))
-                else:
-                    items.append((cur[i].reshape(h, w), (h, w), t.data, w, h, t.bits))
-            outs = _run(op, items, ctx)
-            for (i, _), o in zip(members, outs):
-                cur[i] = o
-    return cur
+            m = len(members)
+            jobs = (_abi.ArgbJob * m)()
+            hosts = (_abi.ArgbHost * m)()
+            for q, i in enumerate(members):
+                t = plans[i][k][1]
+                j, hh = jobs[q], hosts[q]
+                j.src, j.dst, j.data = bufs[i][k & 1], bufs[i][(k + 1) & 1], dptr[i][k]
+                j.width, j.height, j.bits = t.xsize, t.ysize, t.bits
+                if k == 0:
+                    hh.src, hh.src_bytes = cur[i].ctypes.data, cur[i].nbytes
+                if hdata[i][k] is not None:
+                    hh.data, hh.data_bytes = hdata[i][k].ctypes.data, hdata[i][k].nbytes
+                if k == len(plans[i]) - 1:
+                    outs[i] = np.empty((t.ysize, t.xsize), np.uint32)
+                    hh.dst, hh.dst_bytes = outs[i].ctypes.data, outs[i].nbytes
+            ctx._chk(ctx.lib.b2_vp8l_batch_staged(ctx.h, _abi.VP8L_OPS[op], jobs, hosts, m, chunk))
+    return outs
 
 
 # ---- fancy upsampler line-pair table ----------------------------------------------

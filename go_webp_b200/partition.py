@@ -42,3 +42,26 @@ def import_cost_bytes(w: int, h: int, with_alpha: bool = True) -> int:
 
 def upsample_cost_bytes(w: int, h: int, with_alpha: bool = False, bpp: int = 4) -> int:
     return w * h + 2 * ((w + 1) // 2) * ((h + 1) // 2) + bpp * w * h + (w * h if with_alpha else 0)
+
+
+def size_class(w: int, h: int) -> str:
+    """Class of an image for the calibrated cost model of mixed-size batches: the kernels' rate depends
+    on the row alignment (16-byte rows take the vector paths, odd widths the general strips) and on how
+    many full strips a row holds (narrow rows are mostly edge handling)."""
+    al = "w16" if w % 16 == 0 else ("w4" if w % 4 == 0 else ("w2" if w % 2 == 0 else "w1"))
+    sz = "narrow" if w < 512 else ("mid" if w < 2048 else "wide")
+    return al + "/" + sz
+
+
+def full_pipeline_cost_bytes(w: int, h: int) -> int:
+    """import + fancy upsample with alpha plane + 8 B/px ARGB chain (configs[4])."""
+    return import_cost_bytes(w, h) + upsample_cost_bytes(w, h, True) + 8 * w * h
+
+
+def calibrated_costs(sizes, rates: dict, cost_bytes=full_pipeline_cost_bytes):
+    """Per-image cost in TIME: algorithmic bytes / measured rate of the image's class (rates: class ->
+    bytes per millisecond from one warm-up pass).  Classes without a measurement (or a zero one) fall
+    back to the mean rate, so the model degrades to the byte model, never to nonsense."""
+    good = [r for r in rates.values() if r > 0]
+    mean = sum(good) / len(good) if good else 1.0
+    return [cost_bytes(w, h) / (rates.get(size_class(w, h), 0.0) or mean) for (w, h) in sizes]

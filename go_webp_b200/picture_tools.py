@@ -14,9 +14,55 @@ from .picture import (ENC_ERROR_OUT_OF_MEMORY, WEBP_CSP_ALPHA_BIT, Picture, _al,
                       _STATUS_TO_ENC, default_context)
 
 
-def _run(pics, op: str, arg: int = 0, ctx: Context | None = None):
+def _launch(ctx, op, arr, n, use_argb, arg):
+    lib, hnd = ctx.lib, ctx.h
+    if op == "cleanup":
+        ctx._chk(lib.b2_picture_cleanup_transparent(hnd, 0, arr, n, int(use_argb)))
+    elif op == "blend":
+        ctx._chk(lib.b2_picture_blend_alpha(hnd, 0, arr, n, int(use_argb), arg & 0xffffffff))
+    else:
+        ctx._chk(lib.b2_picture_replace_transparent(hnd, 0, arr, n, arg & 0xffffffff))
+
+
+def _run_resident(pics, op: str, arg: int, ctx: Context, download: bool):
+    """Pictures whose planes already live on the device (ImportRGBABatch, YUVAToARGBBatch):
+    the operation runs in place on the device planes; nothing is uploaded, and the result
+    comes back (one copy per picture) only when download is set."""
+    lib, hnd = ctx.lib, ctx.h
+    for use_argb in (False, True):
+        sel = [p for p in pics if bool(p.UseARGB) == use_argb]
+        if not sel:
+            continue
+        jobs = (_abi.PictureJob * len(sel))()
+        for j, pic in zip(jobs, sel):
+            if use_argb:
+                m = pic.memory_argb_
+                j.argb, j.argb_stride, j.width, j.height = m.dev("argb"), m.stride, m.w, m.h
+            else:
+                m = pic.memory_
+                j.y, j.u, j.v, j.a = m.dev("y"), m.dev("u"), m.dev("v"), m.dev("a")
+                j.y_stride, j.uv_stride, j.a_stride, j.width, j.height = m.ys, m.uvs, m.ys, m.w, m.h
+        _launch(ctx, op, jobs, len(sel), use_argb, arg)
+        for k, pic in enumerate(sel):
+            m = pic.memory_argb_ if use_argb else pic.memory_
+            m.host_valid = False
+            if download:
+                ctx._chk(lib.b2_d2h_async(hnd, 0, m.block.pin.ptr + m.off,
+                                          m.block.dev.ptr + m.off, m.nbytes))
+                m.host_valid = True
+    ctx.sync()
+
+
+def _run(pics, op: str, arg: int = 0, ctx: Context | None = None, download: bool = True):
     ctx = ctx or default_context()
     lib, hnd = ctx.lib, ctx.h
+    res = [p for p in pics if p.resident("argb" if p.UseARGB else "yuva")
+           and (p.memory_argb_ if p.UseARGB else p.memory_).block.ctx is ctx]
+    if res:
+        _run_resident(res, op, arg, ctx, download)
+        pics = [p for p in pics if not any(p is r for r in res)]
+        if not pics:
+            return
     metas, need = [], 0
     for pic in pics:
         w, h = pic.Width, pic.Height
@@ -54,12 +100,7 @@ def _run(pics, op: str, arg: int = 0, ctx: Context | None = None):
                     ctx._chk(lib.b2_h2d_2d_async(hnd, 0, p[key], stride, arr.ctypes.data, arr.shape[1], ww, hh))
                 jobs.append(_abi.PictureJob(p["y"], p["u"], p["v"], p["a"], None, s0, s1, s0, 0, w, h))
         arr = (_abi.PictureJob * len(jobs))(*jobs)
-        if op == "cleanup":
-            ctx._chk(lib.b2_picture_cleanup_transparent(hnd, 0, arr, len(jobs), int(use_argb)))
-        elif op == "blend":
-            ctx._chk(lib.b2_picture_blend_alpha(hnd, 0, arr, len(jobs), int(use_argb), arg & 0xffffffff))
-        else:
-            ctx._chk(lib.b2_picture_replace_transparent(hnd, 0, arr, len(jobs), arg & 0xffffffff))
+        _launch(ctx, op, arr, len(jobs), use_argb, arg)
         for i, p in zip(idx, ptrs):
             _, w, h, s0, s1, uvdim, sz = metas[i]
             pic = pics[i]
@@ -79,21 +120,23 @@ def _run(pics, op: str, arg: int = 0, ctx: Context | None = None):
     ctx.sync()
 
 
-def _guarded(pics, op, arg, ctx):
+def _guarded(pics, op, arg, ctx, download=True):
     try:
-        _run(pics, op, arg, ctx)
+        _run(pics, op, arg, ctx, download)
     except B2Error as e:
         for pic in pics:
             pic.SetEncodingError(_STATUS_TO_ENC.get(e.status, ENC_ERROR_OUT_OF_MEMORY))
 
 
-def WebPCleanupTransparentAreaBatch(pics, ctx: Context | None = None) -> None:
+def WebPCleanupTransparentAreaBatch(pics, ctx: Context | None = None, download: bool = True) -> None:
     """Added batched entry point.  picture_tools_enc.c.go:110-183: pictures without the
-    planes the function needs are left alone (:142-144)."""
+    planes the function needs are left alone (:142-144).  Device-resident pictures are
+    processed where they lie (webp_encoding.go:49-72: import -> cleanup without a round trip);
+    download=False leaves the result on the device for the next call."""
     todo = [p for p in pics if p is not None and
-            (p.ARGB is not None if p.UseARGB else all(x is not None for x in (p.Y, p.U, p.V, p.A)))]
+            (p._ARGB is not None if p.UseARGB else all(x is not None for x in (p._Y, p._U, p._V, p._A)))]
     if todo:
-        _guarded(todo, "cleanup", 0, ctx)
+        _guarded(todo, "cleanup", 0, ctx, download)
 
 
 def WebPCleanupTransparentArea(pic: Picture) -> None:
@@ -102,7 +145,7 @@ def WebPCleanupTransparentArea(pic: Picture) -> None:
         WebPCleanupTransparentAreaBatch([pic])
 
 
-def WebPBlendAlphaBatch(pics, background_rgb: int, ctx: Context | None = None) -> None:
+def WebPBlendAlphaBatch(pics, background_rgb: int, ctx: Context | None = None, download: bool = True) -> None:
     """Added batched entry point.  picture_tools_enc.c.go:199-276: a YUV picture without
     alpha (colour space bit or plane) has nothing to blend (:218-219); afterwards every
     alpha value is 0xff."""
@@ -111,12 +154,12 @@ def WebPBlendAlphaBatch(pics, background_rgb: int, ctx: Context | None = None) -
         if p is None:
             continue
         if p.UseARGB:
-            if p.ARGB is not None:
+            if p._ARGB is not None:
                 todo.append(p)
-        elif (p.ColorSpace & WEBP_CSP_ALPHA_BIT) and p.A is not None:
+        elif (p.ColorSpace & WEBP_CSP_ALPHA_BIT) and p._A is not None:
             todo.append(p)
     if todo:
-        _guarded(todo, "blend", background_rgb, ctx)
+        _guarded(todo, "blend", background_rgb, ctx, download)
 
 
 def WebPBlendAlpha(pic: Picture, background_rgb: int) -> None:
@@ -125,11 +168,11 @@ def WebPBlendAlpha(pic: Picture, background_rgb: int) -> None:
         WebPBlendAlphaBatch([pic], background_rgb)
 
 
-def WebPReplaceTransparentPixelsBatch(pics, color: int, ctx: Context | None = None) -> None:
+def WebPReplaceTransparentPixelsBatch(pics, color: int, ctx: Context | None = None, download: bool = True) -> None:
     """Added batched entry point.  picture_tools_enc.c.go:95-108: ARGB pictures only."""
-    todo = [p for p in pics if p is not None and p.UseARGB and p.ARGB is not None]
+    todo = [p for p in pics if p is not None and p.UseARGB and p._ARGB is not None]
     if todo:
-        _guarded(todo, "replace", color, ctx)
+        _guarded(todo, "replace", color, ctx, download)
 
 
 def WebPReplaceTransparentPixels(pic: Picture, color: int) -> None:

@@ -114,6 +114,21 @@ class ImportPipeline:
             c._chk(lib.b2_d2h_async(hnd, s, self.p_flags.ptr + 4 * c0, self.d_flags.ptr + 4 * c0, 4 * m))
         c.sync()
 
+    def run_copies_only(self):
+        """The H2D and D2H copies of run() without the kernel: what the box's PCIe / host path
+        gives this traffic mix (bench.py reports it as the end-to-end ceiling)."""
+        c, lib, hnd = self.ctx, self.ctx.lib, self.ctx.h
+        ns = c.n_streams
+        for k, c0 in enumerate(range(0, self.n, self.chunk)):
+            m = min(self.n, c0 + self.chunk) - c0
+            s = k % ns
+            c._chk(lib.b2_h2d_async(hnd, s, self.d_src.ptr + c0 * self.src_img,
+                                    self.p_src.ptr + c0 * self.src_img, m * self.src_img))
+            for dp, pp, sz in ((self.d_y, self.p_y, self.y_img), (self.d_u, self.p_u, self.uv_img),
+                               (self.d_v, self.p_v, self.uv_img), (self.d_a, self.p_a, self.y_img)):
+                c._chk(lib.b2_d2h_async(hnd, s, pp.ptr + c0 * sz, dp.ptr + c0 * sz, m * sz))
+        c.sync()
+
     def fill_synthetic(self, seed: int, first_img: int = 0, alpha_mode: int = _abi.SYNTH_OPAQUE,
                        to_host: bool = False):
         """Device-side generator (identical to the oracle's orc_synth_fill_u32)."""
@@ -229,8 +244,10 @@ class UpsamplePipeline:
 class ArgbPipeline:
     """Device-resident batch of n equal ARGB images for the VP8L transforms."""
 
-    def __init__(self, ctx: Context, n: int, width: int, height: int, op: str, bits: int):
+    def __init__(self, ctx: Context, n: int, width: int, height: int, op: str, bits: int,
+                 host: bool = False, host_images: int = 4):
         self.ctx, self.n, self.w, self.h, self.op, self.bits = ctx, n, width, height, op, bits
+        self.host, self.host_images = host, min(host_images, n)
         self.index = op == "color_index_inverse"
         sub = lambda v, b: (v + (1 << b) - 1) >> b  # noqa: E731
         self.src_w = sub(width, bits) if self.index else width
@@ -251,6 +268,28 @@ class ArgbPipeline:
                                   width, height, bits, 0) for i in range(n)]
         self._job_arr = (_abi.ArgbJob * n)(*self.jobs)
         self._fn = getattr(ctx.lib, "b2_vp8l_" + op)
+        if self.host:   # pinned staging for the first host_images images (end-to-end runs)
+            m = self.host_images
+            self.p_src = ctx.pinned(self.src_img * m)
+            self.p_dst = ctx.pinned(self.dst_img * m)
+            self.p_data = ctx.pinned(self.data_img * m)
+            self._host_arr = (_abi.ArgbHost * m)(*[
+                _abi.ArgbHost(self.p_src.ptr + i * self.src_img, self.p_dst.ptr + i * self.dst_img,
+                              self.p_data.ptr + i * self.data_img if self.data_words else None,
+                              4 * self.src_w * height, 4 * width * height, 4 * self.data_words) for i in range(m)])
+
+    @property
+    def h2d_bytes(self) -> int:
+        return self.host_images * (4 * self.src_w * self.h + 4 * self.data_words)
+
+    @property
+    def d2h_bytes(self) -> int:
+        return self.host_images * 4 * self.w * self.h
+
+    def run(self, chunk: int = 1):
+        """pinned host -> device -> kernel -> pinned host for the staged images (b2_vp8l_batch_staged)."""
+        c = self.ctx
+        c._chk(c.lib.b2_vp8l_batch_staged(c.h, _abi.VP8L_OPS[self.op], self._job_arr, self._host_arr, self.host_images, chunk))
 
     def fill_synthetic(self, seed: int, first_img: int = 0):
         c = self.ctx
@@ -258,6 +297,12 @@ class ArgbPipeline:
         if self.data_words:
             c.synth_fill(self.d_data.ptr, self.data_words, 1, 4 * self.data_words, self.data_img, self.n, seed, first_img, 6)
         c.sync()
+        if self.host:
+            m = self.host_images
+            c._chk(c.lib.b2_d2h_async(c.h, 0, self.p_src.ptr, self.d_src.ptr, self.src_img * m))
+            if self.data_words:
+                c._chk(c.lib.b2_d2h_async(c.h, 0, self.p_data.ptr, self.d_data.ptr, self.data_img * m))
+            c.sync()
 
     def run_device(self, stream: int = 0):
         c = self.ctx
@@ -271,7 +316,63 @@ class ArgbPipeline:
         return src, data, dst
 
     def close(self):
-        for b in ("d_src", "d_dst", "d_data"):
+        for b in ("d_src", "d_dst", "d_data", "p_src", "p_dst", "p_data"):
+            if hasattr(self, b):
+                getattr(self, b).free()
+
+
+class PalettePipeline:
+    """Device-resident batch of n equal ARGB images whose pixels are all colours of a per-image palette,
+    for ApplyPalette (colour -> packed index).  The images are made on the device: synthetic packed
+    indices through the colour-index inverse, so run_device() must give those indices back."""
+
+    def __init__(self, ctx: Context, n: int, width: int, height: int, palette_size: int):
+        self.ctx, self.n, self.w, self.h, self.psize = ctx, n, width, height, palette_size
+        self.xbits = (3 if palette_size <= 2 else 2) if palette_size <= 4 else (1 if palette_size <= 16 else 0)
+        self.ow = (width + (1 << self.xbits) - 1) >> self.xbits
+        self.pal_words = 1 << (8 >> self.xbits)
+        self.img, self.pk, self.pal_img = _al(4 * width * height), _al(4 * self.ow * height), _al(4 * self.pal_words)
+        self.d_img = ctx.alloc(self.img * n)
+        self.d_idx = ctx.alloc(self.pk * n)     # synthetic packed indices (the expected answer's green bytes)
+        self.d_out = ctx.alloc(self.pk * n)
+        self.d_pal = ctx.alloc(self.pal_img * n)
+        self._jobs = (_abi.PaletteJob * n)(*[
+            _abi.PaletteJob(self.d_img.ptr + i * self.img, self.d_out.ptr + i * self.pk, self.d_pal.ptr + i * self.pal_img,
+                            width, self.ow, width, height, palette_size, self.xbits) for i in range(n)])
+        self._inv = (_abi.ArgbJob * n)(*[
+            _abi.ArgbJob(self.d_idx.ptr + i * self.pk, self.d_img.ptr + i * self.img, self.d_pal.ptr + i * self.pal_img,
+                         width, height, self.xbits, 0) for i in range(n)])
+
+    def fill_synthetic(self, seed: int, palettes: np.ndarray | None = None):
+        """palettes: [n, palette_size] uint32 of distinct colours (host); indices uniform below palette_size
+        when it is a power of two (the synthetic words are masked on the host for the other sizes)."""
+        c = self.ctx
+        c.synth_fill(self.d_idx.ptr, self.ow, self.h, 4 * self.ow, self.pk, self.n, seed, 0, 5)
+        if palettes is None:
+            rng = np.random.default_rng(seed)
+            palettes = np.stack([rng.choice(1 << 24, self.psize, replace=False).astype(np.uint32) | 0xff000000 for _ in range(self.n)])
+        full = np.zeros((self.n, self.pal_img // 4), np.uint32)
+        full[:, :self.psize] = palettes
+        # indices >= palette_size would hit the zero padding: fold them onto entry index % psize by repeating the palette
+        for k in range(self.psize, self.pal_words):
+            full[:, k] = full[:, k % self.psize]
+        c.h2d(self.d_pal.ptr, full)
+        c._chk(c.lib.b2_vp8l_color_index_inverse(c.h, 0, self._inv, self.n))
+        c.sync()
+        self.palettes = palettes
+
+    def run_device(self, stream: int = 0):
+        c = self.ctx
+        c._chk(c.lib.b2_vp8l_apply_palette(c.h, stream, self._jobs, self.n))
+
+    def device_image(self, i: int):
+        c = self.ctx
+        img = c.d2h(self.d_img.ptr + i * self.img, 4 * self.w * self.h).view(np.uint32).reshape(self.h, self.w)
+        out = c.d2h(self.d_out.ptr + i * self.pk, 4 * self.ow * self.h).view(np.uint32).reshape(self.h, self.ow)
+        return img, out
+
+    def close(self):
+        for b in ("d_img", "d_idx", "d_out", "d_pal"):
             getattr(self, b).free()
 
 

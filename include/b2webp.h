@@ -209,6 +209,27 @@ int b2_vp8l_color_index_inverse(b2_ctx* ctx, int stream, const b2_argb_job* jobs
  * ceil(width/2^bits) uint32. */
 int b2_vp8l_bundle_color_map(b2_ctx* ctx, int stream, const b2_argb_job* jobs, int n_jobs);
 
+/* ApplyPalette (pkg/vp8/vp8l_encoder.go:1093-1212; caller MapImageFromPalette :1220-1244): every
+ * ARGB pixel of src becomes its index in 'palette' -- greedy compares below 4 colours, else the first
+ * of the three ApplyPaletteHash functions that is collision-free on the palette, else an exact search
+ * (SearchColorNoIdx, pkg/libwebp/utils/palette.go:74-119) -- and the indices are bundled exactly as
+ * VP8LBundleColorMap does (lossless_enc.go:293-312): dst rows hold ceil(width / 2^xbits) words
+ * 0xff000000 | indices << 8.  The reference goes through a u8 row buffer; here lookup and bundle are
+ * one pass.  palette: DEVICE array of palette_size (1..256) colours; strides in pixels / words; xbits
+ * in [0,3] (MapImageFromPalette: <= 2 colours 3, <= 4: 2, <= 16: 1, else 0).  dst may equal src only
+ * with xbits == 0 and equal strides.  Pixels that are not palette colours give what the reference
+ * gives where it is defined (greedy, hash tables); its binary search does not terminate for them. */
+typedef struct b2_palette_job {
+  const uint32_t* src;
+  uint32_t* dst;
+  const uint32_t* palette;
+  int32_t src_stride, dst_stride;
+  int32_t width, height;
+  int32_t palette_size;
+  int32_t xbits;
+} b2_palette_job;
+int b2_vp8l_apply_palette(b2_ctx* ctx, int stream, const b2_palette_job* jobs, int n_jobs);
+
 /* ---- next row of the table: VP8L predictor transform -----------
  * data = mode image, ceil(w/2^bits) x ceil(h/2^bits) words, mode in bits 8..11
  * (lossless.go:313); bits in [2,9]; dst must not alias src.

@@ -212,6 +212,27 @@ def bundle_color_map(idx, xbits):
     return dst
 
 
+def apply_palette(src, palette, xbits):
+    """ApplyPalette (pkg/vp8/vp8l_encoder.go:1130-1212): ARGB [h, w] -> packed index rows
+    [h, ceil(w / 2^xbits)]; also returns the strategy (0 greedy, 1..3 hash, 4 sorted)."""
+    src = np.ascontiguousarray(src, np.uint32)
+    pal = np.ascontiguousarray(palette, np.uint32).reshape(-1)
+    h, w = src.shape
+    ow = (w + (1 << xbits) - 1) >> xbits
+    dst = np.zeros((h, ow), np.uint32)
+    st = lib().orc_apply_palette(_p(src), w, _p(dst), ow, _p(pal), pal.size, w, h, xbits)
+    if st < 0:
+        raise MemoryError("orc_apply_palette")
+    return dst, st
+
+
+def palette_xbits(palette_size: int) -> int:
+    """MapImageFromPalette's rule (vp8l_encoder.go:1229-1233)."""
+    if palette_size <= 4:
+        return 3 if palette_size <= 2 else 2
+    return 1 if palette_size <= 16 else 0
+
+
 def predictor_inverse(src, modes, bits):
     src = np.ascontiguousarray(src, np.uint32)
     modes = np.ascontiguousarray(modes, np.uint32)

@@ -1040,6 +1040,99 @@ void orc_bundle_color_map(const uint8_t* row, int width, int xbits,
   }
 }
 
+/* ---- ApplyPalette: pkg/vp8/vp8l_encoder.go:1093-1212, the colour -> index half of
+ * row a33 (forward counterpart of colour indexing).  Strategy order as the reference:
+ * greedy compare below 4 colours; else the first of three hashes that maps the palette
+ * without collision into a 2048-entry table; else binary search in the sorted palette
+ * (pkg/libwebp/utils/palette.go:74-119).  The hashes are the intended C ones: the product
+ * is truncated to 32 bits before the shift (the Go text drops the cast).
+ * The reference "assumes that all src[] values have a corresponding entry in the palette";
+ * for the others it is only partly defined: greedy answers 3, a table answers what the
+ * slot holds (0xffff truncated to a byte when empty), the binary search never ends -- here
+ * it stops after 9 halvings and answers the entry it stands on. */
+#define ORC_PALETTE_INV_SIZE_BITS 11
+#define ORC_PALETTE_INV_SIZE (1 << ORC_PALETTE_INV_SIZE_BITS)
+static uint32_t ApplyPaletteHash0(uint32_t color) { return (color >> 8) & 0xff; }           /* :1111-1114 */
+static uint32_t ApplyPaletteHash1(uint32_t color) {                                         /* :1119-1122 */
+  return ((uint32_t)((color & 0x00ffffffu) * 4222244071ull)) >> (32 - ORC_PALETTE_INV_SIZE_BITS);
+}
+static uint32_t ApplyPaletteHash2(uint32_t color) {                                         /* :1124-1127 */
+  return ((uint32_t)((color & 0x00ffffffu) * ((1ull << 31) - 1))) >> (32 - ORC_PALETTE_INV_SIZE_BITS);
+}
+static uint32_t palette_hash(int which, uint32_t c) {
+  return which == 0 ? ApplyPaletteHash0(c) : which == 1 ? ApplyPaletteHash1(c) : ApplyPaletteHash2(c);
+}
+static int SearchColorGreedy(const uint32_t* palette, uint32_t color) {                     /* :1095-1109 */
+  if (color == palette[0]) return 0;
+  if (color == palette[1]) return 1;
+  if (color == palette[2]) return 2;
+  return 3;
+}
+static int SearchColorNoIdxBounded(const uint32_t* sorted, uint32_t color, int num_colors) { /* palette.go:74-96 */
+  int low = 0, hi = num_colors, it;
+  if (sorted[low] == color) return low;
+  for (it = 0; it < 9; ++it) {
+    const int mid = (low + hi) >> 1;
+    if (sorted[mid] == color) return mid;
+    if (sorted[mid] < color) low = mid; else hi = mid;
+  }
+  return low;
+}
+static int cmp_u32(const void* a, const void* b) {
+  const uint32_t x = *(const uint32_t*)a, y = *(const uint32_t*)b;
+  return x < y ? -1 : x > y;
+}
+/* Returns the strategy used: 0 greedy, 1..3 hash 0..2, 4 sorted search. */
+int orc_apply_palette(const uint32_t* src, int src_stride, uint32_t* dst, int dst_stride,
+                      const uint32_t* palette, int palette_size, int width, int height, int xbits) {
+  uint8_t* tmp_row = (uint8_t*)malloc((size_t)width);
+  uint16_t buffer[ORC_PALETTE_INV_SIZE];
+  uint32_t sorted[256], idx_map[256], pal3[3] = {0, 0, 0};
+  int strategy = 0, i, j, x, y;
+  if (tmp_row == NULL) return -1;
+  if (palette_size < 4) {                                                                   /* :1154 */
+    for (i = 0; i < 3 && i < palette_size; ++i) pal3[i] = palette[i];
+    /* entries past palette_size: the reference reads palette[] (MAX_PALETTE_SIZE words, zero beyond) */
+  } else {
+    for (i = 0; i < 3; ++i) {                                                               /* :1168-1184 */
+      int use_LUT = 1;
+      memset(buffer, 0xff, sizeof(buffer));
+      for (j = 0; j < palette_size; ++j) {
+        const uint32_t ind = palette_hash(i, palette[j]);
+        if (buffer[ind] != 0xffffu) { use_LUT = 0; break; }
+        buffer[ind] = (uint16_t)j;
+      }
+      if (use_LUT) break;
+    }
+    strategy = i + 1;
+    if (i == 3) {                                                                           /* :1193-1199, palette.go:99-106 */
+      memcpy(sorted, palette, sizeof(uint32_t) * (size_t)palette_size);
+      qsort(sorted, (size_t)palette_size, sizeof(uint32_t), cmp_u32);
+      for (j = 0; j < palette_size; ++j) idx_map[SearchColorNoIdxBounded(sorted, palette[j], palette_size)] = (uint32_t)j;
+    }
+  }
+  for (y = 0; y < height; ++y) {                                                            /* APPLY_PALETTE_FOR :1130-1147 */
+    /* The reference keeps a one-pixel cache (prev_pix / prev_idx, seeded with palette[0] -> 0) across
+     * the whole image; the index is a pure function of the pixel, so the cache never changes a result. */
+    uint32_t prev_pix = palette[0];
+    int prev_idx = 0;
+    const uint32_t* row = src + (size_t)y * src_stride;
+    for (x = 0; x < width; ++x) {
+      const uint32_t pix = row[x];
+      if (pix != prev_pix) {
+        if (strategy == 0) prev_idx = SearchColorGreedy(pal3, pix);
+        else if (strategy <= 3) prev_idx = buffer[palette_hash(strategy - 1, pix)];
+        else prev_idx = (int)idx_map[SearchColorNoIdxBounded(sorted, pix, palette_size)];
+        prev_pix = pix;
+      }
+      tmp_row[x] = (uint8_t)prev_idx;
+    }
+    orc_bundle_color_map(tmp_row, width, xbits, dst + (size_t)y * dst_stride);
+  }
+  free(tmp_row);
+  return strategy;
+}
+
 /* ---- predictors: pkg/libwebp/dsp/lossless.go:31-333 (row a-next, 8f-1) --- */
 static inline uint32_t AddPixels(uint32_t a, uint32_t b) { /* common.go:110 */
   const uint32_t ag = (a & 0xff00ff00u) + (b & 0xff00ff00u);

@@ -30,21 +30,65 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_strerror():
     lib = _abi.load()
-    assert lib.b2_abi_version() == 0x0104
+    assert lib.b2_abi_version() == 0x0105
     assert lib.b2_strerror(0) == b"ok"
     # messages are the reference's sentinels (pkg/picture/errors.go:8-21)
     assert lib.b2_strerror(_abi.B2_ERR_BAD_DIM) == b"picture has invalid width/height"
     assert lib.b2_strerror(_abi.B2_ERR_NULL) == b"a pointer parameter is nil"
 
 
-def test_struct_layouts_match_header():
-    assert C.sizeof(_abi.ImportJob) == 5 * 8 + 6 * 4
-    assert C.sizeof(_abi.UpsampleJob) == 5 * 8 + 8 * 4
-    assert C.sizeof(_abi.ArgbJob) == 3 * 8 + 4 * 4
-    assert C.sizeof(_abi.PlainJob) == 5 * 8 + 8 * 4
-    assert C.sizeof(_abi.AlphaIndexJob) == 3 * 8 + 4 * 4
-    assert C.sizeof(_abi.ExpandJob) == 2 * 8 + 2 * 4
-    assert C.sizeof(_abi.ConvertJob) == 4 * 8 + 6 * 4
+_STRUCTS = {
+    "b2_import_job": _abi.ImportJob, "b2_upsample_job": _abi.UpsampleJob, "b2_argb_job": _abi.ArgbJob,
+    "b2_plain_job": _abi.PlainJob, "b2_alpha_index_job": _abi.AlphaIndexJob, "b2_expand_job": _abi.ExpandJob,
+    "b2_convert_job": _abi.ConvertJob, "b2_picture_job": _abi.PictureJob, "b2_anim_blend_job": _abi.AnimBlendJob,
+    "b2_anim_compare_job": _abi.AnimCompareJob, "b2_alpha_filter_job": _abi.AlphaFilterJob,
+    "b2_alpha_dequant_job": _abi.AlphaDequantJob, "b2_rescale_job": _abi.RescaleJob,
+    "b2_palette_job": _abi.PaletteJob, "b2_import_host": _abi.ImportHost, "b2_upsample_host": _abi.UpsampleHost, "b2_argb_host": _abi.ArgbHost,
+}
+
+
+def test_struct_layouts_match_header(tmp_path):
+    """sizeof / offsetof of EVERY struct of include/b2webp.h, from the header itself compiled
+    as C99 by gcc, against the ctypes declarations the tests and the host mirror call through."""
+    import subprocess
+    txt = open(os.path.join(ROOT, "include", "b2webp.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    structs = {}
+    for m in re.finditer(r"typedef struct (b2_\w+) \{(.*?)\} (b2_\w+);", txt, flags=re.S):
+        fields = []
+        for decl in m.group(2).split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            for part in decl.split(","):
+                name = re.sub(r"\[.*?\]", "", part.strip().split()[-1]).lstrip("*")
+                fields.append(name)
+        structs[m.group(1)] = fields
+    assert sorted(structs) == sorted(_STRUCTS), "every struct of the header has a ctypes twin (and vice versa)"
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "b2webp.h"', 'int main(void) {']
+    for name, fields in structs.items():
+        lines.append(f'  printf("{name} %zu", sizeof({name}));')
+        for f in fields:
+            lines.append(f'  printf(" {f}=%zu", offsetof({name}, {f}));')
+        lines.append('  printf("\\n");')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           str(src), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)], text=True)
+    seen = 0
+    for line in out.strip().splitlines():
+        parts = line.split()
+        cls = _STRUCTS[parts[0]]
+        assert C.sizeof(cls) == int(parts[1]), parts[0]
+        c_fields = [p.split("=") for p in parts[2:]]
+        assert [f for f, _ in c_fields] == [f[0] for f in cls._fields_], parts[0]
+        for f, off in c_fields:
+            assert getattr(cls, f).offset == int(off), (parts[0], f)
+        seen += 1
+    assert seen == len(_STRUCTS)
 
 
 def test_null_context_is_rejected_without_a_gpu():

@@ -80,3 +80,28 @@ def test_mixed_size_batch_and_lpt_balance():
         parts = partition.lpt_partition(costs, g)
         assert sorted(i for p in parts for i in p) == list(range(256))
         assert max(sum(costs[i] for i in p) for p in parts) * g / sum(costs) < 1.01
+
+
+def test_calibrated_cost_model_balances_time_not_bytes():
+    """configs[4], round 2: LPT on bytes / rate(class).  With rates that differ by class the time
+    imbalance of the byte model shows, the calibrated model removes it; missing classes fall back."""
+    sys.path.insert(0, ROOT)
+    from go_webp_b200 import partition
+    from go_webp_b200.pipeline import mixed_sizes
+    s = mixed_sizes(256)
+    classes = sorted({partition.size_class(w, h) for (w, h) in s})
+    assert len(classes) >= 8 and all(c.split("/")[0] in ("w16", "w4", "w2", "w1") for c in classes)
+    # a plausible machine: odd widths and narrow rows run slower
+    true_rate = {c: (1.0 if c.startswith("w16") else 0.8 if c.startswith("w4") else 0.55) *
+                 (0.5 if c.endswith("narrow") else 1.0) for c in classes}
+    t_true = partition.calibrated_costs(s, true_rate)
+    byte_costs = [partition.full_pipeline_cost_bytes(w, h) for (w, h) in s]
+    for g in (2, 4, 8):
+        by_bytes = partition.lpt_partition(byte_costs, g)
+        by_time = partition.lpt_partition(t_true, g)
+        imb = lambda parts: max(sum(t_true[i] for i in p) for p in parts) * g / sum(t_true)  # noqa: E731
+        assert imb(by_time) < 1.01
+        assert imb(by_time) <= imb(by_bytes)
+    # unmeasured classes use the mean rate: costs stay finite and proportional to bytes
+    c = partition.calibrated_costs([(64, 64), (1920, 1080)], {})
+    assert c[1] / c[0] == pytest.approx(partition.full_pipeline_cost_bytes(1920, 1080) / partition.full_pipeline_cost_bytes(64, 64))

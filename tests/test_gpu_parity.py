@@ -1030,3 +1030,106 @@ def test_rescaler(gpu, golden_dir):
         assert R.WebPPictureRescale(pic, dw, dh) == 1
         assert (pic.ARGB == g[f"{k}/out_argb"]).all(), (k, "argb")
         assert (pic.Width, pic.Height, pic.ARGBStride) == (dw, dh, dw)
+
+
+# ---- ApplyPalette: colour -> index, the forward half of colour indexing (row a33) -------------
+def test_apply_palette_every_strategy_sizes_and_alignments(gpu):
+    """b2_vp8l_apply_palette vs the oracle's restatement of ApplyPalette + VP8LBundleColorMap
+    (vp8l_encoder.go:1093-1212, lossless_enc.go:293-312): palette sizes 2..256 (all four packings), every
+    strategy of the reference, widths around the 4-pixel / word / segment boundaries, rows that miss the
+    vector alignment, one mixed batch per launch."""
+    from _palettes import palette_cases
+    dsp = gpu["dsp"]
+    rng = np.random.default_rng(21)
+    widths = [1, 2, 3, 4, 5, 7, 8, 9, 31, 32, 33, 64, 127, 128, 129, 515, 2048, 2049, 4100]
+    items, expect, strategies = [], [], set()
+    for name, pal in palette_cases(rng):
+        xb = oracle.palette_xbits(pal.size)
+        for w in widths:
+            h = 3 if w < 1000 else 2
+            idx = rng.integers(0, pal.size, (h, w), dtype=np.uint8)
+            img = pal[idx]
+            out, st = oracle.apply_palette(img, pal, xb)
+            strategies.add(st)
+            items.append((img, pal, xb))
+            expect.append(out)
+    assert strategies == {0, 1, 2, 3, 4}
+    got = dsp.ApplyPaletteBatch(items)
+    for (img, pal, xb), e, g in zip(items, expect, got):
+        assert g.shape == e.shape and (g == e).all(), (pal.size, xb, img.shape)
+
+
+def test_apply_palette_pixels_outside_the_palette(gpu):
+    """Where the reference defines an answer for a colour that is not in the palette (greedy: 3; hash
+    tables: whatever the slot holds, 0xffff cut to a byte when empty) the device gives the same."""
+    from _palettes import hash2_palette
+    dsp = gpu["dsp"]
+    rng = np.random.default_rng(22)
+    pals = [rng.choice(1 << 32, 3, replace=False).astype(np.uint32),       # greedy
+            ((np.arange(64, dtype=np.uint64) * 4) * 0x010101 | 0xff000000).astype(np.uint32),   # hash 0
+            rng.choice(1 << 32, 12, replace=False).astype(np.uint32),      # hash 1 (checked below)
+            hash2_palette()]                                               # hash 2
+    items, expect = [], []
+    for pal in pals:
+        xb = oracle.palette_xbits(pal.size)
+        img = rng.integers(0, 2**32, (5, 131), dtype=np.uint32)
+        img[:, ::3] = pal[rng.integers(0, pal.size, img[:, ::3].shape)]
+        out, st = oracle.apply_palette(img, pal, xb)
+        assert st <= 3
+        items.append((img, pal, xb))
+        expect.append(out)
+    for e, g in zip(expect, dsp.ApplyPaletteBatch(items)):
+        assert (g == e).all()
+
+
+def test_apply_palette_reference_signature_and_libwebp_streams(gpu, golden_dir):
+    """dsp.ApplyPalette with the reference's argument list (padded src_stride), and the pin: on the
+    colour-indexed streams the libwebp binary encoded, ApplyPalette of the decoded pixels is the packed
+    index image that sits in the stream (tests/golden/vp8l_libwebp160.npz)."""
+    dsp = gpu["dsp"]
+    rng = np.random.default_rng(23)
+    pal = rng.choice(1 << 32, 9, replace=False).astype(np.uint32)
+    w, h, stride = 45, 6, 52
+    buf = rng.integers(0, 2**32, (h, stride), dtype=np.uint32)
+    buf[:, :w] = pal[rng.integers(0, 9, (h, w))]
+    got = dsp.ApplyPalette(buf, stride, pal, 9, w, h, dsp.PaletteXBits(9))
+    assert (got == oracle.apply_palette(buf[:, :w], pal, 1)[0]).all()
+    from test_oracle_golden import vp8l_vectors
+    sub = lambda v, b: (v + (1 << b) - 1) >> b  # noqa: E731
+    n = 0
+    for name, img, trs, expected in vp8l_vectors(golden_dir):
+        cur = img
+        for (t, b, tw, th, data) in reversed(trs):
+            if t == 0:
+                cur = oracle.predictor_inverse(cur, data.reshape(sub(th, b), sub(tw, b)), b)
+            elif t == 1:
+                cur = oracle.color_space_inverse(cur, data.reshape(sub(th, b), sub(tw, b)), b)
+            elif t == 2:
+                cur = oracle.add_green(cur)
+            else:
+                palette = oracle.expand_color_map(data, b)[:data.size]
+                assert b == dsp.PaletteXBits(data.size)
+                packed = dsp.ApplyPaletteBatch([(expected, palette, b)])[0]
+                assert (packed == cur).all(), name
+                n += 1
+                cur = expected
+    assert n >= 4
+
+
+def test_apply_palette_full_size_round_trip(gpu):
+    """8 x 2048x1024 per packing: synthetic packed indices -> colour-index inverse -> ApplyPalette gives the
+    indices back (green bytes), bit for bit on every image."""
+    from go_webp_b200.pipeline import PalettePipeline
+    ctx = gpu["ctx"]
+    for psize in (2, 4, 16, 256):
+        p = PalettePipeline(ctx, 8, 2048, 1024, psize)
+        p.fill_synthetic(0xB2000003)
+        p.run_device()
+        ctx.sync()
+        idx = ctx.d2h(p.d_idx.ptr, p.pk * p.n).view(np.uint32)
+        out = ctx.d2h(p.d_out.ptr, p.pk * p.n).view(np.uint32)
+        assert ((out >> 24) == 0xff).all() and ((out & 0x00ff00ff) == 0).all()
+        assert (((out ^ idx) >> 8) & 0xff == 0).all(), psize
+        img, o = p.device_image(3)
+        assert (o == oracle.apply_palette(img, p.palettes[3], p.xbits)[0]).all()
+        p.close()

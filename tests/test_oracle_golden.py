@@ -182,7 +182,13 @@ def test_vp8l_forward_inverts_on_libwebp_vectors(golden_dir):
                 nxt = oracle.add_green(cur)
                 assert (oracle.sub_green(nxt) == cur).all(), name
             else:
-                nxt = oracle.color_index_inverse(cur, oracle.expand_color_map(data, b), b, w)
+                pal = oracle.expand_color_map(data, b)
+                nxt = oracle.color_index_inverse(cur, pal, b, w)
+                # ApplyPalette + VP8LBundleColorMap (vp8l_encoder.go:1130-1212) on the decoded pixels give the
+                # packed index image the binary's own encoder wrote into the stream
+                packed, strategy = oracle.apply_palette(nxt, pal[:data.size], b)
+                assert (packed == cur).all(), name
+                assert b == oracle.palette_xbits(data.size), name
             stages.append(nxt)
 
 

@@ -169,3 +169,24 @@ def test_post_conversions_identities():
     # multiply then inverse-multiply recovers premultiplied values up to the reference's own rounding
     m1 = oracle.mult_argb_rows(argb | 0x80000000, 0)
     assert ((m1 >> 24) == ((argb | 0x80000000) >> 24)).all()
+
+
+def test_apply_palette_strategies_and_round_trip():
+    """ApplyPalette (vp8l_encoder.go:1093-1212): every strategy the reference can pick gives the index
+    of the colour, bundled as VP8LBundleColorMap does; colour-index inverse undoes it."""
+    from _palettes import palette_cases
+    rng = np.random.default_rng(11)
+    seen = set()
+    for name, pal in palette_cases(rng):
+        P = pal.size
+        xb = oracle.palette_xbits(P)
+        for (w, h) in [(1, 1), (7, 3), (37, 13), (64, 2), (129, 5)]:
+            idx = rng.integers(0, P, (h, w), dtype=np.uint8)
+            img = pal[idx]
+            out, st = oracle.apply_palette(img, pal, xb)
+            seen.add(st)
+            assert (out == oracle.bundle_color_map(idx, xb)).all(), (name, w, h)
+            full = np.zeros(1 << (8 >> xb), np.uint32)
+            full[:P] = pal
+            assert (oracle.color_index_inverse(out, full, xb, w) == img).all()
+    assert seen == {0, 1, 2, 3, 4}, seen

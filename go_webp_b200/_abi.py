@@ -135,6 +135,8 @@ SYMBOLS = {
     "b2_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "b2_ctx_create": (C.c_int, [C.c_int, C.c_int, C.POINTER(_ctx)]),
     "b2_ctx_destroy": (None, [_ctx]),
+    "b2_ctx_set_swap_16bit_csp": (C.c_int, [_ctx, C.c_int]),
+    "b2_ctx_swap_16bit_csp": (C.c_int, [_ctx]),
     "b2_ctx_device": (C.c_int, [_ctx]),
     "b2_ctx_sm_count": (C.c_int, [_ctx]),
     "b2_last_error": (C.c_char_p, [_ctx]),

@@ -32,6 +32,9 @@ struct b2_ctx {
   void* scratch[B2_MAX_STREAMS];
   size_t scratch_bytes[B2_MAX_STREAMS];
   uint64_t launches;
+  // byte order of the 16-bit output modes (RGBA_4444, RGB_565), library-wide: 1 = the go-webp text
+  // (libwebp built with WEBP_SWAP_16BIT_CSP: ba / gb byte first), 0 = the stock libwebp build (rg first)
+  int swap16;
   // copies issued through the ABI (b2_copy_stats): calls and bytes per direction
   uint64_t h2d_calls, h2d_bytes, d2h_calls, d2h_bytes;
   // host-staged entry points: has-alpha flags (device + pinned mirror), per-chunk events
@@ -68,6 +71,10 @@ int b2_fail_cuda(b2_ctx* ctx, cudaError_t e, const char* what);
 // call for the same stream; growing it waits for the stream).
 int b2_stream_scratch(b2_ctx* ctx, int stream, size_t bytes, void** dev_out);
 
+// Makes sure the NEXT uploads of this stream, 'bytes' in total (every part rounded up to 256), fit the
+// ring without wrapping in between: a launch that reads two uploads (job table + generator
+// polynomials) must not have the second one wrap onto the first.  Wraps now if it has to.
+int b2_desc_reserve(b2_ctx* ctx, int stream, size_t bytes);
 // Copies 'bytes' of host descriptors into the stream's ring; returns device ptr.
 int b2_upload_desc(b2_ctx* ctx, int stream, const void* host, size_t bytes, void** dev_out);
 

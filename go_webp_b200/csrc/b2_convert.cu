@@ -387,7 +387,7 @@ __device__ __forceinline__ void yuv_rgb(uint32_t y, uint32_t u, uint32_t v, uint
 template <bool YUV444>
 __global__ void __launch_bounds__(kThreads, 4)
 yuv_point_kernel(const ConvJobDev* __restrict__ jobs, const uint32_t* __restrict__ prefix, uint32_t n_jobs,
-                 uint32_t uniform, uint32_t total_items, int st) {
+                 uint32_t uniform, uint32_t total_items, int st, bool upstream16) {
   B2_CONV_ITEM_PROLOGUE_WIDE(kItemPx)
     const uint8_t* yr = (const uint8_t*)j.src + (ptrdiff_t)y * j.src_stride + x0;
     // WebPSamplerProcessPlane advances u/v after every odd row (yuv.go:52-55): chroma row y >> 1
@@ -433,16 +433,14 @@ yuv_point_kernel(const ConvJobDev* __restrict__ jobs, const uint32_t* __restrict
           }
         }
       }
-      store_px4(st, false, true, a4, r4, g4, b4, d);
+      store_px4(st, false, upstream16, a4, r4, g4, b4, d);
       continue;
     }
     for (int k = 0; k < nv; ++k) {
       const int cx = YUV444 ? (x0 + k) : ((x0 + k) >> 1);  // row_func: two pixels share a sample (yuv.go:24-30)
       uint32_t r, g, b;
       yuv_rgb(yr[k], ur[cx], vr[cx], &r, &g, &b);
-      if (st == ST_4444) { d[2 * k] = (uint8_t)((r & 0xf0) | (g >> 4)); d[2 * k + 1] = (uint8_t)((b & 0xf0) | 0x0f); }
-      else if (st == ST_565) { d[2 * k] = (uint8_t)((r & 0xf8) | (g >> 5)); d[2 * k + 1] = (uint8_t)(((g << 3) & 0xe0) | (b >> 3)); }
-      else store_px(st, false, true, 0xff, r, g, b, d + k * bpp);
+      store_px(st, false, upstream16, 0xff, r, g, b, d + k * bpp);
     }
     }
   }
@@ -503,7 +501,7 @@ extern "C" int b2_vp8l_convert_from_bgra(b2_ctx* ctx, int stream, const b2_conve
   const int rc = prepare_conv(ctx, stream, jobs, n_jobs, false, bpp_of(st), 128, &dj, &dp, &uni, &tot);
   if (rc != B2_OK) return rc;
   convert_from_bgra_kernel<<<b2_grid_for(ctx, 8, (tot + kWarps - 1) / kWarps), kThreads, 0, ctx->streams[stream]>>>(
-      dj, dp, (uint32_t)n_jobs, uni, tot, st, premult ? 1 : 0, (flags & B2_CONVERT_UPSTREAM_16BIT) ? 1 : 0);
+      dj, dp, (uint32_t)n_jobs, uni, tot, st, premult ? 1 : 0, ((flags & B2_CONVERT_UPSTREAM_16BIT) || !ctx->swap16) ? 1 : 0);
   ctx->launches++;
   B2_CUDA(ctx, cudaGetLastError());
   return B2_OK;
@@ -533,8 +531,9 @@ extern "C" int b2_yuv_to_rgb_point(b2_ctx* ctx, int stream, const b2_convert_job
   const int rc = prepare_conv(ctx, stream, jobs, n_jobs, true, bpp_of(st), kItemPx, &dj, &dp, &uni, &tot);
   if (rc != B2_OK) return rc;
   const int grid = b2_grid_for(ctx, 8, (tot + kWarps - 1) / kWarps);
-  if (yuv444) yuv_point_kernel<true><<<grid, kThreads, 0, ctx->streams[stream]>>>(dj, dp, (uint32_t)n_jobs, uni, tot, st);
-  else yuv_point_kernel<false><<<grid, kThreads, 0, ctx->streams[stream]>>>(dj, dp, (uint32_t)n_jobs, uni, tot, st);
+  const bool up16 = !ctx->swap16;
+  if (yuv444) yuv_point_kernel<true><<<grid, kThreads, 0, ctx->streams[stream]>>>(dj, dp, (uint32_t)n_jobs, uni, tot, st, up16);
+  else yuv_point_kernel<false><<<grid, kThreads, 0, ctx->streams[stream]>>>(dj, dp, (uint32_t)n_jobs, uni, tot, st, up16);
   ctx->launches++;
   B2_CUDA(ctx, cudaGetLastError());
   return B2_OK;

@@ -83,6 +83,7 @@ extern "C" int b2_ctx_create(int device, int n_streams, b2_ctx** out) {
   if (ctx == NULL) return B2_ERR_OOM;
   ctx->device = device;
   ctx->n_streams = n_streams;
+  ctx->swap16 = 1;
   int st = B2_OK;
   do {
     cudaError_t e;
@@ -132,6 +133,13 @@ extern "C" void b2_ctx_destroy(b2_ctx* ctx) {
   free(ctx);
 }
 
+extern "C" int b2_ctx_set_swap_16bit_csp(b2_ctx* ctx, int swap) {
+  if (ctx == NULL) return B2_ERR_NULL;
+  if (swap != 0 && swap != 1) return B2_ERR_INVALID_CONFIG;
+  ctx->swap16 = swap;
+  return B2_OK;
+}
+extern "C" int b2_ctx_swap_16bit_csp(const b2_ctx* ctx) { return ctx ? ctx->swap16 : -1; }
 extern "C" int b2_ctx_device(const b2_ctx* ctx) { return ctx ? ctx->device : -1; }
 extern "C" int b2_ctx_sm_count(const b2_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
 extern "C" const char* b2_last_error(const b2_ctx* ctx) { return ctx ? ctx->err : "nil context"; }
@@ -146,6 +154,15 @@ int b2_stream_scratch(b2_ctx* ctx, int stream, size_t bytes, void** dev_out) {
     ctx->scratch_bytes[stream] = cap;
   }
   *dev_out = ctx->scratch[stream];
+  return B2_OK;
+}
+
+int b2_desc_reserve(b2_ctx* ctx, int stream, size_t bytes) {
+  if (bytes > B2_DESC_RING_BYTES) return B2_ERR_INVALID_CONFIG;
+  if (ctx->desc_off[stream] + bytes > B2_DESC_RING_BYTES) {
+    B2_CUDA(ctx, cudaStreamSynchronize(ctx->streams[stream]));
+    ctx->desc_off[stream] = 0;
+  }
   return B2_OK;
 }
 

@@ -357,7 +357,14 @@ static int import_impl(b2_ctx* ctx, int stream, const b2_import_job* jobs, int n
   if (n_with_a != 0 && n_with_a != n_jobs) tuned = false;  // WRITE_A is a kernel-wide switch
   void* dev = NULL;
   const size_t pre_off = (size_t)((uint8_t*)pre - host);
-  int st = b2_upload_desc(ctx, stream, host, pre_off + 2 * pb, &dev);
+  int st = B2_OK;
+  if (dithering > 0.f) {
+    // the dithered import uploads twice (this table, then the jump polynomials) before the kernels that
+    // read both are launched: reserve room for the pair so the second upload cannot wrap onto the first
+    const size_t poly_bytes3 = 3 * sizeof(uint32_t) * B2_RNG_N * (size_t)n_jobs;
+    st = b2_desc_reserve(ctx, stream, ((pre_off + 2 * pb + 255) & ~(size_t)255) + ((poly_bytes3 + 255) & ~(size_t)255));
+  }
+  if (st == B2_OK) st = b2_upload_desc(ctx, stream, host, pre_off + 2 * pb, &dev);
   free(host);
   if (st != B2_OK) return st;
   const ImportJobDev* djobs = (const ImportJobDev*)dev;

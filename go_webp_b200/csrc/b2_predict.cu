@@ -16,10 +16,16 @@
 //     SKEWED columns k = c + 2r: at step k every lane has its left / top-left / top /
 //     top-right neighbours ready (TR comes from the lane above by one shuffle, the
 //     rest are its own history), and all 32 lanes are busy on every step;
-//   * a band is cut into tiles of 32 skewed columns; tile (i, j) depends on tiles
-//     (i, j-1) and (i-1, j .. j+2), so all tiles with 3i + j == d are independent: one
-//     launch per diagonal d, no flags, no spinning, every dependency satisfied by
-//     stream order.  Tile boundaries read their neighbours back from the output image.
+//   * ONE persistent launch: warps draw bands from a ticket counter in band-major order
+//     (band 0 of every image, then band 1, ...).  Lane 0's row above is the last row of
+//     the band above, read back from the output image behind that band's progress word
+//     (st.release.gpu every kPublish columns, ld.acquire.gpu poll).  Liveness does not
+//     rest on stream order or on residency: a band only ever waits on the band above
+//     it, which holds a LOWER ticket, so it was drawn earlier and is running (or done);
+//     by induction the lowest unfinished ticket never waits on an undrawn band.
+//   * the fused variants (b2_vp8l_predictor_inverse_chain) apply the cross-colour
+//     inverse to the residual before the prediction is added and add-green to the
+//     pixel on its way out; the neighbours a lane keeps are the un-add-greened pixels.
 #include <stdlib.h>
 
 #include <type_traits>

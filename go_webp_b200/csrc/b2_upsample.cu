@@ -39,7 +39,7 @@ struct UpsampleJobDev {
   uint32_t q_lo;               // first row-pair unit: (row_begin + 1) >> 1
   uint32_t pad;
 };
-enum { JOB_FAST = 1 };
+enum { JOB_FAST = 1, JOB_SWAP16 = 2 };   // JOB_SWAP16: ba / gb byte first (b2_ctx_set_swap_16bit_csp)
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
@@ -122,8 +122,13 @@ __device__ __forceinline__ void pixel_generic(const UpsampleJobDev& j, int r, in
   else if (ST == ST_ARGB) { d += 4 * x; d[0] = alpha; d[1] = R; d[2] = G; d[3] = B; }
   else if (ST == ST_RGB) { d += 3 * x; d[0] = R; d[1] = G; d[2] = B; }
   else if (ST == ST_BGR) { d += 3 * x; d[0] = B; d[1] = G; d[2] = R; }
-  else if (ST == ST_4444) { d += 2 * x; d[0] = (R & 0xf0) | (G >> 4); d[1] = (B & 0xf0) | (alpha >> 4); }  // EmitAlphaRGBA4444, io_dec.c.go:197-226
-  else { d += 2 * x; d[0] = (R & 0xf8) | (G >> 5); d[1] = ((G << 3) & 0xe0) | (B >> 3); }
+  else if (ST == ST_4444) {  // VP8YuvToRgba4444 + the alpha nibble of EmitAlphaRGBA4444 (io_dec.c.go:197-226: byte 2i in the Go text's order)
+    const int sw = (j.flags & JOB_SWAP16) ? 1 : 0;
+    d += 2 * x; d[sw] = (R & 0xf0) | (G >> 4); d[sw ^ 1] = (B & 0xf0) | (alpha >> 4);
+  } else {
+    const int sw = (j.flags & JOB_SWAP16) ? 1 : 0;
+    d += 2 * x; d[sw] = (R & 0xf8) | (G >> 5); d[sw ^ 1] = ((G << 3) & 0xe0) | (B >> 3);
+  }
 }
 
 template <int ST>
@@ -494,6 +499,78 @@ __device__ __forceinline__ void convert_pass(const uint8_t* sy, const uint8_t* s
   }
 }
 
+// The last pass of a row when at most 128 pixels are left (1920 = 7.5 passes of 256): instead of
+// half the lanes idling through a whole pass, lanes 0-15 convert the top row and lanes 16-31 the
+// bottom row, 8 pixels each.  The bottom row's interpolation is the top row's with the two chroma
+// rows swapped (tf/ts of b2_interp16 with (tl,t) <-> (l,c) are its bf/bs), so every lane runs the
+// same single-row code on its own operands: about half the work of a full pass.
+template <int ST, bool HAS_ALPHA>
+__device__ __forceinline__ void convert_pass_split(const uint8_t* sp_y, const uint8_t* sp_a, const uint8_t* sp_c, int lane,
+                                                   int xpass, int wv, int uw, uint8_t* drt, uint8_t* drb,
+                                                   const B2YuvConsts& kc, uint8_t* xs, const XposeLane& xl) {
+  constexpr int R = BulkLayout<HAS_ALPHA>::kCRow;
+  constexpr int kTileW = BulkLayout<HAS_ALPHA>::kTW;
+  constexpr int kBpp = (ST == ST_RGB || ST == ST_BGR) ? 3 : 4;
+  const int l = lane & 15;
+  const bool bot = lane >= 16;
+  const int xh = xpass + l * 8;
+  const int row_off = bot ? kTileW : 0;
+  const uint2 yw = *reinterpret_cast<const uint2*>(sp_y + l * 8 + row_off);
+  uint2 aw = make_uint2(0, 0);
+  if (HAS_ALPHA) aw = *reinterpret_cast<const uint2*>(sp_a + l * 8 + row_off);
+  const uint8_t* sc = sp_c + l * 4;
+  const int on = bot ? R : 0, of = bot ? 0 : R;   // chroma row next to this lane's output row / the other one
+  uint32_t wtu = *reinterpret_cast<const uint32_t*>(sc + on);
+  uint32_t wcu = *reinterpret_cast<const uint32_t*>(sc + of);
+  uint32_t wtv = *reinterpret_cast<const uint32_t*>(sc + 2 * R + on);
+  uint32_t wcv = *reinterpret_cast<const uint32_t*>(sc + 2 * R + of);
+  uint32_t ltu = sc[on - 1], lcu = sc[of - 1], ltv = sc[2 * R + on - 1], lcv = sc[2 * R + of - 1];
+  uint32_t rtu = sc[on + 4], rcu = sc[of + 4], rtv = sc[2 * R + on + 4], rcv = sc[2 * R + of + 4];
+  if (xpass == 0 && l == 0) { ltu = wtu & 0xff; lcu = wcu & 0xff; ltv = wtv & 0xff; lcv = wcv & 0xff; }
+  {  // this is the last pass of the row: mirror the last chroma column (upsampling.c.go:93,98)
+    const int kk = uw - 1 - (xh >> 1);
+    if (kk == 3) { rtu = wtu >> 24; rcu = wcu >> 24; rtv = wtv >> 24; rcv = wcv >> 24; }
+    else if (kk >= 0 && kk < 3) {
+      const uint32_t sel = (kk == 0) ? 0x3200u : (kk == 1) ? 0x3110u : 0x2210u;
+      wtu = b2_prmt(wtu, 0u, sel); wcu = b2_prmt(wcu, 0u, sel); wtv = b2_prmt(wtv, 0u, sel); wcv = b2_prmt(wcv, 0u, sel);
+    }
+  }
+  const uint32_t etu = b2_even(wtu), otu = b2_odd(wtu), mtu = b2_prmt(etu, rtu, 0x5432);
+  const uint32_t ecu = b2_even(wcu), ocu = b2_odd(wcu), mcu = b2_prmt(ecu, rcu, 0x5432);
+  const uint32_t etv = b2_even(wtv), otv = b2_odd(wtv), mtv = b2_prmt(etv, rtv, 0x5432);
+  const uint32_t ecv = b2_even(wcv), ocv = b2_odd(wcv), mcv = b2_prmt(ecv, rcv, 0x5432);
+  const B2Quad16 au = b2_interp16(etu, otu, ecu, ocu), bu = b2_interp16(otu, mtu, ocu, mcu);
+  const B2Quad16 av = b2_interp16(etv, otv, ecv, ocv), bv = b2_interp16(otv, mtv, ocv, mcv);
+  const B2Quad16 cq = b2_interp16(b2_prmt(ltu, ltv, 0x5410), b2_prmt(etu, etv, 0x5410),
+                                  b2_prmt(lcu, lcv, 0x5410), b2_prmt(ecu, ecv, 0x5410));
+  const bool lane_ok = xh + 8 <= wv;
+  const uint32_t xc = b2_hi8(cq.ts);
+  const uint32_t u2[4] = {b2_hi8(au.tf), b2_hi8(au.ts), b2_hi8(bu.tf), b2_prmt(xc, b2_hi8(bu.ts), 0x5410)};
+  const uint32_t v2[4] = {b2_hi8(av.tf), b2_hi8(av.ts), b2_hi8(bv.tf), b2_prmt(xc, b2_hi8(bv.ts), 0x5432)};
+  // 16 lanes x 32 bytes = the first 512 bytes of the row's half of the transposition buffer
+  const uint32_t sw = (uint32_t)(l >> 2) & 1u;
+  const uint32_t xw0 = ((2u * l) ^ sw) * 16u, xw1 = ((2u * l + 1u) ^ sw) * 16u;
+  uint8_t* const drow = bot ? drb : drt;
+  emit_row8_packed<ST, HAS_ALPHA>(yw, aw, u2, v2, drow + xh * kBpp, lane_ok, kc,
+                                  (kBpp == 4) ? xs + (bot ? 1024 : 0) : nullptr, xw0, xw1);
+  if (kBpp == 4) {
+    __syncwarp();
+    const int xa = xpass + lane * 4;   // every lane stores pixels xa .. xa+3 of BOTH rows: 512 contiguous bytes per store
+    const int n = wv - xa;
+    const uint4 vt = *reinterpret_cast<const uint4*>(xs + xl.r);
+    const uint4 vb = *reinterpret_cast<const uint4*>(xs + 1024 + xl.r);
+    if (n >= 4) {
+      b2_stg_stream_v4(drt + xa * 4, vt);
+      b2_stg_stream_v4(drb + xa * 4, vb);
+    } else {
+      if (n > 0) { b2_stg_stream_u32(drt + xa * 4, vt.x); b2_stg_stream_u32(drb + xa * 4, vb.x); }
+      if (n > 1) { b2_stg_stream_u32(drt + xa * 4 + 4, vt.y); b2_stg_stream_u32(drb + xa * 4 + 4, vb.y); }
+      if (n > 2) { b2_stg_stream_u32(drt + xa * 4 + 8, vt.z); b2_stg_stream_u32(drb + xa * 4 + 8, vb.z); }
+    }
+    __syncwarp();
+  }
+}
+
 template <int ST, bool HAS_ALPHA>
 __global__ void __launch_bounds__(kBulkThreads, kBulkCtasPerSm)
 upsample_bulk_kernel(const UpsampleJobDev* __restrict__ jobs, const uint32_t* __restrict__ unit_prefix,
@@ -612,7 +689,10 @@ upsample_bulk_kernel(const UpsampleJobDev* __restrict__ jobs, const uint32_t* __
         const uint8_t* sy = sp + BL::kY + p * 256 + lane * 8;
         const uint8_t* sa = sp + BL::kA + p * 256 + lane * 8;
         const uint8_t* sc = sp + BL::kC + 16 + p * 128 + lane * 4;
-        if (xpass == 0 || xpass + 256 >= 2 * uw || xpass + 256 > wv)  // warp-uniform: first / last pass of the row
+        if (top_ok && bot_ok && wv - xpass <= 128)   // warp-uniform: a last pass of at most 128 pixels, both rows wanted
+          convert_pass_split<ST, HAS_ALPHA>(sp + BL::kY + p * 256, sp + BL::kA + p * 256, sp + BL::kC + 16 + p * 128, lane,
+                                            xpass, wv, uw, drt, drb, kc, xbuf, xl);
+        else if (xpass == 0 || xpass + 256 >= 2 * uw || xpass + 256 > wv)  // warp-uniform: first / last pass of the row
           convert_pass<ST, HAS_ALPHA, true>(sy, sa, sc, lane, xpass, wv, uw, top_ok, bot_ok, drt, drb, kc, xbuf, xl);
         else
           convert_pass<ST, HAS_ALPHA, false>(sy, sa, sc, lane, xpass, wv, uw, top_ok, bot_ok, drt, drb, kc, xbuf, xl);
@@ -688,7 +768,7 @@ extern "C" int b2_yuv420a_to_rgba_fancy(b2_ctx* ctx, int stream, const b2_upsamp
                 (((uintptr_t)j.u | (uintptr_t)j.v | (uintptr_t)(uint32_t)j.uv_stride) & 3) == 0 &&
                 (((uintptr_t)j.dst | (uintptr_t)(uint32_t)j.dst_stride) & 15) == 0;
     if (j.a != NULL && (((uintptr_t)j.a | (uintptr_t)(uint32_t)j.a_stride) & 7) != 0) fast = false;
-    d.flags = fast ? JOB_FAST : 0;
+    d.flags = (fast ? JOB_FAST : 0) | (ctx->swap16 ? JOB_SWAP16 : 0);
     if (!fast && bpp == 4) tuned = false;
     if (bpp == 3 && ((((uintptr_t)j.dst | (uintptr_t)(uint32_t)j.dst_stride) & 15) != 0)) tuned = false;
     if ((((uintptr_t)j.y | (uintptr_t)j.u | (uintptr_t)j.v | (uintptr_t)j.a | (uintptr_t)(uint32_t)j.y_stride |

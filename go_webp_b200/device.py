@@ -88,6 +88,16 @@ class Context:
             pass
 
     @property
+    def swap_16bit_csp(self) -> bool:
+        """Byte order of the 16-bit output modes, library-wide: True (default) = the go-webp text
+        (WEBP_SWAP_16BIT_CSP: ba / gb byte first), False = the stock libwebp build (rg first)."""
+        return bool(self.lib.b2_ctx_swap_16bit_csp(self.h))
+
+    @swap_16bit_csp.setter
+    def swap_16bit_csp(self, swap: bool):
+        self._chk(self.lib.b2_ctx_set_swap_16bit_csp(self.h, int(bool(swap))))
+
+    @property
     def sm_count(self) -> int:
         return self.lib.b2_ctx_sm_count(self.h)
 

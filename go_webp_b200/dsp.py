@@ -266,7 +266,9 @@ def _convert(fn_name, uploads, make_job, out_ptr_index, out_shape, out_dtype, ex
 def VP8LConvertFromBGRA(in_data: np.ndarray, num_pixels: int | None, out_colorspace: int,
                         upstream_16bit_order: bool = False) -> np.ndarray:
     """lossless.go:616-666.  in_data: uint32 pixels ([h, w] or flat); returns the bytes of
-    'out_colorspace' ([h, w*bpp]).  Premultiplied modes include WebPApplyAlphaMultiply."""
+    'out_colorspace' ([h, w*bpp]).  Premultiplied modes include WebPApplyAlphaMultiply.
+    16-bit modes: the context's order (Context.swap_16bit_csp, default the Go text's);
+    upstream_16bit_order forces the stock libwebp order for this call."""
     src = np.ascontiguousarray(in_data, np.uint32)
     if src.ndim == 1:
         src = src[:num_pixels].reshape(1, -1)
@@ -285,8 +287,11 @@ def WebPApplyAlphaMultiply(rgba: np.ndarray, alpha_first: int, w: int, h: int, s
                     0, (h, stride), np.uint8, (_abi.ALPHA_APPLY, int(alpha_first)))
 
 
-def WebPApplyAlphaMultiply4444(rgba4444: np.ndarray, w: int, h: int, stride: int, rg_byte_pos: int = 1) -> np.ndarray:
-    """ApplyAlphaMultiply4444_C (alpha_processing.go:141-163; the Go text binds rg_byte_pos = 1)."""
+def WebPApplyAlphaMultiply4444(rgba4444: np.ndarray, w: int, h: int, stride: int, rg_byte_pos: int | None = None) -> np.ndarray:
+    """ApplyAlphaMultiply4444_C (alpha_processing.go:141-163).  rg_byte_pos defaults to the context's 16-bit
+    order: 1 with the Go text's (the value it binds), 0 with the stock libwebp order."""
+    if rg_byte_pos is None:
+        rg_byte_pos = 1 if default_context().swap_16bit_csp else 0
     buf = np.ascontiguousarray(rgba4444, np.uint8).reshape(h, stride)
     return _convert("b2_alpha_multiply", [buf], lambda p, po: _abi.ConvertJob(None, None, None, po, 0, 0, stride, w, h, 0),
                     0, (h, stride), np.uint8, (_abi.ALPHA_APPLY_4444, int(rg_byte_pos)))

@@ -14,7 +14,9 @@ from .picture import _al, _arena, default_context
 WEBP_FILTER_NONE, WEBP_FILTER_HORIZONTAL, WEBP_FILTER_VERTICAL, WEBP_FILTER_GRADIENT = 0, 1, 2, 3
 
 
-def _run(planes, filters, unfilter: bool, ctx: Context | None):
+def _run(planes, filters, unfilter: bool, ctx: Context | None, row_align: int = 16, ptr_offset: int = 0):
+    """row_align: alignment of the device row stride (1 = tightly packed rows); ptr_offset: bytes added to
+    both plane pointers -- the two knobs that take the kernels off their word-aligned paths."""
     ctx = ctx or default_context()
     lib, hnd = ctx.lib, ctx.h
     n = len(planes)
@@ -23,14 +25,14 @@ def _run(planes, filters, unfilter: bool, ctx: Context | None):
     metas, need = [], 0
     for p in planes:
         h, w = p.shape
-        st = _al(w, 16)
+        st = _al(w, row_align)
         metas.append((w, h, st))
-        need += 2 * _al(st * h)
+        need += 2 * _al(st * h + ptr_offset)
     ar = _arena(ctx)
     ar.reset(need)
     jobs, outs_ptr = [], []
     for (w, h, st), p, f in zip(metas, planes, filters):
-        ps, pd = ar.take(st * h), ar.take(st * h)
+        ps, pd = ar.take(st * h + ptr_offset) + ptr_offset, ar.take(st * h + ptr_offset) + ptr_offset
         p = np.ascontiguousarray(p, np.uint8)
         ctx._chk(lib.b2_h2d_2d_async(hnd, 0, ps, st, p.ctypes.data, w, w, h))
         jobs.append(_abi.AlphaFilterJob(ps, pd, st, st, w, h, int(f), 0))
@@ -97,16 +99,16 @@ def WebPDequantizeLevels(data: np.ndarray, width: int, height: int, stride: int,
     return True
 
 
-def AlphaUnfilterBatch(planes, filters, ctx: Context | None = None):
+def AlphaUnfilterBatch(planes, filters, ctx: Context | None = None, row_align: int = 16, ptr_offset: int = 0):
     """Added batched entry point: planes[i] (uint8 [h, w], the filtered alpha plane the ALPH
     chunk decodes to) unfiltered with WebPUnfilters[filters[i]] exactly as the row loop of
     the alpha decoder does (prev = the previous output row, nil for the first)."""
-    return _run(planes, filters, True, ctx)
+    return _run(planes, filters, True, ctx, row_align, ptr_offset)
 
 
-def AlphaFilterBatch(planes, filters, ctx: Context | None = None):
+def AlphaFilterBatch(planes, filters, ctx: Context | None = None, row_align: int = 16, ptr_offset: int = 0):
     """Added batched entry point: WebPFilters[filters[i]] on whole planes (filter 0 copies)."""
-    return _run(planes, filters, False, ctx)
+    return _run(planes, filters, False, ctx, row_align, ptr_offset)
 
 
 def HorizontalFilter_C(data: np.ndarray, width: int, height: int, stride: int, filtered_data: np.ndarray) -> None:

@@ -48,6 +48,16 @@ int b2_device_count(int* count);
 /* One context per GPU.  n_streams in [1,16]. */
 int b2_ctx_create(int device, int n_streams, b2_ctx** out);
 void b2_ctx_destroy(b2_ctx* ctx);
+/* Byte order of the 16-bit output modes (MODE_RGBA_4444, MODE_rgbA_4444, MODE_RGB_565), ONE setting for
+ * every producer and consumer of such pixels (fancy upsampler, point samplers, YUV444 converters,
+ * VP8LConvertFromBGRA, the alpha nibble of EmitAlphaRGBA4444, ApplyAlphaMultiply4444's default
+ * rg_byte_pos in the host mirror).  swap = 1 (default): the order the go-webp text has everywhere --
+ * libwebp built with WEBP_SWAP_16BIT_CSP, the ba / gb byte first (pkg/libwebp/dsp/lossless.go:575-600,
+ * pkg/libwebp/decoder/io_dec.c.go:197-226 writes the alpha nibble into byte 2i,
+ * ApplyAlphaMultiply_16b_C is bound with rg_byte_pos = 1).  swap = 0: the stock libwebp build (rg byte
+ * first), which is what the libwebp 1.6.0 binary behind the golden vectors produces. */
+int b2_ctx_set_swap_16bit_csp(b2_ctx* ctx, int swap);
+int b2_ctx_swap_16bit_csp(const b2_ctx* ctx);
 int b2_ctx_device(const b2_ctx* ctx);
 int b2_ctx_sm_count(const b2_ctx* ctx);
 const char* b2_last_error(const b2_ctx* ctx);
@@ -234,8 +244,10 @@ int b2_vp8l_apply_palette(b2_ctx* ctx, int stream, const b2_palette_job* jobs, i
  * data = mode image, ceil(w/2^bits) x ceil(h/2^bits) words, mode in bits 8..11
  * (lossless.go:313); bits in [2,9]; dst must not alias src.
  * Inverse: PredictorInverseTransform_C + PredictorAdd0..13_C over whole images
- * (pkg/libwebp/dsp/lossless.go:31-333): src = residuals, dst = pixels.  Runs as one
- * launch per wavefront diagonal (see b2_predict.cu).
+ * (pkg/libwebp/dsp/lossless.go:31-333): src = residuals, dst = pixels.  Runs as ONE
+ * persistent launch: warps take 32-row bands from a ticket counter and walk them as a
+ * skewed wavefront, waiting on the band above through a progress word (see b2_predict.cu;
+ * a waited-on band always holds a lower ticket, so it is running: no deadlock).
  * Forward: PredictorSub0..13_C with the given modes (lossless_enc.go:339-557, driven as
  * pkg/libwebp/enc/predictor_enc.go:666-712): src = pixels, dst = residuals. */
 int b2_vp8l_predictor_inverse(b2_ctx* ctx, int stream, const b2_argb_job* jobs, int n_jobs);
@@ -258,9 +270,9 @@ typedef struct b2_convert_job {
 /* VP8LConvertFromBGRA (pkg/libwebp/dsp/lossless.go:616-666) with its row converters
  * (:549-614) and, for the premultiplied modes, WebPApplyAlphaMultiply{,4444}
  * (pkg/libwebp/dsp/alpha_processing.go:100-163).  mode: WEBP_CSP_MODE.  The 16-bit
- * modes write the ba / gb byte first as the Go text does (lossless.go:581-584,593-596:
- * upstream built with WEBP_SWAP_16BIT_CSP); B2_CONVERT_UPSTREAM_16BIT in flags selects
- * the upstream default order (rg first). */
+ * modes follow the context's order (b2_ctx_set_swap_16bit_csp; default: ba / gb byte first as
+ * the Go text does, lossless.go:581-584,593-596); B2_CONVERT_UPSTREAM_16BIT in flags forces
+ * the stock libwebp order (rg first) for this call whatever the context says. */
 #define B2_CONVERT_UPSTREAM_16BIT 0x1
 int b2_vp8l_convert_from_bgra(b2_ctx* ctx, int stream, const b2_convert_job* jobs, int n_jobs, int mode, int flags);
 

@@ -105,7 +105,16 @@ def import_yuva(src: np.ndarray, width: int, height: int, order: str = "RGBA",
     return y, u, v, a, bool(ha)
 
 
-def yuva_to_rgba(y, u, v, a=None, mode: int = MODE_RGBA):
+def _swap16(out, mode, swap16):
+    """16-bit modes in the go-webp text's byte order (WEBP_SWAP_16BIT_CSP: ba / gb first) instead of the
+    stock libwebp build's (rg first), which is what the C functions here and the golden binary produce."""
+    if swap16 and mode in (5, 6, 10):
+        h = out.shape[0]
+        return np.ascontiguousarray(out.reshape(h, -1, 2)[:, :, ::-1]).reshape(h, -1)
+    return out
+
+
+def yuva_to_rgba(y, u, v, a=None, mode: int = MODE_RGBA, swap16: bool = False):
     h, w = y.shape
     y = np.ascontiguousarray(y, np.uint8)
     u = np.ascontiguousarray(u, np.uint8)
@@ -118,10 +127,10 @@ def yuva_to_rgba(y, u, v, a=None, mode: int = MODE_RGBA):
                                 _p(a), w, w, h, _p(dst), w * bpp)
     if not ok:
         raise ValueError("orc_yuva_to_rgba: bad arguments")
-    return dst
+    return _swap16(dst, mode, swap16)
 
 
-def emit_fancy_stream(y, u, v, splits, mode: int = MODE_RGBA):
+def emit_fancy_stream(y, u, v, splits, mode: int = MODE_RGBA, swap16: bool = False):
     h, w = y.shape
     bpp = lib().orc_mode_bpp(mode)
     dst = np.zeros((h, w * bpp), np.uint8)
@@ -130,7 +139,7 @@ def emit_fancy_stream(y, u, v, splits, mode: int = MODE_RGBA):
         mode, _p(np.ascontiguousarray(y)), w, _p(np.ascontiguousarray(u)),
         _p(np.ascontiguousarray(v)), u.shape[1], w, h, _p(sp), len(sp), _p(dst),
         w * bpp)
-    return dst, n
+    return _swap16(dst, mode, swap16), n
 
 
 def upsample_line_pair(mode, top_y, bottom_y, top_u, top_v, cur_u, cur_v):
@@ -316,24 +325,24 @@ def mult_rows(plane, alpha, inverse):
     return out
 
 
-def sampler_process_plane(y, u, v, mode):
+def sampler_process_plane(y, u, v, mode, swap16: bool = False):
     """WebPSamplerProcessPlane (dsp/yuv.go:47-58) = EmitSampledRGB: point-sampled chroma."""
     y, u, v = (np.ascontiguousarray(x, np.uint8) for x in (y, u, v))
     h, w = y.shape
     bpp = lib().orc_mode_bpp(mode)
     dst = np.zeros((h, w * bpp), np.uint8)
     lib().orc_sampler_process_plane(mode, _p(y), w, _p(u), _p(v), u.shape[1], _p(dst), w * bpp, w, h)
-    return dst
+    return _swap16(dst, mode, swap16)
 
 
-def yuv444_to_rgb(y, u, v, mode):
+def yuv444_to_rgb(y, u, v, mode, swap16: bool = False):
     y, u, v = (np.ascontiguousarray(x, np.uint8) for x in (y, u, v))
     h, w = y.shape
     bpp = lib().orc_mode_bpp(mode)
     dst = np.zeros((h, w * bpp), np.uint8)
     for r in range(h):
         lib().orc_yuv444_row(mode, _p(y[r]), _p(u[r]), _p(v[r]), _p(dst[r]), w)
-    return dst
+    return _swap16(dst, mode, swap16)
 
 
 # ---- picture pre-processing (oracle_tools.c, SURVEY 8f-3) -------------------------

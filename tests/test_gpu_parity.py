@@ -164,9 +164,11 @@ def test_import_error_behaviour(gpu):
 
 
 # ---- part 2 ---------------------------------------------------------------------
-@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10])
 def test_upsample_size_sweep_batched(gpu, mode):
+    """Every WEBP_CSP_MODE; the 16-bit ones in the context's default order (the Go text's, ba / gb first)."""
     P = gpu["picture"]
+    assert gpu["ctx"].swap_16bit_csp
     rng = np.random.default_rng(100 + mode)
     for with_a in (False, True):
         pics, exps = [], []
@@ -178,8 +180,8 @@ def test_upsample_size_sweep_batched(gpu, mode):
             a = rng.integers(0, 256, (h, w), dtype=np.uint8) if with_a else None
             pics.append(P.Picture(Width=w, Height=h, Y=y, U=u, V=v, A=a,
                                   ColorSpace=P.WEBP_YUV420A if with_a else P.WEBP_YUV420))
-            omode = {7: 1, 8: 3, 9: 4}.get(mode, mode)  # premultiplied modes alias (upsampling.c.go:280-288)
-            exps.append(oracle.yuva_to_rgba(y, u, v, a, omode))
+            omode = {7: 1, 8: 3, 9: 4, 10: 5}.get(mode, mode)  # premultiplied modes alias (upsampling.c.go:280-288)
+            exps.append(oracle.yuva_to_rgba(y, u, v, a, omode, swap16=True))
         outs = P.YUVAToRGBABatch(pics, mode, chunk=7)
         assert outs is not None
         for o, e, s in zip(outs, exps, SIZES):
@@ -199,18 +201,23 @@ def test_upsample_golden_libwebp(gpu, golden_dir):
 
 
 def test_decoder_golden_all_modes(gpu, golden_dir):
-    """Real lossy files decoded by libwebp 1.6.0: planes in, every RGB mode out."""
+    """Real lossy files decoded by libwebp 1.6.0: planes in, every RGB mode out.  The binary is the stock
+    build (rg byte first in the 16-bit modes): the context is switched to that order for the comparison."""
     P = gpu["picture"]
     g = np.load(os.path.join(golden_dir, "decode_libwebp160.npz"))
-    for i in range(int(g["n"][0])):
-        y, u, v, a = g[f"c{i}_y"], g[f"c{i}_u"], g[f"c{i}_v"], g[f"c{i}_a"]
-        h, w = y.shape
-        for mode in range(7):
-            pic = P.Picture(Width=w, Height=h, Y=y, U=u, V=v, A=a if a.size else None,
-                            ColorSpace=P.WEBP_YUV420A if a.size else P.WEBP_YUV420)
-            got = P.YUVAToRGBABatch([pic], mode)[0]
-            exp = g[f"c{i}_m{mode}"]
-            assert (got == exp).all(), (i, mode)
+    gpu["ctx"].swap_16bit_csp = False
+    try:
+        for i in range(int(g["n"][0])):
+            y, u, v, a = g[f"c{i}_y"], g[f"c{i}_u"], g[f"c{i}_v"], g[f"c{i}_a"]
+            h, w = y.shape
+            for mode in range(7):
+                pic = P.Picture(Width=w, Height=h, Y=y, U=u, V=v, A=a if a.size else None,
+                                ColorSpace=P.WEBP_YUV420A if a.size else P.WEBP_YUV420)
+                got = P.YUVAToRGBABatch([pic], mode)[0]
+                exp = g[f"c{i}_m{mode}"]
+                assert (got == exp).all(), (i, mode)
+    finally:
+        gpu["ctx"].swap_16bit_csp = True
 
 
 def test_upsample_line_pair_table(gpu):
@@ -560,7 +567,7 @@ def test_emit_fancy_rgb_streaming(gpu):
         u = rng.integers(0, 256, (uh, uw), dtype=np.uint8)
         v = rng.integers(0, 256, (uh, uw), dtype=np.uint8)
         a = rng.integers(0, 256, (h, w), dtype=np.uint8) if alpha else None
-        exp = oracle.yuva_to_rgba(y, u, v, a, mode)
+        exp = oracle.yuva_to_rgba(y, u, v, a, mode, swap16=True)
         pic = P.Picture(Width=w, Height=h, ColorSpace=P.WEBP_YUV420A if alpha else P.WEBP_YUV420, Y=y, U=u, V=v, A=a)
         bpp = A.MODE_BPP[mode]
         dst = np.full((h, w * bpp), 0xA5, np.uint8)
@@ -634,10 +641,10 @@ def test_point_sampler_and_yuv444(gpu, mode):
         y = rng.integers(0, 256, (h, w), dtype=np.uint8)
         u = rng.integers(0, 256, ((h + 1) // 2, (w + 1) // 2), dtype=np.uint8)
         v = rng.integers(0, 256, ((h + 1) // 2, (w + 1) // 2), dtype=np.uint8)
-        assert (D.WebPSamplerProcessPlane(y, u, v, mode) == oracle.sampler_process_plane(y, u, v, mode)).all(), (w, h, mode)
+        assert (D.WebPSamplerProcessPlane(y, u, v, mode) == oracle.sampler_process_plane(y, u, v, mode, swap16=True)).all(), (w, h, mode)
         u4 = rng.integers(0, 256, (h, w), dtype=np.uint8)
         v4 = rng.integers(0, 256, (h, w), dtype=np.uint8)
-        assert (D.WebPYUV444ToRGB(y, u4, v4, mode) == oracle.yuv444_to_rgb(y, u4, v4, mode)).all(), (w, h, mode)
+        assert (D.WebPYUV444ToRGB(y, u4, v4, mode) == oracle.yuv444_to_rgb(y, u4, v4, mode, swap16=True)).all(), (w, h, mode)
 
 
 def test_vp8l_golden_libwebp_streams(gpu, golden_dir):
@@ -919,6 +926,21 @@ def test_alpha_filters(gpu, golden_dir):
     back = F.AlphaFilterBatch(un, filts)
     for p, f, o in zip(planes, filts, back):
         assert (o == p).all() and (o == oracle.alpha_filter(oracle.alpha_unfilter(p, f), f)).all(), (p.shape, f)
+    # rows and pointers that are NOT word aligned (the byte-wise gradient wavefront with its
+    # packed / done & ~3 / ragged-tail logic, the non-aligned horizontal and vertical unfilters, the scalar
+    # forward filter) and planes taller than 512 rows (a warp goes through more than 16 bands)
+    planes, filts = [], []
+    for (w, h) in [(1, 3), (3, 70), (37, 41), (129, 33), (255, 130), (301, 35), (130, 700), (64, 1030)]:
+        for f in range(4):
+            planes.append(rng.integers(0, 256, (h, w), dtype=np.uint8))
+            filts.append(f)
+    for (row_align, ptr_offset) in [(1, 0), (1, 1), (4, 2), (16, 3), (2, 5)]:
+        un = F.AlphaUnfilterBatch(planes, filts, row_align=row_align, ptr_offset=ptr_offset)
+        for p, f, o in zip(planes, filts, un):
+            assert (o == oracle.alpha_unfilter(p, f)).all(), (p.shape, f, row_align, ptr_offset)
+        back = F.AlphaFilterBatch(un, filts, row_align=row_align, ptr_offset=ptr_offset)
+        for p, f, o in zip(planes, filts, back):
+            assert (o == p).all(), (p.shape, f, row_align, ptr_offset)
     data = rng.integers(0, 256, 40 * 7, dtype=np.uint8)
     out = np.zeros_like(data)
     F.GradientFilter_C(data, 33, 7, 40, out)
@@ -1133,3 +1155,59 @@ def test_apply_palette_full_size_round_trip(gpu):
         img, o = p.device_image(3)
         assert (o == oracle.apply_palette(img, p.palettes[3], p.xbits)[0]).all()
         p.close()
+
+
+def test_16bit_order_is_library_wide(gpu):
+    """one byte order for the 16-bit modes across a decode path.  The reference flow for
+    MODE_rgbA_4444 is upsample (VP8YuvToRgba4444) -> EmitAlphaRGBA4444 (alpha nibble into byte 2i,
+    io_dec.c.go:197-226) -> WebPApplyAlphaMultiply4444 (rg_byte_pos = 1 in the Go text): with the default
+    context every step uses the Go text's order, with swap_16bit_csp = False every step uses the stock
+    libwebp order, and lossy and lossless outputs of one colourspace share a layout."""
+    P, D, A, ctx = gpu["picture"], gpu["dsp"], gpu["abi"], gpu["ctx"]
+    rng = np.random.default_rng(41)
+    w, h = 37, 9
+    uw, uh = (w + 1) // 2, (h + 1) // 2
+    y = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    u = rng.integers(0, 256, (uh, uw), dtype=np.uint8)
+    v = rng.integers(0, 256, (uh, uw), dtype=np.uint8)
+    a = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    argb = rng.integers(0, 2**32, (h, w), dtype=np.uint32)
+    try:
+        for swap in (True, False):
+            ctx.swap_16bit_csp = swap
+            pic = P.Picture(Width=w, Height=h, ColorSpace=P.WEBP_YUV420A, Y=y, U=u, V=v, A=a)
+            up = P.YUVAToRGBABatch([pic], A.MODE_rgbA_4444)[0]
+            e_up = oracle.yuva_to_rgba(y, u, v, a, A.MODE_RGBA_4444, swap16=swap)
+            assert (up == e_up).all()
+            got = D.WebPApplyAlphaMultiply4444(up, w, h, 2 * w)       # default rg_byte_pos follows the context
+            assert (got == oracle.apply_alpha_multiply_4444(e_up, 1 if swap else 0)).all()
+            # the alpha nibble really is in the ba byte: byte 2i with the Go order, 2i + 1 with the stock one
+            assert ((up[:, (0 if swap else 1)::2] & 0x0f) == (a >> 4)).all()
+            # lossless output of the same colourspace, premultiplied in one go: same layout
+            ll = D.VP8LConvertFromBGRA(argb, None, A.MODE_rgbA_4444)
+            assert (ll == oracle.convert_from_bgra(argb, A.MODE_rgbA_4444, 0 if swap else 1)).all()
+            for mode in (A.MODE_RGB_565, A.MODE_RGBA_4444):
+                s1 = D.WebPSamplerProcessPlane(y, u, v, mode)
+                assert (s1 == oracle.sampler_process_plane(y, u, v, mode, swap16=swap)).all()
+    finally:
+        ctx.swap_16bit_csp = True
+
+
+def test_dithered_import_descriptor_ring_wrap(gpu):
+    """the dithered import uploads its job table and then 660 B of jump polynomials per
+    image before the kernels that read both run.  With ~5700-6350 images the pair crosses the end of
+    the 4 MB descriptor ring of a fresh stream; the second upload must not land on the first."""
+    from go_webp_b200.device import Context
+    P = gpu["picture"]
+    ctx = Context(0, n_streams=1)          # fresh ring: offset 0
+    rng = np.random.default_rng(61)
+    n, w, h = 6000, 4, 2
+    srcs = [rng.integers(0, 256, (h, 4 * w), dtype=np.uint8) for _ in range(n)]
+    pics = [P.Picture(Width=w, Height=h) for _ in range(n)]
+    assert P.ImportRGBABatch(pics, srcs, [4 * w] * n, "BGRA", ctx=ctx, dithering=0.6, chunk=n) == 1
+    for i in list(range(0, n, 397)) + [n - 1]:
+        y, u, v, a, ha = oracle.import_yuva_dithered(srcs[i], w, h, 0.6, "BGRA")
+        assert (pics[i].Y == y).all() and (pics[i].U == u).all() and (pics[i].V == v).all(), i
+    for p in pics:
+        P.WebPPictureFree(p)
+    ctx.close()

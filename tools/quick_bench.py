@@ -199,3 +199,18 @@ if "convert" in which:
         report(f"anim blend rows premult={premult} {n}x1080p", n * w * h, 12.0, timed(lambda: ctx._chk(ctx.lib.b2_anim_blend_rows(ctx.h, 0, jobs, n, premult)), 5))
     for b in (argb, out, yp, up, vp):
         b.free()
+if "palette" in which:
+    from go_webp_b200.pipeline import PalettePipeline
+    for psize, bpp in ((256, 8.0), (16, 4.5), (4, 4.25), (2, 4.125)):
+        nf = int(os.environ.get("B2_ARGB_FRAMES", "16"))
+        p = PalettePipeline(ctx, nf, 4096, 4096, psize)
+        p.fill_synthetic(0xB2000003)
+        ms = timed(p.run_device, 10)
+        report(f"apply_palette {psize} colours xbits={p.xbits} {nf}x4096^2 ({ms * 1e3:.0f} us)", nf * 4096 * 4096, bpp, ms)
+        p.close()
+if "up1080" in which:
+    for mode, wa, bpp, name in ((_abi.MODE_RGBA, False, 5.5, "RGBA"), (_abi.MODE_BGRA, True, 6.5, "BGRA+A"), (_abi.MODE_RGB, False, 4.5, "RGB")):
+        p = UpsamplePipeline(ctx, 256, 1920, 1080, mode, with_alpha=wa, host=False)
+        p.fill_synthetic(0xB2000004)
+        report(f"upsample 256x1080p {name}", 256 * 1920 * 1080, bpp, timed(p.run_device))
+        p.close()

@@ -13,7 +13,7 @@ while [ $# -ge 2 ]; do
   nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -Xptxas -v --use_fast_math $flags \
     -c $src.cu -o build/variants/v_$name.o 2> build/variants/v_$name.log
   objs=""
-  for o in b2_ctx b2_import b2_import_fast b2_upsample b2_vp8l b2_extra b2_predict b2_convert b2_tools b2_dither b2_anim b2_filters b2_rescale b2_dequant; do
+  for o in b2_ctx b2_import b2_import_fast b2_upsample b2_vp8l b2_extra b2_predict b2_convert b2_tools b2_dither b2_anim b2_filters b2_rescale b2_dequant b2_staged b2_palette; do
     if [ $o = $src ]; then objs="$objs build/variants/v_$name.o"; else objs="$objs build/$o.o"; fi
   done
   nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../lib/variants/libb2webp_$name.so $objs -cudart static

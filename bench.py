@@ -398,6 +398,18 @@ def config2_vp8l(ctx, D, peak, steps, total_images=64, e2e_images=16):
                           "api": "b2_vp8l_batch_staged(B2_VP8L_INVERSE_CHAIN) = dsp.VP8LInverseTransformBatch's call, pinned buffers",
                           "sample": f"{m} images per rank per step", "h2d_bytes_per_step": ap.h2d_bytes, "d2h_bytes_per_step": ap.d2h_bytes}
         ap.close()
+    # the whole chain libwebp's encoder writes (cross-colour, predictor, subtract-green), one pass vs three launches
+    from go_webp_b200.pipeline import ChainPipeline
+    cp = ChainPipeline(ctx, n, w, h, 5)
+    cp.fill_synthetic(0xB2000003, first_img=mine.start)
+    ms_f = timed_device(ctx, D, cp.run_device, 3)
+    ms_u = timed_device(ctx, D, cp.run_unfused, 3)
+    px = total_images * w * h
+    out["kernels"]["full_chain_fused_one_pass"] = {"mpixel_per_s": px / ms_f / 1e3, "ms_per_step": ms_f, "bytes_per_px": 8.008,
+                                                   "frac": n * w * h * 8.008 / ms_f / 1e6 / peak}
+    out["kernels"]["full_chain_three_launches"] = {"mpixel_per_s": px / ms_u / 1e3, "ms_per_step": ms_u, "bytes_per_px": 24.008,
+                                                   "speedup_of_fused": ms_u / ms_f}
+    cp.close()
     kk = out["kernels"]["crosscolor_inv_addgreen_fused"]
     out.update({"value": kk["mpixel_per_s"], "unit": "Mpixel/s", "ms_per_step": kk["ms_per_step"],
                 "roofline": {"bound": "hbm", "bytes_per_px": 8.0039, "frac": kk["frac"], "peak": peak, "unit": "GB/s", "per": "GPU"}})

@@ -104,6 +104,17 @@ class PaletteJob(C.Structure):
                 ("xbits", C.c_int32)]
 
 
+class ChainJob(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("predictor_data", C.c_void_p), ("color_data", C.c_void_p),
+                ("width", C.c_int32), ("height", C.c_int32), ("predictor_bits", C.c_int32), ("color_bits", C.c_int32),
+                ("add_green", C.c_int32), ("reserved", C.c_int32)]
+
+
+class ChainHost(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("predictor_data", C.c_void_p), ("color_data", C.c_void_p),
+                ("predictor_bytes", C.c_size_t), ("color_bytes", C.c_size_t)]
+
+
 class ImportHost(C.Structure):
     _fields_ = [("src", C.c_void_p), ("y", C.c_void_p), ("u", C.c_void_p), ("v", C.c_void_p), ("a", C.c_void_p),
                 ("y_stride", C.c_int32), ("uv_stride", C.c_int32), ("a_stride", C.c_int32), ("reserved", C.c_int32)]
@@ -174,6 +185,8 @@ SYMBOLS = {
     "b2_vp8l_bundle_color_map": (C.c_int, [_ctx, C.c_int, C.POINTER(ArgbJob), C.c_int]),
     "b2_vp8l_apply_palette": (C.c_int, [_ctx, C.c_int, C.POINTER(PaletteJob), C.c_int]),
     "b2_vp8l_predictor_inverse": (C.c_int, [_ctx, C.c_int, C.POINTER(ArgbJob), C.c_int]),
+    "b2_vp8l_predictor_inverse_chain": (C.c_int, [_ctx, C.c_int, C.POINTER(ChainJob), C.c_int, C.c_int]),
+    "b2_vp8l_chain_batch_staged": (C.c_int, [_ctx, C.POINTER(ChainJob), C.POINTER(ChainHost), C.c_int, C.c_int, C.c_int]),
     "b2_vp8l_predictor_forward": (C.c_int, [_ctx, C.c_int, C.POINTER(ArgbJob), C.c_int]),
     "b2_vp8l_convert_from_bgra": (C.c_int, [_ctx, C.c_int, C.POINTER(ConvertJob), C.c_int, C.c_int, C.c_int]),
     "b2_alpha_multiply": (C.c_int, [_ctx, C.c_int, C.POINTER(ConvertJob), C.c_int, C.c_int, C.c_int]),

@@ -453,5 +453,14 @@ extern "C" int b2_rgba_to_yuv420a(b2_ctx* ctx, int stream, const b2_import_job* 
 
 extern "C" int b2_rgba_to_yuv420a_dithered(b2_ctx* ctx, int stream, const b2_import_job* jobs, int n_jobs,
                                            int order, int flags, int32_t* has_alpha_dev, float dithering) {
-  return import_impl(ctx, stream, jobs, n_jobs, order, flags, has_alpha_dev, dithering);
+  // 732 B of descriptors + jump polynomials per image must fit the 4 MB ring together: big batches go in
+  // slices (every image has its own generator, so the slicing changes nothing)
+  const int kSlice = 4096;
+  if (jobs == NULL || n_jobs <= kSlice) return import_impl(ctx, stream, jobs, n_jobs, order, flags, has_alpha_dev, dithering);
+  for (int i = 0; i < n_jobs; i += kSlice) {
+    const int m = (n_jobs - i < kSlice) ? n_jobs - i : kSlice;
+    const int st = import_impl(ctx, stream, jobs + i, m, order, flags, has_alpha_dev ? has_alpha_dev + i : NULL, dithering);
+    if (st != B2_OK) return st;
+  }
+  return B2_OK;
 }

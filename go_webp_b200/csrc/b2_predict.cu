@@ -42,7 +42,15 @@ struct PredJobDev {
   uint32_t tiles_per_row;  // mode image row length
   uint32_t bands;          // ceil(height / 32)
   uint32_t flag_off;       // first progress counter of this image (one per band)
+  // fused chain (b2_vp8l_predictor_inverse_chain): cross-colour inverse on the way in, add-green and a
+  // byte-order change on the way out
+  const uint32_t* codes;   // cross-colour tile codes, or NULL
+  int32_t cbits;
+  uint32_t ctiles_per_row;
+  uint32_t chain;          // CH_* bits
+  uint32_t pad;
 };
+enum { CH_CC = 1, CH_GREEN = 2, CH_RGBA = 4, CH_ARGB = 8 };
 
 // ---- pixel arithmetic (lossless_common.go:110-121, lossless.go:31-149) -----------
 __device__ __forceinline__ uint32_t add_pixels(uint32_t a, uint32_t b) {
@@ -266,6 +274,45 @@ __device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
 
+// ---- fused chain pieces (lossless.go:337-374) ----------------------------------------
+__device__ __forceinline__ uint32_t add_green_px(uint32_t argb) {
+  const uint32_t green = (argb >> 8) & 0xff;
+  uint32_t rb = argb & 0x00ff00ffu;
+  rb += (green << 16) | green;
+  return (argb & 0xff00ff00u) | (rb & 0x00ff00ffu);
+}
+__device__ __forceinline__ uint32_t sub_green_px(uint32_t argb) {
+  const uint32_t green = (argb >> 8) & 0xff;
+  uint32_t rb = (argb & 0x00ff00ffu) | 0x01000100u;
+  rb -= (green << 16) | green;
+  return (argb & 0xff00ff00u) | (rb & 0x00ff00ffu);
+}
+__device__ __forceinline__ uint32_t cc_inverse_px(uint32_t code, uint32_t argb) {  // VP8LTransformColorInverse_C
+  const int g2r = (int)(int8_t)(code & 0xff), g2b = (int)(int8_t)((code >> 8) & 0xff), r2b = (int)(int8_t)((code >> 16) & 0xff);
+  const int green = (int)(int8_t)((argb >> 8) & 0xff);
+  int new_red = (int)((argb >> 16) & 0xff);
+  int new_blue = (int)(argb & 0xff);
+  new_red = (new_red + ((g2r * green) >> 5)) & 0xff;
+  new_blue += (g2b * green) >> 5;
+  new_blue += (r2b * (int)(int8_t)new_red) >> 5;
+  new_blue &= 0xff;
+  return (argb & 0xff00ff00u) | ((uint32_t)new_red << 16) | (uint32_t)new_blue;
+}
+// What leaves the kernel for a reconstructed pixel o (uint32 0xAARRGGBB = bytes B,G,R,A), and its inverse
+// (the row above a band is read back from the output image).  chain is warp-uniform.
+__device__ __forceinline__ uint32_t chain_out(uint32_t chain, uint32_t o) {
+  if (chain & CH_GREEN) o = add_green_px(o);
+  if (chain & CH_RGBA) o = __byte_perm(o, 0u, 0x3012);        // B,G,R,A -> R,G,B,A (VP8LConvertBGRAToRGBA_C)
+  else if (chain & CH_ARGB) o = __byte_perm(o, 0u, 0x0123);   // -> A,R,G,B (CopyOrSwap, lossless.go:598-614)
+  return o;
+}
+__device__ __forceinline__ uint32_t chain_back(uint32_t chain, uint32_t v) {
+  if (chain & CH_RGBA) v = __byte_perm(v, 0u, 0x3012);        // R,G,B,A -> B,G,R,A (the permutation is its own inverse)
+  else if (chain & CH_ARGB) v = __byte_perm(v, 0u, 0x0123);
+  if (chain & CH_GREEN) v = sub_green_px(v);
+  return v;
+}
+
 // predict() without divergent branches: the serial chain of the wavefront is one step long,
 // and a divergent switch (the lanes of a band sit in 2-3 different mode tiles) costs more
 // than computing the candidates.  `need` = warp-wide union of the modes in use (bit m set
@@ -311,6 +358,14 @@ __device__ __forceinline__ void inverse_band(const PredJobDev* __restrict__ jp, 
   const uint32_t* flag_up = flags + jp->flag_off + i - 1;
   uint32_t* flag_me = flags + jp->flag_off + i;
   const bool publish = (lane == 31) && (i + 1 < jp->bands);
+  const uint32_t chain = jp->chain;                                  // warp-uniform
+  const int cbits = jp->cbits;
+  const uint32_t* __restrict__ code_row = (chain & CH_CC) ? jp->codes + (size_t)(row >> cbits) * jp->ctiles_per_row : nullptr;
+  const int ct_last = (int)jp->ctiles_per_row - 1;
+  auto load_code = [&](int ct) -> uint32_t {
+    return (row_ok && ct <= ct_last) ? __ldg(code_row + ct) : 0u;
+  };
+  uint32_t code = 0, code_nxt = (chain & CH_CC) ? load_code(0) : 0u;
   uint32_t avail = 0;            // columns of up_row known to be complete
   uint32_t upc = 0;              // lane q: up_row[k0 + 1 + q] of the current 32-column chunk
   uint32_t left = 0, tl = 0, t = 0, first_px = 0;   // left doubles as the value the lane below takes as TR
@@ -342,6 +397,7 @@ __device__ __forceinline__ void inverse_band(const PredJobDev* __restrict__ jp, 
       }
       const int col = k + 1 + lane;
       upc = (lane < kChunk && col < w) ? __ldcg(up_row + col) : 0u;
+      if (chain & ~(uint32_t)CH_CC) upc = chain_back(chain, upc);      // the image holds finished pixels
     }
     // TR = (row-1, c+1): the lane above finished it on the previous step
     uint32_t tr = __shfl_up_sync(0xffffffffu, left, 1);
@@ -371,10 +427,18 @@ __device__ __forceinline__ void inverse_band(const PredJobDev* __restrict__ jp, 
         mode = load_mode(c >> bits);
       }
       need = __reduce_or_sync(0xffffffffu, 1u << mode);
+      if (chain & CH_CC) {   // the cross-colour tile of the group, fetched like the mode
+        if (cbits >= 3) {
+          if (grp && c >= 0) { code = code_nxt; code_nxt = load_code((c + 8) >> cbits); }
+        } else if ((c & 3) == 0 && c >= 0) {
+          code = load_code(c >> cbits);
+        }
+      }
     }
     const bool active = STEADY || (row_ok && (unsigned)c < (unsigned)w);
     uint32_t res;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(res) : "r"(in_s + (uint32_t)(c & (kInSlots - 1)) * 4u) : "memory");
+    if (chain & CH_CC) res = cc_inverse_px(code, res);   // ApplyInverseTransforms order: cross-colour first (vp8l_dec.c.go:710-729)
     if (!STEADY) tr = (c == w - 1) ? first_px : tr;      // upper[x+1] of the last column wraps to the row start
     uint32_t pred = predict_flat(mode, need, left, tl, t, tr);
     if (!STEADY) {
@@ -382,7 +446,10 @@ __device__ __forceinline__ void inverse_band(const PredJobDev* __restrict__ jp, 
       pred = row0 ? ((c == 0) ? 0xff000000u : left) : pred;   // :292-295
     }
     const uint32_t o = add_pixels(res, pred);
-    asm volatile("st.shared.u32 [%0], %1;" :: "r"(out_s + (uint32_t)(c & 7) * 4u), "r"(o) : "memory");
+    // the neighbours a lane keeps (left, t, tl, first_px) are the predictor's own output; add-green and the
+    // byte order only touch what is written out
+    const uint32_t ov = (chain & ~(uint32_t)CH_CC) ? chain_out(chain, o) : o;
+    asm volatile("st.shared.u32 [%0], %1;" :: "r"(out_s + (uint32_t)(c & 7) * 4u), "r"(ov) : "memory");
     if (!STEADY) first_px = (active && c == 0) ? o : first_px;
     left = active ? o : left;
     tl = t;
@@ -448,6 +515,12 @@ predictor_inverse_wave_kernel(const PredJobDev* __restrict__ jobs, const uint32_
 // Uploads the job table and the flat-item prefix (forward), plus -- with_wave -- the
 // band-major ticket order and a zeroed control block {ticket counter, one progress
 // counter per band} for the inverse.
+// what prepare_pred needs of a job, from either ABI struct
+struct PredSrc {
+  const uint32_t* src; uint32_t* dst; const uint32_t* modes; const uint32_t* codes;
+  int32_t width, height, bits, cbits; uint32_t chain;
+};
+
 struct PredPlan {
   const PredJobDev* jobs;
   const uint32_t* prefix;
@@ -455,14 +528,15 @@ struct PredPlan {
   uint32_t* ctl;
   uint32_t uniform, total_items, total_bands;
 };
-int prepare_pred(b2_ctx* ctx, int stream, const b2_argb_job* jobs, int n_jobs, bool with_wave, PredPlan* plan) {
+int prepare_pred(b2_ctx* ctx, int stream, const PredSrc* jobs, int n_jobs, bool with_wave, PredPlan* plan) {
   uint64_t bands_all = 0;
   uint32_t max_bands = 0;
   for (int i = 0; i < n_jobs; ++i) {
-    const b2_argb_job& j = jobs[i];
-    if (j.src == NULL || j.dst == NULL || j.data == NULL) return B2_ERR_NULL;
+    const PredSrc& j = jobs[i];
+    if (j.src == NULL || j.dst == NULL || j.modes == NULL) return B2_ERR_NULL;
     if (j.width <= 0 || j.height <= 0 || j.width > B2_MAX_DIMENSION || j.height > B2_MAX_DIMENSION) return B2_ERR_BAD_DIM;
     if (j.bits < 2 || j.bits > 9 || j.src == j.dst) return B2_ERR_INVALID_CONFIG;  // vp8l_dec.c.go:1243
+    if ((j.chain & CH_CC) && (j.codes == NULL || j.cbits < 2 || j.cbits > 9)) return B2_ERR_INVALID_CONFIG;
     const uint32_t nb = (uint32_t)((j.height + 31) / 32);
     bands_all += nb;
     if (nb > max_bands) max_bands = nb;
@@ -481,10 +555,12 @@ int prepare_pred(b2_ctx* ctx, int stream, const b2_argb_job* jobs, int n_jobs, b
   uint64_t tot = 0;
   uint32_t uni = 0, flag_off = 0;
   for (int i = 0; i < n_jobs; ++i) {
-    const b2_argb_job& j = jobs[i];
+    const PredSrc& j = jobs[i];
     PredJobDev& d = dj[i];
-    d.src = j.src; d.dst = j.dst; d.modes = j.data;
+    d.src = j.src; d.dst = j.dst; d.modes = j.modes;
     d.width = j.width; d.height = j.height; d.bits = j.bits;
+    d.codes = j.codes; d.cbits = j.cbits; d.chain = j.chain; d.pad = 0;
+    d.ctiles_per_row = (j.chain & CH_CC) ? (uint32_t)((j.width + (1 << j.cbits) - 1) >> j.cbits) : 0u;
     d.tiles_per_row = (uint32_t)((j.width + (1 << j.bits) - 1) >> j.bits);
     d.bands = (uint32_t)((j.height + 31) / 32);
     d.flag_off = flag_off;
@@ -514,6 +590,16 @@ int prepare_pred(b2_ctx* ctx, int stream, const b2_argb_job* jobs, int n_jobs, b
   return B2_OK;
 }
 
+PredSrc* plain_jobs(const b2_argb_job* jobs, int n_jobs) {
+  PredSrc* ps = (PredSrc*)malloc(sizeof(PredSrc) * (size_t)n_jobs);
+  if (ps == NULL) return NULL;
+  for (int i = 0; i < n_jobs; ++i) {
+    ps[i].src = jobs[i].src; ps[i].dst = jobs[i].dst; ps[i].modes = jobs[i].data; ps[i].codes = NULL;
+    ps[i].width = jobs[i].width; ps[i].height = jobs[i].height; ps[i].bits = jobs[i].bits; ps[i].cbits = 0; ps[i].chain = 0;
+  }
+  return ps;
+}
+
 }  // namespace
 
 extern "C" int b2_vp8l_predictor_forward(b2_ctx* ctx, int stream, const b2_argb_job* jobs, int n_jobs) {
@@ -522,7 +608,10 @@ extern "C" int b2_vp8l_predictor_forward(b2_ctx* ctx, int stream, const b2_argb_
   if (n_jobs == 0) return B2_OK;
   if (jobs == NULL) return B2_ERR_NULL;
   PredPlan pl;
-  const int st = prepare_pred(ctx, stream, jobs, n_jobs, false, &pl);
+  PredSrc* ps = plain_jobs(jobs, n_jobs);
+  if (ps == NULL) return B2_ERR_OOM;
+  const int st = prepare_pred(ctx, stream, ps, n_jobs, false, &pl);
+  free(ps);
   if (st != B2_OK) return st;
   const int grid = b2_grid_for(ctx, B2_FWD_CTAS, pl.total_items);
   predictor_forward_kernel<<<grid, kFwdThreads, 0, ctx->streams[stream]>>>(pl.jobs, pl.prefix, (uint32_t)n_jobs, pl.uniform, pl.total_items);
@@ -537,7 +626,41 @@ extern "C" int b2_vp8l_predictor_inverse(b2_ctx* ctx, int stream, const b2_argb_
   if (n_jobs == 0) return B2_OK;
   if (jobs == NULL) return B2_ERR_NULL;
   PredPlan pl;
-  const int st = prepare_pred(ctx, stream, jobs, n_jobs, true, &pl);
+  PredSrc* ps = plain_jobs(jobs, n_jobs);
+  if (ps == NULL) return B2_ERR_OOM;
+  const int st = prepare_pred(ctx, stream, ps, n_jobs, true, &pl);
+  free(ps);
+  if (st != B2_OK) return st;
+  const int grid = b2_grid_for(ctx, 8, (pl.total_bands + kInvWarps - 1) / kInvWarps);
+  predictor_inverse_wave_kernel<<<grid, kInvThreads, 0, ctx->streams[stream]>>>(pl.jobs, pl.order, pl.total_bands, pl.ctl);
+  ctx->launches++;
+  B2_CUDA(ctx, cudaGetLastError());
+  return B2_OK;
+}
+
+extern "C" int b2_vp8l_predictor_inverse_chain(b2_ctx* ctx, int stream, const b2_vp8l_chain_job* jobs, int n_jobs, int out_mode) {
+  B2_CHECK_CTX(ctx, stream);
+  if (n_jobs < 0) return B2_ERR_INVALID_CONFIG;
+  if (n_jobs == 0) return B2_OK;
+  if (jobs == NULL) return B2_ERR_NULL;
+  uint32_t order_bits;
+  switch (out_mode) {   // the 4-byte, not premultiplied modes: a byte permutation of the pixel, undone when a band reads the row above back
+    case B2_MODE_BGRA: order_bits = 0; break;
+    case B2_MODE_RGBA: order_bits = CH_RGBA; break;
+    case B2_MODE_ARGB: order_bits = CH_ARGB; break;
+    default: return B2_ERR_INVALID_CONFIG;
+  }
+  PredSrc* ps = (PredSrc*)malloc(sizeof(PredSrc) * (size_t)n_jobs);
+  if (ps == NULL) return B2_ERR_OOM;
+  for (int i = 0; i < n_jobs; ++i) {
+    const b2_vp8l_chain_job& j = jobs[i];
+    ps[i].src = j.src; ps[i].dst = j.dst; ps[i].modes = j.predictor_data; ps[i].codes = j.color_data;
+    ps[i].width = j.width; ps[i].height = j.height; ps[i].bits = j.predictor_bits; ps[i].cbits = j.color_bits;
+    ps[i].chain = (j.color_data ? CH_CC : 0u) | (j.add_green ? CH_GREEN : 0u) | order_bits;
+  }
+  PredPlan pl;
+  const int st = prepare_pred(ctx, stream, ps, n_jobs, true, &pl);
+  free(ps);
   if (st != B2_OK) return st;
   const int grid = b2_grid_for(ctx, 8, (pl.total_bands + kInvWarps - 1) / kInvWarps);
   predictor_inverse_wave_kernel<<<grid, kInvThreads, 0, ctx->streams[stream]>>>(pl.jobs, pl.order, pl.total_bands, pl.ctl);

@@ -246,3 +246,34 @@ extern "C" int b2_vp8l_batch_staged(b2_ctx* ctx, int op, const b2_argb_job* jobs
   for (int i = 0; i < ns; ++i) B2_CUDA(ctx, cudaStreamSynchronize(ctx->streams[i]));
   return B2_OK;
 }
+
+extern "C" int b2_vp8l_chain_batch_staged(b2_ctx* ctx, const b2_vp8l_chain_job* jobs, const b2_vp8l_chain_host* host,
+                                          int n_jobs, int out_mode, int chunk) {
+  B2_CHECK_CTX(ctx, 0);
+  if (n_jobs == 0) return B2_OK;
+  if (jobs == NULL || host == NULL) return B2_ERR_NULL;
+  if (n_jobs < 0) return B2_ERR_INVALID_CONFIG;
+  if (chunk < 1) chunk = 4;
+  const int ns = ctx->n_streams;
+  CopyList cl;
+  int st;
+  for (int k = 0, c0 = 0; c0 < n_jobs; ++k, c0 += chunk) {
+    const int s = k % ns;
+    const int c1 = (c0 + chunk < n_jobs) ? c0 + chunk : n_jobs;
+    for (int i = c0; i < c1; ++i) {
+      const size_t px = (size_t)4 * (size_t)jobs[i].width * (size_t)jobs[i].height;
+      cl.add((void*)jobs[i].src, host[i].src, px, px, px, 1, false);
+      cl.add((void*)jobs[i].predictor_data, host[i].predictor_data, host[i].predictor_bytes, host[i].predictor_bytes, host[i].predictor_bytes, 1, false);
+      cl.add((void*)jobs[i].color_data, host[i].color_data, host[i].color_bytes, host[i].color_bytes, host[i].color_bytes, 1, false);
+    }
+    if ((st = cl.issue(ctx, s, cudaMemcpyHostToDevice)) != B2_OK) return st;
+    if ((st = b2_vp8l_predictor_inverse_chain(ctx, s, jobs + c0, c1 - c0, out_mode)) != B2_OK) return st;
+    for (int i = c0; i < c1; ++i) {
+      const size_t px = (size_t)4 * (size_t)jobs[i].width * (size_t)jobs[i].height;
+      cl.add(host[i].dst, jobs[i].dst, px, px, px, 1, true);
+    }
+    if ((st = cl.issue(ctx, s, cudaMemcpyDeviceToHost)) != B2_OK) return st;
+  }
+  for (int i = 0; i < ns; ++i) B2_CUDA(ctx, cudaStreamSynchronize(ctx->streams[i]));
+  return B2_OK;
+}

@@ -448,54 +448,76 @@ def VP8LInverseTransform(transform: VP8LTransform, row_start: int, row_end: int,
 
 
 def _plan_chain(c):
-    """ApplyInverseTransforms order (vp8l_dec.c.go:710-729): last read, first applied; a
-    cross-colour transform directly followed by add-green becomes the fused kernel."""
-    steps, k, c = [], 0, list(c)
-    while k < len(c):
-        t = c[-1 - k]
-        nxt = c[-2 - k] if k + 1 < len(c) else None
+    """ApplyInverseTransforms order (vp8l_dec.c.go:710-729): last read, first applied.  Steps that have a
+    fused kernel are merged: [cross-colour] -> predictor -> [add-green] is ONE pass of the predictor
+    wavefront (the order libwebp's encoder always writes), cross-colour -> add-green without a predictor is
+    the flat fused kernel.  Returns [(op, transforms)], op 'predictor_chain' taking (cross or None,
+    predictor, subtract-green or None)."""
+    todo = [t for t in reversed(list(c))]
+    steps, k = [], 0
+    while k < len(todo):
+        t = todo[k]
+        nxt = todo[k + 1] if k + 1 < len(todo) else None
+        nx2 = todo[k + 2] if k + 2 < len(todo) else None
+        if t.vtype == CROSS_COLOR_TRANSFORM and nxt is not None and nxt.vtype == PREDICTOR_TRANSFORM:
+            green = nx2 if (nx2 is not None and nx2.vtype == SUBTRACT_GREEN_TRANSFORM) else None
+            steps.append(("predictor_chain", (t, nxt, green)))
+            k += 3 if green is not None else 2
+            continue
+        if t.vtype == PREDICTOR_TRANSFORM and nxt is not None and nxt.vtype == SUBTRACT_GREEN_TRANSFORM:
+            steps.append(("predictor_chain", (None, t, nxt)))
+            k += 2
+            continue
         if t.vtype == CROSS_COLOR_TRANSFORM and nxt is not None and nxt.vtype == SUBTRACT_GREEN_TRANSFORM:
-            steps.append(("inverse_chain", t))
+            steps.append(("inverse_chain", (t,)))
             k += 2
             continue
         op = {CROSS_COLOR_TRANSFORM: "color_inverse", SUBTRACT_GREEN_TRANSFORM: "add_green",
               COLOR_INDEXING_TRANSFORM: "color_index_inverse", PREDICTOR_TRANSFORM: "predictor_inverse"}.get(t.vtype)
         if op is None:
             raise ValueError("unknown transform type")
-        steps.append((op, t))
+        steps.append((op, (t,)))
         k += 1
     return steps
 
 
-def VP8LInverseTransformBatch(imgs, chain, ctx: Context | None = None, chunk: int = 4):
+def VP8LInverseTransformBatch(imgs, chain, ctx: Context | None = None, chunk: int = 4, out_mode: int = _abi.MODE_BGRA):
     """Added batched entry point for part 3 (SURVEY 8b).  imgs: list[VP8LImage];
     chain: list (per image) of the transforms in READ order (ReadTransform,
     vp8l_dec.c.go:1221-1269); they are applied last-read-first exactly like
-    ApplyInverseTransforms (vp8l_dec.c.go:710-729).  A cross-colour transform
-    directly followed by add-green is run as the fused single-pass kernel.  The pixels
-    cross PCIe twice, whatever the length of the chain: decoded pixels up with the first
-    step, final pixels down with the last; everything in between stays on the device
-    (two ping-pong buffers per image)."""
+    ApplyInverseTransforms (vp8l_dec.c.go:710-729).  Fused kernels are used where the chain
+    allows (see _plan_chain): libwebp's own chain -- cross-colour, predictor, subtract-green --
+    is ONE kernel pass.  The pixels cross PCIe twice, whatever the length of the chain: decoded
+    pixels up with the first step, final pixels down with the last; everything in between stays
+    on the device (two ping-pong buffers per image).
+    out_mode: MODE_BGRA returns uint32 0xAARRGGBB pixels; MODE_RGBA / MODE_ARGB the 4-byte orders of
+    EmitRows -> VP8LConvertFromBGRA (vp8l_dec.c.go:771), fused into the last step when that step is the
+    predictor chain (else one more device pass)."""
     ctx = ctx or default_context()
     n = len(imgs)
     cur = [np.ascontiguousarray(im.pixels, np.uint32) for im in imgs]
     plans = [_plan_chain(c) for c in chain]
     if n == 0:
         return cur
+    if out_mode not in (_abi.MODE_BGRA, _abi.MODE_RGBA, _abi.MODE_ARGB):
+        raise ValueError("out_mode: a 4-byte, not premultiplied mode (VP8LConvertFromBGRA does the others)")
     sizes, need = [], 0
     for im, src, plan in zip(imgs, cur, plans):
-        full = max([4 * t.xsize * t.ysize for _, t in plan] + [src.nbytes])
-        dsz = [_al(np.asarray(t.data).size * 4) if t.data is not None else 0 for _, t in plan]
+        full = max([4 * ts[-1].xsize * ts[-1].ysize if op != "predictor_chain" else 4 * ts[1].xsize * ts[1].ysize
+                    for op, ts in plan] + [src.nbytes])
+        dsz = [[_al(np.asarray(t.data).size * 4) if (t is not None and t.data is not None) else 0 for t in ts] for _, ts in plan]
         sizes.append((_al(full), dsz))
-        need += 2 * _al(full) + sum(dsz)
+        need += 2 * _al(full) + sum(sum(d) for d in dsz)
     ar = _arena(ctx)
     ar.reset(need)
     bufs, dptr, hdata = [], [], []
     for (full, dsz), plan in zip(sizes, plans):
         bufs.append([ar.take(full), ar.take(full)])
-        dptr.append([ar.take(z) if z else None for z in dsz])
-        hdata.append([np.ascontiguousarray(t.data, np.uint32) if t.data is not None else None for _, t in plan])
+        dptr.append([[ar.take(z) if z else None for z in d] for d in dsz])
+        hdata.append([[np.ascontiguousarray(t.data, np.uint32) if (t is not None and t.data is not None) else None for t in ts]
+                      for _, ts in plan])
     outs = list(cur)
+    converted = [False] * n
     depth = max((len(p) for p in plans), default=0)
     for k in range(depth):
         groups: dict[str, list] = {}
@@ -504,21 +526,51 @@ def VP8LInverseTransformBatch(imgs, chain, ctx: Context | None = None, chunk: in
                 groups.setdefault(plan[k][0], []).append(i)
         for op, members in groups.items():
             m = len(members)
+            if op == "predictor_chain":
+                # the byte order rides on the last step only; images that stop later convert at the end
+                for mode_now in sorted({(out_mode if k == len(plans[i]) - 1 else _abi.MODE_BGRA) for i in members}):
+                    sel = [i for i in members if (out_mode if k == len(plans[i]) - 1 else _abi.MODE_BGRA) == mode_now]
+                    jobs = (_abi.ChainJob * len(sel))()
+                    hosts = (_abi.ChainHost * len(sel))()
+                    for q, i in enumerate(sel):
+                        cc, pr, gr = plans[i][k][1]
+                        j, hh = jobs[q], hosts[q]
+                        j.src, j.dst = bufs[i][k & 1], bufs[i][(k + 1) & 1]
+                        j.width, j.height, j.predictor_bits = pr.xsize, pr.ysize, pr.bits
+                        j.predictor_data = dptr[i][k][1]
+                        hh.predictor_data, hh.predictor_bytes = hdata[i][k][1].ctypes.data, hdata[i][k][1].nbytes
+                        if cc is not None:
+                            j.color_data, j.color_bits = dptr[i][k][0], cc.bits
+                            hh.color_data, hh.color_bytes = hdata[i][k][0].ctypes.data, hdata[i][k][0].nbytes
+                        j.add_green = int(gr is not None)
+                        if k == 0:
+                            hh.src = cur[i].ctypes.data
+                        if k == len(plans[i]) - 1:
+                            outs[i] = np.empty((pr.ysize, pr.xsize), np.uint32)
+                            hh.dst = outs[i].ctypes.data
+                            converted[i] = True
+                    ctx._chk(ctx.lib.b2_vp8l_chain_batch_staged(ctx.h, jobs, hosts, len(sel), mode_now, chunk))
+                continue
             jobs = (_abi.ArgbJob * m)()
             hosts = (_abi.ArgbHost * m)()
             for q, i in enumerate(members):
-                t = plans[i][k][1]
+                t = plans[i][k][1][0]
                 j, hh = jobs[q], hosts[q]
-                j.src, j.dst, j.data = bufs[i][k & 1], bufs[i][(k + 1) & 1], dptr[i][k]
+                j.src, j.dst, j.data = bufs[i][k & 1], bufs[i][(k + 1) & 1], dptr[i][k][0]
                 j.width, j.height, j.bits = t.xsize, t.ysize, t.bits
                 if k == 0:
                     hh.src, hh.src_bytes = cur[i].ctypes.data, cur[i].nbytes
-                if hdata[i][k] is not None:
-                    hh.data, hh.data_bytes = hdata[i][k].ctypes.data, hdata[i][k].nbytes
+                if hdata[i][k][0] is not None:
+                    hh.data, hh.data_bytes = hdata[i][k][0].ctypes.data, hdata[i][k][0].nbytes
                 if k == len(plans[i]) - 1:
                     outs[i] = np.empty((t.ysize, t.xsize), np.uint32)
                     hh.dst, hh.dst_bytes = outs[i].ctypes.data, outs[i].nbytes
             ctx._chk(ctx.lib.b2_vp8l_batch_staged(ctx.h, _abi.VP8L_OPS[op], jobs, hosts, m, chunk))
+    if out_mode != _abi.MODE_BGRA:
+        for i in range(n):
+            if not converted[i]:
+                o = np.ascontiguousarray(outs[i], np.uint32)
+                outs[i] = VP8LConvertFromBGRA(o, None, out_mode).view(np.uint32).reshape(o.shape)
     return outs
 
 

@@ -321,6 +321,56 @@ class ArgbPipeline:
                 getattr(self, b).free()
 
 
+class ChainPipeline:
+    """Device-resident batch for the whole VP8L inverse chain of libwebp's encoder (cross-colour inverse ->
+    predictor inverse -> add-green, 32x32 tiles): run_device() = the fused single pass
+    (b2_vp8l_predictor_inverse_chain), run_unfused() = the same result as three launches."""
+
+    def __init__(self, ctx: Context, n: int, width: int, height: int, bits: int = 5):
+        self.ctx, self.n, self.w, self.h, self.bits = ctx, n, width, height, bits
+        sub = lambda v, b: (v + (1 << b) - 1) >> b  # noqa: E731
+        self.words = sub(width, bits) * sub(height, bits)
+        self.img, self.dat = _al(4 * width * height), _al(4 * self.words)
+        self.d_src, self.d_dst, self.d_tmp = ctx.alloc(self.img * n), ctx.alloc(self.img * n), ctx.alloc(self.img * n)
+        self.d_modes, self.d_codes = ctx.alloc(self.dat * n), ctx.alloc(self.dat * n)
+        A = _abi
+        self._chain = (A.ChainJob * n)(*[A.ChainJob(self.d_src.ptr + i * self.img, self.d_dst.ptr + i * self.img,
+                                                    self.d_modes.ptr + i * self.dat, self.d_codes.ptr + i * self.dat,
+                                                    width, height, bits, bits, 1, 0) for i in range(n)])
+        mk = lambda s, d, t: (A.ArgbJob * n)(*[A.ArgbJob(s.ptr + i * self.img, d.ptr + i * self.img,  # noqa: E731
+                                                        t.ptr + i * self.dat if t else None, width, height, bits, 0) for i in range(n)])
+        self._cc = mk(self.d_src, self.d_tmp, self.d_codes)
+        self._pred = mk(self.d_tmp, self.d_dst, self.d_modes)
+        self._green = mk(self.d_dst, self.d_dst, None)
+
+    def fill_synthetic(self, seed: int, first_img: int = 0):
+        c = self.ctx
+        c.synth_fill(self.d_src.ptr, self.w, self.h, 4 * self.w, self.img, self.n, seed, first_img, 5)
+        c.synth_fill(self.d_modes.ptr, self.words, 1, 4 * self.words, self.dat, self.n, seed, first_img, 6)
+        c.synth_fill(self.d_codes.ptr, self.words, 1, 4 * self.words, self.dat, self.n, seed, first_img, 7)
+        c.sync()
+
+    def run_device(self, stream: int = 0, out_mode: int = _abi.MODE_BGRA):
+        c = self.ctx
+        c._chk(c.lib.b2_vp8l_predictor_inverse_chain(c.h, stream, self._chain, self.n, out_mode))
+
+    def run_unfused(self, stream: int = 0):
+        c = self.ctx
+        c._chk(c.lib.b2_vp8l_color_inverse(c.h, stream, self._cc, self.n))
+        c._chk(c.lib.b2_vp8l_predictor_inverse(c.h, stream, self._pred, self.n))
+        c._chk(c.lib.b2_vp8l_add_green(c.h, stream, self._green, self.n))
+
+    def device_image(self, i: int):
+        c = self.ctx
+        f = lambda b, nb: c.d2h(b.ptr + i * (self.img if nb == 4 * self.w * self.h else self.dat), nb).view(np.uint32)  # noqa: E731
+        return (f(self.d_src, 4 * self.w * self.h).reshape(self.h, self.w), f(self.d_modes, 4 * self.words),
+                f(self.d_codes, 4 * self.words), f(self.d_dst, 4 * self.w * self.h).reshape(self.h, self.w))
+
+    def close(self):
+        for b in ("d_src", "d_dst", "d_tmp", "d_modes", "d_codes"):
+            getattr(self, b).free()
+
+
 class PalettePipeline:
     """Device-resident batch of n equal ARGB images whose pixels are all colours of a per-image palette,
     for ApplyPalette (colour -> packed index).  The images are made on the device: synthetic packed

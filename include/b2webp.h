@@ -253,6 +253,26 @@ int b2_vp8l_apply_palette(b2_ctx* ctx, int stream, const b2_palette_job* jobs, i
 int b2_vp8l_predictor_inverse(b2_ctx* ctx, int stream, const b2_argb_job* jobs, int n_jobs);
 int b2_vp8l_predictor_forward(b2_ctx* ctx, int stream, const b2_argb_job* jobs, int n_jobs);
 
+/* ApplyInverseTransforms (pkg/vp8/vp8l_dec.c.go:710-729) for the chain libwebp's encoder writes --
+ * cross-colour inverse, then predictor inverse, then add-green -- and the 4-byte output conversion of
+ * EmitRows -> VP8LConvertFromBGRA (vp8l_dec.c.go:771, pkg/libwebp/dsp/lossless.go:598-666) in ONE pass
+ * over the pixels: the wavefront of the predictor inverse applies VP8LTransformColorInverse to each
+ * residual before the prediction is added and VP8LAddGreenToBlueAndRed + the byte order to each pixel on
+ * its way out (8 B/px instead of 24 + 8 for four launches).  color_data NULL: no cross-colour step;
+ * add_green 0: no add-green step; out_mode: B2_MODE_BGRA (uint32 0xAARRGGBB as it is), B2_MODE_RGBA or
+ * B2_MODE_ARGB.  dst must not alias src; rows tightly packed. */
+typedef struct b2_vp8l_chain_job {
+  const uint32_t* src;
+  uint32_t* dst;
+  const uint32_t* predictor_data; /* mode image, ceil(w/2^predictor_bits) x ceil(h/2^predictor_bits) */
+  const uint32_t* color_data;     /* cross-colour codes, ceil(w/2^color_bits) x ceil(h/2^color_bits), or NULL */
+  int32_t width, height;
+  int32_t predictor_bits, color_bits;
+  int32_t add_green;
+  int32_t reserved;
+} b2_vp8l_chain_job;
+int b2_vp8l_predictor_inverse_chain(b2_ctx* ctx, int stream, const b2_vp8l_chain_job* jobs, int n_jobs, int out_mode);
+
 /* ---- next rows: output conversions after parts 2 and 3 ---------
  * One job layout for the three entry points (DEVICE pointers, signed strides). */
 typedef struct b2_convert_job {
@@ -524,6 +544,18 @@ typedef enum b2_vp8l_op {
  * pkg/vp8/vp8l_dec.c.go:710-729) or its forward counterpart over a batch of images. */
 int b2_vp8l_batch_staged(b2_ctx* ctx, int op, const b2_argb_job* jobs, const b2_argb_host* host, int n_jobs,
                          int chunk);
+
+typedef struct b2_vp8l_chain_host {
+  const void* src;            /* 4 * width * height bytes of residuals, or NULL (already resident) */
+  void* dst;                  /* 4 * width * height bytes, or NULL (stays on the device) */
+  const void* predictor_data;
+  const void* color_data;
+  size_t predictor_bytes, color_bytes;
+} b2_vp8l_chain_host;
+/* b2_vp8l_predictor_inverse_chain over host buffers: the whole ApplyInverseTransforms chain of a batch,
+ * pixels up once and down once. */
+int b2_vp8l_chain_batch_staged(b2_ctx* ctx, const b2_vp8l_chain_job* jobs, const b2_vp8l_chain_host* host, int n_jobs,
+                               int out_mode, int chunk);
 
 /* ---- synthetic inputs (SURVEY.md 8d generator, identical to the oracle's) -
  * One uint32 per (row, word) position of n images laid out 'image_bytes'

@@ -43,7 +43,7 @@ _STRUCTS = {
     "b2_convert_job": _abi.ConvertJob, "b2_picture_job": _abi.PictureJob, "b2_anim_blend_job": _abi.AnimBlendJob,
     "b2_anim_compare_job": _abi.AnimCompareJob, "b2_alpha_filter_job": _abi.AlphaFilterJob,
     "b2_alpha_dequant_job": _abi.AlphaDequantJob, "b2_rescale_job": _abi.RescaleJob,
-    "b2_palette_job": _abi.PaletteJob, "b2_import_host": _abi.ImportHost, "b2_upsample_host": _abi.UpsampleHost, "b2_argb_host": _abi.ArgbHost,
+    "b2_palette_job": _abi.PaletteJob, "b2_vp8l_chain_job": _abi.ChainJob, "b2_vp8l_chain_host": _abi.ChainHost, "b2_import_host": _abi.ImportHost, "b2_upsample_host": _abi.UpsampleHost, "b2_argb_host": _abi.ArgbHost,
 }
 
 

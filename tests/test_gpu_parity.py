@@ -1204,10 +1204,51 @@ def test_dithered_import_descriptor_ring_wrap(gpu):
     n, w, h = 6000, 4, 2
     srcs = [rng.integers(0, 256, (h, 4 * w), dtype=np.uint8) for _ in range(n)]
     pics = [P.Picture(Width=w, Height=h) for _ in range(n)]
-    assert P.ImportRGBABatch(pics, srcs, [4 * w] * n, "BGRA", ctx=ctx, dithering=0.6, chunk=n) == 1
-    for i in list(range(0, n, 397)) + [n - 1]:
-        y, u, v, a, ha = oracle.import_yuva_dithered(srcs[i], w, h, 0.6, "BGRA")
-        assert (pics[i].Y == y).all() and (pics[i].U == u).all() and (pics[i].V == v).all(), i
+    # one call with 6000 images (sliced inside the library), then 3000-image calls that walk the ring
+    # over its end: the reserve wraps BEFORE the first of a call's two uploads
+    for lo, hi in [(0, n), (0, 3000), (3000, 6000), (1000, 4000)]:
+        assert P.ImportRGBABatch(pics[lo:hi], srcs[lo:hi], [4 * w] * (hi - lo), "BGRA", ctx=ctx, dithering=0.6, chunk=n) == 1
+        for i in list(range(lo, hi, 397)) + [hi - 1]:
+            y, u, v, a, ha = oracle.import_yuva_dithered(srcs[i], w, h, 0.6, "BGRA")
+            assert (pics[i].Y == y).all() and (pics[i].U == u).all() and (pics[i].V == v).all(), (lo, hi, i)
+        for p in pics[lo:hi:7]:
+            p.memory_.host_valid = False      # next round must really come from the device again
     for p in pics:
         P.WebPPictureFree(p)
     ctx.close()
+
+
+def test_predictor_inverse_chain_fused(gpu):
+    """b2_vp8l_predictor_inverse_chain: [cross-colour inverse] -> predictor inverse -> [add-green] -> 4-byte
+    output order in one pass of the wavefront (vp8l_dec.c.go:710-729, :771) vs the oracle applying the
+    transforms one after the other; every combination, tile sizes of the two transforms that differ, widths
+    that leave the vector path, several bands, images that end inside a band."""
+    D, A = gpu["dsp"], gpu["abi"]
+    rng = np.random.default_rng(88)
+    sub = lambda v, b: (v + (1 << b) - 1) >> b  # noqa: E731
+    perm = {A.MODE_BGRA: None, A.MODE_RGBA: [2, 1, 0, 3], A.MODE_ARGB: [3, 2, 1, 0]}
+    imgs, chains, exps = [], [], []
+    for (w, h, pb, cb) in [(64, 64, 3, 3), (150, 70, 3, 5), (131, 33, 2, 4), (260, 100, 5, 2), (1, 1, 2, 2), (7, 40, 4, 3),
+                           (1024, 96, 5, 5), (36, 513, 3, 2)]:
+        for use_cc in (True, False):
+            for use_green in (True, False):
+                px = rng.integers(0, 2**32, (h, w), dtype=np.uint32)
+                modes = (rng.integers(0, 16, (sub(h, pb), sub(w, pb)), dtype=np.uint32) << 8) | 0xff000000
+                codes = rng.integers(0, 2**24, (sub(h, cb), sub(w, cb)), dtype=np.uint32) | 0xff000000
+                chain = ([D.VP8LTransform(D.SUBTRACT_GREEN_TRANSFORM, 0, w, h)] if use_green else []) + \
+                    [D.VP8LTransform(D.PREDICTOR_TRANSFORM, pb, w, h, modes)] + \
+                    ([D.VP8LTransform(D.CROSS_COLOR_TRANSFORM, cb, w, h, codes)] if use_cc else [])
+                e = oracle.color_space_inverse(px, codes, cb) if use_cc else px
+                e = oracle.predictor_inverse(e, modes, pb)
+                e = oracle.add_green(e) if use_green else e
+                imgs.append(D.VP8LImage(px, w, h))
+                chains.append(chain)
+                exps.append(e)
+    plans = [D._plan_chain(c) for c in chains]
+    assert all(len(p) == 1 for p in plans), "each of these chains is one fused pass (or the plain predictor)"
+    for mode in (A.MODE_BGRA, A.MODE_RGBA, A.MODE_ARGB):
+        outs = D.VP8LInverseTransformBatch(imgs, chains, out_mode=mode)
+        for o, e, im in zip(outs, exps, imgs):
+            if perm[mode] is not None:
+                e = np.ascontiguousarray(e.view(np.uint8).reshape(e.shape[0], -1, 4)[:, :, perm[mode]]).view(np.uint32).reshape(e.shape)
+            assert (o == e).all(), (im.width, im.height, mode)

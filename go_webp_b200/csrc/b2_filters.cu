@@ -275,7 +275,10 @@ alpha_unfilter_vertical_kernel(const FiltJobDev* __restrict__ jobs, const uint32
 // word per warp in shared memory, monotonic), and the warp below waits for the columns it is
 // about to read.  The last row itself travels through global memory (written by lane 31,
 // CTA-scope fence, flag; read back by lane 0 with volatile loads after its own fence).
-constexpr int kGradWarps = 16;
+#ifndef B2_GRAD_WARPS
+#define B2_GRAD_WARPS 16
+#endif
+constexpr int kGradWarps = B2_GRAD_WARPS;
 __global__ void __launch_bounds__(32 * kGradWarps)
 alpha_unfilter_gradient_kernel(const FiltJobDev* __restrict__ jobs, uint32_t n_jobs) {
   __shared__ volatile int progress[kGradWarps];
@@ -333,8 +336,45 @@ alpha_unfilter_gradient_kernel(const FiltJobDev* __restrict__ jobs, uint32_t n_j
 #pragma unroll
         for (int t = 0; t < 8; ++t) { inq[t] = in_word(t - lane); abq[t] = above_word(t); }
         uint32_t my_out = 0, left = 0, tl = 0;
+        // out = (in + clip(left + top - topleft)) & 0xff (GradientUnfilter_C, filters.go:150-171).  Only `left` is a
+        // serial dependence: d = top - topleft is taken off the chain and the clip is ONE add-min-relu, so a pixel
+        // costs three dependent instructions.  No special cases: row 0 has top = topleft = 0 (pred = left: the
+        // horizontal rule of the first row), column 0 starts with left = topleft = 0 (pred = clip(top) = top: the
+        // reference's prev_line[0]).
+        auto quad = [&](uint32_t vin, uint32_t topw) -> uint32_t {
+          const int t0 = (int)(topw & 0xff), t1 = (int)((topw >> 8) & 0xff), t2 = (int)((topw >> 16) & 0xff), t3 = (int)(topw >> 24);
+          const int d0 = t0 - (int)tl, d1 = t1 - t0, d2 = t2 - t1, d3 = t3 - t2;
+          const int v0 = (int)(vin & 0xff), v1 = (int)((vin >> 8) & 0xff), v2 = (int)((vin >> 16) & 0xff), v3 = (int)(vin >> 24);
+          const int o0 = (v0 + __viaddmin_s32_relu((int)left, d0, 255)) & 0xff;
+          const int o1 = (v1 + __viaddmin_s32_relu(o0, d1, 255)) & 0xff;
+          const int o2 = (v2 + __viaddmin_s32_relu(o1, d2, 255)) & 0xff;
+          const int o3 = (v3 + __viaddmin_s32_relu(o2, d3, 255)) & 0xff;
+          left = (uint32_t)o3;   // bytes past the end of the row are never stored and never read again
+          tl = topw >> 24;
+          return (uint32_t)o0 | ((uint32_t)o1 << 8) | ((uint32_t)o2 << 16) | ((uint32_t)o3 << 24);
+        };
+        const bool full_band = band + 31 < h;
+        const int nq_full = w >> 2;
+        const uint32_t* __restrict__ in_w = (const uint32_t*)in;
+        const volatile uint32_t* above_w = (const volatile uint32_t*)above;
+        uint32_t* out_w = (uint32_t*)out;
         for (int q0 = 0; q0 < nq + 31; q0 += 8) {
           wait_for(4 * (q0 + 16));
+          if (full_band && q0 >= 31 && q0 + 15 < nq_full) {
+            // steady state (warp-uniform): every lane is inside its row, on whole words, and so is everything
+            // it fetches 8 quad steps ahead: no predicates, one load, one shuffle, one store per 4 pixels
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+              const int q = q0 + t, m = q - lane;
+              const uint32_t vin = inq[t];
+              uint32_t topw = __shfl_up_sync(0xffffffffu, my_out, 1);
+              if (lane == 0) topw = abq[t];
+              inq[t] = __ldg(in_w + m + 8);
+              if (lane == 0 && band > 0) abq[t] = above_w[q + 8];
+              my_out = quad(vin, topw);
+              out_w[m] = my_out;
+            }
+          } else {
 #pragma unroll
           for (int t = 0; t < 8; ++t) {
             const int q = q0 + t, m = q - lane;
@@ -344,24 +384,12 @@ alpha_unfilter_gradient_kernel(const FiltJobDev* __restrict__ jobs, uint32_t n_j
             inq[t] = in_word(m + 8);
             abq[t] = above_word(q + 8);
             if (row_ok && m >= 0 && m < nq) {
-              uint32_t outw = 0;
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const int c = 4 * m + k;
-                const int v = (int)((vin >> (8 * k)) & 0xff), top = (int)((topw >> (8 * k)) & 0xff);
-                const int tlk = (k == 0) ? (int)tl : (int)((topw >> (8 * (k - 1))) & 0xff);
-                int o;
-                if (row == 0) o = (v + (int)left) & 0xff;                  // first row: horizontal, pred 0 at c == 0
-                else if (c == 0) o = (v + top) & 0xff;                     // left = top = top_left = prev[0]
-                else o = (v + gradient_pred((int)left, top, tlk)) & 0xff;
-                if (c < w) left = (uint32_t)o;
-                outw |= (uint32_t)o << (8 * k);
-              }
-              tl = topw >> 24;
+              const uint32_t outw = quad(vin, topw);
               if (4 * m + 4 <= w) *((uint32_t*)out + m) = outw;
               else for (int t2 = 0; 4 * m + t2 < w; ++t2) out[4 * m + t2] = (uint8_t)(outw >> (8 * t2));
               my_out = outw;
             }
+          }
           }
           if (lane == 31) {            // words 0 .. q0 + 7 - 31 of the band's last row are written
             const int done = min(max(4 * (q0 + 8 - 31), 0), w);

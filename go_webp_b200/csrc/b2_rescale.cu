@@ -158,6 +158,264 @@ rescale_kernel(const RescaleJobDev* __restrict__ jobs, const uint32_t* __restric
   }
 }
 
+// ---- one-channel planes: a thread walks DOWN its output columns -----------------------------------
+// The per-sample kernel above recomputes the horizontally rescaled value frow[xo] of a source row for
+// every output row that touches it (four times per source row when a plane is doubled) and pays a table
+// entry, an address computation and byte loads per sample.  For one-channel planes whose jobs share the
+// direction, a thread instead owns kCols adjacent output columns and walks a group of kRows output rows
+// top to bottom -- the reference's own streaming order (WebPRescalerImport / Export,
+// rescaler_utils.c.go:119-158) -- keeping what the state machine keeps: frow of the last imported row and
+// either the previous row's frow (vertical expansion: irow of ExportRowExpand) or the running sum
+// (shrinking: irow of ExportRowShrink).  Every source row's frow is computed once per column and group,
+// the x entries are loaded once per group, four samples leave as one 32-bit store.
+constexpr int kCols = 4;
+constexpr int kRowsGroup = 32;
+template <int XE, int YE>
+__global__ void __launch_bounds__(kThreads, 3)
+rescale_columns_kernel(const RescaleJobDev* __restrict__ jobs, const uint32_t* __restrict__ prefix, uint32_t n_jobs, uint32_t uniform,
+                       uint32_t total, const XEnt* __restrict__ xpool, const YEnt* __restrict__ ypool) {
+  for (uint32_t unit = blockIdx.x; unit < total; unit += gridDim.x) {
+    uint32_t local;
+    const uint32_t img = b2_find_image(prefix, n_jobs, uniform, unit, &local);
+    const RescaleJobDev j = jobs[img];
+    const int x0 = (int)(local % j.units_x) * kThreads * kCols + (int)threadIdx.x * kCols;
+    if (x0 >= j.dst_width) continue;
+    const int dy0 = (int)(local / j.units_x) * kRowsGroup, dy1 = min(dy0 + kRowsGroup, j.dst_height);
+    const XEnt* __restrict__ xt = xpool + j.xtab;
+    const YEnt* __restrict__ yt = ypool + j.ytab;
+    XEnt ex[kCols], px[kCols];
+    int xo[kCols];
+#pragma unroll
+    for (int k = 0; k < kCols; ++k) {
+      xo[k] = min(x0 + k, j.dst_width - 1);      // columns past the end recompute the last one; they are not stored
+      ex[k] = xt[xo[k]];
+      px[k] = xt[max(xo[k] - 1, 0)];
+    }
+    const int n_valid = min(kCols, j.dst_width - x0);
+    const bool word_ok = n_valid == kCols && ((((uintptr_t)j.dst) | (uintptr_t)(uint32_t)j.dst_stride) & 3) == 0;
+    auto frow_row = [&](int r, uint32_t (&f)[kCols]) {
+      const uint8_t* __restrict__ row = j.src + (ptrdiff_t)r * j.src_stride;
+#pragma unroll
+      for (int k = 0; k < kCols; ++k) f[k] = frow_at<XE, 1>(j, ex[k], px[k], row, xo[k], 0);
+    };
+    auto store = [&](int dy, const uint32_t (&v)[kCols]) {
+      uint8_t* out = j.dst + (ptrdiff_t)dy * j.dst_stride + x0;
+      if (word_ok) {
+        *reinterpret_cast<uint32_t*>(out) = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
+      } else {
+#pragma unroll
+        for (int k = 0; k < kCols; ++k) if (k < n_valid) out[k] = (uint8_t)v[k];
+      }
+    };
+    uint32_t f[kCols] = {0, 0, 0, 0}, g[kCols] = {0, 0, 0, 0};   // f: frow of row `have`; g: frow of row have - 1 (YE) / of the previous export's last row (YS)
+    int have = -2, have_g = -2;
+    for (int dy = dy0; dy < dy1; ++dy) {
+      const YEnt e = yt[dy];
+      if (e.last < 0) continue;                  // the state machine never exports this row
+      uint32_t v[kCols];
+      if (YE) {                                  // ExportRowExpand, rescaler.c.go:110-136
+        if (e.last != have) {
+          if (e.last == have + 1 && have >= 0) {
+#pragma unroll
+            for (int k = 0; k < kCols; ++k) g[k] = f[k];
+          } else if (e.last > 0) {
+            frow_row(e.last - 1, g);
+          }
+          frow_row(e.last, f);
+          have = e.last;
+        }
+        const uint32_t B = e.yscale, A = (uint32_t)(kOne - B);
+#pragma unroll
+        for (int k = 0; k < kCols; ++k) {
+          uint32_t J = f[k];
+          if (e.y_accum != 0) {
+            const uint32_t i = (e.last > 0) ? g[k] : 0u;
+            J = (uint32_t)(((uint64_t)A * f[k] + (uint64_t)B * i + kRounder) >> 32);
+          }
+          v[k] = min(mult_fix(J, j.fy_scale), 255u);
+        }
+      } else {                                   // ExportRowShrink :138-163 over the rows imported since the previous export
+        uint32_t irow[kCols] = {0, 0, 0, 0};
+        if (e.prev_last >= 0 && e.prev_yscale != 0u) {
+          if (have_g != e.prev_last) frow_row(e.prev_last, g);
+#pragma unroll
+          for (int k = 0; k < kCols; ++k) irow[k] = mult_fix_floor(g[k], e.prev_yscale);
+        }
+        for (int r = e.prev_last + 1; r <= e.last; ++r) {
+          frow_row(r, f);
+#pragma unroll
+          for (int k = 0; k < kCols; ++k) irow[k] += f[k];
+        }
+#pragma unroll
+        for (int k = 0; k < kCols; ++k) {
+          if (j.fxy_scale == 0u) v[k] = irow[k] & 0xffu;     // special case, rescaler.c.go:184-191
+          else if (e.yscale != 0u) v[k] = min(mult_fix(irow[k] - mult_fix_floor(f[k], e.yscale), j.fxy_scale), 255u);
+          else v[k] = min(mult_fix(irow[k], j.fxy_scale), 255u);
+          g[k] = f[k];
+        }
+        have_g = e.last;
+      }
+      store(dy, v);
+    }
+  }
+}
+
+// ---- one-channel planes, streamed: source rows go through shared memory ----------------------------
+// The column walker above still waits for its byte loads: a thread needs row r + 1 only after it has
+// finished row r, and 24 warps do not hide a DRAM round trip per source row (measured: 1.3-1.8x the
+// per-sample kernel, 0.05-0.12 of the HBM peak).  Here the CTA streams the source rows of its unit
+// (1024 output columns x 32 output rows) through a two-stage ring in shared memory, four rows per stage,
+// with 16-byte cp.async issued by all threads (whole sectors, every source byte fetched once per unit);
+// the threads then run the same state machine on rows that are already on chip.  Needs 16-byte aligned
+// source rows and a source segment of at most kSegMax bytes per row and unit (the host checks both;
+// otherwise the column walker runs).
+constexpr int kRS = 4;
+constexpr int kSegMax = 4096 + 64;
+constexpr int kStreamSmem = 2 * kRS * kSegMax;
+template <int XE, int YE>
+__global__ void __launch_bounds__(kThreads, 3)
+rescale_stream_kernel(const RescaleJobDev* __restrict__ jobs, const uint32_t* __restrict__ prefix, uint32_t n_jobs, uint32_t uniform,
+                      uint32_t total, const XEnt* __restrict__ xpool, const YEnt* __restrict__ ypool) {
+  extern __shared__ __align__(16) uint8_t ring[];
+  __shared__ YEnt ys[kRowsGroup];
+  __shared__ int info[4];   // lo_al, seg bytes, r_begin, r_end
+  const int tid = (int)threadIdx.x;
+  for (uint32_t unit = blockIdx.x; unit < total; unit += gridDim.x) {
+    uint32_t local;
+    const uint32_t img = b2_find_image(prefix, n_jobs, uniform, unit, &local);
+    const RescaleJobDev j = jobs[img];
+    const int xc0 = (int)(local % j.units_x) * kThreads * kCols, xc1 = min(xc0 + kThreads * kCols, j.dst_width);
+    const int dy0 = (int)(local / j.units_x) * kRowsGroup, ng = min(kRowsGroup, j.dst_height - dy0);
+    const XEnt* __restrict__ xt = xpool + j.xtab;
+    __syncthreads();   // the previous unit is done with ys / info / the ring
+    if (tid < ng) ys[tid] = ypool[j.ytab + dy0 + tid];
+    __syncthreads();
+    if (tid == 0) {
+      const XEnt e0 = xt[xc0], e1 = xt[xc1 - 1];
+      const int lo = XE ? e0.a : max(e0.a - 1, 0), hi = XE ? e1.b + 1 : e1.b;
+      info[0] = lo & ~15;
+      info[1] = hi - (lo & ~15);
+      int r_begin = 0, r_end = -1;
+      for (int k = 0; k < ng; ++k) {
+        if (ys[k].last < 0) continue;
+        if (r_end < 0) {
+          if (YE) r_begin = max(ys[k].last - 1, 0);
+          else r_begin = (ys[k].prev_last >= 0 && ys[k].prev_yscale != 0u) ? ys[k].prev_last : ys[k].prev_last + 1;
+        }
+        r_end = ys[k].last;
+      }
+      info[2] = r_begin; info[3] = r_end;
+    }
+    __syncthreads();
+    const int lo_al = info[0], seg = info[1], r_begin = info[2], r_end = info[3];
+    if (r_end < 0) continue;   // uniform: nothing is exported in this group
+    const int x0 = xc0 + tid * kCols;
+    const bool live = x0 < j.dst_width;
+    XEnt ex[kCols], px[kCols];
+    int xo[kCols];
+#pragma unroll
+    for (int k = 0; k < kCols; ++k) {
+      xo[k] = min(x0 + k, j.dst_width - 1);
+      ex[k] = xt[xo[k]];
+      px[k] = xt[max(xo[k] - 1, 0)];
+    }
+    const int n_valid = min(kCols, j.dst_width - x0);
+    const bool word_ok = n_valid == kCols && ((((uintptr_t)j.dst) | (uintptr_t)(uint32_t)j.dst_stride) & 3) == 0;
+    const int n_chunks = (seg + 15) >> 4;
+    const int n_rows = r_end - r_begin + 1, n_stage = (n_rows + kRS - 1) / kRS;
+    auto issue = [&](int st) {   // all threads: rows r_begin + st * kRS .. of the unit into ring stage st & 1
+      const int rows_here = min(kRS, n_rows - st * kRS);
+      for (int c = tid; c < rows_here * n_chunks; c += kThreads) {
+        const int rr = c / n_chunks, ck = c - rr * n_chunks;
+        const int r = r_begin + st * kRS + rr;
+        const uint8_t* g = j.src + (ptrdiff_t)r * j.src_stride + lo_al + 16 * ck;
+        uint8_t* d = ring + ((st & 1) * kRS + rr) * kSegMax + 16 * ck;
+        if (lo_al + 16 * ck + 16 <= j.src_stride) {   // the row's own bytes (and its padding): a whole 16-byte chunk
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(d)), "l"(g) : "memory");
+        } else {
+          for (int b = 0; lo_al + 16 * ck + b < j.src_stride && b < 16; ++b) d[b] = g[b];
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    uint32_t f[kCols] = {0, 0, 0, 0}, g[kCols] = {0, 0, 0, 0}, acc[kCols] = {0, 0, 0, 0};
+    int dyi = 0;
+    issue(0);
+    for (int st = 0; st < n_stage; ++st) {
+      if (st + 1 < n_stage) {
+        issue(st + 1);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
+      __syncthreads();
+      const int rows_here = min(kRS, n_rows - st * kRS);
+      if (live) {
+        for (int rr = 0; rr < rows_here; ++rr) {
+          const int r = r_begin + st * kRS + rr;
+          const uint8_t* row = ring + ((st & 1) * kRS + rr) * kSegMax - lo_al;   // indexed by source x
+          uint32_t fn[kCols];
+#pragma unroll
+          for (int k = 0; k < kCols; ++k) fn[k] = frow_at<XE, 1>(j, ex[k], px[k], row, xo[k], 0);
+          if (YE) {                                  // ExportRowExpand, rescaler.c.go:110-136
+#pragma unroll
+            for (int k = 0; k < kCols; ++k) { g[k] = f[k]; f[k] = fn[k]; }
+            while (dyi < ng && ys[dyi].last <= r) {
+              const YEnt e = ys[dyi];
+              if (e.last == r) {
+                const uint32_t B = e.yscale, A = (uint32_t)(kOne - B);
+                uint32_t v[kCols];
+#pragma unroll
+                for (int k = 0; k < kCols; ++k) {
+                  uint32_t J = f[k];
+                  if (e.y_accum != 0) {
+                    const uint32_t i = (e.last > 0) ? g[k] : 0u;
+                    J = (uint32_t)(((uint64_t)A * f[k] + (uint64_t)B * i + kRounder) >> 32);
+                  }
+                  v[k] = min(mult_fix(J, j.fy_scale), 255u);
+                }
+                uint8_t* out = j.dst + (ptrdiff_t)(dy0 + dyi) * j.dst_stride + x0;
+                if (word_ok) *reinterpret_cast<uint32_t*>(out) = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
+                else for (int k = 0; k < n_valid; ++k) out[k] = (uint8_t)v[k];
+              }
+              ++dyi;
+            }
+          } else {                                   // ExportRowShrink :138-163
+            while (dyi < ng && ys[dyi].last < 0) ++dyi;
+            if (dyi >= ng) break;
+            const YEnt e = ys[dyi];
+            if (r <= e.prev_last) {                  // the row the previous export ended on: only its fractional rest counts
+#pragma unroll
+              for (int k = 0; k < kCols; ++k) g[k] = fn[k];
+              continue;
+            }
+#pragma unroll
+            for (int k = 0; k < kCols; ++k) acc[k] += fn[k];
+            if (r == e.last) {
+              uint32_t v[kCols];
+#pragma unroll
+              for (int k = 0; k < kCols; ++k) {
+                uint32_t irow = acc[k];
+                if (e.prev_last >= 0 && e.prev_yscale != 0u) irow += mult_fix_floor(g[k], e.prev_yscale);
+                if (j.fxy_scale == 0u) v[k] = irow & 0xffu;     // special case, rescaler.c.go:184-191
+                else if (e.yscale != 0u) v[k] = min(mult_fix(irow - mult_fix_floor(fn[k], e.yscale), j.fxy_scale), 255u);
+                else v[k] = min(mult_fix(irow, j.fxy_scale), 255u);
+                g[k] = fn[k];
+                acc[k] = 0;
+              }
+              uint8_t* out = j.dst + (ptrdiff_t)(dy0 + dyi) * j.dst_stride + x0;
+              if (word_ok) *reinterpret_cast<uint32_t*>(out) = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
+              else for (int k = 0; k < n_valid; ++k) out[k] = (uint8_t)v[k];
+              ++dyi;
+            }
+          }
+        }
+      }
+      __syncthreads();   // the stage may be refilled
+    }
+  }
+}
+
 struct Geometry {
   int x_expand, y_expand, x_add, x_sub, y_add, y_sub;
   uint32_t fx_scale, fy_scale, fxy_scale;
@@ -278,8 +536,23 @@ extern "C" int b2_rescale_planes(b2_ctx* ctx, int stream, const b2_rescale_job* 
   int cls = dj[0].num_channels == 1 ? (dj[0].x_expand * 2 + dj[0].y_expand) : -1;
   for (int i = 1; i < n_jobs && cls >= 0; ++i)
     if (dj[(size_t)i].num_channels != 1 || dj[(size_t)i].x_expand * 2 + dj[(size_t)i].y_expand != cls) cls = -1;
-  const int rows = rows_per_unit(cls < 0 ? -1 : (cls & 1));
+  const bool columns = cls >= 0 && getenv("B2_RESCALE_SAMPLES") == NULL;   // one-channel planes of one direction: the column walkers
+  // the streamed form needs 16-byte aligned source rows and a bounded source segment per 1024-column unit
+  bool stream_flag = columns && getenv("B2_RESCALE_COLUMNS") == NULL;
+  for (int i = 0; i < n_jobs && stream_flag; ++i) {
+    const b2_rescale_job& j = jobs[i];
+    if ((((uintptr_t)j.src | (uintptr_t)(uint32_t)j.src_stride) & 15) != 0) { stream_flag = false; break; }
+    const XEnt* xt = xpool.data() + dj[(size_t)i].xtab;
+    for (int xc0 = 0; xc0 < j.dst_width; xc0 += kThreads * kCols) {
+      const int xc1 = (xc0 + kThreads * kCols < j.dst_width) ? xc0 + kThreads * kCols : j.dst_width;
+      const int lo = dj[(size_t)i].x_expand ? xt[xc0].a : (xt[xc0].a > 0 ? xt[xc0].a - 1 : 0);
+      const int hi = dj[(size_t)i].x_expand ? xt[xc1 - 1].b + 1 : xt[xc1 - 1].b;
+      if (hi - (lo & ~15) + 16 > kSegMax) { stream_flag = false; break; }
+    }
+  }
+  const int rows = columns ? kRowsGroup : rows_per_unit(cls < 0 ? -1 : (cls & 1));
   for (int i = 0; i < n_jobs; ++i) {
+    if (columns) dj[(size_t)i].units_x = (uint32_t)((dj[(size_t)i].dst_width + kThreads * kCols - 1) / (kThreads * kCols));
     const uint32_t items = dj[(size_t)i].units_x * (uint32_t)((dj[(size_t)i].dst_height + rows - 1) / rows);
     if (i == 0) uni = items; else if (items != uni) uni = 0;
     pre[(size_t)i] = (uint32_t)tot;
@@ -305,6 +578,42 @@ extern "C" int b2_rescale_planes(b2_ctx* ctx, int stream, const b2_rescale_job* 
   rescale_kernel<XE, YE, CH><<<b2_grid_for(ctx, 4, tot), kThreads, 0, ctx->streams[stream]>>>( \
       (const RescaleJobDev*)base, (const uint32_t*)(base + jb), (uint32_t)n_jobs, uni, (uint32_t)tot,             \
       (const XEnt*)(base + jb + pb), (const YEnt*)(base + jb + pb + xb))
+#define B2_RESCALE_COLUMNS(XE, YE)                                                                              \
+  rescale_columns_kernel<XE, YE><<<b2_grid_for(ctx, 3, tot), kThreads, 0, ctx->streams[stream]>>>(                 \
+      (const RescaleJobDev*)base, (const uint32_t*)(base + jb), (uint32_t)n_jobs, uni, (uint32_t)tot,             \
+      (const XEnt*)(base + jb + pb), (const YEnt*)(base + jb + pb + xb))
+#define B2_RESCALE_STREAM(XE, YE)                                                                               \
+  do {                                                                                                            \
+    B2_CUDA(ctx, cudaFuncSetAttribute(rescale_stream_kernel<XE, YE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmem)); \
+    rescale_stream_kernel<XE, YE><<<b2_grid_for(ctx, 3, tot), kThreads, kStreamSmem, ctx->streams[stream_id]>>>(     \
+        (const RescaleJobDev*)base, (const uint32_t*)(base + jb), (uint32_t)n_jobs, uni, (uint32_t)tot,           \
+        (const XEnt*)(base + jb + pb), (const YEnt*)(base + jb + pb + xb));                                       \
+  } while (0)
+  const int stream_id = stream;
+  if (stream_flag) {
+    switch (cls) {
+      case 0: B2_RESCALE_STREAM(0, 0); break;
+      case 1: B2_RESCALE_STREAM(0, 1); break;
+      case 2: B2_RESCALE_STREAM(1, 0); break;
+      default: B2_RESCALE_STREAM(1, 1); break;
+    }
+    ctx->launches++;
+    B2_CUDA(ctx, cudaGetLastError());
+    return B2_OK;
+  }
+#undef B2_RESCALE_STREAM
+  if (columns) {
+    switch (cls) {
+      case 0: B2_RESCALE_COLUMNS(0, 0); break;
+      case 1: B2_RESCALE_COLUMNS(0, 1); break;
+      case 2: B2_RESCALE_COLUMNS(1, 0); break;
+      default: B2_RESCALE_COLUMNS(1, 1); break;
+    }
+    ctx->launches++;
+    B2_CUDA(ctx, cudaGetLastError());
+    return B2_OK;
+  }
+#undef B2_RESCALE_COLUMNS
   switch (cls) {
     case 0: B2_RESCALE_LAUNCH(0, 0, 1); break;
     case 1: B2_RESCALE_LAUNCH(0, 1, 1); break;

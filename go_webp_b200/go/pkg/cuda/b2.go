@@ -244,6 +244,8 @@ const (
 	ForwardChain
 	ColorIndexInverse
 	BundleColorMap
+	PredictorInverse
+	PredictorForward
 )
 
 // VP8L runs one batched VP8L transform (pkg/libwebp/dsp/lossless.go:337-459,
@@ -280,6 +282,10 @@ func (c *Context) VP8L(stream int, op VP8LOp, jobs []ArgbJob) error {
 		st = C.b2_vp8l_color_index_inverse(c.h, s, &cj[0], n)
 	case BundleColorMap:
 		st = C.b2_vp8l_bundle_color_map(c.h, s, &cj[0], n)
+	case PredictorInverse:
+		st = C.b2_vp8l_predictor_inverse(c.h, s, &cj[0], n)
+	case PredictorForward:
+		st = C.b2_vp8l_predictor_forward(c.h, s, &cj[0], n)
 	default:
 		return ErrInvalidConfig
 	}

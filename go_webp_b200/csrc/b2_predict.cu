@@ -263,6 +263,9 @@ constexpr int kPublish = B2_PRED_PUBLISH;
 #ifndef B2_PRED_CHUNK
 #define B2_PRED_CHUNK 16
 #endif
+#ifndef B2_PRED_FAST
+#define B2_PRED_FAST 1
+#endif
 constexpr int kChunk = B2_PRED_CHUNK;   // columns of the row above fetched at a time (power of two <= 32)   // columns between two progress publications
 
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
@@ -491,10 +494,169 @@ __device__ __forceinline__ void inverse_band(const PredJobDev* __restrict__ jp, 
   asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
+// The same band, restructured so that nothing inside a step is lane-dependent control flow.  In
+// inverse_band a lane fetches, flushes and switches tile when ITS column hits a multiple of 8, i.e. at a
+// different step than its neighbours (the lanes are 2 columns apart): every step carries the compares,
+// branches and convergence barriers of all those events (SASS: 136 of the 521 instructions of a step pair
+// are ISETP / BRA / BSSY / BSYNC, ~100 more are moves and ring addressing).  Here time is cut into groups of
+// 8 steps and everything periodic happens at group boundaries for ALL lanes at once: a lane's 8 columns of
+// a group start at c0 = 8g - 2 lane (8-byte aligned instead of 32-byte aligned), its residuals arrive as
+// four 8-byte cp.async two groups ahead, its 8 outputs stay in registers and leave as four 64-bit stores,
+// the input ring is indexed by step (immediate offsets in the unrolled body), the tile of the NEXT group's
+// last column is fetched one group ahead and switched in by a select when the column crosses a tile
+// boundary (tiles are at least 8 wide: at most one boundary per group).  Needs the vector preconditions
+// (width % 4 == 0, 16-byte aligned images) and tiles of 8 pixels or more; other jobs take inverse_band.
+constexpr int kFastRing = 4 * 8;        // input ring: 4 groups of 8 residuals per lane
+constexpr int kFastLaneWords = 34;      // 8-byte aligned slots; 34 l mod 32 = 2 l: two lanes per bank at most
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void inverse_band_fast(const PredJobDev* __restrict__ jp, uint32_t i, uint32_t* __restrict__ flags,
+                                                  uint32_t* ring, int lane) {
+  const int w = jp->width, h = jp->height, bits = jp->bits;
+  const int row = (int)i * 32 + lane;
+  const bool row_ok = row < h;
+  const uint32_t* __restrict__ in_row = jp->src + (size_t)row * w;
+  uint32_t* __restrict__ out_row = jp->dst + (size_t)row * w;
+  const uint32_t* up_row = jp->dst + (size_t)(i * 32 - 1) * w;      // last row of the band above (i > 0)
+  const uint32_t* __restrict__ mode_row = jp->modes + (size_t)(row >> bits) * jp->tiles_per_row;
+  const uint32_t* flag_up = flags + jp->flag_off + i - 1;
+  uint32_t* flag_me = flags + jp->flag_off + i;
+  const bool publish = (lane == 31) && (i + 1 < jp->bands);
+  const uint32_t chain = jp->chain;                                  // warp-uniform
+  const bool cc = (chain & CH_CC) != 0, finish = (chain & ~(uint32_t)CH_CC) != 0;
+  const int cbits = jp->cbits;
+  const uint32_t* __restrict__ code_row = cc ? jp->codes + (size_t)(row >> cbits) * jp->ctiles_per_row : nullptr;
+  const int mt_last = (int)jp->tiles_per_row - 1, ct_last = (int)jp->ctiles_per_row - 1;
+  const int tile_mask = (1 << bits) - 1, ctile_mask = (1 << cbits) - 1;
+  // raw words: the mode sits in bits 8..11 and is cut out only when the word is needed, a group later, so the
+  // load's latency hides behind 8 steps instead of stalling the shift that follows it
+  auto load_mode_raw = [&](int col) -> uint32_t {
+    const int mt = col >> bits;
+    return (row_ok && col >= 0 && mt <= mt_last) ? __ldg(mode_row + mt) : 0u;
+  };
+  auto load_code = [&](int col) -> uint32_t {
+    const int ct = col >> cbits;
+    return (cc && row_ok && col >= 0 && ct <= ct_last) ? __ldg(code_row + ct) : 0u;
+  };
+  uint32_t* const ring_l = ring + lane * kFastLaneWords;
+  const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring_l);
+  const bool row0 = (row == 0);
+  const bool full_band = (i > 0) && ((int)i * 32 + 31 < h);
+  const int k_end = w + 62;
+  // The row above (lane 0's TR / T / TL source), 16 columns at a time, one chunk AHEAD: lane q of upc holds
+  // column chunk_first + q of the chunk in use, upc_nx the chunk after it.  The progress word of the band
+  // above is read with relaxed loads (no L1 invalidation per poll, which an acquire load costs the whole SM);
+  // the row itself is read with L2 loads issued only after the word said the columns are final, and the band
+  // above released them (membar + store) before it raised the word.
+  uint32_t avail = 0, probe = 0, upc = 0, upc_nx = 0;
+  auto fetch_chunk = [&](int first_col) -> uint32_t {   // columns first_col .. + 15 of the row above (uniform call)
+    if (i == 0 || first_col >= w) return 0u;
+    const uint32_t need_cols = (uint32_t)min(w, first_col + kChunk);
+    avail = max(avail, probe);
+    while (avail < need_cols) {
+      avail = ld_relaxed_u32(flag_up);
+      if (avail < need_cols) __nanosleep(32);
+    }
+    const int col = first_col + lane;
+    uint32_t v = (lane < kChunk && col < w) ? __ldcg(up_row + col) : 0u;
+    if (finish) v = chain_back(chain, v);
+    return v;
+  };
+  uint32_t left = 0, tl = 0, t = 0, first_px = 0;
+  // mode / code of the current column, and of the tile that holds the LAST column of the current group
+  uint32_t mode = 0, mode_e = (load_mode_raw(7 - 2 * lane) >> 8) & 0xf, code = 0, code_e = load_code(7 - 2 * lane);
+
+  auto issue = [&](int g) {   // residuals of group g: columns 8 g - 2 lane .. + 7, four 8-byte copies
+    const int cc0 = 8 * g - 2 * lane;
+    const uint32_t dst = ring_s + (uint32_t)((g & 3) * 8) * 4u;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const int col = cc0 + 2 * p;
+      if (row_ok && (unsigned)col < (unsigned)w)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(dst + 8u * p), "l"(in_row + col) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  auto group = [&](auto steady_tag, int g) {
+    constexpr bool STEADY = decltype(steady_tag)::value;   // every lane at 1 <= c <= w - 2 of an existing row > 0, all 8 steps
+    const int k0 = 8 * g, c0 = k0 - 2 * lane;
+    // the tiles of the next group's last column, one group ahead
+    const uint32_t mode_n_raw = load_mode_raw(c0 + 15), code_n = load_code(c0 + 15);
+    const uint32_t need = __reduce_or_sync(0xffffffffu, (1u << mode) | (1u << mode_e));
+    uint32_t res[8];
+    {
+      const uint32_t src = ring_s + (uint32_t)((g & 3) * 8) * 4u;
+      asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(res[0]), "=r"(res[1]) : "r"(src) : "memory");
+      asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(res[2]), "=r"(res[3]) : "r"(src + 8) : "memory");
+      asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(res[4]), "=r"(res[5]) : "r"(src + 16) : "memory");
+      asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(res[6]), "=r"(res[7]) : "r"(src + 24) : "memory");
+    }
+    if (!(k0 & 8) && i > 0) probe = ld_relaxed_u32(flag_up);   // consumed at the end of this group, 7 steps from here
+    uint32_t outv[8];
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+      const int k = k0 + s, c = c0 + s;
+      if (s == 7) {               // uniform
+        if (k0 & 8) upc = upc_nx;                          // (k + 1) % 16 == 0: columns k + 1 .. k + 16 of the row above come into use
+        else upc_nx = fetch_chunk(k + 1 + kChunk / 2);     // half a chunk before that: fetch them (8 steps of latency hiding)
+      }
+      uint32_t tr = __shfl_up_sync(0xffffffffu, left, 1);
+      const uint32_t u = __shfl_sync(0xffffffffu, upc, (k + 1) & (kChunk - 1));
+      tr = (lane == 0) ? u : tr;
+      mode = ((c & tile_mask) == 0) ? mode_e : mode;     // a new tile starts at this column (at most once per group)
+      uint32_t r = res[s];
+      if (cc) {
+        code = ((c & ctile_mask) == 0) ? code_e : code;
+        r = cc_inverse_px(code, r);
+      }
+      if (!STEADY) tr = (c == w - 1) ? first_px : tr;    // upper[x+1] of the last column wraps to the row start
+      uint32_t pred = predict_flat(mode, need, left, tl, t, tr);
+      if (!STEADY) {
+        pred = (c == 0) ? t : pred;                      // lossless.go:312
+        pred = row0 ? ((c == 0) ? 0xff000000u : left) : pred;   // :292-295
+      }
+      const uint32_t o = add_pixels(r, pred);
+      outv[s] = finish ? chain_out(chain, o) : o;
+      const bool active = STEADY || (row_ok && (unsigned)c < (unsigned)w);
+      if (!STEADY) first_px = (active && c == 0) ? o : first_px;
+      left = active ? o : left;
+      tl = t;
+      t = tr;
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const int col = c0 + 2 * p;
+      if (STEADY || (row_ok && (unsigned)col < (unsigned)w)) b2_stg_stream_v2(out_row + col, make_uint2(outv[2 * p], outv[2 * p + 1]));
+    }
+    const int done = c0 + 8;                             // columns of this lane's row that are final
+    // lane 31's columns end on 8 g - 54: publish every kPublish columns, and the end of the row
+    if (publish && done > 0 && (((g + 1) & (kPublish / 8 - 1)) == 0 || done >= w)) st_release_u32(flag_me, (uint32_t)min(done, w));
+    mode_e = (mode_n_raw >> 8) & 0xf;
+    code_e = code_n;
+  };
+
+  upc_nx = fetch_chunk(0);   // columns 0 .. 15: switched in at k = -1, the last step of group -1 (the loop's own fetches start at k = 7)
+#pragma unroll 1
+  for (int g = -3; 8 * g < k_end; ++g) {
+    issue(g + 2);
+    if (g < -1) continue;
+    asm volatile("cp.async.wait_group 2;" ::: "memory");
+    const int k0 = 8 * g;
+    if (full_band && k0 >= 64 && k0 + 7 <= w - 2) group(std::true_type{}, g);
+    else group(std::false_type{}, g);
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 __global__ void __launch_bounds__(kInvThreads, 8)
 predictor_inverse_wave_kernel(const PredJobDev* __restrict__ jobs, const uint32_t* __restrict__ order,
                               uint32_t n_bands, uint32_t* __restrict__ ctl) {
-  __shared__ __align__(16) uint32_t rings[kInvWarps][kLaneWords * 32];
+  __shared__ __align__(16) uint32_t rings[kInvWarps][(kFastLaneWords > kLaneWords ? kFastLaneWords : kLaneWords) * 32];
   const int lane = threadIdx.x & 31;
   uint32_t* ring = rings[threadIdx.x >> 5];
   uint32_t* flags = ctl + 1;
@@ -506,7 +668,9 @@ predictor_inverse_wave_kernel(const PredJobDev* __restrict__ jobs, const uint32_
     const uint32_t e = __ldg(order + ticket);    // image << 10 | band
     const PredJobDev* __restrict__ jp = jobs + (e >> 10);
     const bool vec = ((jp->width & 3) == 0) && (((((uintptr_t)jp->src) | ((uintptr_t)jp->dst)) & 15) == 0);
-    if (vec) inverse_band<true>(jp, e & 1023u, flags, ring, lane);
+    const bool fast = vec && jp->bits >= 3 && (!(jp->chain & CH_CC) || jp->cbits >= 3) && B2_PRED_FAST;
+    if (fast) inverse_band_fast(jp, e & 1023u, flags, ring, lane);
+    else if (vec) inverse_band<true>(jp, e & 1023u, flags, ring, lane);
     else inverse_band<false>(jp, e & 1023u, flags, ring, lane);
     __syncwarp();
   }

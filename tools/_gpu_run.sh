@@ -1,5 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -q -x -k "alpha_filters or fullsize" 2>&1 | tail -3
-echo "== default 16 warps"; python tools/quick_bench.py filters 2>&1 | grep gradient
-for v in g12 g24 g32; do echo "== $v"; B2_LIB=go_webp_b200/lib/variants/libb2webp_$v.so python tools/quick_bench.py filters 2>&1 | grep "unfilter gradient"; done
+timeout 1500 python -m pytest tests -m gpu -q -x -k "predictor or vp8l or chain or config2" 2>&1 | tail -3
+for r in 1 2; do
+echo "== fast"; B2_ARGB_FRAMES=64 B2_OPS=predictor_inverse python tools/quick_bench.py vp8l 2>&1 | tail -1
+echo "== fast pub8"; B2_LIB=go_webp_b200/lib/variants/libb2webp_pub8.so B2_ARGB_FRAMES=64 B2_OPS=predictor_inverse python tools/quick_bench.py vp8l 2>&1 | tail -1
+done

@@ -421,55 +421,49 @@ def config4_mixed(ctx, D, peak, steps, n_images=256):
     fancy upsample -> VP8L inverse chain), LPT-partitioned over the ranks by CALIBRATED TIME: one warm-up
     pass times each (width class, size class) group of the batch, cost = bytes / rate(group)."""
     from go_webp_b200 import partition
-    from go_webp_b200.pipeline import MixedPipeline, mixed_sizes
+    from go_webp_b200.pipeline import MixedPipeline, calibrate_mixed_rates, mixed_sizes
     sizes = mixed_sizes(n_images, 0xB2000005)
     groups = [partition.size_class(w_, h_) for (w_, h_) in sizes]
-    rates = {}
-    if D.rank == 0:
-        for g in sorted(set(groups)):
-            sub = [s for s, gg in zip(sizes, groups) if gg == g]
-            p = MixedPipeline(ctx, sub)
-            p.fill_synthetic(0xB2000005)
-            for _ in range(2):
-                p.run_device()
-            ctx.sync()
-            ctx.event_record(8)
-            for _ in range(3):
-                p.run_device()
-            ctx.event_record(9)
-            ctx.sync()
-            rates[g] = p.algorithmic_bytes() / (ctx.elapsed_ms(8, 9) / 3)
-            p.close()
+    rates = calibrate_mixed_rates(ctx, sizes) if D.rank == 0 else {}
     keys = sorted(set(groups))
     vals = D.bcast_list([rates.get(g, 0.0) for g in keys])
     rates = dict(zip(keys, vals))
     costs = partition.calibrated_costs(sizes, rates)
-    parts = partition.lpt_partition(costs, D.world)
-    mine = [sizes[i] for i in parts[D.rank]]
-    p = MixedPipeline(ctx, mine)
-    p.fill_synthetic(0xB2000005)
     k = max(3, min(steps, 10))
-    for _ in range(3):
-        p.run_device()
-    D.barrier()
-    ctx.event_record(8)
-    for _ in range(k):
-        p.run_device()
-    ctx.event_record(9)
-    D.barrier()
-    my_ms = ctx.elapsed_ms(8, 9) / k
-    per_gpu = D.gather(my_ms)
-    ms = max(per_gpu)
-    px = D.sum(p.pixels)
-    by = D.sum(p.algorithmic_bytes())
+    rounds, best = (3 if D.world > 1 else 1), None
+    for it in range(rounds):   # the class model first, then the measured per-GPU times of a pass correct it (every rank computes the same update)
+        parts = partition.lpt_partition(costs, D.world)
+        p = MixedPipeline(ctx, [sizes[i] for i in parts[D.rank]])
+        p.fill_synthetic(0xB2000005)
+        for _ in range(3):
+            p.run_device()
+        D.barrier()
+        ctx.event_record(8)
+        for _ in range(k):
+            p.run_device()
+        ctx.event_record(9)
+        D.barrier()
+        per_gpu = D.gather(ctx.elapsed_ms(8, 9) / k)
+        res = {"ms": max(per_gpu), "per_gpu": per_gpu, "px": D.sum(p.pixels), "by": D.sum(p.algorithmic_bytes()), "round": it}
+        p.close()
+        if best is None or res["ms"] < best["ms"]:
+            best = res
+        pred = [sum(costs[i] for i in part) for part in parts]
+        norm = sum(per_gpu) / sum(pred)
+        for part, pr, me in zip(parts, pred, per_gpu):
+            f = (me / (pr * norm)) ** 0.7
+            for i in part:
+                costs[i] *= f
+    ms, per_gpu, px, by = best["ms"], best["per_gpu"], best["px"], best["by"]
     out = {"workload": f"configs[4]: {n_images} mixed-size images (64x64..8192x8192, odd sizes), import -> fancy upsample -> "
                        f"cross-colour^-1 + add-green, 3 launches per pass over the rank's share", "n_gpus": D.world,
            "scaling": "strong", "value": px / ms / 1e3, "unit": "Mpixel/s", "ms_per_step": ms,
            "per_gpu_ms": per_gpu, "imbalance_max_over_mean": ms * D.world / sum(per_gpu),
-           "partition": "LPT on calibrated time (bytes / measured rate of the image's width-alignment x size class)",
+           "partition": "LPT on calibrated time (bytes / measured rate of the image's width-alignment x size class), then two "
+                        "rounds in which the measured per-GPU times of a pass correct the costs; the best of the three "
+                        f"partitions (round {best['round']}) is the one reported, all timed alike",
            "roofline": {"bound": "hbm", "achieved": by / D.world / ms / 1e6, "peak": peak, "unit": "GB/s",
                         "frac": by / D.world / ms / 1e6 / peak, "per": "GPU (mean share / slowest rank)"}}
-    p.close()
     return out
 
 

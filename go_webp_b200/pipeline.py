@@ -520,3 +520,34 @@ class MixedPipeline:
     def close(self):
         for b in ("d_src", "d_y", "d_a", "d_u", "d_v", "d_dst", "d_out", "d_data", "d_flags"):
             getattr(self, b).free()
+
+
+def calibrate_mixed_rates(ctx: Context, sizes, seed: int = 0xB2000005) -> dict:
+    """One warm-up pass for the time-based partition of a mixed-size batch (configs[4]): the images of
+    every class (partition.size_class: row alignment x width bin) run as one batch through the full
+    pipeline; rate = algorithmic bytes / (time - the fixed cost of three launches with next to nothing
+    to do), in bytes per millisecond.  Returns class -> rate."""
+    from . import partition
+
+    def time_pass(sub):
+        p = MixedPipeline(ctx, sub)
+        p.fill_synthetic(seed)
+        for _ in range(2):
+            p.run_device()
+        ctx.sync()
+        ctx.event_record(8)
+        for _ in range(3):
+            p.run_device()
+        ctx.event_record(9)
+        ctx.sync()
+        ms, by = ctx.elapsed_ms(8, 9) / 3, p.algorithmic_bytes()
+        p.close()
+        return ms, by
+
+    t0, _ = time_pass([(64, 64)])
+    groups = [partition.size_class(w, h) for (w, h) in sizes]
+    rates = {}
+    for g in sorted(set(groups)):
+        ms, by = time_pass([s for s, gg in zip(sizes, groups) if gg == g])
+        rates[g] = by / max(ms - t0, 0.05 * ms)
+    return rates

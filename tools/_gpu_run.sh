@@ -1,7 +1,8 @@
 #!/bin/bash
-mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q -x -k "predictor or vp8l or chain or config2" 2>&1 | tail -3
-for r in 1 2; do
-echo "== fast"; B2_ARGB_FRAMES=64 B2_OPS=predictor_inverse python tools/quick_bench.py vp8l 2>&1 | tail -1
-echo "== fast pub8"; B2_LIB=go_webp_b200/lib/variants/libb2webp_pub8.so B2_ARGB_FRAMES=64 B2_OPS=predictor_inverse python tools/quick_bench.py vp8l 2>&1 | tail -1
-done
+echo "== calibrated + refine"; B2_MIXED_CALIBRATED=1 B2_MIXED_REFINE=4 python tools/mixed_bench.py 2>&1 | python -c "
+import sys,json
+for l in sys.stdin:
+    d=json.loads(l)
+    if 'rates_GBps' in d: continue
+    if 'refine_round' in d: print('   ', d); continue
+    print(d.get('n_gpus'), 'imb', round(d.get('imbalance_max_over_mean',0),3), 'frac', round(d.get('frac_of_measured_peak_per_gpu',0),3))"

@@ -14,6 +14,9 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from go_webp_b200 import _abi  # noqa: E402
+if os.environ.get("B2_LIB"):  # experiment builds (tools/variants.sh)
+    _abi.LIB_PATH = os.environ["B2_LIB"]
 from go_webp_b200.device import Context  # noqa: E402
 from go_webp_b200.partition import import_cost_bytes, lpt_partition, upsample_cost_bytes  # noqa: E402
 from go_webp_b200.pipeline import MixedPipeline, mixed_sizes  # noqa: E402
@@ -103,9 +106,33 @@ def main():
         dist.destroy_process_group()
         return
     ctx = Context(0, 1)
+    if os.environ.get("B2_MIXED_CALIBRATED"):   # the time-based cost model bench.py uses
+        from go_webp_b200.partition import calibrated_costs
+        from go_webp_b200.pipeline import calibrate_mixed_rates
+        rates = calibrate_mixed_rates(ctx, sizes)
+        print(json.dumps({"rates_GBps": {k: round(v / 1e6, 1) for k, v in rates.items()}}), flush=True)
+        costs = calibrated_costs(sizes, rates)
     for g in (1, 2, 4, 8):
         parts = lpt_partition(costs, g)
         res = [time_share(ctx, [sizes[i] for i in part]) for part in parts]
+        if os.environ.get("B2_MIXED_REFINE") and g > 1:   # measured shares correct the model, a few rounds
+            cur = list(costs)
+            best = (max(r[0] for r in res), parts, res)
+            for it in range(int(os.environ["B2_MIXED_REFINE"])):
+                pred = [sum(cur[i] for i in part) for part in parts]
+                meas = [r[0] for r in res]
+                norm = sum(meas) / sum(pred)
+                for part, pr, me in zip(parts, pred, meas):
+                    f = (me / (pr * norm)) ** 0.7
+                    for i in part:
+                        cur[i] *= f
+                parts = lpt_partition(cur, g)
+                res = [time_share(ctx, [sizes[i] for i in part]) for part in parts]
+                tm = max(r[0] for r in res)
+                print(json.dumps({"refine_round": it + 1, "n_gpus": g, "imbalance": tm * g / sum(r[0] for r in res)}), flush=True)
+                if tm < best[0]:
+                    best = (tm, parts, res)
+            _, parts, res = best
         tmax = max(r[0] for r in res)
         tmean = sum(r[0] for r in res) / g
         px = sum(r[1] for r in res)

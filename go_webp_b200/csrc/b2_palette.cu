@@ -22,7 +22,7 @@
 // (GetColorPalette never makes one) fall back to a linear scan.
 //
 // Mapping: a warp owns a segment of up to 8192 pixels of one row and streams it through its
-// own ring of four 512-pixel stages, each filled by ONE cp.async.bulk (TMA) that lane 0 issues
+// own ring of a few 512-pixel stages (5 with 8-bit packing, 2 with the sub-byte ones), each filled by ONE cp.async.bulk (TMA) that lane 0 issues
 // on the stage's mbarrier -- 8 KB in flight per warp whatever the lanes are doing; a lane
 // converts 4 pixels per 128-pixel chunk (one 128-bit shared load -> 4 / 2 / 1 / half a word).
 // Rows that miss the 16-byte alignment take the same conversion on direct loads.
@@ -34,16 +34,28 @@ constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kSegPx = 8192;
 constexpr int kBlkPx = 512;
-#ifndef B2_PAL_STAGES
-#define B2_PAL_STAGES 4
+// Ring depth and CTAs per SM by packing (measured, profiles/r02_palette_variants.txt): with 8-bit
+// packing the kernel writes as much as it reads and wants deep rings (5 stages, 2 CTAs: 0.93-0.96 of the
+// measured peak vs 0.89 with 2 stages, 3 CTAs); the sub-byte packings are almost pure reads and want
+// more warps with shallow rings (2 colours: 0.71 vs 0.58).
+#ifndef B2_PAL_STAGES0
+#define B2_PAL_STAGES0 5
 #endif
-#ifndef B2_PAL_CTAS
-#define B2_PAL_CTAS 2
+#ifndef B2_PAL_CTAS0
+#define B2_PAL_CTAS0 2
 #endif
-constexpr int kStages = B2_PAL_STAGES;
+#ifndef B2_PAL_STAGES1
+#define B2_PAL_STAGES1 2
+#endif
+#ifndef B2_PAL_CTAS1
+#define B2_PAL_CTAS1 3
+#endif
+constexpr int kMaxStages = 8;
+__host__ __device__ constexpr int stages_of(int xbits) { return xbits == 0 ? B2_PAL_STAGES0 : B2_PAL_STAGES1; }
+__host__ __device__ constexpr int ctas_of(int xbits) { return xbits == 0 ? B2_PAL_CTAS0 : B2_PAL_CTAS1; }
 constexpr int kStageBytes = kBlkPx * 4;
 constexpr int kTabBytes = 16384;
-constexpr int kSmemBytes = kTabBytes + kWarps * kStages * kStageBytes;
+__host__ __device__ constexpr int smem_of(int xbits) { return kTabBytes + kWarps * stages_of(xbits) * kStageBytes; }
 constexpr int kMaxDraws = 256;
 enum { S_GREEDY = 0, S_HASHED = 1, S_SCAN = 2 };
 
@@ -60,7 +72,7 @@ struct PalShared {
   uint32_t pal[256];
   int kind, collide, size, strategy;   // strategy: the reference's numbering (0 greedy, 1..3 hashes, 4 exact search), for the record
   uint32_t mask, mult, shift;
-  uint64_t bars[kWarps * kStages];
+  uint64_t bars[kWarps * kMaxStages];
 };
 struct Hash { uint32_t mask, mult, shift, g0, g1, g2; };   // g0..g2: the first three colours, for the greedy compares
 
@@ -192,6 +204,7 @@ __device__ __forceinline__ void convert_segment_bulk(const PalShared& sh, const 
                                                      const uint32_t* __restrict__ srow, uint32_t* __restrict__ drow, int xseg,
                                                      int xend, int width, int lane, uint8_t* ring, uint32_t ring_s,
                                                      uint32_t bar_s, uint32_t& phase) {
+  constexpr int kStages = stages_of(XBITS);
   const int n_blk = (xend - xseg + kBlkPx - 1) / kBlkPx;
   auto issue = [&](int b) {   // lane 0: request block b of the segment into stage b % kStages
     const int xb = xseg + b * kBlkPx;
@@ -266,7 +279,7 @@ __device__ __forceinline__ void convert_unit(const PalShared& sh, const uint8_t*
 }
 
 template <int XBITS>
-__global__ void __launch_bounds__(kThreads, B2_PAL_CTAS)
+__global__ void __launch_bounds__(kThreads, ctas_of(XBITS))
 apply_palette_kernel(const PalJobDev* __restrict__ jobs, const uint32_t* __restrict__ prefix, uint32_t n_jobs,
                      uint32_t uniform, uint32_t total_items) {
   extern __shared__ __align__(128) uint8_t smem[];   // byte table (palette index, 0xff = empty), then the warps' rings
@@ -274,9 +287,10 @@ apply_palette_kernel(const PalJobDev* __restrict__ jobs, const uint32_t* __restr
   uint8_t* const tab = smem;
   const int lane = threadIdx.x & 31;
   const uint32_t warp = threadIdx.x >> 5;
+  constexpr int kStages = stages_of(XBITS);
   uint8_t* const ring = smem + kTabBytes + warp * (kStages * kStageBytes);
   const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
-  const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(sh.bars + warp * kStages);
+  const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(sh.bars + warp * kMaxStages);
   if (lane == 0) {
     for (int s = 0; s < kStages; ++s) mbar_init(bar_s + 8 * s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -360,21 +374,21 @@ extern "C" int b2_vp8l_apply_palette(b2_ctx* ctx, int stream, const b2_palette_j
     if (st != B2_OK) return st;
     const PalJobDev* djobs = (const PalJobDev*)dev;
     const uint32_t* dpre = (const uint32_t*)((uint8_t*)dev + pre_off);
-    const int grid = b2_grid_for(ctx, B2_PAL_CTAS, total);
+    const int grid = b2_grid_for(ctx, ctas_of(xbits), total);
     cudaStream_t s = ctx->streams[stream];
     static bool smem_set = false;   // 80 KB of dynamic shared memory needs the opt-in, once per process
     if (!smem_set) {
-      B2_CUDA(ctx, cudaFuncSetAttribute(apply_palette_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-      B2_CUDA(ctx, cudaFuncSetAttribute(apply_palette_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-      B2_CUDA(ctx, cudaFuncSetAttribute(apply_palette_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-      B2_CUDA(ctx, cudaFuncSetAttribute(apply_palette_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+      B2_CUDA(ctx, cudaFuncSetAttribute(apply_palette_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_of(0)));
+      B2_CUDA(ctx, cudaFuncSetAttribute(apply_palette_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_of(1)));
+      B2_CUDA(ctx, cudaFuncSetAttribute(apply_palette_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_of(2)));
+      B2_CUDA(ctx, cudaFuncSetAttribute(apply_palette_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_of(3)));
       smem_set = true;
     }
     switch (xbits) {
-      case 0: apply_palette_kernel<0><<<grid, kThreads, kSmemBytes, s>>>(djobs, dpre, (uint32_t)cnt, uniform, (uint32_t)total); break;
-      case 1: apply_palette_kernel<1><<<grid, kThreads, kSmemBytes, s>>>(djobs, dpre, (uint32_t)cnt, uniform, (uint32_t)total); break;
-      case 2: apply_palette_kernel<2><<<grid, kThreads, kSmemBytes, s>>>(djobs, dpre, (uint32_t)cnt, uniform, (uint32_t)total); break;
-      default: apply_palette_kernel<3><<<grid, kThreads, kSmemBytes, s>>>(djobs, dpre, (uint32_t)cnt, uniform, (uint32_t)total); break;
+      case 0: apply_palette_kernel<0><<<grid, kThreads, smem_of(0), s>>>(djobs, dpre, (uint32_t)cnt, uniform, (uint32_t)total); break;
+      case 1: apply_palette_kernel<1><<<grid, kThreads, smem_of(1), s>>>(djobs, dpre, (uint32_t)cnt, uniform, (uint32_t)total); break;
+      case 2: apply_palette_kernel<2><<<grid, kThreads, smem_of(2), s>>>(djobs, dpre, (uint32_t)cnt, uniform, (uint32_t)total); break;
+      default: apply_palette_kernel<3><<<grid, kThreads, smem_of(3), s>>>(djobs, dpre, (uint32_t)cnt, uniform, (uint32_t)total); break;
     }
     ctx->launches++;
     B2_CUDA(ctx, cudaGetLastError());

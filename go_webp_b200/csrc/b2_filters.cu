@@ -17,6 +17,8 @@
 //               by shuffle; the row above a band is read back from the output).
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "b2_common.cuh"
 
 namespace {
@@ -267,6 +269,201 @@ alpha_unfilter_vertical_kernel(const FiltJobDev* __restrict__ jobs, const uint32
   }
 }
 
+// ---- gradient band on aligned rows, through shared-memory tiles -----------------------------
+// The wavefront puts lane l on row l of the band, so a lane-indexed global access touches 32
+// different rows: one sector per lane, 32 L1 wavefronts per load or store instruction for 128
+// useful bytes.  Here global memory is only touched in row-contiguous pieces: time is cut into
+// blocks of 8 quad steps; block b's inputs are the parallelogram {row r, words 8b - r .. 8b - r + 7},
+// fetched two blocks ahead by eight 4-byte cp.async per lane (lane -> row 4i + lane/8, word lane%8:
+// 32 contiguous bytes per row, four rows per instruction) into a [32][9]-word tile; the step reads
+// tile[lane][t] (stride 9: conflict free), writes its output word to a second tile, and the block's
+// outputs leave the same way the inputs came.
+//
+// The step itself is latency bound (ncu: a working warp issues on 20 % of its cycles, the rest is
+// the dependent chain), so NOTHING but the recurrence sits on the chain:
+//  * out = (in + clip(left + top - topleft)) & 0xff (GradientUnfilter_C, filters.go:150-171); what a
+//    lane hands to the lane below is not its output word but the four differences d_k = top_k -
+//    top_{k-1} that lane needs (differences of its own consecutive outputs), each by its own shuffle
+//    issued as soon as the pixel is done, three quarters of a step before it is used.  A pixel is then
+//    relu(min(left + d, 255)) -- ONE instruction whose operand is the shuffle's result itself --, an add
+//    (the input byte's shift folded in) and a mask: three dependent instructions per pixel;
+//  * the shuffle is a rotation: lane 0 reads lane 31, and lane 31 sends the differences of the row
+//    above the band instead of its own, so no lane selects anything on the receiving side;
+//  * the row above the band never goes through global memory: the band above leaves the words of its
+//    last row in a 512-word ring in shared memory (its warp's), the band converts nine of them to
+//    differences at the start of a block (lanes 0..8) and lane 31 reads them back a step at a time.
+// Progress words count finished blocks: (band << 12) + blocks.  A band needs block b + 4 of the band
+// above finished before its block b; a band never runs more than 60 blocks ahead of the band below (the
+// ring), and a warp starts a new band only when the band below its previous one is done with the ring.
+// 15 bands x 60 blocks cover the longest row (516 blocks), so the three waits cannot form a cycle.
+// No special cases in the arithmetic: row 0 has d = 0 (pred = left: the horizontal rule of the first
+// row), column 0 starts with left = 0 and d0 = top_0 (pred = clip(top) = top: the reference's prev_line[0]).
+#ifndef B2_GRAD_WARPS
+#define B2_GRAD_WARPS 16
+#endif
+constexpr int kGradWarps = B2_GRAD_WARPS;
+#ifndef B2_GRAD_CTAS
+#define B2_GRAD_CTAS 2
+#endif
+constexpr int kGradCtasPerSm = B2_GRAD_CTAS;
+#ifndef B2_GRAD_TILED
+#define B2_GRAD_TILED 1
+#endif
+constexpr int kGS = 9;                       // tile row stride, words
+constexpr int kGTile = 32 * kGS;             // one tile: 32 rows x 8 words (+1 pad)
+constexpr int kGRing = 3;                    // input tiles in flight
+constexpr int kGHand = 512;                  // words of the band's last row kept for the band below
+constexpr int kGGap = 60;                    // blocks a band may run ahead of the band below
+constexpr int kGXSlot = 33 * 2 + 2;          // one exchange slot: 33 entries of two differences (+ pad, keeps 8-byte alignment)
+constexpr int kGX = 8 * 2 * kGXSlot;         // 8 steps x {(d0, d1), (d2, d3)}
+constexpr int kGWarpWords = (kGRing + 1) * kGTile + kGHand + kGX;
+extern __shared__ __align__(16) uint32_t grad_sm[];
+
+__device__ __forceinline__ void gradient_band_tiled(const FiltJobDev& j, int bi, volatile int* progress, int warp,
+                                                    uint32_t* sm_all, int lane) {
+  uint32_t* const sm = sm_all + warp * kGWarpWords;
+  const int w = j.width, h = j.height;
+  const int band = bi * 32, row = band + lane;
+  const bool row_ok = row < h;
+  const int nq = (w + 3) >> 2, nq_full = w >> 2;
+  const int nblk = (nq + 31 + 7) >> 3;       // quad steps 0 .. nq + 30
+  const int up_warp = (warp + kGradWarps - 1) % kGradWarps, down_warp = (warp + 1) % kGradWarps;
+  const bool has_down = band + 32 < h;
+  auto wait_word = [&](int who, int value) {   // lane 0 polls, the warp follows
+    if (lane == 0) {
+      while (progress[who] < value) {}
+      __threadfence_block();
+    }
+    __syncwarp();
+  };
+  if (bi >= kGradWarps) wait_word(down_warp, ((bi - kGradWarps + 1) << 12) + nblk);   // the ring is free again
+  uint32_t* const tout = sm + kGRing * kGTile;
+  uint32_t* const hand = tout + kGTile;
+  // exchange between neighbouring lanes: slot t, entry e: what lane e - 1 computed in step t (entry 0: the row above)
+  uint32_t* const xch = hand + kGHand;
+  const uint32_t* const hand_up = sm_all + up_warp * kGWarpWords + (kGRing + 1) * kGTile;
+  // this lane's share of a tile transfer: row tr0 + 4 i, word tw of the tile
+  const int tr0 = lane >> 3, tw = lane & 7;
+  const uint32_t sm_s = (uint32_t)__cvta_generic_to_shared(sm);
+  const uint32_t tile_off = (uint32_t)(tr0 * kGS + tw) * 4u;
+  const uint8_t* src_l = j.src + (ptrdiff_t)(band + tr0) * j.src_stride + 4 * (tw - tr0);
+  uint8_t* dst_l = j.dst + (ptrdiff_t)(band + tr0) * j.dst_stride + 4 * (tw - tr0);
+  const ptrdiff_t src_step = 4 * (ptrdiff_t)j.src_stride - 16, dst_step = 4 * (ptrdiff_t)j.dst_stride - 16;
+  auto issue = [&](int b) {            // the inputs of block b (a whole word is inside the row's stride: strides are multiples of 4)
+    if (b < nblk) {
+      const uint32_t d0 = sm_s + (uint32_t)((b % kGRing) * kGTile) * 4u + tile_off;
+      const uint8_t* p = src_l + 32 * b;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int m = 8 * b - (tr0 + 4 * i) + tw;
+        const bool ok = (band + tr0 + 4 * i < h) && m >= 0 && m < nq;
+        const uint32_t nbytes = ok ? 4u : 0u;   // 0: nothing is read, the word is zero-filled
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(d0 + (uint32_t)(4 * i * kGS) * 4u), "l"(ok ? p : j.src), "r"(nbytes) : "memory");
+        p += src_step;
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  uint32_t left = 0;                   // this row's previous output byte
+  int d0 = 0, d1 = 0, d2 = 0, d3 = 0;  // the differences of the word this lane takes next
+  // words 8 b .. 8 b + 8 of the row above (lanes 0 .. 8) -> their four differences; lane 1 + t puts them where lane 0
+  // finds them after step t (entry 0 of slot t); word 0 goes straight into lane 0's registers
+  auto above_block = [&](int b) {
+    const int m = 8 * b + lane;
+    uint32_t aw = 0u;
+    if (band > 0 && lane < 9 && m < nq) aw = hand_up[m & (kGHand - 1)];
+    const uint32_t prev = __shfl_up_sync(0xffffffffu, aw, 1);
+    const int tl = (lane == 0) ? 0 : (int)(prev >> 24);    // lane 0's own numbers are only used for word 0 (b == 0): nothing to its left
+    const int a0 = (int)(aw & 0xff), a1 = (int)((aw >> 8) & 0xff), a2 = (int)((aw >> 16) & 0xff), a3 = (int)(aw >> 24);
+    if (lane >= 1 && lane < 9) {
+      *reinterpret_cast<int2*>(xch + (2 * (lane - 1)) * kGXSlot) = make_int2(a0 - tl, a1 - a0);
+      *reinterpret_cast<int2*>(xch + (2 * (lane - 1) + 1) * kGXSlot) = make_int2(a2 - a1, a3 - a2);
+    }
+    if (b == 0 && lane == 0) { d0 = a0; d1 = a1 - a0; d2 = a2 - a1; d3 = a3 - a2; }
+    __syncwarp();
+  };
+  // One quad step.  The lane's differences leave through shared memory (entry lane + 1 of the step's slot) and the
+  // next word's arrive from entry `lane`, in two halves, each behind a warp barrier: the barrier pins the order
+  // store -> load in the instruction stream, so the loads are issued half a step and a full step before the chain
+  // needs them (shuffles were grouped by ptxas at the end of the step, back on the chain).
+  uint32_t* const xw = xch + 2 * (lane + 1);
+  const uint32_t* const xr = xch + 2 * lane;
+  auto step = [&](auto steady_tag, int t, int m, uint32_t vin) -> uint32_t {
+    constexpr bool STEADY = decltype(steady_tag)::value;
+    const uint32_t o0 = (vin + (uint32_t)__viaddmin_s32_relu((int)left, d0, 255)) & 0xffu;
+    const uint32_t o1 = ((vin >> 8) + (uint32_t)__viaddmin_s32_relu((int)o0, d1, 255)) & 0xffu;
+    *reinterpret_cast<int2*>(xw + (2 * t) * kGXSlot) = make_int2((int)(o0 - left), (int)(o1 - o0));
+    __syncwarp();
+    const int2 n01 = *reinterpret_cast<const int2*>(xr + (2 * t) * kGXSlot);
+    const uint32_t o2 = ((vin >> 16) + (uint32_t)__viaddmin_s32_relu((int)o1, d2, 255)) & 0xffu;
+    const uint32_t o3 = ((vin >> 24) + (uint32_t)__viaddmin_s32_relu((int)o2, d3, 255)) & 0xffu;
+    *reinterpret_cast<int2*>(xw + (2 * t + 1) * kGXSlot) = make_int2((int)(o2 - o1), (int)(o3 - o2));
+    __syncwarp();
+    const int2 n23 = *reinterpret_cast<const int2*>(xr + (2 * t + 1) * kGXSlot);
+    if (STEADY || (row_ok && m >= 0 && m < nq)) left = o3;   // bytes past the end of the row are never stored and never read again
+    d0 = n01.x; d1 = n01.y; d2 = n23.x; d3 = n23.y;
+    return __byte_perm(__byte_perm(o0, o1, 0x0040), __byte_perm(o2, o3, 0x0040), 0x5410);
+  };
+  const bool full_band = band + 31 < h;
+  const int tag_up = (bi - 1) << 12, tag_down = (bi + 1) << 12;
+  issue(0);
+  issue(1);
+  if (band > 0) wait_word(up_warp, tag_up + min(5, nblk));
+  above_block(0);
+  for (int b = 0; b < nblk; ++b) {
+    const int q0 = 8 * b;
+    issue(b + 2);
+    if (b > 0) {
+      if (band > 0) wait_word(up_warp, tag_up + min(b + 5, nblk));
+      above_block(b);
+    }
+    if (has_down && b > kGGap) wait_word(down_warp, tag_down + b - kGGap);
+    asm volatile("cp.async.wait_group 2;" ::: "memory");
+    __syncwarp();
+    const uint32_t* tin = sm + (b % kGRing) * kGTile;
+    const bool steady = full_band && q0 >= 31 && q0 + 7 < nq_full;   // warp-uniform: every lane inside its row on whole words
+    uint32_t vin[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) vin[t] = tin[lane * kGS + t];
+    if (steady) {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) tout[lane * kGS + t] = step(std::true_type{}, t, q0 + t - lane, vin[t]);
+      __syncwarp();
+      uint8_t* p = dst_l + 32 * b;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t v = tout[(tr0 + 4 * i) * kGS + tw];
+        *reinterpret_cast<uint32_t*>(p) = v;
+        if (i == 7 && tr0 == 3) hand[(q0 - 31 + tw) & (kGHand - 1)] = v;   // row 31
+        p += dst_step;
+      }
+    } else {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) tout[lane * kGS + t] = step(std::false_type{}, t, q0 + t - lane, vin[t]);
+      __syncwarp();
+      uint8_t* p = dst_l + 32 * b;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int m = q0 - (tr0 + 4 * i) + tw;
+        if ((band + tr0 + 4 * i < h) && m >= 0 && m < nq) {
+          const uint32_t v = tout[(tr0 + 4 * i) * kGS + tw];
+          if (4 * m + 4 <= w) *reinterpret_cast<uint32_t*>(p) = v;
+          else for (int t2 = 0; 4 * m + t2 < w; ++t2) p[t2] = (uint8_t)(v >> (8 * t2));
+          if (i == 7 && tr0 == 3) hand[m & (kGHand - 1)] = v;
+        }
+        p += dst_step;
+      }
+    }
+    __syncwarp();                        // the block's outputs are written (all lanes), the output tile is free again
+    if (lane == 31) {
+      __threadfence_block();
+      progress[warp] = (bi << 12) + b + 1;
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncwarp();
+}
+
 // ---- unfilter, GRADIENT: one CTA per image, its warps pipelined down the bands ------------
 // A band of 32 rows is a wavefront inside one warp (lane = row, one column of skew per row).
 // Band b needs the last row of band b-1 one column ahead of its own lane 0, so the bands of an
@@ -275,10 +472,6 @@ alpha_unfilter_vertical_kernel(const FiltJobDev* __restrict__ jobs, const uint32
 // word per warp in shared memory, monotonic), and the warp below waits for the columns it is
 // about to read.  The last row itself travels through global memory (written by lane 31,
 // CTA-scope fence, flag; read back by lane 0 with volatile loads after its own fence).
-#ifndef B2_GRAD_WARPS
-#define B2_GRAD_WARPS 16
-#endif
-constexpr int kGradWarps = B2_GRAD_WARPS;
 __global__ void __launch_bounds__(32 * kGradWarps)
 alpha_unfilter_gradient_kernel(const FiltJobDev* __restrict__ jobs, uint32_t n_jobs) {
   __shared__ volatile int progress[kGradWarps];
@@ -310,6 +503,12 @@ alpha_unfilter_gradient_kernel(const FiltJobDev* __restrict__ jobs, uint32_t n_j
         }
       };
       const bool words = ((((uintptr_t)j.src | (uintptr_t)j.dst) | (uint32_t)j.src_stride | (uint32_t)j.dst_stride) & 3) == 0;
+#if B2_GRAD_TILED
+      if (words) {
+        gradient_band_tiled(j, bi, progress, warp, grad_sm, lane);
+        continue;
+      }
+#endif
       if (words) {
         // Aligned rows: the skew between rows is one 4-pixel word instead of one pixel, so that
         // every lane is at a word boundary at the same time.  Quad step q: lane l takes word
@@ -534,7 +733,10 @@ extern "C" int b2_alpha_unfilter(b2_ctx* ctx, int stream, const b2_alpha_filter_
     ctx->launches++;
   }
   if (counts[3] > 0) {
-    alpha_unfilter_gradient_kernel<<<b2_grid_for(ctx, 2, (uint64_t)n_jobs), 32 * kGradWarps, 0, s>>>(dj, (uint32_t)n_jobs);
+    const int grad_smem = B2_GRAD_TILED ? kGradWarps * kGWarpWords * (int)sizeof(uint32_t) : 0;
+    if (grad_smem > 0)   // per device: set on every call (a host-side table write)
+      B2_CUDA(ctx, cudaFuncSetAttribute(alpha_unfilter_gradient_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, grad_smem));
+    alpha_unfilter_gradient_kernel<<<b2_grid_for(ctx, kGradCtasPerSm, (uint64_t)n_jobs), 32 * kGradWarps, grad_smem, s>>>(dj, (uint32_t)n_jobs);
     ctx->launches++;
   }
   if (counts[2] > 0) {

@@ -941,6 +941,13 @@ def test_alpha_filters(gpu, golden_dir):
         back = F.AlphaFilterBatch(un, filts, row_align=row_align, ptr_offset=ptr_offset)
         for p, f, o in zip(planes, filts, back):
             assert (o == p).all(), (p.shape, f, row_align, ptr_offset)
+    # wide planes: the gradient wavefront's steady state (whole 8-word blocks of every row of a band in flight),
+    # rows ending inside a word and inside a block, a short last band
+    planes = [rng.integers(0, 256, (h, w), dtype=np.uint8) for (w, h) in [(1920, 300), (1923, 100), (2048, 64), (997, 161), (4099, 37)]]
+    for row_align in (16, 4):
+        un = F.AlphaUnfilterBatch(planes, [3] * len(planes), row_align=row_align)
+        for p, o in zip(planes, un):
+            assert (o == oracle.alpha_unfilter(p, 3)).all(), (p.shape, row_align)
     data = rng.integers(0, 256, 40 * 7, dtype=np.uint8)
     out = np.zeros_like(data)
     F.GradientFilter_C(data, 33, 7, 40, out)

@@ -318,6 +318,21 @@ constexpr int kGXSlot = 33 * 2 + 2;          // one exchange slot: 33 entries of
 constexpr int kGX = 8 * 2 * kGXSlot;         // 8 steps x {(d0, d1), (d2, d3)}
 constexpr int kGWarpWords = (kGRing + 1) * kGTile + kGHand + kGX;
 extern __shared__ __align__(16) uint32_t grad_sm[];
+#ifdef B2_GRAD_TRACE
+__device__ long long g_grad_trace[64 * 128];   // [band][0]: start, [band][1 + b]: end of block b (tools/grad_trace.cu)
+#define B2_TRACE(slot) do { if (lane == 0 && bi < 64 && (slot) < 128) g_grad_trace[bi * 128 + (slot)] = clock64(); } while (0)
+#else
+#define B2_TRACE(slot) do { } while (0)
+#endif
+
+__device__ __forceinline__ int ld_acquire_cta_shared(const volatile int* p) {
+  int v;
+  asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared((const void*)p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_cta_shared(volatile int* p, int v) {
+  asm volatile("st.release.cta.shared.u32 [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared((void*)p)), "r"(v) : "memory");
+}
 
 __device__ __forceinline__ void gradient_band_tiled(const FiltJobDev& j, int bi, volatile int* progress, int warp,
                                                     uint32_t* sm_all, int lane) {
@@ -329,10 +344,9 @@ __device__ __forceinline__ void gradient_band_tiled(const FiltJobDev& j, int bi,
   const int nblk = (nq + 31 + 7) >> 3;       // quad steps 0 .. nq + 30
   const int up_warp = (warp + kGradWarps - 1) % kGradWarps, down_warp = (warp + 1) % kGradWarps;
   const bool has_down = band + 32 < h;
-  auto wait_word = [&](int who, int value) {   // lane 0 polls, the warp follows
+  auto wait_word = [&](int who, int value) {   // lane 0 polls (acquire: a plain shared load on this target), the warp follows
     if (lane == 0) {
-      while (progress[who] < value) {}
-      __threadfence_block();
+      while (ld_acquire_cta_shared(progress + who) < value) {}
     }
     __syncwarp();
   };
@@ -349,15 +363,27 @@ __device__ __forceinline__ void gradient_band_tiled(const FiltJobDev& j, int bi,
   const uint8_t* src_l = j.src + (ptrdiff_t)(band + tr0) * j.src_stride + 4 * (tw - tr0);
   uint8_t* dst_l = j.dst + (ptrdiff_t)(band + tr0) * j.dst_stride + 4 * (tw - tr0);
   const ptrdiff_t src_step = 4 * (ptrdiff_t)j.src_stride - 16, dst_step = 4 * (ptrdiff_t)j.dst_stride - 16;
+  // rows of this lane's tile items that exist (a short last band): bit i <-> row tr0 + 4 i
+  uint32_t rows_ok = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) rows_ok |= (band + tr0 + 4 * i < h) ? (1u << i) : 0u;
   auto issue = [&](int b) {            // the inputs of block b (a whole word is inside the row's stride: strides are multiples of 4)
-    if (b < nblk) {
-      const uint32_t d0 = sm_s + (uint32_t)((b % kGRing) * kGTile) * 4u + tile_off;
-      const uint8_t* p = src_l + 32 * b;
+    const uint32_t d0 = sm_s + (uint32_t)((b % kGRing) * kGTile) * 4u + tile_off;
+    const uint8_t* p = src_l + 32 * b;
+    if (8 * b >= 31 && 8 * b + 7 < nq) {    // warp-uniform: the whole parallelogram is inside the rows
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const bool ok = (rows_ok >> i) & 1u;
+        const uint32_t nbytes = ok ? 4u : 0u;   // 0: nothing is read, the word is zero-filled
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(d0 + (uint32_t)(4 * i * kGS) * 4u), "l"(ok ? p : j.src), "r"(nbytes) : "memory");
+        p += src_step;
+      }
+    } else if (b < nblk) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int m = 8 * b - (tr0 + 4 * i) + tw;
-        const bool ok = (band + tr0 + 4 * i < h) && m >= 0 && m < nq;
-        const uint32_t nbytes = ok ? 4u : 0u;   // 0: nothing is read, the word is zero-filled
+        const bool ok = ((rows_ok >> i) & 1u) && m >= 0 && m < nq;
+        const uint32_t nbytes = ok ? 4u : 0u;
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(d0 + (uint32_t)(4 * i * kGS) * 4u), "l"(ok ? p : j.src), "r"(nbytes) : "memory");
         p += src_step;
       }
@@ -404,8 +430,8 @@ __device__ __forceinline__ void gradient_band_tiled(const FiltJobDev& j, int bi,
     d0 = n01.x; d1 = n01.y; d2 = n23.x; d3 = n23.y;
     return __byte_perm(__byte_perm(o0, o1, 0x0040), __byte_perm(o2, o3, 0x0040), 0x5410);
   };
-  const bool full_band = band + 31 < h;
   const int tag_up = (bi - 1) << 12, tag_down = (bi + 1) << 12;
+  B2_TRACE(0);
   issue(0);
   issue(1);
   if (band > 0) wait_word(up_warp, tag_up + min(5, nblk));
@@ -421,27 +447,41 @@ __device__ __forceinline__ void gradient_band_tiled(const FiltJobDev& j, int bi,
     asm volatile("cp.async.wait_group 2;" ::: "memory");
     __syncwarp();
     const uint32_t* tin = sm + (b % kGRing) * kGTile;
-    const bool steady = full_band && q0 >= 31 && q0 + 7 < nq_full;   // warp-uniform: every lane inside its row on whole words
+    const bool steady = q0 >= 31 && q0 + 7 < nq_full;   // warp-uniform: every lane inside its row (if the row exists) on whole words
     uint32_t vin[8];
 #pragma unroll
     for (int t = 0; t < 8; ++t) vin[t] = tin[lane * kGS + t];
+    // lane 31's words are the row above the next band: they go to the ring as they are made, and the band below
+    // is told before this block's outputs start for global memory
     if (steady) {
 #pragma unroll
-      for (int t = 0; t < 8; ++t) tout[lane * kGS + t] = step(std::true_type{}, t, q0 + t - lane, vin[t]);
-      __syncwarp();
-      uint8_t* p = dst_l + 32 * b;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const uint32_t v = tout[(tr0 + 4 * i) * kGS + tw];
-        *reinterpret_cast<uint32_t*>(p) = v;
-        if (i == 7 && tr0 == 3) hand[(q0 - 31 + tw) & (kGHand - 1)] = v;   // row 31
-        p += dst_step;
+      for (int t = 0; t < 8; ++t) {
+        const uint32_t o = step(std::true_type{}, t, q0 + t - lane, vin[t]);
+        tout[lane * kGS + t] = o;
+        if (lane == 31 && has_down) hand[(q0 + t - 31) & (kGHand - 1)] = o;
       }
     } else {
 #pragma unroll
-      for (int t = 0; t < 8; ++t) tout[lane * kGS + t] = step(std::false_type{}, t, q0 + t - lane, vin[t]);
-      __syncwarp();
-      uint8_t* p = dst_l + 32 * b;
+      for (int t = 0; t < 8; ++t) {
+        const int m = q0 + t - lane;
+        const uint32_t o = step(std::false_type{}, t, m, vin[t]);
+        tout[lane * kGS + t] = o;
+        if (lane == 31 && row_ok && m >= 0 && m < nq) hand[m & (kGHand - 1)] = o;
+      }
+    }
+    __syncwarp();                        // the block's outputs are in the output tile
+    if (lane == 31) st_release_cta_shared(progress + warp, (bi << 12) + b + 1);
+    uint8_t* p = dst_l + 32 * b;
+    if (steady) {
+      uint32_t v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = tout[(tr0 + 4 * i) * kGS + tw];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if ((rows_ok >> i) & 1u) *reinterpret_cast<uint32_t*>(p) = v[i];
+        p += dst_step;
+      }
+    } else {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int m = q0 - (tr0 + 4 * i) + tw;
@@ -449,16 +489,12 @@ __device__ __forceinline__ void gradient_band_tiled(const FiltJobDev& j, int bi,
           const uint32_t v = tout[(tr0 + 4 * i) * kGS + tw];
           if (4 * m + 4 <= w) *reinterpret_cast<uint32_t*>(p) = v;
           else for (int t2 = 0; 4 * m + t2 < w; ++t2) p[t2] = (uint8_t)(v >> (8 * t2));
-          if (i == 7 && tr0 == 3) hand[m & (kGHand - 1)] = v;
         }
         p += dst_step;
       }
     }
-    __syncwarp();                        // the block's outputs are written (all lanes), the output tile is free again
-    if (lane == 31) {
-      __threadfence_block();
-      progress[warp] = (bi << 12) + b + 1;
-    }
+    __syncwarp();                        // the output tile is free again
+    B2_TRACE(1 + b);
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncwarp();

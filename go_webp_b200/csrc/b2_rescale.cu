@@ -416,6 +416,166 @@ rescale_stream_kernel(const RescaleJobDev* __restrict__ jobs, const uint32_t* __
   }
 }
 
+// ---- one-channel planes shrinking both ways by less than 4: no loops over source samples -----------
+// ncu on the streamed kernel above, 4K -> 1080p: 45 thread instructions per INPUT pixel, issue slots 57 % busy --
+// the per-sample loop over source bytes (a byte load from shared memory, an add, a compare and a branch each),
+// a 64-bit product to re-derive the previous sample's rest for every sample, the walk over the y entries for
+// every source row and an integer division per staged chunk.  With windows of at most 5 source samples
+// (ratio <= 4) a sample's window lies in two aligned words, so here
+//   * the window sum is two dot products (dp4a) of those words with 0/1 byte masks computed once per unit,
+//     the window's last sample one byte permute; the rest a sample leaves for its right neighbour
+//     (MULT_FIX(frac, fx_scale), rescaler.c.go:84-100) is chained through the thread's four columns, so it
+//     is computed once per sample, not twice;
+//   * what happens to a source row (rest only / accumulate / accumulate and export output row dy with
+//     yscale) is a two-word entry of a per-unit schedule in shared memory, built by the first 32 threads;
+//   * the rest a row leaves for the next output row (MULT_FIX_FLOOR(frow, yscale), :150-158) is the very
+//     number the export subtracts: it stays in the accumulator instead of being recomputed.
+// Same staging (16-byte cp.async, four rows per stage, two stages), same results bit for bit.
+struct RowAct { uint32_t scale; int32_t act; };   // act >= 0: accumulate, export output row dy0 + act with yscale = scale;
+                                                  // -1: accumulate; -2: only its rest counts (scale = the previous export's yscale)
+constexpr int kMaxWin = 5;
+constexpr int kMaxUnitRows = kRowsGroup * kMaxWin + 8;
+__global__ void __launch_bounds__(kThreads, 3)
+rescale_shrink_fast_kernel(const RescaleJobDev* __restrict__ jobs, const uint32_t* __restrict__ prefix, uint32_t n_jobs, uint32_t uniform,
+                           uint32_t total, const XEnt* __restrict__ xpool, const YEnt* __restrict__ ypool) {
+  extern __shared__ __align__(16) uint8_t ring[];
+  __shared__ RowAct acts[kMaxUnitRows];
+  __shared__ int info[4];   // lo_al, seg bytes, r_begin, r_end
+  const int tid = (int)threadIdx.x;
+  for (uint32_t unit = blockIdx.x; unit < total; unit += gridDim.x) {
+    uint32_t local;
+    const uint32_t img = b2_find_image(prefix, n_jobs, uniform, unit, &local);
+    const RescaleJobDev j = jobs[img];
+    const int xc0 = (int)(local % j.units_x) * kThreads * kCols, xc1 = min(xc0 + kThreads * kCols, j.dst_width);
+    const int dy0 = (int)(local / j.units_x) * kRowsGroup, ng = min(kRowsGroup, j.dst_height - dy0);
+    const XEnt* __restrict__ xt = xpool + j.xtab;
+    __syncthreads();   // the previous unit is done with acts / info / the ring
+    if (tid < 32) {    // the unit's row schedule: lane t owns output row dy0 + t
+      YEnt e = YEnt{-1, -1, 0, 0u, 0u};
+      if (tid < ng) e = ypool[j.ytab + dy0 + tid];
+      const uint32_t valid = __ballot_sync(0xffffffffu, e.last >= 0);
+      int r_begin = 0, r_end = -1;
+      if (valid) {
+        const int first = __ffs(valid) - 1, last = 31 - __clz(valid);
+        const int f_prev = __shfl_sync(0xffffffffu, e.prev_last, first);
+        const uint32_t f_scale = __shfl_sync(0xffffffffu, e.prev_yscale, first);
+        r_end = __shfl_sync(0xffffffffu, e.last, last);
+        const bool rest_row = f_prev >= 0 && f_scale != 0u;
+        r_begin = rest_row ? f_prev : f_prev + 1;
+        if (tid == first && rest_row) acts[0] = RowAct{f_scale, -2};
+        if (e.last >= 0) {
+          for (int r = e.prev_last + 1; r < e.last; ++r) acts[r - r_begin] = RowAct{0u, -1};
+          acts[e.last - r_begin] = RowAct{e.yscale, tid};
+        }
+      }
+      if (tid == 0) {
+        const XEnt e0 = xt[xc0], e1 = xt[xc1 - 1];
+        const int lo = max(e0.a - 1, 0);
+        info[0] = lo & ~15;
+        info[1] = e1.b - (lo & ~15);
+        info[2] = r_begin; info[3] = r_end;
+      }
+    }
+    __syncthreads();
+    const int lo_al = info[0], seg = info[1], r_begin = info[2], r_end = info[3];
+    if (r_end < 0) continue;   // uniform: nothing is exported in this group
+    const int x0 = xc0 + tid * kCols;
+    const bool live = x0 < j.dst_width;
+    const int n_valid = min(kCols, j.dst_width - x0);
+    const bool word_ok = n_valid == kCols && ((((uintptr_t)j.dst) | (uintptr_t)(uint32_t)j.dst_stride) & 3) == 0;
+    // per column: byte offset of the window's first word in a staged row, the 0/1 masks of the window in that word
+    // and the next, the byte permute that picks its last sample, -accum
+    uint32_t woff[kCols], m0[kCols], m1[kCols], sel[kCols], nacc[kCols];
+#pragma unroll
+    for (int k = 0; k < kCols; ++k) {
+      const XEnt e = xt[min(x0 + min(k, max(n_valid - 1, 0)), j.dst_width - 1)];   // columns past the end repeat the last one; they are not stored
+      const int rel = e.a - lo_al, s0 = rel & 3, len = e.b - e.a;
+      const uint64_t m = (0x0101010101ull & ((1ull << (8 * len)) - 1ull)) << (8 * s0);
+      woff[k] = (uint32_t)(rel & ~3);
+      m0[k] = (uint32_t)m;
+      m1[k] = (uint32_t)(m >> 32);
+      sel[k] = 0x4440u | (uint32_t)(s0 + len - 1);   // byte s0 + len - 1 of {next word : word} into byte 0 (the rest is masked off)
+      nacc[k] = (uint32_t)(-e.accum);
+    }
+    // the rest the sample left of the thread's first column hands over: its last source sample and -accum
+    int prev_rel = -1;
+    uint32_t prev_nacc = 0;
+    if (live && x0 > 0) {
+      const XEnt p = xt[x0 - 1];
+      prev_rel = p.b - 1 - lo_al;
+      prev_nacc = (uint32_t)(-p.accum);
+    }
+    const int n_chunks = (seg + 15) >> 4;
+    const int n_rows = r_end - r_begin + 1, n_stage = (n_rows + kRS - 1) / kRS;
+    auto issue = [&](int st) {   // all threads: rows r_begin + st * kRS .. of the unit into ring stage st & 1
+      const int rows_here = min(kRS, n_rows - st * kRS);
+      for (int rr = 0; rr < rows_here; ++rr) {
+        const uint8_t* g = j.src + (ptrdiff_t)(r_begin + st * kRS + rr) * j.src_stride + lo_al;
+        uint8_t* d = ring + ((st & 1) * kRS + rr) * kSegMax;
+        for (int ck = tid; ck < n_chunks; ck += kThreads) {
+          if (lo_al + 16 * ck + 16 <= j.src_stride) {   // the row's own bytes (and its padding): a whole 16-byte chunk
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(d + 16 * ck)), "l"(g + 16 * ck) : "memory");
+          } else {
+            for (int b = 0; lo_al + 16 * ck + b < j.src_stride && b < 16; ++b) d[16 * ck + b] = g[16 * ck + b];
+          }
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    uint32_t acc[kCols] = {0, 0, 0, 0};
+    issue(0);
+    for (int st = 0; st < n_stage; ++st) {
+      if (st + 1 < n_stage) {
+        issue(st + 1);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
+      __syncthreads();
+      const int rows_here = min(kRS, n_rows - st * kRS);
+      if (live) {
+        for (int rr = 0; rr < rows_here; ++rr) {
+          const uint8_t* row = ring + ((st & 1) * kRS + rr) * kSegMax;   // indexed by source x - lo_al
+          const RowAct ra = acts[st * kRS + rr];
+          uint32_t fn[kCols];
+          uint32_t carry = 0;
+          if (prev_rel >= 0) carry = mult_fix((uint32_t)row[prev_rel] * prev_nacc, j.fx_scale);
+#pragma unroll
+          for (int k = 0; k < kCols; ++k) {
+            const uint32_t w0 = *reinterpret_cast<const uint32_t*>(row + woff[k]);
+            const uint32_t w1 = *reinterpret_cast<const uint32_t*>(row + woff[k] + 4);
+            const uint32_t sum = __dp4a(w1, m1[k], __dp4a(w0, m0[k], carry));
+            const uint32_t base = __byte_perm(w0, w1, sel[k]) & 0xffu;
+            const uint32_t frac = base * nacc[k];
+            fn[k] = sum * (uint32_t)j.x_sub - frac;
+            carry = mult_fix(frac, j.fx_scale);
+          }
+          if (ra.act == -2) {                        // the row the previous unit's last export ended on: only its rest counts
+#pragma unroll
+            for (int k = 0; k < kCols; ++k) acc[k] = mult_fix_floor(fn[k], ra.scale);
+            continue;
+          }
+#pragma unroll
+          for (int k = 0; k < kCols; ++k) acc[k] += fn[k];
+          if (ra.act >= 0) {                         // ExportRowShrink, rescaler.c.go:138-163
+            uint32_t v[kCols];
+#pragma unroll
+            for (int k = 0; k < kCols; ++k) {
+              const uint32_t rest = mult_fix_floor(fn[k], ra.scale);   // yscale == 0: no rest
+              v[k] = min(mult_fix(acc[k] - rest, j.fxy_scale), 255u);
+              acc[k] = rest;
+            }
+            uint8_t* out = j.dst + (ptrdiff_t)(dy0 + ra.act) * j.dst_stride + x0;
+            if (word_ok) *reinterpret_cast<uint32_t*>(out) = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
+            else for (int k = 0; k < n_valid; ++k) out[k] = (uint8_t)v[k];
+          }
+        }
+      }
+      __syncthreads();   // the stage may be refilled
+    }
+  }
+}
+
 struct Geometry {
   int x_expand, y_expand, x_add, x_sub, y_add, y_sub;
   uint32_t fx_scale, fy_scale, fxy_scale;
@@ -550,6 +710,16 @@ extern "C" int b2_rescale_planes(b2_ctx* ctx, int stream, const b2_rescale_job* 
       if (hi - (lo & ~15) + 16 > kSegMax) { stream_flag = false; break; }
     }
   }
+  // shrinking both ways with windows of at most kMaxWin samples: the loop-free kernel
+  bool shrink_fast = stream_flag && cls == 0 && getenv("B2_RESCALE_NOFAST") == NULL;
+  for (int i = 0; i < n_jobs && shrink_fast; ++i) {
+    const RescaleJobDev& d = dj[(size_t)i];
+    if (d.fxy_scale == 0u) { shrink_fast = false; break; }
+    const XEnt* xt = xpool.data() + d.xtab;
+    for (int x = 0; x < d.dst_width && shrink_fast; ++x) if (xt[x].b - xt[x].a > kMaxWin) shrink_fast = false;
+    const YEnt* yt = ypool.data() + d.ytab;
+    for (int y = 0; y < d.dst_height && shrink_fast; ++y) if (yt[y].last >= 0 && yt[y].last - yt[y].prev_last > kMaxWin) shrink_fast = false;
+  }
   const int rows = columns ? kRowsGroup : rows_per_unit(cls < 0 ? -1 : (cls & 1));
   for (int i = 0; i < n_jobs; ++i) {
     if (columns) dj[(size_t)i].units_x = (uint32_t)((dj[(size_t)i].dst_width + kThreads * kCols - 1) / (kThreads * kCols));
@@ -590,6 +760,15 @@ extern "C" int b2_rescale_planes(b2_ctx* ctx, int stream, const b2_rescale_job* 
         (const XEnt*)(base + jb + pb), (const YEnt*)(base + jb + pb + xb));                                       \
   } while (0)
   const int stream_id = stream;
+  if (shrink_fast) {
+    B2_CUDA(ctx, cudaFuncSetAttribute(rescale_shrink_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmem));
+    rescale_shrink_fast_kernel<<<b2_grid_for(ctx, 3, tot), kThreads, kStreamSmem, ctx->streams[stream_id]>>>(
+        (const RescaleJobDev*)base, (const uint32_t*)(base + jb), (uint32_t)n_jobs, uni, (uint32_t)tot,
+        (const XEnt*)(base + jb + pb), (const YEnt*)(base + jb + pb + xb));
+    ctx->launches++;
+    B2_CUDA(ctx, cudaGetLastError());
+    return B2_OK;
+  }
   if (stream_flag) {
     switch (cls) {
       case 0: B2_RESCALE_STREAM(0, 0); break;

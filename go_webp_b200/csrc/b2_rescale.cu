@@ -434,8 +434,19 @@ rescale_stream_kernel(const RescaleJobDev* __restrict__ jobs, const uint32_t* __
 struct RowAct { uint32_t scale; int32_t act; };   // act >= 0: accumulate, export output row dy0 + act with yscale = scale;
                                                   // -1: accumulate; -2: only its rest counts (scale = the previous export's yscale)
 constexpr int kMaxWin = 5;
+#ifndef B2_RESCALE_RSF
+#define B2_RESCALE_RSF 8
+#endif
+constexpr int kRSF = B2_RESCALE_RSF;             // source rows per ring stage
+#ifndef B2_RESCALE_FT
+#define B2_RESCALE_FT 128
+#endif
+constexpr int kFT = B2_RESCALE_FT;                // threads per CTA: a unit is kFT * kCols output columns
+constexpr int kFSegMax = kFT * kCols * 4 + 64;    // source bytes per row and unit (ratio <= 4)
+constexpr int kFastSmem = 2 * kRSF * kFSegMax;
+constexpr int kFCtas = 768 / kFT;
 constexpr int kMaxUnitRows = kRowsGroup * kMaxWin + 8;
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kFT, kFCtas)
 rescale_shrink_fast_kernel(const RescaleJobDev* __restrict__ jobs, const uint32_t* __restrict__ prefix, uint32_t n_jobs, uint32_t uniform,
                            uint32_t total, const XEnt* __restrict__ xpool, const YEnt* __restrict__ ypool) {
   extern __shared__ __align__(16) uint8_t ring[];
@@ -446,7 +457,7 @@ rescale_shrink_fast_kernel(const RescaleJobDev* __restrict__ jobs, const uint32_
     uint32_t local;
     const uint32_t img = b2_find_image(prefix, n_jobs, uniform, unit, &local);
     const RescaleJobDev j = jobs[img];
-    const int xc0 = (int)(local % j.units_x) * kThreads * kCols, xc1 = min(xc0 + kThreads * kCols, j.dst_width);
+    const int xc0 = (int)(local % j.units_x) * kFT * kCols, xc1 = min(xc0 + kFT * kCols, j.dst_width);
     const int dy0 = (int)(local / j.units_x) * kRowsGroup, ng = min(kRowsGroup, j.dst_height - dy0);
     const XEnt* __restrict__ xt = xpool + j.xtab;
     __syncthreads();   // the previous unit is done with acts / info / the ring
@@ -483,45 +494,49 @@ rescale_shrink_fast_kernel(const RescaleJobDev* __restrict__ jobs, const uint32_
     const bool live = x0 < j.dst_width;
     const int n_valid = min(kCols, j.dst_width - x0);
     const bool word_ok = n_valid == kCols && ((((uintptr_t)j.dst) | (uintptr_t)(uint32_t)j.dst_stride) & 3) == 0;
-    // per column: byte offset of the window's first word in a staged row, the 0/1 masks of the window in that word
-    // and the next, the byte permute that picks its last sample, -accum
-    uint32_t woff[kCols], m0[kCols], m1[kCols], sel[kCols], nacc[kCols];
+    // per column: shared-memory address of the window's first word in stage row 0, the 0/1 masks of the window in that
+    // word and the next, the byte permute that picks its last sample, -accum
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
+    uint32_t waddr[kCols], m0[kCols], m1[kCols], sel[kCols], nacc[kCols];
 #pragma unroll
     for (int k = 0; k < kCols; ++k) {
       const XEnt e = xt[min(x0 + min(k, max(n_valid - 1, 0)), j.dst_width - 1)];   // columns past the end repeat the last one; they are not stored
       const int rel = e.a - lo_al, s0 = rel & 3, len = e.b - e.a;
       const uint64_t m = (0x0101010101ull & ((1ull << (8 * len)) - 1ull)) << (8 * s0);
-      woff[k] = (uint32_t)(rel & ~3);
+      waddr[k] = ring_s + (uint32_t)(rel & ~3);
       m0[k] = (uint32_t)m;
       m1[k] = (uint32_t)(m >> 32);
       sel[k] = 0x4440u | (uint32_t)(s0 + len - 1);   // byte s0 + len - 1 of {next word : word} into byte 0 (the rest is masked off)
       nacc[k] = (uint32_t)(-e.accum);
     }
-    // the rest the sample left of the thread's first column hands over: its last source sample and -accum
-    int prev_rel = -1;
-    uint32_t prev_nacc = 0;
+    // the rest the sample left of the thread's first column hands over: its last source sample times -accum (none: times 0)
+    uint32_t prev_addr = ring_s, prev_nacc = 0;
     if (live && x0 > 0) {
       const XEnt p = xt[x0 - 1];
-      prev_rel = p.b - 1 - lo_al;
+      prev_addr = ring_s + (uint32_t)(p.b - 1 - lo_al);
       prev_nacc = (uint32_t)(-p.accum);
     }
     const int n_chunks = (seg + 15) >> 4;
-    const int n_rows = r_end - r_begin + 1, n_stage = (n_rows + kRS - 1) / kRS;
-    auto issue = [&](int st) {   // all threads: rows r_begin + st * kRS .. of the unit into ring stage st & 1
-      const int rows_here = min(kRS, n_rows - st * kRS);
+    const int n_rows = r_end - r_begin + 1, n_stage = (n_rows + kRSF - 1) / kRSF;
+    auto issue = [&](int st) {   // all threads: rows r_begin + st * kRSF .. of the unit into ring stage st & 1
+      const int rows_here = min(kRSF, n_rows - st * kRSF);
       for (int rr = 0; rr < rows_here; ++rr) {
-        const uint8_t* g = j.src + (ptrdiff_t)(r_begin + st * kRS + rr) * j.src_stride + lo_al;
-        uint8_t* d = ring + ((st & 1) * kRS + rr) * kSegMax;
-        for (int ck = tid; ck < n_chunks; ck += kThreads) {
+        const uint8_t* g = j.src + (ptrdiff_t)(r_begin + st * kRSF + rr) * j.src_stride + lo_al;
+        const uint32_t d = ring_s + (uint32_t)(((st & 1) * kRSF + rr) * kFSegMax);
+        for (int ck = tid; ck < n_chunks; ck += kFT) {
           if (lo_al + 16 * ck + 16 <= j.src_stride) {   // the row's own bytes (and its padding): a whole 16-byte chunk
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(d + 16 * ck)), "l"(g + 16 * ck) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d + 16u * ck), "l"(g + 16 * ck) : "memory");
           } else {
-            for (int b = 0; lo_al + 16 * ck + b < j.src_stride && b < 16; ++b) d[16 * ck + b] = g[16 * ck + b];
+            uint8_t* dd = ring + ((st & 1) * kRSF + rr) * kFSegMax;
+            for (int b = 0; lo_al + 16 * ck + b < j.src_stride && b < 16; ++b) dd[16 * ck + b] = g[16 * ck + b];
           }
         }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
+    auto lds32 = [](uint32_t a) -> uint32_t { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; };
+    auto lds8 = [](uint32_t a) -> uint32_t { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; };
+    const uint32_t x_sub = (uint32_t)j.x_sub, fx_scale = j.fx_scale, fxy_scale = j.fxy_scale;
     uint32_t acc[kCols] = {0, 0, 0, 0};
     issue(0);
     for (int st = 0; st < n_stage; ++st) {
@@ -532,42 +547,42 @@ rescale_shrink_fast_kernel(const RescaleJobDev* __restrict__ jobs, const uint32_
         asm volatile("cp.async.wait_group 0;" ::: "memory");
       }
       __syncthreads();
-      const int rows_here = min(kRS, n_rows - st * kRS);
+      const int rows_here = min(kRSF, n_rows - st * kRSF);
       if (live) {
-        for (int rr = 0; rr < rows_here; ++rr) {
-          const uint8_t* row = ring + ((st & 1) * kRS + rr) * kSegMax;   // indexed by source x - lo_al
-          const RowAct ra = acts[st * kRS + rr];
+        uint32_t roff = (uint32_t)((st & 1) * kRSF * kFSegMax);
+        for (int rr = 0; rr < rows_here; ++rr, roff += kFSegMax) {
+          const RowAct ra = acts[st * kRSF + rr];
           uint32_t fn[kCols];
-          uint32_t carry = 0;
-          if (prev_rel >= 0) carry = mult_fix((uint32_t)row[prev_rel] * prev_nacc, j.fx_scale);
+          uint32_t carry = mult_fix(lds8(prev_addr + roff) * prev_nacc, fx_scale);
 #pragma unroll
           for (int k = 0; k < kCols; ++k) {
-            const uint32_t w0 = *reinterpret_cast<const uint32_t*>(row + woff[k]);
-            const uint32_t w1 = *reinterpret_cast<const uint32_t*>(row + woff[k] + 4);
+            const uint32_t w0 = lds32(waddr[k] + roff), w1 = lds32(waddr[k] + roff + 4u);
             const uint32_t sum = __dp4a(w1, m1[k], __dp4a(w0, m0[k], carry));
             const uint32_t base = __byte_perm(w0, w1, sel[k]) & 0xffu;
             const uint32_t frac = base * nacc[k];
-            fn[k] = sum * (uint32_t)j.x_sub - frac;
-            carry = mult_fix(frac, j.fx_scale);
+            fn[k] = sum * x_sub - frac;
+            carry = mult_fix(frac, fx_scale);
           }
-          if (ra.act == -2) {                        // the row the previous unit's last export ended on: only its rest counts
+          // the rest this row would leave for the next output row: used by an exporting row and by the row the
+          // previous unit's last export ended on (scale 0 otherwise: no rest)
+          const bool only_rest = ra.act == -2, exports = ra.act >= 0;
+          uint32_t rest[kCols];
 #pragma unroll
-            for (int k = 0; k < kCols; ++k) acc[k] = mult_fix_floor(fn[k], ra.scale);
-            continue;
+          for (int k = 0; k < kCols; ++k) {
+            rest[k] = mult_fix_floor(fn[k], ra.scale);
+            acc[k] = only_rest ? 0u : acc[k] + fn[k];
           }
-#pragma unroll
-          for (int k = 0; k < kCols; ++k) acc[k] += fn[k];
-          if (ra.act >= 0) {                         // ExportRowShrink, rescaler.c.go:138-163
+          if (exports) {                             // ExportRowShrink, rescaler.c.go:138-163
             uint32_t v[kCols];
 #pragma unroll
-            for (int k = 0; k < kCols; ++k) {
-              const uint32_t rest = mult_fix_floor(fn[k], ra.scale);   // yscale == 0: no rest
-              v[k] = min(mult_fix(acc[k] - rest, j.fxy_scale), 255u);
-              acc[k] = rest;
-            }
+            for (int k = 0; k < kCols; ++k) v[k] = min(mult_fix(acc[k] - rest[k], fxy_scale), 255u);
             uint8_t* out = j.dst + (ptrdiff_t)(dy0 + ra.act) * j.dst_stride + x0;
             if (word_ok) *reinterpret_cast<uint32_t*>(out) = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
             else for (int k = 0; k < n_valid; ++k) out[k] = (uint8_t)v[k];
+          }
+          if (only_rest || exports) {
+#pragma unroll
+            for (int k = 0; k < kCols; ++k) acc[k] = rest[k];
           }
         }
       }
@@ -720,9 +735,19 @@ extern "C" int b2_rescale_planes(b2_ctx* ctx, int stream, const b2_rescale_job* 
     const YEnt* yt = ypool.data() + d.ytab;
     for (int y = 0; y < d.dst_height && shrink_fast; ++y) if (yt[y].last >= 0 && yt[y].last - yt[y].prev_last > kMaxWin) shrink_fast = false;
   }
+  for (int i = 0; i < n_jobs && shrink_fast; ++i) {   // the source segment of a unit (one sample of the previous unit included)
+    const RescaleJobDev& d = dj[(size_t)i];
+    const XEnt* xt = xpool.data() + d.xtab;
+    for (int xc0 = 0; xc0 < d.dst_width && shrink_fast; xc0 += kFT * kCols) {
+      const int xc1 = (xc0 + kFT * kCols < d.dst_width) ? xc0 + kFT * kCols : d.dst_width;
+      const int lo = xt[xc0].a > 0 ? xt[xc0].a - 1 : 0;
+      if (xt[xc1 - 1].b - (lo & ~15) + 16 > kFSegMax) shrink_fast = false;
+    }
+  }
   const int rows = columns ? kRowsGroup : rows_per_unit(cls < 0 ? -1 : (cls & 1));
+  const int unit_cols = shrink_fast ? kFT * kCols : kThreads * kCols;
   for (int i = 0; i < n_jobs; ++i) {
-    if (columns) dj[(size_t)i].units_x = (uint32_t)((dj[(size_t)i].dst_width + kThreads * kCols - 1) / (kThreads * kCols));
+    if (columns) dj[(size_t)i].units_x = (uint32_t)((dj[(size_t)i].dst_width + unit_cols - 1) / unit_cols);
     const uint32_t items = dj[(size_t)i].units_x * (uint32_t)((dj[(size_t)i].dst_height + rows - 1) / rows);
     if (i == 0) uni = items; else if (items != uni) uni = 0;
     pre[(size_t)i] = (uint32_t)tot;
@@ -761,8 +786,8 @@ extern "C" int b2_rescale_planes(b2_ctx* ctx, int stream, const b2_rescale_job* 
   } while (0)
   const int stream_id = stream;
   if (shrink_fast) {
-    B2_CUDA(ctx, cudaFuncSetAttribute(rescale_shrink_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmem));
-    rescale_shrink_fast_kernel<<<b2_grid_for(ctx, 3, tot), kThreads, kStreamSmem, ctx->streams[stream_id]>>>(
+    B2_CUDA(ctx, cudaFuncSetAttribute(rescale_shrink_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmem));
+    rescale_shrink_fast_kernel<<<b2_grid_for(ctx, kFCtas, tot), kFT, kFastSmem, ctx->streams[stream_id]>>>(
         (const RescaleJobDev*)base, (const uint32_t*)(base + jb), (uint32_t)n_jobs, uni, (uint32_t)tot,
         (const XEnt*)(base + jb + pb), (const YEnt*)(base + jb + pb + xb));
     ctx->launches++;

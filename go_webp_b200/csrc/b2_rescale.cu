@@ -591,6 +591,127 @@ rescale_shrink_fast_kernel(const RescaleJobDev* __restrict__ jobs, const uint32_
   }
 }
 
+// ---- one-channel planes expanding both ways: the unit's source rows staged at once ------------------
+// Expanding, an output row needs the horizontally expanded source row `last` and the one before it
+// (ExportRowExpand, rescaler.c.go:110-136), and `last` moves by at most one row per output row: a unit of
+// 32 output rows reads at most 34 source rows of at most 512 + a few samples -- all of them go to shared
+// memory in one wave of 16-byte cp.async.  A thread's four output columns take their left / right samples
+// (ImportRowExpand :39-72) from the two aligned words that hold them (byte permutes computed once per
+// unit), the row walk is `advance while have < last`, the vertical blend is two 32 x 32 -> 64 products.
+struct ExpAct { uint32_t B; int32_t last; };      // last < 0: the row is never exported; B == 0: y_accum == 0 (J = frow)
+constexpr int kERows = 40;
+constexpr int kESeg = kFT * kCols + 64;
+constexpr int kExpSmem = kERows * kESeg;
+#ifndef B2_RESCALE_ECTAS
+#define B2_RESCALE_ECTAS 8
+#endif
+constexpr int kECtas = B2_RESCALE_ECTAS;
+__global__ void __launch_bounds__(kFT, kECtas)
+rescale_expand_fast_kernel(const RescaleJobDev* __restrict__ jobs, const uint32_t* __restrict__ prefix, uint32_t n_jobs, uint32_t uniform,
+                           uint32_t total, const XEnt* __restrict__ xpool, const YEnt* __restrict__ ypool) {
+  extern __shared__ __align__(16) uint8_t ring[];
+  __shared__ ExpAct acts[kRowsGroup];
+  __shared__ int info[4];   // lo_al, seg bytes, r_begin, r_end
+  const int tid = (int)threadIdx.x;
+  const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
+  for (uint32_t unit = blockIdx.x; unit < total; unit += gridDim.x) {
+    uint32_t local;
+    const uint32_t img = b2_find_image(prefix, n_jobs, uniform, unit, &local);
+    const RescaleJobDev j = jobs[img];
+    const int xc0 = (int)(local % j.units_x) * kFT * kCols, xc1 = min(xc0 + kFT * kCols, j.dst_width);
+    const int dy0 = (int)(local / j.units_x) * kRowsGroup, ng = min(kRowsGroup, j.dst_height - dy0);
+    const XEnt* __restrict__ xt = xpool + j.xtab;
+    __syncthreads();   // the previous unit is done with acts / info / the ring
+    if (tid < 32) {
+      YEnt e = YEnt{-1, -1, 0, 0u, 0u};
+      if (tid < ng) e = ypool[j.ytab + dy0 + tid];
+      acts[tid] = ExpAct{e.y_accum != 0 ? e.yscale : 0u, e.last};
+      const uint32_t valid = __ballot_sync(0xffffffffu, e.last >= 0);
+      if (tid == 0) { info[2] = 0; info[3] = -1; }
+      if (valid) {
+        const int first = __ffs(valid) - 1, last = 31 - __clz(valid);
+        const int l0 = __shfl_sync(0xffffffffu, e.last, first), l1 = __shfl_sync(0xffffffffu, e.last, last);
+        if (tid == 0) { info[2] = max(l0 - 1, 0); info[3] = l1; }
+      }
+      if (tid == 0) {
+        const XEnt e0 = xt[xc0], e1 = xt[xc1 - 1];
+        info[0] = e0.a & ~15;
+        info[1] = e1.b + 1 - (e0.a & ~15);
+      }
+    }
+    __syncthreads();
+    const int lo_al = info[0], seg = info[1], r_begin = info[2], r_end = info[3];
+    if (r_end < 0) continue;   // uniform: nothing is exported in this group
+    {   // every source row of the unit, 16 bytes per copy
+      const int n_chunks = (seg + 15) >> 4, n_rows = r_end - r_begin + 1;
+      for (int rr = 0; rr < n_rows; ++rr) {
+        const uint8_t* g = j.src + (ptrdiff_t)(r_begin + rr) * j.src_stride + lo_al;
+        for (int ck = tid; ck < n_chunks; ck += kFT) {
+          if (lo_al + 16 * ck + 16 <= j.src_stride) {
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(ring_s + (uint32_t)(rr * kESeg + 16 * ck)), "l"(g + 16 * ck) : "memory");
+          } else {
+            for (int b = 0; lo_al + 16 * ck + b < j.src_stride && b < 16; ++b) ring[rr * kESeg + 16 * ck + b] = g[16 * ck + b];
+          }
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    const int x0 = xc0 + tid * kCols;
+    const bool live = x0 < j.dst_width;
+    const int n_valid = min(kCols, j.dst_width - x0);
+    const bool word_ok = n_valid == kCols && ((((uintptr_t)j.dst) | (uintptr_t)(uint32_t)j.dst_stride) & 3) == 0;
+    // the thread's samples lie in the aligned word that holds its first left sample and the next one
+    const XEnt e_first = xt[min(x0, j.dst_width - 1)];
+    const uint32_t wbase = ring_s + (uint32_t)((e_first.a - lo_al) & ~3);
+    uint32_t sel_l[kCols], sel_r[kCols], c_l[kCols], c_r[kCols];
+#pragma unroll
+    for (int k = 0; k < kCols; ++k) {
+      const XEnt e = xt[min(x0 + min(k, max(n_valid - 1, 0)), j.dst_width - 1)];
+      const int base = (e_first.a - lo_al) & ~3;
+      sel_l[k] = 0x4440u | (uint32_t)(e.a - lo_al - base);   // bytes 0 .. 7 of {word 1 : word 0}
+      sel_r[k] = 0x4440u | (uint32_t)(e.b - lo_al - base);
+      // frow = right * x_add + (left - right) * accum = left * accum + right * (x_add - accum)
+      c_l[k] = (uint32_t)e.accum;
+      c_r[k] = (uint32_t)j.x_add - (uint32_t)e.accum;
+    }
+    auto lds32 = [](uint32_t a) -> uint32_t { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; };
+    const uint32_t fy_scale = j.fy_scale;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    if (!live) continue;
+    uint32_t f[kCols] = {0, 0, 0, 0}, g[kCols] = {0, 0, 0, 0};
+    int have = r_begin - 1;
+    for (int dy = 0; dy < ng; ++dy) {
+      const ExpAct a = acts[dy];
+      if (a.last < 0) continue;
+      while (have < a.last) {
+        ++have;
+        const uint32_t ra = wbase + (uint32_t)((have - r_begin) * kESeg);
+        const uint32_t w0 = lds32(ra), w1 = lds32(ra + 4u);
+#pragma unroll
+        for (int k = 0; k < kCols; ++k) {
+          g[k] = f[k];
+          const uint32_t left = __byte_perm(w0, w1, sel_l[k]) & 0xffu, right = __byte_perm(w0, w1, sel_r[k]) & 0xffu;
+          f[k] = left * c_l[k] + right * c_r[k];
+        }
+      }
+      uint32_t v[kCols];
+#pragma unroll
+      for (int k = 0; k < kCols; ++k) {
+        uint32_t J = f[k];
+        if (a.B != 0u) {                          // y_accum != 0: blend with the previous row's frow (zero above the plane)
+          const uint32_t i = (a.last > 0) ? g[k] : 0u;
+          J = (uint32_t)(((uint64_t)(uint32_t)(kOne - a.B) * f[k] + (uint64_t)a.B * i + kRounder) >> 32);
+        }
+        v[k] = min(mult_fix(J, fy_scale), 255u);
+      }
+      uint8_t* out = j.dst + (ptrdiff_t)(dy0 + dy) * j.dst_stride + x0;
+      if (word_ok) *reinterpret_cast<uint32_t*>(out) = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
+      else for (int k = 0; k < n_valid; ++k) out[k] = (uint8_t)v[k];
+    }
+  }
+}
+
 struct Geometry {
   int x_expand, y_expand, x_add, x_sub, y_add, y_sub;
   uint32_t fx_scale, fy_scale, fxy_scale;
@@ -744,8 +865,36 @@ extern "C" int b2_rescale_planes(b2_ctx* ctx, int stream, const b2_rescale_job* 
       if (xt[xc1 - 1].b - (lo & ~15) + 16 > kFSegMax) shrink_fast = false;
     }
   }
+  // expanding both ways: the kernel that stages a unit's source rows at once
+  bool expand_fast = columns && cls == 3 && getenv("B2_RESCALE_NOFAST") == NULL;
+  for (int i = 0; i < n_jobs && expand_fast; ++i) {
+    const b2_rescale_job& j = jobs[i];
+    const RescaleJobDev& d = dj[(size_t)i];
+    if ((((uintptr_t)j.src | (uintptr_t)(uint32_t)j.src_stride) & 15) != 0) { expand_fast = false; break; }
+    const XEnt* xt = xpool.data() + d.xtab;
+    for (int xc0 = 0; xc0 < d.dst_width && expand_fast; xc0 += kFT * kCols) {
+      const int xc1 = (xc0 + kFT * kCols < d.dst_width) ? xc0 + kFT * kCols : d.dst_width;
+      if (xt[xc1 - 1].b + 1 - (xt[xc0].a & ~15) + 16 > kESeg) expand_fast = false;
+      // a thread's four columns must find their samples in two aligned words
+      for (int x = xc0; x < xc1 && expand_fast; x += kCols) {
+        const int base = xt[x].a & ~3, xe = (x + kCols - 1 < d.dst_width) ? x + kCols - 1 : d.dst_width - 1;
+        if (xt[xe].b - base > 7) expand_fast = false;
+      }
+    }
+    const YEnt* yt = ypool.data() + d.ytab;
+    for (int y0 = 0; y0 < d.dst_height && expand_fast; y0 += kRowsGroup) {
+      int lo = -1, hi = -1;
+      for (int y = y0; y < y0 + kRowsGroup && y < d.dst_height; ++y) {
+        if (yt[y].last < 0) continue;
+        if (lo < 0) lo = yt[y].last;
+        if (yt[y].last < hi) expand_fast = false;     // the walk only moves forward
+        hi = yt[y].last;
+      }
+      if (hi >= 0 && hi - (lo > 0 ? lo - 1 : 0) + 1 > kERows) expand_fast = false;
+    }
+  }
   const int rows = columns ? kRowsGroup : rows_per_unit(cls < 0 ? -1 : (cls & 1));
-  const int unit_cols = shrink_fast ? kFT * kCols : kThreads * kCols;
+  const int unit_cols = (shrink_fast || expand_fast) ? kFT * kCols : kThreads * kCols;
   for (int i = 0; i < n_jobs; ++i) {
     if (columns) dj[(size_t)i].units_x = (uint32_t)((dj[(size_t)i].dst_width + unit_cols - 1) / unit_cols);
     const uint32_t items = dj[(size_t)i].units_x * (uint32_t)((dj[(size_t)i].dst_height + rows - 1) / rows);
@@ -788,6 +937,15 @@ extern "C" int b2_rescale_planes(b2_ctx* ctx, int stream, const b2_rescale_job* 
   if (shrink_fast) {
     B2_CUDA(ctx, cudaFuncSetAttribute(rescale_shrink_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmem));
     rescale_shrink_fast_kernel<<<b2_grid_for(ctx, kFCtas, tot), kFT, kFastSmem, ctx->streams[stream_id]>>>(
+        (const RescaleJobDev*)base, (const uint32_t*)(base + jb), (uint32_t)n_jobs, uni, (uint32_t)tot,
+        (const XEnt*)(base + jb + pb), (const YEnt*)(base + jb + pb + xb));
+    ctx->launches++;
+    B2_CUDA(ctx, cudaGetLastError());
+    return B2_OK;
+  }
+  if (expand_fast) {
+    B2_CUDA(ctx, cudaFuncSetAttribute(rescale_expand_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kExpSmem));
+    rescale_expand_fast_kernel<<<b2_grid_for(ctx, kECtas, tot), kFT, kExpSmem, ctx->streams[stream_id]>>>(
         (const RescaleJobDev*)base, (const uint32_t*)(base + jb), (uint32_t)n_jobs, uni, (uint32_t)tot,
         (const XEnt*)(base + jb + pb), (const YEnt*)(base + jb + pb + xb));
     ctx->launches++;

@@ -680,6 +680,12 @@ def other_kernels(ctx, peak, steps):
     row("rescale_1080p_to_4k_luma", n * W * H, 5.0, lambda: ctx._chk(ctx.lib.b2_rescale_planes(ctx.h, 0, rj, n)), {"note": "Mpx/s of input; 1 B in + 4 B out per input pixel"})
     rj2 = (_abi.RescaleJob * n)(*[_abi.RescaleJob(src.ptr + i * st * H, dst.ptr + i * st * H, W, H, st, 1280, 720, 1280, 1, 0) for i in range(n)])
     row("rescale_1080p_to_720p_luma", n * W * H, 1.0 + 1280 * 720 / (W * H), lambda: ctx._chk(ctx.lib.b2_rescale_planes(ctx.h, 0, rj2, n)), {"note": "Mpx/s of input"})
+    # the upscaled planes (dst: 128 x 4K) halved again: 4K -> 1080p, the 2 : 1 case of the shrinking kernel
+    n4 = 64
+    rj3 = (_abi.RescaleJob * n4)(*[_abi.RescaleJob(dst.ptr + i * 4 * st * H, src.ptr + i * st * H, 2 * W, 2 * H, 2 * st, W, H, st, 1, 0) for i in range(n4)])
+    ms = timed(lambda: ctx._chk(ctx.lib.b2_rescale_planes(ctx.h, 0, rj3, n4)), k5)
+    out["rescale_4k_to_1080p_luma"] = {"frames": n4, "mpixel_per_s": n4 * 4 * W * H / ms / 1e3, "bytes_per_px": 1.25, "gbs": n4 * 4 * W * H * 1.25 / ms / 1e6,
+                                       "frac": n4 * 4 * W * H * 1.25 / ms / 1e6 / peak, "note": "Mpx/s of input; 1 B in + 0.25 B out per input pixel"}
     src.free()
     dst.free()
     return out

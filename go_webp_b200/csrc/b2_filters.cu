@@ -309,6 +309,9 @@ constexpr int kGradCtasPerSm = B2_GRAD_CTAS;
 #ifndef B2_GRAD_TILED
 #define B2_GRAD_TILED 1
 #endif
+#ifndef B2_GRAD_SLEEP
+#define B2_GRAD_SLEEP 200
+#endif
 constexpr int kGS = 9;                       // tile row stride, words
 constexpr int kGTile = 32 * kGS;             // one tile: 32 rows x 8 words (+1 pad)
 constexpr int kGRing = 3;                    // input tiles in flight
@@ -346,7 +349,11 @@ __device__ __forceinline__ void gradient_band_tiled(const FiltJobDev& j, int bi,
   const bool has_down = band + 32 < h;
   auto wait_word = [&](int who, int value) {   // lane 0 polls (acquire: a plain shared load on this target), the warp follows
     if (lane == 0) {
-      while (ld_acquire_cta_shared(progress + who) < value) {}
+      while (ld_acquire_cta_shared(progress + who) < value) {
+#if B2_GRAD_SLEEP > 0
+        __nanosleep(B2_GRAD_SLEEP);
+#endif
+      }
     }
     __syncwarp();
   };
@@ -373,18 +380,16 @@ __device__ __forceinline__ void gradient_band_tiled(const FiltJobDev& j, int bi,
     if (8 * b >= 31 && 8 * b + 7 < nq) {    // warp-uniform: the whole parallelogram is inside the rows
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const bool ok = (rows_ok >> i) & 1u;
-        const uint32_t nbytes = ok ? 4u : 0u;   // 0: nothing is read, the word is zero-filled
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(d0 + (uint32_t)(4 * i * kGS) * 4u), "l"(ok ? p : j.src), "r"(nbytes) : "memory");
+        const uint32_t nbytes = ((rows_ok >> i) & 1u) ? 4u : 0u;   // 0: nothing is read (the address is not touched), the word is zero-filled
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(d0 + (uint32_t)(4 * i * kGS) * 4u), "l"(p), "r"(nbytes) : "memory");
         p += src_step;
       }
     } else if (b < nblk) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int m = 8 * b - (tr0 + 4 * i) + tw;
-        const bool ok = ((rows_ok >> i) & 1u) && m >= 0 && m < nq;
-        const uint32_t nbytes = ok ? 4u : 0u;
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(d0 + (uint32_t)(4 * i * kGS) * 4u), "l"(ok ? p : j.src), "r"(nbytes) : "memory");
+        const uint32_t nbytes = (((rows_ok >> i) & 1u) && m >= 0 && m < nq) ? 4u : 0u;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(d0 + (uint32_t)(4 * i * kGS) * 4u), "l"(p), "r"(nbytes) : "memory");
         p += src_step;
       }
     }
@@ -414,8 +419,11 @@ __device__ __forceinline__ void gradient_band_tiled(const FiltJobDev& j, int bi,
   // needs them (shuffles were grouped by ptxas at the end of the step, back on the chain).
   uint32_t* const xw = xch + 2 * (lane + 1);
   const uint32_t* const xr = xch + 2 * lane;
-  auto step = [&](auto steady_tag, int t, int m, uint32_t vin) -> uint32_t {
-    constexpr bool STEADY = decltype(steady_tag)::value;
+  // No activity test in the step: a lane that is not inside its row yet (word < 0), or whose row does not exist,
+  // reads zero-filled inputs and differences that are zero, so it produces zeros, keeps left = 0 and hands zeros
+  // down -- exactly the state the first word of its row must start from; past the end of the row the numbers are
+  // garbage that only reaches lanes which are past the end too.  Only the stores know about the edges.
+  auto step = [&](int t, uint32_t vin) -> uint32_t {
     const uint32_t o0 = (vin + (uint32_t)__viaddmin_s32_relu((int)left, d0, 255)) & 0xffu;
     const uint32_t o1 = ((vin >> 8) + (uint32_t)__viaddmin_s32_relu((int)o0, d1, 255)) & 0xffu;
     *reinterpret_cast<int2*>(xw + (2 * t) * kGXSlot) = make_int2((int)(o0 - left), (int)(o1 - o0));
@@ -426,7 +434,7 @@ __device__ __forceinline__ void gradient_band_tiled(const FiltJobDev& j, int bi,
     *reinterpret_cast<int2*>(xw + (2 * t + 1) * kGXSlot) = make_int2((int)(o2 - o1), (int)(o3 - o2));
     __syncwarp();
     const int2 n23 = *reinterpret_cast<const int2*>(xr + (2 * t + 1) * kGXSlot);
-    if (STEADY || (row_ok && m >= 0 && m < nq)) left = o3;   // bytes past the end of the row are never stored and never read again
+    left = o3;
     d0 = n01.x; d1 = n01.y; d2 = n23.x; d3 = n23.y;
     return __byte_perm(__byte_perm(o0, o1, 0x0040), __byte_perm(o2, o3, 0x0040), 0x5410);
   };
@@ -447,50 +455,36 @@ __device__ __forceinline__ void gradient_band_tiled(const FiltJobDev& j, int bi,
     asm volatile("cp.async.wait_group 2;" ::: "memory");
     __syncwarp();
     const uint32_t* tin = sm + (b % kGRing) * kGTile;
-    const bool steady = q0 >= 31 && q0 + 7 < nq_full;   // warp-uniform: every lane inside its row (if the row exists) on whole words
+    const bool steady = q0 >= 31 && q0 + 7 < nq_full;   // warp-uniform: every lane inside its row (if the row exists) on whole words: plain stores
     uint32_t vin[8];
 #pragma unroll
     for (int t = 0; t < 8; ++t) vin[t] = tin[lane * kGS + t];
     // lane 31's words are the row above the next band: they go to the ring as they are made, and the band below
     // is told before this block's outputs start for global memory
-    if (steady) {
 #pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        const uint32_t o = step(std::true_type{}, t, q0 + t - lane, vin[t]);
-        tout[lane * kGS + t] = o;
-        if (lane == 31 && has_down) hand[(q0 + t - 31) & (kGHand - 1)] = o;
-      }
-    } else {
-#pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        const int m = q0 + t - lane;
-        const uint32_t o = step(std::false_type{}, t, m, vin[t]);
-        tout[lane * kGS + t] = o;
-        if (lane == 31 && row_ok && m >= 0 && m < nq) hand[m & (kGHand - 1)] = o;
-      }
+    for (int t = 0; t < 8; ++t) {
+      const int m31 = q0 + t - 31;       // lane 31's word
+      const uint32_t o = step(t, vin[t]);
+      tout[lane * kGS + t] = o;
+      if (lane == 31 && has_down && (steady || (m31 >= 0 && m31 < nq))) hand[m31 & (kGHand - 1)] = o;
     }
     __syncwarp();                        // the block's outputs are in the output tile
     if (lane == 31) st_release_cta_shared(progress + warp, (bi << 12) + b + 1);
     uint8_t* p = dst_l + 32 * b;
-    if (steady) {
-      uint32_t v[8];
+    uint32_t v[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = tout[(tr0 + 4 * i) * kGS + tw];
+    for (int i = 0; i < 8; ++i) v[i] = tout[(tr0 + 4 * i) * kGS + tw];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if ((rows_ok >> i) & 1u) *reinterpret_cast<uint32_t*>(p) = v[i];
-        p += dst_step;
-      }
-    } else {
+    for (int i = 0; i < 8; ++i) {
+      const int m = q0 - (tr0 + 4 * i) + tw;
+      if (((rows_ok >> i) & 1u) && (steady || (m >= 0 && m < nq_full))) *reinterpret_cast<uint32_t*>(p + i * dst_step) = v[i];
+    }
+    if (!steady && (w & 3)) {            // the row's last, partial word
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int m = q0 - (tr0 + 4 * i) + tw;
-        if ((band + tr0 + 4 * i < h) && m >= 0 && m < nq) {
-          const uint32_t v = tout[(tr0 + 4 * i) * kGS + tw];
-          if (4 * m + 4 <= w) *reinterpret_cast<uint32_t*>(p) = v;
-          else for (int t2 = 0; 4 * m + t2 < w; ++t2) p[t2] = (uint8_t)(v >> (8 * t2));
-        }
-        p += dst_step;
+        if (((rows_ok >> i) & 1u) && m == nq_full)
+          for (int t2 = 0; 4 * m + t2 < w; ++t2) p[i * dst_step + t2] = (uint8_t)(v[i] >> (8 * t2));
       }
     }
     __syncwarp();                        // the output tile is free again

@@ -12,9 +12,11 @@
 //   vertical    out[y][x] = out[0][x] + sum_{1<=r<=y} in[r][x] with out[0] the horizontal
 //               prefix of row 0: a thread per 4 columns walks down the rows (whole 128-byte
 //               lines per warp), after summing row 0 up to its segment;
-//   gradient    clip(left + top - topleft) is not linear: a wavefront, one warp per image,
-//               32 rows at a time, lane r one column behind lane r-1 (top / top-left arrive
-//               by shuffle; the row above a band is read back from the output).
+//   gradient    clip(left + top - topleft) is not linear: a wavefront.  A band of 32 rows runs inside
+//               one warp (lane = row, one 4-pixel word of skew per row), the bands of a plane run as
+//               a pipeline over the 16 warps of one CTA; with 4-byte aligned rows everything moves
+//               through shared-memory tiles (gradient_band_tiled), unaligned rows keep the
+//               byte-skewed loop that reads the row above a band back from the output.
 #include <stdlib.h>
 
 #include <type_traits>
@@ -306,9 +308,6 @@ constexpr int kGradWarps = B2_GRAD_WARPS;
 #define B2_GRAD_CTAS 2
 #endif
 constexpr int kGradCtasPerSm = B2_GRAD_CTAS;
-#ifndef B2_GRAD_TILED
-#define B2_GRAD_TILED 1
-#endif
 #ifndef B2_GRAD_SLEEP
 #define B2_GRAD_SLEEP 200
 #endif
@@ -495,13 +494,13 @@ __device__ __forceinline__ void gradient_band_tiled(const FiltJobDev& j, int bi,
 }
 
 // ---- unfilter, GRADIENT: one CTA per image, its warps pipelined down the bands ------------
-// A band of 32 rows is a wavefront inside one warp (lane = row, one column of skew per row).
-// Band b needs the last row of band b-1 one column ahead of its own lane 0, so the bands of an
-// image run as a pipeline: warp w takes bands w, w + kGradWarps, ...; after every 8 steps it
-// publishes how many columns of its band's last row are final (band * 2^14 + columns, one
-// word per warp in shared memory, monotonic), and the warp below waits for the columns it is
-// about to read.  The last row itself travels through global memory (written by lane 31,
-// CTA-scope fence, flag; read back by lane 0 with volatile loads after its own fence).
+// Warp w takes bands w, w + kGradWarps, ... of its image.  Aligned rows: gradient_band_tiled above.
+// Unaligned rows (the byte-skewed loop below): a band is a wavefront inside one warp (lane = row, one
+// column of skew per row); band b needs the last row of band b-1 one column ahead of its own lane 0, so
+// after every 8 steps a warp publishes how many columns of its band's last row are final (band * 2^14 +
+// columns, one word per warp in shared memory, monotonic) and the warp below waits for the columns it is
+// about to read.  The last row itself travels through global memory (written by lane 31, CTA-scope
+// fence, flag; read back by lane 0 with volatile loads after its own fence).
 __global__ void __launch_bounds__(32 * kGradWarps)
 alpha_unfilter_gradient_kernel(const FiltJobDev* __restrict__ jobs, uint32_t n_jobs) {
   __shared__ volatile int progress[kGradWarps];
@@ -533,99 +532,8 @@ alpha_unfilter_gradient_kernel(const FiltJobDev* __restrict__ jobs, uint32_t n_j
         }
       };
       const bool words = ((((uintptr_t)j.src | (uintptr_t)j.dst) | (uint32_t)j.src_stride | (uint32_t)j.dst_stride) & 3) == 0;
-#if B2_GRAD_TILED
-      if (words) {
+      if (words) {                     // 4-byte aligned rows: the band through shared-memory tiles (above)
         gradient_band_tiled(j, bi, progress, warp, grad_sm, lane);
-        continue;
-      }
-#endif
-      if (words) {
-        // Aligned rows: the skew between rows is one 4-pixel word instead of one pixel, so that
-        // every lane is at a word boundary at the same time.  Quad step q: lane l takes word
-        // m = q - l of its row; the word above it is lane l-1's output of the previous quad step
-        // (one shuffle per 4 pixels), the pixel above-left the last byte of the word before that.
-        // Inputs and (lane 0) the row above are whole words fetched 8 quad steps ahead.
-        const int nq = (w + 3) >> 2;
-        auto in_word = [&](int m) -> uint32_t {
-          if (!row_ok || m < 0 || m >= nq) return 0u;
-          if (4 * m + 4 <= w) return __ldg((const uint32_t*)in + m);
-          uint32_t v = 0;
-          for (int t = 0; 4 * m + t < w; ++t) v |= (uint32_t)in[4 * m + t] << (8 * t);
-          return v;
-        };
-        auto above_word = [&](int m) -> uint32_t {
-          if (lane != 0 || band == 0 || m < 0 || m >= nq) return 0u;
-          if (4 * m + 4 <= w) return *((const volatile uint32_t*)above + m);
-          uint32_t v = 0;
-          for (int t = 0; 4 * m + t < w; ++t) v |= (uint32_t)*(const volatile uint8_t*)(above + 4 * m + t) << (8 * t);
-          return v;
-        };
-        uint32_t inq[8], abq[8];
-        wait_for(32);
-#pragma unroll
-        for (int t = 0; t < 8; ++t) { inq[t] = in_word(t - lane); abq[t] = above_word(t); }
-        uint32_t my_out = 0, left = 0, tl = 0;
-        // out = (in + clip(left + top - topleft)) & 0xff (GradientUnfilter_C, filters.go:150-171).  Only `left` is a
-        // serial dependence: d = top - topleft is taken off the chain and the clip is ONE add-min-relu, so a pixel
-        // costs three dependent instructions.  No special cases: row 0 has top = topleft = 0 (pred = left: the
-        // horizontal rule of the first row), column 0 starts with left = topleft = 0 (pred = clip(top) = top: the
-        // reference's prev_line[0]).
-        auto quad = [&](uint32_t vin, uint32_t topw) -> uint32_t {
-          const int t0 = (int)(topw & 0xff), t1 = (int)((topw >> 8) & 0xff), t2 = (int)((topw >> 16) & 0xff), t3 = (int)(topw >> 24);
-          const int d0 = t0 - (int)tl, d1 = t1 - t0, d2 = t2 - t1, d3 = t3 - t2;
-          const int v0 = (int)(vin & 0xff), v1 = (int)((vin >> 8) & 0xff), v2 = (int)((vin >> 16) & 0xff), v3 = (int)(vin >> 24);
-          const int o0 = (v0 + __viaddmin_s32_relu((int)left, d0, 255)) & 0xff;
-          const int o1 = (v1 + __viaddmin_s32_relu(o0, d1, 255)) & 0xff;
-          const int o2 = (v2 + __viaddmin_s32_relu(o1, d2, 255)) & 0xff;
-          const int o3 = (v3 + __viaddmin_s32_relu(o2, d3, 255)) & 0xff;
-          left = (uint32_t)o3;   // bytes past the end of the row are never stored and never read again
-          tl = topw >> 24;
-          return (uint32_t)o0 | ((uint32_t)o1 << 8) | ((uint32_t)o2 << 16) | ((uint32_t)o3 << 24);
-        };
-        const bool full_band = band + 31 < h;
-        const int nq_full = w >> 2;
-        const uint32_t* __restrict__ in_w = (const uint32_t*)in;
-        const volatile uint32_t* above_w = (const volatile uint32_t*)above;
-        uint32_t* out_w = (uint32_t*)out;
-        for (int q0 = 0; q0 < nq + 31; q0 += 8) {
-          wait_for(4 * (q0 + 16));
-          if (full_band && q0 >= 31 && q0 + 15 < nq_full) {
-            // steady state (warp-uniform): every lane is inside its row, on whole words, and so is everything
-            // it fetches 8 quad steps ahead: no predicates, one load, one shuffle, one store per 4 pixels
-#pragma unroll
-            for (int t = 0; t < 8; ++t) {
-              const int q = q0 + t, m = q - lane;
-              const uint32_t vin = inq[t];
-              uint32_t topw = __shfl_up_sync(0xffffffffu, my_out, 1);
-              if (lane == 0) topw = abq[t];
-              inq[t] = __ldg(in_w + m + 8);
-              if (lane == 0 && band > 0) abq[t] = above_w[q + 8];
-              my_out = quad(vin, topw);
-              out_w[m] = my_out;
-            }
-          } else {
-#pragma unroll
-          for (int t = 0; t < 8; ++t) {
-            const int q = q0 + t, m = q - lane;
-            const uint32_t vin = inq[t];
-            uint32_t topw = __shfl_up_sync(0xffffffffu, my_out, 1);
-            if (lane == 0) topw = abq[t];
-            inq[t] = in_word(m + 8);
-            abq[t] = above_word(q + 8);
-            if (row_ok && m >= 0 && m < nq) {
-              const uint32_t outw = quad(vin, topw);
-              if (4 * m + 4 <= w) *((uint32_t*)out + m) = outw;
-              else for (int t2 = 0; 4 * m + t2 < w; ++t2) out[4 * m + t2] = (uint8_t)(outw >> (8 * t2));
-              my_out = outw;
-            }
-          }
-          }
-          if (lane == 31) {            // words 0 .. q0 + 7 - 31 of the band's last row are written
-            const int done = min(max(4 * (q0 + 8 - 31), 0), w);
-            __threadfence_block();
-            progress[warp] = (bi << 14) + done;
-          }
-        }
         continue;
       }
       int left = 0, top_left = 0, cur_out = 0;
@@ -763,7 +671,7 @@ extern "C" int b2_alpha_unfilter(b2_ctx* ctx, int stream, const b2_alpha_filter_
     ctx->launches++;
   }
   if (counts[3] > 0) {
-    const int grad_smem = B2_GRAD_TILED ? kGradWarps * kGWarpWords * (int)sizeof(uint32_t) : 0;
+    const int grad_smem = kGradWarps * kGWarpWords * (int)sizeof(uint32_t);
     if (grad_smem > 0)   // per device: set on every call (a host-side table write)
       B2_CUDA(ctx, cudaFuncSetAttribute(alpha_unfilter_gradient_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, grad_smem));
     alpha_unfilter_gradient_kernel<<<b2_grid_for(ctx, kGradCtasPerSm, (uint64_t)n_jobs), 32 * kGradWarps, grad_smem, s>>>(dj, (uint32_t)n_jobs);

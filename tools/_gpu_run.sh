@@ -1,3 +1,3 @@
 #!/bin/bash
-timeout 600 python -m pytest tests -m gpu -q -x -k "alpha_filters or maximum_dimension_next or rescale" 2>&1 | tail -3
-python tools/quick_bench.py filters 2>&1 | grep -i "unfilter gradient"
+B2_MIXED_BREAKDOWN=1 python tools/mixed_bench.py > gpurun_out/r02_mixed_breakdown.txt 2>&1
+cat gpurun_out/r02_mixed_breakdown.txt

@@ -5,7 +5,7 @@
 // Same arithmetic as b2_import.cu (pkg/libwebp/dsp/yuv.go:124-382,
 // pkg/color/yuv/conversion.go:51-69); what changes is the instruction budget.  The
 // first version spent ~410 warp instructions per 4x2-pixel strip and was issue
-// bound at 48% of HBM peak (profiles/r01_*).  Here:
+// bound at 48% of HBM peak (profiles/r01a_ncu_full_first_kernels.csv).  Here:
 //   * a warp walks one whole row pair (the reference's own unit of work,
 //     yuv.go:316), so image lookup, descriptor loads and 64-bit address math are
 //     paid once per row pair, and the next strip is prefetched while the current

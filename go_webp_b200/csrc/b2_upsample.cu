@@ -808,7 +808,7 @@ extern "C" int b2_yuv420a_to_rgba_fancy(b2_ctx* ctx, int stream, const b2_upsamp
   const int grid = b2_grid_for(ctx, 8, (total + kWarps - 1) / kWarps);
   const uint32_t tot = (uint32_t)total;
   if (tuned && staged) {
-    // Persistent CTAs per SM (of the 6 that fit).  Measured (profiles/r01d_upsample_grid_sweep.txt):
+    // Persistent CTAs per SM (of the 6 that fit).  Measured (profiles/r01d_grid_sweeps.md):
     // 4 per SM is best for 4K rows (0.85 of the measured HBM peak vs 0.82 at 6), 5 per SM for
     // 1080p rows (0.785 vs 0.755); the address window the warps sweep together matters
     // more than the extra latency hiding.

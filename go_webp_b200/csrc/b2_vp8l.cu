@@ -464,7 +464,7 @@ int run_flat(b2_ctx* ctx, int stream, const b2_argb_job* jobs, int n_jobs) {
   Prepared p;
   const int st = prepare(ctx, stream, jobs, n_jobs, needs_codes<OP>() ? KIND_FLAT_CODES : KIND_FLAT, &p);
   if (st != B2_OK) return st;
-  // Persistent CTAs per SM.  Measured on 4096^2 batches (profiles/r01d_flat_grid_sweep.txt):
+  // Persistent CTAs per SM.  Measured on 4096^2 batches (profiles/r01d_grid_sweeps.md):
   // the pure copies (add/sub-green) peak at 4 per SM (0.95 of the measured HBM peak vs
   // 0.88 at 3, 5 or 6), the cross-colour kernels need the extra warps of 6 per SM.
   const int grid_ctas = needs_codes<OP>() ? B2_FLAT_CTAS : 4;
@@ -518,7 +518,7 @@ extern "C" int b2_vp8l_color_index_inverse(b2_ctx* ctx, int stream, const b2_arg
     cudaStream_t s = ctx->streams[stream];
     if (rows) {
       // 3 persistent CTAs per SM measured best for the sub-byte depths (0.85-0.92 of the
-      // measured HBM peak vs 0.80-0.84 at 8; profiles/r01d_index_grid_sweep.txt)
+      // measured HBM peak vs 0.80-0.84 at 8; profiles/r01d_grid_sweeps.md)
       const int rgrid = b2_grid_for(ctx, 3, (p.total + kWarps - 1) / kWarps);
       switch (bits) {
         case 0: color_index_rows_kernel<0><<<rgrid, kThreads, 0, s>>>(p.jobs, p.prefix, cnt, p.uniform, p.total); break;

@@ -1037,6 +1037,19 @@ def test_rescaler(gpu, golden_dir):
             o = R.RescalePlane(src, dw, dh, ch)
             e = oracle.rescale_plane(src, dw, dh, ch)
             assert (o == e).all(), (ch, w, h, dw, dh, np.argwhere(o != e)[:3])
+    # one-channel planes around the limits of the loop-free kernels: shrink ratios up to and past 4 (windows of 4, 5,
+    # 6 samples: the last falls back), several 512-column units with a ragged last one, heights off the 32-row
+    # groups, near-identity ratios, expansion over several units, a batch of several geometries of one direction
+    shrink = [(1000, 64, 250, 16), (1001, 70, 250, 19), (1100, 33, 250, 31), (3000, 100, 1500, 50),
+              (2051, 67, 1027, 33), (640, 640, 639, 161), (1536, 45, 1535, 44)]
+    wide = [(1300, 40, 250, 9), (1000, 64, 250, 16), (900, 600, 300, 100)]    # a 6-sample window sends the whole batch to the streamed kernel
+    expand = [(700, 300, 1500, 650), (300, 200, 301, 201), (513, 40, 2049, 161), (64, 9, 1100, 70)]
+    for group in (shrink, wide, expand):
+        planes = [rng.integers(0, 256, (h, w), dtype=np.uint8) for (w, h, dw, dh) in group]
+        outs = R.RescalePlanesBatch(planes, [(dw, dh) for (w, h, dw, dh) in group])
+        for (w, h, dw, dh), src, o in zip(group, planes, outs):
+            e = oracle.rescale_plane(src, dw, dh)
+            assert (o == e).all(), (w, h, dw, dh, np.argwhere(o != e)[:3])
     y = rng.integers(0, 256, (90, 160), dtype=np.uint8)
     u = rng.integers(0, 256, (45, 80), dtype=np.uint8)
     v = rng.integers(0, 256, (45, 80), dtype=np.uint8)

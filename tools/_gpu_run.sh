@@ -1,3 +1,2 @@
 #!/bin/bash
-B2_MIXED_BREAKDOWN=1 python tools/mixed_bench.py > gpurun_out/r02_mixed_breakdown.txt 2>&1
-cat gpurun_out/r02_mixed_breakdown.txt
+timeout 600 python -m pytest tests -m gpu -q -x -k "rescale" 2>&1 | tail -8

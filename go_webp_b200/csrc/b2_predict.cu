@@ -49,6 +49,7 @@ struct PredJobDev {
   uint32_t ctiles_per_row;
   uint32_t chain;          // CH_* bits
   uint32_t pad;
+  unsigned long long* msg; // one row of `width` 8-byte messages per band: {column + 1, pixel} of the band's last row (fast bands)
 };
 enum { CH_CC = 1, CH_GREEN = 2, CH_RGBA = 4, CH_ARGB = 8 };
 
@@ -507,7 +508,23 @@ __device__ __forceinline__ void inverse_band(const PredJobDev* __restrict__ jp, 
 // boundary (tiles are at least 8 wide: at most one boundary per group).  Needs the vector preconditions
 // (width % 4 == 0, 16-byte aligned images) and tiles of 8 pixels or more; other jobs take inverse_band.
 constexpr int kFastRing = 4 * 8;        // input ring: 4 groups of 8 residuals per lane
+#ifndef B2_PRED_FETCH_AT
+#define B2_PRED_FETCH_AT 4
+#endif
+constexpr int kFetchAt = B2_PRED_FETCH_AT;   // step of a group at which the next group's chunk of the row above is fetched
 constexpr int kFastLaneWords = 34;      // 8-byte aligned slots; 34 l mod 32 = 2 l: two lanes per bank at most
+// The last row of a band goes to the band below as 8-byte messages {pixel, column + 1}: a naturally aligned 64-bit
+// access is single-copy atomic, so the tag says that the pixel next to it is the final one -- no fence on the
+// writing side (a st.release costs the band a MEMBAR.GPU: every prior store acknowledged by L2), no acquire on
+// the reading side, and the row is published pixel by pixel instead of every 16 columns.
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
   uint32_t v;
   asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -521,10 +538,9 @@ __device__ __forceinline__ void inverse_band_fast(const PredJobDev* __restrict__
   const bool row_ok = row < h;
   const uint32_t* __restrict__ in_row = jp->src + (size_t)row * w;
   uint32_t* __restrict__ out_row = jp->dst + (size_t)row * w;
-  const uint32_t* up_row = jp->dst + (size_t)(i * 32 - 1) * w;      // last row of the band above (i > 0)
   const uint32_t* __restrict__ mode_row = jp->modes + (size_t)(row >> bits) * jp->tiles_per_row;
-  const uint32_t* flag_up = flags + jp->flag_off + i - 1;
-  uint32_t* flag_me = flags + jp->flag_off + i;
+  unsigned long long* const msg_me = jp->msg + (size_t)i * w;                        // this band's last row, for the band below
+  const unsigned long long* const msg_up = jp->msg + (size_t)(i > 0 ? i - 1 : 0) * w;   // the last row of the band above (i > 0)
   const bool publish = (lane == 31) && (i + 1 < jp->bands);
   const uint32_t chain = jp->chain;                                  // warp-uniform
   const bool cc = (chain & CH_CC) != 0, finish = (chain & ~(uint32_t)CH_CC) != 0;
@@ -547,24 +563,25 @@ __device__ __forceinline__ void inverse_band_fast(const PredJobDev* __restrict__
   const bool row0 = (row == 0);
   const bool full_band = (i > 0) && ((int)i * 32 + 31 < h);
   const int k_end = w + 62;
-  // The row above (lane 0's TR / T / TL source), 16 columns at a time, one chunk AHEAD: lane q of upc holds
-  // column chunk_first + q of the chunk in use, upc_nx the chunk after it.  The progress word of the band
-  // above is read with relaxed loads (no L1 invalidation per poll, which an acquire load costs the whole SM);
-  // the row itself is read with L2 loads issued only after the word said the columns are final, and the band
-  // above released them (membar + store) before it raised the word.
-  uint32_t avail = 0, probe = 0, upc = 0, upc_nx = 0;
-  auto fetch_chunk = [&](int first_col) -> uint32_t {   // columns first_col .. + 15 of the row above (uniform call)
+  // The row above (lane 0's TR / T / TL source), 8 columns at a time: group g uses columns 8g + 1 .. 8g + 8 (lane q
+  // of upc holds column 8g + 1 + q), the next group's chunk is fetched kFetchAt steps into the group -- a few steps
+  // cover an L2 round trip -- into upc_nx.  A chunk is 8 messages read by 8 lanes with relaxed 64-bit loads,
+  // repeated until every tag says its pixel is the final one.  The messages carry the predictor's own output,
+  // before add-green and the byte order, so nothing is undone here.  The band below thus starts
+  // 62 (the skew) + 8 + (8 - kFetchAt) columns behind, not 62 + 16 + 8 + the publication period.
+  uint32_t upc = 0, upc_nx = 0;
+  auto fetch_chunk = [&](int first_col) -> uint32_t {   // columns first_col .. + 7 of the row above (uniform call)
     if (i == 0 || first_col >= w) return 0u;
-    const uint32_t need_cols = (uint32_t)min(w, first_col + kChunk);
-    avail = max(avail, probe);
-    while (avail < need_cols) {
-      avail = ld_relaxed_u32(flag_up);
-      if (avail < need_cols) __nanosleep(32);
-    }
     const int col = first_col + lane;
-    uint32_t v = (lane < kChunk && col < w) ? __ldcg(up_row + col) : 0u;
-    if (finish) v = chain_back(chain, v);
-    return v;
+    const bool want = lane < 8 && col >= 0 && col < w;
+    unsigned long long m = 0ull;
+    for (;;) {
+      if (want) m = ld_relaxed_u64(msg_up + col);
+      const bool ok = !want || (uint32_t)(m >> 32) == (uint32_t)(col + 1);
+      if (__all_sync(0xffffffffu, ok)) break;
+      __nanosleep(32);
+    }
+    return want ? (uint32_t)m : 0u;
   };
   uint32_t left = 0, tl = 0, t = 0, first_px = 0;
   // mode / code of the current column, and of the tile that holds the LAST column of the current group
@@ -596,17 +613,13 @@ __device__ __forceinline__ void inverse_band_fast(const PredJobDev* __restrict__
       asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(res[4]), "=r"(res[5]) : "r"(src + 16) : "memory");
       asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(res[6]), "=r"(res[7]) : "r"(src + 24) : "memory");
     }
-    if (!(k0 & 8) && i > 0) probe = ld_relaxed_u32(flag_up);   // consumed at the end of this group, 7 steps from here
     uint32_t outv[8];
 #pragma unroll
     for (int s = 0; s < 8; ++s) {
       const int k = k0 + s, c = c0 + s;
-      if (s == 7) {               // uniform
-        if (k0 & 8) upc = upc_nx;                          // (k + 1) % 16 == 0: columns k + 1 .. k + 16 of the row above come into use
-        else upc_nx = fetch_chunk(k + 1 + kChunk / 2);     // half a chunk before that: fetch them (8 steps of latency hiding)
-      }
+      if (s == kFetchAt) upc_nx = fetch_chunk(k0 + 9);     // uniform: the next group's columns
       uint32_t tr = __shfl_up_sync(0xffffffffu, left, 1);
-      const uint32_t u = __shfl_sync(0xffffffffu, upc, (k + 1) & (kChunk - 1));
+      const uint32_t u = __shfl_sync(0xffffffffu, upc, s);
       tr = (lane == 0) ? u : tr;
       mode = ((c & tile_mask) == 0) ? mode_e : mode;     // a new tile starts at this column (at most once per group)
       uint32_t r = res[s];
@@ -623,6 +636,7 @@ __device__ __forceinline__ void inverse_band_fast(const PredJobDev* __restrict__
       const uint32_t o = add_pixels(r, pred);
       outv[s] = finish ? chain_out(chain, o) : o;
       const bool active = STEADY || (row_ok && (unsigned)c < (unsigned)w);
+      if (publish && active) st_relaxed_u64(msg_me + c, ((unsigned long long)(uint32_t)(c + 1) << 32) | o);
       if (!STEADY) first_px = (active && c == 0) ? o : first_px;
       left = active ? o : left;
       tl = t;
@@ -633,14 +647,12 @@ __device__ __forceinline__ void inverse_band_fast(const PredJobDev* __restrict__
       const int col = c0 + 2 * p;
       if (STEADY || (row_ok && (unsigned)col < (unsigned)w)) b2_stg_stream_v2(out_row + col, make_uint2(outv[2 * p], outv[2 * p + 1]));
     }
-    const int done = c0 + 8;                             // columns of this lane's row that are final
-    // lane 31's columns end on 8 g - 54: publish every kPublish columns, and the end of the row
-    if (publish && done > 0 && (((g + 1) & (kPublish / 8 - 1)) == 0 || done >= w)) st_release_u32(flag_me, (uint32_t)min(done, w));
     mode_e = (mode_n_raw >> 8) & 0xf;
     code_e = code_n;
+    upc = upc_nx;
   };
 
-  upc_nx = fetch_chunk(0);   // columns 0 .. 15: switched in at k = -1, the last step of group -1 (the loop's own fetches start at k = 7)
+  upc = fetch_chunk(-7);     // group -1: column 0 is read at k = -1
 #pragma unroll 1
   for (int g = -3; 8 * g < k_end; ++g) {
     issue(g + 2);
@@ -706,6 +718,19 @@ int prepare_pred(b2_ctx* ctx, int stream, const PredSrc* jobs, int n_jobs, bool 
     if (nb > max_bands) max_bands = nb;
   }
   if (with_wave && (n_jobs > (1 << 22) || max_bands > 1024)) return B2_ERR_INVALID_CONFIG;  // order entry = image << 10 | band
+  // message rows of the inverse wavefront (one row of `width` 8-byte messages per band), cleared on every launch:
+  // a tag left by an earlier launch must not read as "final"
+  unsigned long long* msg_base = NULL;
+  if (with_wave) {
+    size_t entries = 0;
+    for (int i = 0; i < n_jobs; ++i) entries += (size_t)((jobs[i].height + 31) / 32) * (size_t)jobs[i].width;
+    void* sp = NULL;
+    const int st = b2_stream_scratch(ctx, stream, entries * sizeof(unsigned long long), &sp);
+    if (st != B2_OK) return st;
+    msg_base = (unsigned long long*)sp;
+    cudaError_t e = cudaMemsetAsync(sp, 0, entries * sizeof(unsigned long long), ctx->streams[stream]);
+    if (e != cudaSuccess) return b2_fail_cuda(ctx, e, "cudaMemsetAsync(message rows)");
+  }
   const size_t jb = (sizeof(PredJobDev) * (size_t)n_jobs + 15) & ~(size_t)15;
   const size_t pb = (sizeof(uint32_t) * ((size_t)n_jobs + 1) + 15) & ~(size_t)15;
   const size_t ob = with_wave ? (sizeof(uint32_t) * (size_t)bands_all + 15) & ~(size_t)15 : 0;
@@ -718,6 +743,7 @@ int prepare_pred(b2_ctx* ctx, int stream, const PredSrc* jobs, int n_jobs, bool 
   uint32_t* ord = (uint32_t*)(host + jb + pb);
   uint64_t tot = 0;
   uint32_t uni = 0, flag_off = 0;
+  size_t msg_off = 0;
   for (int i = 0; i < n_jobs; ++i) {
     const PredSrc& j = jobs[i];
     PredJobDev& d = dj[i];
@@ -729,6 +755,8 @@ int prepare_pred(b2_ctx* ctx, int stream, const PredSrc* jobs, int n_jobs, bool 
     d.bands = (uint32_t)((j.height + 31) / 32);
     d.flag_off = flag_off;
     flag_off += d.bands;
+    d.msg = msg_base ? msg_base + msg_off : NULL;
+    msg_off += (size_t)d.bands * (size_t)j.width;
     const uint32_t items = (uint32_t)((j.width + kFwdBlock - 1) / kFwdBlock) * (uint32_t)((j.height + kFwdRows - 1) / kFwdRows);
     if (i == 0) uni = items; else if (items != uni) uni = 0;
     pre[i] = (uint32_t)tot;

@@ -18,11 +18,15 @@
 //     rest are its own history), and all 32 lanes are busy on every step;
 //   * ONE persistent launch: warps draw bands from a ticket counter in band-major order
 //     (band 0 of every image, then band 1, ...).  Lane 0's row above is the last row of
-//     the band above, read back from the output image behind that band's progress word
-//     (st.release.gpu every kPublish columns, ld.acquire.gpu poll).  Liveness does not
-//     rest on stream order or on residency: a band only ever waits on the band above
-//     it, which holds a LOWER ticket, so it was drawn earlier and is running (or done);
-//     by induction the lowest unfinished ticket never waits on an undrawn band.
+//     the band above.  The fast bands (aligned images, tiles of 8 pixels or more) hand it
+//     over as 8-byte messages {pixel, column + 1}, one relaxed 64-bit store per pixel and
+//     relaxed 64-bit loads on the other side: the tag says the pixel next to it is final,
+//     so there is no fence at all.  The general bands read it back from the output image
+//     behind the band's progress word (st.release.gpu every kPublish columns,
+//     ld.acquire.gpu poll).  Liveness does not rest on stream order or on residency: a
+//     band only ever waits on the band above it, which holds a LOWER ticket, so it was
+//     drawn earlier and is running (or done); by induction the lowest unfinished ticket
+//     never waits on an undrawn band.
 //   * the fused variants (b2_vp8l_predictor_inverse_chain) apply the cross-colour
 //     inverse to the residual before the prediction is added and add-green to the
 //     pixel on its way out; the neighbours a lane keeps are the un-add-greened pixels.

@@ -246,8 +246,10 @@ int b2_vp8l_apply_palette(b2_ctx* ctx, int stream, const b2_palette_job* jobs, i
  * Inverse: PredictorInverseTransform_C + PredictorAdd0..13_C over whole images
  * (pkg/libwebp/dsp/lossless.go:31-333): src = residuals, dst = pixels.  Runs as ONE
  * persistent launch: warps take 32-row bands from a ticket counter and walk them as a
- * skewed wavefront, waiting on the band above through a progress word (see b2_predict.cu;
- * a waited-on band always holds a lower ticket, so it is running: no deadlock).
+ * skewed wavefront, waiting on the band above (per-pixel tagged messages, or a progress word
+ * for unaligned images / 4-pixel tiles: see b2_predict.cu; a waited-on band always holds a
+ * lower ticket, so it is running: no deadlock).  Uses the stream's scratch: 8 bytes per pixel
+ * of every 32nd row, cleared by the call.
  * Forward: PredictorSub0..13_C with the given modes (lossless_enc.go:339-557, driven as
  * pkg/libwebp/enc/predictor_enc.go:666-712): src = pixels, dst = residuals. */
 int b2_vp8l_predictor_inverse(b2_ctx* ctx, int stream, const b2_argb_job* jobs, int n_jobs);

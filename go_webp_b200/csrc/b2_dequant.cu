@@ -107,26 +107,42 @@ dq_levels_kernel(const DqJobDev* __restrict__ jobs, DqStats* __restrict__ stats)
   if (lane == 0 && bits) atomicOr(&stats[blockIdx.y].used[warp], bits);
 }
 
-__global__ void dq_finalize_kernel(DqStats* __restrict__ stats, uint32_t n_jobs) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_jobs) return;
-  DqStats& s = stats[i];
-  int mn = 255, mx = 0, n = 0, last = -1, dist = 255;
-#pragma unroll
-  for (int word = 0; word < 8; ++word) {
-    uint32_t bits = s.used[word];
-    while (bits) {
-      const int v = word * 32 + __ffs(bits) - 1;
-      bits &= bits - 1;
-      ++n;
-      if (v < mn) mn = v;
-      mx = v;
-      if (last >= 0 && v - last < dist) dist = v - last;
-      last = v;
-    }
+// CountLevels (:186-219) from the used-level bitmap, by the whole CTA: thread t owns level t; a used level looks
+// for the used level below it (its own word first, then the words below), the smallest gap is reduced over the CTA.
+__device__ __forceinline__ void count_levels(const uint32_t* __restrict__ used, int* sh /*[4 + 2 * kWarps]*/) {
+  const int t = threadIdx.x, word = t >> 5, bit = t & 31;
+  const uint32_t mine = __ldg(used + word);
+  int gap = 255;
+  const bool is_used = (mine >> bit) & 1u;
+  if (is_used) {
+    uint32_t below = mine & ((1u << bit) - 1u);
+    int wd = word;
+    while (below == 0u && wd > 0) below = __ldg(used + --wd);
+    if (below != 0u) gap = t - (wd * 32 + 31 - __clz(below));
   }
-  if (mx - mn < dist) dist = mx - mn;
-  s.min = mn; s.max = mx; s.min_dist = dist; s.num_levels = n;
+  const uint32_t ballot = __ballot_sync(0xffffffffu, is_used);
+  for (int o = 16; o > 0; o >>= 1) gap = min(gap, __shfl_xor_sync(0xffffffffu, gap, o));
+  if (bit == 0) {
+    sh[4 + word] = gap;
+    sh[4 + kWarps + word] = (int)ballot;
+  }
+  __syncthreads();
+  if (t == 0) {
+    int mn = 255, mx = 0, n = 0, dist = 255;
+    for (int k = 0; k < kWarps; ++k) {
+      const uint32_t bts = (uint32_t)sh[4 + kWarps + k];
+      if (bts) {
+        if (n == 0) mn = k * 32 + __ffs(bts) - 1;
+        mx = k * 32 + 31 - __clz(bts);
+        n += __popc(bts);
+      }
+      dist = min(dist, sh[4 + k]);
+    }
+    if (n == 0) { mn = 255; mx = 0; }
+    if (mx - mn < dist) dist = mx - mn;
+    sh[0] = mn; sh[1] = mx; sh[2] = dist; sh[3] = n;
+  }
+  __syncthreads();
 }
 
 template <int DFIX>
@@ -135,10 +151,12 @@ dq_smooth_kernel(const DqJobDev* __restrict__ jobs, const DqStats* __restrict__ 
   __shared__ int16_t lut[2 * kLutSize + 1];
   const DqJobDev j = jobs[blockIdx.y];
   if (blockIdx.x * kWarps >= j.units) return;
-  const int vmin = stats[blockIdx.y].min, vmax = stats[blockIdx.y].max;
-  const bool active = j.radius > 0 && stats[blockIdx.y].num_levels > 2;
+  __shared__ int lv[4 + 2 * kWarps];   // min, max, min distance, number of levels; scratch
+  count_levels(stats[blockIdx.y].used, lv);
+  const int vmin = lv[0], vmax = lv[1];
+  const bool active = j.radius > 0 && lv[3] > 2;
   if (active) {   // InitCorrectionLUT
-    const int threshold1 = stats[blockIdx.y].min_dist << kLfix;
+    const int threshold1 = lv[2] << kLfix;
     const int threshold2 = (3 * threshold1) >> 2;
     const int max_threshold = threshold2 << DFIX;
     const int delta = threshold1 - threshold2;
@@ -299,8 +317,7 @@ extern "C" int b2_alpha_dequantize_levels(b2_ctx* ctx, int stream, const b2_alph
     if (gx > cap) gx = cap;
     if (gx < 1) gx = 1;
     dq_levels_kernel<<<dim3(gx, (unsigned)n_jobs), kThreads, 0, s>>>(dj, ds);
-    dq_finalize_kernel<<<(n_jobs + 63) / 64, 64, 0, s>>>(ds, (uint32_t)n_jobs);
-    ctx->launches += 2;
+    ctx->launches += 1;
   }
   const dim3 grid((max_units + kWarps - 1) / kWarps, (unsigned)n_jobs);
   if (ordered_dither) dq_smooth_kernel<4><<<grid, kThreads, 0, s>>>(dj, ds);

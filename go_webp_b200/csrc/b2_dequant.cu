@@ -16,8 +16,8 @@
 // then ApplyFilter (:139-157) through the correction table (InitCorrectionLUT :162-184) built
 // from the smallest distance between two used levels (CountLevels :186-219).
 //
-// Three launches: used-level bitmap per plane (256 bits, atomicOr), one thread per plane
-// turning it into min / max / min distance / count, then the smoother: a warp owns 120
+// Two launches: used-level bitmap per plane (256 bits, atomicOr), then the smoother, whose CTAs
+// first turn the bitmap into min / max / min distance / count (count_levels): a warp owns 120
 // output columns x 32 rows, each lane keeps the vertical sums of its 4 columns in registers
 // (sliding down the band), neighbours' sums come by shuffle (r <= 4: one lane each side, the
 // two outer lanes of a warp are halo only), the correction table sits in shared memory.

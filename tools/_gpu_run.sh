@@ -1,2 +1,4 @@
 #!/bin/bash
-B2_FRAMES=32 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active,launch__registers_per_thread --clock-control none -k regex:dq_ -c 4 python tools/quick_bench.py dequant 2>&1 | grep -E "dq_.*kernel|gpu__time|inst_executed|issue_active|warps_active|registers" | sed -E 's/\(const.*//' | paste - - - - - - | head -6
+timeout 600 python -m pytest tests -m gpu -q -x -k "rescale" 2>&1 | tail -3
+python tools/quick_bench.py rescale 2>&1 | tail -3
+for v in rsf8 rsf4; do echo $v; B2_LIB=go_webp_b200/lib/variants/libb2webp_$v.so python tools/quick_bench.py rescale 2>&1 | tail -3; done

@@ -948,6 +948,12 @@ def test_alpha_filters(gpu, golden_dir):
         un = F.AlphaUnfilterBatch(planes, [3] * len(planes), row_align=row_align)
         for p, o in zip(planes, un):
             assert (o == oracle.alpha_unfilter(p, 3)).all(), (p.shape, row_align)
+    # more gradient planes than resident CTAs (2 per SM): a CTA goes through several planes, its shared progress
+    # words, ring and tiles are reused from plane to plane
+    planes = [rng.integers(0, 256, (33 + (i % 5) * 16, 60 + (i % 7) * 8), dtype=np.uint8) for i in range(700)]
+    un = F.AlphaUnfilterBatch(planes, [3] * len(planes))
+    for i, (p, o) in enumerate(zip(planes, un)):
+        assert (o == oracle.alpha_unfilter(p, 3)).all(), (i, p.shape)
     data = rng.integers(0, 256, 40 * 7, dtype=np.uint8)
     out = np.zeros_like(data)
     F.GradientFilter_C(data, 33, 7, 40, out)

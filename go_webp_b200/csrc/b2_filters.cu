@@ -58,7 +58,17 @@ __device__ __forceinline__ uint32_t filter_pred4(int filter, bool top_row, uint3
   return pred;
 }
 
-__global__ void __launch_bounds__(kThreads, 8)
+// unit = (group of kFwdRows rows, 512-pixel segment): the rows of a group are fetched together (one 128-bit load per
+// lane and row when the rows are 16-byte aligned), a row's upper neighbour is the previous row's registers, and
+// the job table, the division by the segment count and the edge tests are paid once per group, not per row.
+#ifndef B2_FWD_ROWS
+#define B2_FWD_ROWS 4
+#endif
+#ifndef B2_FWDF_CTAS
+#define B2_FWDF_CTAS 4
+#endif
+constexpr int kFwdRows = B2_FWD_ROWS;
+__global__ void __launch_bounds__(kThreads, B2_FWDF_CTAS)
 alpha_filter_kernel(const FiltJobDev* __restrict__ jobs, const uint32_t* __restrict__ prefix, uint32_t n_jobs,
                     uint32_t uniform, uint32_t total) {
   const int lane = threadIdx.x & 31;
@@ -67,51 +77,72 @@ alpha_filter_kernel(const FiltJobDev* __restrict__ jobs, const uint32_t* __restr
     const uint32_t img = b2_find_image(prefix, n_jobs, uniform, unit, &local);
     const FiltJobDev j = jobs[img];
     const uint32_t fwd_units = (uint32_t)((j.width + kFwdUnit - 1) / kFwdUnit);
-    const int y = (int)(local / fwd_units), x0 = (int)(local % fwd_units) * kFwdUnit + lane * kFwdLane;
-    const uint8_t* cur = j.src + (ptrdiff_t)y * j.src_stride;
-    const uint8_t* up = cur - j.src_stride;
-    uint8_t* dst = j.dst + (ptrdiff_t)y * j.dst_stride;
+    const int y0 = (int)(local / fwd_units) * kFwdRows, x0 = (int)(local % fwd_units) * kFwdUnit + lane * kFwdLane;
+    const int ny = min(kFwdRows, j.height - y0);
     // whole words when the rows are 4-byte aligned: the left / upper-left neighbours of a
     // lane's first pixel are the last bytes of the previous lane's words (one shuffle each)
-    const bool aligned = (((((uintptr_t)j.src) | (uintptr_t)j.dst) | (uint32_t)j.src_stride | (uint32_t)j.dst_stride) & 3) == 0;
+    const uintptr_t bits = ((uintptr_t)j.src | (uintptr_t)j.dst) | (uint32_t)j.src_stride | (uint32_t)j.dst_stride;
+    const bool aligned = (bits & 3) == 0, al16 = (bits & 15) == 0;
     const bool vec = aligned && x0 + kFwdLane <= j.width;
-    const bool use_up = y > 0 && j.filter >= 2;
-    uint32_t c[4] = {0, 0, 0, 0}, t[4] = {0, 0, 0, 0};
-    if (vec) {
+    // the group's rows and the row above it (vertical / gradient), all requested before the first is used
+    uint32_t c[kFwdRows + 1][4];
+    auto row_words = [&](int y, uint32_t (&w)[4]) {
+      w[0] = w[1] = w[2] = w[3] = 0u;
+      if (!vec || y < 0 || y >= j.height) return;
+      const uint8_t* p = j.src + (ptrdiff_t)y * j.src_stride + x0;
+      if (al16) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
+        w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w;
+      } else {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) c[q] = __ldg((const uint32_t*)(cur + x0) + q);
-      if (use_up) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) t[q] = __ldg((const uint32_t*)(up + x0) + q);
+        for (int q = 0; q < 4; ++q) w[q] = __ldg((const uint32_t*)p + q);
       }
-    }
-    uint32_t left = __shfl_up_sync(0xffffffffu, c[3] >> 24, 1), up_left = __shfl_up_sync(0xffffffffu, t[3] >> 24, 1);
-    if (vec) {
-      if (lane == 0) {
-        left = x0 > 0 ? cur[x0 - 1] : 0u;
-        up_left = (x0 > 0 && use_up) ? up[x0 - 1] : 0u;
-      }
-      uint32_t o[4];
+    };
+    row_words((j.filter >= 2) ? y0 - 1 : -1, c[0]);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        uint32_t pred = filter_pred4(j.filter, y == 0, c[q], left, t[q], up_left);
-        if (q == 0 && x0 == 0 && j.filter != 0) pred = (pred & 0xffffff00u) | (y == 0 ? 0u : (uint32_t)up[0]);   // leftmost pixel: as is / from above
-        o[q] = __vsub4(c[q], pred);
-        left = c[q] >> 24;
-        up_left = t[q] >> 24;
-      }
+    for (int r = 0; r < kFwdRows; ++r) row_words(r < ny ? y0 + r : -1, c[r + 1]);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) *((uint32_t*)(dst + x0) + q) = o[q];
-      continue;
-    }
-    for (int x = x0; x < min(x0 + kFwdLane, j.width); ++x) {
-      int pred;
-      if (j.filter == 0) pred = 0;
-      else if (x == 0) pred = (y == 0) ? 0 : up[0];                        // leftmost pixel: as is / from above
-      else if (y == 0 || j.filter == 1) pred = cur[x - 1];                // top row and horizontal: from the left
-      else if (j.filter == 2) pred = up[x];
-      else pred = gradient_pred(cur[x - 1], up[x], up[x - 1]);
-      dst[x] = (uint8_t)(cur[x] - pred);
+    for (int r = 0; r < kFwdRows; ++r) {
+      if (r >= ny) break;
+      const int y = y0 + r;
+      const uint8_t* cur = j.src + (ptrdiff_t)y * j.src_stride;
+      const uint8_t* up = cur - j.src_stride;
+      uint8_t* dst = j.dst + (ptrdiff_t)y * j.dst_stride;
+      const bool use_up = y > 0 && j.filter >= 2;
+      const uint32_t (&cw)[4] = c[r + 1];
+      const uint32_t (&t)[4] = c[r];              // zeros when the row above is not used
+      uint32_t left = __shfl_up_sync(0xffffffffu, cw[3] >> 24, 1), up_left = __shfl_up_sync(0xffffffffu, t[3] >> 24, 1);   // every lane, vector or not
+      if (vec) {
+        if (lane == 0) {
+          left = x0 > 0 ? cur[x0 - 1] : 0u;
+          up_left = (x0 > 0 && use_up) ? up[x0 - 1] : 0u;
+        }
+        uint32_t o[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t pred = filter_pred4(j.filter, y == 0, cw[q], left, t[q], up_left);
+          if (q == 0 && x0 == 0 && j.filter != 0) pred = (pred & 0xffffff00u) | (y == 0 ? 0u : (uint32_t)up[0]);   // leftmost pixel: as is / from above
+          o[q] = __vsub4(cw[q], pred);
+          left = cw[q] >> 24;
+          up_left = t[q] >> 24;
+        }
+        if (al16) {
+          *reinterpret_cast<uint4*>(dst + x0) = make_uint4(o[0], o[1], o[2], o[3]);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) *((uint32_t*)(dst + x0) + q) = o[q];
+        }
+        continue;
+      }
+      for (int x = x0; x < min(x0 + kFwdLane, j.width); ++x) {
+        int pred;
+        if (j.filter == 0) pred = 0;
+        else if (x == 0) pred = (y == 0) ? 0 : up[0];                        // leftmost pixel: as is / from above
+        else if (y == 0 || j.filter == 1) pred = cur[x - 1];                // top row and horizontal: from the left
+        else if (j.filter == 2) pred = up[x];
+        else pred = gradient_pred(cur[x - 1], up[x], up[x - 1]);
+        dst[x] = (uint8_t)(cur[x] - pred);
+      }
     }
   }
 }
@@ -721,7 +752,7 @@ int prepare_filt(b2_ctx* ctx, int stream, const b2_alpha_filter_job* jobs, int n
     if (counts) counts[j.filter]++;
     uint32_t items = 0;
     switch (kind) {
-      case KIND_FORWARD: items = (uint32_t)((j.width + kFwdUnit - 1) / kFwdUnit) * (uint32_t)j.height; break;
+      case KIND_FORWARD: items = (uint32_t)((j.width + kFwdUnit - 1) / kFwdUnit) * (uint32_t)((j.height + kFwdRows - 1) / kFwdRows); break;
       case KIND_ROWS: items = (uint32_t)((j.height + kRowsPerWarp - 1) / kRowsPerWarp); break;
       default: items = d[i].units_x; break;
     }

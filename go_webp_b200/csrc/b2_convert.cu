@@ -161,7 +161,7 @@ __device__ __forceinline__ void store_px4(int st, bool premult, bool upstream16,
 
 // Item walk of the in-place multiplies and the YUV converters: a warp takes kItemPx pixels of one row, 128 at a time, a lane 4 of them
 // (the item's image lookup and job descriptor are paid once per kItemPx pixels).
-constexpr int kItemPx = 512;   // the in-place multiplies and the YUV converters; the ARGB converters keep 128 (registers)
+constexpr int kItemPx = 512;   // the ARGB converter, the in-place multiplies and the YUV converters; the use_argb import keeps 128
 #define B2_CONV_ITEM_PROLOGUE_WIDE(ITEM_PX)                                                                        \
   const int lane = threadIdx.x & 31;                                                                 \
   const uint32_t warp = threadIdx.x >> 5;                                                            \
@@ -176,37 +176,57 @@ constexpr int kItemPx = 512;   // the in-place multiplies and the YUV converters
     const int nv = min(4, j.width - x0);
 
 // ---- VP8LConvertFromBGRA ----------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 8)
+// A warp takes 512 pixels of one row: the four 128-bit loads of a lane are all requested before the first is
+// converted (with one load per lane in flight the converters sat at 0.6 of the copy bandwidth: 64 warps x 512 bytes
+// per SM is not enough to cover the memory latency), and the image lookup is paid once per 512 pixels.
+__global__ void __launch_bounds__(kThreads, 4)
 convert_from_bgra_kernel(const ConvJobDev* __restrict__ jobs, const uint32_t* __restrict__ prefix, uint32_t n_jobs,
                          uint32_t uniform, uint32_t total_items, int st, int premult, int upstream16) {
-  B2_CONV_ITEM_PROLOGUE
-    const uint32_t* s = (const uint32_t*)j.src + (ptrdiff_t)y * j.src_stride + x0;
-    uint32_t p[4];
-    if (nv == 4 && (((uintptr_t)s) & 15) == 0) {
-      const uint4 q = b2_ldg_stream_v4(s);
-      p[0] = q.x; p[1] = q.y; p[2] = q.z; p[3] = q.w;
-    } else {
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp = threadIdx.x >> 5;
+  for (uint32_t item = blockIdx.x * kWarps + warp; item < total_items; item += gridDim.x * kWarps) {
+    uint32_t local;
+    const uint32_t img = b2_find_image(prefix, n_jobs, uniform, item, &local);
+    const ConvJobDev j = jobs[img];
+    const uint32_t y = local / j.chunks_x;
+    const int xc = (int)(local - y * j.chunks_x) * kItemPx;
+    const uint32_t* srow = (const uint32_t*)j.src + (ptrdiff_t)y * j.src_stride;
+    uint32_t p[4][4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) p[k] = (k < nv) ? __ldg(s + k) : 0u;
+    for (int u = 0; u < 4; ++u) {
+      const int x0 = xc + u * 128 + lane * 4, nv = min(4, j.width - x0);
+      const uint32_t* s = srow + x0;
+      if (nv == 4 && (((uintptr_t)s) & 15) == 0) {
+        const uint4 q = b2_ldg_stream_v4(s);
+        p[u][0] = q.x; p[u][1] = q.y; p[u][2] = q.z; p[u][3] = q.w;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) p[u][k] = (k < nv) ? __ldg(s + k) : 0u;
+      }
     }
     const int bpp = bpp_of(st);
-    uint8_t* d = j.dst + (ptrdiff_t)y * j.dst_stride + x0 * bpp;
-    if (bpp == 4 && nv == 4 && (((uintptr_t)d) & 15) == 0) {
-      uint4 o;
-      o.x = pack_px(st, premult, p[0] >> 24, (p[0] >> 16) & 0xff, (p[0] >> 8) & 0xff, p[0] & 0xff);
-      o.y = pack_px(st, premult, p[1] >> 24, (p[1] >> 16) & 0xff, (p[1] >> 8) & 0xff, p[1] & 0xff);
-      o.z = pack_px(st, premult, p[2] >> 24, (p[2] >> 16) & 0xff, (p[2] >> 8) & 0xff, p[2] & 0xff);
-      o.w = pack_px(st, premult, p[3] >> 24, (p[3] >> 16) & 0xff, (p[3] >> 8) & 0xff, p[3] & 0xff);
-      b2_stg_stream_v4(d, o);
-    } else if (nv == 4) {
-      uint32_t a4[4], r4[4], g4[4], b4[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { a4[k] = p[k] >> 24; r4[k] = (p[k] >> 16) & 0xff; g4[k] = (p[k] >> 8) & 0xff; b4[k] = p[k] & 0xff; }
-      store_px4(st, premult, upstream16, a4, r4, g4, b4, d);
-    } else {
+    for (int u = 0; u < 4; ++u) {
+      const int x0 = xc + u * 128 + lane * 4, nv = min(4, j.width - x0);
+      if (nv <= 0) continue;
+      uint8_t* d = j.dst + (ptrdiff_t)y * j.dst_stride + x0 * bpp;
+      if (bpp == 4 && nv == 4 && (((uintptr_t)d) & 15) == 0) {
+        uint4 o;
+        o.x = pack_px(st, premult, p[u][0] >> 24, (p[u][0] >> 16) & 0xff, (p[u][0] >> 8) & 0xff, p[u][0] & 0xff);
+        o.y = pack_px(st, premult, p[u][1] >> 24, (p[u][1] >> 16) & 0xff, (p[u][1] >> 8) & 0xff, p[u][1] & 0xff);
+        o.z = pack_px(st, premult, p[u][2] >> 24, (p[u][2] >> 16) & 0xff, (p[u][2] >> 8) & 0xff, p[u][2] & 0xff);
+        o.w = pack_px(st, premult, p[u][3] >> 24, (p[u][3] >> 16) & 0xff, (p[u][3] >> 8) & 0xff, p[u][3] & 0xff);
+        b2_stg_stream_v4(d, o);
+      } else if (nv == 4) {
+        uint32_t a4[4], r4[4], g4[4], b4[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (k < nv) store_px(st, premult, upstream16, p[k] >> 24, (p[k] >> 16) & 0xff, (p[k] >> 8) & 0xff, p[k] & 0xff, d + k * bpp);
+        for (int k = 0; k < 4; ++k) { a4[k] = p[u][k] >> 24; r4[k] = (p[u][k] >> 16) & 0xff; g4[k] = (p[u][k] >> 8) & 0xff; b4[k] = p[u][k] & 0xff; }
+        store_px4(st, premult, upstream16, a4, r4, g4, b4, d);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (k < nv) store_px(st, premult, upstream16, p[u][k] >> 24, (p[u][k] >> 16) & 0xff, (p[u][k] >> 8) & 0xff, p[u][k] & 0xff, d + k * bpp);
+      }
     }
   }
 }
@@ -498,7 +518,7 @@ extern "C" int b2_vp8l_convert_from_bgra(b2_ctx* ctx, int stream, const b2_conve
   if (st < 0) return B2_ERR_INVALID_CONFIG;
   for (int i = 0; i < n_jobs; ++i) if (jobs[i].src == NULL) return B2_ERR_NULL;
   const ConvJobDev* dj; const uint32_t* dp; uint32_t uni, tot;
-  const int rc = prepare_conv(ctx, stream, jobs, n_jobs, false, bpp_of(st), 128, &dj, &dp, &uni, &tot);
+  const int rc = prepare_conv(ctx, stream, jobs, n_jobs, false, bpp_of(st), kItemPx, &dj, &dp, &uni, &tot);
   if (rc != B2_OK) return rc;
   convert_from_bgra_kernel<<<b2_grid_for(ctx, 8, (tot + kWarps - 1) / kWarps), kThreads, 0, ctx->streams[stream]>>>(
       dj, dp, (uint32_t)n_jobs, uni, tot, st, premult ? 1 : 0, ((flags & B2_CONVERT_UPSTREAM_16BIT) || !ctx->swap16) ? 1 : 0);

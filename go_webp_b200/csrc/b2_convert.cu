@@ -14,6 +14,7 @@
 #include <stdlib.h>
 
 #include "b2_common.cuh"
+#include "b2_upsample_core.cuh"
 
 namespace {
 
@@ -416,6 +417,37 @@ yuv_point_kernel(const ConvJobDev* __restrict__ jobs, const uint32_t* __restrict
     const uint8_t* vr = j.v + crow;
     const int bpp = bpp_of(st);
     uint8_t* d = j.dst + (ptrdiff_t)y * j.dst_stride + x0 * bpp;
+    if (x0 == xc + lane * 4 && xc + kItemPx <= j.width &&
+        ((((uintptr_t)yr) & 3) | (((uintptr_t)(ur + (YUV444 ? x0 : (x0 >> 1))) | (uintptr_t)(vr + (YUV444 ? x0 : (x0 >> 1)))) & (YUV444 ? 3 : 1))) == 0) {
+      // a whole 512-pixel item on aligned rows (warp-uniform): the twelve loads of the lane's four groups first
+      uint32_t yw4[4], uw4[4], vw4[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        yw4[g] = __ldg((const uint32_t*)(yr + 128 * g));
+        if (YUV444) {
+          uw4[g] = __ldg((const uint32_t*)(ur + x0 + 128 * g));
+          vw4[g] = __ldg((const uint32_t*)(vr + x0 + 128 * g));
+        } else {
+          uw4[g] = __byte_perm((uint32_t)__ldg((const uint16_t*)(ur + (x0 >> 1) + 64 * g)), 0, 0x1100);
+          vw4[g] = __byte_perm((uint32_t)__ldg((const uint16_t*)(vr + (x0 >> 1) + 64 * g)), 0, 0x1100);
+        }
+      }
+      const B2YuvConsts kc = b2_yuv_consts();
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint32_t a4[4] = {0xff, 0xff, 0xff, 0xff}, r4[4], g4[4], b4[4];
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+          const uint32_t sel = p ? 0x4342u : 0x4140u;
+          const B2Rgb14 c = b2_yuv_pair(b2_luma14(__byte_perm(yw4[g], 0u, sel), kc), __byte_perm(uw4[g], 0u, sel), __byte_perm(vw4[g], 0u, sel), kc);
+          r4[2 * p] = (c.r >> 6) & 0xffu; r4[2 * p + 1] = c.r >> 22;
+          g4[2 * p] = (c.g >> 6) & 0xffu; g4[2 * p + 1] = c.g >> 22;
+          b4[2 * p] = (c.b >> 6) & 0xffu; b4[2 * p + 1] = c.b >> 22;
+        }
+        store_px4(st, false, upstream16, a4, r4, g4, b4, d + 128 * g * bpp);
+      }
+      break;   // the item is done
+    }
     if (nv == 4) {   // whole words in (x0 is a multiple of 4: its chroma pair starts at x0 / 2), whole words out
       const uint32_t yw = ((((uintptr_t)yr) & 3) == 0) ? __ldg((const uint32_t*)yr)
                                                        : (uint32_t)yr[0] | ((uint32_t)yr[1] << 8) | ((uint32_t)yr[2] << 16) | ((uint32_t)yr[3] << 24);
@@ -433,25 +465,18 @@ yuv_point_kernel(const ConvJobDev* __restrict__ jobs, const uint32_t* __restrict
         uw = __byte_perm(u2, 0, 0x1100);   // row_func: two pixels share a sample (yuv.go:24-30)
         vw = __byte_perm(v2, 0, 0x1100);
       }
+      // two pixels per 32-bit register through the fancy upsampler's packed core (b2_upsample_core.cuh: the same
+      // MultHi / Clip8 arithmetic on 16-bit lanes, checked over all 2^24 (y, u, v) on the host): half the multiplies
+      // and clamps of the scalar form; uw / vw already hold one chroma byte per pixel in both samplings
       uint32_t a4[4] = {0xff, 0xff, 0xff, 0xff}, r4[4], g4[4], b4[4];
-      if (YUV444) {
+      const B2YuvConsts kc = b2_yuv_consts();
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          yuv_rgb((yw >> (8 * k)) & 0xff, (uw >> (8 * k)) & 0xff, (vw >> (8 * k)) & 0xff, &r4[k], &g4[k], &b4[k]);
-      } else {   // two pixels per chroma sample: its three terms once (the same integer sums as yuv_rgb)
-#pragma unroll
-        for (int p = 0; p < 2; ++p) {
-          const uint32_t u = (uw >> (16 * p)) & 0xff, v = (vw >> (16 * p)) & 0xff;
-          const int cr = ((int)(v * 26149u) >> 8) - 14234, cg = 8708 - ((int)(u * 6419u) >> 8) - ((int)(v * 13320u) >> 8),
-                    cb = ((int)(u * 33050u) >> 8) - 17685;
-#pragma unroll
-          for (int k = 2 * p; k < 2 * p + 2; ++k) {
-            const int yy = (int)(((yw >> (8 * k)) & 0xff) * 19077u) >> 8;
-            r4[k] = (uint32_t)min(max((yy + cr) >> 6, 0), 255);
-            g4[k] = (uint32_t)min(max((yy + cg) >> 6, 0), 255);
-            b4[k] = (uint32_t)min(max((yy + cb) >> 6, 0), 255);
-          }
-        }
+      for (int p = 0; p < 2; ++p) {
+        const uint32_t sel = p ? 0x4342u : 0x4140u;   // bytes (2p, 2p + 1) into the two 16-bit lanes
+        const B2Rgb14 c = b2_yuv_pair(b2_luma14(__byte_perm(yw, 0u, sel), kc), __byte_perm(uw, 0u, sel), __byte_perm(vw, 0u, sel), kc);
+        r4[2 * p] = (c.r >> 6) & 0xffu; r4[2 * p + 1] = c.r >> 22;
+        g4[2 * p] = (c.g >> 6) & 0xffu; g4[2 * p + 1] = c.g >> 22;
+        b4[2 * p] = (c.b >> 6) & 0xffu; b4[2 * p + 1] = c.b >> 22;
       }
       store_px4(st, false, upstream16, a4, r4, g4, b4, d);
       continue;

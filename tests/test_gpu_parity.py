@@ -591,7 +591,7 @@ def test_emit_fancy_rgb_streaming(gpu):
 def test_convert_from_bgra(gpu, mode):
     D = gpu["dsp"]
     rng = np.random.default_rng(200 + mode)
-    for (w, h) in [(1, 1), (3, 2), (4, 4), (7, 5), (128, 3), (131, 4), (516, 2)]:
+    for (w, h) in [(1, 1), (3, 2), (4, 4), (7, 5), (128, 3), (131, 4), (516, 2), (1024, 3), (1543, 2)]:
         argb = rng.integers(0, 2**32, (h, w), dtype=np.uint32)
         argb[0, 0] |= 0xff000000            # opaque, translucent and transparent pixels all present
         if w > 2:
@@ -637,7 +637,7 @@ def test_alpha_multiplies(gpu):
 def test_point_sampler_and_yuv444(gpu, mode):
     D = gpu["dsp"]
     rng = np.random.default_rng(300 + mode)
-    for (w, h) in [(1, 1), (2, 3), (5, 4), (127, 3), (260, 5)]:
+    for (w, h) in [(1, 1), (2, 3), (5, 4), (127, 3), (260, 5), (512, 2), (1030, 5), (1536, 3)]:   # the last three: whole 512-pixel items
         y = rng.integers(0, 256, (h, w), dtype=np.uint8)
         u = rng.integers(0, 256, ((h + 1) // 2, (w + 1) // 2), dtype=np.uint8)
         v = rng.integers(0, 256, ((h + 1) // 2, (w + 1) // 2), dtype=np.uint8)

@@ -165,9 +165,93 @@ constexpr int kRowsPerWarp = 8;
 #ifndef B2_ROWS_CTAS
 #define B2_ROWS_CTAS 4
 #endif
+// The fast path of alpha_unfilter_rows_kernel (16-byte aligned rows, width a multiple of 16), one instantiation per
+// filter so that the loop holds ONE load site: with the copy and the scan in one loop the compiler merges their loads
+// through a spare register and copies it into the ring at the end of the item -- i.e. waits for it there.
+template <int FILTER>
+__device__ __forceinline__ void unfilter_rows_fast(const FiltJobDev& j, int y0, int y1, uint32_t col0, int lane, uint4* ring) {
+      // Whole 16-byte pieces everywhere: the (row, 512-byte chunk) items of the group as one list, fetched
+      // kAhead items ahead by 16-byte cp.async into a ring in shared memory (a lane reads back what it copied: no
+      // barrier) -- the scan of a chunk waits for nothing but its own carry.  One chunk at a time, the warp had a
+      // single 512-byte load in flight (0.42 of the measured peak); a ring of REGISTERS does not survive the
+      // compiler, which parks the new load in a spare register and copies it into the ring at the end of the item,
+      // i.e. waits for it there (ncu: 44 % of the warp time on that copy).
+      constexpr int kAhead = B2_ROWS_AHEAD;
+      const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
+      const int cpr = (j.width + 511) >> 9, n_items = (y1 - y0) * cpr;
+      int pr = y0, pc = 0;                         // the item the next fetch takes
+      auto fetch = [&](int slot) {
+        const int x = pc * 512 + lane * 16;
+        if (pr < y1 && x < j.width)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(ring_s + (uint32_t)slot * 512u), "l"(j.src + (ptrdiff_t)pr * j.src_stride + x) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (++pc == cpr) { pc = 0; ++pr; }
+      };
+#pragma unroll
+      for (int q = 0; q < kAhead; ++q) fetch(q);
+      int cr = y0, cc = 0;
+      uint32_t carry = 0;
+      for (int i0 = 0; i0 < n_items; i0 += kAhead) {
+#pragma unroll
+        for (int q = 0; q < kAhead; ++q) {
+          if (i0 + q < n_items) {                  // warp-uniform
+            asm volatile("cp.async.wait_group %0;" :: "n"(kAhead - 1) : "memory");
+            const uint4 v = ring[q * 32];
+            if (cc == 0) {                         // a new row: the value left of it, then its own first sample joins the column sum
+              carry = col0 & 0xffu;
+              col0 += __shfl_sync(0xffffffffu, v.x & 0xffu, 0);
+            }
+            const int x = cc * 512 + lane * 16;
+            uint8_t* const dp = j.dst + (ptrdiff_t)cr * j.dst_stride + x;
+            if (FILTER != 1) {                     // filter NONE: a copy
+              if (x < j.width) b2_stg_stream_v4(dp, v);
+              fetch(q);
+            } else {
+              // The running sums of the lane's 16 bytes in 16-bit fields (no packed byte adds, which cost five
+              // instructions each): for a word [b0 b1 b2 b3], e = [b0, b2], o = [b1, b3], x = e + o, the even outputs
+              // are e + (x << 16) = [b0, b0+b1+b2] and the odd ones x * 0x10001 = [b0+b1, b0+b1+b2+b3]; what precedes
+              // the word (the words before it in the lane, the lanes before it, the chunks before it) is one
+              // multiply-add per register, and the low bytes of the fields are the outputs mod 256.
+              const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+              uint32_t pe[4], po[4], off[4];
+              uint32_t run = 0;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint32_t e = w[k] & 0x00ff00ffu, o = __byte_perm(w[k], 0u, 0x4341);
+                const uint32_t xs = e + o;
+                pe[k] = e + (xs << 16);
+                po[k] = xs * 0x00010001u;
+                off[k] = run;
+                run += po[k] >> 16;
+              }
+              fetch(q);                            // the slot's words are in registers: refill it
+              const uint32_t tot = run;            // lane total, then an exclusive scan over the lanes
+              uint32_t scan = tot;
+#pragma unroll
+              for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, scan, o);
+                if (lane >= o) scan += t;
+              }
+              const uint32_t before = (scan - tot + carry) & 0xffu;
+              uint32_t ow[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint32_t sk = (off[k] + before) * 0x00010001u;
+                ow[k] = __byte_perm(pe[k] + sk, po[k] + sk, 0x6240);
+              }
+              carry = (__shfl_sync(0xffffffffu, scan, 31) + carry) & 0xffu;
+              if (x < j.width) b2_stg_stream_v4(dp, make_uint4(ow[0], ow[1], ow[2], ow[3]));
+            }
+            if (++cc == cpr) { cc = 0; ++cr; }
+          }
+        }
+      }
+}
+
 __global__ void __launch_bounds__(kThreads, B2_ROWS_CTAS)
 alpha_unfilter_rows_kernel(const FiltJobDev* __restrict__ jobs, const uint32_t* __restrict__ prefix, uint32_t n_jobs,
                            uint32_t uniform, uint32_t total) {
+  __shared__ uint4 ring_sm[kWarps][B2_ROWS_AHEAD][32];   // the fast path's prefetch ring, 512 bytes per warp and stage
   const int lane = threadIdx.x & 31;
   for (uint32_t unit = blockIdx.x * kWarps + (threadIdx.x >> 5); unit < total; unit += gridDim.x * kWarps) {
     uint32_t group;
@@ -178,7 +262,15 @@ alpha_unfilter_rows_kernel(const FiltJobDev* __restrict__ jobs, const uint32_t* 
     uint32_t col0 = 0;                           // sum of column 0 over the rows above y
     if (j.filter == 1 && y0 > 0) {
       uint32_t s = 0;
-      for (int r = lane; r < y0; r += 32) s += j.src[(ptrdiff_t)r * j.src_stride];
+      int r = lane;
+      for (; r + 7 * 32 < y0; r += 8 * 32) {       // eight independent loads at a time: one per iteration makes this walk
+        uint32_t t[8];                              // (y0 / 32 round trips to L2) as long as the group's own 8 rows
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t[k] = __ldg(j.src + (ptrdiff_t)(r + 32 * k) * j.src_stride);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += t[k];
+      }
+      for (; r < y0; r += 32) s += __ldg(j.src + (ptrdiff_t)r * j.src_stride);
 #pragma unroll
       for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
       col0 = s;
@@ -186,73 +278,8 @@ alpha_unfilter_rows_kernel(const FiltJobDev* __restrict__ jobs, const uint32_t* 
     const uintptr_t bits = (uintptr_t)j.src | (uintptr_t)j.dst | (uintptr_t)(uint32_t)j.src_stride | (uintptr_t)(uint32_t)j.dst_stride;
     const bool al4 = (bits & 3) == 0, al16 = (bits & 15) == 0;
     if (al16 && (j.width & 15) == 0) {
-      // Whole 16-byte pieces everywhere: the (row, 512-byte chunk) items of the group as one list, fetched
-      // kAhead items ahead into a register ring -- the scan of a chunk waits for nothing but its own carry.  (One
-      // chunk at a time, the warp had a single 512-byte load in flight: 0.42 of the measured peak.)
-      constexpr int kAhead = B2_ROWS_AHEAD;
-      const int cpr = (j.width + 511) >> 9, n_items = (y1 - y0) * cpr;
-      int pr = y0, pc = 0;                         // the item the next fetch takes
-      auto fetch = [&]() -> uint4 {
-        uint4 q = make_uint4(0, 0, 0, 0);
-        const int x = pc * 512 + lane * 16;
-        if (pr < y1 && x < j.width) q = b2_ldg_stream_v4(j.src + (ptrdiff_t)pr * j.src_stride + x);
-        if (++pc == cpr) { pc = 0; ++pr; }
-        return q;
-      };
-      uint4 ring[kAhead];
-#pragma unroll
-      for (int q = 0; q < kAhead; ++q) ring[q] = fetch();
-      int cr = y0, cc = 0;
-      uint32_t carry = 0;
-      for (int i0 = 0; i0 < n_items; i0 += kAhead) {
-#pragma unroll
-        for (int q = 0; q < kAhead; ++q) {
-          if (i0 + q < n_items) {                  // warp-uniform
-            const uint4 v = ring[q];
-            ring[q] = fetch();
-            if (cc == 0) {                         // a new row: the value left of it, then its own first sample joins the column sum
-              carry = col0 & 0xffu;
-              col0 += __shfl_sync(0xffffffffu, v.x & 0xffu, 0);
-            }
-            uint32_t w[4] = {v.x, v.y, v.z, v.w};
-            if (j.filter == 1) {
-              // The running sums of the lane's 16 bytes in 16-bit fields (no packed byte adds, which cost five
-              // instructions each): for a word [b0 b1 b2 b3], e = [b0, b2], o = [b1, b3], x = e + o, the even outputs
-              // are e + (x << 16) = [b0, b0+b1+b2] and the odd ones x * 0x10001 = [b0+b1, b0+b1+b2+b3]; what precedes
-              // the word (the words before it in the lane, the lanes before it, the chunks before it) is one
-              // multiply-add per register, and the low bytes of the fields are the outputs mod 256.
-              uint32_t pe[4], po[4], off[4];
-              uint32_t run = 0;
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint32_t e = w[k] & 0x00ff00ffu, o = __byte_perm(w[k], 0u, 0x4341);
-                const uint32_t x = e + o;
-                pe[k] = e + (x << 16);
-                po[k] = x * 0x00010001u;
-                off[k] = run;
-                run += po[k] >> 16;
-              }
-              const uint32_t tot = run;            // lane total, then an exclusive scan over the lanes
-              uint32_t scan = tot;
-#pragma unroll
-              for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, scan, o);
-                if (lane >= o) scan += t;
-              }
-              const uint32_t before = (scan - tot + carry) & 0xffu;
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint32_t sk = (off[k] + before) * 0x00010001u;
-                w[k] = __byte_perm(pe[k] + sk, po[k] + sk, 0x6240);
-              }
-              carry = (__shfl_sync(0xffffffffu, scan, 31) + carry) & 0xffu;
-            }
-            const int x = cc * 512 + lane * 16;
-            if (x < j.width) b2_stg_stream_v4(j.dst + (ptrdiff_t)cr * j.dst_stride + x, make_uint4(w[0], w[1], w[2], w[3]));
-            if (++cc == cpr) { cc = 0; ++cr; }
-          }
-        }
-      }
+      if (j.filter == 1) unfilter_rows_fast<1>(j, y0, y1, col0, lane, &ring_sm[threadIdx.x >> 5][0][lane]);
+      else unfilter_rows_fast<0>(j, y0, y1, col0, lane, &ring_sm[threadIdx.x >> 5][0][lane]);
       continue;
     }
     for (int y = y0; y < y1; ++y) {

@@ -4,6 +4,9 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <chrono>
+#include <thread>
+
 #include "b2_common.cuh"
 
 int b2_fail_cuda(b2_ctx* ctx, cudaError_t e, const char* what) {
@@ -32,9 +35,20 @@ extern "C" const char* b2_strerror(int status) {
 
 extern "C" int b2_device_count(int* count) {
   if (count == NULL) return B2_ERR_NULL;
+  // A box that has just come up can answer cudaErrorSystemNotReady / NoDevice for a
+  // moment while the driver's persistence daemon starts: ask again for up to 3 s
+  // before reporting that there is no device.
   int n = 0;
-  cudaError_t e = cudaGetDeviceCount(&n);
-  if (e != cudaSuccess) { (void)cudaGetLastError(); *count = 0; return B2_ERR_CUDA; }
+  cudaError_t e = cudaSuccess;
+  for (int attempt = 0; attempt < 10; ++attempt) {
+    n = 0;
+    e = cudaGetDeviceCount(&n);
+    if (e == cudaSuccess && n > 0) break;
+    if (e == cudaErrorInsufficientDriver) break;  // no driver at all: nothing to wait for
+    (void)cudaGetLastError();
+    std::this_thread::sleep_for(std::chrono::milliseconds(300));
+  }
+  if (e != cudaSuccess) { *count = 0; return B2_ERR_CUDA; }
   *count = n;
   return B2_OK;
 }

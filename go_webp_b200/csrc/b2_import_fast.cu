@@ -199,6 +199,12 @@ __device__ __forceinline__ void cp_async16_full(uint32_t dst, const void* src) {
 __device__ __forceinline__ void cp_async4(uint32_t dst, const void* src, uint32_t nbytes) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(dst), "l"(src), "r"(nbytes) : "memory");
 }
+__device__ __forceinline__ void cp_async4_full(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8_full(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(dst), "l"(src) : "memory");
+}
 __device__ __forceinline__ uint4 lds128_ring(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
@@ -315,14 +321,32 @@ import_fast_kernel(const ImportJobDev* __restrict__ jobs, const uint32_t* __rest
     // part in the vote of block_sums) and store nothing.
     const bool al16 = ((((uintptr_t)jp->src) | (uintptr_t)(uint32_t)sstride) & 15) == 0;  // warp-uniform
     const int tiles_x = (width + 127) >> 7;
+#ifdef B2_IMPORT_FULL_UNALIGNED
+    const bool al8 = ((((uintptr_t)jp->src) | (uintptr_t)(uint32_t)sstride) & 7) == 0;
+    const int full = width >> 7;
+#else
     const int full = al16 ? (width >> 7) : 0;
+#endif
     const uint8_t* g0 = s0;
     const uint8_t* g1 = s1;
     uint32_t wr = slot0, rd = slot0;
     auto issue = [&](int t) {  // one commit group per call, possibly empty
       if (t < full) {
+#ifdef B2_IMPORT_FULL_UNALIGNED
+        if (al16) {
+          cp_async16_full(wr, g0);
+          cp_async16_full(wr + 512, g1);
+        } else if (al8) {
+          cp_async8_full(wr, g0); cp_async8_full(wr + 8, g0 + 8);
+          cp_async8_full(wr + 512, g1); cp_async8_full(wr + 520, g1 + 8);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { cp_async4_full(wr + 4 * k, g0 + 4 * k); cp_async4_full(wr + 512 + 4 * k, g1 + 4 * k); }
+        }
+#else
         cp_async16_full(wr, g0);
         cp_async16_full(wr + 512, g1);
+#endif
       } else if (t < tiles_x) {
         const int nv = min(max(width - ((int)lane4 + t * 128), 0), 4);
         const uint8_t* q0 = nv ? g0 : s0 - phase * 512;   // lanes past the row: zero fill from a valid address

@@ -37,7 +37,13 @@ enum Op { OP_ADD_GREEN, OP_SUB_GREEN, OP_CC_INV, OP_CC_FWD, OP_CHAIN_INV, OP_CHA
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kItemPx = 256;  // flat kernels: pixels per warp item (2 x uint4 per thread)
+#ifndef B2_FLAT_ITEM
+#define B2_FLAT_ITEM 2048
+#endif
+#ifndef B2_FLAT_GROUPS
+#define B2_FLAT_GROUPS 4
+#endif
+constexpr int kItemPx = B2_FLAT_ITEM;         // flat kernels: pixels per warp item
 
 __device__ __forceinline__ uint32_t add_green(uint32_t argb) {
   const uint32_t green = (argb >> 8) & 0xff;
@@ -105,32 +111,6 @@ __device__ __forceinline__ Mult fetch_mult(const ArgbJobDev& j, uint32_t i) {
   }
   return m;
 }
-// Tile codes of the 4 consecutive flat pixels i .. i+3 (i % 4 == 0).  With width % 4
-// == 0 (and bits >= 2) they share a row and a tile; otherwise the group may run over
-// the end of a row, so every pixel looks its own tile up.
-template <int OP>
-__device__ __forceinline__ uint4 fetch_codes4(const ArgbJobDev& j, uint32_t i) {
-  uint4 c = make_uint4(0, 0, 0, 0);
-  if (!needs_codes<OP>()) return c;
-  const uint32_t w = (uint32_t)j.width;
-  const uint32_t y = i / w, x = i - y * w;
-  const uint32_t* __restrict__ row = j.data + (y >> j.bits) * j.tiles_per_row;
-  c.x = __ldg(row + (x >> j.bits));
-  if ((w & 3u) == 0) {
-    c.y = c.z = c.w = c.x;
-  } else if (x + 3 < w) {
-    c.y = __ldg(row + ((x + 1) >> j.bits)); c.z = __ldg(row + ((x + 2) >> j.bits)); c.w = __ldg(row + ((x + 3) >> j.bits));
-  } else {  // the group runs over the end of the row
-    const uint32_t* __restrict__ nrow = j.data + ((y + 1) >> j.bits) * j.tiles_per_row;
-    uint32_t xx = x + 1;
-    c.y = (xx < w) ? __ldg(row + (xx >> j.bits)) : __ldg(nrow + ((xx - w) >> j.bits));
-    xx = x + 2;
-    c.z = (xx < w) ? __ldg(row + (xx >> j.bits)) : __ldg(nrow + ((xx - w) >> j.bits));
-    xx = x + 3;
-    c.w = (xx < w) ? __ldg(row + (xx >> j.bits)) : __ldg(nrow + ((xx - w) >> j.bits));
-  }
-  return c;
-}
 template <int OP>
 __device__ __forceinline__ uint4 apply4(uint4 codes, uint4 p, bool one_tile) {
   uint4 o;
@@ -145,38 +125,105 @@ __device__ __forceinline__ uint4 apply4(uint4 codes, uint4 p, bool one_tile) {
 }
 
 #ifndef B2_FLAT_CTAS
-#define B2_FLAT_CTAS 6
+#define B2_FLAT_CTAS 4
 #endif
+#ifndef B2_FLAT_GRID_AL
+#define B2_FLAT_GRID_AL 3
+#endif
+#ifndef B2_FLAT_GRID_UN
+#define B2_FLAT_GRID_UN 4
+#endif
+#ifndef B2_FLAT_GROUPS_PLAIN
+#define B2_FLAT_GROUPS_PLAIN 2
+#endif
+// Tile codes of the 4 consecutive flat pixels that start at (y, x).  Nearly always they lie
+// in one tile of one row (always when width % 4 == 0): one load.  A group that crosses a
+// tile boundary or the end of its row looks every pixel up.
 template <int OP>
-__global__ void __launch_bounds__(kThreads, B2_FLAT_CTAS)
+__device__ __forceinline__ uint4 codes_at(const uint32_t* __restrict__ data, uint32_t tpr, uint32_t bits,
+                                          uint32_t w, uint32_t y, uint32_t x, bool* same) {
+  uint4 c = make_uint4(0, 0, 0, 0);
+  *same = true;
+  if (!needs_codes<OP>()) return c;
+  const uint32_t* __restrict__ row = data + (y >> bits) * tpr;
+  const uint32_t tx = x >> bits;
+  c.x = __ldg(row + tx);
+  c.y = c.z = c.w = c.x;
+  *same = (x + 3 < w) && (((x + 3) >> bits) == tx);
+  if (!*same) {
+#pragma unroll
+    for (uint32_t k = 1; k < 4; ++k) {
+      uint32_t xx = x + k, yy = y;
+      while (xx >= w) { xx -= w; ++yy; }
+      (k == 1 ? c.y : k == 2 ? c.z : c.w) = __ldg(data + (yy >> bits) * tpr + (xx >> bits));
+    }
+  }
+  return c;
+}
+
+// A warp item = kItemPx consecutive flat pixels of one image, walked in steps of kSubPx (four
+// 128-bit groups per lane, all loads issued before the first store).  The image lookup, the
+// descriptor and the one division (flat index -> row, column) are paid once per item; from
+// there a lane follows its (row, column) by additions.
+template <int OP>
+__global__ void __launch_bounds__(kThreads, needs_codes<OP>() ? B2_FLAT_CTAS : 4)
 flat_kernel(const ArgbJobDev* __restrict__ jobs, const uint32_t* __restrict__ prefix,
             uint32_t n_jobs, uint32_t uniform, uint32_t total_items) {
-  const int lane = threadIdx.x & 31;
+  // groups per lane and step: the transforms with tile codes want four loads in flight, the
+  // plain copies (add / sub green) run best with two (measured: 0.98 against 0.93 of the peak)
+  constexpr int kSubGroups = needs_codes<OP>() ? B2_FLAT_GROUPS : B2_FLAT_GROUPS_PLAIN;
+  constexpr int kSubPx = 128 * kSubGroups;
+  static_assert(kItemPx % kSubPx == 0, "flat item");
+  const uint32_t lane = threadIdx.x & 31;
   const uint32_t warp = threadIdx.x >> 5;
   for (uint32_t item = blockIdx.x * kWarps + warp; item < total_items; item += gridDim.x * kWarps) {
     uint32_t local;
-    const uint32_t img = b2_find_image(prefix, n_jobs, uniform, item, &local);
-    const ArgbJobDev j = jobs[img];
-    const uint32_t n = (uint32_t)j.width * (uint32_t)j.height;
-    const uint32_t i0 = local * kItemPx + lane * 4;
-    const uint32_t i1 = i0 + 128;
-    if ((j.flags & JOB_VEC) && i1 + 4 <= n) {
-      const uint4 a = b2_ld_stream_v4(j.src + i0);  // not .nc: dst may alias src
-      const uint4 b = b2_ld_stream_v4(j.src + i1);
-      const uint4 ca = fetch_codes4<OP>(j, i0), cb = fetch_codes4<OP>(j, i1);
-      const bool one_tile = (j.width & 3) == 0;
-      b2_stg_stream_v4(j.dst + i0, apply4<OP>(ca, a, one_tile));
-      b2_stg_stream_v4(j.dst + i1, apply4<OP>(cb, b, one_tile));
-    } else {
+    const uint32_t img = b2_find_image_warp(prefix, n_jobs, uniform, item, &local, lane);
+    const ArgbJobDev* __restrict__ jp = jobs + img;
+    const uint32_t w = (uint32_t)jp->width;
+    const uint32_t n = w * (uint32_t)jp->height;
+    const uint32_t* src = jp->src;   // not restrict: dst may alias src
+    uint32_t* dst = jp->dst;
+    const uint32_t* __restrict__ data = jp->data;
+    const uint32_t bits = (uint32_t)jp->bits, tpr = jp->tiles_per_row;
+    const bool vec = (jp->flags & JOB_VEC) != 0;
+    const uint32_t base = local * kItemPx;
+    const uint32_t end = min(n, base + (uint32_t)kItemPx);
+    uint32_t i = base + lane * 4;
+    uint32_t y = 0, x = 0;
+    if (needs_codes<OP>()) { y = i / w; x = i - y * w; }
+    for (uint32_t s0 = base; s0 < end; s0 += kSubPx, i += kSubPx) {
+      if (vec && s0 + kSubPx <= n) {
+        uint4 p[kSubGroups], c[kSubGroups];
+        bool same = true;
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const uint32_t base = h ? i1 : i0;
-        for (uint32_t k = 0; k < 4; ++k) {
-          const uint32_t i = base + k;
-          if (i < n) {
-            const Mult m = fetch_mult<OP>(j, i);
-            j.dst[i] = apply_px<OP>(m, j.src[i]);
+        for (int g = 0; g < kSubGroups; ++g) p[g] = b2_ld_stream_v4(src + i + 128 * g);  // not .nc: dst may alias src
+#pragma unroll
+        for (int g = 0; g < kSubGroups; ++g) {
+          bool sg;
+          c[g] = codes_at<OP>(data, tpr, bits, w, y, x, &sg);
+          same = same && sg;
+          if (needs_codes<OP>()) { x += 128; while (x >= w) { x -= w; ++y; } }
+        }
+        const bool one_tile = __all_sync(0xffffffffu, same);
+#pragma unroll
+        for (int g = 0; g < kSubGroups; ++g) b2_stg_stream_v4(dst + i + 128 * g, apply4<OP>(c[g], p[g], one_tile));
+      } else {
+        for (int g = 0; g < kSubGroups; ++g) {
+          const uint32_t gi = i + 128 * g;
+          if (vec && gi + 4 <= n) {
+            bool sg;
+            const uint4 cg = codes_at<OP>(data, tpr, bits, w, y, x, &sg);
+            b2_stg_stream_v4(dst + gi, apply4<OP>(cg, b2_ld_stream_v4(src + gi), false));
+          } else {
+            for (uint32_t k = 0; k < 4; ++k) {
+              if (gi + k < n) {
+                const Mult m = fetch_mult<OP>(*jp, gi + k);
+                dst[gi + k] = apply_px<OP>(m, src[gi + k]);
+              }
+            }
           }
+          if (needs_codes<OP>()) { x += 128; while (x >= w) { x -= w; ++y; } }
         }
       }
     }
@@ -467,7 +514,13 @@ int run_flat(b2_ctx* ctx, int stream, const b2_argb_job* jobs, int n_jobs) {
   // Persistent CTAs per SM.  Measured on 4096^2 batches (profiles/r01d_grid_sweeps.md):
   // the pure copies (add/sub-green) peak at 4 per SM (0.95 of the measured HBM peak vs
   // 0.88 at 3, 5 or 6), the cross-colour kernels need the extra warps of 6 per SM.
-  const int grid_ctas = needs_codes<OP>() ? B2_FLAT_CTAS : 4;
+  // Resident CTAs per SM (the grid is persistent; the register budget allows B2_FLAT_CTAS).  Measured on
+  // 64 x 4096^2 and on the mixed-size batch of configs[4] (profiles/r02c_mixed_sizes.md): images whose
+  // rows are whole 4-pixel groups stream best with 3 CTAs per SM (0.99 of the measured peak against 0.90
+  // with 4: fewer concurrent DRAM streams), the others carry more instructions per pixel and want 4.
+  bool whole_groups = true;
+  for (int i = 0; i < n_jobs; ++i) whole_groups = whole_groups && (jobs[i].width & 3) == 0;
+  const int grid_ctas = !needs_codes<OP>() ? 4 : (whole_groups ? B2_FLAT_GRID_AL : B2_FLAT_GRID_UN);
   const int grid = b2_grid_for(ctx, grid_ctas, (p.total + kWarps - 1) / kWarps);
   flat_kernel<OP><<<grid, kThreads, 0, ctx->streams[stream]>>>(p.jobs, p.prefix, n_jobs, p.uniform, p.total);
   ctx->launches++;

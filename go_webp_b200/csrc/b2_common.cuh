@@ -10,6 +10,7 @@
 #include "../../include/b2webp.h"
 
 #define B2_MAX_STREAMS 16
+#define B2_TICKET_WORDS 32
 #define B2_EVENT_SLOTS 32
 // Staging ring for batch descriptors (pinned host + device mirror) per stream.
 #define B2_DESC_RING_BYTES (4u << 20)
@@ -32,6 +33,9 @@ struct b2_ctx {
   void* scratch[B2_MAX_STREAMS];
   size_t scratch_bytes[B2_MAX_STREAMS];
   uint64_t launches;
+  // work counters of the kernels that hand their units out by ticket: B2_TICKET_WORDS words per stream,
+  // zero between launches (the last warp of a launch clears the two it used)
+  uint32_t* tickets_dev;
   // byte order of the 16-bit output modes (RGBA_4444, RGB_565), library-wide: 1 = the go-webp text
   // (libwebp built with WEBP_SWAP_16BIT_CSP: ba / gb byte first), 0 = the stock libwebp build (rg first)
   int swap16;
@@ -79,6 +83,9 @@ int b2_desc_reserve(b2_ctx* ctx, int stream, size_t bytes);
 int b2_upload_desc(b2_ctx* ctx, int stream, const void* host, size_t bytes, void** dev_out);
 
 // Persistent-grid sizing: ctas_per_sm resident CTAs on every SM, capped by work.
+static inline uint32_t* b2_tickets(const b2_ctx* ctx, int stream, int slot) {
+  return ctx->tickets_dev + (size_t)stream * B2_TICKET_WORDS + 2 * slot;
+}
 static inline int b2_grid_for(const b2_ctx* ctx, int ctas_per_sm, uint64_t units_of_work) {
   uint64_t g = (uint64_t)ctx->sm_count * (uint64_t)ctas_per_sm;
   if (units_of_work < g) g = units_of_work;

@@ -124,6 +124,9 @@ extern "C" int b2_ctx_create(int device, int n_streams, b2_ctx** out) {
     e = cudaMemcpy(ctx->tab_dev, tab, sizeof(uint32_t) * B2_TAB_WORDS, cudaMemcpyHostToDevice);
     free(tab);
     if (e != cudaSuccess) { st = b2_fail_cuda(ctx, e, "tab copy"); break; }
+    const size_t tb = sizeof(uint32_t) * B2_TICKET_WORDS * B2_MAX_STREAMS;
+    if ((e = cudaMalloc((void**)&ctx->tickets_dev, tb)) != cudaSuccess) { st = b2_fail_cuda(ctx, e, "tickets"); break; }
+    if ((e = cudaMemset(ctx->tickets_dev, 0, tb)) != cudaSuccess) { st = b2_fail_cuda(ctx, e, "tickets clear"); break; }
   } while (0);
   if (st != B2_OK) { b2_ctx_destroy(ctx); return st; }
   *out = ctx;
@@ -141,6 +144,7 @@ extern "C" void b2_ctx_destroy(b2_ctx* ctx) {
   }
   for (int i = 0; i < B2_EVENT_SLOTS; ++i) if (ctx->events[i]) (void)cudaEventDestroy(ctx->events[i]);
   if (ctx->tab_dev) (void)cudaFree(ctx->tab_dev);
+  if (ctx->tickets_dev) (void)cudaFree(ctx->tickets_dev);
   if (ctx->flags_dev) (void)cudaFree(ctx->flags_dev);
   if (ctx->flags_host) (void)cudaFreeHost(ctx->flags_host);
   for (int i = 0; i < B2_STAGED_EVENTS; ++i) if (ctx->staged_ev[i]) (void)cudaEventDestroy(ctx->staged_ev[i]);

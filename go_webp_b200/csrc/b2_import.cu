@@ -316,6 +316,7 @@ static int import_impl(b2_ctx* ctx, int stream, const b2_import_job* jobs, int n
   uint32_t* upre = (uint32_t*)((uint8_t*)pre + pb);  // prefix in row pairs (fast kernel)
   bool fast = (step == 4);
   bool tuned = (step == 4);   // b2_import_fast.cu preconditions
+  bool unaligned = false;     // some source row is not 16-byte aligned
   int n_with_a = 0;
   uint64_t total = 0, utotal = 0;
   uint32_t uniform = 0, uuniform = 0;
@@ -339,6 +340,7 @@ static int import_impl(b2_ctx* ctx, int stream, const b2_import_job* jobs, int n
     if (j.a && (((uintptr_t)j.a | (uintptr_t)(uint32_t)j.a_stride) & 3) == 0) d.flags |= JOB_A_ALIGNED;
     if ((((uintptr_t)j.u | (uintptr_t)j.v | (uintptr_t)(uint32_t)j.uv_stride) & 1) == 0) d.flags |= JOB_UV_ALIGNED;
     if ((((uintptr_t)j.src | (uintptr_t)(uint32_t)j.src_stride) & 3) != 0) fast = false;
+    if ((((uintptr_t)j.src | (uintptr_t)(uint32_t)j.src_stride) & 15) != 0) unaligned = true;
     if ((((uintptr_t)j.src | (uintptr_t)(uint32_t)j.src_stride) & 3) != 0 ||
         !(d.flags & JOB_Y_ALIGNED) || !(d.flags & JOB_UV_ALIGNED) || (j.a && !(d.flags & JOB_A_ALIGNED))) tuned = false;
     n_with_a += (j.a != NULL);
@@ -426,7 +428,8 @@ static int import_impl(b2_ctx* ctx, int stream, const b2_import_job* jobs, int n
   }
   if (tuned) {
     B2_CUDA(ctx, b2_import_fast_launch(ctx, s, djobs, dupre, (uint32_t)n_jobs, uuniform, (uint32_t)utotal,
-                                       order, alpha, n_with_a != 0, divt, has_alpha_dev, dither));
+                                       order, alpha, n_with_a != 0, divt, has_alpha_dev, dither,
+                                       b2_tickets(ctx, stream, 0), unaligned));
   } else if (fast) {
     if (order == B2_ORDER_RGBA) {
       if (alpha) import_kernel<0, true><<<grid, kThreads, 0, s>>>(djobs, dpre, n_jobs, uniform, tot, ctx->tab_dev, divt, has_alpha_dev);

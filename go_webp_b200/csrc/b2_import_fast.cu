@@ -51,12 +51,15 @@ constexpr int kUnroll = B2_IMPORT_UNROLL;
 constexpr int kSplit = B2_IMPORT_SPLIT;  // power of two
 constexpr int kFastWarps = kFastThreads / 32;
 constexpr int kFastCtasPerSm = 1;
-constexpr int kRingStages = B2_IMPORT_RING;         // power of two
+constexpr int kRingStages = B2_IMPORT_RING;
 constexpr int kDist = kRingStages - 1;              // strips in flight ahead of the computation
-constexpr uint32_t kStageBytes = 1024;              // row 0 at +0, row 1 at +512, 16 bytes per lane
-constexpr uint32_t kRingBytes = kRingStages * kStageBytes;   // per warp; rings are aligned to their size
-constexpr uint32_t kStageMask = kRingBytes - kStageBytes;
-static_assert((kRingStages & (kRingStages - 1)) == 0 && kRingStages >= 2 && kRingStages <= 4, "ring");
+// A stage holds one strip of both rows: 32 chunks of 16 bytes (one per lane) + a 33rd chunk, which
+// rows that are not 16-byte aligned need (UNAL kernels: their 128 pixels start up to 12 bytes into
+// chunk 0 and end as far into chunk 32).  Row 0 at +0, row 1 at +kRow1.
+constexpr uint32_t kRow1 = 33 * 16;
+constexpr uint32_t kStageBytes = 2 * kRow1;
+constexpr uint32_t kRingBytes = kRingStages * kStageBytes;   // per warp
+static_assert(kRingStages == 2, "the ring toggles between two stages (next = base + base + stage - current)");
 
 // Shared-memory map, in shared-window addresses (what LDS takes).  T = the first 64 KB
 // boundary at or after the start of dynamic shared memory; with the tables on 64 KB
@@ -199,27 +202,23 @@ __device__ __forceinline__ void cp_async16_full(uint32_t dst, const void* src) {
 __device__ __forceinline__ void cp_async4(uint32_t dst, const void* src, uint32_t nbytes) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(dst), "l"(src), "r"(nbytes) : "memory");
 }
-__device__ __forceinline__ void cp_async4_full(uint32_t dst, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async8_full(uint32_t dst, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(dst), "l"(src) : "memory");
-}
 __device__ __forceinline__ uint4 lds128_ring(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
   return v;
 }
-// next stage of a ring slot address (rings are aligned to their size)
-__device__ __forceinline__ uint32_t ring_next(uint32_t a) {
-  return (a & ~kStageMask) | ((a + kStageBytes) & kStageMask);
-}
 
-template <int ORDER, bool ALPHA, bool WRITE_A, bool TABLE, bool DITHER>
+// UNAL: source rows that are only 4-byte aligned (a tight 4 * width stride with width % 4 != 0).  A lane
+// still fetches whole aligned 16-byte chunks -- chunk 32 t + lane of the row's enclosing aligned span, lane 0
+// chunk 32 t + 32 as well -- and takes its four pixels out of its own chunk and the next one (two 128-bit
+// shared loads and a register shift by the row's misalignment, warp-uniform) instead of fetching 4 bytes at
+// a time: 0.55 -> 0.8 of the measured peak on such images (profiles/r02c_mixed_sizes.md).
+template <int ORDER, bool ALPHA, bool WRITE_A, bool TABLE, bool DITHER, bool UNAL>
 __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm)
 import_fast_kernel(const ImportJobDev* __restrict__ jobs, const uint32_t* __restrict__ unit_prefix,
                    uint32_t n_jobs, uint32_t uniform_units, uint32_t total_units,
-                   const uint32_t* __restrict__ tab, int32_t* __restrict__ has_alpha, const ImportDither dither) {
+                   const uint32_t* __restrict__ tab, int32_t* __restrict__ has_alpha, const ImportDither dither,
+                   uint32_t* __restrict__ tickets) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
   const uint32_t tbase = (sbase + 0xffffu) & ~0xffffu;       // T
@@ -252,23 +251,24 @@ import_fast_kernel(const ImportJobDev* __restrict__ jobs, const uint32_t* __rest
   const uint32_t lbase = (tbase + kOffL2G) | lane4;
   const uint32_t dbase = tbase + kOffDiv;
   // this warp's ring: below the tables while there is room, else above them
-  const uint32_t ring_lo = (sbase + kRingBytes - 1) & ~(kRingBytes - 1);
+  const uint32_t ring_lo = (sbase + 15u) & ~15u;
   const uint32_t n_lo = (tbase - ring_lo) / kRingBytes;
   const uint32_t slot0 = (warp < n_lo ? ring_lo + warp * kRingBytes
                                       : tbase + kOffRingHi + (warp - n_lo) * kRingBytes) + lane * 16;
+  const uint32_t slot_sum = 2 * slot0 + kStageBytes;   // the other stage of a slot address a: slot_sum - a
 
-#if B2_IMPORT_CHUNKED
-  // every CTA takes one contiguous share of the row pairs (equal to within one), its warps
-  // walk it round-robin: all SMs finish together whatever the batch size
-  const uint32_t all_units = total_units * kSplit;
-  const uint32_t unit_lo = (uint32_t)(((uint64_t)all_units * blockIdx.x) / gridDim.x);
-  const uint32_t unit_hi = (uint32_t)(((uint64_t)all_units * (blockIdx.x + 1)) / gridDim.x);
-  for (uint32_t unit = unit_lo + warp; unit < unit_hi; unit += kFastWarps) {
-#else
-  for (uint32_t unit = blockIdx.x * kFastWarps + warp; unit < total_units * kSplit; unit += gridDim.x * kFastWarps) {
-#endif
+  // Row pairs are handed out by a ticket counter (tickets[0]; tickets[1] counts the warps that
+  // are done, the last one clears both for the next launch on this stream): in a batch of mixed
+  // sizes a row pair costs anything from 1 to 64 strips, and with a fixed stride the warp with the
+  // most wide rows decides when the kernel ends (0.50 -> 0.6x of the measured peak on configs[4]).
+  // The next ticket is drawn before the current row pair is worked on, so its latency is hidden.
+  const uint32_t n_warps_total = gridDim.x * kFastWarps;
+  uint32_t unit = blockIdx.x * kFastWarps + warp;
+  while (unit < total_units * kSplit) {
+    uint32_t next_unit = 0;
+    if (lane == 0) next_unit = n_warps_total + atomicAdd(tickets, 1u);
     uint32_t rp;
-    const uint32_t img = b2_find_image(unit_prefix, n_jobs, uniform_units, unit / kSplit, &rp);
+    const uint32_t img = b2_find_image_warp(unit_prefix, n_jobs, uniform_units, unit / kSplit, &rp, lane);
     const int phase = (int)(unit % kSplit);
     const ImportJobDev* __restrict__ jp = jobs + img;
     const int width = jp->width;
@@ -315,65 +315,86 @@ import_fast_kernel(const ImportJobDev* __restrict__ jobs, const uint32_t* __rest
 
     // Strips of 128 pixels.  Rows that are 16-byte aligned are fetched with one 16-byte
     // cp.async per lane and row; whole strips of such rows take the check-free code.  The
-    // last partial strip, and every strip of rows that are only 4-byte aligned (a tight
-    // 4*width stride with width % 4 != 0), fetch the valid pixels only and take the
-    // general code, where lanes past the end of the row run on zeros (every lane takes
-    // part in the vote of block_sums) and store nothing.
+    // last partial strip fetches the valid pixels only and takes the general code, where
+    // lanes past the end of the row run on zeros (every lane takes part in the vote of
+    // block_sums) and store nothing.  Rows that are only 4-byte aligned (a tight 4 * width
+    // stride with width % 4 != 0): the UNAL kernels fetch the aligned chunks that enclose them;
+    // the others (dithered import only) fetch 4 bytes at a time and take the general code.
     const bool al16 = ((((uintptr_t)jp->src) | (uintptr_t)(uint32_t)sstride) & 15) == 0;  // warp-uniform
     const int tiles_x = (width + 127) >> 7;
-#ifdef B2_IMPORT_FULL_UNALIGNED
-    const bool al8 = ((((uintptr_t)jp->src) | (uintptr_t)(uint32_t)sstride) & 7) == 0;
-    const int full = width >> 7;
-#else
-    const int full = al16 ? (width >> 7) : 0;
-#endif
+    const int full = (UNAL || al16) ? (width >> 7) : 0;
     const uint8_t* g0 = s0;
     const uint8_t* g1 = s1;
+    // UNAL: m = pixels between the enclosing aligned address and the row start (0..3), g = this lane's
+    // chunk of that aligned span, rem = bytes from the start of the chunk to the end of the row
+    uint32_t m0 = 0, m1 = 0;
+    int rem0 = 0, rem1 = 0;
+    if (UNAL) {
+      m0 = ((uint32_t)(uintptr_t)s0 >> 2) & 3u;
+      m1 = ((uint32_t)(uintptr_t)s1 >> 2) & 3u;
+      g0 = s0 - 4 * m0;
+      g1 = s1 - 4 * m1;
+      rem0 = 4 * width + 4 * (int)m0 - 16 * (int)lane;
+      rem1 = 4 * width + 4 * (int)m1 - 16 * (int)lane;
+    }
     uint32_t wr = slot0, rd = slot0;
     auto issue = [&](int t) {  // one commit group per call, possibly empty
-      if (t < full) {
-#ifdef B2_IMPORT_FULL_UNALIGNED
-        if (al16) {
-          cp_async16_full(wr, g0);
-          cp_async16_full(wr + 512, g1);
-        } else if (al8) {
-          cp_async8_full(wr, g0); cp_async8_full(wr + 8, g0 + 8);
-          cp_async8_full(wr + 512, g1); cp_async8_full(wr + 520, g1 + 8);
-        } else {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) { cp_async4_full(wr + 4 * k, g0 + 4 * k); cp_async4_full(wr + 512 + 4 * k, g1 + 4 * k); }
+      if (UNAL) {
+        if (t < tiles_x) {
+          // chunk 32 t + lane of both rows, lane 0 chunk 32 t + 32 too; only bytes inside the row are read
+          // (the rest of a chunk is zero-filled).  A chunk past the row is not fetched at all: its lanes
+          // compute on whatever an earlier strip left in the slot and store nothing (nvalid <= 0).
+          if (rem0 > 0) cp_async16(wr, g0, (uint32_t)min(rem0, 16));
+          if (rem1 > 0) cp_async16(wr + kRow1, g1, (uint32_t)min(rem1, 16));
+          if (lane == 0) {
+            if (rem0 > 512) cp_async16(wr + 512, g0 + 512, (uint32_t)min(rem0 - 512, 16));
+            if (rem1 > 512) cp_async16(wr + kRow1 + 512, g1 + 512, (uint32_t)min(rem1 - 512, 16));
+          }
+          rem0 -= 512; rem1 -= 512;
         }
-#else
+      } else if (t < full) {
         cp_async16_full(wr, g0);
-        cp_async16_full(wr + 512, g1);
-#endif
+        cp_async16_full(wr + kRow1, g1);
       } else if (t < tiles_x) {
         const int nv = min(max(width - ((int)lane4 + t * 128), 0), 4);
         const uint8_t* q0 = nv ? g0 : s0 - phase * 512;   // lanes past the row: zero fill from a valid address
         const uint8_t* q1 = nv ? g1 : s1 - phase * 512;
         if (al16) {
           cp_async16(wr, q0, 4u * nv);
-          cp_async16(wr + 512, q1, 4u * nv);
+          cp_async16(wr + kRow1, q1, 4u * nv);
         } else {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint32_t nb = (k < nv) ? 4u : 0u;
             cp_async4(wr + 4 * k, q0 + (nb ? 4 * k : 0), nb);
-            cp_async4(wr + 512 + 4 * k, q1 + (nb ? 4 * k : 0), nb);
+            cp_async4(wr + kRow1 + 4 * k, q1 + (nb ? 4 * k : 0), nb);
           }
         }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
-      wr = ring_next(wr);
+      wr = slot_sum - wr;
       g0 += 512 * kSplit; g1 += 512 * kSplit;
+    };
+    // UNAL: the lane's four pixels start m words into its chunk and end in the next one
+    auto shifted = [&](uint4& c, uint32_t next_addr, uint32_t m) {
+      if (m != 0) {            // warp-uniform
+        const uint4 n = lds128_ring(next_addr);
+        if (m == 1) c = make_uint4(c.y, c.z, c.w, n.x);
+        else if (m == 2) c = make_uint4(c.z, c.w, n.x, n.y);
+        else c = make_uint4(c.w, n.x, n.y, n.z);
+      }
     };
     auto strip = [&](auto full_tag, int t) {
       constexpr bool FULL = decltype(full_tag)::value;
       issue(t + kDist * kSplit);
       asm volatile("cp.async.wait_group %0;" :: "n"(kDist) : "memory");
       uint4 c0 = lds128_ring(rd);
-      uint4 c1 = lds128_ring(rd + 512);
-      rd = ring_next(rd);
+      uint4 c1 = lds128_ring(rd + kRow1);
+      if (UNAL) {
+        shifted(c0, rd + 16, m0);
+        shifted(c1, rd + kRow1 + 16, m1);
+      }
+      rd = slot_sum - rd;
       uint4 dq0 = make_uint4(0, 0, 0, 0), dq1 = dq0, dq2 = dq0;
       if (DITHER) {
         // the next 128 draws of the three streams, 24 per step: s_n = s_(n-55) - s_(n-24) mod 2^31
@@ -473,35 +494,47 @@ import_fast_kernel(const ImportJobDev* __restrict__ jobs, const uint32_t* __rest
     if (ALPHA && has_alpha != nullptr) {
       if (__any_sync(0xffffffffu, and_acc != 0xffffffffu) && lane == 0) atomicOr(has_alpha + img, 1);
     }
+    unit = __shfl_sync(0xffffffffu, next_unit, 0);
+  }
+  if (lane == 0) {
+    if (atomicAdd(tickets + 1, 1u) == n_warps_total - 1) { tickets[0] = 0; tickets[1] = 0; }
   }
 }
 
-template <int ORDER, bool ALPHA, bool WRITE_A, bool TABLE, bool DITHER>
-cudaError_t launch2(int grid, cudaStream_t s, const ImportJobDev* jobs, const uint32_t* unit_prefix,
-                    uint32_t n_jobs, uint32_t uniform_units, uint32_t total_units, const uint32_t* tab,
-                    int32_t* has_alpha, ImportDither dither) {
-  auto k = import_fast_kernel<ORDER, ALPHA, WRITE_A, TABLE, DITHER>;
+struct FastArgs {
+  int grid;
+  cudaStream_t s;
+  const ImportJobDev* jobs;
+  const uint32_t* unit_prefix;
+  uint32_t n_jobs, uniform_units, total_units;
+  const uint32_t* tab;
+  int32_t* has_alpha;
+  ImportDither dither;
+  uint32_t* tickets;
+  bool unaligned;
+};
+template <int ORDER, bool ALPHA, bool WRITE_A, bool TABLE, bool DITHER, bool UNAL>
+cudaError_t launch3(const FastArgs& a) {
+  auto k = import_fast_kernel<ORDER, ALPHA, WRITE_A, TABLE, DITHER, UNAL>;
   const int smem = kSmemBytes + (DITHER ? kFastWarps * (int)kDitherWarpBytes : 0);
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
-  k<<<grid, kFastThreads, smem, s>>>(jobs, unit_prefix, n_jobs, uniform_units, total_units, tab, has_alpha, dither);
+  k<<<a.grid, kFastThreads, smem, a.s>>>(a.jobs, a.unit_prefix, a.n_jobs, a.uniform_units, a.total_units, a.tab,
+                                         a.has_alpha, a.dither, a.tickets);
   return cudaGetLastError();
 }
 template <int ORDER, bool ALPHA, bool WRITE_A, bool TABLE>
-cudaError_t launch1(int grid, cudaStream_t s, const ImportJobDev* jobs, const uint32_t* unit_prefix,
-                    uint32_t n_jobs, uint32_t uniform_units, uint32_t total_units, const uint32_t* tab,
-                    int32_t* has_alpha, ImportDither dither) {
-  if (dither.rng_states != nullptr)
-    return launch2<ORDER, ALPHA, WRITE_A, TABLE, true>(grid, s, jobs, unit_prefix, n_jobs, uniform_units, total_units, tab, has_alpha, dither);
-  return launch2<ORDER, ALPHA, WRITE_A, TABLE, false>(grid, s, jobs, unit_prefix, n_jobs, uniform_units, total_units, tab, has_alpha, dither);
+cudaError_t launch1(const FastArgs& a) {
+  // the dithered import keeps the 4-bytes-at-a-time fetch for rows that are not 16-byte aligned
+  if (a.dither.rng_states != nullptr) return launch3<ORDER, ALPHA, WRITE_A, TABLE, true, false>(a);
+  if (a.unaligned) return launch3<ORDER, ALPHA, WRITE_A, TABLE, false, true>(a);
+  return launch3<ORDER, ALPHA, WRITE_A, TABLE, false, false>(a);
 }
 template <int ORDER, bool ALPHA, bool WRITE_A>
-cudaError_t launch(int grid, cudaStream_t s, const ImportJobDev* jobs, const uint32_t* unit_prefix,
-                   uint32_t n_jobs, uint32_t uniform_units, uint32_t total_units, const uint32_t* tab,
-                   int div_table, int32_t* has_alpha, ImportDither dither) {
+cudaError_t launch(const FastArgs& a, int div_table) {
   // the divide mode only matters when alpha is imported
-  if (ALPHA && div_table) return launch1<ORDER, ALPHA, WRITE_A, true>(grid, s, jobs, unit_prefix, n_jobs, uniform_units, total_units, tab, has_alpha, dither);
-  return launch1<ORDER, ALPHA, WRITE_A, false>(grid, s, jobs, unit_prefix, n_jobs, uniform_units, total_units, tab, has_alpha, dither);
+  if (ALPHA && div_table) return launch1<ORDER, ALPHA, WRITE_A, true>(a);
+  return launch1<ORDER, ALPHA, WRITE_A, false>(a);
 }
 
 }  // namespace
@@ -510,9 +543,13 @@ cudaError_t b2_import_fast_launch(const b2_ctx* ctx, cudaStream_t s, const Impor
                                   const uint32_t* unit_prefix, uint32_t n_jobs,
                                   uint32_t uniform_units, uint32_t total_units, int order,
                                   bool alpha, bool write_a, int div_table, int32_t* has_alpha,
-                                  ImportDither dither) {
-  const int grid = b2_grid_for(ctx, kFastCtasPerSm, ((uint64_t)total_units * kSplit + kFastWarps - 1) / kFastWarps);
-#define B2_GO(O, A, W) return launch<O, A, W>(grid, s, jobs, unit_prefix, n_jobs, uniform_units, total_units, ctx->tab_dev, div_table, has_alpha, dither)
+                                  ImportDither dither, uint32_t* tickets, bool unaligned) {
+  FastArgs a;
+  a.grid = b2_grid_for(ctx, kFastCtasPerSm, ((uint64_t)total_units * kSplit + kFastWarps - 1) / kFastWarps);
+  a.s = s; a.jobs = jobs; a.unit_prefix = unit_prefix; a.n_jobs = n_jobs; a.uniform_units = uniform_units;
+  a.total_units = total_units; a.tab = ctx->tab_dev; a.has_alpha = has_alpha; a.dither = dither;
+  a.tickets = tickets; a.unaligned = unaligned;
+#define B2_GO(O, A, W) return launch<O, A, W>(a, div_table)
   if (order == B2_ORDER_RGBA) {
     if (alpha) { if (write_a) B2_GO(0, true, true); else B2_GO(0, true, false); }
     else       { if (write_a) B2_GO(0, false, true); else B2_GO(0, false, false); }

@@ -574,7 +574,8 @@ __device__ __forceinline__ void convert_pass_split(const uint8_t* sp_y, const ui
 template <int ST, bool HAS_ALPHA>
 __global__ void __launch_bounds__(kBulkThreads, kBulkCtasPerSm)
 upsample_bulk_kernel(const UpsampleJobDev* __restrict__ jobs, const uint32_t* __restrict__ unit_prefix,
-                     uint32_t n_jobs, uint32_t uniform_units, uint32_t total_units, const B2YuvConsts kc) {
+                     uint32_t n_jobs, uint32_t uniform_units, uint32_t total_units, const B2YuvConsts kc,
+                     uint32_t* __restrict__ tickets) {
   using BL = BulkLayout<HAS_ALPHA>;
   constexpr int kTileW = BL::kTW;
   __shared__ __align__(128) uint8_t ring[kBulkWarps * 2 * BL::kBytes];
@@ -595,6 +596,16 @@ upsample_bulk_kernel(const UpsampleJobDev* __restrict__ jobs, const uint32_t* __
   const uint32_t unit_stride = gridDim.x * kBulkWarps;
   total_units = uni(total_units);
 
+  // Row pairs are handed out by a ticket counter (tickets[0]; tickets[1] counts the warps that are done,
+  // the last one clears both for the next launch on the stream): a warp starts on row pair first_unit and
+  // draws the following ones, so in a batch of mixed sizes no warp is left with more wide rows than the
+  // others.  The ticket after the producer's row pair is always drawn one row pair early (ahead, lane 0).
+  // The consumer walks the same sequence at most two row pairs behind the producer (c_next1, c_next2).
+  uint32_t ahead = 0;
+  if (lane == 0) ahead = unit_stride + atomicAdd(tickets, 1u);
+  uint32_t c_next1 = 0, c_next2 = 0;
+  int n_pending = 0;
+
   // ---- producer: lane 0 issues every copy of a tile (one mbarrier arrival) ----
   uint32_t p_unit = first_unit;
   int p_t = 0, p_tiles = 0, p_ylen = 0, p_clen = 0;
@@ -603,7 +614,7 @@ upsample_bulk_kernel(const UpsampleJobDev* __restrict__ jobs, const uint32_t* __
   auto producer_setup = [&]() {
     if (p_unit >= total_units) return;
     uint32_t q;
-    const uint32_t img = b2_find_image(unit_prefix, n_jobs, uniform_units, p_unit, &q);
+    const uint32_t img = b2_find_image_warp(unit_prefix, n_jobs, uniform_units, p_unit, &q, (uint32_t)lane);
     const UpsampleJobDev* __restrict__ jp = jobs + img;
     q += jp->q_lo;
     const int width = jp->width, height = jp->height;
@@ -648,7 +659,13 @@ upsample_bulk_kernel(const UpsampleJobDev* __restrict__ jobs, const uint32_t* __
         bulk_g2s(sb + BL::kA + kTileW, p_a + p_adelta + ys0, yb, bar);
       }
     }
-    if (++p_t == p_tiles) { p_unit += unit_stride; producer_setup(); }
+    if (++p_t == p_tiles) {
+      p_unit = __shfl_sync(0xffffffffu, ahead, 0);
+      if (lane == 0 && p_unit < total_units) ahead = unit_stride + atomicAdd(tickets, 1u);
+      if (n_pending == 0) c_next1 = p_unit; else c_next2 = p_unit;
+      ++n_pending;
+      producer_setup();
+    }
   };
 
   // ---- consumer ----
@@ -663,7 +680,7 @@ upsample_bulk_kernel(const UpsampleJobDev* __restrict__ jobs, const uint32_t* __
   uint32_t stage = 0, phase = 0;  // phase bit s = parity to wait for on stage s
   while (c_unit < total_units) {
     uint32_t q;
-    const uint32_t img = b2_find_image(unit_prefix, n_jobs, uniform_units, c_unit, &q);
+    const uint32_t img = b2_find_image_warp(unit_prefix, n_jobs, uniform_units, c_unit, &q, (uint32_t)lane);
     const UpsampleJobDev* __restrict__ jp = jobs + img;
     q += jp->q_lo;
     const int width = jp->width;
@@ -705,7 +722,12 @@ upsample_bulk_kernel(const UpsampleJobDev* __restrict__ jobs, const uint32_t* __
       if (top_ok) pixel_generic<ST>(j, rt, wv + lane);
       if (bot_ok) pixel_generic<ST>(j, rb, wv + lane);
     }
-    c_unit += unit_stride;
+    c_unit = c_next1;   // the producer moved on when it issued this row pair's last tile
+    c_next1 = c_next2;
+    --n_pending;
+  }
+  if (lane == 0) {
+    if (atomicAdd(tickets + 1, 1u) == unit_stride - 1) { tickets[0] = 0; tickets[1] = 0; }
   }
 }
 
@@ -817,7 +839,7 @@ extern "C" int b2_yuv420a_to_rgba_fancy(b2_ctx* ctx, int stream, const b2_upsamp
     const int bgrid = b2_grid_for(ctx, bulk_grid_ctas, (utotal + kBulkWarps - 1) / kBulkWarps);
     const uint32_t ut = (uint32_t)utotal;
     const bool ha = n_with_a != 0;
-#define B2_UPK(ST_, HA_) upsample_bulk_kernel<ST_, HA_><<<bgrid, kBulkThreads, 0, s>>>(djobs, dupre, n_jobs, uuniform, ut, b2_yuv_consts())
+#define B2_UPK(ST_, HA_) upsample_bulk_kernel<ST_, HA_><<<bgrid, kBulkThreads, 0, s>>>(djobs, dupre, n_jobs, uuniform, ut, b2_yuv_consts(), b2_tickets(ctx, stream, 1))
     switch (st_mode) {
       case ST_RGBA: if (ha) B2_UPK(ST_RGBA, true); else B2_UPK(ST_RGBA, false); break;
       case ST_BGRA: if (ha) B2_UPK(ST_BGRA, true); else B2_UPK(ST_BGRA, false); break;

@@ -1278,3 +1278,84 @@ def test_predictor_inverse_chain_fused(gpu):
             if perm[mode] is not None:
                 e = np.ascontiguousarray(e.view(np.uint8).reshape(e.shape[0], -1, 4)[:, :, perm[mode]]).view(np.uint32).reshape(e.shape)
             assert (o == e).all(), (im.width, im.height, mode)
+
+
+def test_import_unaligned_source_rows_raw_abi(gpu):
+    """Source rows that are only 4-byte aligned (b2_import_fast.cu, UNAL kernels): every misalignment of
+    the pointer (0, 4, 8, 12 bytes) and of the stride, widths around the strip and chunk boundaries,
+    1-pixel images, with and without the alpha plane -- through the raw C ABI on two streams, several
+    launches in a row (the row pairs are handed out by a ticket counter that the last warp of a launch
+    clears for the next one)."""
+    from go_webp_b200.device import Context
+    A = gpu["abi"]
+    ctx = Context(0, n_streams=2)
+    rng = np.random.default_rng(0x0a11)
+    widths = [1, 2, 3, 5, 31, 33, 124, 127, 128, 129, 131, 255, 256, 257, 260, 515, 1021, 1028]
+    cases = []
+    for k, w in enumerate(widths):
+        h = 1 + (k * 5) % 9
+        cases.append((w, h, 4 * (k % 4), 4 * ((k // 4) % 4)))       # pointer offset, stride padding
+    cases += [(128, 3, 4, 0), (256, 2, 12, 0), (132, 4, 8, 4), (4, 1, 12, 12)]
+    al = lambda v, a=256: (v + a - 1) // a * a  # noqa: E731
+    lay, tot = [], dict(src=0, y=0, uv=0)
+    for (w, h, off, pad) in cases:
+        stride = 4 * w + pad
+        ys, uvs = al(w, 4), al((w + 1) // 2, 2)
+        lay.append((tot["src"] + off, stride, tot["y"], ys, tot["uv"], uvs))
+        tot["src"] += al(off + stride * h + 16)
+        tot["y"] += al(ys * h)
+        tot["uv"] += al(uvs * ((h + 1) // 2))
+    host_src = np.zeros(tot["src"], np.uint8)
+    srcs = []
+    for (w, h, off, pad), (so, stride, *_r) in zip(cases, lay):
+        img = rng.integers(0, 256, (h, stride), dtype=np.uint8)
+        img[:, 3:4 * w:4][rng.random((h, w)) < 0.6] = 255
+        host_src[so:so + stride * h] = img.reshape(-1)
+        srcs.append(img)
+    d_src, d_y, d_a = ctx.alloc(tot["src"]), ctx.alloc(tot["y"]), ctx.alloc(tot["y"])
+    d_u, d_v, d_f = ctx.alloc(tot["uv"]), ctx.alloc(tot["uv"]), ctx.alloc(al(4 * len(cases)))
+    ctx.h2d(d_src.ptr, host_src)
+    jobs = [A.ImportJob(d_src.ptr + so, d_y.ptr + yo, d_u.ptr + uo, d_v.ptr + uo, d_a.ptr + yo, stride, ys, uvs, ys, w, h)
+            for (w, h, off, pad), (so, stride, yo, ys, uo, uvs) in zip(cases, lay)]
+    arr = (A.ImportJob * len(jobs))(*jobs)
+    for rep in range(4):
+        stream = rep % 2
+        order, flags = (A.ORDER_RGBA, A.IMPORT_ALPHA) if rep < 3 else (A.ORDER_BGRA, 0)
+        for buf, nb in ((d_y, tot["y"]), (d_a, tot["y"]), (d_u, tot["uv"]), (d_v, tot["uv"])):
+            ctx.h2d(buf.ptr, np.full(nb, 0x5a, np.uint8))
+        ctx._chk(ctx.lib.b2_rgba_to_yuv420a(ctx.h, stream, arr, len(jobs), order, flags, d_f.ptr))
+        ctx.sync()
+        Y, U, V, Aa = (ctx.d2h(b.ptr, nb) for b, nb in ((d_y, tot["y"]), (d_u, tot["uv"]), (d_v, tot["uv"]), (d_a, tot["y"])))
+        fl = ctx.d2h(d_f.ptr, 4 * len(cases)).view(np.int32)
+        for i, ((w, h, off, pad), (so, stride, yo, ys, uo, uvs), src) in enumerate(zip(cases, lay, srcs)):
+            name = "RGBA" if rep < 3 else "BGRX"
+            y, u, v, a, ha = oracle.import_yuva(src, w, h, name, stride=stride)
+            uh, uw = (h + 1) // 2, (w + 1) // 2
+            got_y = Y[yo:yo + ys * h].reshape(h, ys)
+            assert (got_y[:, :w] == y).all(), (rep, i, w, h, off, pad)
+            assert (got_y[:, w:] == 0x5a).all(), (rep, i, "wrote past the end of a Y row")
+            assert (U[uo:uo + uvs * uh].reshape(uh, uvs)[:, :uw] == u).all(), (rep, i, w, h, off, pad)
+            assert (V[uo:uo + uvs * uh].reshape(uh, uvs)[:, :uw] == v).all(), (rep, i, w, h, off, pad)
+            if rep < 3:
+                assert bool(fl[i]) == bool(ha), (rep, i)
+                assert (Aa[yo:yo + ys * h].reshape(h, ys)[:, :w] == src[:, 3:4 * w:4]).all(), (rep, i)
+    for b in (d_src, d_y, d_a, d_u, d_v, d_f):
+        b.free()
+    ctx.close()
+
+
+def test_vp8l_flat_items_odd_widths_and_tile_edges(gpu):
+    """Flat VP8L kernels (2048-pixel items walked by additions): widths that are not multiples of 4, narrower
+    than a 128-pixel step, images of less than one item and of several, every tile size, in one batch."""
+    D = gpu["dsp"]
+    rng = np.random.default_rng(0xf1a7)
+    sizes = [(1, 1), (3, 700), (5, 5), (63, 40), (127, 33), (129, 17), (130, 64), (257, 9), (1021, 7), (2049, 3), (4099, 2), (333, 333)]
+    for bits in (2, 3, 5, 9):
+        imgs, chains = [], []
+        for (w, h) in sizes:
+            imgs.append(rng.integers(0, 2**32, (h, w), dtype=np.uint32))
+            codes = rng.integers(0, 2**24, (D.VP8LSubSampleSize(h, bits), D.VP8LSubSampleSize(w, bits)), dtype=np.uint32) | 0xff000000
+            chains.append([D.VP8LTransform(D.SUBTRACT_GREEN_TRANSFORM, 0, w, h), D.VP8LTransform(D.CROSS_COLOR_TRANSFORM, bits, w, h, codes)])
+        res = D.VP8LInverseTransformBatch([D.VP8LImage(a, w, h) for a, (w, h) in zip(imgs, sizes)], chains)
+        for r, a, ch, sz in zip(res, imgs, chains, sizes):
+            assert (r == oracle.add_green(oracle.color_space_inverse(a, ch[1].data, bits))).all(), (bits, sz)

@@ -17,6 +17,9 @@
 
 #include "b2_common.cuh"
 
+#ifndef B2_CLEANUP_CTAS
+#define B2_CLEANUP_CTAS 3
+#endif
 namespace {
 
 constexpr int kThreads = 256;
@@ -53,7 +56,7 @@ __device__ __forceinline__ int carry_out(uint32_t tmask, int base, int carry, in
 
 // ---- WebPCleanupTransparentArea, YUVA form ------------------------------------------
 // unit = one band of 8 rows (the last band may be shorter: SmoothenBlock only, :173-181)
-__global__ void __launch_bounds__(kThreads, 5)
+__global__ void __launch_bounds__(kThreads, B2_CLEANUP_CTAS)
 cleanup_yuva_kernel(const PicJobDev* __restrict__ jobs, const uint32_t* __restrict__ prefix, uint32_t n_jobs,
                     uint32_t uniform, uint32_t total) {
   const int lane = threadIdx.x & 31;
@@ -82,6 +85,47 @@ cleanup_yuva_kernel(const PicJobDev* __restrict__ jobs, const uint32_t* __restri
       uint32_t a_lo[8], a_hi[8];
       int count = 0, sum = 0;
       const int n_blk = max(bw, 0) * bh;
+      if (full_band && al8 && (base + 32) * 8 <= width) {
+        // Whole chunk of whole 8x8 blocks (warp-uniform): straight-line code, so the eight alpha loads of
+        // a block are in flight together, and so are its eight luma loads (the general code below
+        // decides row by row and waits for every load on its own: 16 round trips per chunk).  The
+        // luma stays in registers between the sum and the rewrite.
+        const uint8_t* ap = ab + x0;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const uint2 av = *reinterpret_cast<const uint2*>(ap + (ptrdiff_t)r * as);
+          a_lo[r] = av.x; a_hi[r] = av.y;
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) count += (__popc(__vcmpne4(a_lo[r], 0u)) + __popc(__vcmpne4(a_hi[r], 0u))) >> 3;
+        const bool partial = count > 0 && count < 64;
+        if (__any_sync(0xffffffffu, partial)) {
+          uint8_t* yp = yb + x0;
+          uint32_t y_lo[8], y_hi[8];
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            y_lo[r] = y_hi[r] = 0u;
+            if (partial) {
+              const uint2 yv = *reinterpret_cast<const uint2*>(yp + (ptrdiff_t)r * ys);
+              y_lo[r] = yv.x; y_hi[r] = yv.y;
+            }
+          }
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            const uint32_t m_lo = __vcmpne4(a_lo[r], 0u), m_hi = __vcmpne4(a_hi[r], 0u);
+            sum += (int)__dp4a(y_lo[r] & m_lo, 0x01010101u, 0u) + (int)__dp4a(y_hi[r] & m_hi, 0x01010101u, 0u);
+          }
+          if (partial) {
+            const uint32_t avg4 = ((uint32_t)(sum / count) & 0xffu) * 0x01010101u;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+              const uint32_t m_lo = __vcmpne4(a_lo[r], 0u), m_hi = __vcmpne4(a_hi[r], 0u);
+              *reinterpret_cast<uint2*>(yp + (ptrdiff_t)r * ys) =
+                  make_uint2((y_lo[r] & m_lo) | (avg4 & ~m_lo), (y_hi[r] & m_hi) | (avg4 & ~m_hi));
+            }
+          }
+        }
+      } else {
       auto load_luma = [&](int r, uint32_t* lo, uint32_t* hi) {
         const uint8_t* yp = yb + (ptrdiff_t)r * ys + x0;
         *lo = *hi = 0u;
@@ -146,6 +190,7 @@ cleanup_yuva_kernel(const PicJobDev* __restrict__ jobs, const uint32_t* __restri
             }
           }
         }
+      }
       }
       // fully transparent 8x8 blocks of a full band are flattened to their run's first values
       const bool transp = full_band && bw == 8 && count == 0;
@@ -300,16 +345,16 @@ blend_yuva_kernel(const PicJobDev* __restrict__ jobs, const uint32_t* __restrict
       uint8_t* ap0 = j->a + (ptrdiff_t)(2 * rp) * j->a_stride + x;
       uint8_t* yp1 = has_row1 ? yp0 + j->y_stride : yp0;
       uint8_t* ap1 = has_row1 ? ap0 + j->a_stride : ap0;   // a_ptr2 = a_ptr on the last row (:228)
-      const uint2 a0 = *reinterpret_cast<const uint2*>(ap0), a1 = *reinterpret_cast<const uint2*>(ap1);
-      const uint2 y0v = *reinterpret_cast<const uint2*>(yp0);
-      *reinterpret_cast<uint2*>(yp0) = make_uint2(blend_luma4(y0v.x, a0.x, Y0), blend_luma4(y0v.y, a0.y, Y0));
-      if (has_row1) {
-        const uint2 y1v = *reinterpret_cast<const uint2*>(yp1);
-        *reinterpret_cast<uint2*>(yp1) = make_uint2(blend_luma4(y1v.x, a1.x, Y0), blend_luma4(y1v.y, a1.y, Y0));
-      }
       uint8_t* up = j->u + (ptrdiff_t)rp * j->uv_stride + cx0;
       uint8_t* vp = j->v + (ptrdiff_t)rp * j->uv_stride + cx0;
+      // every load of the unit before its first store (the planes may alias as far as the compiler knows,
+      // so a store in between would split the loads into three dependent round trips)
+      const uint2 a0 = *reinterpret_cast<const uint2*>(ap0), a1 = *reinterpret_cast<const uint2*>(ap1);
+      const uint2 y0v = *reinterpret_cast<const uint2*>(yp0);
+      const uint2 y1v = *reinterpret_cast<const uint2*>(yp1);
       const uint32_t u4 = *reinterpret_cast<const uint32_t*>(up), v4 = *reinterpret_cast<const uint32_t*>(vp);
+      *reinterpret_cast<uint2*>(yp0) = make_uint2(blend_luma4(y0v.x, a0.x, Y0), blend_luma4(y0v.y, a0.y, Y0));
+      if (has_row1) *reinterpret_cast<uint2*>(yp1) = make_uint2(blend_luma4(y1v.x, a1.x, Y0), blend_luma4(y1v.y, a1.y, Y0));
       // per chroma sample: alpha summed over its 2x2 block (pairs of bytes of both rows)
       uint32_t un = 0, vn = 0;
 #pragma unroll
@@ -439,7 +484,7 @@ extern "C" int b2_picture_cleanup_transparent(b2_ctx* ctx, int stream, const b2_
   if (tot == 0) return B2_OK;   // images lower than one block row: nothing to clean
   const int grid = b2_grid_for(ctx, 4, (tot + kWarps - 1) / kWarps);
   if (use_argb) cleanup_argb_kernel<<<grid, kThreads, 0, ctx->streams[stream]>>>(dj, dp, (uint32_t)n_jobs, uni, tot);
-  else cleanup_yuva_kernel<<<b2_grid_for(ctx, 5, (tot + kWarps - 1) / kWarps), kThreads, 0, ctx->streams[stream]>>>(dj, dp, (uint32_t)n_jobs, uni, tot);
+  else cleanup_yuva_kernel<<<b2_grid_for(ctx, B2_CLEANUP_CTAS, (tot + kWarps - 1) / kWarps), kThreads, 0, ctx->streams[stream]>>>(dj, dp, (uint32_t)n_jobs, uni, tot);
   ctx->launches++;
   B2_CUDA(ctx, cudaGetLastError());
   return B2_OK;

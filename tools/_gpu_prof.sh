@@ -1,3 +1,3 @@
 #!/bin/bash
-B2_FRAMES=64 ncu --set full --import-source on --clock-control none -k regex:unfilter_rows -c 1 -s 1 -o gpurun_out/r02b_unfilter_rows python tools/quick_bench.py filters > gpurun_out/r02b_rows_ncu.log 2>&1
-tail -2 gpurun_out/r02b_rows_ncu.log
+B2_FRAMES=64 ncu --set full --import-source on --clock-control none -k regex:cleanup_yuva -c 1 -s 2 -o gpurun_out/r02c_cleanup python tools/quick_bench.py tools > gpurun_out/r02c_cleanup_ncu.log 2>&1
+tail -2 gpurun_out/r02c_cleanup_ncu.log

@@ -153,10 +153,55 @@ __device__ __forceinline__ void forward4(const uint32_t (&cur)[4], const uint32_
   }
 }
 
+// Rows y_first, y_first + 4, ... < y_end of one lane's 4-pixel column, all in one mode tile row (mode known at
+// compile time); whole groups, 16-byte aligned rows.  NOT unrolled: with the row loop unrolled twice the fourteen
+// instantiations no longer fit the instruction cache (0.51 of the peak instead of 0.72, profiles/r02c_predictor_forward.md);
+// prefetch.global.L2 of the rows 1..8 passes ahead was measured at 0.57..0.46.
+#ifndef B2_FWD_SEGMENTS
+#define B2_FWD_SEGMENTS 1
+#endif
+#ifndef B2_FWD_SEG_UNROLL
+#define B2_FWD_SEG_UNROLL 1
+#endif
+constexpr int kFwdSegUnroll = B2_FWD_SEG_UNROLL;
+template <int MODE>
+__device__ __forceinline__ void forward_rows(const uint32_t* __restrict__ a, uint32_t* __restrict__ dst, int w, int x,
+                                             int y_first, int y_end, size_t step) {
+  const uint32_t* ap = a + (size_t)y_first * w + x;
+  uint32_t* dp = dst + (size_t)y_first * w + x;
+#pragma unroll kFwdSegUnroll
+  for (int y = y_first; y < y_end; y += 4, ap += step, dp += step) {
+    const uint4 cv = b2_ldg_stream_v4(ap);
+    const uint32_t cur[4] = {cv.x, cv.y, cv.z, cv.w};
+    uint32_t o[4];
+    if (y == 0) {  // first row = L, first pixel = black (lossless_enc.go / predictor_enc.go:683-689)
+      uint32_t l = (x == 0) ? 0xff000000u : __ldg(ap - 1);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { o[k] = sub_pixels(cur[k], l); l = cur[k]; }
+    } else {
+      uint32_t up[6];
+      const uint4 uv = __ldg(reinterpret_cast<const uint4*>(ap - w));
+      up[1] = uv.x; up[2] = uv.y; up[3] = uv.z; up[4] = uv.w;
+      // the neighbours a mode does not look at are not loaded
+      constexpr bool kNeedL = MODE == 1 || MODE == 5 || MODE == 6 || MODE == 7 || MODE == 10 || MODE == 11 || MODE == 12 || MODE == 13;
+      constexpr bool kNeedTL = MODE == 4 || MODE == 6 || MODE == 8 || MODE == 10 || MODE == 11 || MODE == 12 || MODE == 13;
+      constexpr bool kNeedTR = MODE == 3 || MODE == 5 || MODE == 9 || MODE == 10;
+      up[0] = (kNeedTL && x != 0) ? __ldg(ap - w - 1) : 0u;
+      up[5] = kNeedTR ? __ldg(ap - w + 4) : 0u;   // upper[x + 1] of the last column is the first pixel of the current row
+      const uint32_t l0 = (kNeedL && x != 0) ? __ldg(ap - 1) : 0u;
+      forward4<MODE>(cur, up, l0, x == 0, o);
+    }
+    b2_stg_stream_v4(dp, make_uint4(o[0], o[1], o[2], o[3]));
+  }
+}
+
 // ---- forward ----------------------------------------------------------------------
 constexpr int kFwdThreads = 256;
 constexpr int kFwdBlock = 256;  // item = a 256-pixel wide, kFwdRows tall block of one image: a warp per 32-pixel
-constexpr int kFwdRows = 64;    // column, 4 rows per pass
+#ifndef B2_FWD_ROWS
+#define B2_FWD_ROWS 64
+#endif
+constexpr int kFwdRows = B2_FWD_ROWS;    // column, 4 rows per pass
 // A CTA takes a 256-pixel wide block (1 KB of every row it touches), a warp a 32-pixel
 // column of it, 4 rows per pass, a lane 4 consecutive pixels of one row: a warp-wide
 // access is four whole 128-byte lines.  With the reference's usual tile
@@ -191,6 +236,27 @@ predictor_forward_kernel(const PredJobDev* __restrict__ jobs, const uint32_t* __
     const uint32_t tiles_per_row = j->tiles_per_row;
     uint32_t* __restrict__ dst = j->dst;
     const int y_end = min(h, by0 + kFwdRows);
+    if (B2_FWD_SEGMENTS && ((w & 3) == 0) && (((((uintptr_t)a) | ((uintptr_t)j->dst)) & 15) == 0)) {
+      // Whole 4-pixel groups on 16-byte aligned rows: the rows of the block are walked one mode-tile row at a
+      // time, with the mode looked up once per segment and the dispatch OUTSIDE the row loop, so the loop body
+      // is straight-line code for one predictor (no mode load, no branch tree and no address rebuild per row)
+      // and a row's loads are not held up behind the previous row's dispatch.
+      const int ry = lane >> 3;
+      const size_t step = 4 * (size_t)w;
+      for (int ys = by0; ys < y_end; ys = ((ys >> mode_shift) + 1) << mode_shift) {
+        const int ye = min(y_end, ((ys >> mode_shift) + 1) << mode_shift);
+        const uint32_t mode = (__ldg(mode_col + (size_t)((uint32_t)ys >> mode_shift) * tiles_per_row) >> 8) & 0xf;
+        const int y_first = ys + ry;
+        switch (mode) {
+#define B2_FWD_CASE(M) case M: forward_rows<M>(a, dst, w, x, y_first, ye, step); break;
+          B2_FWD_CASE(1) B2_FWD_CASE(2) B2_FWD_CASE(3) B2_FWD_CASE(4) B2_FWD_CASE(5) B2_FWD_CASE(6) B2_FWD_CASE(7)
+          B2_FWD_CASE(8) B2_FWD_CASE(9) B2_FWD_CASE(10) B2_FWD_CASE(11) B2_FWD_CASE(12) B2_FWD_CASE(13)
+#undef B2_FWD_CASE
+          default: forward_rows<0>(a, dst, w, x, y_first, ye, step); break;
+        }
+      }
+      continue;
+    }
 #pragma unroll kFwdUnroll
     for (int y = by0 + (lane >> 3); y < y_end; y += 4) {
     const size_t p0 = (size_t)y * w + x;

@@ -604,7 +604,7 @@ def test_convert_from_bgra(gpu, mode):
 def test_alpha_multiplies(gpu):
     D = gpu["dsp"]
     rng = np.random.default_rng(31)
-    for (w, h) in [(1, 1), (5, 3), (64, 4), (130, 2)]:
+    for (w, h) in [(1, 1), (5, 3), (64, 4), (130, 2), (512, 3), (1040, 2), (1536, 2)]:   # the last three: whole 512-sample items
         rgba = rng.integers(0, 256, (h, 4 * w + 8), dtype=np.uint8)   # stride > 4 w
         rgba[:, 3::4][rng.random((h, rgba[:, 3::4].shape[1])) < 0.3] = 255
         for af in (0, 1):

@@ -598,6 +598,9 @@ rescale_shrink_fast_kernel(const RescaleJobDev* __restrict__ jobs, const uint32_
 // memory in one wave of 16-byte cp.async.  A thread's four output columns take their left / right samples
 // (ImportRowExpand :39-72) from the two aligned words that hold them (byte permutes computed once per
 // unit), the row walk is `advance while have < last`, the vertical blend is two 32 x 32 -> 64 products.
+#ifndef B2_RESCALE_ONE_PRODUCT
+#define B2_RESCALE_ONE_PRODUCT 1
+#endif
 struct ExpAct { uint32_t B; int32_t last; };      // last < 0: the row is never exported; B == 0: y_accum == 0 (J = frow)
 constexpr int kERows = 40;
 constexpr int kESeg = kFT * kCols + 64;
@@ -701,7 +704,15 @@ rescale_expand_fast_kernel(const RescaleJobDev* __restrict__ jobs, const uint32_
         uint32_t J = f[k];
         if (a.B != 0u) {                          // y_accum != 0: blend with the previous row's frow (zero above the plane)
           const uint32_t i = (a.last > 0) ? g[k] : 0u;
+#if B2_RESCALE_ONE_PRODUCT
+          // A * f + B * i with A = 2^32 - B (rescaler.c.go:121-124) is 2^32 * f + B * (i - f): ONE 32 x 32 -> 64 product
+          // instead of two.  i - f wraps when it is negative, which adds B * 2^32 to the product: taken off the high word.
+          const uint32_t du = i - f[k];
+          const uint32_t hi = (uint32_t)(((uint64_t)a.B * du + kRounder) >> 32);
+          J = f[k] + hi - (a.B & (uint32_t)((int32_t)du >> 31));
+#else
           J = (uint32_t)(((uint64_t)(uint32_t)(kOne - a.B) * f[k] + (uint64_t)a.B * i + kRounder) >> 32);
+#endif
         }
         v[k] = min(mult_fix(J, fy_scale), 255u);
       }

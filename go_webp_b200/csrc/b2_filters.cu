@@ -71,6 +71,51 @@ __device__ __forceinline__ uint32_t filter_pred4(int filter, bool top_row, uint3
 #define B2_FWDF_CTAS 4
 #endif
 constexpr int kFwdRows = B2_FWD_ROWS;
+// A whole 512-pixel unit on 16-byte aligned rows, the filter known at compile time: the loads of the unit's rows (and
+// of the row above it for the vertical / gradient filters) first, then straight-line code per row -- the generic body
+// below tests the filter, the alignment and the lane's share of the row for every word (10 instructions per pixel,
+// issue slots 65 % busy on a kernel that only moves 2 B/px).
+#ifndef B2_FWDF_FAST
+#define B2_FWDF_FAST 1
+#endif
+template <int F>
+__device__ __forceinline__ void forward_unit_fast(const FiltJobDev& j, int y0, int ny, int x0, int lane) {
+  const bool live = x0 < j.width;   // the row may end before this lane's 16 pixels (never inside them: width % 16 == 0)
+  const uint8_t* p = j.src + (ptrdiff_t)y0 * j.src_stride + x0;
+  uint8_t* d = j.dst + (ptrdiff_t)y0 * j.dst_stride + x0;
+  uint4 c[kFwdRows + 1];
+  c[0] = make_uint4(0u, 0u, 0u, 0u);
+  if (F >= 2 && y0 > 0 && live) c[0] = __ldg(reinterpret_cast<const uint4*>(p - j.src_stride));
+#pragma unroll
+  for (int r = 0; r < kFwdRows; ++r) {
+    c[r + 1] = make_uint4(0u, 0u, 0u, 0u);
+    if (r < ny && live) c[r + 1] = __ldg(reinterpret_cast<const uint4*>(p + (ptrdiff_t)r * j.src_stride));
+  }
+#pragma unroll
+  for (int r = 0; r < kFwdRows; ++r) {
+    if (r >= ny) break;
+    const int y = y0 + r;
+    const uint32_t cw[4] = {c[r + 1].x, c[r + 1].y, c[r + 1].z, c[r + 1].w};
+    const uint32_t t[4] = {c[r].x, c[r].y, c[r].z, c[r].w};
+    uint32_t left = __shfl_up_sync(0xffffffffu, cw[3] >> 24, 1);
+    uint32_t up_left = (F == 3) ? __shfl_up_sync(0xffffffffu, t[3] >> 24, 1) : 0u;
+    if (lane == 0) {   // the byte before the unit comes from memory (zero at the row start)
+      left = x0 > 0 ? p[(ptrdiff_t)r * j.src_stride - 1] : 0u;
+      if (F == 3) up_left = (x0 > 0 && y > 0) ? p[(ptrdiff_t)(r - 1) * j.src_stride - 1] : 0u;
+    }
+    uint32_t o[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint32_t pred = filter_pred4(F, y == 0, cw[q], left, t[q], up_left);
+      if (q == 0 && x0 == 0) pred = (pred & 0xffffff00u) | (y == 0 ? 0u : (uint32_t)p[(ptrdiff_t)(r - 1) * j.src_stride]);   // leftmost pixel: as is / from above
+      o[q] = __vsub4(cw[q], pred);
+      left = cw[q] >> 24;
+      if (F == 3) up_left = t[q] >> 24;
+    }
+    if (live) *reinterpret_cast<uint4*>(d + (ptrdiff_t)r * j.dst_stride) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, B2_FWDF_CTAS)
 alpha_filter_kernel(const FiltJobDev* __restrict__ jobs, const uint32_t* __restrict__ prefix, uint32_t n_jobs,
                     uint32_t uniform, uint32_t total) {
@@ -87,6 +132,12 @@ alpha_filter_kernel(const FiltJobDev* __restrict__ jobs, const uint32_t* __restr
     const uintptr_t bits = ((uintptr_t)j.src | (uintptr_t)j.dst) | (uint32_t)j.src_stride | (uint32_t)j.dst_stride;
     const bool aligned = (bits & 3) == 0, al16 = (bits & 15) == 0;
     const bool vec = aligned && x0 + kFwdLane <= j.width;
+    if (B2_FWDF_FAST && al16 && (j.width & 15) == 0 && j.filter >= 1 && j.filter <= 3) {   // warp-uniform
+      if (j.filter == 1) forward_unit_fast<1>(j, y0, ny, x0, lane);
+      else if (j.filter == 2) forward_unit_fast<2>(j, y0, ny, x0, lane);
+      else forward_unit_fast<3>(j, y0, ny, x0, lane);
+      continue;
+    }
     // the group's rows and the row above it (vertical / gradient), all requested before the first is used
     uint32_t c[kFwdRows + 1][4];
     auto row_words = [&](int y, uint32_t (&w)[4]) {

@@ -948,6 +948,13 @@ def test_alpha_filters(gpu, golden_dir):
         un = F.AlphaUnfilterBatch(planes, [3] * len(planes), row_align=row_align)
         for p, o in zip(planes, un):
             assert (o == oracle.alpha_unfilter(p, 3)).all(), (p.shape, row_align)
+    # forward filters on 16-byte aligned rows whose width is a multiple of 16 (the templated whole-unit path): every
+    # filter, rows shorter than / equal to / longer than a 512-pixel unit, groups of 4 rows with a short last group
+    planes = [rng.integers(0, 256, (h, w), dtype=np.uint8) for (w, h) in [(1920, 37), (2048, 9), (528, 70), (512, 4), (16, 5), (1040, 3)]]
+    for f in (1, 2, 3):
+        fw = F.AlphaFilterBatch(planes, [f] * len(planes), row_align=16)
+        for p, o in zip(planes, fw):
+            assert (o == oracle.alpha_filter(p, f)).all(), (p.shape, f)
     # more gradient planes than resident CTAs (2 per SM): a CTA goes through several planes, its shared progress
     # words, ring and tiles are reused from plane to plane
     planes = [rng.integers(0, 256, (33 + (i % 5) * 16, 60 + (i % 7) * 8), dtype=np.uint8) for i in range(700)]

@@ -315,7 +315,7 @@ static int import_impl(b2_ctx* ctx, int stream, const b2_import_job* jobs, int n
   uint32_t* pre = (uint32_t*)(host + ((jb + 15) & ~(size_t)15));
   uint32_t* upre = (uint32_t*)((uint8_t*)pre + pb);  // prefix in row pairs (fast kernel)
   bool fast = (step == 4);
-  bool tuned = (step == 4);   // b2_import_fast.cu preconditions
+  bool tuned = true;          // b2_import_fast.cu preconditions (3-byte pixels: rows of any alignment)
   bool unaligned = false;     // some source row is not 16-byte aligned
   int n_with_a = 0;
   uint64_t total = 0, utotal = 0;
@@ -341,7 +341,7 @@ static int import_impl(b2_ctx* ctx, int stream, const b2_import_job* jobs, int n
     if ((((uintptr_t)j.u | (uintptr_t)j.v | (uintptr_t)(uint32_t)j.uv_stride) & 1) == 0) d.flags |= JOB_UV_ALIGNED;
     if ((((uintptr_t)j.src | (uintptr_t)(uint32_t)j.src_stride) & 3) != 0) fast = false;
     if ((((uintptr_t)j.src | (uintptr_t)(uint32_t)j.src_stride) & 15) != 0) unaligned = true;
-    if ((((uintptr_t)j.src | (uintptr_t)(uint32_t)j.src_stride) & 3) != 0 ||
+    if ((step == 4 && (((uintptr_t)j.src | (uintptr_t)(uint32_t)j.src_stride) & 3) != 0) ||
         !(d.flags & JOB_Y_ALIGNED) || !(d.flags & JOB_UV_ALIGNED) || (j.a && !(d.flags & JOB_A_ALIGNED))) tuned = false;
     n_with_a += (j.a != NULL);
     const uint32_t units = (uint32_t)((j.height + 1) >> 1);

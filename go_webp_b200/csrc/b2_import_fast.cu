@@ -202,6 +202,11 @@ __device__ __forceinline__ void cp_async16_full(uint32_t dst, const void* src) {
 __device__ __forceinline__ void cp_async4(uint32_t dst, const void* src, uint32_t nbytes) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(dst), "l"(src), "r"(nbytes) : "memory");
 }
+__device__ __forceinline__ uint32_t lds32_ring(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ uint4 lds128_ring(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
@@ -213,7 +218,14 @@ __device__ __forceinline__ uint4 lds128_ring(uint32_t addr) {
 // chunk 32 t + 32 as well -- and takes its four pixels out of its own chunk and the next one (two 128-bit
 // shared loads and a register shift by the row's misalignment, warp-uniform) instead of fetching 4 bytes at
 // a time: 0.55 -> 0.8 of the measured peak on such images (profiles/r02c_mixed_sizes.md).
-template <int ORDER, bool ALPHA, bool WRITE_A, bool TABLE, bool DITHER, bool UNAL>
+// STEP3: 3-byte pixels (WebPPictureImportRGB / BGR, picture_csp_enc.c.go step = 3), rows of any byte alignment.  The
+// same enclosing-chunk fetch -- a strip of 128 pixels is 384 bytes = 24 chunks (+ 1 when the row does not start on a
+// 16-byte boundary), lanes 0 .. 24 fetch one each -- and a lane takes its 12 bytes from the stage with four aligned
+// 32-bit shared loads (lane stride 3 words: conflict-free), three funnel shifts by the row's byte misalignment and
+// three byte permutes that spread them into four 4-byte pixels; from there on the code is the 4-byte kernel's (the
+// fourth byte of a pixel is never looked at when no alpha is imported).  Was import_generic_kernel: a byte load per
+// channel, 0.32 of the measured peak.
+template <int ORDER, bool ALPHA, bool WRITE_A, bool TABLE, bool DITHER, bool UNAL, bool STEP3 = false>
 __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm)
 import_fast_kernel(const ImportJobDev* __restrict__ jobs, const uint32_t* __restrict__ unit_prefix,
                    uint32_t n_jobs, uint32_t uniform_units, uint32_t total_units,
@@ -278,7 +290,7 @@ import_fast_kernel(const ImportJobDev* __restrict__ jobs, const uint32_t* __rest
     // odd last row: the source row is duplicated (yuv.go:377), so row 1 of every output is
     // the same as row 0 and is written over it
     const int ystride = has_row1 ? jp->y_stride : 0;
-    const uint8_t* const s0 = jp->src + (ptrdiff_t)y0 * sstride + lane * 16 + phase * 512;
+    const uint8_t* const s0 = jp->src + (ptrdiff_t)y0 * sstride + (STEP3 ? 0u : lane * 16 + phase * 512);
     const uint8_t* const s1 = has_row1 ? s0 + sstride : s0;
     uint8_t* yp = jp->y + (ptrdiff_t)y0 * jp->y_stride + lane4 + phase * 128;
     uint8_t* ap = nullptr;
@@ -322,14 +334,21 @@ import_fast_kernel(const ImportJobDev* __restrict__ jobs, const uint32_t* __rest
     // the others (dithered import only) fetch 4 bytes at a time and take the general code.
     const bool al16 = ((((uintptr_t)jp->src) | (uintptr_t)(uint32_t)sstride) & 15) == 0;  // warp-uniform
     const int tiles_x = (width + 127) >> 7;
-    const int full = (UNAL || al16) ? (width >> 7) : 0;
+    const int full = (UNAL || STEP3 || al16) ? (width >> 7) : 0;
     const uint8_t* g0 = s0;
     const uint8_t* g1 = s1;
     // UNAL: m = pixels between the enclosing aligned address and the row start (0..3), g = this lane's
     // chunk of that aligned span, rem = bytes from the start of the chunk to the end of the row
     uint32_t m0 = 0, m1 = 0;
     int rem0 = 0, rem1 = 0;
-    if (UNAL) {
+    if (STEP3) {   // m = BYTES between the enclosing aligned address and the row start (0..15)
+      m0 = (uint32_t)(uintptr_t)s0 & 15u;
+      m1 = (uint32_t)(uintptr_t)s1 & 15u;
+      g0 = s0 - m0 + 16 * lane;
+      g1 = s1 - m1 + 16 * lane;
+      rem0 = 3 * width + (int)m0 - 16 * (int)lane;
+      rem1 = 3 * width + (int)m1 - 16 * (int)lane;
+    } else if (UNAL) {
       m0 = ((uint32_t)(uintptr_t)s0 >> 2) & 3u;
       m1 = ((uint32_t)(uintptr_t)s1 >> 2) & 3u;
       g0 = s0 - 4 * m0;
@@ -339,7 +358,15 @@ import_fast_kernel(const ImportJobDev* __restrict__ jobs, const uint32_t* __rest
     }
     uint32_t wr = slot0, rd = slot0;
     auto issue = [&](int t) {  // one commit group per call, possibly empty
-      if (UNAL) {
+      if (STEP3) {
+        if (t < tiles_x) {   // chunk 24 t + lane of both rows, lanes 0 .. 24; only bytes inside the row are read
+          if (lane < 25) {
+            if (rem0 > 0) cp_async16(wr, g0, (uint32_t)min(rem0, 16));
+            if (rem1 > 0) cp_async16(wr + kRow1, g1, (uint32_t)min(rem1, 16));
+          }
+          rem0 -= 384; rem1 -= 384;
+        }
+      } else if (UNAL) {
         if (t < tiles_x) {
           // chunk 32 t + lane of both rows, lane 0 chunk 32 t + 32 too; only bytes inside the row are read
           // (the rest of a chunk is zero-filled).  A chunk past the row is not fetched at all: its lanes
@@ -373,7 +400,16 @@ import_fast_kernel(const ImportJobDev* __restrict__ jobs, const uint32_t* __rest
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
       wr = slot_sum - wr;
-      g0 += 512 * kSplit; g1 += 512 * kSplit;
+      g0 += (STEP3 ? 384 : 512) * kSplit; g1 += (STEP3 ? 384 : 512) * kSplit;
+    };
+    // STEP3: the lane's 12 bytes start m + 12 lane bytes into the stage row
+    auto unpack3 = [&](uint32_t row_addr, uint32_t m) -> uint4 {
+      const uint32_t off = m + 12u * lane;
+      const uint32_t a = row_addr + (off & ~3u), sh = 8u * (off & 3u);
+      const uint32_t w0 = lds32_ring(a), w1 = lds32_ring(a + 4u), w2 = lds32_ring(a + 8u), w3 = lds32_ring(a + 12u);
+      const uint32_t b0 = __funnelshift_r(w0, w1, sh), b1 = __funnelshift_r(w1, w2, sh), b2 = __funnelshift_r(w2, w3, sh);
+      // pixels = bytes 0-2, 3-5, 6-8, 9-11; the top byte of each word is whatever comes next (never used)
+      return make_uint4(b0, __byte_perm(b0, b1, 0x6543), __byte_perm(b1, b2, 0x5432), __byte_perm(b2, 0u, 0x0321));
     };
     // UNAL: the lane's four pixels start m words into its chunk and end in the next one
     auto shifted = [&](uint4& c, uint32_t next_addr, uint32_t m) {
@@ -388,8 +424,14 @@ import_fast_kernel(const ImportJobDev* __restrict__ jobs, const uint32_t* __rest
       constexpr bool FULL = decltype(full_tag)::value;
       issue(t + kDist * kSplit);
       asm volatile("cp.async.wait_group %0;" :: "n"(kDist) : "memory");
-      uint4 c0 = lds128_ring(rd);
-      uint4 c1 = lds128_ring(rd + kRow1);
+      uint4 c0, c1;
+      if (STEP3) {
+        c0 = unpack3(rd - 16u * lane, m0);
+        c1 = unpack3(rd - 16u * lane + kRow1, m1);
+      } else {
+        c0 = lds128_ring(rd);
+        c1 = lds128_ring(rd + kRow1);
+      }
       if (UNAL) {
         shifted(c0, rd + 16, m0);
         shifted(c1, rd + kRow1 + 16, m1);
@@ -513,9 +555,9 @@ struct FastArgs {
   uint32_t* tickets;
   bool unaligned;
 };
-template <int ORDER, bool ALPHA, bool WRITE_A, bool TABLE, bool DITHER, bool UNAL>
+template <int ORDER, bool ALPHA, bool WRITE_A, bool TABLE, bool DITHER, bool UNAL, bool STEP3 = false>
 cudaError_t launch3(const FastArgs& a) {
-  auto k = import_fast_kernel<ORDER, ALPHA, WRITE_A, TABLE, DITHER, UNAL>;
+  auto k = import_fast_kernel<ORDER, ALPHA, WRITE_A, TABLE, DITHER, UNAL, STEP3>;
   const int smem = kSmemBytes + (DITHER ? kFastWarps * (int)kDitherWarpBytes : 0);
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
@@ -549,6 +591,11 @@ cudaError_t b2_import_fast_launch(const b2_ctx* ctx, cudaStream_t s, const Impor
   a.s = s; a.jobs = jobs; a.unit_prefix = unit_prefix; a.n_jobs = n_jobs; a.uniform_units = uniform_units;
   a.total_units = total_units; a.tab = ctx->tab_dev; a.has_alpha = has_alpha; a.dither = dither;
   a.tickets = tickets; a.unaligned = unaligned;
+  if (order == B2_ORDER_RGB || order == B2_ORDER_BGR) {   // 3-byte pixels: no alpha to import, no dithering here
+    if (alpha || dither.rng_states != nullptr) return cudaErrorInvalidValue;
+    if (order == B2_ORDER_RGB) return write_a ? launch3<0, false, true, false, false, false, true>(a) : launch3<0, false, false, false, false, false, true>(a);
+    return write_a ? launch3<1, false, true, false, false, false, true>(a) : launch3<1, false, false, false, false, false, true>(a);
+  }
 #define B2_GO(O, A, W) return launch<O, A, W>(a, div_table)
   if (order == B2_ORDER_RGBA) {
     if (alpha) { if (write_a) B2_GO(0, true, true); else B2_GO(0, true, false); }

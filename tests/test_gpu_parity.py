@@ -105,6 +105,30 @@ def test_import_orders_strides(gpu, order):
         check_import(pic2, oracle.import_yuva(src, w, h, order, stride=-stride), gpu)
 
 
+@pytest.mark.parametrize("order", ["RGB", "BGR"])
+def test_import_three_byte_pixels_fast_kernel(gpu, order):
+    """WebPPictureImportRGB / BGR through the tuned kernel (b2_import_fast.cu, STEP3): rows of every byte
+    alignment (stride = 3 w + pad), widths around the 128-pixel strip and the 16-byte chunk, one and many
+    rows, flipped buffers, several images per call."""
+    P = gpu["picture"]
+    rng = np.random.default_rng(33 + len(order))
+    cases = [(1, 1, 0), (2, 3, 1), (3, 2, 0), (5, 5, 2), (16, 4, 0), (21, 7, 5), (127, 3, 0), (128, 2, 0), (129, 5, 1),
+             (131, 4, 3), (256, 6, 0), (260, 3, 7), (515, 9, 0), (1030, 2, 2), (1920, 4, 0), (2050, 3, 1)]
+    srcs, pics, strides = [], [], []
+    for (w, h, pad) in cases:
+        stride = 3 * w + pad
+        srcs.append(rng.integers(0, 256, (h, stride), dtype=np.uint8))
+        pics.append(P.Picture(Width=w, Height=h))
+        strides.append(stride)
+    assert P.ImportRGBABatch(pics, srcs, strides, order) == 1
+    for pic, src, (w, h, pad), stride in zip(pics, srcs, cases, strides):
+        check_import(pic, oracle.import_yuva(src, w, h, order, stride=stride), gpu)
+    pics2 = [P.Picture(Width=w, Height=h) for (w, h, pad) in cases]
+    assert P.ImportRGBABatch(pics2, srcs, [-s for s in strides], order) == 1
+    for pic, src, (w, h, pad), stride in zip(pics2, srcs, cases, strides):
+        check_import(pic, oracle.import_yuva(src, w, h, order, stride=-stride), gpu)
+
+
 def test_import_golden_libwebp(gpu, golden_dir):
     """Against the libwebp 1.6.0 binary's outputs (table-divide mode)."""
     P = gpu["picture"]

@@ -612,6 +612,20 @@ def other_kernels(ctx, peak, steps):
         out[name] = {"frames": frames, "mpixel_per_s": px / ms / 1e3, "bytes_per_px": bpp,
                      "gbs": px * bpp / ms / 1e6, "frac": px * bpp / ms / 1e6 / peak}
         up.close()
+    # 3-byte imports (WebPPictureImportRGB / BGR: 3 B in, 1.5 B out per pixel), 128 x 1080p
+    al = lambda v: (v + 255) // 256 * 256  # noqa: E731
+    n3 = 128
+    s3, y3 = ctx.alloc(n3 * al(3 * W * H)), ctx.alloc(n3 * al(W * H))
+    u3, v3 = ctx.alloc(n3 * al(W * H // 4)), ctx.alloc(n3 * al(W * H // 4))
+    ctx.synth_fill(s3.ptr, (3 * W) // 4, H, 3 * W, al(3 * W * H), n3, SEED, 0, 4)
+    ctx.sync()
+    j3 = (_abi.ImportJob * n3)(*[_abi.ImportJob(s3.ptr + i * al(3 * W * H), y3.ptr + i * al(W * H), u3.ptr + i * al(W * H // 4),
+                                                 v3.ptr + i * al(W * H // 4), None, 3 * W, W, W // 2, 0, W, H) for i in range(n3)])
+    ms = timed(lambda: ctx._chk(ctx.lib.b2_rgba_to_yuv420a(ctx.h, 0, j3, n3, _abi.ORDER_RGB, 0, None)), k)
+    out["import_rgb_3_bytes_1080p"] = {"frames": n3, "mpixel_per_s": n3 * W * H / ms / 1e3, "bytes_per_px": 4.5,
+                                       "gbs": n3 * W * H * 4.5 / ms / 1e6, "frac": n3 * W * H * 4.5 / ms / 1e6 / peak}
+    for b in (s3, y3, u3, v3):
+        b.free()
     # picture pre-processing on the planes an import just wrote: binary alpha makes every
     # 8x8 block partially transparent (SmoothenBlock rewrites its luma: read A + Y, write Y = 3 B/px);
     # blend reads and writes Y, U, V, A (5 B/px on the first pass)

@@ -232,7 +232,8 @@ upsample_kernel(const UpsampleJobDev* __restrict__ jobs, const uint32_t* __restr
 template <int ST, bool HAS_ALPHA>
 __device__ __forceinline__ void emit_row8_packed(uint2 yw, uint2 aw, const uint32_t (&u2)[4],
                                                  const uint32_t (&v2)[4], uint8_t* dp, bool store_ok,
-                                                 const B2YuvConsts& kc, uint8_t* xs, uint32_t xw0, uint32_t xw1) {
+                                                 const B2YuvConsts& kc, uint8_t* xs, uint32_t xw0, uint32_t xw1,
+                                                 uint32_t sel16 = 0x7351u) {
   const uint32_t ye_x = b2_even(yw.x), yo_x = b2_odd(yw.x), ye_y = b2_even(yw.y), yo_y = b2_odd(yw.y);
   const uint32_t y2[4] = {b2_prmt(yo_x, yo_y, 0x5410), b2_prmt(ye_x, ye_y, 0x7632),
                           b2_prmt(yo_x, yo_y, 0x7632), b2_prmt(ye_x, ye_y, 0x5410)};
@@ -260,6 +261,20 @@ __device__ __forceinline__ void emit_row8_packed(uint2 yw, uint2 aw, const uint3
       const uint32_t gb = b2_prmt(g4, b4, 0x7351);                  // g b g' b'
       lo = b2_prmt(ar, gb, 0x5410);
       hi = b2_prmt(ar, gb, 0x7632);
+    } else if (ST == ST_565 || ST == ST_4444) {
+      // VP8YuvToRgb565 / VP8YuvToRgba4444 (conversion.go) on the pair: the 8-bit values sit in bytes 1 and 3.
+      // lo = the pair's two 16-bit pixels; sel16 puts the rg byte first (stock libwebp) or second (go-webp text)
+      uint32_t rg, gb;
+      if (ST == ST_565) {
+        rg = (r4 & 0xf800f800u) | ((g4 >> 5) & 0x07000700u);
+        gb = ((g4 << 3) & 0xe000e000u) | ((b4 >> 3) & 0x1f001f00u);
+      } else {
+        const uint32_t a2 = HAS_ALPHA ? b2_prmt(ap, 0u, k0 ? 0x1404 : 0x3424) : 0xff00ff00u;   // EmitAlphaRGBA4444's nibble
+        rg = (r4 & 0xf000f000u) | ((g4 >> 4) & 0x0f000f00u);
+        gb = (b4 & 0xf000f000u) | ((a2 >> 4) & 0x0f000f00u);
+      }
+      lo = b2_prmt(rg, gb, sel16);
+      hi = 0u;
     } else {  // ST_RGB / ST_BGR: three bytes per pixel, byte 3 is dropped below
       const uint32_t c0 = (ST == ST_RGB) ? r4 : b4, c2 = (ST == ST_RGB) ? b4 : r4;
       const uint32_t cg = b2_prmt(c0, g4, 0x7351);
@@ -270,7 +285,12 @@ __device__ __forceinline__ void emit_row8_packed(uint2 yw, uint2 aw, const uint3
     o[first] = lo;
     o[first + 4] = hi;
   }
-  if (ST == ST_RGB || ST == ST_BGR) {
+  if (ST == ST_565 || ST == ST_4444) {
+    // o[k] (k = 0..3) = pixels k and k + 4 as 16-bit halves; a lane's 8 pixels are 16 contiguous bytes and the
+    // lanes of a pass follow each other: one 128-bit store per lane covers 512 contiguous bytes per instruction
+    if (store_ok) b2_stg_stream_v4(dp, make_uint4(b2_prmt(o[0], o[1], 0x5410), b2_prmt(o[2], o[3], 0x5410),
+                                                   b2_prmt(o[0], o[1], 0x7632), b2_prmt(o[2], o[3], 0x7632)));
+  } else if (ST == ST_RGB || ST == ST_BGR) {
     uint32_t w[6];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -292,6 +312,10 @@ __device__ __forceinline__ void emit_row8_packed(uint2 yw, uint2 aw, const uint3
     *reinterpret_cast<uint4*>(xs + xw0) = make_uint4(o[0], o[1], o[2], o[3]);
     *reinterpret_cast<uint4*>(xs + xw1) = make_uint4(o[4], o[5], o[6], o[7]);
   }
+}
+
+template <int ST> __host__ __device__ constexpr int bulk_bpp() {
+  return (ST == ST_RGB || ST == ST_BGR) ? 3 : (ST == ST_565 || ST == ST_4444) ? 2 : 4;
 }
 
 // ---- bulk-copy (TMA) staged kernel -------------------------------------------------
@@ -384,10 +408,11 @@ __device__ __forceinline__ XposeLane xpose_lane(int lane) {
 template <int ST, bool HAS_ALPHA, bool EDGE>
 __device__ __forceinline__ void convert_pass(const uint8_t* sy, const uint8_t* sa, const uint8_t* sc, int lane,
                                              int xpass, int wv, int uw, bool top_ok, bool bot_ok, uint8_t* drt,
-                                             uint8_t* drb, const B2YuvConsts& kc, uint8_t* xs, const XposeLane& xl) {
+                                             uint8_t* drb, const B2YuvConsts& kc, uint8_t* xs, const XposeLane& xl,
+                                             uint32_t sel16) {
   constexpr int R = BulkLayout<HAS_ALPHA>::kCRow;
   constexpr int kTileW = BulkLayout<HAS_ALPHA>::kTW;
-  constexpr int kBpp = (ST == ST_RGB || ST == ST_BGR) ? 3 : 4;
+  constexpr int kBpp = bulk_bpp<ST>();
   const int xh = xpass + lane * 8;
   constexpr int loff = -1, roff = 4;  // left / right neighbour samples; the image edges are fixed up below
   const uint2 yt = *reinterpret_cast<const uint2*>(sy);
@@ -440,13 +465,13 @@ __device__ __forceinline__ void convert_pass(const uint8_t* sy, const uint8_t* s
     const uint32_t xc = b2_hi8(cq.ts);
     const uint32_t u2[4] = {b2_hi8(au.tf), b2_hi8(au.ts), b2_hi8(bu.tf), b2_prmt(xc, b2_hi8(bu.ts), 0x5410)};
     const uint32_t v2[4] = {b2_hi8(av.tf), b2_hi8(av.ts), b2_hi8(bv.tf), b2_prmt(xc, b2_hi8(bv.ts), 0x5432)};
-    emit_row8_packed<ST, HAS_ALPHA>(yt, at, u2, v2, drt + xh * kBpp, lane_ok, kc, xst, xw0, xl.w1);
+    emit_row8_packed<ST, HAS_ALPHA>(yt, at, u2, v2, drt + xh * kBpp, lane_ok, kc, xst, xw0, xl.w1, sel16);
   }
   if (bot_ok) {
     const uint32_t xc = b2_hi8(cq.bs);
     const uint32_t u2[4] = {b2_hi8(au.bf), b2_hi8(au.bs), b2_hi8(bu.bf), b2_prmt(xc, b2_hi8(bu.bs), 0x5410)};
     const uint32_t v2[4] = {b2_hi8(av.bf), b2_hi8(av.bs), b2_hi8(bv.bf), b2_prmt(xc, b2_hi8(bv.bs), 0x5432)};
-    emit_row8_packed<ST, HAS_ALPHA>(yb, ab, u2, v2, drb + xh * kBpp, lane_ok, kc, xst ? xst + 1024 : nullptr, xw0, xl.w1);
+    emit_row8_packed<ST, HAS_ALPHA>(yb, ab, u2, v2, drb + xh * kBpp, lane_ok, kc, xst ? xst + 1024 : nullptr, xw0, xl.w1, sel16);
   }
   if (kBpp == 4) {
     __syncwarp();
@@ -507,10 +532,10 @@ __device__ __forceinline__ void convert_pass(const uint8_t* sy, const uint8_t* s
 template <int ST, bool HAS_ALPHA>
 __device__ __forceinline__ void convert_pass_split(const uint8_t* sp_y, const uint8_t* sp_a, const uint8_t* sp_c, int lane,
                                                    int xpass, int wv, int uw, uint8_t* drt, uint8_t* drb,
-                                                   const B2YuvConsts& kc, uint8_t* xs, const XposeLane& xl) {
+                                                   const B2YuvConsts& kc, uint8_t* xs, const XposeLane& xl, uint32_t sel16) {
   constexpr int R = BulkLayout<HAS_ALPHA>::kCRow;
   constexpr int kTileW = BulkLayout<HAS_ALPHA>::kTW;
-  constexpr int kBpp = (ST == ST_RGB || ST == ST_BGR) ? 3 : 4;
+  constexpr int kBpp = bulk_bpp<ST>();
   const int l = lane & 15;
   const bool bot = lane >= 16;
   const int xh = xpass + l * 8;
@@ -552,7 +577,7 @@ __device__ __forceinline__ void convert_pass_split(const uint8_t* sp_y, const ui
   const uint32_t xw0 = ((2u * l) ^ sw) * 16u, xw1 = ((2u * l + 1u) ^ sw) * 16u;
   uint8_t* const drow = bot ? drb : drt;
   emit_row8_packed<ST, HAS_ALPHA>(yw, aw, u2, v2, drow + xh * kBpp, lane_ok, kc,
-                                  (kBpp == 4) ? xs + (bot ? 1024 : 0) : nullptr, xw0, xw1);
+                                  (kBpp == 4) ? xs + (bot ? 1024 : 0) : nullptr, xw0, xw1, sel16);
   if (kBpp == 4) {
     __syncwarp();
     const int xa = xpass + lane * 4;   // every lane stores pixels xa .. xa+3 of BOTH rows: 512 contiguous bytes per store
@@ -689,8 +714,9 @@ upsample_bulk_kernel(const UpsampleJobDev* __restrict__ jobs, const uint32_t* __
     const int row_begin = jp->row_begin, row_end = jp->row_end;
     const bool top_ok = (rt >= row_begin) && (rt < row_end), bot_ok = (rb >= row_begin) && (rb < row_end);
     const int dstride = jp->dst_stride;
-    constexpr int kBppK = (ST == ST_RGB || ST == ST_BGR) ? 3 : 4;
+    constexpr int kBppK = bulk_bpp<ST>();
     const int wv = (kBppK == 4) ? width : (width & ~7);  // the vector path covers pixels [0, wv)
+    const uint32_t sel16 = (jp->flags & JOB_SWAP16) ? 0x3715u : 0x7351u;   // 16-bit modes: which byte of a pixel comes first
     uint8_t* const drt = jp->dst + (ptrdiff_t)(top_ok ? rt : rb) * dstride;
     uint8_t* const drb = jp->dst + (ptrdiff_t)(bot_ok ? rb : rt) * dstride;
     const int tiles = (width + kTileW - 1) / kTileW;
@@ -708,16 +734,16 @@ upsample_bulk_kernel(const UpsampleJobDev* __restrict__ jobs, const uint32_t* __
         const uint8_t* sc = sp + BL::kC + 16 + p * 128 + lane * 4;
         if (top_ok && bot_ok && wv - xpass <= 128)   // warp-uniform: a last pass of at most 128 pixels, both rows wanted
           convert_pass_split<ST, HAS_ALPHA>(sp + BL::kY + p * 256, sp + BL::kA + p * 256, sp + BL::kC + 16 + p * 128, lane,
-                                            xpass, wv, uw, drt, drb, kc, xbuf, xl);
+                                            xpass, wv, uw, drt, drb, kc, xbuf, xl, sel16);
         else if (xpass == 0 || xpass + 256 >= 2 * uw || xpass + 256 > wv)  // warp-uniform: first / last pass of the row
-          convert_pass<ST, HAS_ALPHA, true>(sy, sa, sc, lane, xpass, wv, uw, top_ok, bot_ok, drt, drb, kc, xbuf, xl);
+          convert_pass<ST, HAS_ALPHA, true>(sy, sa, sc, lane, xpass, wv, uw, top_ok, bot_ok, drt, drb, kc, xbuf, xl, sel16);
         else
-          convert_pass<ST, HAS_ALPHA, false>(sy, sa, sc, lane, xpass, wv, uw, top_ok, bot_ok, drt, drb, kc, xbuf, xl);
+          convert_pass<ST, HAS_ALPHA, false>(sy, sa, sc, lane, xpass, wv, uw, top_ok, bot_ok, drt, drb, kc, xbuf, xl, sel16);
       }
       __syncwarp();  // every lane is done reading this stage before it is refilled
       stage ^= 1;
     }
-    if (kBppK == 3 && wv + lane < width) {  // 3-byte modes: ragged right edge (width % 8 pixels), per pixel from global
+    if (kBppK != 4 && wv + lane < width) {  // 3- and 2-byte modes: ragged right edge (width % 8 pixels), per pixel from global
       const UpsampleJobDev j = *jp;
       if (top_ok) pixel_generic<ST>(j, rt, wv + lane);
       if (bot_ok) pixel_generic<ST>(j, rb, wv + lane);
@@ -768,7 +794,7 @@ extern "C" int b2_yuv420a_to_rgba_fancy(b2_ctx* ctx, int stream, const b2_upsamp
   uint32_t* upre = (uint32_t*)(host + pre_off + pb);  // prefix in row pairs (tuned kernel)
   uint64_t total = 0, utotal = 0;
   uint32_t uniform = 0, uuniform = 0;
-  bool tuned = (st_mode <= ST_BGR);  // 4- and 3-byte modes have a staged vector kernel
+  bool tuned = (st_mode <= ST_565);  // every mode has a staged vector kernel (4-, 3- and 2-byte pixels)
   bool staged = true;  // cp.async kernel: 16-byte aligned planes with positive strides
   int n_with_a = 0;
   int max_width = 0;
@@ -792,7 +818,7 @@ extern "C" int b2_yuv420a_to_rgba_fancy(b2_ctx* ctx, int stream, const b2_upsamp
     if (j.a != NULL && (((uintptr_t)j.a | (uintptr_t)(uint32_t)j.a_stride) & 7) != 0) fast = false;
     d.flags = (fast ? JOB_FAST : 0) | (ctx->swap16 ? JOB_SWAP16 : 0);
     if (!fast && bpp == 4) tuned = false;
-    if (bpp == 3 && ((((uintptr_t)j.dst | (uintptr_t)(uint32_t)j.dst_stride) & 15) != 0)) tuned = false;
+    if (bpp != 4 && ((((uintptr_t)j.dst | (uintptr_t)(uint32_t)j.dst_stride) & 15) != 0)) tuned = false;
     if ((((uintptr_t)j.y | (uintptr_t)j.u | (uintptr_t)j.v | (uintptr_t)j.a | (uintptr_t)(uint32_t)j.y_stride |
           (uintptr_t)(uint32_t)j.uv_stride | (uintptr_t)(uint32_t)(j.a ? j.a_stride : 0)) & 15) != 0 ||
         j.y_stride < 0 || j.uv_stride < 0 || (j.a && j.a_stride < 0)) staged = false;
@@ -818,7 +844,7 @@ extern "C" int b2_yuv420a_to_rgba_fancy(b2_ctx* ctx, int stream, const b2_upsamp
   }
   pre[n_jobs] = (uint32_t)total;
   upre[n_jobs] = (uint32_t)utotal;
-  if (n_with_a != 0 && n_with_a != n_jobs && bpp == 4) tuned = false;  // HAS_ALPHA is a kernel-wide switch
+  if (n_with_a != 0 && n_with_a != n_jobs && (bpp == 4 || st_mode == ST_4444)) tuned = false;  // HAS_ALPHA is a kernel-wide switch
   void* dev = NULL;
   int st = b2_upload_desc(ctx, stream, host, pre_off + 2 * pb, &dev);
   free(host);
@@ -845,7 +871,9 @@ extern "C" int b2_yuv420a_to_rgba_fancy(b2_ctx* ctx, int stream, const b2_upsamp
       case ST_BGRA: if (ha) B2_UPK(ST_BGRA, true); else B2_UPK(ST_BGRA, false); break;
       case ST_ARGB: if (ha) B2_UPK(ST_ARGB, true); else B2_UPK(ST_ARGB, false); break;
       case ST_RGB: B2_UPK(ST_RGB, false); break;
-      default: B2_UPK(ST_BGR, false); break;
+      case ST_BGR: B2_UPK(ST_BGR, false); break;
+      case ST_4444: if (ha) B2_UPK(ST_4444, true); else B2_UPK(ST_4444, false); break;   // the alpha nibble merged (EmitAlphaRGBA4444)
+      default: B2_UPK(ST_565, false); break;
     }
 #undef B2_UPK
     ctx->launches++;

@@ -527,7 +527,7 @@ def test_predictor_inverse_and_forward(gpu, bits):
     D = gpu["dsp"]
     rng = np.random.default_rng(100 + bits)
     for (w, h) in [(1, 1), (1, 5), (2, 2), (5, 1), (7, 9), (33, 34), (64, 65), (127, 3), (129, 40),
-                   (200, 33), (300, 70), (513, 97)]:
+                   (200, 33), (300, 70), (513, 97), (2, 40), (6, 33), (66, 70), (130, 64), (1026, 45), (2050, 35)]:   # the last six: even widths that are not multiples of 4 (pair-wise fast band)
         modes = _rand_modes(rng, w, h, bits)
         img = rng.integers(0, 2**32, (h, w), dtype=np.uint32)
         t = D.VP8LTransform(D.PREDICTOR_TRANSFORM, bits, w, h, modes)

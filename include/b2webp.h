@@ -45,7 +45,12 @@ typedef struct b2_ctx b2_ctx;
 int b2_abi_version(void);
 const char* b2_strerror(int status);
 int b2_device_count(int* count);
-/* One context per GPU.  n_streams in [1,16]. */
+/* One context per GPU.  n_streams in [1,16].  A context owns, per stream, a descriptor ring, a grow-only
+ * scratch area and a few work-counter words (the import and the fancy upsampler hand their row pairs out
+ * by ticket; the last warp of a launch clears the counters it used).  Consequence for callers: launches on
+ * ONE stream of ONE context must come from one host thread at a time (they are stream-ordered on the
+ * device); different streams and different contexts are independent.
+ * b2_device_count asks the driver again for up to 3 s when a box has only just come up. */
 int b2_ctx_create(int device, int n_streams, b2_ctx** out);
 void b2_ctx_destroy(b2_ctx* ctx);
 /* Byte order of the 16-bit output modes (MODE_RGBA_4444, MODE_rgbA_4444, MODE_RGB_565), ONE setting for

@@ -661,7 +661,7 @@ def test_alpha_multiplies(gpu):
 def test_point_sampler_and_yuv444(gpu, mode):
     D = gpu["dsp"]
     rng = np.random.default_rng(300 + mode)
-    for (w, h) in [(1, 1), (2, 3), (5, 4), (127, 3), (260, 5), (512, 2), (1030, 5), (1536, 3)]:   # the last three: whole 512-pixel items
+    for (w, h) in [(1, 1), (2, 3), (5, 4), (127, 3), (260, 5), (512, 2), (1030, 5), (1536, 3), (640, 3), (896, 2), (1920, 2)]:   # from 512 on: whole 512-pixel items, then rows whose last item is 1 - 3 whole 128-pixel groups
         y = rng.integers(0, 256, (h, w), dtype=np.uint8)
         u = rng.integers(0, 256, ((h + 1) // 2, (w + 1) // 2), dtype=np.uint8)
         v = rng.integers(0, 256, ((h + 1) // 2, (w + 1) // 2), dtype=np.uint8)

@@ -338,16 +338,33 @@ color_index_rows_kernel(const ArgbJobDev* __restrict__ jobs, const uint32_t* __r
     const uint32_t* __restrict__ srow = jp->src + (size_t)y * jp->tiles_per_row;
     uint32_t* __restrict__ drow = jp->dst + (size_t)y * (uint32_t)width;
     const int xend = min(width, xseg + kSegPx);
+    // rows of any width and alignment: vector accesses where this ROW allows them (warp-uniform), word by word
+    // otherwise; the last group of a row may hold fewer than 4 pixels
+    const bool dal = (((uintptr_t)drow) & 15) == 0;
+    const bool sal = (((uintptr_t)srow) & (BITS == 0 ? 15 : 7)) == 0;
+    const int src_words = (int)jp->tiles_per_row;
     for (int xc = xseg + lane * 4; xc < xend + lane * 4; xc += 4 * 128) {  // warp-uniform trip count
       uint32_t s0[4], s1[4];
       uint4 sv[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int x4 = xc + u * 128;
+        s0[u] = s1[u] = 0u;
+        sv[u] = make_uint4(0u, 0u, 0u, 0u);
         if (x4 < xend) {
-          if (BITS == 0) sv[u] = b2_ldg_stream_v4(srow + x4);
-          else if (BITS == 1) { const uint2 t = b2_ldg_stream_v2(srow + (x4 >> 1)); s0[u] = t.x; s1[u] = t.y; }
-          else s0[u] = __ldg(srow + (x4 >> BITS));   // shared by 1 (BITS == 2) or 2 lanes
+          if (BITS == 0) {
+            if (sal && x4 + 4 <= xend) sv[u] = b2_ldg_stream_v4(srow + x4);
+            else {
+              sv[u].x = __ldg(srow + x4);
+              if (x4 + 1 < xend) sv[u].y = __ldg(srow + x4 + 1);
+              if (x4 + 2 < xend) sv[u].z = __ldg(srow + x4 + 2);
+              if (x4 + 3 < xend) sv[u].w = __ldg(srow + x4 + 3);
+            }
+          } else if (BITS == 1) {
+            const int sw = x4 >> 1;
+            if (sal && sw + 2 <= src_words) { const uint2 t = b2_ldg_stream_v2(srow + sw); s0[u] = t.x; s1[u] = t.y; }
+            else { s0[u] = __ldg(srow + sw); if (sw + 1 < src_words) s1[u] = __ldg(srow + sw + 1); }
+          } else s0[u] = __ldg(srow + (x4 >> BITS));   // shared by 1 (BITS == 2) or 2 lanes
         }
       }
 #pragma unroll
@@ -372,7 +389,14 @@ color_index_rows_kernel(const ArgbJobDev* __restrict__ jobs, const uint32_t* __r
             o.z = *reinterpret_cast<const uint32_t*>(palb + ((g >> (6 + 2 * kBpp)) & kMask4));
             o.w = *reinterpret_cast<const uint32_t*>(palb + ((g >> (6 + 3 * kBpp)) & kMask4));
           }
-          b2_stg_stream_v4(drow + x4, o);
+          if (dal && x4 + 4 <= xend) {
+            b2_stg_stream_v4(drow + x4, o);
+          } else {
+            drow[x4] = o.x;
+            if (x4 + 1 < xend) drow[x4 + 1] = o.y;
+            if (x4 + 2 < xend) drow[x4 + 2] = o.z;
+            if (x4 + 3 < xend) drow[x4 + 3] = o.w;
+          }
         }
       }
     }
@@ -495,11 +519,10 @@ int prepare(b2_ctx* ctx, int stream, const b2_argb_job* jobs, int n_jobs, Kind k
   return B2_OK;
 }
 
-// The tuned colour-index kernel needs whole 4-pixel groups and aligned vector accesses.
+// The tuned colour-index kernel takes any width and alignment (it picks vector or word accesses per row).
 bool index_rows_ok(const b2_argb_job& j) {
   return j.src != NULL && j.dst != NULL && j.data != NULL && j.src != j.dst && j.width > 0 && j.height > 0 &&
-         j.width <= B2_MAX_DIMENSION && j.height <= B2_MAX_DIMENSION && (j.width & 3) == 0 &&
-         (((uintptr_t)j.dst) & 15) == 0 && (((uintptr_t)j.src) & (j.bits == 0 ? 15 : 7)) == 0;
+         j.width <= B2_MAX_DIMENSION && j.height <= B2_MAX_DIMENSION;
 }
 
 template <int OP>

@@ -486,7 +486,15 @@ int prepare(b2_ctx* ctx, int stream, const b2_argb_job* jobs, int n_jobs, Kind k
         if (j.src == j.dst) { st = B2_ERR_INVALID_CONFIG; break; }
         d.tiles_per_row = (uint32_t)((j.width + (1 << j.bits) - 1) >> j.bits);
         d.chunks_x = (uint32_t)((j.width + 127) / 128);
-        items = (uint32_t)(((uint64_t)d.chunks_x * j.height + kWarps - 1) / kWarps);  // CTA items
+        if (j.bits == 0) {
+          // 8-bit indices are a per-pixel map of a tightly packed image onto a tightly packed image: seen as ONE row
+          // of width * height pixels, every 4-pixel group is a 16-byte aligned access whatever the width
+          // (4095- and 4094-wide images ran at 0.69 / 0.75 of the peak against 0.90, word by word)
+          d.width = (int32_t)n; d.height = 1;
+          d.tiles_per_row = (uint32_t)n;
+          d.chunks_x = (uint32_t)((n + 127) / 128);
+        }
+        items = (uint32_t)(((uint64_t)d.chunks_x * (uint32_t)d.height + kWarps - 1) / kWarps);  // CTA items
         break;
       case KIND_INDEX_ROWS:  // preconditions were checked by the caller (index_rows_ok)
         d.tiles_per_row = (uint32_t)((j.width + (1 << j.bits) - 1) >> j.bits);

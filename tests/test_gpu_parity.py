@@ -628,13 +628,17 @@ def test_convert_from_bgra(gpu, mode):
 def test_alpha_multiplies(gpu):
     D = gpu["dsp"]
     rng = np.random.default_rng(31)
-    for (w, h) in [(1, 1), (5, 3), (64, 4), (130, 2), (512, 3), (1040, 2), (1536, 2)]:   # the last three: whole 512-sample items
+    for (w, h) in [(1, 1), (5, 3), (64, 4), (130, 2), (512, 3), (1040, 2), (1536, 2), (1922, 3), (515, 5)]:   # (512..1536): whole 512-sample items; the last two: packed rows of odd alignment
         rgba = rng.integers(0, 256, (h, 4 * w + 8), dtype=np.uint8)   # stride > 4 w
         rgba[:, 3::4][rng.random((h, rgba[:, 3::4].shape[1])) < 0.3] = 255
         for af in (0, 1):
             exp = rgba.copy()
             exp[:, :4 * w] = oracle.apply_alpha_multiply(np.ascontiguousarray(rgba[:, :4 * w]), af)
             assert (D.WebPApplyAlphaMultiply(rgba, af, w, h, rgba.shape[1]) == exp).all()
+        # tightly packed rows (stride = 4 w): widths that are not multiples of 4 are handed to the kernel as one row
+        tight = np.ascontiguousarray(rgba[:, :4 * w])
+        for af in (0, 1):
+            assert (D.WebPApplyAlphaMultiply(tight, af, w, h, 4 * w) == oracle.apply_alpha_multiply(tight, af)).all(), (w, h, af)
         p16 = rng.integers(0, 256, (h, 2 * w), dtype=np.uint8)
         for pos in (0, 1):
             assert (D.WebPApplyAlphaMultiply4444(p16, w, h, 2 * w, pos) == oracle.apply_alpha_multiply_4444(p16, pos)).all()

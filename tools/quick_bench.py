@@ -165,7 +165,7 @@ if "convert" in which:
     # output conversions (8f-2) on NF 1080p pictures: ARGB words in, packed bytes out; alpha multiplies in place;
     # point-sampled and 4:4:4 YUV -> RGBA; the use_argb import (RGBA bytes -> ARGB words); animation blend
     n = NF
-    w, h = 1920, 1080
+    w, h = int(os.environ.get("B2_CONV_W", "1920")), 1080   # widths that are not multiples of 4: B2_CONV_W=1924 / 1922 (even: the chroma planes stay whole)
     argb = ctx.alloc(n * 4 * w * h)
     out = ctx.alloc(n * 4 * w * h)
     yp = ctx.alloc(n * w * h)
@@ -173,7 +173,7 @@ if "convert" in which:
     vp = ctx.alloc(n * w * h)
     ctx.synth_fill(argb.ptr, w, h, 4 * w, 4 * w * h, n, 0xB200000A, 0, 0)
     for pl, tag in ((yp, 1), (up, 2), (vp, 3)):
-        ctx.synth_fill(pl.ptr, w // 4, h, w, w * h, n, 0xB200000A + tag, 0, 4)
+        ctx.synth_fill(pl.ptr, (w * h) // 4, 1, w * h, w * h, n, 0xB200000A + tag, 0, 4)   # a plane as one row of words: any width
     ctx.sync()
     CJ = _abi.ConvertJob
     for mode, name, bpp in ((_abi.MODE_RGBA, "RGBA", 4), (_abi.MODE_RGB, "RGB", 3), (_abi.MODE_RGB_565, "RGB565", 2), (_abi.MODE_rgbA, "rgbA (premultiplied)", 4)):

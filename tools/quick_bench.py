@@ -113,10 +113,11 @@ if "tools" in which:
 if "filters" in which:
     # alpha-plane filters on NF 1080p planes (read + write = 2 B/px)
     n = NF
-    w, h, st = 1920, 1080, 1920
-    src = ctx.alloc(n * st * h)
-    dst = ctx.alloc(n * st * h)
-    ctx.synth_fill(src.ptr, st // 4, h, st, st * h, n, 0xB2000007, 0, 4)
+    w = int(os.environ.get("B2_FILT_W", "1920"))   # packed rows (stride = width): B2_FILT_W=1922 / 1921 for rows that are not 16-byte aligned
+    h, st = 1080, w
+    src = ctx.alloc(n * st * h + 16)
+    dst = ctx.alloc(n * st * h + 16)
+    ctx.synth_fill(src.ptr, (n * st * h + 3) // 4, 1, 4 * ((n * st * h + 3) // 4), 4 * ((n * st * h + 3) // 4), 1, 0xB2000007, 0, 4)
     ctx.sync()
     for f, name in ((1, "horizontal"), (2, "vertical"), (3, "gradient")):
         jobs = (_abi.AlphaFilterJob * n)(*[_abi.AlphaFilterJob(src.ptr + i * st * h, dst.ptr + i * st * h, st, st, w, h, f, 0) for i in range(n)])
@@ -140,8 +141,9 @@ if "dequant" in which:
     # alpha level smoothing on NF 1080p planes (3 B/px: the level scan reads the plane, the smoother reads + writes it)
     import numpy as np
     n = NF
-    w, h, st = 1920, 1080, 1920
-    src = ctx.alloc(n * st * h)
+    w = int(os.environ.get("B2_FILT_W", "1920"))   # packed rows (stride = width): B2_FILT_W=1922 / 1921 for rows that are not 16-byte aligned
+    h, st = 1080, w
+    src = ctx.alloc(n * st * h + 16)
     dst = ctx.alloc(n * st * h)
     yy, xx = np.mgrid[0:h, 0:w]
     smooth = ((128 + 100 * np.sin(xx / 90.0) * np.cos(yy / 70.0)).astype(np.int64) // 16 * 16).astype(np.uint8)

@@ -851,16 +851,153 @@ int prepare_filt(b2_ctx* ctx, int stream, const b2_alpha_filter_job* jobs, int n
   return B2_OK;
 }
 
-}  // namespace
+// ---- rows that miss the fast layout: re-pitch into padded scratch, run the fast kernels there, re-pitch back -------
+// The reference's alpha plane is tightly packed (stride = width), so three planes in four have rows of every byte
+// alignment, which the kernels above can only walk byte by byte (0.02 - 0.13 of the copy bandwidth against 0.27 - 0.81).
+// A job whose pointers or strides are not multiples of 16 is therefore copied into stream scratch with a stride (and
+// a working width) rounded up to 16 -- extra columns on the right never influence the columns left of them, in any of
+// the filters, either direction --, filtered there by the fast paths, and copied back: two more passes of 2 B/px.
+struct PitchJobDev {
+  const uint8_t* src;
+  uint8_t* dst;
+  int32_t src_stride, dst_stride, width, height;
+  uint32_t segs, pad;
+};
+constexpr int kPitchSegWords = 1024;   // destination words of one row per warp item
+__global__ void __launch_bounds__(kThreads, 8)
+repitch_kernel(const PitchJobDev* __restrict__ jobs, const uint32_t* __restrict__ prefix, uint32_t n_jobs, uint32_t uniform,
+               uint32_t total) {
+  const int lane = threadIdx.x & 31;
+  for (uint32_t item = blockIdx.x * kWarps + (threadIdx.x >> 5); item < total; item += gridDim.x * kWarps) {
+    uint32_t local;
+    const uint32_t img = b2_find_image_warp(prefix, n_jobs, uniform, item, &local, (uint32_t)lane);
+    const PitchJobDev* __restrict__ j = jobs + img;
+    const int w = j->width;
+    const uint32_t y = local / j->segs;
+    const int seg = (int)(local - y * j->segs);
+    const uint8_t* s0 = j->src + (ptrdiff_t)y * j->src_stride;
+    uint8_t* d0 = j->dst + (ptrdiff_t)y * j->dst_stride;
+    const int db = (int)((uintptr_t)d0 & 3);                 // the row's first byte inside its first aligned word
+    uint32_t* const dw = (uint32_t*)((uintptr_t)d0 & ~(uintptr_t)3);
+    const int n_words = (db + w + 3) >> 2;
+    const uintptr_t s_first = (uintptr_t)s0 & ~(uintptr_t)3, s_last = (uintptr_t)(s0 + w - 1) & ~(uintptr_t)3;   // words that hold a byte of the row
+    const int k_end = min(n_words, (seg + 1) * kPitchSegWords);
+    for (int k0 = seg * kPitchSegWords + lane; k0 < k_end + lane; k0 += 4 * 32) {   // warp-uniform trip count
+      uint32_t lo[4], hi[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int k = k0 + 32 * u;
+        lo[u] = hi[u] = 0u;
+        if (k < k_end) {
+          const uintptr_t sa = (uintptr_t)(s0 + (4 * k - db));
+          const uintptr_t a = sa & ~(uintptr_t)3;
+          if (a >= s_first && a <= s_last) lo[u] = __ldg((const uint32_t*)a);
+          if ((sa & 3) != 0 && a + 4 >= s_first && a + 4 <= s_last) hi[u] = __ldg((const uint32_t*)(a + 4));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int k = k0 + 32 * u;
+        if (k < k_end) {
+          const int o = 4 * k - db;                          // offset in the row of the word's first byte
+          const uint32_t sm = (uint32_t)((uintptr_t)(s0 + o) & 3);
+          const uint32_t v = __funnelshift_r(lo[u], hi[u], 8u * sm);
+          if (o >= 0 && o + 4 <= w) {
+            dw[k] = v;
+          } else {
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+              if (o + b >= 0 && o + b < w) ((uint8_t*)(dw + k))[b] = (uint8_t)(v >> (8 * b));
+          }
+        }
+      }
+    }
+  }
+}
 
-#define B2_FILT_ENTRY_CHECKS          \
-  B2_CHECK_CTX(ctx, stream);          \
-  if (n_jobs < 0) return B2_ERR_INVALID_CONFIG; \
-  if (n_jobs == 0) return B2_OK;      \
-  if (jobs == NULL) return B2_ERR_NULL;
+int launch_repitch(b2_ctx* ctx, int stream, const PitchJobDev* host_jobs, int n) {
+  const size_t jb = (sizeof(PitchJobDev) * (size_t)n + 15) & ~(size_t)15;
+  const size_t pb = sizeof(uint32_t) * ((size_t)n + 1);
+  if (jb + pb > B2_DESC_RING_BYTES) return B2_ERR_INVALID_CONFIG;
+  uint8_t* host = (uint8_t*)calloc(1, jb + pb);
+  if (host == NULL) return B2_ERR_OOM;
+  PitchJobDev* d = (PitchJobDev*)host;
+  uint32_t* pre = (uint32_t*)(host + jb);
+  uint64_t tot = 0;
+  uint32_t uni = 0;
+  for (int i = 0; i < n; ++i) {
+    d[i] = host_jobs[i];
+    d[i].segs = (uint32_t)((((d[i].width + 6) >> 2) + kPitchSegWords - 1) / kPitchSegWords);   // up to (3 + w + 3) / 4 words
+    const uint32_t items = d[i].segs * (uint32_t)d[i].height;
+    if (i == 0) uni = items; else if (items != uni) uni = 0;
+    pre[i] = (uint32_t)tot;
+    tot += items;
+    if (tot > 0x7fffffffull) { free(host); return B2_ERR_BAD_DIM; }
+  }
+  pre[n] = (uint32_t)tot;
+  void* dev = NULL;
+  const int st = b2_upload_desc(ctx, stream, host, jb + pb, &dev);
+  free(host);
+  if (st != B2_OK) return st;
+  repitch_kernel<<<b2_grid_for(ctx, 8, (tot + kWarps - 1) / kWarps), kThreads, 0, ctx->streams[stream]>>>(
+      (const PitchJobDev*)dev, (const uint32_t*)((uint8_t*)dev + jb), (uint32_t)n, uni, (uint32_t)tot);
+  ctx->launches++;
+  B2_CUDA(ctx, cudaGetLastError());
+  return B2_OK;
+}
 
-extern "C" int b2_alpha_filter(b2_ctx* ctx, int stream, const b2_alpha_filter_job* jobs, int n_jobs) {
-  B2_FILT_ENTRY_CHECKS
+int filter_aligned(b2_ctx* ctx, int stream, const b2_alpha_filter_job* jobs, int n_jobs);
+int unfilter_aligned(b2_ctx* ctx, int stream, const b2_alpha_filter_job* jobs, int n_jobs);
+
+// Validates like prepare_filt, then runs `jobs` with the rows of the misaligned ones moved onto padded scratch.
+int run_with_repitch(b2_ctx* ctx, int stream, const b2_alpha_filter_job* jobs, int n_jobs, bool unfilter) {
+  size_t scratch = 0;
+  int n_bad = 0;
+  for (int i = 0; i < n_jobs; ++i) {
+    const b2_alpha_filter_job& j = jobs[i];
+    if (j.src == NULL || j.dst == NULL) return B2_ERR_NULL;
+    if (j.width <= 0 || j.height <= 0 || j.width > B2_MAX_DIMENSION || j.height > B2_MAX_DIMENSION) return B2_ERR_BAD_DIM;
+    if (j.src_stride < j.width || j.dst_stride < j.width) return B2_ERR_BAD_DIM;
+    if (j.filter < 0 || j.filter > 3 || (const uint8_t*)j.dst == j.src) return B2_ERR_INVALID_CONFIG;
+    const bool bad = ((((uintptr_t)j.src | (uintptr_t)j.dst) | (uint32_t)j.src_stride | (uint32_t)j.dst_stride) & 15) != 0;
+    if (bad && j.width >= 64) {   // narrower planes are not worth three launches
+      ++n_bad;
+      scratch += 2 * (size_t)((j.width + 15) & ~15) * (size_t)j.height;
+    }
+  }
+  if (n_bad == 0) return unfilter ? unfilter_aligned(ctx, stream, jobs, n_jobs) : filter_aligned(ctx, stream, jobs, n_jobs);
+  void* sp = NULL;
+  int st = b2_stream_scratch(ctx, stream, scratch + 256, &sp);
+  if (st != B2_OK) return st;
+  uint8_t* base = (uint8_t*)(((uintptr_t)sp + 255) & ~(uintptr_t)255);
+  b2_alpha_filter_job* work = (b2_alpha_filter_job*)malloc(sizeof(b2_alpha_filter_job) * (size_t)n_jobs);
+  PitchJobDev* cin = (PitchJobDev*)calloc((size_t)n_bad, sizeof(PitchJobDev));
+  PitchJobDev* cout = (PitchJobDev*)calloc((size_t)n_bad, sizeof(PitchJobDev));
+  if (work == NULL || cin == NULL || cout == NULL) { free(work); free(cin); free(cout); return B2_ERR_OOM; }
+  size_t off = 0;
+  int k = 0;
+  for (int i = 0; i < n_jobs; ++i) {
+    const b2_alpha_filter_job& j = jobs[i];
+    work[i] = j;
+    const bool bad = ((((uintptr_t)j.src | (uintptr_t)j.dst) | (uint32_t)j.src_stride | (uint32_t)j.dst_stride) & 15) != 0;
+    if (!(bad && j.width >= 64)) continue;
+    const int pw = (j.width + 15) & ~15;
+    uint8_t* s_in = base + off;
+    uint8_t* s_out = s_in + (size_t)pw * j.height;
+    off += 2 * (size_t)pw * j.height;
+    cin[k].src = j.src; cin[k].dst = s_in; cin[k].src_stride = j.src_stride; cin[k].dst_stride = pw; cin[k].width = j.width; cin[k].height = j.height;
+    cout[k].src = s_out; cout[k].dst = j.dst; cout[k].src_stride = pw; cout[k].dst_stride = j.dst_stride; cout[k].width = j.width; cout[k].height = j.height;
+    work[i].src = s_in; work[i].dst = s_out; work[i].src_stride = pw; work[i].dst_stride = pw; work[i].width = pw;
+    ++k;
+  }
+  st = launch_repitch(ctx, stream, cin, n_bad);
+  if (st == B2_OK) st = unfilter ? unfilter_aligned(ctx, stream, work, n_jobs) : filter_aligned(ctx, stream, work, n_jobs);
+  if (st == B2_OK) st = launch_repitch(ctx, stream, cout, n_bad);
+  free(work); free(cin); free(cout);
+  return st;
+}
+
+int filter_aligned(b2_ctx* ctx, int stream, const b2_alpha_filter_job* jobs, int n_jobs) {
   const FiltJobDev* dj; const uint32_t* dp; uint32_t uni, tot;
   const int rc = prepare_filt(ctx, stream, jobs, n_jobs, KIND_FORWARD, &dj, &dp, &uni, &tot, NULL);
   if (rc != B2_OK) return rc;
@@ -870,8 +1007,7 @@ extern "C" int b2_alpha_filter(b2_ctx* ctx, int stream, const b2_alpha_filter_jo
   return B2_OK;
 }
 
-extern "C" int b2_alpha_unfilter(b2_ctx* ctx, int stream, const b2_alpha_filter_job* jobs, int n_jobs) {
-  B2_FILT_ENTRY_CHECKS
+int unfilter_aligned(b2_ctx* ctx, int stream, const b2_alpha_filter_job* jobs, int n_jobs) {
   cudaStream_t s = ctx->streams[stream];
   int counts[4] = {0, 0, 0, 0};
   const FiltJobDev* dj; const uint32_t* dp; uint32_t uni, tot;
@@ -896,4 +1032,22 @@ extern "C" int b2_alpha_unfilter(b2_ctx* ctx, int stream, const b2_alpha_filter_
   }
   B2_CUDA(ctx, cudaGetLastError());
   return B2_OK;
+}
+
+}  // namespace
+
+#define B2_FILT_ENTRY_CHECKS          \
+  B2_CHECK_CTX(ctx, stream);          \
+  if (n_jobs < 0) return B2_ERR_INVALID_CONFIG; \
+  if (n_jobs == 0) return B2_OK;      \
+  if (jobs == NULL) return B2_ERR_NULL;
+
+extern "C" int b2_alpha_filter(b2_ctx* ctx, int stream, const b2_alpha_filter_job* jobs, int n_jobs) {
+  B2_FILT_ENTRY_CHECKS
+  return run_with_repitch(ctx, stream, jobs, n_jobs, false);
+}
+
+extern "C" int b2_alpha_unfilter(b2_ctx* ctx, int stream, const b2_alpha_filter_job* jobs, int n_jobs) {
+  B2_FILT_ENTRY_CHECKS
+  return run_with_repitch(ctx, stream, jobs, n_jobs, true);
 }

@@ -17,6 +17,9 @@
 //               a pipeline over the 16 warps of one CTA; with 4-byte aligned rows everything moves
 //               through shared-memory tiles (gradient_band_tiled), unaligned rows keep the
 //               byte-skewed loop that reads the row above a band back from the output.
+// Planes whose rows are not 16-byte aligned (the reference's packed alpha plane at three widths in
+// four) are re-pitched into padded scratch, filtered there by the aligned paths and copied back
+// (run_with_repitch at the end of the file); the byte-wise paths remain for planes narrower than 64.
 #include <stdlib.h>
 
 #include <type_traits>

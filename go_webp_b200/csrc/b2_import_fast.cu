@@ -1,6 +1,7 @@
-// b2_import_fast.cu -- tuned RGBA -> YUV420(+A) import for the common case: 4-byte
-// pixels, 4-byte aligned source rows (128-bit loads when they are 16-byte aligned),
-// any width, 4-byte aligned Y/A rows.
+// b2_import_fast.cu -- tuned RGBA -> YUV420(+A) import: 4-byte pixels on 4-byte aligned
+// source rows (UNAL instantiations when a row is not 16-byte aligned) and 3-byte pixels on
+// rows of any alignment (STEP3), any width, 4-byte aligned Y/A rows.  Row pairs are handed
+// out by a ticket counter (b2_ctx::tickets_dev).
 //
 // Same arithmetic as b2_import.cu (pkg/libwebp/dsp/yuv.go:124-382,
 // pkg/color/yuv/conversion.go:51-69); what changes is the instruction budget.  The

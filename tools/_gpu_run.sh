@@ -1,6 +1,2 @@
 #!/bin/bash
-timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -5 > gpurun_out/r02_gpu_tests_f6.log
-cat gpurun_out/r02_gpu_tests_f6.log
-timeout 600 python bench.py > gpurun_out/r02_bench_f6.json 2> gpurun_out/r02_bench_f6.err
-tail -c 200 gpurun_out/r02_bench_f6.json
-python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -1
+for w in 1920 1922 1921; do echo "== $w"; B2_FILT_W=$w python tools/quick_bench.py dequant 2>&1 | grep "random bytes s=100"; done

@@ -151,7 +151,7 @@ if "dequant" in which:
     edge[edge >= 240] = 255
     for name in ("random bytes", "smooth, 16 levels apart", "flat with a soft edge"):
         if name == "random bytes":
-            ctx.synth_fill(src.ptr, st // 4, h, st, st * h, n, 0xB2000009, 0, 4)
+            ctx.synth_fill(src.ptr, (n * st * h + 3) // 4, 1, 4 * ((n * st * h + 3) // 4), 4 * ((n * st * h + 3) // 4), 1, 0xB2000009, 0, 4)
         else:
             host = smooth if name.startswith("smooth") else edge
             for i in range(n):

@@ -969,6 +969,11 @@ int run_with_repitch(b2_ctx* ctx, int stream, const b2_alpha_filter_job* jobs, i
     }
   }
   if (n_bad == 0) return unfilter ? unfilter_aligned(ctx, stream, jobs, n_jobs) : filter_aligned(ctx, stream, jobs, n_jobs);
+  if (scratch > ((size_t)2 << 30) && n_jobs > 1) {   // keep the (grow-only) stream scratch bounded: halves, one after the other
+    const int half = n_jobs / 2;
+    const int st0 = run_with_repitch(ctx, stream, jobs, half, unfilter);
+    return st0 != B2_OK ? st0 : run_with_repitch(ctx, stream, jobs + half, n_jobs - half, unfilter);
+  }
   void* sp = NULL;
   int st = b2_stream_scratch(ctx, stream, scratch + 256, &sp);
   if (st != B2_OK) return st;

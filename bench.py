@@ -430,7 +430,7 @@ def config4_mixed(ctx, D, peak, steps, n_images=256):
     rates = dict(zip(keys, vals))
     costs = partition.calibrated_costs(sizes, rates)
     k = max(3, min(steps, 10))
-    rounds, best = (3 if D.world > 1 else 1), None
+    rounds, best = (5 if D.world > 1 else 1), None
     for it in range(rounds):   # the class model first, then the measured per-GPU times of a pass correct it (every rank computes the same update)
         parts = partition.lpt_partition(costs, D.world)
         p = MixedPipeline(ctx, [sizes[i] for i in parts[D.rank]])
@@ -459,8 +459,8 @@ def config4_mixed(ctx, D, peak, steps, n_images=256):
                        f"cross-colour^-1 + add-green, 3 launches per pass over the rank's share", "n_gpus": D.world,
            "scaling": "strong", "value": px / ms / 1e3, "unit": "Mpixel/s", "ms_per_step": ms,
            "per_gpu_ms": per_gpu, "imbalance_max_over_mean": ms * D.world / sum(per_gpu),
-           "partition": "LPT on calibrated time (bytes / measured rate of the image's width-alignment x size class), then two "
-                        "rounds in which the measured per-GPU times of a pass correct the costs; the best of the three "
+           "partition": "LPT on calibrated time (bytes / measured rate of the image's width-alignment x size class), then four "
+                        "rounds in which the measured per-GPU times of a pass correct the costs; the best of the five "
                         f"partitions (round {best['round']}) is the one reported, all timed alike",
            "roofline": {"bound": "hbm", "achieved": by / D.world / ms / 1e6, "peak": peak, "unit": "GB/s",
                         "frac": by / D.world / ms / 1e6 / peak, "per": "GPU (mean share / slowest rank)"}}

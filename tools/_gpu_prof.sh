@@ -1,5 +1,6 @@
 #!/bin/bash
-N="--set full --import-source on --clock-control none -c 1"
-ncu $N -k regex:upsample_bulk_kernel -s 47 -o gpurun_out/r02c_uprgb python tools/quick_bench.py up1080 > gpurun_out/r02c_prof9.log 2>&1
-ncu $N -k regex:upsample_bulk_kernel -s 1 -o gpurun_out/r02c_uprgba python tools/quick_bench.py up1080 > gpurun_out/r02c_prof10.log 2>&1
-ls -la gpurun_out/r02c_uprgb.ncu-rep gpurun_out/r02c_uprgba.ncu-rep
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_ncu_launches_bench_steps5.csv python bench.py --steps 5 --warmup 3 > gpurun_out/r02_ncu_launches.log 2>&1
+tail -c 200 gpurun_out/r02_ncu_launches.log
+wc -l gpurun_out/r02_ncu_launches_bench_steps5.csv
+ncu --set full --import-source on --clock-control none -k regex:import_fast_kernel -c 1 -s 4 -o gpurun_out/r02c_import_full python bench.py --steps 5 --warmup 3 > gpurun_out/r02c_import_full.log 2>&1
+ls -la gpurun_out/r02c_import_full.ncu-rep

@@ -1,3 +1,4 @@
 #!/bin/bash
-timeout 900 python -m pytest tests -m gpu -q -x -k "filter or rescaled or alpha" 2>&1 | tail -3 | cut -c1-300
-for w in 1920 1922 1921; do echo "== $w"; B2_FILT_W=$w python tools/quick_bench.py dequant 2>&1 | grep "random bytes s=100"; done
+timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -5 > gpurun_out/r02_gpu_tests_f7.log
+cat gpurun_out/r02_gpu_tests_f7.log
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -1

@@ -1,4 +1,4 @@
 #!/bin/bash
-timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -5 > gpurun_out/r02_gpu_tests_f7.log
-cat gpurun_out/r02_gpu_tests_f7.log
-python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -1
+B2_MIXED_BREAKDOWN=1 python tools/mixed_bench.py > gpurun_out/r02_mixed_breakdown.txt 2>&1
+python tools/mixed_classes.py >> gpurun_out/r02_mixed_breakdown.txt 2>&1
+tail -3 gpurun_out/r02_mixed_breakdown.txt | cut -c1-200

@@ -426,10 +426,18 @@ static int import_impl(b2_ctx* ctx, int stream, const b2_import_job* jobs, int n
     dither.rng_poly_w = (const uint32_t*)pdev + (size_t)n_jobs * B2_RNG_N;
     dither.amp = amp;
   }
+  // row pairs per ticket: about 16 strips of 128 pixels (a 1080p row pair has 15), at most 8 row pairs
+  uint32_t ticket_batch = 1;
+  if (utotal > 0) {
+    const uint64_t strips_per_unit = (total + utotal - 1) / utotal;   // `total` counts strips (tiles_x per row pair)
+    if (strips_per_unit < 16) ticket_batch = (uint32_t)(16 / strips_per_unit);
+    if (ticket_batch > 8) ticket_batch = 8;
+    if (ticket_batch < 1) ticket_batch = 1;
+  }
   if (tuned) {
     B2_CUDA(ctx, b2_import_fast_launch(ctx, s, djobs, dupre, (uint32_t)n_jobs, uuniform, (uint32_t)utotal,
                                        order, alpha, n_with_a != 0, divt, has_alpha_dev, dither,
-                                       b2_tickets(ctx, stream, 0), unaligned));
+                                       b2_tickets(ctx, stream, 0), unaligned, ticket_batch));
   } else if (fast) {
     if (order == B2_ORDER_RGBA) {
       if (alpha) import_kernel<0, true><<<grid, kThreads, 0, s>>>(djobs, dpre, n_jobs, uniform, tot, ctx->tab_dev, divt, has_alpha_dev);

@@ -18,7 +18,8 @@ enum { JOB_Y_ALIGNED = 1, JOB_A_ALIGNED = 2, JOB_UV_ALIGNED = 4 };
 // Fast path (b2_import_fast.cu): every job is step 4, source rows 4-byte aligned
 // (pointer and stride, any width), Y/A rows 4-byte and U/V rows 2-byte aligned.  unit_prefix counts
 // row pairs.  tickets = the stream's two work-counter words (b2_tickets), zero between launches.
-// unaligned = some job's source rows are not 16-byte aligned (pointer or stride).  Returns a cudaError_t
+// unaligned = some job's source rows are not 16-byte aligned (pointer or stride).  ticket_batch = row pairs per ticket
+// (>= 1; more than 1 for batches of narrow images).  Returns a cudaError_t
 // from the launch.
 // Dithered import (b2_dither.cu): rng_states = the VP8Random window (55 words) every row
 // pair starts with, rng_poly_w = per image x^width mod P; amp = VP8Random.amp.  NULL
@@ -32,7 +33,7 @@ cudaError_t b2_import_fast_launch(const b2_ctx* ctx, cudaStream_t s, const Impor
                                   const uint32_t* unit_prefix, uint32_t n_jobs,
                                   uint32_t uniform_units, uint32_t total_units, int order,
                                   bool alpha, bool write_a, int div_table, int32_t* has_alpha,
-                                  ImportDither dither, uint32_t* tickets, bool unaligned);
+                                  ImportDither dither, uint32_t* tickets, bool unaligned, uint32_t ticket_batch);
 
 // ---- VP8Random skip-ahead (b2_dither.cu) ---------------------------------------------
 #define B2_RNG_N 55

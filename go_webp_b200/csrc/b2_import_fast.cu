@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm)
 import_fast_kernel(const ImportJobDev* __restrict__ jobs, const uint32_t* __restrict__ unit_prefix,
                    uint32_t n_jobs, uint32_t uniform_units, uint32_t total_units,
                    const uint32_t* __restrict__ tab, int32_t* __restrict__ has_alpha, const ImportDither dither,
-                   uint32_t* __restrict__ tickets) {
+                   uint32_t* __restrict__ tickets, const uint32_t ticket_batch) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
   const uint32_t tbase = (sbase + 0xffffu) & ~0xffffu;       // T
@@ -276,10 +276,15 @@ import_fast_kernel(const ImportJobDev* __restrict__ jobs, const uint32_t* __rest
   // most wide rows decides when the kernel ends (0.50 -> 0.6x of the measured peak on configs[4]).
   // The next ticket is drawn before the current row pair is worked on, so its latency is hidden.
   const uint32_t n_warps_total = gridDim.x * kFastWarps;
-  uint32_t unit = blockIdx.x * kFastWarps + warp;
-  while (unit < total_units * kSplit) {
-    uint32_t next_unit = 0;
-    if (lane == 0) next_unit = n_warps_total + atomicAdd(tickets, 1u);
+  // A ticket stands for ticket_batch consecutive row pairs (1 unless the rows are narrow: a batch of 128-pixel-wide
+  // images has one strip per row pair, and half a million tickets drawn on one address took as long as the conversion).
+  const uint32_t n_units = total_units * kSplit;
+  uint32_t chunk = blockIdx.x * kFastWarps + warp;
+  while ((uint64_t)chunk * ticket_batch < n_units) {
+    uint32_t next_chunk = 0;
+    if (lane == 0) next_chunk = n_warps_total + atomicAdd(tickets, 1u);
+    const uint32_t unit_end = (uint32_t)min((uint64_t)(chunk + 1) * ticket_batch, (uint64_t)n_units);
+    for (uint32_t unit = chunk * ticket_batch; unit < unit_end; ++unit) {
     uint32_t rp;
     const uint32_t img = b2_find_image_warp(unit_prefix, n_jobs, uniform_units, unit / kSplit, &rp, lane);
     const int phase = (int)(unit % kSplit);
@@ -537,7 +542,8 @@ import_fast_kernel(const ImportJobDev* __restrict__ jobs, const uint32_t* __rest
     if (ALPHA && has_alpha != nullptr) {
       if (__any_sync(0xffffffffu, and_acc != 0xffffffffu) && lane == 0) atomicOr(has_alpha + img, 1);
     }
-    unit = __shfl_sync(0xffffffffu, next_unit, 0);
+    }
+    chunk = __shfl_sync(0xffffffffu, next_chunk, 0);
   }
   if (lane == 0) {
     if (atomicAdd(tickets + 1, 1u) == n_warps_total - 1) { tickets[0] = 0; tickets[1] = 0; }
@@ -555,6 +561,7 @@ struct FastArgs {
   ImportDither dither;
   uint32_t* tickets;
   bool unaligned;
+  uint32_t ticket_batch;
 };
 template <int ORDER, bool ALPHA, bool WRITE_A, bool TABLE, bool DITHER, bool UNAL, bool STEP3 = false>
 cudaError_t launch3(const FastArgs& a) {
@@ -563,7 +570,7 @@ cudaError_t launch3(const FastArgs& a) {
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   k<<<a.grid, kFastThreads, smem, a.s>>>(a.jobs, a.unit_prefix, a.n_jobs, a.uniform_units, a.total_units, a.tab,
-                                         a.has_alpha, a.dither, a.tickets);
+                                         a.has_alpha, a.dither, a.tickets, a.ticket_batch);
   return cudaGetLastError();
 }
 template <int ORDER, bool ALPHA, bool WRITE_A, bool TABLE>
@@ -586,8 +593,9 @@ cudaError_t b2_import_fast_launch(const b2_ctx* ctx, cudaStream_t s, const Impor
                                   const uint32_t* unit_prefix, uint32_t n_jobs,
                                   uint32_t uniform_units, uint32_t total_units, int order,
                                   bool alpha, bool write_a, int div_table, int32_t* has_alpha,
-                                  ImportDither dither, uint32_t* tickets, bool unaligned) {
+                                  ImportDither dither, uint32_t* tickets, bool unaligned, uint32_t ticket_batch) {
   FastArgs a;
+  a.ticket_batch = ticket_batch < 1 ? 1u : ticket_batch;
   a.grid = b2_grid_for(ctx, kFastCtasPerSm, ((uint64_t)total_units * kSplit + kFastWarps - 1) / kFastWarps);
   a.s = s; a.jobs = jobs; a.unit_prefix = unit_prefix; a.n_jobs = n_jobs; a.uniform_units = uniform_units;
   a.total_units = total_units; a.tab = ctx->tab_dev; a.has_alpha = has_alpha; a.dither = dither;

@@ -1,10 +1,9 @@
 #!/bin/bash
-timeout 900 python -m pytest tests -m gpu -q -x -k "import or config1 or config4 or dither" 2>&1 | tail -3 | cut -c1-300
-python tools/mixed_classes.py 128,1080 130,1080 256,1080 1920,1080 2>&1 | python -c "
+timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -5 > gpurun_out/r02_gpu_tests_f8.log
+cat gpurun_out/r02_gpu_tests_f8.log
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -1
+python bench.py --steps 10 --warmup 3 2>/dev/null | python -c "
 import sys, json
-for l in sys.stdin:
-    try: d = json.loads(l)
-    except Exception: continue
-    print('%-22s import %.3f  upsample %.3f  chain %.3f' % (d['subset'], d['import']['frac'], d['upsample']['frac'], d['chain']['frac']))
+d = json.loads([l for l in sys.stdin if l.startswith('{')][-1])
+print('bench', d['value'], d['roofline']['frac'], d['e2e']['value'], d['other_configs']['configs[4]']['value'])
 "
-python tools/quick_bench.py import 2>&1 | grep "sparse  \|opaque"
